@@ -1,0 +1,376 @@
+"""world-b200: B200-native WORLD analysis/synthesis (Dio, StoneMask, Harvest, CheapTrick, D4C,
+Synthesis) behind the reference's C API.  This module is the Python host-side mirror of that
+API: numpy in / numpy out wrappers over the C ABI of libworld_b200.so, plus the batched
+`Corpus` handle that replaces the reference's one-process-per-utterance loop
+(data/Makefile.in:125-242).
+
+There is deliberately no CPU path: if the shared library is missing or no CUDA device is
+visible, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libworld_b200.so")
+
+
+class DioOption(C.Structure):          # W/src/world/dio.h:16-23
+    _fields_ = [("f0_floor", C.c_double), ("f0_ceil", C.c_double),
+                ("channels_in_octave", C.c_double), ("frame_period", C.c_double),
+                ("speed", C.c_int), ("allowed_range", C.c_double)]
+
+
+class CheapTrickOption(C.Structure):   # W/src/world/cheaptrick.h:16-20
+    _fields_ = [("q1", C.c_double), ("f0_floor", C.c_double), ("fft_size", C.c_int)]
+
+
+class D4COption(C.Structure):          # W/src/world/d4c.h:16-18
+    _fields_ = [("threshold", C.c_double)]
+
+
+class HarvestOption(C.Structure):      # W/src/world/harvest.h:16-20
+    _fields_ = [("f0_floor", C.c_double), ("f0_ceil", C.c_double), ("frame_period", C.c_double)]
+
+
+_dp = C.POINTER(C.c_double)
+_dpp = C.POINTER(_dp)
+_ip = C.POINTER(C.c_int)
+_lib = None
+
+
+class WorldB200Error(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _rows(a2d):
+    n = a2d.shape[0]
+    arr = (_dp * n)()
+    base, stride = a2d.ctypes.data, a2d.strides[0]
+    for i in range(n):
+        arr[i] = C.cast(base + i * stride, _dp)
+    return arr
+
+
+def lib():
+    """The loaded C-ABI library.  Raises loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise WorldB200Error(
+            "%s not found: run `python hts-train-world_b200/build.py` (nvcc, sm_100a). "
+            "There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH, mode=os.RTLD_LOCAL | os.RTLD_NOW)
+    vp, i32, i64, f64 = C.c_void_p, C.c_int, C.c_longlong, C.c_double
+    sigs = {
+        # WORLD API
+        "Dio": (None, [_dp, i32, i32, C.POINTER(DioOption), _dp, _dp]),
+        "InitializeDioOption": (None, [C.POINTER(DioOption)]),
+        "GetSamplesForDIO": (i32, [i32, i32, f64]),
+        "StoneMask": (None, [_dp, i32, i32, _dp, _dp, i32, _dp]),
+        "CheapTrick": (None, [_dp, i32, i32, _dp, _dp, i32, C.POINTER(CheapTrickOption), _dpp]),
+        "InitializeCheapTrickOption": (None, [i32, C.POINTER(CheapTrickOption)]),
+        "GetFFTSizeForCheapTrick": (i32, [i32, C.POINTER(CheapTrickOption)]),
+        "GetF0FloorForCheapTrick": (f64, [i32, i32]),
+        "D4C": (None, [_dp, i32, i32, _dp, _dp, i32, i32, C.POINTER(D4COption), _dpp]),
+        "InitializeD4COption": (None, [C.POINTER(D4COption)]),
+        "Synthesis": (None, [_dp, i32, _dpp, _dpp, i32, f64, i32, i32, _dp]),
+        "Harvest": (None, [_dp, i32, i32, C.POINTER(HarvestOption), _dp, _dp]),
+        "InitializeHarvestOption": (None, [C.POINTER(HarvestOption)]),
+        "GetSamplesForHarvest": (i32, [i32, i32, f64]),
+        # extension API (include/world_b200.h)
+        "wb200_last_error": (C.c_char_p, []),
+        "wb200_init": (i32, [i32]),
+        "wb200_launch_count": (C.c_ulonglong, []),
+        "wb200_stage_times": (None, [C.POINTER(C.c_float)]),
+        "wb200_randn_stream": (i32, [_dp, i64]),
+        "wb200_batch_create": (vp, [i32, f64, i32, _ip]),
+        "wb200_batch_destroy": (None, [vp]),
+        "wb200_batch_total_frames": (i32, [vp]),
+        "wb200_batch_total_samples": (i64, [vp]),
+        "wb200_batch_frame_layout": (i32, [vp, _ip, _ip]),
+        "wb200_batch_upload_pcm16": (i32, [vp, vp]),
+        "wb200_batch_upload_f64": (i32, [vp, vp]),
+        "wb200_batch_set_pcm16_device": (i32, [vp, vp]),
+        "wb200_batch_dio": (i32, [vp, C.POINTER(DioOption)]),
+        "wb200_batch_stonemask": (i32, [vp]),
+        "wb200_batch_harvest": (i32, [vp, C.POINTER(HarvestOption)]),
+        "wb200_batch_cheaptrick": (i32, [vp, C.POINTER(CheapTrickOption)]),
+        "wb200_batch_d4c": (i32, [vp, i32, C.POINTER(D4COption)]),
+        "wb200_batch_synthesis": (i32, [vp, _ip]),
+        "wb200_batch_get_f0": (i32, [vp, _dp, i32]),
+        "wb200_batch_set_f0": (i32, [vp, _dp, i32]),
+        "wb200_batch_get_sp": (i32, [vp, vp]),
+        "wb200_batch_get_ap": (i32, [vp, vp]),
+        "wb200_batch_set_sp_ap": (i32, [vp, i32, _dp, _dp]),
+        "wb200_batch_total_y": (i64, [vp]),
+        "wb200_batch_y_layout": (i32, [vp, C.POINTER(i64), _ip]),
+        "wb200_batch_get_y": (i32, [vp, vp]),
+        "wb200_batch_get_y_pcm16": (i32, [vp, vp]),
+        "wb200_batch_device_ptr": (vp, [vp, C.c_char_p]),
+        "wb200_batch_lf0_stats": (i32, [vp, _dp]),
+        "wb200_sync": (i32, []),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = None  # filled lazily by tests from include/*.h
+
+
+def last_error():
+    return lib().wb200_last_error().decode()
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise WorldB200Error("%s failed: %s" % (what, last_error()))
+
+
+def init(device=0):
+    _check(lib().wb200_init(int(device)), "wb200_init")
+
+
+def launch_count():
+    return int(lib().wb200_launch_count())
+
+
+def stage_times():
+    out = (C.c_float * 6)()
+    lib().wb200_stage_times(out)
+    return dict(zip(["dio", "stonemask", "cheaptrick", "d4c", "synthesis", "harvest"], list(out)))
+
+
+def randn_stream(n):
+    out = np.zeros(int(n))
+    _check(lib().wb200_randn_stream(_ptr(out), int(n)), "wb200_randn_stream")
+    return out
+
+
+def _nan_check(a, what):
+    if a.size and np.isnan(a).all():
+        raise WorldB200Error("%s failed: %s" % (what, last_error()))
+    return a
+
+
+# ---------------------------------------------------------------------------------------------
+# one-utterance calls: same names, argument meaning and defaults as the reference C API
+# ---------------------------------------------------------------------------------------------
+def dio_option(frame_period=5.0, f0_floor=71.0, f0_ceil=800.0, speed=1, allowed_range=0.1,
+               channels_in_octave=2.0):
+    o = DioOption()
+    lib().InitializeDioOption(C.byref(o))
+    o.frame_period, o.f0_floor, o.f0_ceil = frame_period, f0_floor, f0_ceil
+    o.speed, o.allowed_range, o.channels_in_octave = speed, allowed_range, channels_in_octave
+    return o
+
+
+def dio(x, fs, **kw):
+    x = np.ascontiguousarray(x, np.float64)
+    o = dio_option(**kw)
+    n = lib().GetSamplesForDIO(fs, len(x), o.frame_period)
+    t, f0 = np.zeros(n), np.zeros(n)
+    lib().Dio(_ptr(x), len(x), fs, C.byref(o), _ptr(t), _ptr(f0))
+    return t, _nan_check(f0, "Dio")
+
+
+def stonemask(x, fs, t, f0):
+    x, t, f0 = (np.ascontiguousarray(a, np.float64) for a in (x, t, f0))
+    out = np.zeros_like(f0)
+    lib().StoneMask(_ptr(x), len(x), fs, _ptr(t), _ptr(f0), len(f0), _ptr(out))
+    return _nan_check(out, "StoneMask")
+
+
+def harvest(x, fs, frame_period=5.0, f0_floor=71.0, f0_ceil=800.0):
+    x = np.ascontiguousarray(x, np.float64)
+    o = HarvestOption()
+    lib().InitializeHarvestOption(C.byref(o))
+    o.frame_period, o.f0_floor, o.f0_ceil = frame_period, f0_floor, f0_ceil
+    n = lib().GetSamplesForHarvest(fs, len(x), frame_period)
+    t, f0 = np.zeros(n), np.zeros(n)
+    lib().Harvest(_ptr(x), len(x), fs, C.byref(o), _ptr(t), _ptr(f0))
+    return t, _nan_check(f0, "Harvest")
+
+
+def cheaptrick_option(fs, q1=-0.15, f0_floor=71.0, fft_size=None):
+    o = CheapTrickOption()
+    lib().InitializeCheapTrickOption(fs, C.byref(o))
+    o.q1, o.f0_floor = q1, f0_floor
+    o.fft_size = fft_size or lib().GetFFTSizeForCheapTrick(fs, C.byref(o))
+    return o
+
+
+def cheaptrick(x, fs, t, f0, **kw):
+    x, t, f0 = (np.ascontiguousarray(a, np.float64) for a in (x, t, f0))
+    o = cheaptrick_option(fs, **kw)
+    sp = np.zeros((len(f0), o.fft_size // 2 + 1))
+    lib().CheapTrick(_ptr(x), len(x), fs, _ptr(t), _ptr(f0), len(f0), C.byref(o), _rows(sp))
+    return _nan_check(sp, "CheapTrick")
+
+
+def d4c(x, fs, t, f0, fft_size, threshold=0.0):
+    x, t, f0 = (np.ascontiguousarray(a, np.float64) for a in (x, t, f0))
+    o = D4COption()
+    lib().InitializeD4COption(C.byref(o))
+    o.threshold = threshold
+    ap = np.zeros((len(f0), fft_size // 2 + 1))
+    lib().D4C(_ptr(x), len(x), fs, _ptr(t), _ptr(f0), len(f0), fft_size, C.byref(o), _rows(ap))
+    return _nan_check(ap, "D4C")
+
+
+def synthesis(f0, sp, ap, fft_size, frame_period, fs, y_length=None):
+    f0, sp, ap = (np.ascontiguousarray(a, np.float64) for a in (f0, sp, ap))
+    if y_length is None:   # W/test/synth.cpp:259
+        y_length = int((len(f0) - 1) * frame_period / 1000.0 * fs) + 1
+    y = np.zeros(y_length)
+    lib().Synthesis(_ptr(f0), len(f0), _rows(sp), _rows(ap), fft_size, float(frame_period), fs,
+                    y_length, _ptr(y))
+    return _nan_check(y, "Synthesis")
+
+
+# ---------------------------------------------------------------------------------------------
+# the batched path
+# ---------------------------------------------------------------------------------------------
+class Corpus:
+    """A batch of utterances resident in HBM (include/world_b200.h)."""
+
+    def __init__(self, fs, x_lengths, frame_period=5.0):
+        self.fs, self.frame_period = int(fs), float(frame_period)
+        self.x_lengths = np.ascontiguousarray(x_lengths, np.int32)
+        self.n_utt = len(self.x_lengths)
+        self._h = lib().wb200_batch_create(self.fs, self.frame_period, self.n_utt,
+                                           self.x_lengths.ctypes.data_as(_ip))
+        if not self._h:
+            raise WorldB200Error("wb200_batch_create failed: " + last_error())
+        self.total_frames = lib().wb200_batch_total_frames(self._h)
+        self.f_off = np.zeros(self.n_utt, np.int32)
+        self.f_len = np.zeros(self.n_utt, np.int32)
+        lib().wb200_batch_frame_layout(self._h, self.f_off.ctypes.data_as(_ip),
+                                       self.f_len.ctypes.data_as(_ip))
+        self.fft_size = None
+
+    def close(self):
+        if self._h:
+            lib().wb200_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # inputs -------------------------------------------------------------------------------
+    def upload_pcm16(self, pcm):
+        """pcm: int16 numpy array or pinned torch tensor, utterances back to back."""
+        ptr = pcm.data_ptr() if hasattr(pcm, "data_ptr") else pcm.ctypes.data
+        _check(lib().wb200_batch_upload_pcm16(self._h, ptr), "upload_pcm16")
+        self._keep = pcm
+
+    def set_pcm16_device(self, dev_tensor):
+        _check(lib().wb200_batch_set_pcm16_device(self._h, dev_tensor.data_ptr()), "set_pcm16_device")
+
+    def upload_f64(self, x):
+        x = np.ascontiguousarray(x, np.float64)
+        _check(lib().wb200_batch_upload_f64(self._h, x.ctypes.data), "upload_f64")
+
+    # stages -------------------------------------------------------------------------------
+    def dio(self, **kw):
+        kw.setdefault("frame_period", self.frame_period)
+        o = dio_option(**kw)
+        _check(lib().wb200_batch_dio(self._h, C.byref(o)), "batch dio")
+
+    def stonemask(self):
+        _check(lib().wb200_batch_stonemask(self._h), "batch stonemask")
+
+    def harvest(self, f0_floor=71.0, f0_ceil=800.0):
+        o = HarvestOption(f0_floor, f0_ceil, self.frame_period)
+        _check(lib().wb200_batch_harvest(self._h, C.byref(o)), "batch harvest")
+
+    def cheaptrick(self, **kw):
+        o = cheaptrick_option(self.fs, **kw)
+        self.fft_size = o.fft_size
+        _check(lib().wb200_batch_cheaptrick(self._h, C.byref(o)), "batch cheaptrick")
+
+    def d4c(self, threshold=0.0, fft_size=None):
+        self.fft_size = fft_size or self.fft_size or cheaptrick_option(self.fs).fft_size
+        o = D4COption(threshold)
+        _check(lib().wb200_batch_d4c(self._h, self.fft_size, C.byref(o)), "batch d4c")
+
+    def synthesis(self, y_lengths=None):
+        p = None
+        if y_lengths is not None:
+            y_lengths = np.ascontiguousarray(y_lengths, np.int32)
+            p = y_lengths.ctypes.data_as(_ip)
+        _check(lib().wb200_batch_synthesis(self._h, p), "batch synthesis")
+
+    def analyze(self, threshold=0.0):
+        """Dio -> StoneMask -> CheapTrick -> D4C with the analysis tool's options
+        (W/test/analysis.cpp:93-203)."""
+        self.dio()
+        self.stonemask()
+        self.cheaptrick()
+        self.d4c(threshold=threshold)
+
+    # results ------------------------------------------------------------------------------
+    def f0(self, refined=True):
+        out = np.zeros(self.total_frames)
+        _check(lib().wb200_batch_get_f0(self._h, _ptr(out), int(refined)), "get_f0")
+        return out
+
+    def set_f0(self, f0, refined=True):
+        f0 = np.ascontiguousarray(f0, np.float64)
+        assert len(f0) == self.total_frames
+        _check(lib().wb200_batch_set_f0(self._h, _ptr(f0), int(refined)), "set_f0")
+
+    def sp(self):
+        out = np.zeros((self.total_frames, self.fft_size // 2 + 1))
+        _check(lib().wb200_batch_get_sp(self._h, out.ctypes.data), "get_sp")
+        return out
+
+    def ap(self):
+        out = np.zeros((self.total_frames, self.fft_size // 2 + 1))
+        _check(lib().wb200_batch_get_ap(self._h, out.ctypes.data), "get_ap")
+        return out
+
+    def set_sp_ap(self, fft_size, sp, ap):
+        sp, ap = (np.ascontiguousarray(a, np.float64) for a in (sp, ap))
+        self.fft_size = int(fft_size)
+        _check(lib().wb200_batch_set_sp_ap(self._h, self.fft_size, _ptr(sp), _ptr(ap)), "set_sp_ap")
+
+    def y_layout(self):
+        off = np.zeros(self.n_utt, np.int64)
+        ln = np.zeros(self.n_utt, np.int32)
+        lib().wb200_batch_y_layout(self._h, off.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                   ln.ctypes.data_as(_ip))
+        return off, ln
+
+    def y(self):
+        out = np.zeros(int(lib().wb200_batch_total_y(self._h)))
+        _check(lib().wb200_batch_get_y(self._h, out.ctypes.data), "get_y")
+        return out
+
+    def y_pcm16(self, out=None):
+        n = int(lib().wb200_batch_total_y(self._h))
+        if out is None:
+            out = np.zeros(n, np.int16)
+        ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+        _check(lib().wb200_batch_get_y_pcm16(self._h, ptr), "get_y_pcm16")
+        return out
+
+    def lf0_stats(self):
+        out = np.zeros(3)
+        _check(lib().wb200_batch_lf0_stats(self._h, _ptr(out)), "lf0_stats")
+        return out
+
+    def frames_of(self, u):
+        return slice(int(self.f_off[u]), int(self.f_off[u] + self.f_len[u]))

@@ -1,0 +1,494 @@
+// world-b200: the C ABI.  (1) the unchanged WORLD entry points of the reference
+// (W/src/world/*.h) as one-utterance batches, (2) the batched extension API of
+// include/world_b200.h.  Host code only stages data; all arithmetic runs in the kernels.
+#include <math.h>
+#include <string.h>
+#include <limits>
+#include <string>
+#include "../../include/world_b200.h"
+#include "wb_batch.h"
+
+using namespace wb;
+
+struct wb200_batch {
+  Batch b;
+  DevBuf<int16_t> pcm_stage;
+};
+
+namespace {
+
+const double kNaN = std::numeric_limits<double>::quiet_NaN();
+
+struct StageTimer {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  float* dst;
+  cudaStream_t st;
+  explicit StageTimer(float* d) : dst(d) {
+    Context* c = ctx();
+    st = c ? c->stream : nullptr;
+    if (c && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
+      cudaEventRecord(e0, st);
+  }
+  ~StageTimer() {
+    if (e0 && e1) {
+      cudaEventRecord(e1, st);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) *dst = ms;
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  }
+};
+
+int samples_for_dio(int fs, int x_length, double frame_period) {
+  return static_cast<int>(1000.0 * x_length / fs / frame_period) + 1;   // W/src/dio.cpp:638-640
+}
+
+__global__ void pcm16_to_double_kernel(const int16_t* __restrict__ pcm, const long long* __restrict__ src_off,
+                                       const long long* __restrict__ x_off, const int* __restrict__ x_len,
+                                       double* __restrict__ x) {
+  const int u = blockIdx.y;
+  const int n = x_len[u];
+  const int16_t* s = pcm + src_off[u];
+  double* d = x + x_off[u];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    d[i] = static_cast<double>(s[i]) / 32768.0;
+}
+
+__global__ void y_to_pcm16_kernel(const double* __restrict__ y, long long n, int16_t* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // W/test/audioio.cpp:115-170: (short)(MyMax(-32768, MyMin(32767, (int)(x * 32767))))
+  double v = y[i] * 32767.0;
+  int iv = (v != v) ? 0 : (v > 2147483000.0 ? 2147483000 : (v < -2147483000.0 ? -2147483000 : (int)v));
+  iv = max(-32768, min(32767, iv));
+  out[i] = (int16_t)iv;
+}
+
+__global__ void lf0_stats_kernel(const double* __restrict__ f0, int n, double* __restrict__ out3) {
+  __shared__ double red[96];
+  double v[3] = {0.0, 0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double f = f0[i];
+    if (f > 0.0) { const double l = log(f); v[0] += 1.0; v[1] += l; v[2] += l * l; }
+  }
+  block_sum<3>(v, red);
+  if (threadIdx.x == 0) { atomicAdd(&out3[0], v[0]); atomicAdd(&out3[1], v[1]); atomicAdd(&out3[2], v[2]); }
+}
+
+bool single_utt_batch(Batch* b, const double* x, int x_length, int fs, double frame_period,
+                      int f0_length) {
+  if (!batch_layout(b, fs, frame_period, 1, &x_length, &f0_length)) return false;
+  Context* c = ctx();
+  if (x_length > 0 && x)
+    if (!WB_CUDA(cudaMemcpyAsync(b->x.p, x, (size_t)x_length * sizeof(double), cudaMemcpyHostToDevice, c->stream)))
+      return false;
+  return true;
+}
+
+bool upload_frames(Batch* b, const double* tpos, const double* f0, int n) {
+  Context* c = ctx();
+  std::vector<int> zeros(n > 0 ? n : 1, 0);
+  if (n <= 0) return true;
+  return WB_CUDA(cudaMemcpyAsync(b->frame_utt.p, zeros.data(), n * sizeof(int), cudaMemcpyHostToDevice, c->stream)) &&
+         WB_CUDA(cudaMemcpyAsync(b->frame_t.p, tpos, n * sizeof(double), cudaMemcpyHostToDevice, c->stream)) &&
+         WB_CUDA(cudaMemcpyAsync(b->f0.p, f0, n * sizeof(double), cudaMemcpyHostToDevice, c->stream)) &&
+         WB_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+void fill_nan(double* p, long long n) { for (long long i = 0; i < n; ++i) p[i] = kNaN; }
+
+}  // namespace
+
+extern "C" {
+
+// =============================================================================================
+// the WORLD API (drop-in)
+// =============================================================================================
+void InitializeDioOption(DioOption* option) {      // W/src/dio.cpp:649-665
+  option->channels_in_octave = 2.0;
+  option->f0_ceil = kCeilF0;
+  option->f0_floor = kFloorF0;
+  option->frame_period = 5;
+  option->speed = 1;
+  option->allowed_range = 0.1;
+}
+int GetSamplesForDIO(int fs, int x_length, double frame_period) {
+  return samples_for_dio(fs, x_length, frame_period);
+}
+void Dio(const double* x, int x_length, int fs, const DioOption* option,
+         double* temporal_positions, double* f0) {
+  const int n = samples_for_dio(fs, x_length, option->frame_period);
+  for (int i = 0; i < n; ++i) temporal_positions[i] = i * option->frame_period / 1000.0;
+  // W/src/dio.cpp:264-266: FixF0Contour returns without writing f0 for very short inputs
+  const int voice_range_minimum =
+      static_cast<int>(0.5 + 1000.0 / option->frame_period / option->f0_floor) * 2 + 1;
+  if (n <= voice_range_minimum) return;
+  Batch b;
+  DioParams p = {option->f0_floor, option->f0_ceil, option->channels_in_octave,
+                 option->frame_period, option->speed, option->allowed_range};
+  bool ok = ctx() && single_utt_batch(&b, x, x_length, fs, option->frame_period, n) &&
+            batch_default_frames(&b);
+  if (ok) { StageTimer t(&g_times.dio); ok = dio_run(&b, p, b.f0_raw.p); }
+  ok = ok && WB_CUDA(cudaMemcpyAsync(f0, b.f0_raw.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx()->stream)) &&
+       WB_CUDA(cudaStreamSynchronize(ctx()->stream));
+  if (!ok) fill_nan(f0, n);
+}
+
+void StoneMask(const double* x, int x_length, int fs, const double* temporal_positions,
+               const double* f0, int f0_length, double* refined_f0) {
+  if (f0_length <= 0) return;
+  Batch b;
+  bool ok = ctx() && single_utt_batch(&b, x, x_length, fs, 5.0, f0_length) &&
+            upload_frames(&b, temporal_positions, f0, f0_length);
+  if (ok) {
+    StageTimer t(&g_times.stonemask);
+    ok = stonemask_run(b.view(), fs, f0_length, b.frame_utt.p, b.frame_t.p, b.f0.p, b.f0_raw.p);
+  }
+  ok = ok && WB_CUDA(cudaMemcpyAsync(refined_f0, b.f0_raw.p, f0_length * sizeof(double), cudaMemcpyDeviceToHost, ctx()->stream)) &&
+       WB_CUDA(cudaStreamSynchronize(ctx()->stream));
+  if (!ok) fill_nan(refined_f0, f0_length);
+}
+
+int GetFFTSizeForCheapTrick(int fs, const CheapTrickOption* option) {   // W/src/cheaptrick.cpp:191-194
+  return static_cast<int>(pow(2.0, 1.0 + static_cast<int>(log(3.0 * fs / option->f0_floor + 1) / kLog2)));
+}
+double GetF0FloorForCheapTrick(int fs, int fft_size) { return 3.0 * fs / (fft_size - 3.0); }
+void InitializeCheapTrickOption(int fs, CheapTrickOption* option) {     // :230-239
+  option->q1 = -0.15;
+  option->f0_floor = kFloorF0;
+  option->fft_size = GetFFTSizeForCheapTrick(fs, option);
+}
+
+static void scatter_rows(const std::vector<double>& flat, int rows, int cols, double** dst) {
+  for (int i = 0; i < rows; ++i) memcpy(dst[i], flat.data() + (size_t)i * cols, cols * sizeof(double));
+}
+
+void CheapTrick(const double* x, int x_length, int fs, const double* temporal_positions,
+                const double* f0, int f0_length, const CheapTrickOption* option,
+                double** spectrogram) {
+  if (f0_length <= 0) return;
+  const int cols = option->fft_size / 2 + 1;
+  Batch b;
+  std::vector<double> flat((size_t)f0_length * cols, kNaN);
+  bool ok = ctx() && single_utt_batch(&b, x, x_length, fs, 5.0, f0_length) &&
+            upload_frames(&b, temporal_positions, f0, f0_length) && b.sp.alloc(flat.size());
+  if (ok) {
+    StageTimer t(&g_times.cheaptrick);
+    ok = cheaptrick_run(b.view(), fs, f0_length, b.frame_utt.p, b.frame_t.p, b.f0.p,
+                        option->fft_size, option->q1, b.sp.p);
+  }
+  ok = ok && WB_CUDA(cudaMemcpyAsync(flat.data(), b.sp.p, flat.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx()->stream)) &&
+       WB_CUDA(cudaStreamSynchronize(ctx()->stream));
+  if (!ok) std::fill(flat.begin(), flat.end(), kNaN);
+  scatter_rows(flat, f0_length, cols, spectrogram);
+}
+
+void InitializeD4COption(D4COption* option) { option->threshold = kThreshold; }
+
+void D4C(const double* x, int x_length, int fs, const double* temporal_positions,
+         const double* f0, int f0_length, int fft_size, const D4COption* option,
+         double** aperiodicity) {
+  if (f0_length <= 0) return;
+  const int cols = fft_size / 2 + 1;
+  Batch b;
+  std::vector<double> flat((size_t)f0_length * cols, kNaN);
+  bool ok = ctx() && single_utt_batch(&b, x, x_length, fs, 5.0, f0_length) &&
+            upload_frames(&b, temporal_positions, f0, f0_length) && b.ap.alloc(flat.size());
+  if (ok) {
+    StageTimer t(&g_times.d4c);
+    ok = d4c_run(b.view(), fs, f0_length, b.frame_utt.p, b.frame_t.p, b.f0.p, fft_size,
+                 option->threshold, b.ap.p);
+  }
+  ok = ok && WB_CUDA(cudaMemcpyAsync(flat.data(), b.ap.p, flat.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx()->stream)) &&
+       WB_CUDA(cudaStreamSynchronize(ctx()->stream));
+  if (!ok) std::fill(flat.begin(), flat.end(), kNaN);
+  scatter_rows(flat, f0_length, cols, aperiodicity);
+}
+
+void Synthesis(const double* f0, int f0_length, const double* const* spectrogram,
+               const double* const* aperiodicity, int fft_size, double frame_period, int fs,
+               int y_length, double* y) {
+  if (y_length <= 0) return;
+  const int cols = fft_size / 2 + 1;
+  Batch b;
+  int zero_len = 0;
+  bool ok = ctx() && f0_length >= 2 && batch_layout(&b, fs, frame_period, 1, &zero_len, &f0_length);
+  std::vector<double> flat((size_t)(f0_length > 0 ? f0_length : 1) * cols);
+  Context* c = ctx();
+  ok = ok && b.sp.alloc(flat.size()) && b.ap.alloc(flat.size());
+  if (ok) {
+    b.fft_size = fft_size;
+    for (int i = 0; i < f0_length; ++i) memcpy(flat.data() + (size_t)i * cols, spectrogram[i], cols * sizeof(double));
+    ok = WB_CUDA(cudaMemcpyAsync(b.sp.p, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream)) &&
+         WB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < f0_length; ++i) memcpy(flat.data() + (size_t)i * cols, aperiodicity[i], cols * sizeof(double));
+    ok = ok && WB_CUDA(cudaMemcpyAsync(b.ap.p, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream)) &&
+         WB_CUDA(cudaMemcpyAsync(b.f0.p, f0, f0_length * sizeof(double), cudaMemcpyHostToDevice, c->stream)) &&
+         WB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  if (ok) { StageTimer t(&g_times.synthesis); ok = synthesis_run(&b, &y_length); }
+  ok = ok && WB_CUDA(cudaMemcpyAsync(y, b.y.p, (size_t)y_length * sizeof(double), cudaMemcpyDeviceToHost, c->stream)) &&
+       WB_CUDA(cudaStreamSynchronize(c->stream));
+  if (!ok) fill_nan(y, y_length);
+}
+
+void InitializeHarvestOption(HarvestOption* option) {   // W/src/harvest.cpp:1257-1262
+  option->f0_ceil = kCeilF0;
+  option->f0_floor = kFloorF0;
+  option->frame_period = 5;
+}
+int GetSamplesForHarvest(int fs, int x_length, double frame_period) {
+  return static_cast<int>(1000.0 * x_length / fs / frame_period) + 1;
+}
+void Harvest(const double* x, int x_length, int fs, const HarvestOption* option,
+             double* temporal_positions, double* f0) {
+  const int n = GetSamplesForHarvest(fs, x_length, option->frame_period);
+  for (int i = 0; i < n; ++i) temporal_positions[i] = i * option->frame_period / 1000.0;
+  Batch b;
+  HarvestParams p = {option->f0_floor, option->f0_ceil, option->frame_period};
+  bool ok = ctx() && single_utt_batch(&b, x, x_length, fs, option->frame_period, n) &&
+            batch_default_frames(&b);
+  if (ok) { StageTimer t(&g_times.harvest); ok = harvest_run(&b, p, b.f0.p); }
+  ok = ok && WB_CUDA(cudaMemcpyAsync(f0, b.f0.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx()->stream)) &&
+       WB_CUDA(cudaStreamSynchronize(ctx()->stream));
+  if (!ok) fill_nan(f0, n);
+}
+
+// =============================================================================================
+// extension API
+// =============================================================================================
+const char* wb200_last_error(void) { return last_error(); }
+int wb200_init(int device) {
+  if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", device); return 1; }
+  return ctx() ? 0 : 1;
+}
+unsigned long long wb200_launch_count(void) { return g_launch_count; }
+void wb200_stage_times(float* o) {
+  o[0] = g_times.dio; o[1] = g_times.stonemask; o[2] = g_times.cheaptrick;
+  o[3] = g_times.d4c; o[4] = g_times.synthesis; o[5] = g_times.harvest;
+}
+int wb200_sync(void) {
+  Context* c = ctx();
+  if (!c) return 1;
+  return WB_CUDA(cudaStreamSynchronize(c->stream)) ? 0 : 1;
+}
+int wb200_randn_stream(double* out, long long n) {
+  Context* c = ctx();
+  if (!c || !ensure_randn((size_t)n)) return 1;
+  std::vector<uint32_t> h((size_t)n);
+  if (!WB_CUDA(cudaMemcpy(h.data(), c->d_randn, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost))) return 1;
+  for (long long i = 0; i < n; ++i) out[i] = h[i] / 268435456.0 - 6.0;
+  return 0;
+}
+
+wb200_batch* wb200_batch_create(int fs, double frame_period, int n_utt, const int* x_lengths) {
+  if (!ctx()) return nullptr;
+  wb200_batch* h = new wb200_batch();
+  std::vector<int> f_len(n_utt > 0 ? n_utt : 1);
+  for (int u = 0; u < n_utt; ++u) f_len[u] = samples_for_dio(fs, x_lengths[u], frame_period);
+  if (!batch_layout(&h->b, fs, frame_period, n_utt, x_lengths, f_len.data()) ||
+      !batch_default_frames(&h->b)) {
+    delete h;
+    return nullptr;
+  }
+  return h;
+}
+void wb200_batch_destroy(wb200_batch* h) {
+  if (!h) return;
+  if (ctx()) cudaStreamSynchronize(ctx()->stream);
+  delete h;
+}
+int wb200_batch_total_frames(const wb200_batch* h) { return h->b.total_frames; }
+long long wb200_batch_total_samples(const wb200_batch* h) {
+  long long s = 0;
+  for (int v : h->b.h_x_len) s += v;
+  return s;
+}
+int wb200_batch_frame_layout(const wb200_batch* h, int* f_off, int* f_len) {
+  for (int u = 0; u < h->b.n_utt; ++u) { f_off[u] = h->b.h_f_off[u]; f_len[u] = h->b.h_f_len[u]; }
+  return 0;
+}
+
+static int convert_pcm(wb200_batch* h, const int16_t* dev_pcm) {
+  Batch& b = h->b;
+  Context* c = ctx();
+  std::vector<long long> src(b.n_utt);
+  long long o = 0;
+  for (int u = 0; u < b.n_utt; ++u) { src[u] = o; o += b.h_x_len[u]; }
+  DevBuf<long long> d_src;
+  if (!d_src.alloc(b.n_utt)) return 1;
+  if (!WB_CUDA(cudaMemcpyAsync(d_src.p, src.data(), b.n_utt * sizeof(long long), cudaMemcpyHostToDevice, c->stream))) return 1;
+  dim3 grid(64, b.n_utt);
+  pcm16_to_double_kernel<<<grid, 256, 0, c->stream>>>(dev_pcm, d_src.p, b.x_off.p, b.x_len.p, b.x.p);
+  WB_LAUNCH_CHECK();
+  return WB_CUDA(cudaStreamSynchronize(c->stream)) ? 0 : 1;
+}
+int wb200_batch_upload_pcm16(wb200_batch* h, const int16_t* host_pcm) {
+  Context* c = ctx();
+  if (!c) return 1;
+  const long long n = wb200_batch_total_samples(h);
+  if (!h->pcm_stage.alloc((size_t)n)) return 1;
+  if (!WB_CUDA(cudaMemcpyAsync(h->pcm_stage.p, host_pcm, (size_t)n * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream))) return 1;
+  return convert_pcm(h, h->pcm_stage.p);
+}
+int wb200_batch_set_pcm16_device(wb200_batch* h, const int16_t* dev_pcm) {
+  if (!ctx()) return 1;
+  return convert_pcm(h, dev_pcm);
+}
+int wb200_batch_upload_f64(wb200_batch* h, const double* host_x) {
+  Context* c = ctx();
+  if (!c) return 1;
+  Batch& b = h->b;
+  long long o = 0;
+  for (int u = 0; u < b.n_utt; ++u) {
+    if (b.h_x_len[u] > 0 &&
+        !WB_CUDA(cudaMemcpyAsync(b.x.p + b.h_x_off[u], host_x + o, (size_t)b.h_x_len[u] * sizeof(double), cudaMemcpyHostToDevice, c->stream)))
+      return 1;
+    o += b.h_x_len[u];
+  }
+  return WB_CUDA(cudaStreamSynchronize(c->stream)) ? 0 : 1;
+}
+
+int wb200_batch_dio(wb200_batch* h, const DioOption* o) {
+  if (!ctx()) return 1;
+  DioParams p = {o->f0_floor, o->f0_ceil, o->channels_in_octave, o->frame_period, o->speed, o->allowed_range};
+  StageTimer t(&g_times.dio);
+  return dio_run(&h->b, p, h->b.f0_raw.p) ? 0 : 1;
+}
+int wb200_batch_stonemask(wb200_batch* h) {
+  if (!ctx()) return 1;
+  Batch& b = h->b;
+  StageTimer t(&g_times.stonemask);
+  return stonemask_run(b.view(), b.fs, b.total_frames, b.frame_utt.p, b.frame_t.p, b.f0_raw.p, b.f0.p) ? 0 : 1;
+}
+int wb200_batch_harvest(wb200_batch* h, const HarvestOption* o) {
+  if (!ctx()) return 1;
+  HarvestParams p = {o->f0_floor, o->f0_ceil, o->frame_period};
+  StageTimer t(&g_times.harvest);
+  return harvest_run(&h->b, p, h->b.f0.p) ? 0 : 1;
+}
+int wb200_batch_cheaptrick(wb200_batch* h, const CheapTrickOption* o) {
+  if (!ctx()) return 1;
+  Batch& b = h->b;
+  b.fft_size = o->fft_size;
+  if (!b.sp.alloc((size_t)b.total_frames * (o->fft_size / 2 + 1))) return 1;
+  StageTimer t(&g_times.cheaptrick);
+  return cheaptrick_run(b.view(), b.fs, b.total_frames, b.frame_utt.p, b.frame_t.p, b.f0.p, o->fft_size, o->q1, b.sp.p) ? 0 : 1;
+}
+int wb200_batch_d4c(wb200_batch* h, int fft_size, const D4COption* o) {
+  if (!ctx()) return 1;
+  Batch& b = h->b;
+  b.fft_size = fft_size;
+  if (!b.ap.alloc((size_t)b.total_frames * (fft_size / 2 + 1))) return 1;
+  StageTimer t(&g_times.d4c);
+  return d4c_run(b.view(), b.fs, b.total_frames, b.frame_utt.p, b.frame_t.p, b.f0.p, fft_size, o->threshold, b.ap.p) ? 0 : 1;
+}
+int wb200_batch_synthesis(wb200_batch* h, const int* y_lengths) {
+  if (!ctx()) return 1;
+  Batch& b = h->b;
+  std::vector<int> yl(b.n_utt > 0 ? b.n_utt : 1);
+  for (int u = 0; u < b.n_utt; ++u)
+    yl[u] = y_lengths ? y_lengths[u]
+                      : static_cast<int>((b.h_f_len[u] - 1) * b.frame_period / 1000.0 * b.fs) + 1;
+  StageTimer t(&g_times.synthesis);
+  return synthesis_run(&b, yl.data()) ? 0 : 1;
+}
+
+static int d2h(void* dst, const void* src, size_t bytes) {
+  Context* c = ctx();
+  if (!c || !src) { set_error("result not available (stage not run?)"); return 1; }
+  return (WB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream)) &&
+          WB_CUDA(cudaStreamSynchronize(c->stream))) ? 0 : 1;
+}
+static int h2d(void* dst, const void* src, size_t bytes) {
+  Context* c = ctx();
+  if (!c) return 1;
+  return (WB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream)) &&
+          WB_CUDA(cudaStreamSynchronize(c->stream))) ? 0 : 1;
+}
+int wb200_batch_get_f0(wb200_batch* h, double* out, int refined) {
+  return d2h(out, refined ? h->b.f0.p : h->b.f0_raw.p, (size_t)h->b.total_frames * sizeof(double));
+}
+int wb200_batch_set_f0(wb200_batch* h, const double* in, int refined) {
+  return h2d(refined ? h->b.f0.p : h->b.f0_raw.p, in, (size_t)h->b.total_frames * sizeof(double));
+}
+int wb200_batch_get_sp(wb200_batch* h, double* out) {
+  return d2h(out, h->b.sp.p, (size_t)h->b.total_frames * (h->b.fft_size / 2 + 1) * sizeof(double));
+}
+int wb200_batch_get_ap(wb200_batch* h, double* out) {
+  return d2h(out, h->b.ap.p, (size_t)h->b.total_frames * (h->b.fft_size / 2 + 1) * sizeof(double));
+}
+int wb200_batch_set_sp_ap(wb200_batch* h, int fft_size, const double* sp, const double* ap) {
+  Batch& b = h->b;
+  b.fft_size = fft_size;
+  const size_t n = (size_t)b.total_frames * (fft_size / 2 + 1);
+  if (!b.sp.alloc(n) || !b.ap.alloc(n)) return 1;
+  return h2d(b.sp.p, sp, n * sizeof(double)) || h2d(b.ap.p, ap, n * sizeof(double));
+}
+long long wb200_batch_total_y(const wb200_batch* h) {
+  long long s = 0;
+  for (int v : h->b.h_y_len) s += v;
+  return s;
+}
+int wb200_batch_y_layout(const wb200_batch* h, long long* y_off, int* y_len) {
+  long long o = 0;
+  for (size_t u = 0; u < h->b.h_y_len.size(); ++u) { y_off[u] = o; y_len[u] = h->b.h_y_len[u]; o += h->b.h_y_len[u]; }
+  return 0;
+}
+int wb200_batch_get_y(wb200_batch* h, double* out) {
+  Context* c = ctx();
+  Batch& b = h->b;
+  if (!c || !b.y.p) { set_error("synthesis has not been run"); return 1; }
+  long long o = 0;
+  for (int u = 0; u < b.n_utt; ++u) {
+    if (b.h_y_len[u] > 0 &&
+        !WB_CUDA(cudaMemcpyAsync(out + o, b.y.p + b.h_y_off[u], (size_t)b.h_y_len[u] * sizeof(double), cudaMemcpyDeviceToHost, c->stream)))
+      return 1;
+    o += b.h_y_len[u];
+  }
+  return WB_CUDA(cudaStreamSynchronize(c->stream)) ? 0 : 1;
+}
+int wb200_batch_get_y_pcm16(wb200_batch* h, int16_t* out) {
+  Context* c = ctx();
+  Batch& b = h->b;
+  if (!c || !b.y.p) { set_error("synthesis has not been run"); return 1; }
+  DevBuf<int16_t> tmp;
+  if (!tmp.alloc((size_t)b.total_y)) return 1;
+  y_to_pcm16_kernel<<<(unsigned)((b.total_y + 255) / 256), 256, 0, c->stream>>>(b.y.p, b.total_y, tmp.p);
+  WB_LAUNCH_CHECK();
+  long long o = 0;
+  for (int u = 0; u < b.n_utt; ++u) {
+    if (b.h_y_len[u] > 0 &&
+        !WB_CUDA(cudaMemcpyAsync(out + o, tmp.p + b.h_y_off[u], (size_t)b.h_y_len[u] * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream)))
+      return 1;
+    o += b.h_y_len[u];
+  }
+  return WB_CUDA(cudaStreamSynchronize(c->stream)) ? 0 : 1;
+}
+void* wb200_batch_device_ptr(wb200_batch* h, const char* which) {
+  Batch& b = h->b;
+  const std::string w(which);
+  if (w == "x") return b.x.p;
+  if (w == "f0_raw") return b.f0_raw.p;
+  if (w == "f0") return b.f0.p;
+  if (w == "sp") return b.sp.p;
+  if (w == "ap") return b.ap.p;
+  if (w == "y") return b.y.p;
+  return nullptr;
+}
+int wb200_batch_lf0_stats(wb200_batch* h, double* out3) {
+  Context* c = ctx();
+  if (!c) return 1;
+  DevBuf<double> d;
+  if (!d.alloc(3)) return 1;
+  if (!WB_CUDA(cudaMemsetAsync(d.p, 0, 3 * sizeof(double), c->stream))) return 1;
+  if (h->b.total_frames > 0) {
+    lf0_stats_kernel<<<148, 256, 0, c->stream>>>(h->b.f0.p, h->b.total_frames, d.p);
+    WB_LAUNCH_CHECK();
+  }
+  return d2h(out3, d.p, 3 * sizeof(double));
+}
+
+}  // extern "C"

@@ -1,0 +1,202 @@
+// world-b200: CheapTrick spectral envelope, one CTA per frame.
+//
+// Reference: W/src/cheaptrick.cpp (CheapTrick :200-228, CheapTrickGeneralBody :159-187,
+// GetWindowedWaveform :112-142, GetPowerSpectrum :64-82, SmoothingWithRecovery :22-57,
+// AddInfinitesimalNoise :147-151) and W/src/common.cpp (DCCorrection :56-75,
+// LinearSmoothing :77-111).  The reference walks the frames of one utterance sequentially on
+// one core; here every frame of every utterance in the batch is an independent CTA whose
+// whole working set (windowed frame, power spectrum, mirrored cumulative spectrum, cepstrum)
+// stays in shared memory; HBM sees one read of the window and one write of the output row.
+//
+// randn: the reference draws (2*hwl+1) + (N/2+1) variates per frame, in frame order
+// (SURVEY Appendix A1).  A per-utterance exclusive scan of those counts gives each frame its
+// offset into the precomputed randn table, so the dither is bit-identical to the reference.
+#include "wb_batch.h"
+#include "wb_fft.cuh"
+
+namespace wb {
+
+__device__ __forceinline__ double cheaptrick_f0(double f0, double f0_floor) {
+  return f0 <= f0_floor ? kDefaultF0 : f0;       // W/src/cheaptrick.cpp:217
+}
+__device__ __forceinline__ int cheaptrick_hwl(int fs, double f0c) {
+  return matlab_round(div_rn(mul_rn(1.5, (double)fs), f0c));   // :114
+}
+
+__global__ void cheaptrick_count_kernel(const double* __restrict__ f0, int total_frames, int fs,
+                                        int fft_size, double f0_floor,
+                                        long long* __restrict__ counts) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= total_frames) return;
+  const double f0c = cheaptrick_f0(f0[f], f0_floor);
+  counts[f] = 2LL * cheaptrick_hwl(fs, f0c) + 1 + fft_size / 2 + 1;
+}
+
+// dynamic shared memory: [ buf: cpad_size(N/2) double2 | aux: N + 16 doubles | red: 96 doubles ]
+__global__ void __launch_bounds__(256)
+cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __restrict__ frame_t,
+                  const double* __restrict__ f0_in, const long long* __restrict__ rng_off,
+                  const uint32_t* __restrict__ randn_tab, const double2* __restrict__ tw,
+                  int fs, int log2n, double q1, double f0_floor, double* __restrict__ sp_out) {
+  extern __shared__ double2 smem2[];
+  const int N = 1 << log2n, M = N >> 1, log2m = log2n - 1, half = M;   // half = N/2
+  double2* buf = smem2;
+  double* bufd = reinterpret_cast<double*>(buf);
+  double* aux = reinterpret_cast<double*>(buf + cpad_size(M));
+  double* red = aux + N + 16;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int f = blockIdx.x;
+  const int utt = frame_utt[f];
+  const double* __restrict__ x = u.x + u.x_off[utt];
+  const int x_len = u.x_len[utt];
+  const double t_pos = frame_t[f];
+  const double f0c = cheaptrick_f0(f0_in[f], f0_floor);
+  const uint32_t* __restrict__ rn = randn_tab + rng_off[f];
+  double* __restrict__ out = sp_out + (size_t)f * (half + 1);
+
+  const int hwl = cheaptrick_hwl(fs, f0c);
+  const int W = 2 * hwl + 1;
+  const int boundary = static_cast<int>(mul_rn(f0c * 2.0 / 3.0, (double)N) / fs) + 1;
+  if (W > N || half + 2 * boundary + 1 > N + 16 || !(f0c > 0.0)) {
+    // outside the domain the reference supports (it would index out of bounds)
+    for (int k = tid; k <= half; k += T) out[k] = __longlong_as_double(0x7ff8000000000000LL);
+    return;
+  }
+
+  // ---- GetWindowedWaveform (:112-142) ---------------------------------------------------
+  const int origin = matlab_round(add_rn(mul_rn(t_pos, (double)fs), 0.001));
+  double acc[3];
+  acc[0] = 0.0;
+  for (int i = tid; i < W; i += T) {
+    const double position = div_rn(div_rn((double)(i - hwl), 1.5), (double)fs);
+    const double w = 0.5 * cos(kPi * position * f0c) + 0.5;
+    aux[i] = w;
+    acc[0] += w * w;
+  }
+  {
+    double v1[1] = {acc[0]};
+    block_sum<1>(v1, red);
+    acc[0] = v1[0];
+  }
+  const double norm = sqrt(acc[0]);
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = tid; i < N; i += T) {
+    double wave = 0.0;
+    if (i < W) {
+      const double w = aux[i] / norm;
+      aux[i] = w;
+      const int idx = min(x_len - 1, max(0, origin + i - hwl));
+      wave = x[idx] * w + randn_from_u32(rn[i]) * kMySafeGuardMinimum;
+      s1 += wave;
+      s2 += w;
+    }
+    bufd[rfft_in_slot(i, log2m)] = wave;
+  }
+  {
+    double v2[2] = {s1, s2};
+    block_sum<2>(v2, red);
+    s1 = v2[0]; s2 = v2[1];
+  }
+  const double coef = s1 / s2;
+  for (int i = tid; i < W; i += T) bufd[rfft_in_slot(i, log2m)] -= aux[i] * coef;
+
+  // ---- GetPowerSpectrum (:64-82) -----------------------------------------------------------
+  fft_dit<false>(buf, log2m, tw);
+  for (int k = tid; k <= half; k += T) {
+    const double2 X = rfft_bin(buf, log2m, k, tw);
+    aux[k] = X.x * X.x + X.y * X.y;
+  }
+  __syncthreads();
+  // DCCorrection (common.cpp:56-75)
+  const double df = (double)fs / N;                 // exact: N is a power of two
+  {
+    const int upper_limit = 2 + static_cast<int>(mul_rn(f0c, (double)N) / fs);
+    for (int i = tid; i < upper_limit - 1; i += T)
+      bufd[i] = interp1q_at(f0c, -df, aux, upper_limit + 1, mul_rn((double)i, (double)fs) / N);
+    __syncthreads();
+    for (int i = tid; i < upper_limit - 1; i += T) aux[i] += bufd[i];
+    __syncthreads();
+  }
+  // ---- LinearSmoothing (common.cpp:77-111), width = f0 * 2 / 3 ------------------------------
+  const double width = f0c * 2.0 / 3.0;
+  const int len = half + 2 * boundary + 1;
+  for (int i = tid; i < len; i += T) {
+    double v;
+    if (i < boundary) v = aux[boundary - i];
+    else if (i < half + boundary) v = aux[i - boundary];
+    else v = aux[half - (i - (half + boundary))];
+    bufd[i] = mul_rn(v, (double)fs) / N;
+  }
+  __syncthreads();
+  block_inclusive_scan(bufd, len, red);
+  {
+    const double origin_axis = -(boundary - 0.5) * fs / N;
+    const uint32_t* __restrict__ rn2 = rn + W;
+    for (int k = tid; k <= half; k += T) {
+      const double fa = add_rn(mul_rn((double)k / N, (double)fs), -width / 2.0);
+      const double low = interp1q_at(origin_axis, df, bufd, len, fa);
+      const double high = interp1q_at(origin_axis, df, bufd, len, add_rn(fa, width));
+      const double sm = (high - low) / width;
+      // AddInfinitesimalNoise (:147-151) then log (:38-39)
+      aux[k] = log(sm + fabs(randn_from_u32(rn2[k])) * kEps);
+    }
+  }
+  __syncthreads();
+  // ---- SmoothingWithRecovery (:22-57) ---------------------------------------------------------
+  for (int i = tid; i < N; i += T) bufd[rfft_in_slot(i, log2m)] = aux[i <= half ? i : N - i];
+  fft_dit<false>(buf, log2m, tw);
+  for (int k = tid; k <= half; k += T) {
+    const double re = rfft_bin(buf, log2m, k, tw).x;
+    double lifter = 1.0, comp = (1.0 - 2.0 * q1) + 2.0 * q1;
+    if (k > 0) {
+      const double quefrency = (double)k / fs;
+      const double a = kPi * f0c * quefrency;
+      lifter = sin(a) / a;
+      comp = (1.0 - 2.0 * q1) + 2.0 * q1 * cos(2.0 * kPi * quefrency * f0c);
+    }
+    aux[k] = re * lifter * comp / N;
+  }
+  __syncthreads();
+  for (int k = tid; k < half; k += T) {
+    const double2 z = c2r_pack(make_double2(aux[k], 0.0), make_double2(aux[half - k], 0.0), k, log2m, tw);
+    buf[cpad(brev(k, log2m))] = z;
+  }
+  fft_dit<true>(buf, log2m, tw);
+  for (int k = tid; k <= half; k += T) out[k] = exp(bufd[rfft_out_slot(k)]);
+}
+
+bool cheaptrick_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
+                    const double* frame_t, const double* f0, int fft_size, double q1,
+                    double* sp) {
+  Context* c = ctx();
+  if (!c) return false;
+  if (total_frames <= 0) return true;
+  int log2n = 0;
+  while ((1 << log2n) < fft_size) ++log2n;
+  if ((1 << log2n) != fft_size || log2n < 5 || log2n > 14) {
+    set_error("CheapTrick: unsupported fft_size %d", fft_size);
+    return false;
+  }
+  const double f0_floor = 3.0 * fs / (fft_size - 3.0);      // GetF0FloorForCheapTrick :196-198
+  DevBuf<long long> counts, offs, totals;
+  if (!counts.alloc(total_frames) || !offs.alloc(total_frames) || !totals.alloc(u.n_utt)) return false;
+  cudaStream_t st = c->stream;
+  cheaptrick_count_kernel<<<(total_frames + 255) / 256, 256, 0, st>>>(f0, total_frames, fs, fft_size, f0_floor, counts.p);
+  WB_LAUNCH_CHECK();
+  if (!segmented_exclusive_scan(counts.p, u.f_off, u.f_len, u.n_utt, offs.p, totals.p)) return false;
+  std::vector<long long> h_tot(u.n_utt);
+  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_tot.data(), totals.p, u.n_utt * sizeof(long long), cudaMemcpyDeviceToHost, st), false);
+  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  long long mx = 0;
+  for (long long v : h_tot) mx = v > mx ? v : mx;
+  if (!ensure_randn((size_t)mx)) return false;
+  const size_t smem = cpad_size(fft_size / 2) * sizeof(double2) + (fft_size + 16 + 96) * sizeof(double);
+  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(cheaptrick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+  cheaptrick_kernel<<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0, offs.p, c->d_randn, c->d_twiddle, fs, log2n, q1, f0_floor, sp);
+  WB_LAUNCH_CHECK();
+  // counts/offs are freed when this returns: make sure the kernel is done with them
+  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  return true;
+}
+
+}  // namespace wb

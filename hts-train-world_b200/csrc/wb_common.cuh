@@ -1,0 +1,173 @@
+// world-b200: shared host/device declarations for the sm_100a WORLD kernels.
+//
+// Layout conventions:
+//   * a "batch" is a set of utterances resident in HBM; samples of all utterances are
+//     concatenated in one double array, frames of all utterances are concatenated in one
+//     frame table (utterance id, time position, f0), spectrogram / aperiodicity are dense
+//     [total_frames][fft_size/2+1] double matrices.
+//   * every per-frame (or per-pulse) kernel runs one CTA per frame (pulse) with the frame
+//     staged in shared memory; FFTs are FP64 radix-8 shared-memory transforms (wb_fft.cuh).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace wb {
+
+// ---- constants of the reference (W/src/world/constantnumbers.h) -------------------------
+constexpr double kPi = 3.1415926535897932384;
+constexpr double kMySafeGuardMinimum = 0.000000000001;
+constexpr double kEps = 0.00000000000000022204460492503131;
+constexpr double kFloorF0 = 71.0;
+constexpr double kCeilF0 = 800.0;
+constexpr double kDefaultF0 = 500.0;
+constexpr double kLog2 = 0.69314718055994529;
+constexpr double kMaximumValue = 100000.0;
+constexpr double kFloorF0StoneMask = 40.0;
+constexpr double kFrequencyInterval = 3000.0;
+constexpr double kUpperLimit = 15000.0;
+constexpr double kThreshold = 0.85;
+constexpr double kFloorF0D4C = 47.0;
+
+// twiddle table: tw[k] = exp(-2 pi i k / kTwN), k in [0, kTwN/2]
+constexpr int kTwLog2 = 15;
+constexpr int kTwN = 1 << kTwLog2;
+
+// ---- error channel (the WORLD API is void) ----------------------------------
+void set_error(const char* fmt, ...);
+const char* last_error();
+bool check_cuda(cudaError_t e, const char* what, const char* file, int line);
+#define WB_CUDA(x) ::wb::check_cuda((x), #x, __FILE__, __LINE__)
+#define WB_CUDA_OR_RETURN(x, ret) do { if (!WB_CUDA(x)) return ret; } while (0)
+
+extern unsigned long long g_launch_count;   // kernels launched by this library
+#define WB_LAUNCH_CHECK() do { ++::wb::g_launch_count; ::wb::check_cuda(cudaGetLastError(), "kernel launch", __FILE__, __LINE__); } while (0)
+
+// ---- device context ---------------------------------------------------------------------
+struct Context {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  double2* d_twiddle = nullptr;          // [kTwN/2 + 1]
+  uint32_t* d_randn = nullptr;           // randn table: variate k = d_randn[k] / 2^28 - 6
+  size_t randn_count = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+};
+Context* ctx();                           // lazily initialised; nullptr on failure
+bool ensure_randn(size_t count);          // grow the randn table to >= count variates
+
+// simple stream-ordered device buffer
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  bool alloc(size_t count) {
+    if (count <= n && p) return true;
+    release();
+    if (count == 0) count = 1;
+    if (!WB_CUDA(cudaMalloc((void**)&p, count * sizeof(T)))) { p = nullptr; n = 0; return false; }
+    n = count;
+    return true;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DevBuf() { release(); }
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+#ifdef __CUDACC__
+// ---- small device helpers ----------------------------------------------------------------
+// matlab_round (W/src/matlabfunctions.cpp:212-214): half away from zero via truncation.
+__host__ __device__ __forceinline__ int matlab_round(double x) {
+  return x > 0 ? static_cast<int>(x + 0.5) : static_cast<int>(x - 0.5);
+}
+
+// Non-contracted arithmetic for index-determining expressions (the reference is compiled
+// without FMA contraction; an fma() here could move a rounding across an integer boundary).
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+__device__ __forceinline__ double randn_from_u32(uint32_t v) {
+  return static_cast<double>(v) / 268435456.0 - 6.0;   // W/src/matlabfunctions.cpp:276
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of up to 3 values; every thread gets the totals. `red` = >= 3*32 doubles
+// of shared scratch.  Contains two __syncthreads().
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();          // protect `red` from a previous use
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[i * 32 + wid] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double t = lane < nw ? red[i * 32 + lane] : 0.0;
+    v[i] = warp_sum(t);
+  }
+}
+
+// In-place inclusive prefix sum of a[0..n) in shared memory (FP64), blockDim.x threads.
+// Each thread scans a contiguous chunk, chunk totals are scanned with warp shuffles.
+// `red` = >= 33 doubles of shared scratch.  Ends with a __syncthreads().
+__device__ __forceinline__ void block_inclusive_scan(double* a, int n, double* red) {
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int per = (n + T - 1) / T;
+  const int lo = min(n, tid * per), hi = min(n, lo + per);
+  double s = 0.0;
+  for (int i = lo; i < hi; ++i) { s += a[i]; a[i] = s; }
+  // exclusive scan of s across threads
+  const int lane = tid & 31, wid = tid >> 5, nw = (T + 31) >> 5;
+  double inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) red[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    double w = lane < nw ? red[lane] : 0.0;
+    double winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      double t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    red[lane] = winc - w;    // exclusive warp offsets
+  }
+  __syncthreads();
+  const double offset = red[wid] + (inc - s);
+  if (offset != 0.0)
+    for (int i = lo; i < hi; ++i) a[i] += offset;
+  __syncthreads();
+}
+
+// interp1Q (W/src/matlabfunctions.cpp:220-241) for one query: uniform grid starting at x0
+// with step dx, n samples in y; delta_y[n-1] is defined as 0 by the reference.
+__device__ __forceinline__ double interp1q_at(double x0, double dx, const double* y, int n,
+                                              double xi) {
+  const double r = div_rn(add_rn(xi, -x0), dx);
+  int base = static_cast<int>(r);
+  const double frac = r - base;
+  base = max(0, min(n - 1, base));                 // memory guard only (UB in the reference)
+  const double y0 = y[base];
+  const double dy = base + 1 < n ? y[base + 1] - y0 : 0.0;
+  return add_rn(y0, mul_rn(dy, frac));
+}
+#endif  // __CUDACC__
+
+}  // namespace wb

@@ -1,0 +1,303 @@
+// world-b200: device context, error channel, twiddle table, randn table, batch layout.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+#include <mutex>
+#include <string>
+#include "wb_batch.h"
+
+namespace wb {
+
+// ---------------------------------------------------------------------------------------------
+// error channel: the WORLD API returns void, so failures are recorded here and
+// the caller's outputs are NaN-filled by the API layer.
+// ---------------------------------------------------------------------------------------------
+static std::mutex g_err_mutex;
+static std::string g_err;
+unsigned long long g_launch_count = 0;
+StageTimes g_times;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  std::lock_guard<std::mutex> lock(g_err_mutex);
+  g_err = buf;
+  fprintf(stderr, "[world_b200] error: %s\n", buf);
+}
+const char* last_error() {
+  std::lock_guard<std::mutex> lock(g_err_mutex);
+  return g_err.c_str();
+}
+bool check_cuda(cudaError_t e, const char* what, const char* file, int line) {
+  if (e == cudaSuccess) return true;
+  set_error("%s failed at %s:%d: %s", what, file, line, cudaGetErrorString(e));
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// randn table.  The reference's randn() (W/src/matlabfunctions.cpp:247-277) is a xorshift128
+// stream re-seeded at the top of CheapTrick / D4C / Synthesis, so variate k of a call is a
+// data-independent constant.  We materialise the stream once in HBM (uint32 sum of the twelve
+// (w >> 4) terms; value = sum / 2^28 - 6) and every kernel indexes it.  The table is generated
+// on the GPU: the host only computes, by GF(2) matrix powers of the xorshift step, the
+// generator state at the start of every chunk of kRandnChunk variates.
+// ---------------------------------------------------------------------------------------------
+struct XState { uint32_t x, y, z, w; };
+constexpr int kRandnChunk = 1024;
+
+__host__ __device__ inline void xorshift_step(XState& s) {
+  const uint32_t t = s.x ^ (s.x << 11);
+  s.x = s.y; s.y = s.z; s.z = s.w;
+  s.w = (s.w ^ (s.w >> 19)) ^ (t ^ (t >> 8));
+}
+
+struct GF2Mat { XState col[128]; };   // column i = image of basis vector i
+
+static XState gf2_apply(const GF2Mat& m, const XState& s) {
+  XState r = {0, 0, 0, 0};
+  const uint32_t w[4] = {s.x, s.y, s.z, s.w};
+  for (int i = 0; i < 128; ++i)
+    if ((w[i >> 5] >> (i & 31)) & 1u) {
+      r.x ^= m.col[i].x; r.y ^= m.col[i].y; r.z ^= m.col[i].z; r.w ^= m.col[i].w;
+    }
+  return r;
+}
+static void gf2_mul(const GF2Mat& a, const GF2Mat& b, GF2Mat* out) {   // out = a * b
+  GF2Mat r;
+  for (int i = 0; i < 128; ++i) r.col[i] = gf2_apply(a, b.col[i]);
+  *out = r;
+}
+static void gf2_step_matrix(GF2Mat* m) {
+  for (int i = 0; i < 128; ++i) {
+    uint32_t w[4] = {0, 0, 0, 0};
+    w[i >> 5] = 1u << (i & 31);
+    XState s = {w[0], w[1], w[2], w[3]};
+    xorshift_step(s);
+    m->col[i] = s;
+  }
+}
+static void gf2_pow(const GF2Mat& base, unsigned long long e, GF2Mat* out) {
+  GF2Mat result, b = base;
+  for (int i = 0; i < 128; ++i) {          // identity
+    uint32_t w[4] = {0, 0, 0, 0};
+    w[i >> 5] = 1u << (i & 31);
+    result.col[i] = XState{w[0], w[1], w[2], w[3]};
+  }
+  while (e) {
+    if (e & 1ull) gf2_mul(b, result, &result);
+    gf2_mul(b, b, &b);
+    e >>= 1;
+  }
+  *out = result;
+}
+
+__global__ void randn_table_kernel(const XState* __restrict__ starts, uint32_t* __restrict__ out,
+                                   size_t n_chunks) {
+  const size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (c >= n_chunks) return;
+  XState s = starts[c];
+  uint32_t* o = out + c * kRandnChunk;
+  for (int k = 0; k < kRandnChunk; ++k) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) { xorshift_step(s); acc += s.w >> 4; }
+    o[k] = acc;
+  }
+}
+
+static std::mutex g_ctx_mutex;
+static Context g_ctx;
+static bool g_ctx_ok = false, g_ctx_failed = false;
+
+Context* ctx() {
+  std::lock_guard<std::mutex> lock(g_ctx_mutex);
+  if (g_ctx_ok) return &g_ctx;
+  if (g_ctx_failed) return nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: world_b200 has no CPU fallback");
+    g_ctx_failed = true;
+    return nullptr;
+  }
+  int dev = 0;
+  if (!WB_CUDA(cudaGetDevice(&dev))) { g_ctx_failed = true; return nullptr; }
+  g_ctx.device = dev;
+  cudaDeviceProp prop;
+  if (!WB_CUDA(cudaGetDeviceProperties(&prop, dev))) { g_ctx_failed = true; return nullptr; }
+  g_ctx.sm_count = prop.multiProcessorCount;
+  g_ctx.smem_optin = prop.sharedMemPerBlockOptin;
+  if (!WB_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking))) {
+    g_ctx_failed = true; return nullptr;
+  }
+  // twiddles, rounded from long double
+  std::vector<double2> tw(kTwN / 2 + 1);
+  for (int k = 0; k <= kTwN / 2; ++k) {
+    const long double a = -2.0L * 3.14159265358979323846264338327950288L * k / kTwN;
+    tw[k] = make_double2((double)cosl(a), (double)sinl(a));
+  }
+  if (!WB_CUDA(cudaMalloc((void**)&g_ctx.d_twiddle, tw.size() * sizeof(double2))) ||
+      !WB_CUDA(cudaMemcpy(g_ctx.d_twiddle, tw.data(), tw.size() * sizeof(double2),
+                          cudaMemcpyHostToDevice))) {
+    g_ctx_failed = true; return nullptr;
+  }
+  g_ctx_ok = true;
+  return &g_ctx;
+}
+
+bool ensure_randn(size_t count) {
+  Context* c = ctx();
+  if (!c) return false;
+  if (count <= c->randn_count) return true;
+  size_t n_chunks = (count + kRandnChunk - 1) / kRandnChunk;
+  const size_t min_chunks = (size_t)4096;               // 4 Mi variates at least
+  if (n_chunks < min_chunks) n_chunks = min_chunks;
+  n_chunks = (n_chunks * 5 / 4 + 1023) / 1024 * 1024;  // head-room, fewer regenerations
+  static GF2Mat jump;
+  static bool have_jump = false;
+  if (!have_jump) {
+    GF2Mat step;
+    gf2_step_matrix(&step);
+    gf2_pow(step, 12ull * kRandnChunk, &jump);
+    have_jump = true;
+  }
+  std::vector<XState> starts(n_chunks);
+  XState s = {123456789u, 362436069u, 521288629u, 88675123u};   // randn_reseed()
+  for (size_t i = 0; i < n_chunks; ++i) { starts[i] = s; s = gf2_apply(jump, s); }
+  XState* d_starts = nullptr;
+  uint32_t* d_tab = nullptr;
+  if (!WB_CUDA(cudaMalloc((void**)&d_starts, n_chunks * sizeof(XState)))) return false;
+  if (!WB_CUDA(cudaMalloc((void**)&d_tab, n_chunks * kRandnChunk * sizeof(uint32_t)))) {
+    cudaFree(d_starts); return false;
+  }
+  bool ok = WB_CUDA(cudaMemcpyAsync(d_starts, starts.data(), n_chunks * sizeof(XState),
+                                    cudaMemcpyHostToDevice, c->stream));
+  if (ok) {
+    randn_table_kernel<<<(unsigned)((n_chunks + 127) / 128), 128, 0, c->stream>>>(d_starts, d_tab, n_chunks);
+    WB_LAUNCH_CHECK();
+    ok = WB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  cudaFree(d_starts);
+  if (!ok) { cudaFree(d_tab); return false; }
+  if (c->d_randn) cudaFree(c->d_randn);
+  c->d_randn = d_tab;
+  c->randn_count = n_chunks * kRandnChunk;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// segmented exclusive scan over the frames of each utterance (one CTA per utterance)
+// ---------------------------------------------------------------------------------------------
+__global__ void seg_scan_kernel(const long long* __restrict__ counts, const int* __restrict__ f_off,
+                                const int* __restrict__ f_len, long long* __restrict__ out,
+                                long long* __restrict__ totals) {
+  __shared__ long long wsum[32];
+  __shared__ long long carry_s;
+  const int u = blockIdx.x;
+  const int off = f_off[u], len = f_len[u];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < len; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const long long v = i < len ? counts[off + i] : 0;
+    long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      const long long w = lane < nw ? wsum[lane] : 0;
+      long long winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+      }
+      wsum[lane] = winc - w;
+      if (lane == 31) wsum[31] = winc - w;   // keep exclusive; total handled below
+    }
+    __syncthreads();
+    const long long carry = carry_s;
+    const long long excl = carry + wsum[wid] + (inc - v);
+    if (i < len) out[off + i] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && totals) totals[u] = carry_s;
+}
+
+bool segmented_exclusive_scan(const long long* counts, const int* f_off, const int* f_len,
+                              int n_utt, long long* out, long long* totals) {
+  Context* c = ctx();
+  if (!c) return false;
+  if (n_utt <= 0) return true;
+  seg_scan_kernel<<<n_utt, 256, 0, c->stream>>>(counts, f_off, f_len, out, totals);
+  WB_LAUNCH_CHECK();
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batch layout
+// ---------------------------------------------------------------------------------------------
+__global__ void default_frames_kernel(const int* __restrict__ f_off, const int* __restrict__ f_len,
+                                      double frame_period, int* __restrict__ frame_utt,
+                                      double* __restrict__ frame_t) {
+  const int u = blockIdx.x;
+  const int off = f_off[u], len = f_len[u];
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    frame_utt[off + i] = u;
+    frame_t[off + i] = __ddiv_rn(__dmul_rn((double)i, frame_period), 1000.0);  // i * fp / 1000.0
+  }
+}
+
+bool batch_layout(Batch* b, int fs, double frame_period, int n_utt, const int* x_len,
+                  const int* f_len) {
+  Context* c = ctx();
+  if (!c) return false;
+  b->fs = fs; b->frame_period = frame_period; b->n_utt = n_utt;
+  b->h_x_off.resize(n_utt); b->h_x_len.assign(x_len, x_len + n_utt);
+  b->h_f_off.resize(n_utt); b->h_f_len.assign(f_len, f_len + n_utt);
+  long long so = 0; long long fo = 0;
+  b->max_x_len = 0; b->max_f_len = 0;
+  for (int u = 0; u < n_utt; ++u) {
+    b->h_x_off[u] = so; so += (x_len[u] + 1) & ~1LL;    // keep every utterance 16-byte aligned
+    b->h_f_off[u] = (int)fo; fo += f_len[u];
+    if (x_len[u] > b->max_x_len) b->max_x_len = x_len[u];
+    if (f_len[u] > b->max_f_len) b->max_f_len = f_len[u];
+  }
+  if (fo > 0x7fffffffLL) { set_error("batch has too many frames (%lld)", fo); return false; }
+  b->total_samples = so; b->total_frames = (int)fo;
+  if (!b->x.alloc((size_t)so) || !b->x_off.alloc(n_utt) || !b->x_len.alloc(n_utt) ||
+      !b->f_off.alloc(n_utt) || !b->f_len.alloc(n_utt) || !b->frame_utt.alloc(fo) ||
+      !b->frame_t.alloc(fo) || !b->f0_raw.alloc(fo) || !b->f0.alloc(fo))
+    return false;
+  cudaStream_t st = c->stream;
+  bool ok = true;
+  if (n_utt > 0) {
+    ok = ok && WB_CUDA(cudaMemcpyAsync(b->x_off.p, b->h_x_off.data(), n_utt * sizeof(long long), cudaMemcpyHostToDevice, st));
+    ok = ok && WB_CUDA(cudaMemcpyAsync(b->x_len.p, b->h_x_len.data(), n_utt * sizeof(int), cudaMemcpyHostToDevice, st));
+    ok = ok && WB_CUDA(cudaMemcpyAsync(b->f_off.p, b->h_f_off.data(), n_utt * sizeof(int), cudaMemcpyHostToDevice, st));
+    ok = ok && WB_CUDA(cudaMemcpyAsync(b->f_len.p, b->h_f_len.data(), n_utt * sizeof(int), cudaMemcpyHostToDevice, st));
+    ok = ok && WB_CUDA(cudaStreamSynchronize(st));     // the host vectors may be reallocated later
+  }
+  return ok;
+}
+
+bool batch_default_frames(Batch* b) {
+  Context* c = ctx();
+  if (!c) return false;
+  if (b->n_utt <= 0) return true;
+  default_frames_kernel<<<b->n_utt, 256, 0, c->stream>>>(b->f_off.p, b->f_len.p, b->frame_period,
+                                                        b->frame_utt.p, b->frame_t.p);
+  WB_LAUNCH_CHECK();
+  return true;
+}
+
+}  // namespace wb

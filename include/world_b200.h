@@ -1,0 +1,88 @@
+/* world-b200 — batched extension API of libworld_b200.so (plain C ABI).
+ *
+ * The drop-in WORLD entry points (include/world/{dio,stonemask,cheaptrick,d4c,synthesis,harvest}.h)
+ * keep the reference's one-utterance-per-call signatures.  The reference pipeline forks one
+ * `analysis` process per utterance (data/Makefile.in:125,214); that loop is what this API
+ * replaces: many utterances are laid out once in HBM and every stage runs as kernels batched
+ * over all frames (or pulses) of all utterances.  f0 / spectrogram / aperiodicity stay on
+ * the device between stages.
+ *
+ * All functions return 0 on success and non-zero on failure; wb200_last_error() then holds a
+ * message.  There is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef WORLD_B200_H_
+#define WORLD_B200_H_
+#include <stdint.h>
+#include "world/cheaptrick.h"
+#include "world/d4c.h"
+#include "world/dio.h"
+#include "world/harvest.h"
+#include "world/stonemask.h"
+#include "world/synthesis.h"
+
+WORLD_BEGIN_C_DECLS
+
+typedef struct wb200_batch wb200_batch;
+
+/* error channel for the void-returning WORLD API */
+WORLD_API const char *wb200_last_error(void);
+/* bind the calling thread's CUDA device and build the context (twiddles, stream). */
+WORLD_API int wb200_init(int device);
+/* number of kernels this library has launched so far */
+WORLD_API unsigned long long wb200_launch_count(void);
+/* device time (ms, CUDA events on the library stream) of the last call of each stage:
+ * out[0..5] = dio, stonemask, cheaptrick, d4c, synthesis, harvest */
+WORLD_API void wb200_stage_times(float *out6);
+/* first `n` values of the randn table as doubles (test hook: must equal the reference's
+ * randn() stream after randn_reseed(), W/src/matlabfunctions.cpp:247-277) */
+WORLD_API int wb200_randn_stream(double *out, long long n);
+
+/* ---- batch life cycle ----------------------------------------------------------------- */
+/* x_lengths[n_utt] samples per utterance.  Frames per utterance follow GetSamplesForDIO
+ * (W/src/dio.cpp:638-640) and temporal positions are i * frame_period / 1000. */
+WORLD_API wb200_batch *wb200_batch_create(int fs, double frame_period, int n_utt,
+                                          const int *x_lengths);
+WORLD_API void wb200_batch_destroy(wb200_batch *b);
+WORLD_API int wb200_batch_total_frames(const wb200_batch *b);
+WORLD_API long long wb200_batch_total_samples(const wb200_batch *b);
+/* f_off[n_utt], f_len[n_utt]: where each utterance's frames sit in the flat frame table */
+WORLD_API int wb200_batch_frame_layout(const wb200_batch *b, int *f_off, int *f_len);
+
+/* inputs: utterances back to back (no padding) in host memory (pinned memory makes the copy
+ * asynchronous) or already in device memory. pcm16 is converted as pcm / 32768.0, the
+ * convention of the reference's wavread (W/test/audioio.cpp:229-251). */
+WORLD_API int wb200_batch_upload_pcm16(wb200_batch *b, const int16_t *host_pcm);
+WORLD_API int wb200_batch_upload_f64(wb200_batch *b, const double *host_x);
+WORLD_API int wb200_batch_set_pcm16_device(wb200_batch *b, const int16_t *dev_pcm);
+
+/* ---- stages (each = the reference function of the same name over the whole batch) -------- */
+WORLD_API int wb200_batch_dio(wb200_batch *b, const DioOption *option);        /* -> raw f0 */
+WORLD_API int wb200_batch_stonemask(wb200_batch *b);                           /* raw f0 -> f0 */
+WORLD_API int wb200_batch_harvest(wb200_batch *b, const HarvestOption *option);/* -> f0 */
+WORLD_API int wb200_batch_cheaptrick(wb200_batch *b, const CheapTrickOption *option);
+WORLD_API int wb200_batch_d4c(wb200_batch *b, int fft_size, const D4COption *option);
+/* y_lengths may be NULL: int((f0_length-1) * frame_period / 1000 * fs) + 1 (W/test/synth.cpp:259) */
+WORLD_API int wb200_batch_synthesis(wb200_batch *b, const int *y_lengths);
+
+/* ---- results / injection of upstream values (flat over the frame table) ------------------- */
+WORLD_API int wb200_batch_get_f0(wb200_batch *b, double *host_f0, int refined);
+WORLD_API int wb200_batch_set_f0(wb200_batch *b, const double *host_f0, int refined);
+WORLD_API int wb200_batch_get_sp(wb200_batch *b, double *host_sp);   /* [frames][fft/2+1] */
+WORLD_API int wb200_batch_get_ap(wb200_batch *b, double *host_ap);
+WORLD_API int wb200_batch_set_sp_ap(wb200_batch *b, int fft_size, const double *host_sp,
+                                    const double *host_ap);
+WORLD_API long long wb200_batch_total_y(const wb200_batch *b);
+WORLD_API int wb200_batch_y_layout(const wb200_batch *b, long long *y_off, int *y_len);
+WORLD_API int wb200_batch_get_y(wb200_batch *b, double *host_y);     /* back to back */
+/* 16-bit output as the reference's wavwrite: trunc(y * 32767) clamped (W/test/audioio.cpp:115-170) */
+WORLD_API int wb200_batch_get_y_pcm16(wb200_batch *b, int16_t *host_pcm);
+/* device pointers for zero-copy consumers: which = "x","f0_raw","f0","sp","ap","y" */
+WORLD_API void *wb200_batch_device_ptr(wb200_batch *b, const char *which);
+/* corpus statistics of voiced log-f0 over the batch: out = {count, sum, sum of squares};
+ * the per-GPU partials that the NCCL all-reduce combines */
+WORLD_API int wb200_batch_lf0_stats(wb200_batch *b, double *out3);
+/* block until everything queued on the library stream has finished */
+WORLD_API int wb200_sync(void);
+
+WORLD_END_C_DECLS
+#endif
