@@ -1,4 +1,444 @@
+// world-b200: D4C band aperiodicity, one CTA per frame.
+//
+// Reference: W/src/d4c.cpp — D4C :337-397, D4CLoveTrain(+Sub) :225-282, D4CGeneralBody :290-316,
+// GetCentroid :90-119, GetStaticCentroid :125-142, GetSmoothedPowerSpectrum :148-164,
+// GetStaticGroupDelay :170-186, GetCoarseAperiodicity :192-223, GetAperiodicity :325-333,
+// GetWindowedWaveform :52-84.
+//
+// What changed relative to the reference's one-core loop:
+//   * the two real FFTs of GetCentroid (x.w and (n+1).x.w) are one complex FFT; the centroid
+//     is then (a d + b c)/2 with Z[k] = a+ib, Z[N-k] = c+id — no spectrum is ever unpacked;
+//   * band spectra are transformed two at a time the same way;
+//   * std::sort + cumulative sum (25 % of the reference's CPU time) is replaced by an exact
+//     MSB-first bitwise selection of the (boundary+1)-th largest power held in registers:
+//     sorted_cumsum[N/2-boundary-1] == sum of everything below that element;
+//   * the randn dither is read from the precomputed table at the offset the sequential
+//     reference would have reached (LoveTrain draws of all voiced frames first, then
+//     3 windows per processed frame).
 #include "wb_batch.h"
+#include "wb_fft.cuh"
+#include "wb_spectral.cuh"
+
 namespace wb {
-bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt, const double* frame_t, const double* f0, int fft_size, double threshold, double* ap) { set_error("d4c: not implemented yet"); return false; }
+
+namespace {
+
+constexpr int kHanning = 1, kBlackman = 2;
+constexpr int kMaxBands = 8;
+constexpr int kVP = 9;        // power values per thread kept in registers during selection
+
+__device__ __forceinline__ int d4c_hwl(double ratio, int fs, double f0) {
+  return matlab_round(div_rn(div_rn(mul_rn(ratio, (double)fs), f0), 2.0));   // d4c.cpp:55-56
 }
+
+struct D4CConst {
+  int fs, log2nd, log2lt, nbands, window_length, sel_boundary;
+  int lt_b0, lt_b1, lt_b2;
+  int out_half;              // fft_size/2 of the output axis
+  double threshold;
+  int centers[kMaxBands];
+};
+
+// windowed waveform with dither and weighted-mean removal (d4c.cpp:52-84).  Sample i is
+// written to base[wslot(i)], its window value to base[vslot(i)] (scratch).  Returns W.
+// Contains block syncs; on return every thread has finished its own slots only.
+template <typename WS, typename VS>
+__device__ __forceinline__ int windowed_waveform(const double* __restrict__ x, int x_len, int fs,
+                                                 double f0, double position, int window_type,
+                                                 double ratio, const uint32_t* __restrict__ rn,
+                                                 double* base, WS wslot, VS vslot, double* red) {
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int hwl = d4c_hwl(ratio, fs, f0);
+  const int W = 2 * hwl + 1;
+  const int origin = matlab_round(add_rn(mul_rn(position, (double)fs), 0.001));
+  double s[2] = {0.0, 0.0};
+  for (int i = tid; i < W; i += T) {
+    const double pos = div_rn(div_rn(mul_rn(2.0, (double)(i - hwl)), ratio), (double)fs);
+    const double a = kPi * pos * f0;
+    const double w = window_type == kHanning ? 0.5 * cos(a) + 0.5
+                                             : 0.42 + 0.5 * cos(a) + 0.08 * cos(a * 2);
+    const int idx = min(x_len - 1, max(0, origin + i - hwl));
+    const double wave = x[idx] * w + randn_from_u32(rn[i]) * kMySafeGuardMinimum;
+    base[wslot(i)] = wave;
+    base[vslot(i)] = w;
+    s[0] += wave;
+    s[1] += w;
+  }
+  block_sum<2>(s, red);
+  const double coef = s[0] / s[1];
+  for (int i = tid; i < W; i += T) base[wslot(i)] -= base[vslot(i)] * coef;
+  return W;
+}
+
+// ---- LoveTrain (d4c.cpp:225-282): ap0 for every voiced frame -----------------------------------
+__global__ void d4c_lt_count_kernel(const double* __restrict__ f0, int n, int fs,
+                                    long long* __restrict__ counts) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  const double v = f0[f];
+  counts[f] = v == 0.0 ? 0 : 2LL * matlab_round(div_rn(mul_rn(1.5, (double)fs), fmax(v, 40.0))) + 1;
+}
+
+__global__ void __launch_bounds__(256)
+d4c_lovetrain_kernel(UttView u, const int* __restrict__ frame_utt, const double* __restrict__ frame_t,
+                     const double* __restrict__ f0_in, const long long* __restrict__ rng_off,
+                     const uint32_t* __restrict__ randn_tab, const double2* __restrict__ tw,
+                     D4CConst c, double* __restrict__ ap0_out) {
+  extern __shared__ double2 smem2[];
+  const int f = blockIdx.x;
+  const double f0 = f0_in[f];
+  if (f0 == 0.0) { if (threadIdx.x == 0) ap0_out[f] = 0.0; return; }
+  const int N = 1 << c.log2lt, M = N >> 1, log2m = c.log2lt - 1;
+  double2* buf = smem2;
+  double* bufd = reinterpret_cast<double*>(buf);
+  // layout: [ buf: 2*cpad_size(M) doubles | window scratch: N + 8 doubles | red: 96 ]
+  const int vbase = 2 * cpad_size(M);
+  double* red = bufd + vbase + N + 8;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int utt = frame_utt[f];
+  const double* __restrict__ x = u.x + u.x_off[utt];
+  const double cur_f0 = fmax(f0, 40.0);
+  auto wslot = [log2m](int i) { return rfft_in_slot(i, log2m); };
+  auto vslot = [vbase](int i) { return vbase + i; };
+  const int W = windowed_waveform(x, u.x_len[utt], c.fs, cur_f0, frame_t[f], kBlackman, 3.0,
+                                  randn_tab + rng_off[f], bufd, wslot, vslot, red);
+  for (int i = W + tid; i < N; i += T) bufd[rfft_in_slot(i, log2m)] = 0.0;
+  fft_dit<false>(buf, log2m, tw);
+  double s[2] = {0.0, 0.0};
+  for (int k = c.lt_b0 + 1 + tid; k <= c.lt_b2; k += T) {
+    const double2 X = rfft_bin(buf, log2m, k, tw);
+    const double p = X.x * X.x + X.y * X.y;
+    if (k <= c.lt_b1) s[0] += p;
+    s[1] += p;
+  }
+  block_sum<2>(s, red);
+  if (tid == 0) ap0_out[f] = s[0] / s[1];
+}
+
+__global__ void d4c_main_count_kernel(const double* __restrict__ f0, const double* __restrict__ ap0,
+                                      int n, int fs, double threshold, long long* __restrict__ counts) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  const double v = f0[f];
+  if (v == 0.0 || ap0[f] <= threshold) { counts[f] = 0; return; }   // d4c.cpp:380
+  counts[f] = 3LL * (2LL * d4c_hwl(4.0, fs, fmax(kFloorF0D4C, v)) + 1);
+}
+
+// Exact sum of everything below the (K)-th largest of the thread-distributed non-negative
+// values v[0..nv) (invalid entries flagged by valid bit mask).  Two independent sets (a, b)
+// are processed together; counts travel packed in one 64-bit word per pass.
+// Result: low[0], low[1] = sum of the (count - K) smallest values; tot[0], tot[1] = sum of all.
+struct SelectScratch { unsigned long long cnt[2][32]; };
+
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* slot) {
+  // slot: 32 entries, alternate between two buffers so one __syncthreads per call suffices
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) slot[wid] = v;
+  __syncthreads();
+  unsigned long long t = lane < nw ? slot[lane] : 0ull;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
+
+__device__ __forceinline__ void select_low_sums(const double (&pa)[kVP], const double (&pb)[kVP],
+                                                unsigned valid, int K, SelectScratch* sc,
+                                                double* red, double (&low)[2], double (&tot)[2]) {
+  unsigned long long pre[2] = {0ull, 0ull};
+  unsigned long long k_rem[2] = {(unsigned long long)K, (unsigned long long)K};
+  bool done[2] = {false, false};
+  int pass = 0;
+  for (int bit = 62; bit >= 0; --bit) {      // bit 63 (sign) is 0 for every power value
+    if (done[0] && done[1]) break;
+    const unsigned long long mask_hi = ~((2ull << bit) - 1ull);   // bits above `bit`
+    const unsigned long long b = 1ull << bit;
+    unsigned int c1[2] = {0u, 0u}, cc[2] = {0u, 0u};
+#pragma unroll
+    for (int j = 0; j < kVP; ++j) {
+      if (!((valid >> j) & 1u)) continue;
+      const unsigned long long ka = (unsigned long long)__double_as_longlong(pa[j]);
+      const unsigned long long kb = (unsigned long long)__double_as_longlong(pb[j]);
+      if ((ka & mask_hi) == pre[0]) { ++cc[0]; if (ka & b) ++c1[0]; }
+      if ((kb & mask_hi) == pre[1]) { ++cc[1]; if (kb & b) ++c1[1]; }
+    }
+    const unsigned long long packed = (unsigned long long)c1[0] | ((unsigned long long)cc[0] << 16) |
+                                      ((unsigned long long)c1[1] << 32) | ((unsigned long long)cc[1] << 48);
+    const unsigned long long t = block_sum_u64(packed, sc->cnt[pass & 1]);
+    ++pass;
+    const unsigned long long n1[2] = {t & 0xffffull, (t >> 32) & 0xffffull};
+    const unsigned long long nc[2] = {(t >> 16) & 0xffffull, (t >> 48) & 0xffffull};
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      if (done[s]) continue;
+      if (nc[s] == k_rem[s]) { done[s] = true; continue; }   // every candidate is in the top set
+      if (n1[s] >= k_rem[s]) pre[s] |= b; else k_rem[s] -= n1[s];
+    }
+  }
+  // keys >= pre[s] form the top set, except (when the loop ran to bit 0 with ties) that only
+  // k_rem[s] copies of the value pre[s] belong to it.
+  double acc[3] = {0.0, 0.0, 0.0};
+  double acc2[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int j = 0; j < kVP; ++j) {
+    if (!((valid >> j) & 1u)) continue;
+    const unsigned long long ka = (unsigned long long)__double_as_longlong(pa[j]);
+    const unsigned long long kb = (unsigned long long)__double_as_longlong(pb[j]);
+    acc[0] += pa[j]; if (ka < pre[0]) acc[1] += pa[j]; if (!done[0] && ka == pre[0]) acc[2] += 1.0;
+    acc2[0] += pb[j]; if (kb < pre[1]) acc2[1] += pb[j]; if (!done[1] && kb == pre[1]) acc2[2] += 1.0;
+  }
+  block_sum<3>(acc, red);
+  block_sum<3>(acc2, red);
+  tot[0] = acc[0]; tot[1] = acc2[0];
+  low[0] = acc[1]; low[1] = acc2[1];
+  if (!done[0]) low[0] += (acc[2] - (double)k_rem[0]) * __longlong_as_double((long long)pre[0]);
+  if (!done[1]) low[1] += (acc2[2] - (double)k_rem[1]) * __longlong_as_double((long long)pre[1]);
+}
+
+// dynamic shared memory: [ cbuf: cpad_size(Nd) double2 | cen: Hd+8 | pw: Hd+8 | red: 96 |
+//                          SelectScratch | coarse: kMaxBands+2 ]
+__global__ void
+d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __restrict__ frame_t,
+                const double* __restrict__ f0_in, const double* __restrict__ ap0,
+                const long long* __restrict__ rng_off, const long long* __restrict__ lt_totals,
+                const uint32_t* __restrict__ randn_tab, const double2* __restrict__ tw,
+                const double* __restrict__ nuttall, D4CConst c, double* __restrict__ ap_out) {
+  extern __shared__ double2 smem2[];
+  const int Nd = 1 << c.log2nd, Hd = Nd >> 1;
+  double2* cbuf = smem2;
+  double* cbufd = reinterpret_cast<double*>(cbuf);
+  double* cen = reinterpret_cast<double*>(cbuf + cpad_size(Nd));
+  double* pw = cen + Hd + 8;
+  double* red = pw + Hd + 8;
+  SelectScratch* sc = reinterpret_cast<SelectScratch*>(red + 96);
+  double* coarse = reinterpret_cast<double*>(sc + 1);
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int f = blockIdx.x;
+  double* __restrict__ out = ap_out + (size_t)f * (c.out_half + 1);
+  const double f0 = f0_in[f];
+  if (f0 == 0.0 || ap0[f] <= c.threshold) {           // d4c.cpp:380 + InitializeAperiodicity
+    for (int k = tid; k <= c.out_half; k += T) out[k] = 1.0 - kMySafeGuardMinimum;
+    return;
+  }
+  const int utt = frame_utt[f];
+  const double* __restrict__ x = u.x + u.x_off[utt];
+  const int x_len = u.x_len[utt];
+  const double t_pos = frame_t[f];
+  const double cur_f0 = fmax(kFloorF0D4C, f0);
+  const uint32_t* __restrict__ rn = randn_tab + lt_totals[utt] + rng_off[f];
+  const int W4 = 2 * d4c_hwl(4.0, c.fs, cur_f0) + 1;
+  if (W4 > Nd || Hd + 2 * smoothing_boundary(cur_f0, c.fs, Nd) + 1 > 2 * cpad_size(Nd)) {
+    for (int k = tid; k <= c.out_half; k += T) out[k] = __longlong_as_double(0x7ff8000000000000LL);
+    return;
+  }
+  const int log2nd = c.log2nd;
+  auto cslot = [log2nd](int i) { return cpad(brev(i, log2nd)); };
+
+  // ---- GetStaticCentroid (:125-142): two centroids, each one packed complex FFT ----------------
+  for (int side = 0; side < 2; ++side) {
+    const double pos = add_rn(t_pos, side == 0 ? -0.25 / cur_f0 : 0.25 / cur_f0);
+    __syncthreads();                                    // previous readers of cbuf are done
+    auto cw = [log2nd](int i) { return 2 * cpad(brev(i, log2nd)); };
+    auto cv = [log2nd](int i) { return 2 * cpad(brev(i, log2nd)) + 1; };
+    const int W = windowed_waveform(x, x_len, c.fs, cur_f0, pos, kBlackman, 4.0,
+                                    rn + (size_t)side * W4, cbufd, cw, cv, red);
+    double pwr[1] = {0.0};
+    for (int i = tid; i < W; i += T) { const double v = cbuf[cslot(i)].x; pwr[0] += v * v; }
+    block_sum<1>(pwr, red);
+    const double sq = sqrt(pwr[0]);
+    for (int i = tid; i < Nd; i += T) {
+      double2 z = make_double2(0.0, 0.0);
+      if (i < W) { const double v = cbuf[cslot(i)].x / sq; z = make_double2(v, v * (i + 1.0)); }
+      cbuf[cslot(i)] = z;
+    }
+    fft_dit<false>(cbuf, log2nd, tw);
+    for (int k = tid; k <= Hd; k += T) {
+      const double2 A = cbuf[cpad(k)];
+      const double2 B = cbuf[cpad((Nd - k) & (Nd - 1))];
+      const double cval = 0.5 * (A.x * B.y + A.y * B.x);
+      cen[k] = side == 0 ? cval : cen[k] + cval;
+    }
+  }
+  __syncthreads();
+  dc_correction(cen, pw, cur_f0, c.fs, Nd);
+
+  // ---- GetSmoothedPowerSpectrum (:148-164) ----------------------------------------------------
+  {
+    const int log2m = log2nd - 1;
+    // real FFT input in the first 2*cpad_size(Hd) doubles of cbuf, window scratch after it
+    // (2*cpad_size(Nd) - 2*cpad_size(Hd) = 1.125 Nd doubles >= W)
+    const int vbase = 2 * cpad_size(Hd);
+    auto pwslot = [log2m](int i) { return rfft_in_slot(i, log2m); };
+    auto pvslot = [vbase](int i) { return vbase + i; };
+    __syncthreads();                                    // centroid readers of cbuf are done
+    const int W = windowed_waveform(x, x_len, c.fs, cur_f0, t_pos, kHanning, 4.0,
+                                    rn + 2 * (size_t)W4, cbufd, pwslot, pvslot, red);
+    for (int i = W + tid; i < Nd; i += T) cbufd[rfft_in_slot(i, log2m)] = 0.0;
+    fft_dit<false>(cbuf, log2m, tw);
+    for (int k = tid; k <= Hd; k += T) {
+      const double2 X = rfft_bin(cbuf, log2m, k, tw);
+      pw[k] = X.x * X.x + X.y * X.y;
+    }
+    __syncthreads();
+    dc_correction(pw, cbufd, cur_f0, c.fs, Nd);
+    linear_smoothing(pw, pw, cbufd, red, cur_f0, c.fs, Nd);
+  }
+  // ---- GetStaticGroupDelay (:170-186) ------------------------------------------------------------
+  for (int k = tid; k <= Hd; k += T) cen[k] = cen[k] / pw[k];
+  __syncthreads();
+  linear_smoothing(cen, cen, cbufd, red, cur_f0 / 2.0, c.fs, Nd);
+  linear_smoothing(cen, pw, cbufd, red, cur_f0, c.fs, Nd);
+  for (int k = tid; k <= Hd; k += T) cen[k] -= pw[k];
+  __syncthreads();
+
+  // ---- GetCoarseAperiodicity (:192-223): two bands per complex FFT -------------------------------
+  const int hw = c.window_length / 2;
+  unsigned valid = 0;
+#pragma unroll
+  for (int j = 0; j < kVP; ++j) if (tid + j * T <= Hd) valid |= 1u << j;
+  for (int b0 = 0; b0 < c.nbands; b0 += 2) {
+    const bool two = b0 + 1 < c.nbands;
+    const int ca = c.centers[b0] - hw, cb = two ? c.centers[b0 + 1] - hw : 0;
+    for (int i = tid; i < Nd; i += T) {
+      double2 z = make_double2(0.0, 0.0);
+      if (i < c.window_length) {
+        const double w = nuttall[i];
+        z.x = cen[ca + i] * w;
+        if (two) z.y = cen[cb + i] * w;
+      }
+      cbuf[cslot(i)] = z;
+    }
+    fft_dit<false>(cbuf, log2nd, tw);
+    double pa[kVP], pb[kVP];
+#pragma unroll
+    for (int j = 0; j < kVP; ++j) {
+      pa[j] = 0.0; pb[j] = 0.0;
+      const int k = tid + j * T;
+      if (k <= Hd) {
+        const double2 A = cbuf[cpad(k)];
+        const double2 B = cbuf[cpad((Nd - k) & (Nd - 1))];
+        const double xr = 0.5 * (A.x + B.x), xi = 0.5 * (A.y - B.y);
+        const double yr = 0.5 * (A.y + B.y), yi = 0.5 * (B.x - A.x);
+        pa[j] = xr * xr + xi * xi;
+        pb[j] = yr * yr + yi * yi;
+      }
+    }
+    double low[2], tot[2];
+    select_low_sums(pa, pb, valid, c.sel_boundary + 1, sc, red, low, tot);
+    if (tid == 0) {
+      coarse[1 + b0] = fmin(0.0, 10.0 * log10(low[0] / tot[0]) + (cur_f0 - 100.0) / 50.0);
+      if (two) coarse[2 + b0] = fmin(0.0, 10.0 * log10(low[1] / tot[1]) + (cur_f0 - 100.0) / 50.0);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) { coarse[0] = -60.0; coarse[c.nbands + 1] = -kMySafeGuardMinimum; }
+  __syncthreads();
+  // ---- GetAperiodicity (:325-333): interp1 over {0, 3k, ..., fs/2} then 10^(dB/20) ---------------
+  const int nk = c.nbands + 2;
+  const int N_out = 2 * c.out_half;
+  for (int k = tid; k <= c.out_half; k += T) {
+    const double xi = mul_rn((double)k, (double)c.fs) / N_out;
+    int seg = 1;                                   // clamp(upper_bound(axis, xi), 1, nk-1)
+    while (seg < nk - 1) {
+      const double knot = seg <= c.nbands ? seg * kFrequencyInterval : c.fs / 2.0;
+      if (xi < knot) break;
+      ++seg;
+    }
+    const double x0 = (seg - 1) * kFrequencyInterval;
+    const double x1 = seg <= c.nbands ? seg * kFrequencyInterval : c.fs / 2.0;
+    const double s = (xi - x0) / (x1 - x0);
+    const double v = add_rn(coarse[seg - 1], mul_rn(s, coarse[seg] - coarse[seg - 1]));
+    out[k] = pow(10.0, v / 20.0);
+  }
+}
+
+}  // namespace
+
+bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
+             const double* frame_t, const double* f0, int fft_size, double threshold,
+             double* ap) {
+  Context* ctxp = ctx();
+  if (!ctxp) return false;
+  if (total_frames <= 0) return true;
+  cudaStream_t st = ctxp->stream;
+  D4CConst c;
+  c.fs = fs;
+  c.threshold = threshold;
+  c.out_half = fft_size / 2;
+  const int nd = static_cast<int>(pow(2.0, 1.0 + static_cast<int>(log(4.0 * fs / kFloorF0D4C + 1) / kLog2)));  // d4c.cpp:344-346
+  const int nlt = static_cast<int>(pow(2.0, 1.0 + static_cast<int>(log(3.0 * fs / 40.0 + 1) / kLog2)));        // :261-262
+  c.log2nd = 0; while ((1 << c.log2nd) < nd) ++c.log2nd;
+  c.log2lt = 0; while ((1 << c.log2lt) < nlt) ++c.log2lt;
+  if (c.log2nd > 13 || c.log2nd < 6) { set_error("D4C: unsupported sampling rate %d", fs); return false; }
+  c.nbands = static_cast<int>(fmin(kUpperLimit, fs / 2.0 - kFrequencyInterval) / kFrequencyInterval);  // :351-353
+  if (c.nbands < 1 || c.nbands > kMaxBands) { set_error("D4C: unsupported number of bands %d (fs %d)", c.nbands, fs); return false; }
+  c.window_length = static_cast<int>(kFrequencyInterval * nd / fs) * 2 + 1;                         // :356-357
+  c.sel_boundary = matlab_round(nd * 8.0 / c.window_length);                                        // :196-197
+  for (int i = 0; i < c.nbands; ++i)
+    c.centers[i] = static_cast<int>(kFrequencyInterval * (i + 1) * nd / fs);                        // :204-205
+  c.lt_b0 = static_cast<int>(ceil(100.0 * nlt / fs));                                               // :267-269
+  c.lt_b1 = static_cast<int>(ceil(4000.0 * nlt / fs));
+  c.lt_b2 = static_cast<int>(ceil(7900.0 * nlt / fs));
+  if (c.lt_b2 > nlt / 2) c.lt_b2 = nlt / 2;      // the reference reads uninitialised memory here (fs < 15.8 kHz)
+  if (c.lt_b1 > c.lt_b2) c.lt_b1 = c.lt_b2;
+
+  std::vector<double> h_win(c.window_length);
+  for (int i = 0; i < c.window_length; ++i) {                                                       // common.cpp:113-121
+    const double tmp = i / (c.window_length - 1.0);
+    h_win[i] = 0.355768 - 0.487396 * cos(2.0 * kPi * tmp) + 0.144232 * cos(4.0 * kPi * tmp) -
+               0.012604 * cos(6.0 * kPi * tmp);
+  }
+  DevBuf<double> d_win, d_ap0;
+  DevBuf<long long> counts, offs_lt, offs_main, tot_lt, tot_main;
+  if (!d_win.alloc(c.window_length) || !d_ap0.alloc(total_frames) || !counts.alloc(total_frames) ||
+      !offs_lt.alloc(total_frames) || !offs_main.alloc(total_frames) || !tot_lt.alloc(u.n_utt) ||
+      !tot_main.alloc(u.n_utt))
+    return false;
+  WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_win.p, h_win.data(), c.window_length * sizeof(double), cudaMemcpyHostToDevice, st), false);
+
+  const int nblk = (total_frames + 255) / 256;
+  std::vector<long long> h_lt(u.n_utt), h_main(u.n_utt);
+  auto need_randn = [&]() {
+    long long mx = 0;
+    for (int i = 0; i < u.n_utt; ++i) mx = std::max(mx, h_lt[i] + h_main[i]);
+    return ensure_randn((size_t)mx);
+  };
+  // LoveTrain
+  d4c_lt_count_kernel<<<nblk, 256, 0, st>>>(f0, total_frames, fs, counts.p);
+  WB_LAUNCH_CHECK();
+  if (!segmented_exclusive_scan(counts.p, u.f_off, u.f_len, u.n_utt, offs_lt.p, tot_lt.p)) return false;
+  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_lt.data(), tot_lt.p, u.n_utt * sizeof(long long), cudaMemcpyDeviceToHost, st), false);
+  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  std::fill(h_main.begin(), h_main.end(), 0);
+  if (!need_randn()) return false;
+  {
+    const int nl = 1 << c.log2lt;
+    const size_t smem = (size_t)(2 * cpad_size(nl / 2) + nl + 8 + 96) * sizeof(double);
+    WB_CUDA_OR_RETURN(cudaFuncSetAttribute(d4c_lovetrain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+    d4c_lovetrain_kernel<<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0, offs_lt.p, ctxp->d_randn, ctxp->d_twiddle, c, d_ap0.p);
+    WB_LAUNCH_CHECK();
+  }
+  // main
+  d4c_main_count_kernel<<<nblk, 256, 0, st>>>(f0, d_ap0.p, total_frames, fs, threshold, counts.p);
+  WB_LAUNCH_CHECK();
+  if (!segmented_exclusive_scan(counts.p, u.f_off, u.f_len, u.n_utt, offs_main.p, tot_main.p)) return false;
+  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_main.data(), tot_main.p, u.n_utt * sizeof(long long), cudaMemcpyDeviceToHost, st), false);
+  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  if (!need_randn()) return false;
+  {
+    const int hd = nd / 2;
+    const size_t smem = cpad_size(nd) * sizeof(double2) + (size_t)(2 * (hd + 8) + 96) * sizeof(double) +
+                        sizeof(SelectScratch) + (kMaxBands + 2) * sizeof(double);
+    const int threads = nd > 4096 ? 512 : 256;
+    if (hd / threads + 1 > kVP) { set_error("D4C: fft size %d too large", nd); return false; }
+    WB_CUDA_OR_RETURN(cudaFuncSetAttribute(d4c_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+    d4c_main_kernel<<<total_frames, threads, smem, st>>>(u, frame_utt, frame_t, f0, d_ap0.p, offs_main.p, tot_lt.p, ctxp->d_randn,
+                                                         ctxp->d_twiddle, d_win.p, c, ap);
+    WB_LAUNCH_CHECK();
+  }
+  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  return true;
+}
+
+}  // namespace wb

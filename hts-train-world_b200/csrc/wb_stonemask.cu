@@ -1,4 +1,152 @@
+// world-b200: StoneMask F0 refinement, one CTA per frame.
+//
+// Reference: W/src/stonemask.cpp — StoneMask :211-217, GetRefinedF0 :184-207, GetMeanF0 :136-178,
+// GetBaseIndex :24-28, GetMainWindow :33-43, GetDiffWindow :49-55, GetSpectra :61-91,
+// FixF0 :96-117, GetTentativeF0 :122-131.
+//
+// The reference plans and runs two real FFTs per voiced frame (x.w and x.w').  Here both are
+// one packed complex FFT z = x.w + i x.w'; with Z[k] = a+ib and Z[N-k] = c+id the two
+// quantities StoneMask needs are
+//     power[k]     = |X_w[k]|^2                     = ((a+c)^2 + (b-d)^2) / 4
+//     numerator[k] = Re X_w Im X_w' - Im X_w Re X_w' = (|Z[N-k]|^2 - |Z[k]|^2) / 4
+// and only the <= 8 harmonic bins that FixF0 reads are ever evaluated.
 #include "wb_batch.h"
+#include "wb_fft.cuh"
+
 namespace wb {
-bool stonemask_run(const UttView& u, int fs, int total_frames, const int* frame_utt, const double* frame_t, const double* f0_in, double* f0_out) { set_error("stonemask: not implemented yet"); return false; }
+namespace {
+
+__device__ __forceinline__ bool stonemask_in_range(double f0, int fs) {
+  return !(f0 <= kFloorF0StoneMask || f0 > fs / 12.0);          // :186-187
 }
+__device__ __forceinline__ int stonemask_hwl(double f0, int fs) {
+  return static_cast<int>(add_rn(div_rn(mul_rn(1.5, (double)fs), f0), 1.0));   // :188
+}
+__device__ __forceinline__ int stonemask_log2fft(int hwl) {
+  return 2 + (31 - __clz(2 * hwl + 1));                          // :192-193 (2*hwl+1 is odd)
+}
+
+__global__ void stonemask_maxfft_kernel(const double* __restrict__ f0, int n, int fs, int* __restrict__ out) {
+  int m = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double v = f0[i];
+    if (stonemask_in_range(v, fs)) m = max(m, stonemask_log2fft(stonemask_hwl(v, fs)));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+struct Bins { double power, numer; };
+
+__device__ __forceinline__ Bins stonemask_bin(const double2* cbuf, int nfft, int k) {
+  k = max(0, min(nfft / 2, k));                    // memory guard (UB in the reference beyond N/2)
+  const double2 A = cbuf[cpad(k)];
+  const double2 B = cbuf[cpad((nfft - k) & (nfft - 1))];
+  Bins r;
+  const double re = 0.5 * (A.x + B.x), im = 0.5 * (A.y - B.y);
+  const double dre = 0.5 * (A.y + B.y), dim = 0.5 * (B.x - A.x);
+  r.power = re * re + im * im;
+  r.numer = re * dim - im * dre;
+  return r;
+}
+
+// FixF0 (:96-117), evaluated by one thread
+__device__ double stonemask_fix_f0(const double2* cbuf, int nfft, int fs, double initial_f0, int nh) {
+  double numerator = 0.0, denominator = 0.0;
+  for (int i = 0; i < nh; ++i) {
+    const int index = matlab_round(mul_rn(div_rn(mul_rn(initial_f0, (double)nfft), (double)fs), (double)(i + 1)));
+    const Bins b = stonemask_bin(cbuf, nfft, index);
+    const double inst = b.power == 0.0 ? 0.0
+        : add_rn(div_rn(mul_rn((double)index, (double)fs), (double)nfft),
+                 div_rn(div_rn(mul_rn(div_rn(b.numer, b.power), (double)fs), 2.0), kPi));
+    const double amp = sqrt(b.power);
+    numerator += amp * inst;
+    denominator += amp * (i + 1);
+  }
+  return numerator / (denominator + kMySafeGuardMinimum);
+}
+
+// dynamic shared memory: [ cbuf: cpad_size(max fft) double2 | win: max_fft/2 + 8 doubles ]
+__global__ void __launch_bounds__(256)
+stonemask_kernel(UttView u, const int* __restrict__ frame_utt, const double* __restrict__ frame_t,
+                 const double* __restrict__ f0_in, const double2* __restrict__ tw, int fs,
+                 int max_log2fft, double* __restrict__ f0_out) {
+  extern __shared__ double2 smem2[];
+  const int f = blockIdx.x;
+  const double f0 = f0_in[f];
+  if (!stonemask_in_range(f0, fs)) { if (threadIdx.x == 0) f0_out[f] = 0.0; return; }
+  double2* cbuf = smem2;
+  double* win = reinterpret_cast<double*>(cbuf + cpad_size(1 << max_log2fft));
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int utt = frame_utt[f];
+  const double* __restrict__ x = u.x + u.x_off[utt];
+  const int x_len = u.x_len[utt];
+  const double t_pos = frame_t[f];
+  const int hwl = stonemask_hwl(f0, fs);
+  const int W = 2 * hwl + 1;
+  const int log2fft = stonemask_log2fft(hwl);
+  const int nfft = 1 << log2fft;
+  const double wlen = div_rn(add_rn(mul_rn(2.0, (double)hwl), 1.0), (double)fs);   // :189
+  // GetBaseIndex + GetMainWindow
+  for (int i = tid; i < W; i += T) {
+    const double base_time = div_rn((double)(i - hwl), (double)fs);
+    const int index_raw = matlab_round(mul_rn(add_rn(t_pos, base_time), (double)fs));
+    const double tmp = add_rn(div_rn(index_raw - 1.0, (double)fs), -t_pos);
+    win[i] = 0.42 + 0.5 * cos(div_rn(mul_rn(2.0 * kPi, tmp), wlen)) +
+             0.08 * cos(div_rn(mul_rn(4.0 * kPi, tmp), wlen));
+  }
+  __syncthreads();
+  // GetDiffWindow + GetSpectra, packed
+  for (int i = tid; i < nfft; i += T) {
+    double2 z = make_double2(0.0, 0.0);
+    if (i < W) {
+      const double base_time = div_rn((double)(i - hwl), (double)fs);
+      const int index_raw = matlab_round(mul_rn(add_rn(t_pos, base_time), (double)fs));
+      const int idx = max(0, min(x_len - 1, index_raw - 1));
+      const double xv = x[idx];
+      double dw;
+      if (i == 0) dw = -win[1] / 2.0;
+      else if (i == W - 1) dw = win[W - 2] / 2.0;
+      else dw = -(win[i + 1] - win[i - 1]) / 2.0;
+      z = make_double2(xv * win[i], xv * dw);
+    }
+    cbuf[cpad(brev(i, log2fft))] = z;
+  }
+  fft_dit<false>(cbuf, log2fft, tw);
+  if (tid == 0) {
+    // GetTentativeF0 (:122-131) and the 20 % sanity check of GetRefinedF0 (:203-204)
+    double mean_f0 = 0.0;
+    const double tentative = stonemask_fix_f0(cbuf, nfft, fs, f0, 2);
+    if (!(tentative <= 0.0 || tentative > f0 * 2)) mean_f0 = stonemask_fix_f0(cbuf, nfft, fs, tentative, 6);
+    if (fabs(mean_f0 - f0) / f0 > 0.2) mean_f0 = f0;
+    f0_out[f] = mean_f0;
+  }
+}
+
+}  // namespace
+
+bool stonemask_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
+                   const double* frame_t, const double* f0_in, double* f0_out) {
+  Context* c = ctx();
+  if (!c) return false;
+  if (total_frames <= 0) return true;
+  cudaStream_t st = c->stream;
+  DevBuf<int> d_max;
+  if (!d_max.alloc(1)) return false;
+  WB_CUDA_OR_RETURN(cudaMemsetAsync(d_max.p, 0, sizeof(int), st), false);
+  stonemask_maxfft_kernel<<<std::min(1024, (total_frames + 255) / 256), 256, 0, st>>>(f0_in, total_frames, fs, d_max.p);
+  WB_LAUNCH_CHECK();
+  int h_max = 0;
+  WB_CUDA_OR_RETURN(cudaMemcpyAsync(&h_max, d_max.p, sizeof(int), cudaMemcpyDeviceToHost, st), false);
+  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  if (h_max < 3) h_max = 3;
+  if (h_max > 13) { set_error("StoneMask: FFT size 2^%d not supported", h_max); return false; }
+  const size_t smem = cpad_size(1 << h_max) * sizeof(double2) + ((size_t)(1 << h_max) / 2 + 8) * sizeof(double);
+  if (smem > c->smem_optin) { set_error("StoneMask: needs %zu bytes of shared memory", smem); return false; }
+  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(stonemask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+  stonemask_kernel<<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0_in, c->d_twiddle, fs, h_max, f0_out);
+  WB_LAUNCH_CHECK();
+  return true;
+}
+
+}  // namespace wb
