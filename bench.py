@@ -1,0 +1,472 @@
+#!/usr/bin/env python
+"""bench.py — xRT (audio seconds per second) of WORLD analysis + synthesis at 48 kHz / 5 ms.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--utts U]
+
+Workload (BASELINE.json configs[1]): a 1 132-utterance ARCTIC-sized synthetic
+48 kHz corpus (hts-train-world_b200/signals.py, seeds = utterance ids), fft_size 2048.  One
+"step" = Dio -> StoneMask -> CheapTrick -> D4C -> Synthesis over the whole corpus shard of this
+rank, plus the lf0 statistics partials; with N > 1 every rank owns its own 1 132 utterances
+(weak scaling, utterance-sharded, no collective on the hot path) and one all-reduce of the
+three lf0 statistics closes the step.
+
+  value  whole-job xRT with the int16 PCM already resident in HBM (device-timed, max over ranks)
+  e2e    the same through the public batch API from pinned HOST memory: H2D of the PCM, all five
+         stages, D2H of the resynthesised 16-bit waveform and of the F0 contour, every step
+  roofline      the dominant kernel, timed live with CUDA events on the library stream
+  cpu_baseline  the compiled reference (oracle/_ref) on this box's host cores, bounded sample
+
+--impl reference times the unmodified reference WORLD_v2 (oracle/_ref, built from
+/root/reference by oracle/Makefile) on all host cores, one process per core.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FS = 48000
+FRAME_PERIOD = 5.0
+METRIC = "xRT (audio s/s) WORLD analysis+synthesis, 48 kHz 5 ms"
+UNIT = "audio_s/s"
+
+
+# =================================================================================================
+# reference arm / cpu baseline: the compiled reference, one process per host core
+# =================================================================================================
+def _worker_main(conn, opt):
+    """Worker process: owns one copy of the reference library (its RNG is a global, so threads
+    are not an option: SURVEY.md 5) and a private cache of generated utterances."""
+    import torch
+    torch.set_num_threads(1)
+    from hts_train_world_b200 import signals
+    from oracle import ref
+    R = ref.load(opt=opt)
+    cache = {}
+    while True:
+        cmd, utts = conn.recv()
+        if cmd == "quit":
+            return
+        if cmd == "prep":
+            for u in utts:
+                if u not in cache:
+                    cache[u] = signals.pcm_to_double(signals.make_utterance(u, FS)[0])
+            conn.send(len(cache))
+            continue
+        # "run": Dio -> StoneMask -> CheapTrick -> D4C -> Synthesis with the analysis tool's options
+        # (W/test/analysis.cpp:93-203, W/test/synth.cpp:259); per-stage seconds are returned
+        acc = np.zeros(5)
+        for u in utts:
+            x = cache[u]
+            t = [time.perf_counter()]
+            tp, f0r = R.dio(x, FS, frame_period=FRAME_PERIOD); t.append(time.perf_counter())
+            f0 = R.stonemask(x, FS, tp, f0r); t.append(time.perf_counter())
+            sp = R.cheaptrick(x, FS, tp, f0); t.append(time.perf_counter())
+            n = sp.shape[1] * 2 - 2
+            ap = R.d4c(x, FS, tp, f0, n, threshold=0.0); t.append(time.perf_counter())
+            R.synthesis(f0, sp, ap, n, FRAME_PERIOD, FS); t.append(time.perf_counter())
+            acc += np.diff(t)
+        conn.send(acc)
+
+
+class ReferencePool:
+    """`cores` processes; utterances are dealt round-robin."""
+
+    def __init__(self, cores, opt=True):
+        import multiprocessing as mp
+        ctx = mp.get_context("fork")
+        self.cores = cores
+        self.conns, self.procs = [], []
+        for _ in range(cores):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_worker_main, args=(b, opt), daemon=True)
+            p.start()
+            self.conns.append(a)
+            self.procs.append(p)
+
+    def _all(self, cmd, utts):
+        for i, cn in enumerate(self.conns):
+            cn.send((cmd, utts[i::self.cores]))
+        return [cn.recv() for cn in self.conns]
+
+    def prepare(self, utts):
+        self._all("prep", utts)
+
+    def run(self, utts):
+        t0 = time.perf_counter()
+        stages = self._all("run", utts)
+        dt = time.perf_counter() - t0
+        return dt, np.sum(np.asarray(stages), axis=0)
+
+    def close(self):
+        for cn in self.conns:
+            cn.send(("quit", None))
+        for p in self.procs:
+            p.join(timeout=10)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_sample_utts(cores, per_core):
+    return list(range(cores * per_core))
+
+
+def run_reference_pass(pool, utts, passes):
+    """-> (audio seconds per pass, [seconds per pass], per-stage cpu seconds summed)."""
+    from hts_train_world_b200 import signals
+    audio = sum(signals.utterance_params(u)["T"] for u in utts)
+    pool.prepare(utts)          # synthetic signals are generated untimed, inside each worker
+    times, stages = [], np.zeros(5)
+    for _ in range(passes):
+        dt, st = pool.run(utts)
+        times.append(dt)
+        stages += st
+    return audio, times, stages
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import ref
+    opt = True
+    if not os.path.exists(ref.ref_path(opt)):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libworld_ref_O3.so was not built "
+                          "(needs /root/reference at build time)"}))
+        return 0
+    cores = host_cores()
+    utts = reference_sample_utts(cores, 2)
+    pool = ReferencePool(cores, opt)
+    audio, times, stages = run_reference_pass(pool, utts, args.warmup + args.steps)
+    pool.close()
+    timed = times[args.warmup:]
+    total = float(sum(timed))
+    value = audio * len(timed) / total
+    sample = ("%d utterances (ids 0..%d, %.1f s of 48 kHz audio) per step, one process per core; reference "
+              "WORLD_v2 sources compiled -O3 (no -ffast-math)" % (len(utts), len(utts) - 1, audio))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(timed),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "1132-utterance synthetic 48 kHz corpus, 5 ms frames, fft_size 2048: "
+                               "Dio+StoneMask+CheapTrick+D4C+Synthesis (bounded sample per step)",
+                   "fs": FS, "frame_period_ms": FRAME_PERIOD, "utterances_per_step": len(utts)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "stage_cpu_seconds": dict(zip(["dio", "stonemask", "cheaptrick", "d4c", "synthesis"],
+                                      [float(s) for s in stages])),
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# =================================================================================================
+# our arm
+# =================================================================================================
+class ClockSampler:
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, ln in self.rows:
+            if ts < t0 or ts > t1 + 0.1:
+                continue
+            f = [v.strip() for v in ln.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_shard(args, rank, world):
+    """Utterance ids of this rank.  Weak scaling: the job is world * utts utterances, dealt
+    longest-first to the ranks (hts-train-world_b200/corpus.py)."""
+    from hts_train_world_b200 import corpus, signals
+    n_total = args.utts * world
+    lengths = [int(round(signals.utterance_params(u)["T"] * FS)) for u in range(n_total)]
+    ids = corpus.shard_utterances(lengths, rank, world)
+    return ids, [lengths[i] for i in ids]
+
+
+def ours_arm(args):
+    import torch
+    import torch.distributed as dist
+    import hts_train_world_b200 as wb
+    from hts_train_world_b200 import corpus, roofline, signals
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU reference)")
+    cpu_pool = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import ref
+        if os.path.exists(ref.ref_path(True)):
+            cpu_pool = ReferencePool(host_cores(), True)    # forked before CUDA is initialised; idle until the end
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wb.init(local)
+    stream = torch.cuda.Stream()
+    wb.set_stream(stream.cuda_stream)
+
+    # ---- synthetic corpus shard: generated on the GPU, then parked in pinned host memory ---------
+    ids, lengths = build_shard(args, rank, world)
+    t_gen = time.perf_counter()
+    pcm_dev = torch.empty(sum(lengths), dtype=torch.int16, device="cuda")
+    o = 0
+    for u, n in zip(ids, lengths):
+        p = signals.make_utterance(int(u), FS, device="cuda")[0]
+        assert p.numel() == n
+        pcm_dev[o:o + n] = p
+        o += n
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen
+    pcm_host = torch.empty_like(pcm_dev, device="cpu").pin_memory()
+    pcm_host.copy_(pcm_dev)
+    audio_s = sum(lengths) / float(FS)
+
+    c = wb.Corpus(FS, lengths, FRAME_PERIOD)
+    y_host = None
+    f0_host = torch.empty(c.total_frames, dtype=torch.float64).pin_memory()
+
+    def reduce_stats(st):
+        if world > 1:
+            t = torch.as_tensor(st, dtype=torch.float64, device="cuda")
+            dist.all_reduce(t)
+            return t.cpu().numpy()
+        return st
+
+    def step_resident():
+        c.set_pcm16_device(pcm_dev)
+        c.analyze()
+        c.synthesis()
+        return reduce_stats(c.lf0_stats())
+
+    def step_e2e():
+        nonlocal y_host
+        c.upload_pcm16(pcm_host)
+        c.analyze()
+        c.synthesis()
+        if y_host is None:
+            y_host = torch.empty(int(wb.lib().wb200_batch_total_y(c._h)), dtype=torch.int16).pin_memory()
+        c.y_pcm16(y_host)
+        wb._check(wb.lib().wb200_batch_get_f0(c._h, wb.C.cast(f0_host.data_ptr(), wb._dp), 1), "get_f0")
+        return reduce_stats(c.lf0_stats())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            out = fn()
+        e1.record(stream)
+        barrier()
+        t1 = time.perf_counter()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms, (t1 - t0) * 1e3], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1])
+        else:
+            wall = (t1 - t0) * 1e3
+        return ms, wall, out, (t0, t1)
+
+    for _ in range(args.warmup):
+        step_resident()
+    wb.kernel_timing(True)
+    wb.kernel_times_reset()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    n0 = wb.launch_count()
+    ms, wall, stats, (t0, t1) = timed(step_resident, args.steps)
+    launches = wb.launch_count() - n0
+    kernel_ms = {k: wb.kernel_time(k) for k in
+                 ["d4c_main_kernel", "d4c_lovetrain_kernel", "cheaptrick_kernel", "synth_pulse_kernel",
+                  "synth_timebase_kernel", "stonemask_kernel", "dio_filter_kernel", "dio_zc_kernel",
+                  "dio_candidates_kernel", "dio_fix_kernel"]}
+    wb.kernel_timing(False)
+    stage_ms = wb.stage_times()
+    clk = clocks.stop(t0, t1) if rank == 0 else None
+    value = audio_s * world * args.steps / (ms * 1e-3)
+
+    # ---- end to end from host memory --------------------------------------------------------------
+    step_e2e()
+    ms_e, wall_e, _, _ = timed(step_e2e, args.steps)
+    e2e_value = audio_s * world * args.steps / (max(ms_e, wall_e) * 1e-3)
+    h2d = pcm_host.numel() * 2
+    d2h = y_host.numel() * 2 + f0_host.numel() * 8 + 24
+
+    # ---- roofline of the dominant kernel --------------------------------------------------------------
+    f0 = f0_host.numpy().copy()
+    voiced = f0 > 0
+    pv = float((f0[voiced] * FRAME_PERIOD / 1000.0).sum())
+    pu = float((~voiced).sum() * 500.0 * FRAME_PERIOD / 1000.0)
+    counts = roofline.stage_counts(FS, f0, sum(lengths), pv, pu, fft_size=c.fft_size, n_utt=len(lengths))
+    fp64_peak = wb.fma_peak_tflops(True)
+    fp32_peak = wb.fma_peak_tflops(False)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    kmap = {"d4c_main_kernel": "d4c_main", "d4c_lovetrain_kernel": "d4c_lovetrain",
+            "cheaptrick_kernel": "cheaptrick", "synth_pulse_kernel": "synthesis",
+            "stonemask_kernel": "stonemask", "dio_filter_kernel": "dio"}
+    kernels = {}
+    for k, (tot_ms, n) in kernel_ms.items():
+        if n == 0:
+            continue
+        ent = {"ms_per_launch": tot_ms / n, "launches_per_step": n / args.steps}
+        if k in kmap:
+            cnt = counts[kmap[k]]
+            per_launch_s = tot_ms * 1e-3 / args.steps      # all launches of this kernel in one step
+            ent["tflops"] = cnt["flops"] / per_launch_s / 1e12
+            ent["gbs"] = cnt["bytes"] / per_launch_s / 1e9
+            ent["frac_fp64"] = ent["tflops"] / fp64_peak if fp64_peak else None
+            ent["frac_hbm"] = ent["gbs"] / hbm_peak
+        kernels[k] = ent
+    dom = max((k for k in kernels if k in kmap), key=lambda k: kernel_ms[k][0])
+    dcnt = counts[kmap[dom]]
+    dsec = kernel_ms[dom][0] * 1e-3 / args.steps
+    t_flop, t_byte = dcnt["flops"] / (fp64_peak * 1e12), dcnt["bytes"] / (hbm_peak * 1e9)
+    if t_flop >= t_byte:
+        roof = {"bound": "fp64", "achieved": dcnt["flops"] / dsec / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                "peak_source": "measured live: FP64 FMA micro-benchmark on this GPU (nominal 37.2)"}
+    else:
+        roof = {"bound": "hbm", "achieved": dcnt["bytes"] / dsec / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}
+    roof.update({"frac": roof["achieved"] / roof["peak"], "traffic": None, "kernel": dom,
+                 "algorithmic_flops_per_launch": dcnt["flops"], "algorithmic_bytes_per_launch": dcnt["bytes"],
+                 "units_per_launch": dcnt["units"], "ms_per_launch": dsec * 1e3,
+                 "share_of_step": kernel_ms[dom][0] / ms,
+                 "note": "every stage of this path is bound by the CUDA-core FP64 pipe, not HBM or tensor "
+                         "cores (SURVEY.md 8d); hbm fraction of the same kernel: %.4f" %
+                         (dcnt["bytes"] / dsec / 1e9 / hbm_peak)})
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            roof["traffic"] = json.load(open(tp)).get(dom)
+        except Exception:
+            pass
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%d-utterance synthetic 48 kHz corpus per GPU (%.0f s audio, %d frames), 5 ms "
+                               "frames, fft_size %d: Dio+StoneMask+CheapTrick+D4C+Synthesis + lf0 statistics"
+                               % (len(lengths), audio_s, c.total_frames, c.fft_size),
+                   "fs": FS, "frame_period_ms": FRAME_PERIOD, "utterances_per_gpu": len(lengths),
+                   "parallelism": "utterance-sharded x%d, no hot-path collective" % world,
+                   "l2": "inputs larger than L2 (%.0f MB PCM, GBs of intermediates per step)" % (h2d / 1e6)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": max(ms_e, wall_e) / args.steps,
+                "result": "16-bit resynthesised waveform + f0 contour + lf0 statistics; sp/ap stay in HBM"},
+        "gpu_launches": int(launches),
+        "wall_ms_per_step": wall / args.steps,
+        "stage_ms": stage_ms,
+        "roofline": roof,
+        "kernels": kernels,
+        "peaks": {"fp64_tflops_measured": fp64_peak, "fp32_tflops_measured": fp32_peak, "hbm_gbs": hbm_peak},
+        "clocks": clk,
+        "lf0_stats": corpus.merge_stats([stats]),
+        "gen_seconds": t_gen,
+    }
+
+    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if cpu_pool is not None:
+            cores = cpu_pool.cores
+            utts = reference_sample_utts(cores, 2)
+            audio, times, stages = run_reference_pass(cpu_pool, utts, 1)
+            cpu_pool.close()
+            line["cpu_baseline"] = {
+                "value": audio / times[0], "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": "%d utterances (ids 0..%d, %.1f s audio), one pass, one process per core, reference "
+                          "sources compiled -O3" % (len(utts), len(utts) - 1, audio),
+                "stage_cpu_seconds": dict(zip(["dio", "stonemask", "cheaptrick", "d4c", "synthesis"],
+                                              [float(s) for s in stages]))}
+        else:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                                    "sample": "oracle/_ref not built"}
+    if rank == 0:
+        print(json.dumps(line))
+    c.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--utts", type=int, default=1132, help="utterances per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return ours_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -90,6 +90,11 @@ def lib():
         "wb200_launch_count": (C.c_ulonglong, []),
         "wb200_stage_times": (None, [C.POINTER(C.c_float)]),
         "wb200_randn_stream": (i32, [_dp, i64]),
+        "wb200_set_stream": (i32, [vp]),
+        "wb200_kernel_timing": (None, [i32]),
+        "wb200_kernel_times_reset": (None, []),
+        "wb200_kernel_time": (i32, [C.c_char_p, _dp, C.POINTER(i64)]),
+        "wb200_measure_fma_peak": (f64, [i32]),
         "wb200_batch_create": (vp, [i32, f64, i32, _ip]),
         "wb200_batch_destroy": (None, [vp]),
         "wb200_batch_total_frames": (i32, [vp]),
@@ -148,6 +153,34 @@ def stage_times():
     out = (C.c_float * 6)()
     lib().wb200_stage_times(out)
     return dict(zip(["dio", "stonemask", "cheaptrick", "d4c", "synthesis", "harvest"], list(out)))
+
+
+def set_stream(cuda_stream):
+    """cuda_stream: a cudaStream_t as an integer (e.g. torch.cuda.Stream().cuda_stream)."""
+    _check(lib().wb200_set_stream(C.c_void_p(int(cuda_stream))), "wb200_set_stream")
+
+
+def kernel_timing(on=True):
+    lib().wb200_kernel_timing(int(bool(on)))
+
+
+def kernel_times_reset():
+    lib().wb200_kernel_times_reset()
+
+
+def kernel_time(name):
+    """-> (total ms, launches) of the named kernel since the last reset."""
+    ms, n = C.c_double(0.0), C.c_longlong(0)
+    lib().wb200_kernel_time(name.encode(), C.byref(ms), C.byref(n))
+    return ms.value, n.value
+
+
+def fma_peak_tflops(fp64=True):
+    return float(lib().wb200_measure_fma_peak(int(bool(fp64))))
+
+
+def sync():
+    _check(lib().wb200_sync(), "wb200_sync")
 
 
 def randn_stream(n):

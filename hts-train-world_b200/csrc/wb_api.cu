@@ -269,6 +269,17 @@ void wb200_stage_times(float* o) {
   o[0] = g_times.dio; o[1] = g_times.stonemask; o[2] = g_times.cheaptrick;
   o[3] = g_times.d4c; o[4] = g_times.synthesis; o[5] = g_times.harvest;
 }
+int wb200_set_stream(void* stream) {
+  if (!ctx()) return 1;
+  set_stream(reinterpret_cast<cudaStream_t>(stream));
+  return 0;
+}
+void wb200_kernel_timing(int on) { kernel_timing_enable(on != 0); }
+void wb200_kernel_times_reset(void) { kernel_times_reset(); }
+int wb200_kernel_time(const char* name, double* ms_total, long long* launches) {
+  return kernel_time_query(name, ms_total, launches) ? 0 : 1;
+}
+double wb200_measure_fma_peak(int fp64) { return measure_fma_peak(fp64 != 0); }
 int wb200_sync(void) {
   Context* c = ctx();
   if (!c) return 1;

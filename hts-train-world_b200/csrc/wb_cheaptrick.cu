@@ -192,8 +192,9 @@ bool cheaptrick_run(const UttView& u, int fs, int total_frames, const int* frame
   if (!ensure_randn((size_t)mx)) return false;
   const size_t smem = cpad_size(fft_size / 2) * sizeof(double2) + (fft_size + 16 + 96) * sizeof(double);
   WB_CUDA_OR_RETURN(cudaFuncSetAttribute(cheaptrick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+  KernelTimer kt1("cheaptrick_kernel");
   cheaptrick_kernel<<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0, offs.p, c->d_randn, c->d_twiddle, fs, log2n, q1, f0_floor, sp);
-  WB_LAUNCH_CHECK();
+  WB_LAUNCH_CHECK(); kt1.stop();
   // counts/offs are freed when this returns: make sure the kernel is done with them
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
   return true;

@@ -56,6 +56,21 @@ struct Context {
 Context* ctx();                           // lazily initialised; nullptr on failure
 bool ensure_randn(size_t count);          // grow the randn table to >= count variates
 
+// Optional per-kernel device timing (CUDA events on the library stream around one launch).
+// Off by default; bench.py switches it on to measure the dominant kernel live.
+struct KernelTimer {
+  explicit KernelTimer(const char* name);
+  ~KernelTimer() { stop(); }
+  void stop();
+  const char* name_;
+  cudaEvent_t e0_ = nullptr, e1_ = nullptr;
+};
+double measure_fma_peak(bool fp64);       // TFLOP/s of the CUDA-core FMA pipe, measured
+void set_stream(cudaStream_t s);          // run everything on a caller-owned stream
+void kernel_timing_enable(bool on);
+bool kernel_time_query(const char* name, double* ms_total, long long* launches);
+void kernel_times_reset();
+
 // simple stream-ordered device buffer
 template <typename T>
 struct DevBuf {

@@ -2,8 +2,11 @@
 #include <math.h>
 #include <stdarg.h>
 #include <string.h>
+#include <algorithm>
+#include <map>
 #include <mutex>
 #include <string>
+#include <vector>
 #include "wb_batch.h"
 
 namespace wb {
@@ -108,9 +111,113 @@ __global__ void randn_table_kernel(const XState* __restrict__ starts, uint32_t* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// per-kernel timing: events are queued at launch and resolved when queried
+// ---------------------------------------------------------------------------------------------
+struct PendingTime { std::string name; cudaEvent_t e0, e1; };
+struct TimeAcc { double ms = 0.0; long long n = 0; };
+static std::mutex g_kt_mutex;
+static bool g_kt_on = false;
+static std::vector<PendingTime> g_kt_pending;
+static std::map<std::string, TimeAcc> g_kt_acc;
+
+void kernel_timing_enable(bool on) { std::lock_guard<std::mutex> l(g_kt_mutex); g_kt_on = on; }
+KernelTimer::KernelTimer(const char* name) : name_(name) {
+  if (!g_kt_on) return;
+  Context* c = ctx();
+  if (!c) return;
+  if (cudaEventCreate(&e0_) != cudaSuccess || cudaEventCreate(&e1_) != cudaSuccess) { e0_ = e1_ = nullptr; return; }
+  cudaEventRecord(e0_, c->stream);
+}
+void KernelTimer::stop() {
+  if (!e0_ || !e1_) return;
+  cudaEventRecord(e1_, ctx()->stream);
+  std::lock_guard<std::mutex> l(g_kt_mutex);
+  g_kt_pending.push_back(PendingTime{name_, e0_, e1_});
+  e0_ = e1_ = nullptr;
+}
+static void kernel_times_resolve() {
+  for (auto& p : g_kt_pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(p.e1) == cudaSuccess && cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+      TimeAcc& a = g_kt_acc[p.name];
+      a.ms += ms; a.n += 1;
+    }
+    cudaEventDestroy(p.e0); cudaEventDestroy(p.e1);
+  }
+  g_kt_pending.clear();
+}
+bool kernel_time_query(const char* name, double* ms_total, long long* launches) {
+  std::lock_guard<std::mutex> l(g_kt_mutex);
+  kernel_times_resolve();
+  auto it = g_kt_acc.find(name);
+  if (it == g_kt_acc.end()) { *ms_total = 0.0; *launches = 0; return false; }
+  *ms_total = it->second.ms; *launches = it->second.n;
+  return true;
+}
+void kernel_times_reset() {
+  std::lock_guard<std::mutex> l(g_kt_mutex);
+  kernel_times_resolve();
+  g_kt_acc.clear();
+}
+
+// ---------------------------------------------------------------------------------------------
+// CUDA-core peak micro-benchmark: dependent-free FMA chains, 8
+// accumulators per thread, 8 CTAs of 256 threads per SM.  Returns TFLOP/s (2 flops per FMA).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T b) {
+  T v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = static_cast<T>(threadIdx.x + j);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = v[j] * a + b;
+  }
+  T s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += v[j];
+  if (s == static_cast<T>(-1.2345)) out[0] = s;     // never true; keeps the chain alive
+}
+
+template <typename T>
+static double fma_peak(Context* c) {
+  T* d = nullptr;
+  if (cudaMalloc((void**)&d, sizeof(T)) != cudaSuccess) return 0.0;
+  const int blocks = c->sm_count * 8, iters = 1 << 14;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, c->stream);
+    fma_peak_kernel<T><<<blocks, 256, 0, c->stream>>>(d, iters, static_cast<T>(0.999999), static_cast<T>(1e-7));
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 32.0 * (double)iters * 256.0 * blocks;
+    if (rep > 0 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  return best;
+}
+double measure_fma_peak(bool fp64) {
+  Context* c = ctx();
+  if (!c) return 0.0;
+  return fp64 ? fma_peak<double>(c) : fma_peak<float>(c);
+}
+
 static std::mutex g_ctx_mutex;
 static Context g_ctx;
 static bool g_ctx_ok = false, g_ctx_failed = false;
+
+void set_stream(cudaStream_t s) {
+  Context* c = ctx();
+  if (c) { cudaStreamSynchronize(c->stream); c->stream = s; }
+}
 
 Context* ctx() {
   std::lock_guard<std::mutex> lock(g_ctx_mutex);

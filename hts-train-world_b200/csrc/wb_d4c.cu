@@ -416,8 +416,9 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
     const int nl = 1 << c.log2lt;
     const size_t smem = (size_t)(2 * cpad_size(nl / 2) + nl + 8 + 96) * sizeof(double);
     WB_CUDA_OR_RETURN(cudaFuncSetAttribute(d4c_lovetrain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+    KernelTimer kt1("d4c_lovetrain_kernel");
     d4c_lovetrain_kernel<<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0, offs_lt.p, ctxp->d_randn, ctxp->d_twiddle, c, d_ap0.p);
-    WB_LAUNCH_CHECK();
+    WB_LAUNCH_CHECK(); kt1.stop();
   }
   // main
   d4c_main_count_kernel<<<nblk, 256, 0, st>>>(f0, d_ap0.p, total_frames, fs, threshold, counts.p);
@@ -433,9 +434,10 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
     const int threads = nd > 4096 ? 512 : 256;
     if (hd / threads + 1 > kVP) { set_error("D4C: fft size %d too large", nd); return false; }
     WB_CUDA_OR_RETURN(cudaFuncSetAttribute(d4c_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+    KernelTimer kt2("d4c_main_kernel");
     d4c_main_kernel<<<total_frames, threads, smem, st>>>(u, frame_utt, frame_t, f0, d_ap0.p, offs_main.p, tot_lt.p, ctxp->d_randn,
                                                          ctxp->d_twiddle, d_win.p, c, ap);
-    WB_LAUNCH_CHECK();
+    WB_LAUNCH_CHECK(); kt2.stop();
   }
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
   return true;

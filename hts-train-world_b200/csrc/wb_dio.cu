@@ -520,11 +520,13 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
         !d_ltot.alloc(n_lists) || !d_loff.alloc(n_lists))
       return false;
     WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_foff.p, h_foff.data(), nu * sizeof(long long), cudaMemcpyHostToDevice, st), false);
+    KernelTimer kt1("dio_filter_kernel");
     dio_filter_kernel<<<dim3(n_blocks, nu), 256, smem, st>>>(b->x.p, b->x_off.p, b->x_len.p, d_ylen.p, d_mask.p, d_mean.p,
                                                             d_foff.p, fb->G.p, ctxp->d_twiddle, c, u0, d_F.p);
-    WB_LAUNCH_CHECK();
+    WB_LAUNCH_CHECK(); kt1.stop();
+    KernelTimer kt2("dio_zc_kernel");
     dio_zc_kernel<false><<<dim3(n_chunks, nu * c.nb), 256, 0, st>>>(d_F.p, d_foff.p, d_ylen.p, c.nb, u0, n_chunks, d_counts.p, nullptr, nullptr);
-    WB_LAUNCH_CHECK();
+    WB_LAUNCH_CHECK(); kt2.stop();
     dio_zc_scan_kernel<<<(n_lists + 127) / 128, 128, 0, st>>>(d_counts.p, n_lists, n_chunks, d_ltot.p);
     WB_LAUNCH_CHECK();
     std::vector<int> h_ltot(n_lists);
@@ -535,17 +537,20 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
     for (int l = 0; l < n_lists; ++l) { h_loff[l] = etot; etot += h_ltot[l]; }
     if (!d_edges.alloc((size_t)etot + 2)) return false;
     WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_loff.p, h_loff.data(), n_lists * sizeof(long long), cudaMemcpyHostToDevice, st), false);
+    KernelTimer kt3("dio_zc_kernel");
     dio_zc_kernel<true><<<dim3(n_chunks, nu * c.nb), 256, 0, st>>>(d_F.p, d_foff.p, d_ylen.p, c.nb, u0, n_chunks, d_counts.p, d_loff.p, d_edges.p);
-    WB_LAUNCH_CHECK();
+    WB_LAUNCH_CHECK(); kt3.stop();
     int max_f = 0;
     for (int u = u0; u < u1; ++u) max_f = std::max(max_f, b->h_f_len[u]);
     if (max_f > 0) {
+      KernelTimer kt4("dio_candidates_kernel");
       dio_candidates_kernel<<<dim3((max_f + 127) / 128, nu * c.nb), 128, 0, st>>>(d_edges.p, d_loff.p, d_ltot.p, b->f_off.p, b->f_len.p,
                                                                                b->frame_t.p, c, u0, TF, d_cand.p, d_score.p);
-      WB_LAUNCH_CHECK();
+      WB_LAUNCH_CHECK(); kt4.stop();
     }
+    KernelTimer kt5("dio_fix_kernel");
     dio_fix_kernel<<<nu, 256, 0, st>>>(d_cand.p, d_score.p, b->f_off.p, b->f_len.p, c, u0, TF, d_tmp1.p, d_tmp2.p, d_pos.p, d_neg.p, d_f0_out);
-    WB_LAUNCH_CHECK();
+    WB_LAUNCH_CHECK(); kt5.stop();
     WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);      // scratch buffers die with this scope
     u0 = u1;
   }

@@ -144,8 +144,9 @@ bool stonemask_run(const UttView& u, int fs, int total_frames, const int* frame_
   const size_t smem = cpad_size(1 << h_max) * sizeof(double2) + ((size_t)(1 << h_max) / 2 + 8) * sizeof(double);
   if (smem > c->smem_optin) { set_error("StoneMask: needs %zu bytes of shared memory", smem); return false; }
   WB_CUDA_OR_RETURN(cudaFuncSetAttribute(stonemask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+  KernelTimer kt1("stonemask_kernel");
   stonemask_kernel<<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0_in, c->d_twiddle, fs, h_max, f0_out);
-  WB_LAUNCH_CHECK();
+  WB_LAUNCH_CHECK(); kt1.stop();
   return true;
 }
 

@@ -351,9 +351,10 @@ bool synthesis_run(Batch* b, const int* y_len) {
 
   DevBuf<int> d_cnt, d_poff;
   if (!d_cnt.alloc(n_utt) || !d_poff.alloc(n_utt)) return false;
+  KernelTimer kt1("synth_timebase_kernel");
   synth_timebase_kernel<false><<<n_utt, 512, 0, st>>>(b->f0.p, b->f_off.p, b->f_len.p, b->y_len.p, c, d_cnt.p,
                                                       nullptr, nullptr, nullptr, nullptr, nullptr);
-  WB_LAUNCH_CHECK();
+  WB_LAUNCH_CHECK(); kt1.stop();
   std::vector<int> h_cnt(n_utt), h_poff(n_utt);
   WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_cnt.data(), d_cnt.p, n_utt * sizeof(int), cudaMemcpyDeviceToHost, st), false);
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
@@ -368,9 +369,10 @@ bool synthesis_run(Batch* b, const int* y_len) {
   DevBuf<unsigned char> p_vuv;
   if (!p_index.alloc(total_p) || !p_utt.alloc(total_p) || !p_shift.alloc(total_p) || !p_vuv.alloc(total_p) || !d_rem.alloc(N)) return false;
   WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_poff.p, h_poff.data(), n_utt * sizeof(int), cudaMemcpyHostToDevice, st), false);
+  KernelTimer kt2("synth_timebase_kernel");
   synth_timebase_kernel<true><<<n_utt, 512, 0, st>>>(b->f0.p, b->f_off.p, b->f_len.p, b->y_len.p, c, nullptr, d_poff.p,
                                                      p_index.p, p_shift.p, p_vuv.p, p_utt.p);
-  WB_LAUNCH_CHECK();
+  WB_LAUNCH_CHECK(); kt2.stop();
   // GetDCRemover (:322-334)
   std::vector<double> rem(N);
   double dc_component = 0.0;
@@ -385,10 +387,11 @@ bool synthesis_run(Batch* b, const int* y_len) {
                       (size_t)(N / 2 + 8) * sizeof(double2) + 96 * sizeof(double);
   if (N / 256 > 8) { set_error("Synthesis: fft_size %d too large for the register fold", N); return false; }
   WB_CUDA_OR_RETURN(cudaFuncSetAttribute(synth_pulse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+  KernelTimer kt3("synth_pulse_kernel");
   synth_pulse_kernel<<<(unsigned)total_p, 256, smem, st>>>(b->f0.p, b->sp.p, b->ap.p, b->f_off.p, b->f_len.p, b->y_off.p, b->y_len.p,
                                                            d_poff.p, d_cnt.p, p_index.p, p_shift.p, p_vuv.p, p_utt.p, ctxp->d_randn,
                                                            ctxp->d_twiddle, d_rem.p, c, b->y.p);
-  WB_LAUNCH_CHECK();
+  WB_LAUNCH_CHECK(); kt3.stop();
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
   return true;
 }

@@ -33,6 +33,17 @@ WORLD_API unsigned long long wb200_launch_count(void);
 /* device time (ms, CUDA events on the library stream) of the last call of each stage:
  * out[0..5] = dio, stonemask, cheaptrick, d4c, synthesis, harvest */
 WORLD_API void wb200_stage_times(float *out6);
+/* run all library work on a caller-owned CUDA stream (cudaStream_t); the caller keeps it alive */
+WORLD_API int wb200_set_stream(void *stream);
+/* per-kernel device timing (CUDA events on the library stream around each launch of the named
+ * kernel).  Off by default.  wb200_kernel_time returns 0 and the accumulated milliseconds and
+ * launch count since the last reset, 1 if the kernel never ran. */
+WORLD_API void wb200_kernel_timing(int on);
+WORLD_API void wb200_kernel_times_reset(void);
+WORLD_API int wb200_kernel_time(const char *name, double *ms_total, long long *launches);
+/* measured CUDA-core FMA peak in TFLOP/s (fp64 != 0: double, else float) — the roofline
+ * denominator of SURVEY.md 8(d) */
+WORLD_API double wb200_measure_fma_peak(int fp64);
 /* first `n` values of the randn table as doubles (test hook: must equal the reference's
  * randn() stream after randn_reseed(), W/src/matlabfunctions.cpp:247-277) */
 WORLD_API int wb200_randn_stream(double *out, long long n);
