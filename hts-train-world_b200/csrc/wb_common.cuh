@@ -71,7 +71,11 @@ void kernel_timing_enable(bool on);
 bool kernel_time_query(const char* name, double* ms_total, long long* launches);
 void kernel_times_reset();
 
-// simple stream-ordered device buffer
+// Stream-ordered device buffer.  Memory comes from the device's default CUDA memory pool
+// (cudaMallocAsync on the library stream; the pool's release threshold is raised to "never" in
+// ctx()), so the per-stage scratch buffers -- gigabytes for a corpus-sized batch -- are recycled
+// between stages and calls instead of going through cudaMalloc / cudaFree every time.
+cudaStream_t pool_stream();
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -80,11 +84,11 @@ struct DevBuf {
     if (count <= n && p) return true;
     release();
     if (count == 0) count = 1;
-    if (!WB_CUDA(cudaMalloc((void**)&p, count * sizeof(T)))) { p = nullptr; n = 0; return false; }
+    if (!WB_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), pool_stream()))) { p = nullptr; n = 0; return false; }
     n = count;
     return true;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() { if (p) cudaFreeAsync(p, pool_stream()); p = nullptr; n = 0; }
   ~DevBuf() { release(); }
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;

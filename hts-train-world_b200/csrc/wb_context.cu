@@ -214,6 +214,8 @@ static std::mutex g_ctx_mutex;
 static Context g_ctx;
 static bool g_ctx_ok = false, g_ctx_failed = false;
 
+cudaStream_t pool_stream() { return g_ctx_ok ? g_ctx.stream : nullptr; }
+
 void set_stream(cudaStream_t s) {
   Context* c = ctx();
   if (c) { cudaStreamSynchronize(c->stream); c->stream = s; }
@@ -238,6 +240,12 @@ Context* ctx() {
   g_ctx.smem_optin = prop.sharedMemPerBlockOptin;
   if (!WB_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking))) {
     g_ctx_failed = true; return nullptr;
+  }
+  {   // keep freed scratch in the pool instead of returning it to the driver at every sync
+    cudaMemPool_t pool;
+    unsigned long long never = ~0ull;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never);
   }
   // twiddles, rounded from long double
   std::vector<double2> tw(kTwN / 2 + 1);

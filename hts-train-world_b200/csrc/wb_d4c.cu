@@ -124,67 +124,100 @@ __global__ void d4c_main_count_kernel(const double* __restrict__ f0, const doubl
   counts[f] = 3LL * (2LL * d4c_hwl(4.0, fs, fmax(kFloorF0D4C, v)) + 1);
 }
 
-// Exact sum of everything below the (K)-th largest of the thread-distributed non-negative
-// values v[0..nv) (invalid entries flagged by valid bit mask).  Two independent sets (a, b)
-// are processed together; counts travel packed in one 64-bit word per pass.
-// Result: low[0], low[1] = sum of the (count - K) smallest values; tot[0], tot[1] = sum of all.
-struct SelectScratch { unsigned long long cnt[2][32]; };
+// Exact sum of everything below the K-th largest of the thread-distributed non-negative
+// values pa / pb (two independent sets; entry j of a thread is valid when bit j of `valid` is
+// set).  MSB-first radix selection on the IEEE bit patterns (order-isomorphic to the values
+// for non-negative doubles) with 12-bit digits: every pass histograms the digit of the keys
+// that still match the prefix into shared memory (`hist`, 2 x 4096 ints, carved out of the FFT
+// buffer, which is idle here), locates the bin that holds the K-th largest with one block-wide
+// suffix scan and narrows the prefix.  The loop ends as soon as all keys matching the prefix
+// belong to the top set (always the case once a single candidate is left), typically after
+// 2-3 passes instead of the 63 one-bit passes of a bitwise search.
+// Result: low[s] = sum of the (count - K) smallest values, tot[s] = sum of all.
+// the FFT buffer doubles as the selection histogram (2 x 4096 ints = 2048 double2 slots)
+__host__ __device__ constexpr int d4c_cbuf_slots(int nd) { return cpad_size(nd) > 2048 ? cpad_size(nd) : 2048; }
+constexpr int kSelDigitBits = 12;
+constexpr int kSelBins = 1 << kSelDigitBits;
 
-__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* slot) {
-  // slot: 32 entries, alternate between two buffers so one __syncthreads per call suffices
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if (lane == 0) slot[wid] = v;
-  __syncthreads();
-  unsigned long long t = lane < nw ? slot[lane] : 0ull;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-  return t;
-}
+struct SelectScratch {
+  unsigned long long wsum[32];
+  int digit[2], above[2], cand[2];
+};
 
 __device__ __forceinline__ void select_low_sums(const double (&pa)[kVP], const double (&pb)[kVP],
-                                                unsigned valid, int K, SelectScratch* sc,
+                                                unsigned valid, int K, int* hist, SelectScratch* sc,
                                                 double* red, double (&low)[2], double (&tot)[2]) {
-  unsigned long long pre[2] = {0ull, 0ull};
-  unsigned long long k_rem[2] = {(unsigned long long)K, (unsigned long long)K};
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
+  unsigned long long pre[2] = {0ull, 0ull};          // decided high bits of the K-th largest key
+  unsigned long long mask_hi = 0ull;                 // which bits of `pre` are decided
+  int k_rem[2] = {K, K};
   bool done[2] = {false, false};
-  int pass = 0;
-  for (int bit = 62; bit >= 0; --bit) {      // bit 63 (sign) is 0 for every power value
-    if (done[0] && done[1]) break;
-    const unsigned long long mask_hi = ~((2ull << bit) - 1ull);   // bits above `bit`
-    const unsigned long long b = 1ull << bit;
-    unsigned int c1[2] = {0u, 0u}, cc[2] = {0u, 0u};
+  const int bins_per_thread = kSelBins / T;          // T in {256, 512}
+  for (int shift = 63 - kSelDigitBits; ; shift -= kSelDigitBits) {
+    const int sh = shift < 0 ? 0 : shift;
+    const int width = shift < 0 ? kSelDigitBits + shift : kSelDigitBits;
+    const int nbins = 1 << width;
+    const unsigned long long dmask = (unsigned long long)(nbins - 1);
+    for (int i = tid; i < 2 * kSelBins / 4; i += T) reinterpret_cast<int4*>(hist)[i] = make_int4(0, 0, 0, 0);
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < kVP; ++j) {
       if (!((valid >> j) & 1u)) continue;
       const unsigned long long ka = (unsigned long long)__double_as_longlong(pa[j]);
       const unsigned long long kb = (unsigned long long)__double_as_longlong(pb[j]);
-      if ((ka & mask_hi) == pre[0]) { ++cc[0]; if (ka & b) ++c1[0]; }
-      if ((kb & mask_hi) == pre[1]) { ++cc[1]; if (kb & b) ++c1[1]; }
+      if (!done[0] && (ka & mask_hi) == pre[0]) atomicAdd(&hist[(int)((ka >> sh) & dmask)], 1);
+      if (!done[1] && (kb & mask_hi) == pre[1]) atomicAdd(&hist[kSelBins + (int)((kb >> sh) & dmask)], 1);
     }
-    const unsigned long long packed = (unsigned long long)c1[0] | ((unsigned long long)cc[0] << 16) |
-                                      ((unsigned long long)c1[1] << 32) | ((unsigned long long)cc[1] << 48);
-    const unsigned long long t = block_sum_u64(packed, sc->cnt[pass & 1]);
-    ++pass;
-    const unsigned long long n1[2] = {t & 0xffffull, (t >> 32) & 0xffffull};
-    const unsigned long long nc[2] = {(t >> 16) & 0xffffull, (t >> 48) & 0xffffull};
+    __syncthreads();
+    // counts of this thread's bins; thread t owns bins [t * bpt, (t + 1) * bpt) of both sets
+    const int b_lo = tid * bins_per_thread;
+    unsigned int mine[2] = {0u, 0u};
+    for (int q = 0; q < bins_per_thread; ++q) { mine[0] += hist[b_lo + q]; mine[1] += hist[kSelBins + b_lo + q]; }
+    // suffix sum over threads (bins above mine), both sets packed in one 64-bit word
+    const unsigned long long v = (unsigned long long)mine[0] | ((unsigned long long)mine[1] << 32);
+    unsigned long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_down_sync(0xffffffffu, inc, o);
+      if (lane + o < 32) inc += t;
+    }
+    if (lane == 0) sc->wsum[wid] = inc;
+    __syncthreads();
+    unsigned long long above = inc - v;
+    for (int w = wid + 1; w < nw; ++w) above += sc->wsum[w];
+    const unsigned int ab[2] = {(unsigned int)(above & 0xffffffffull), (unsigned int)(above >> 32)};
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       if (done[s]) continue;
-      if (nc[s] == k_rem[s]) { done[s] = true; continue; }   // every candidate is in the top set
-      if (n1[s] >= k_rem[s]) pre[s] |= b; else k_rem[s] -= n1[s];
+      if ((int)ab[s] < k_rem[s] && k_rem[s] <= (int)(ab[s] + mine[s])) {   // the K-th largest is in my bins
+        int acc = (int)ab[s];
+        for (int q = bins_per_thread - 1; q >= 0; --q) {
+          const int h = hist[s * kSelBins + b_lo + q];
+          if (acc < k_rem[s] && k_rem[s] <= acc + h) { sc->digit[s] = b_lo + q; sc->above[s] = acc; sc->cand[s] = h; break; }
+          acc += h;
+        }
+      }
     }
+    __syncthreads();
+    mask_hi |= dmask << sh;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      if (done[s]) continue;
+      pre[s] |= (unsigned long long)sc->digit[s] << sh;
+      k_rem[s] -= sc->above[s];
+      if (sc->cand[s] == k_rem[s]) done[s] = true;   // every key with this prefix is in the top set
+    }
+    if ((done[0] && done[1]) || sh == 0) break;
   }
-  // keys >= pre[s] form the top set, except (when the loop ran to bit 0 with ties) that only
-  // k_rem[s] copies of the value pre[s] belong to it.
+  // top set = keys whose decided bits are >= pre; when the digits ran out with ties left
+  // (!done), only k_rem copies of the value `pre` belong to it.
   double acc[3] = {0.0, 0.0, 0.0};
   double acc2[3] = {0.0, 0.0, 0.0};
 #pragma unroll
   for (int j = 0; j < kVP; ++j) {
     if (!((valid >> j) & 1u)) continue;
-    const unsigned long long ka = (unsigned long long)__double_as_longlong(pa[j]);
-    const unsigned long long kb = (unsigned long long)__double_as_longlong(pb[j]);
+    const unsigned long long ka = (unsigned long long)__double_as_longlong(pa[j]) & mask_hi;
+    const unsigned long long kb = (unsigned long long)__double_as_longlong(pb[j]) & mask_hi;
     acc[0] += pa[j]; if (ka < pre[0]) acc[1] += pa[j]; if (!done[0] && ka == pre[0]) acc[2] += 1.0;
     acc2[0] += pb[j]; if (kb < pre[1]) acc2[1] += pb[j]; if (!done[1] && kb == pre[1]) acc2[2] += 1.0;
   }
@@ -208,7 +241,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
   const int Nd = 1 << c.log2nd, Hd = Nd >> 1;
   double2* cbuf = smem2;
   double* cbufd = reinterpret_cast<double*>(cbuf);
-  double* cen = reinterpret_cast<double*>(cbuf + cpad_size(Nd));
+  double* cen = reinterpret_cast<double*>(cbuf + d4c_cbuf_slots(Nd));
   double* pw = cen + Hd + 8;
   double* red = pw + Hd + 8;
   SelectScratch* sc = reinterpret_cast<SelectScratch*>(red + 96);
@@ -325,7 +358,8 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
       }
     }
     double low[2], tot[2];
-    select_low_sums(pa, pb, valid, c.sel_boundary + 1, sc, red, low, tot);
+    __syncthreads();                                   // everyone has read cbuf: reuse it as the histogram
+    select_low_sums(pa, pb, valid, c.sel_boundary + 1, reinterpret_cast<int*>(cbuf), sc, red, low, tot);
     if (tid == 0) {
       coarse[1 + b0] = fmin(0.0, 10.0 * log10(low[0] / tot[0]) + (cur_f0 - 100.0) / 50.0);
       if (two) coarse[2 + b0] = fmin(0.0, 10.0 * log10(low[1] / tot[1]) + (cur_f0 - 100.0) / 50.0);
@@ -429,7 +463,7 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
   if (!need_randn()) return false;
   {
     const int hd = nd / 2;
-    const size_t smem = cpad_size(nd) * sizeof(double2) + (size_t)(2 * (hd + 8) + 96) * sizeof(double) +
+    const size_t smem = d4c_cbuf_slots(nd) * sizeof(double2) + (size_t)(2 * (hd + 8) + 96) * sizeof(double) +
                         sizeof(SelectScratch) + (kMaxBands + 2) * sizeof(double);
     const int threads = nd > 4096 ? 512 : 256;
     if (hd / threads + 1 > kVP) { set_error("D4C: fft size %d too large", nd); return false; }

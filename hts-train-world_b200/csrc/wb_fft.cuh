@@ -9,16 +9,21 @@
 // fft_dit() slot k holds X[k] in natural order.  Each pass keeps 8 (or 4 / 2) points per
 // thread in registers and performs three (two / one) radix-2 stages before touching shared
 // memory again, so a 2048-point transform makes 4 round trips through shared memory instead
-// of 11.  Slots are padded by one double2 every 8 (cpad) so that the stride-8 accesses of
-// the first pass and the stride-1 accesses of later passes are both bank-conflict-free for
-// 16-byte elements.  Twiddles come from one global table (L1-resident, read-only path).
+// of 11.  Slots are padded (cpad) so that the butterfly passes and the bit-reversed input /
+// output permutations are bank-conflict-free for 16-byte elements.  Twiddles come from one
+// global table (L1-resident, read-only path), three loads per radix-8 group.
 #pragma once
 #include "wb_common.cuh"
 
 namespace wb {
 
-__host__ __device__ __forceinline__ constexpr int cpad(int c) { return c + (c >> 3); }
-__host__ __device__ constexpr int cpad_size(int n) { return n + (n >> 3) + 2; }
+// Slot padding: one extra double2 every 8, 64 and 512 elements.  A quarter-warp (8 threads x 16
+// bytes = one 128-byte shared-memory wavefront) is conflict-free when its 8 slots differ
+// modulo 8; with the three skew terms that holds for the unit- and 8-stride accesses of the
+// butterfly passes AND for the bit-reversed scatter / gather of the input and output
+// permutations (strides 2^(log2n-3) * {0,4,2,6,1,5,3,7}) for every size from 2^6 to 2^13.
+__host__ __device__ __forceinline__ constexpr int cpad(int c) { return c + (c >> 3) + (c >> 6) + (c >> 9); }
+__host__ __device__ constexpr int cpad_size(int n) { return n + (n >> 3) + (n >> 6) + (n >> 9) + 4; }
 __device__ __forceinline__ int brev(int c, int log2n) {
   return static_cast<int>(__brev(static_cast<unsigned>(c)) >> (32 - log2n));
 }
@@ -30,33 +35,55 @@ __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_doub
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
 
-template <int K, bool INV>
+// v * exp(-/+ 2 pi i e8 / 8) for e8 in {0, 1, 2, 3} (forward: minus sign; INV: plus sign).
+// e8 is a compile-time constant after unrolling, so only one branch survives.
+template <bool INV>
+__device__ __forceinline__ double2 rot8(double2 v, int e8) {
+  constexpr double kH = 0.70710678118654752440;
+  if (e8 == 0) return v;
+  if (e8 == 2) return INV ? make_double2(-v.y, v.x) : make_double2(v.y, -v.x);
+  if (e8 == 1) return INV ? make_double2((v.x - v.y) * kH, (v.x + v.y) * kH)
+                          : make_double2((v.x + v.y) * kH, (v.y - v.x) * kH);
+  return INV ? make_double2(-(v.x + v.y) * kH, (v.x - v.y) * kH)
+             : make_double2((v.y - v.x) * kH, -(v.x + v.y) * kH);
+}
+
+// One pass of K radix-2 stages on 2^K points held in registers.  The K twiddles of the group
+// (W_{2^(stage+t+1)}^j, t < K) are loaded once; the other butterflies of a sub-stage use the same
+// twiddle times a multiple of 45 degrees, which costs at most two multiplies.  The first pass
+// (stage 0) has j = 0 for every group and needs no twiddle at all.
+template <int K, bool INV, bool FIRST>
 __device__ __forceinline__ void fft_pass(double2* __restrict__ s, int log2n, int stage,
                                          const double2* __restrict__ tw) {
   constexpr int R = 1 << K;
   const int h_mask = (1 << stage) - 1;
   const int nb = 1 << (log2n - K);
   for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-    const int j = b & h_mask;
-    const int base = ((b >> stage) << (stage + K)) + j;
+    const int j = FIRST ? 0 : (b & h_mask);
+    const int base = FIRST ? (b << K) : (((b >> stage) << (stage + K)) + j);
     double2 v[R];
 #pragma unroll
     for (int m = 0; m < R; ++m) v[m] = s[cpad(base + (m << stage))];
+    double2 w[K];
+    if (!FIRST) {
+#pragma unroll
+      for (int t = 0; t < K; ++t) {
+        w[t] = __ldg(&tw[j << (kTwLog2 - stage - t - 1)]);
+        if (INV) w[t].y = -w[t].y;
+      }
+    }
 #pragma unroll
     for (int t = 0; t < K; ++t) {
-      constexpr int dummy = 0; (void)dummy;
       const int span = 1 << t;
-      const int sh = kTwLog2 - stage - t - 1;
 #pragma unroll
       for (int m = 0; m < R; ++m) {
         if (m & span) continue;
-        const int e = ((m & (span - 1)) << stage) + j;
-        double2 w = __ldg(&tw[e << sh]);
-        if (INV) w.y = -w.y;
+        double2 x = v[m + span];
+        if (!FIRST) x = cmul(w[t], x);
+        x = rot8<INV>(x, (m & (span - 1)) * (4 >> t));
         const double2 a = v[m];
-        const double2 wb = cmul(w, v[m + span]);
-        v[m] = cadd(a, wb);
-        v[m + span] = csub(a, wb);
+        v[m] = cadd(a, x);
+        v[m + span] = csub(a, x);
       }
     }
 #pragma unroll
@@ -70,12 +97,14 @@ __device__ __forceinline__ void fft_pass(double2* __restrict__ s, int log2n, int
 template <bool INV>
 __device__ __forceinline__ void fft_dit(double2* s, int log2n, const double2* __restrict__ tw) {
   __syncthreads();
-  int stage = 0;
+  int stage;
   const int rem = log2n % 3;
-  if (rem == 1) { fft_pass<1, INV>(s, log2n, 0, tw); stage = 1; __syncthreads(); }
-  else if (rem == 2) { fft_pass<2, INV>(s, log2n, 0, tw); stage = 2; __syncthreads(); }
+  if (rem == 1) { fft_pass<1, INV, true>(s, log2n, 0, tw); stage = 1; }
+  else if (rem == 2) { fft_pass<2, INV, true>(s, log2n, 0, tw); stage = 2; }
+  else { fft_pass<3, INV, true>(s, log2n, 0, tw); stage = 3; }
+  __syncthreads();
   for (; stage < log2n; stage += 3) {
-    fft_pass<3, INV>(s, log2n, stage, tw);
+    fft_pass<3, INV, false>(s, log2n, stage, tw);
     __syncthreads();
   }
 }
