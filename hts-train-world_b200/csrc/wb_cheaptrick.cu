@@ -33,12 +33,15 @@ __global__ void cheaptrick_count_kernel(const double* __restrict__ f0, int total
 }
 
 // dynamic shared memory: [ buf: cpad_size(N/2) double2 | aux: N + 16 doubles | red: 96 doubles ]
+template <int LOG2N>      // 0: size given at run time (log2n_rt)
 __global__ void __launch_bounds__(256)
 cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __restrict__ frame_t,
                   const double* __restrict__ f0_in, const long long* __restrict__ rng_off,
                   const uint32_t* __restrict__ randn_tab, const double2* __restrict__ tw,
-                  int fs, int log2n, double q1, double f0_floor, double* __restrict__ sp_out) {
+                  int fs, int log2n_rt, double q1, double f0_floor, double* __restrict__ sp_out) {
   extern __shared__ double2 smem2[];
+  const int log2n = LOG2N > 0 ? LOG2N : log2n_rt;
+  constexpr int LM = LOG2N > 0 ? LOG2N - 1 : 0;
   const int N = 1 << log2n, M = N >> 1, log2m = log2n - 1, half = M;   // half = N/2
   double2* buf = smem2;
   double* bufd = reinterpret_cast<double*>(buf);
@@ -101,7 +104,7 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
   for (int i = tid; i < W; i += T) bufd[rfft_in_slot(i, log2m)] -= aux[i] * coef;
 
   // ---- GetPowerSpectrum (:64-82) -----------------------------------------------------------
-  fft_dit<false>(buf, log2m, tw);
+  fft_dit<LM, false, 256>(buf, log2m, tw);
   for (int k = tid; k <= half; k += T) {
     const double2 X = rfft_bin(buf, log2m, k, tw);
     aux[k] = X.x * X.x + X.y * X.y;
@@ -144,7 +147,7 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
   __syncthreads();
   // ---- SmoothingWithRecovery (:22-57) ---------------------------------------------------------
   for (int i = tid; i < N; i += T) bufd[rfft_in_slot(i, log2m)] = aux[i <= half ? i : N - i];
-  fft_dit<false>(buf, log2m, tw);
+  fft_dit<LM, false, 256>(buf, log2m, tw);
   for (int k = tid; k <= half; k += T) {
     const double re = rfft_bin(buf, log2m, k, tw).x;
     double lifter = 1.0, comp = (1.0 - 2.0 * q1) + 2.0 * q1;
@@ -161,7 +164,7 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
     const double2 z = c2r_pack(make_double2(aux[k], 0.0), make_double2(aux[half - k], 0.0), k, log2m, tw);
     buf[cpad(brev(k, log2m))] = z;
   }
-  fft_dit<true>(buf, log2m, tw);
+  fft_dit<LM, true, 256>(buf, log2m, tw);
   for (int k = tid; k <= half; k += T) out[k] = exp(bufd[rfft_out_slot(k)]);
 }
 
@@ -191,9 +194,19 @@ bool cheaptrick_run(const UttView& u, int fs, int total_frames, const int* frame
   for (long long v : h_tot) mx = v > mx ? v : mx;
   if (!ensure_randn((size_t)mx)) return false;
   const size_t smem = cpad_size(fft_size / 2) * sizeof(double2) + (fft_size + 16 + 96) * sizeof(double);
-  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(cheaptrick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
   KernelTimer kt1("cheaptrick_kernel");
-  cheaptrick_kernel<<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0, offs.p, c->d_randn, c->d_twiddle, fs, log2n, q1, f0_floor, sp);
+#define WB_CT_LAUNCH(L)                                                                                             \
+  do {                                                                                                              \
+    WB_CUDA_OR_RETURN(cudaFuncSetAttribute(cheaptrick_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
+    cheaptrick_kernel<L><<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0, offs.p, c->d_randn, c->d_twiddle, fs, log2n, q1, f0_floor, sp); \
+  } while (0)
+  switch (log2n) {
+    case 10: WB_CT_LAUNCH(10); break;
+    case 11: WB_CT_LAUNCH(11); break;
+    case 12: WB_CT_LAUNCH(12); break;
+    default: WB_CT_LAUNCH(0); break;
+  }
+#undef WB_CT_LAUNCH
   WB_LAUNCH_CHECK(); kt1.stop();
   // counts/offs are freed when this returns: make sure the kernel is done with them
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);

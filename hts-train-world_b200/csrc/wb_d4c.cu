@@ -51,10 +51,10 @@ __device__ __forceinline__ int windowed_waveform(const double* __restrict__ x, i
   const int hwl = d4c_hwl(ratio, fs, f0);
   const int W = 2 * hwl + 1;
   const int origin = matlab_round(add_rn(mul_rn(position, (double)fs), 0.001));
+  const double ang_step = kPi * 2.0 * f0 / (ratio * fs);
   double s[2] = {0.0, 0.0};
   for (int i = tid; i < W; i += T) {
-    const double pos = div_rn(div_rn(mul_rn(2.0, (double)(i - hwl)), ratio), (double)fs);
-    const double a = kPi * pos * f0;
+    const double a = (double)(i - hwl) * ang_step;      // pi * (2 (i - hwl) / ratio / fs) * f0
     const double w = window_type == kHanning ? 0.5 * cos(a) + 0.5
                                              : 0.42 + 0.5 * cos(a) + 0.08 * cos(a * 2);
     const int idx = min(x_len - 1, max(0, origin + i - hwl));
@@ -79,6 +79,7 @@ __global__ void d4c_lt_count_kernel(const double* __restrict__ f0, int n, int fs
   counts[f] = v == 0.0 ? 0 : 2LL * matlab_round(div_rn(mul_rn(1.5, (double)fs), fmax(v, 40.0))) + 1;
 }
 
+template <int LOG2LT>     // 0: size given at run time (c.log2lt)
 __global__ void __launch_bounds__(256)
 d4c_lovetrain_kernel(UttView u, const int* __restrict__ frame_utt, const double* __restrict__ frame_t,
                      const double* __restrict__ f0_in, const long long* __restrict__ rng_off,
@@ -88,7 +89,9 @@ d4c_lovetrain_kernel(UttView u, const int* __restrict__ frame_utt, const double*
   const int f = blockIdx.x;
   const double f0 = f0_in[f];
   if (f0 == 0.0) { if (threadIdx.x == 0) ap0_out[f] = 0.0; return; }
-  const int N = 1 << c.log2lt, M = N >> 1, log2m = c.log2lt - 1;
+  constexpr int LM = LOG2LT > 0 ? LOG2LT - 1 : 0;
+  const int log2m = LOG2LT > 0 ? LOG2LT - 1 : c.log2lt - 1;
+  const int M = 1 << log2m, N = M << 1;
   double2* buf = smem2;
   double* bufd = reinterpret_cast<double*>(buf);
   // layout: [ buf: 2*cpad_size(M) doubles | window scratch: N + 8 doubles | red: 96 ]
@@ -103,7 +106,7 @@ d4c_lovetrain_kernel(UttView u, const int* __restrict__ frame_utt, const double*
   const int W = windowed_waveform(x, u.x_len[utt], c.fs, cur_f0, frame_t[f], kBlackman, 3.0,
                                   randn_tab + rng_off[f], bufd, wslot, vslot, red);
   for (int i = W + tid; i < N; i += T) bufd[rfft_in_slot(i, log2m)] = 0.0;
-  fft_dit<false>(buf, log2m, tw);
+  fft_dit<LM, false, 256>(buf, log2m, tw);
   double s[2] = {0.0, 0.0};
   for (int k = c.lt_b0 + 1 + tid; k <= c.lt_b2; k += T) {
     const double2 X = rfft_bin(buf, log2m, k, tw);
@@ -153,6 +156,9 @@ __device__ __forceinline__ void select_low_sums(const double (&pa)[kVP], const d
   int k_rem[2] = {K, K};
   bool done[2] = {false, false};
   const int bins_per_thread = kSelBins / T;          // T in {256, 512}
+  // bin b = t * bins_per_thread + q lives at [q * T + t]: a thread's own bins are conflict-free
+  const int bpt_shift = 31 - __clz(bins_per_thread);
+  auto hslot = [=](int bin) { return (bin & (bins_per_thread - 1)) * T + (bin >> bpt_shift); };
   for (int shift = 63 - kSelDigitBits; ; shift -= kSelDigitBits) {
     const int sh = shift < 0 ? 0 : shift;
     const int width = shift < 0 ? kSelDigitBits + shift : kSelDigitBits;
@@ -165,14 +171,14 @@ __device__ __forceinline__ void select_low_sums(const double (&pa)[kVP], const d
       if (!((valid >> j) & 1u)) continue;
       const unsigned long long ka = (unsigned long long)__double_as_longlong(pa[j]);
       const unsigned long long kb = (unsigned long long)__double_as_longlong(pb[j]);
-      if (!done[0] && (ka & mask_hi) == pre[0]) atomicAdd(&hist[(int)((ka >> sh) & dmask)], 1);
-      if (!done[1] && (kb & mask_hi) == pre[1]) atomicAdd(&hist[kSelBins + (int)((kb >> sh) & dmask)], 1);
+      if (!done[0] && (ka & mask_hi) == pre[0]) atomicAdd(&hist[hslot((int)((ka >> sh) & dmask))], 1);
+      if (!done[1] && (kb & mask_hi) == pre[1]) atomicAdd(&hist[kSelBins + hslot((int)((kb >> sh) & dmask))], 1);
     }
     __syncthreads();
     // counts of this thread's bins; thread t owns bins [t * bpt, (t + 1) * bpt) of both sets
     const int b_lo = tid * bins_per_thread;
     unsigned int mine[2] = {0u, 0u};
-    for (int q = 0; q < bins_per_thread; ++q) { mine[0] += hist[b_lo + q]; mine[1] += hist[kSelBins + b_lo + q]; }
+    for (int q = 0; q < bins_per_thread; ++q) { mine[0] += hist[q * T + tid]; mine[1] += hist[kSelBins + q * T + tid]; }
     // suffix sum over threads (bins above mine), both sets packed in one 64-bit word
     const unsigned long long v = (unsigned long long)mine[0] | ((unsigned long long)mine[1] << 32);
     unsigned long long inc = v;
@@ -192,7 +198,7 @@ __device__ __forceinline__ void select_low_sums(const double (&pa)[kVP], const d
       if ((int)ab[s] < k_rem[s] && k_rem[s] <= (int)(ab[s] + mine[s])) {   // the K-th largest is in my bins
         int acc = (int)ab[s];
         for (int q = bins_per_thread - 1; q >= 0; --q) {
-          const int h = hist[s * kSelBins + b_lo + q];
+          const int h = hist[s * kSelBins + q * T + tid];
           if (acc < k_rem[s] && k_rem[s] <= acc + h) { sc->digit[s] = b_lo + q; sc->above[s] = acc; sc->cand[s] = h; break; }
           acc += h;
         }
@@ -231,14 +237,17 @@ __device__ __forceinline__ void select_low_sums(const double (&pa)[kVP], const d
 
 // dynamic shared memory: [ cbuf: cpad_size(Nd) double2 | cen: Hd+8 | pw: Hd+8 | red: 96 |
 //                          SelectScratch | coarse: kMaxBands+2 ]
-__global__ void
+template <int LOG2ND, int THREADS>    // LOG2ND 0: size given at run time (c.log2nd)
+__global__ void __launch_bounds__(THREADS)
 d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __restrict__ frame_t,
                 const double* __restrict__ f0_in, const double* __restrict__ ap0,
                 const long long* __restrict__ rng_off, const long long* __restrict__ lt_totals,
                 const uint32_t* __restrict__ randn_tab, const double2* __restrict__ tw,
                 const double* __restrict__ nuttall, D4CConst c, double* __restrict__ ap_out) {
   extern __shared__ double2 smem2[];
-  const int Nd = 1 << c.log2nd, Hd = Nd >> 1;
+  const int log2nd = LOG2ND > 0 ? LOG2ND : c.log2nd;
+  constexpr int LMD = LOG2ND > 0 ? LOG2ND - 1 : 0;
+  const int Nd = 1 << log2nd, Hd = Nd >> 1;
   double2* cbuf = smem2;
   double* cbufd = reinterpret_cast<double*>(cbuf);
   double* cen = reinterpret_cast<double*>(cbuf + d4c_cbuf_slots(Nd));
@@ -246,7 +255,8 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
   double* red = pw + Hd + 8;
   SelectScratch* sc = reinterpret_cast<SelectScratch*>(red + 96);
   double* coarse = reinterpret_cast<double*>(sc + 1);
-  const int tid = threadIdx.x, T = blockDim.x;
+  const int tid = threadIdx.x;
+  constexpr int T = THREADS;
   const int f = blockIdx.x;
   double* __restrict__ out = ap_out + (size_t)f * (c.out_half + 1);
   const double f0 = f0_in[f];
@@ -265,7 +275,6 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
     for (int k = tid; k <= c.out_half; k += T) out[k] = __longlong_as_double(0x7ff8000000000000LL);
     return;
   }
-  const int log2nd = c.log2nd;
   auto cslot = [log2nd](int i) { return cpad(brev(i, log2nd)); };
 
   // ---- GetStaticCentroid (:125-142): two centroids, each one packed complex FFT ----------------
@@ -285,7 +294,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
       if (i < W) { const double v = cbuf[cslot(i)].x / sq; z = make_double2(v, v * (i + 1.0)); }
       cbuf[cslot(i)] = z;
     }
-    fft_dit<false>(cbuf, log2nd, tw);
+    fft_dit<LOG2ND, false, THREADS>(cbuf, log2nd, tw);
     for (int k = tid; k <= Hd; k += T) {
       const double2 A = cbuf[cpad(k)];
       const double2 B = cbuf[cpad((Nd - k) & (Nd - 1))];
@@ -308,7 +317,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
     const int W = windowed_waveform(x, x_len, c.fs, cur_f0, t_pos, kHanning, 4.0,
                                     rn + 2 * (size_t)W4, cbufd, pwslot, pvslot, red);
     for (int i = W + tid; i < Nd; i += T) cbufd[rfft_in_slot(i, log2m)] = 0.0;
-    fft_dit<false>(cbuf, log2m, tw);
+    fft_dit<LMD, false, THREADS>(cbuf, log2m, tw);
     for (int k = tid; k <= Hd; k += T) {
       const double2 X = rfft_bin(cbuf, log2m, k, tw);
       pw[k] = X.x * X.x + X.y * X.y;
@@ -342,7 +351,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
       }
       cbuf[cslot(i)] = z;
     }
-    fft_dit<false>(cbuf, log2nd, tw);
+    fft_dit<LOG2ND, false, THREADS>(cbuf, log2nd, tw);
     double pa[kVP], pb[kVP];
 #pragma unroll
     for (int j = 0; j < kVP; ++j) {
@@ -383,7 +392,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
     const double x1 = seg <= c.nbands ? seg * kFrequencyInterval : c.fs / 2.0;
     const double s = (xi - x0) / (x1 - x0);
     const double v = add_rn(coarse[seg - 1], mul_rn(s, coarse[seg] - coarse[seg - 1]));
-    out[k] = pow(10.0, v / 20.0);
+    out[k] = exp(v * 0.11512925464970228420);        // 10^(v/20) = e^(v ln(10)/20)
   }
 }
 
@@ -449,9 +458,18 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
   {
     const int nl = 1 << c.log2lt;
     const size_t smem = (size_t)(2 * cpad_size(nl / 2) + nl + 8 + 96) * sizeof(double);
-    WB_CUDA_OR_RETURN(cudaFuncSetAttribute(d4c_lovetrain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
     KernelTimer kt1("d4c_lovetrain_kernel");
-    d4c_lovetrain_kernel<<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0, offs_lt.p, ctxp->d_randn, ctxp->d_twiddle, c, d_ap0.p);
+#define WB_LT_LAUNCH(L)                                                                                             \
+  do {                                                                                                              \
+    WB_CUDA_OR_RETURN(cudaFuncSetAttribute(d4c_lovetrain_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
+    d4c_lovetrain_kernel<L><<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0, offs_lt.p, ctxp->d_randn, ctxp->d_twiddle, c, d_ap0.p); \
+  } while (0)
+    switch (c.log2lt) {
+      case 11: WB_LT_LAUNCH(11); break;
+      case 12: WB_LT_LAUNCH(12); break;
+      default: WB_LT_LAUNCH(0); break;
+    }
+#undef WB_LT_LAUNCH
     WB_LAUNCH_CHECK(); kt1.stop();
   }
   // main
@@ -467,10 +485,18 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
                         sizeof(SelectScratch) + (kMaxBands + 2) * sizeof(double);
     const int threads = nd > 4096 ? 512 : 256;
     if (hd / threads + 1 > kVP) { set_error("D4C: fft size %d too large", nd); return false; }
-    WB_CUDA_OR_RETURN(cudaFuncSetAttribute(d4c_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
     KernelTimer kt2("d4c_main_kernel");
-    d4c_main_kernel<<<total_frames, threads, smem, st>>>(u, frame_utt, frame_t, f0, d_ap0.p, offs_main.p, tot_lt.p, ctxp->d_randn,
-                                                         ctxp->d_twiddle, d_win.p, c, ap);
+#define WB_D4C_LAUNCH(L, TH)                                                                                        \
+  do {                                                                                                              \
+    WB_CUDA_OR_RETURN(cudaFuncSetAttribute(d4c_main_kernel<L, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
+    d4c_main_kernel<L, TH><<<total_frames, TH, smem, st>>>(u, frame_utt, frame_t, f0, d_ap0.p, offs_main.p, tot_lt.p, ctxp->d_randn, \
+                                                           ctxp->d_twiddle, d_win.p, c, ap);                         \
+  } while (0)
+    if (threads == 512) WB_D4C_LAUNCH(0, 512);
+    else if (c.log2nd == 12) WB_D4C_LAUNCH(12, 256);
+    else if (c.log2nd == 11) WB_D4C_LAUNCH(11, 256);
+    else WB_D4C_LAUNCH(0, 256);
+#undef WB_D4C_LAUNCH
     WB_LAUNCH_CHECK(); kt2.stop();
   }
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);

@@ -133,6 +133,7 @@ __global__ void dio_mean_kernel(const double* __restrict__ x_all, const long lon
 
 // ---- overlap-save filtering: one CTA per (block, utterance) ---------------------------------------
 // dynamic shared memory: [ xs: cpad_size(bn/2) double2 | ws: cpad_size(bn/2) double2 ]
+template <int LOG2BN>     // 0: block size given at run time (c.log2bn)
 __global__ void __launch_bounds__(256)
 dio_filter_kernel(const double* __restrict__ x_all, const long long* __restrict__ x_off,
                   const int* __restrict__ x_len, const int* __restrict__ y_len_all,
@@ -144,7 +145,8 @@ dio_filter_kernel(const double* __restrict__ x_all, const long long* __restrict_
   const int y_len = y_len_all[u];
   const int n0 = blockIdx.x * c.V;
   if (n0 >= y_len) return;
-  const int M = c.bn >> 1, log2m = c.log2bn - 1;
+  constexpr int LM = LOG2BN > 0 ? LOG2BN - 1 : 0;
+  const int log2m = LOG2BN > 0 ? LOG2BN - 1 : c.log2bn - 1, M = 1 << log2m;
   double2* xs = smem2;
   double2* ws = smem2 + cpad_size(M);
   double* xsd = reinterpret_cast<double*>(xs);
@@ -161,7 +163,7 @@ dio_filter_kernel(const double* __restrict__ x_all, const long long* __restrict_
     if (m < y_len) v = (m < xl ? x[m] : 0.0) - mean;
     xsd[rfft_in_slot(i, log2m)] = v;
   }
-  fft_dit<false>(xs, log2m, tw);
+  fft_dit<LM, false, 256>(xs, log2m, tw);
   // half spectrum in place: slot k = X[k] (k < M), slot 0 = (X[0], X[M])
   for (int k = tid; k <= M / 2; k += T) {
     if (k == 0) {
@@ -191,7 +193,7 @@ dio_filter_kernel(const double* __restrict__ x_all, const long long* __restrict_
         if (k != M - k) ws[cpad(brev(M - k, log2m))] = c2r_pack(ym, yk, M - k, log2m, tw);
       }
     }
-    fft_dit<true>(ws, log2m, tw);
+    fft_dit<LM, true, 256>(ws, log2m, tw);
     const int shift = c.D + 2 * c.hal[b] + c.hN;       // filtered_b[n] = conv[n - n0 + shift]
     double* __restrict__ dst = Fu + (size_t)b * y_len + n0;
     for (int i = tid; i < n_out; i += T) dst[i] = wsd[rfft_out_slot(i + shift)];
@@ -491,7 +493,8 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
   WB_LAUNCH_CHECK();
 
   const size_t smem = 2 * cpad_size(c.bn / 2) * sizeof(double2);
-  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(dio_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(dio_filter_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(dio_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
 
   // sub-batches bounded by the size of the filtered-signal scratch (nb * y_len doubles per utterance)
   const size_t kMaxScratchDoubles = (size_t)2 << 30;           // 16 GiB
@@ -521,7 +524,11 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
       return false;
     WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_foff.p, h_foff.data(), nu * sizeof(long long), cudaMemcpyHostToDevice, st), false);
     KernelTimer kt1("dio_filter_kernel");
-    dio_filter_kernel<<<dim3(n_blocks, nu), 256, smem, st>>>(b->x.p, b->x_off.p, b->x_len.p, d_ylen.p, d_mask.p, d_mean.p,
+    if (c.log2bn == 13)
+      dio_filter_kernel<13><<<dim3(n_blocks, nu), 256, smem, st>>>(b->x.p, b->x_off.p, b->x_len.p, d_ylen.p, d_mask.p, d_mean.p,
+                                                            d_foff.p, fb->G.p, ctxp->d_twiddle, c, u0, d_F.p);
+    else
+      dio_filter_kernel<0><<<dim3(n_blocks, nu), 256, smem, st>>>(b->x.p, b->x_off.p, b->x_len.p, d_ylen.p, d_mask.p, d_mean.p,
                                                             d_foff.p, fb->G.p, ctxp->d_twiddle, c, u0, d_F.p);
     WB_LAUNCH_CHECK(); kt1.stop();
     KernelTimer kt2("dio_zc_kernel");

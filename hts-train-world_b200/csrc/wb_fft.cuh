@@ -48,27 +48,36 @@ __device__ __forceinline__ double2 rot8(double2 v, int e8) {
              : make_double2((v.y - v.x) * kH, -(v.x + v.y) * kH);
 }
 
-// One pass of K radix-2 stages on 2^K points held in registers.  The K twiddles of the group
-// (W_{2^(stage+t+1)}^j, t < K) are loaded once; the other butterflies of a sub-stage use the same
+// One pass of K radix-2 stages on 2^K points held in registers.  Size, stage and block size
+// are compile-time constants, so every shared-memory offset inside a group is an immediate and
+// the groups of one thread are unrolled (their loads overlap).  The K twiddles of the group
+// (W_{2^(STAGE+t+1)}^j, t < K) are loaded once; the other butterflies of a sub-stage use the same
 // twiddle times a multiple of 45 degrees, which costs at most two multiplies.  The first pass
-// (stage 0) has j = 0 for every group and needs no twiddle at all.
-template <int K, bool INV, bool FIRST>
-__device__ __forceinline__ void fft_pass(double2* __restrict__ s, int log2n, int stage,
-                                         const double2* __restrict__ tw) {
+// (STAGE 0) has j = 0 for every group and needs no twiddle at all.
+//
+// cpad() is additive over non-overlapping bit fields: the group base has zeros where
+// (m << STAGE) lives, hence cpad(base + (m << STAGE)) = cpad(base) + cpad(m << STAGE).
+template <int K, bool INV, int LOG2N, int STAGE, int THREADS>
+__device__ __forceinline__ void fft_pass(double2* __restrict__ s, const double2* __restrict__ tw) {
   constexpr int R = 1 << K;
-  const int h_mask = (1 << stage) - 1;
-  const int nb = 1 << (log2n - K);
-  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-    const int j = FIRST ? 0 : (b & h_mask);
-    const int base = FIRST ? (b << K) : (((b >> stage) << (stage + K)) + j);
+  constexpr bool FIRST = STAGE == 0;
+  constexpr int NB = 1 << (LOG2N - K);
+  constexpr int ITERS = (NB + THREADS - 1) / THREADS;
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int b = threadIdx.x + it * THREADS;
+    if (NB % THREADS != 0 && b >= NB) break;
+    const int j = FIRST ? 0 : (b & ((1 << STAGE) - 1));
+    const int base = FIRST ? (b << K) : (((b >> STAGE) << (STAGE + K)) + j);
+    double2* __restrict__ sb = s + cpad(base);
     double2 v[R];
 #pragma unroll
-    for (int m = 0; m < R; ++m) v[m] = s[cpad(base + (m << stage))];
+    for (int m = 0; m < R; ++m) v[m] = sb[cpad(m << STAGE)];
     double2 w[K];
     if (!FIRST) {
 #pragma unroll
       for (int t = 0; t < K; ++t) {
-        w[t] = __ldg(&tw[j << (kTwLog2 - stage - t - 1)]);
+        w[t] = __ldg(&tw[j << (kTwLog2 - STAGE - t - 1)]);
         if (INV) w[t].y = -w[t].y;
       }
     }
@@ -87,26 +96,55 @@ __device__ __forceinline__ void fft_pass(double2* __restrict__ s, int log2n, int
       }
     }
 #pragma unroll
-    for (int m = 0; m < R; ++m) s[cpad(base + (m << stage))] = v[m];
+    for (int m = 0; m < R; ++m) sb[cpad(m << STAGE)] = v[m];
   }
 }
 
-// In-place complex FFT of 2^log2n points held in shared memory at padded slots.
-// Input: element c stored at slot brev(c, log2n).  Output: slot k = X[k].
-// Starts and ends with __syncthreads().
-template <bool INV>
-__device__ __forceinline__ void fft_dit(double2* s, int log2n, const double2* __restrict__ tw) {
-  __syncthreads();
-  int stage;
-  const int rem = log2n % 3;
-  if (rem == 1) { fft_pass<1, INV, true>(s, log2n, 0, tw); stage = 1; }
-  else if (rem == 2) { fft_pass<2, INV, true>(s, log2n, 0, tw); stage = 2; }
-  else { fft_pass<3, INV, true>(s, log2n, 0, tw); stage = 3; }
-  __syncthreads();
-  for (; stage < log2n; stage += 3) {
-    fft_pass<3, INV, false>(s, log2n, stage, tw);
+template <int LOG2N, int STAGE, bool INV, int THREADS>
+__device__ __forceinline__ void fft_later_passes(double2* s, const double2* __restrict__ tw) {
+  if constexpr (STAGE < LOG2N) {
+    fft_pass<3, INV, LOG2N, STAGE, THREADS>(s, tw);
     __syncthreads();
+    fft_later_passes<LOG2N, STAGE + 3, INV, THREADS>(s, tw);
   }
+}
+
+// In-place complex FFT of 2^LOG2N points held in shared memory at padded slots.
+// Input: element c stored at slot brev(c, LOG2N).  Output: slot k = X[k].
+// Starts and ends with __syncthreads().
+template <int LOG2N, bool INV, int THREADS>
+__device__ __forceinline__ void fft_dit_fixed(double2* s, const double2* __restrict__ tw) {
+  constexpr int K0 = LOG2N % 3 == 0 ? 3 : LOG2N % 3;
+  __syncthreads();
+  fft_pass<K0, INV, LOG2N, 0, THREADS>(s, tw);
+  __syncthreads();
+  fft_later_passes<LOG2N, K0, INV, THREADS>(s, tw);
+}
+
+// Size chosen at run time (block-uniform): sizes 2^3 .. 2^13.
+template <bool INV, int THREADS>
+__device__ __noinline__ void fft_dit_rt(double2* s, int log2n, const double2* __restrict__ tw) {
+  switch (log2n) {
+    case 3: fft_dit_fixed<3, INV, THREADS>(s, tw); break;
+    case 4: fft_dit_fixed<4, INV, THREADS>(s, tw); break;
+    case 5: fft_dit_fixed<5, INV, THREADS>(s, tw); break;
+    case 6: fft_dit_fixed<6, INV, THREADS>(s, tw); break;
+    case 7: fft_dit_fixed<7, INV, THREADS>(s, tw); break;
+    case 8: fft_dit_fixed<8, INV, THREADS>(s, tw); break;
+    case 9: fft_dit_fixed<9, INV, THREADS>(s, tw); break;
+    case 10: fft_dit_fixed<10, INV, THREADS>(s, tw); break;
+    case 11: fft_dit_fixed<11, INV, THREADS>(s, tw); break;
+    case 12: fft_dit_fixed<12, INV, THREADS>(s, tw); break;
+    case 13: fft_dit_fixed<13, INV, THREADS>(s, tw); break;
+    default: break;
+  }
+}
+
+// LOG2N > 0: compile-time size; LOG2N == 0: the run-time value log2n_rt.
+template <int LOG2N, bool INV, int THREADS>
+__device__ __forceinline__ void fft_dit(double2* s, int log2n_rt, const double2* __restrict__ tw) {
+  if constexpr (LOG2N > 0) fft_dit_fixed<LOG2N, INV, THREADS>(s, tw);
+  else fft_dit_rt<INV, THREADS>(s, log2n_rt, tw);
 }
 
 // ---- real transforms on top of a half-size complex FFT -----------------------------------

@@ -112,7 +112,7 @@ stonemask_kernel(UttView u, const int* __restrict__ frame_utt, const double* __r
     }
     cbuf[cpad(brev(i, log2fft))] = z;
   }
-  fft_dit<false>(cbuf, log2fft, tw);
+  fft_dit<0, false, 256>(cbuf, log2fft, tw);
   if (tid == 0) {
     // GetTentativeF0 (:122-131) and the 20 % sanity check of GetRefinedF0 (:203-204)
     double mean_f0 = 0.0;

@@ -161,6 +161,7 @@ synth_timebase_kernel(const double* __restrict__ f0_all, const int* __restrict__
 
 // dynamic shared memory: [ cbuf: cpad_size(N) double2 | sa: 2*(N/2+8) doubles (se | ar, later P) |
 //                          nz: (N/2+8) double2 | red: 96 doubles ]
+template <int LOG2N>      // 0: size given at run time (c.log2n)
 __global__ void __launch_bounds__(256)
 synth_pulse_kernel(const double* __restrict__ f0_all, const double* __restrict__ sp_all,
                    const double* __restrict__ ap_all, const int* __restrict__ f_off,
@@ -172,7 +173,9 @@ synth_pulse_kernel(const double* __restrict__ f0_all, const double* __restrict__
                    const double2* __restrict__ tw, const double* __restrict__ dc_remover,
                    SynthConst c, double* __restrict__ y_all) {
   extern __shared__ double2 smem2[];
-  const int N = 1 << c.log2n, half = N >> 1, log2n = c.log2n;
+  const int log2n = LOG2N > 0 ? LOG2N : c.log2n;
+  const int N = 1 << log2n, half = N >> 1;
+  constexpr int LM = LOG2N > 0 ? LOG2N - 1 : 0;
   double2* cbuf = smem2;
   double* cbufd = reinterpret_cast<double*>(cbuf);
   double* se = reinterpret_cast<double*>(cbuf + cpad_size(N));
@@ -225,7 +228,7 @@ synth_pulse_kernel(const double* __restrict__ f0_all, const double* __restrict__
     const double average = s1[0] / noise_size_raw;
     for (int i = tid; i < N; i += T)
       cbufd[rfft_in_slot(i, log2m)] = i < noise_size ? randn_from_u32(rn[i]) - average : 0.0;
-    fft_dit<false>(cbuf, log2m, tw);
+    fft_dit<LM, false, 256>(cbuf, log2m, tw);
     for (int k = tid; k <= half; k += T) nz[k] = rfft_bin(cbuf, log2m, k, tw);
   }
   __syncthreads();
@@ -241,7 +244,7 @@ synth_pulse_kernel(const double* __restrict__ f0_all, const double* __restrict__
     const int k = i <= half ? i : N - i;                                         // even extension
     cbuf[cpad(brev(i, log2n))] = make_double2(se[k], ar[k]);
   }
-  fft_dit<false>(cbuf, log2n, tw);
+  fft_dit<LOG2N, false, 256>(cbuf, log2n, tw);
   // fold (common.cpp:194-206) into registers, then transform B
   {
     double2 keep[8];
@@ -262,7 +265,7 @@ synth_pulse_kernel(const double* __restrict__ f0_all, const double* __restrict__
       if (i < N) cbuf[cpad(brev(i, log2n))] = keep[q];
     }
   }
-  fft_dit<false>(cbuf, log2n, tw);
+  fft_dit<LOG2N, false, 256>(cbuf, log2n, tw);
   // ---- minimum-phase spectra, time shift, noise product ---------------------------------------
   const double coefficient = div_rn(mul_rn(mul_rn(kTwoPi, p_shift[p]), (double)c.fs), (double)N);   // :128-129
   for (int k = tid; k <= half; k += T) {
@@ -298,7 +301,7 @@ synth_pulse_kernel(const double* __restrict__ f0_all, const double* __restrict__
     if (k > half) { Pv.y = -Pv.y; Av.y = -Av.y; }
     cbuf[cpad(brev(k, log2n))] = make_double2(Pv.x - Av.y, Pv.y + Av.x);
   }
-  fft_dit<true>(cbuf, log2n, tw);
+  fft_dit<LOG2N, true, 256>(cbuf, log2n, tw);
   // ---- fftshift, RemoveDCComponent (:73-82), mix (:214-217), overlap-add (:376-383) ----------
   double dc[1] = {0.0};
   if (periodic)
@@ -386,11 +389,19 @@ bool synthesis_run(Batch* b, const int* y_len) {
   const size_t smem = cpad_size(N) * sizeof(double2) + (size_t)(2 * (N / 2 + 8)) * sizeof(double) +
                       (size_t)(N / 2 + 8) * sizeof(double2) + 96 * sizeof(double);
   if (N / 256 > 8) { set_error("Synthesis: fft_size %d too large for the register fold", N); return false; }
-  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(synth_pulse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
   KernelTimer kt3("synth_pulse_kernel");
-  synth_pulse_kernel<<<(unsigned)total_p, 256, smem, st>>>(b->f0.p, b->sp.p, b->ap.p, b->f_off.p, b->f_len.p, b->y_off.p, b->y_len.p,
-                                                           d_poff.p, d_cnt.p, p_index.p, p_shift.p, p_vuv.p, p_utt.p, ctxp->d_randn,
-                                                           ctxp->d_twiddle, d_rem.p, c, b->y.p);
+#define WB_SP_LAUNCH(L)                                                                                             \
+  do {                                                                                                              \
+    WB_CUDA_OR_RETURN(cudaFuncSetAttribute(synth_pulse_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
+    synth_pulse_kernel<L><<<(unsigned)total_p, 256, smem, st>>>(b->f0.p, b->sp.p, b->ap.p, b->f_off.p, b->f_len.p, b->y_off.p, b->y_len.p, d_poff.p, d_cnt.p, p_index.p, p_shift.p, p_vuv.p, p_utt.p, ctxp->d_randn, ctxp->d_twiddle, d_rem.p, c, b->y.p); \
+  } while (0)
+  switch (log2n) {
+    case 10: WB_SP_LAUNCH(10); break;
+    case 11: WB_SP_LAUNCH(11); break;
+    case 12: WB_SP_LAUNCH(12); break;
+    default: WB_SP_LAUNCH(0); break;
+  }
+#undef WB_SP_LAUNCH
   WB_LAUNCH_CHECK(); kt3.stop();
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
   return true;

@@ -8,6 +8,7 @@ import sys
 
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+sort_key = {"samples": 3, "inst": 4, "shared": 5}[sys.argv[4] if len(sys.argv) > 4 else "samples"]
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "-k", "regex:" + kern],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
@@ -32,8 +33,8 @@ for r in rows:
             pass
 ts = sum(i[3] for i in items) or 1
 ti = sum(i[4] for i in items) or 1
-print("total samples %d, warp instructions %d" % (ts, ti))
+print("total samples %d, warp instructions %d, shared wavefronts %d (ideal %d)" % (ts, ti, sum(i[5] for i in items), sum(i[6] for i in items)))
 print("%-22s %5s %6s %6s %9s  %s" % ("file", "line", "smpl%", "inst%", "shm x/id", "source"))
-for it in sorted(items, key=lambda x: -x[3])[:top]:
-    print("%-22s %5d %5.1f%% %5.1f%% %4.1f      %s" % (it[0][:22], it[1], 100.0 * it[3] / ts, 100.0 * it[4] / ti,
-                                                   (it[5] / it[6]) if it[6] else 0.0, it[2][:110]))
+for it in sorted(items, key=lambda x: -x[sort_key])[:top]:
+    print("%-22s %5d %5.1f%% %5.1f%% %4.1f %5.1f%% %s" % (it[0][:22], it[1], 100.0 * it[3] / ts, 100.0 * it[4] / ti,
+                                                   (it[5] / it[6]) if it[6] else 0.0, 100.0 * it[5] / max(1, sum(i[5] for i in items)), it[2][:100]))
