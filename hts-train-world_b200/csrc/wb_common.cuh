@@ -48,6 +48,7 @@ struct Context {
   int device = -1;
   cudaStream_t stream = nullptr;
   double2* d_twiddle = nullptr;          // [kTwN/2 + 1]
+  float2* d_twiddle_f = nullptr;         // the same table rounded to FP32
   uint32_t* d_randn = nullptr;           // randn table: variate k = d_randn[k] / 2^28 - 6
   size_t randn_count = 0;
   int sm_count = 0;

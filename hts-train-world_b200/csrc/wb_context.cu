@@ -253,8 +253,13 @@ Context* ctx() {
     const long double a = -2.0L * 3.14159265358979323846264338327950288L * k / kTwN;
     tw[k] = make_double2((double)cosl(a), (double)sinl(a));
   }
+  std::vector<float2> twf(tw.size());
+  for (size_t k = 0; k < tw.size(); ++k) twf[k] = make_float2((float)tw[k].x, (float)tw[k].y);
   if (!WB_CUDA(cudaMalloc((void**)&g_ctx.d_twiddle, tw.size() * sizeof(double2))) ||
       !WB_CUDA(cudaMemcpy(g_ctx.d_twiddle, tw.data(), tw.size() * sizeof(double2),
+                          cudaMemcpyHostToDevice)) ||
+      !WB_CUDA(cudaMalloc((void**)&g_ctx.d_twiddle_f, twf.size() * sizeof(float2))) ||
+      !WB_CUDA(cudaMemcpy(g_ctx.d_twiddle_f, twf.data(), twf.size() * sizeof(float2),
                           cudaMemcpyHostToDevice))) {
     g_ctx_failed = true; return nullptr;
   }

@@ -15,6 +15,7 @@
 //   * the randn dither is read from the precomputed table at the offset the sequential
 //     reference would have reached (LoveTrain draws of all voiced frames first, then
 //     3 windows per processed frame).
+#include <stdlib.h>
 #include "wb_batch.h"
 #include "wb_fft.cuh"
 #include "wb_spectral.cuh"
@@ -238,7 +239,7 @@ __device__ __forceinline__ void select_low_sums(const double (&pa)[kVP], const d
 // dynamic shared memory: [ cbuf: cpad_size(Nd) double2 | cen: Hd+8 | pw: Hd+8 | red: 96 |
 //                          SelectScratch | coarse: kMaxBands+2 ]
 template <int LOG2ND, int THREADS>    // LOG2ND 0: size given at run time (c.log2nd)
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 2)
 d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __restrict__ frame_t,
                 const double* __restrict__ f0_in, const double* __restrict__ ap0,
                 const long long* __restrict__ rng_off, const long long* __restrict__ lt_totals,
@@ -483,7 +484,7 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
     const int hd = nd / 2;
     const size_t smem = d4c_cbuf_slots(nd) * sizeof(double2) + (size_t)(2 * (hd + 8) + 96) * sizeof(double) +
                         sizeof(SelectScratch) + (kMaxBands + 2) * sizeof(double);
-    const int threads = nd > 4096 ? 512 : 256;
+    const int threads = (nd > 4096 || getenv("WB_D4C_T512")) ? 512 : 256;
     if (hd / threads + 1 > kVP) { set_error("D4C: fft size %d too large", nd); return false; }
     KernelTimer kt2("d4c_main_kernel");
 #define WB_D4C_LAUNCH(L, TH)                                                                                        \
@@ -492,7 +493,8 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
     d4c_main_kernel<L, TH><<<total_frames, TH, smem, st>>>(u, frame_utt, frame_t, f0, d_ap0.p, offs_main.p, tot_lt.p, ctxp->d_randn, \
                                                            ctxp->d_twiddle, d_win.p, c, ap);                         \
   } while (0)
-    if (threads == 512) WB_D4C_LAUNCH(0, 512);
+    if (threads == 512 && c.log2nd == 12) WB_D4C_LAUNCH(12, 512);
+    else if (threads == 512) WB_D4C_LAUNCH(0, 512);
     else if (c.log2nd == 12) WB_D4C_LAUNCH(12, 256);
     else if (c.log2nd == 11) WB_D4C_LAUNCH(11, 256);
     else WB_D4C_LAUNCH(0, 256);

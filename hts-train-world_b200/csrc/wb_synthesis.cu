@@ -16,6 +16,7 @@
 //   D: the two responses come out of one inverse complex FFT of P + i A.
 // The noise of pulse i is table[pulse_index[i] - pulse_index[0] + n], so
 // the output is independent of pulse scheduling.  Overlap-add uses FP64 atomics (RED.ADD.F64).
+#include <stdlib.h>
 #include <algorithm>
 #include "wb_batch.h"
 #include "wb_fft.cuh"
@@ -159,165 +160,286 @@ synth_timebase_kernel(const double* __restrict__ f0_all, const int* __restrict__
   if (!WRITE && tid == 0) pulse_count[u] = carry_cnt;
 }
 
-// dynamic shared memory: [ cbuf: cpad_size(N) double2 | sa: 2*(N/2+8) doubles (se | ar, later P) |
-//                          nz: (N/2+8) double2 | red: 96 doubles ]
-template <int LOG2N>      // 0: size given at run time (c.log2n)
-__global__ void __launch_bounds__(256)
-synth_pulse_kernel(const double* __restrict__ f0_all, const double* __restrict__ sp_all,
-                   const double* __restrict__ ap_all, const int* __restrict__ f_off,
-                   const int* __restrict__ f_len, const long long* __restrict__ y_off,
-                   const int* __restrict__ y_len_all, const int* __restrict__ pulse_off,
-                   const int* __restrict__ pulse_cnt, const int* __restrict__ p_index,
-                   const double* __restrict__ p_shift, const unsigned char* __restrict__ p_vuv,
-                   const int* __restrict__ p_utt, const uint32_t* __restrict__ randn_tab,
-                   const double2* __restrict__ tw, const double* __restrict__ dc_remover,
-                   SynthConst c, double* __restrict__ y_all) {
+// ---- pulse classification -------------------------------------------------------------------
+// A pulse has a periodic response when it is voiced and its aperiodicity at DC is <= 0.999
+// (GetPeriodicResponse :110).  Pulses are split into two work lists: "periodic" pulses need
+// two minimum-phase spectra (periodic + aperiodic part), all others need one.  The pulse
+// kernel transforms two real sequences per complex FFT, so a periodic pulse is one work item
+// and two non-periodic pulses share one.
+struct PulseFrames { int fr_floor, fr_ceil; double interp; };
+__device__ __forceinline__ PulseFrames pulse_frames(int index, int fs, double frame_period_s, int n_frames) {
+  const double current_time = (double)index / (double)fs;
+  const double pos_f = current_time / frame_period_s;                 // :145-146, :164-165
+  PulseFrames r;
+  r.fr_floor = min(n_frames - 1, static_cast<int>(floor(pos_f)));
+  r.fr_ceil = min(n_frames - 1, static_cast<int>(ceil(pos_f)));
+  r.interp = pos_f - r.fr_floor;
+  return r;
+}
+__device__ __forceinline__ double safe_ap(double x) { return fmax(0.001, fmin(0.999999999999, x)); }   // common.h:111-113
+
+__global__ void synth_classify_kernel(const double* __restrict__ ap_all, const int* __restrict__ f_off,
+                                      const int* __restrict__ f_len, const int* __restrict__ p_index,
+                                      const unsigned char* __restrict__ p_vuv, const int* __restrict__ p_utt,
+                                      int total_p, SynthConst c, int* __restrict__ cnt2,
+                                      int* __restrict__ list_per, int* __restrict__ list_aper) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total_p) return;
+  bool periodic = false;
+  if (p_vuv[p]) {
+    const int u = p_utt[p];
+    const int half = (1 << c.log2n) >> 1;
+    const PulseFrames fr = pulse_frames(p_index[p], c.fs, c.frame_period_s, f_len[u]);
+    const double a0 = safe_ap(ap_all[((size_t)f_off[u] + fr.fr_floor) * (half + 1)]);
+    double ar;
+    if (fr.fr_floor == fr.fr_ceil) ar = a0 * a0;
+    else {
+      const double a1 = safe_ap(ap_all[((size_t)f_off[u] + fr.fr_ceil) * (half + 1)]);
+      const double m = add_rn(mul_rn(1.0 - fr.interp, a0), mul_rn(fr.interp, a1));
+      ar = m * m;
+    }
+    periodic = !(ar > 0.999);
+  }
+  if (periodic) list_per[atomicAdd(&cnt2[0], 1)] = p;
+  else list_aper[atomicAdd(&cnt2[1], 1)] = p;
+}
+
+// ---- one work item: two minimum-phase responses through four complex FFTs -----------------
+// Channel 0 / 1 of a periodic item: the periodic and the aperiodic response of one pulse.
+// Channel 0 / 1 of a pair item: the aperiodic responses of two non-periodic pulses.
+//   C: noise of both channels, n0 + i n1            -> spectra by Hermitian split
+//   A: even extensions of the log spectra, L0 + i L1 -> both cepstra (Re, Im)
+//   B: folded cepstra (common.cpp:194-206)           -> both analytic log spectra (split)
+//   D: inverse of Y0 + i Y1 (Hermitian extensions)   -> both responses (Re, Im)
+// C = float2 by default: every quantity here is a log spectrum, a cepstrum, unit-variance
+// noise or a response that is accumulated into y, and 2^-24 relative to the largest element
+// leaves the resynthesis > 90 dB above the error (tolerance: 60 dB).  Pulse positions, the
+// interpolation of sp / ap and the overlap-add itself stay in FP64.
+// dynamic shared memory: [ cbuf: cpad_size(N) C | nzb: cpad_size(N) C | red: 96 doubles ]
+struct ChanInfo {
+  int p, index, noise_raw, noise_size, utt, y_len, fr_floor, fr_ceil;
+  bool vuv;
+  double interp;
+  size_t row0;
+  const uint32_t* rn;
+};
+
+__device__ __forceinline__ ChanInfo chan_info(int p, const int* __restrict__ p_index, const int* __restrict__ p_utt,
+                                              const unsigned char* __restrict__ p_vuv,
+                                              const int* __restrict__ pulse_off, const int* __restrict__ pulse_cnt,
+                                              const int* __restrict__ f_off, const int* __restrict__ f_len,
+                                              const int* __restrict__ y_len_all, const uint32_t* __restrict__ randn_tab,
+                                              const SynthConst& c, int N) {
+  ChanInfo ci;
+  ci.p = p;
+  if (p < 0) { ci.index = 0; ci.noise_raw = 0; ci.noise_size = 0; ci.utt = 0; ci.y_len = 0; ci.fr_floor = ci.fr_ceil = 0;
+               ci.vuv = false; ci.interp = 0.0; ci.row0 = 0; ci.rn = randn_tab; return ci; }
+  const int u = p_utt[p];
+  const int first = pulse_off[u], last = first + pulse_cnt[u] - 1;
+  ci.utt = u;
+  ci.index = p_index[p];
+  ci.noise_raw = p_index[min(last, p + 1)] - ci.index;                    // :370-371
+  ci.noise_size = min(ci.noise_raw, N);                                   // memory guard
+  ci.vuv = p_vuv[p] != 0;
+  ci.y_len = y_len_all[u];
+  const PulseFrames fr = pulse_frames(ci.index, c.fs, c.frame_period_s, f_len[u]);
+  ci.fr_floor = fr.fr_floor; ci.fr_ceil = fr.fr_ceil; ci.interp = fr.interp;
+  ci.row0 = (size_t)f_off[u];
+  ci.rn = randn_tab + (ci.index - p_index[first]);
+  return ci;
+}
+
+// interpolated spectral envelope and squared aperiodicity of bin k (:140-178)
+__device__ __forceinline__ void envelope_at(const ChanInfo& ci, const double* __restrict__ sp_all,
+                                            const double* __restrict__ ap_all, int half, int k, double* s_out,
+                                            double* a_out) {
+  const size_t r0 = (ci.row0 + ci.fr_floor) * (half + 1) + k, r1 = (ci.row0 + ci.fr_ceil) * (half + 1) + k;
+  const double a0 = safe_ap(ap_all[r0]);
+  if (ci.fr_floor == ci.fr_ceil) {
+    *s_out = fabs(sp_all[r0]);
+    *a_out = a0 * a0;
+  } else {
+    const double a1 = safe_ap(ap_all[r1]);
+    *s_out = add_rn(mul_rn(1.0 - ci.interp, fabs(sp_all[r0])), mul_rn(ci.interp, fabs(sp_all[r1])));
+    const double m = add_rn(mul_rn(1.0 - ci.interp, a0), mul_rn(ci.interp, a1));
+    *a_out = m * m;
+  }
+}
+
+__device__ __forceinline__ void exp_sincos(double re, double im, double* er, double* ei) {
+  const double e = exp(re); double sn, cs; sincos(im, &sn, &cs); *er = e * cs; *ei = e * sn;
+}
+__device__ __forceinline__ void exp_sincos(float re, float im, float* er, float* ei) {
+  const float e = expf(re); float sn, cs; sincosf(im, &sn, &cs); *er = e * cs; *ei = e * sn;
+}
+__device__ __forceinline__ double log_of(double v, double) { return log(v); }
+__device__ __forceinline__ float log_of(double v, float) { return logf(static_cast<float>(v)); }
+
+template <int LOG2N, typename C>      // LOG2N 0: size given at run time (c.log2n)
+__global__ void __launch_bounds__(256, 3)
+synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ ap_all,
+                  const int* __restrict__ f_off, const int* __restrict__ f_len,
+                  const long long* __restrict__ y_off, const int* __restrict__ y_len_all,
+                  const int* __restrict__ pulse_off, const int* __restrict__ pulse_cnt,
+                  const int* __restrict__ p_index, const double* __restrict__ p_shift,
+                  const unsigned char* __restrict__ p_vuv, const int* __restrict__ p_utt,
+                  const int* __restrict__ list_per, const int* __restrict__ list_aper, int n_per, int n_aper,
+                  const uint32_t* __restrict__ randn_tab, const C* __restrict__ tw,
+                  const double* __restrict__ dc_remover, SynthConst c, double* __restrict__ y_all) {
+  using R = scalar_t<C>;
   extern __shared__ double2 smem2[];
   const int log2n = LOG2N > 0 ? LOG2N : c.log2n;
   const int N = 1 << log2n, half = N >> 1;
-  constexpr int LM = LOG2N > 0 ? LOG2N - 1 : 0;
-  double2* cbuf = smem2;
-  double* cbufd = reinterpret_cast<double*>(cbuf);
-  double* se = reinterpret_cast<double*>(cbuf + cpad_size(N));
-  double* ar = se + half + 8;
-  double2* Pk = reinterpret_cast<double2*>(se);
-  double2* nz = reinterpret_cast<double2*>(ar + half + 8);
-  double* red = reinterpret_cast<double*>(nz + half + 8);
-  const int tid = threadIdx.x, T = blockDim.x;
-  const int p = blockIdx.x;
-  const int u = p_utt[p];
-  const int first = pulse_off[u], last = first + pulse_cnt[u] - 1;
-  const int index = p_index[p];
-  const int noise_size_raw = p_index[min(last, p + 1)] - index;           // :370-371
-  const int noise_size = min(noise_size_raw, N);                          // memory guard
-  const bool vuv = p_vuv[p] != 0;
-  const int n_frames = f_len[u];
-  const size_t row0 = (size_t)f_off[u];
-  const double current_time = (double)index / (double)c.fs;
-  // ---- GetSpectralEnvelope / GetAperiodicRatio (:140-178) ------------------------------------
-  const double pos_f = current_time / c.frame_period_s;
-  const int fr_floor = min(n_frames - 1, static_cast<int>(floor(pos_f)));
-  const int fr_ceil = min(n_frames - 1, static_cast<int>(ceil(pos_f)));
-  const double interp = pos_f - fr_floor;
-  const double* __restrict__ sp0 = sp_all + (row0 + fr_floor) * (half + 1);
-  const double* __restrict__ sp1 = sp_all + (row0 + fr_ceil) * (half + 1);
-  const double* __restrict__ ap0 = ap_all + (row0 + fr_floor) * (half + 1);
-  const double* __restrict__ ap1 = ap_all + (row0 + fr_ceil) * (half + 1);
+  constexpr int T = 256;
+  constexpr int kQ = 9;                 // (N/2 + 1) / T rounded up, N <= 4096
+  C* cbuf = reinterpret_cast<C*>(smem2);
+  C* nzb = cbuf + cpad_size(N);
+  double* red = reinterpret_cast<double*>(nzb + cpad_size(N));
+  const int tid = threadIdx.x;
+  const int item = blockIdx.x;
+  const bool per_item = item < n_per;
+  int pa, pb;
+  if (per_item) { pa = pb = list_per[item]; }
+  else {
+    const int j = 2 * (item - n_per);
+    if (j >= n_aper) return;
+    pa = list_aper[j];
+    pb = j + 1 < n_aper ? list_aper[j + 1] : -1;
+  }
+  const ChanInfo c0 = chan_info(pa, p_index, p_utt, p_vuv, pulse_off, pulse_cnt, f_off, f_len, y_len_all, randn_tab, c, N);
+  const ChanInfo c1 = per_item ? c0 : chan_info(pb, p_index, p_utt, p_vuv, pulse_off, pulse_cnt, f_off, f_len, y_len_all, randn_tab, c, N);
+
+  // ---- log spectra (:45-51, :115-117), written as the even extension in bit-reversed order ----
   for (int k = tid; k <= half; k += T) {
+    R l0 = 0, l1 = 0;
     double s, a;
-    const double a0 = fmax(0.001, fmin(0.999999999999, ap0[k]));          // common.h:111-113
-    if (fr_floor == fr_ceil) {
-      s = fabs(sp0[k]);
-      a = a0 * a0;
+    envelope_at(c0, sp_all, ap_all, half, k, &s, &a);
+    if (per_item) {
+      l0 = log_of(s * (1.0 - a) + kMySafeGuardMinimum, R()) / 2;
+      l1 = log_of(s * a, R()) / 2;
     } else {
-      const double a1 = fmax(0.001, fmin(0.999999999999, ap1[k]));
-      s = add_rn(mul_rn(1.0 - interp, fabs(sp0[k])), mul_rn(interp, fabs(sp1[k])));
-      const double m = add_rn(mul_rn(1.0 - interp, a0), mul_rn(interp, a1));
-      a = m * m;
+      l0 = log_of(c0.vuv ? s * a : s, R()) / 2;
+      if (pb >= 0) {
+        envelope_at(c1, sp_all, ap_all, half, k, &s, &a);
+        l1 = log_of(c1.vuv ? s * a : s, R()) / 2;
+      }
     }
-    se[k] = s;
-    ar[k] = a;
+    const C z = mk2(l0, l1);
+    cbuf[cpad(brev(k, log2n))] = z;
+    if (k > 0 && k < half) cbuf[cpad(brev(N - k, log2n))] = z;
   }
-  // ---- GetNoiseSpectrum (:19-33): transform C ------------------------------------------------
+  // ---- noise of both channels (:19-33) -----------------------------------------------------------
   {
-    const int log2m = log2n - 1;
-    const uint32_t* __restrict__ rn = randn_tab + (index - p_index[first]);
-    double s1[1] = {0.0};
-    for (int i = tid; i < noise_size; i += T) s1[0] += randn_from_u32(rn[i]);
-    block_sum<1>(s1, red);
-    const double average = s1[0] / noise_size_raw;
-    for (int i = tid; i < N; i += T)
-      cbufd[rfft_in_slot(i, log2m)] = i < noise_size ? randn_from_u32(rn[i]) - average : 0.0;
-    fft_dit<LM, false, 256>(cbuf, log2m, tw);
-    for (int k = tid; k <= half; k += T) nz[k] = rfft_bin(cbuf, log2m, k, tw);
+    double s2[2] = {0.0, 0.0};
+    if (!per_item) for (int i = tid; i < c0.noise_size; i += T) s2[0] += randn_from_u32(c0.rn[i]);
+    for (int i = tid; i < c1.noise_size; i += T) s2[1] += randn_from_u32(c1.rn[i]);
+    block_sum<2>(s2, red);
+    const double av0 = s2[0] / c0.noise_raw, av1 = s2[1] / c1.noise_raw;
+    for (int i = tid; i < N; i += T) {
+      const R n0 = (!per_item && i < c0.noise_size) ? static_cast<R>(randn_from_u32(c0.rn[i]) - av0) : static_cast<R>(0);
+      const R n1 = i < c1.noise_size ? static_cast<R>(randn_from_u32(c1.rn[i]) - av1) : static_cast<R>(0);
+      nzb[cpad(brev(i, log2n))] = mk2(n0, n1);
+    }
   }
-  __syncthreads();
-  const bool periodic = vuv && !(ar[0] > 0.999);                          // :110
-  // ---- transform A: cepstra of the two log spectra -----------------------------------------------
-  for (int k = tid; k <= half; k += T) {
-    const double s = se[k], a = ar[k];
-    se[k] = periodic ? log(s * (1.0 - a) + kMySafeGuardMinimum) / 2.0 : 0.0;   // :115-117
-    ar[k] = vuv ? log(s * a) / 2.0 : log(s) / 2.0;                               // :45-51
-  }
-  __syncthreads();
-  for (int i = tid; i < N; i += T) {
-    const int k = i <= half ? i : N - i;                                         // even extension
-    cbuf[cpad(brev(i, log2n))] = make_double2(se[k], ar[k]);
-  }
-  fft_dit<LOG2N, false, 256>(cbuf, log2n, tw);
-  // fold (common.cpp:194-206) into registers, then transform B
+  fft_dit<LOG2N, false, T, 4>(nzb, log2n, tw);       // C
+  fft_dit<LOG2N, false, T, 4>(cbuf, log2n, tw);      // A
+  // ---- fold the cepstra (common.cpp:194-206) -----------------------------------------------------
   {
-    double2 keep[8];
+    C keep[kQ];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < kQ; ++q) {
       const int i = tid + q * T;
-      double2 z = make_double2(0.0, 0.0);
+      C z = mk2(static_cast<R>(0), static_cast<R>(0));
       if (i <= half) {
         z = cbuf[cpad(i)];
-        if (i > 0 && i < half) { z.x *= 2.0; z.y *= 2.0; }
+        if (i > 0 && i < half) { z.x *= 2; z.y *= 2; }
       }
       keep[q] = z;
     }
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < kQ; ++q) {
       const int i = tid + q * T;
-      if (i < N) cbuf[cpad(brev(i, log2n))] = keep[q];
+      if (i <= half) cbuf[cpad(brev(i, log2n))] = keep[q];
+    }
+    for (int i = half + 1 + tid; i < N; i += T) cbuf[cpad(brev(i, log2n))] = mk2(static_cast<R>(0), static_cast<R>(0));
+  }
+  fft_dit<LOG2N, false, T, 4>(cbuf, log2n, tw);      // B
+  // ---- minimum-phase spectra, time shift / noise product (:56-65, :88-100, :120-131) ------------
+  {
+    const double coefficient = per_item
+        ? div_rn(mul_rn(mul_rn(kTwoPi, p_shift[pa]), (double)c.fs), (double)N) : 0.0;     // :128-129
+    const R inv_n = static_cast<R>(1.0 / N), hlf = static_cast<R>(0.5);
+    C y0[kQ], y1[kQ];
+#pragma unroll
+    for (int q = 0; q < kQ; ++q) {
+      const int k = tid + q * T;
+      y0[q] = mk2(static_cast<R>(0), static_cast<R>(0));
+      y1[q] = y0[q];
+      if (k > half) continue;
+      const int km = (N - k) & (N - 1);
+      const C A = cbuf[cpad(k)], B = cbuf[cpad(km)];
+      const C Zn = nzb[cpad(k)], Zm = nzb[cpad(km)];
+      // S0 = (A + conj B)/2, S1 = (A - conj B)/(2i); likewise for the noise spectra
+      const R s0r = hlf * (A.x + B.x), s0i = hlf * (A.y - B.y);
+      const R s1r = hlf * (A.y + B.y), s1i = hlf * (B.x - A.x);
+      const C X0 = mk2(hlf * (Zn.x + Zm.x), hlf * (Zn.y - Zm.y));
+      const C X1 = mk2(hlf * (Zn.y + Zm.y), hlf * (Zm.x - Zn.x));
+      C m0, m1;
+      exp_sincos(s0r * inv_n, s0i * inv_n, &m0.x, &m0.y);
+      exp_sincos(s1r * inv_n, s1i * inv_n, &m1.x, &m1.y);
+      if (per_item) {
+        // cos(c k) - j sqrt(1 - cos^2(c k))  (:93-96; the square root is |sin|)
+        double sn, cs;
+        sincos(coefficient * k, &sn, &cs);
+        y0[q] = cmul(m0, mk2(static_cast<R>(cs), static_cast<R>(-fabs(sn))));
+      } else {
+        y0[q] = cmul(m0, X0);
+      }
+      y1[q] = (per_item || pb >= 0) ? cmul(m1, X1) : mk2(static_cast<R>(0), static_cast<R>(0));
+    }
+    __syncthreads();
+    // D input: Y0 + i Y1 at bin k, conj(Y0) + i conj(Y1) at bin N - k; Im of bins 0 and N/2
+    // is ignored by the reference's c2r (W/src/fft.cpp:27-34)
+#pragma unroll
+    for (int q = 0; q < kQ; ++q) {
+      const int k = tid + q * T;
+      if (k > half) continue;
+      C a = y0[q], b = y1[q];
+      if (k == 0 || k == half) { a.y = 0; b.y = 0; }
+      cbuf[cpad(brev(k, log2n))] = mk2(a.x - b.y, a.y + b.x);
+      if (k > 0 && k < half) cbuf[cpad(brev(N - k, log2n))] = mk2(a.x + b.y, b.x - a.y);
     }
   }
-  fft_dit<LOG2N, false, 256>(cbuf, log2n, tw);
-  // ---- minimum-phase spectra, time shift, noise product ---------------------------------------
-  const double coefficient = div_rn(mul_rn(mul_rn(kTwoPi, p_shift[p]), (double)c.fs), (double)N);   // :128-129
-  for (int k = tid; k <= half; k += T) {
-    const double2 A = cbuf[cpad(k)];
-    const double2 B = cbuf[cpad((N - k) & (N - 1))];
-    // S1 = (A + conj B)/2, S2 = (A - conj B)/(2i)
-    const double s1r = 0.5 * (A.x + B.x), s1i = 0.5 * (A.y - B.y);
-    const double s2r = 0.5 * (A.y + B.y), s2i = 0.5 * (B.x - A.x);
-    double2 Pv = make_double2(0.0, 0.0);
-    if (periodic) {
-      const double e1 = exp(s1r / N);
-      double sn, cs;
-      sincos(s1i / N, &sn, &cs);
-      const double mr = e1 * cs, mi = e1 * sn;
-      const double re2 = cos(coefficient * k);
-      const double im2 = sqrt(1.0 - re2 * re2);                          // :95 (always >= 0)
-      Pv = make_double2(mr * re2 + mi * im2, mi * re2 - mr * im2);
-    }
-    const double e2 = exp(s2r / N);
-    double sn2, cs2;
-    sincos(s2i / N, &sn2, &cs2);
-    const double2 M2 = make_double2(e2 * cs2, e2 * sn2);
-    const double2 Z = nz[k];
-    nz[k] = make_double2(M2.x * Z.x - M2.y * Z.y, M2.x * Z.y + M2.y * Z.x);   // :56-65
-    Pk[k] = Pv;
-  }
-  __syncthreads();
-  // ---- transform D: inverse of P + i A (Hermitian extensions; Im of bins 0 and N/2 ignored) ---
-  for (int k = tid; k < N; k += T) {
-    const int kk = k <= half ? k : N - k;
-    double2 Pv = Pk[kk], Av = nz[kk];
-    if (kk == 0 || kk == half) { Pv.y = 0.0; Av.y = 0.0; }
-    if (k > half) { Pv.y = -Pv.y; Av.y = -Av.y; }
-    cbuf[cpad(brev(k, log2n))] = make_double2(Pv.x - Av.y, Pv.y + Av.x);
-  }
-  fft_dit<LOG2N, true, 256>(cbuf, log2n, tw);
-  // ---- fftshift, RemoveDCComponent (:73-82), mix (:214-217), overlap-add (:376-383) ----------
-  double dc[1] = {0.0};
-  if (periodic)
+  fft_dit<LOG2N, true, T, 4>(cbuf, log2n, tw);       // D
+  // ---- fftshift, RemoveDCComponent (:73-82), mix (:214-217), overlap-add (:376-383) -------------
+  if (per_item) {
+    double dc[1] = {0.0};
     for (int i = tid; i < half; i += T) dc[0] += cbuf[cpad(i)].x;        // shifted [N/2, N) = raw [0, N/2)
-  block_sum<1>(dc, red);
-  const double sqrt_noise = sqrt((double)noise_size_raw);
-  const int y_len = y_len_all[u];
-  double* __restrict__ y = y_all + y_off[u];
-  for (int jj = tid; jj < N; jj += T) {
-    const int raw = jj < half ? jj + half : jj - half;                   // fftshift
-    const double2 v = cbuf[cpad(raw)];
-    double pr = 0.0;
-    if (periodic) pr = jj < half ? -dc[0] * dc_remover[jj] : v.x - dc[0] * dc_remover[jj];
-    const double r = (pr * sqrt_noise + v.y) / N;
-    const int oi = jj + index - half + 1;
-    if (oi >= 0 && oi <= y_len - 1) atomicAdd(&y[oi], r);
+    block_sum<1>(dc, red);
+    const double sqrt_noise = sqrt((double)c0.noise_raw);
+    double* __restrict__ y = y_all + y_off[c0.utt];
+    for (int jj = tid; jj < N; jj += T) {
+      const int raw = jj < half ? jj + half : jj - half;                 // fftshift
+      const C v = cbuf[cpad(raw)];
+      const double pr = jj < half ? -dc[0] * dc_remover[jj] : (double)v.x - dc[0] * dc_remover[jj];
+      const double r = (pr * sqrt_noise + (double)v.y) / N;
+      const int oi = jj + c0.index - half + 1;
+      if (oi >= 0 && oi <= c0.y_len - 1) atomicAdd(&y[oi], r);
+    }
+  } else {
+    double* __restrict__ ya = y_all + y_off[c0.utt];
+    double* __restrict__ yb = y_all + y_off[c1.utt];
+    for (int jj = tid; jj < N; jj += T) {
+      const int raw = jj < half ? jj + half : jj - half;
+      const C v = cbuf[cpad(raw)];
+      const int oa = jj + c0.index - half + 1;
+      if (oa >= 0 && oa <= c0.y_len - 1) atomicAdd(&ya[oa], (double)v.x / N);
+      if (pb >= 0) {
+        const int ob = jj + c1.index - half + 1;
+        if (ob >= 0 && ob <= c1.y_len - 1) atomicAdd(&yb[ob], (double)v.y / N);
+      }
+    }
   }
 }
 
@@ -386,20 +508,40 @@ bool synthesis_run(Batch* b, const int* y_len) {
   }
   for (int i = 0; i < N / 2; ++i) { rem[i] /= dc_component; rem[N - i - 1] = rem[i]; }
   WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_rem.p, rem.data(), N * sizeof(double), cudaMemcpyHostToDevice, st), false);
-  const size_t smem = cpad_size(N) * sizeof(double2) + (size_t)(2 * (N / 2 + 8)) * sizeof(double) +
-                      (size_t)(N / 2 + 8) * sizeof(double2) + 96 * sizeof(double);
-  if (N / 256 > 8) { set_error("Synthesis: fft_size %d too large for the register fold", N); return false; }
+  // classify the pulses into periodic / non-periodic work lists
+  DevBuf<int> d_cnt2, list_per, list_aper;
+  if (!d_cnt2.alloc(2) || !list_per.alloc(total_p) || !list_aper.alloc(total_p)) return false;
+  WB_CUDA_OR_RETURN(cudaMemsetAsync(d_cnt2.p, 0, 2 * sizeof(int), st), false);
+  synth_classify_kernel<<<(unsigned)((total_p + 255) / 256), 256, 0, st>>>(b->ap.p, b->f_off.p, b->f_len.p, p_index.p, p_vuv.p,
+                                                                          p_utt.p, (int)total_p, c, d_cnt2.p, list_per.p, list_aper.p);
+  WB_LAUNCH_CHECK();
+  int h_cnt2[2] = {0, 0};
+  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_cnt2, d_cnt2.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st), false);
+  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  const int n_per = h_cnt2[0], n_aper = h_cnt2[1];
+  const unsigned n_items = (unsigned)(n_per + (n_aper + 1) / 2);
+  static const bool fp64 = getenv("WB_SYNTH_FP64") != nullptr;      // debugging aid: all four transforms in FP64
+  const size_t smem = 2 * cpad_size(N) * (fp64 ? sizeof(double2) : sizeof(float2)) + 96 * sizeof(double);
+  if (N / 2 / 256 + 1 > 9) { set_error("Synthesis: fft_size %d too large for the register fold", N); return false; }
   KernelTimer kt3("synth_pulse_kernel");
-#define WB_SP_LAUNCH(L)                                                                                             \
+#define WB_SP_LAUNCH(L, CT, TW)                                                                                     \
   do {                                                                                                              \
-    WB_CUDA_OR_RETURN(cudaFuncSetAttribute(synth_pulse_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
-    synth_pulse_kernel<L><<<(unsigned)total_p, 256, smem, st>>>(b->f0.p, b->sp.p, b->ap.p, b->f_off.p, b->f_len.p, b->y_off.p, b->y_len.p, d_poff.p, d_cnt.p, p_index.p, p_shift.p, p_vuv.p, p_utt.p, ctxp->d_randn, ctxp->d_twiddle, d_rem.p, c, b->y.p); \
+    WB_CUDA_OR_RETURN(cudaFuncSetAttribute(synth_item_kernel<L, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
+    synth_item_kernel<L, CT><<<n_items, 256, smem, st>>>(b->sp.p, b->ap.p, b->f_off.p, b->f_len.p, b->y_off.p, b->y_len.p, d_poff.p, d_cnt.p, \
+        p_index.p, p_shift.p, p_vuv.p, p_utt.p, list_per.p, list_aper.p, n_per, n_aper, ctxp->d_randn, TW, d_rem.p, c, b->y.p); \
   } while (0)
-  switch (log2n) {
-    case 10: WB_SP_LAUNCH(10); break;
-    case 11: WB_SP_LAUNCH(11); break;
-    case 12: WB_SP_LAUNCH(12); break;
-    default: WB_SP_LAUNCH(0); break;
+  if (fp64) {
+    switch (log2n) {
+      case 11: WB_SP_LAUNCH(11, double2, ctxp->d_twiddle); break;
+      default: WB_SP_LAUNCH(0, double2, ctxp->d_twiddle); break;
+    }
+  } else {
+    switch (log2n) {
+      case 10: WB_SP_LAUNCH(10, float2, ctxp->d_twiddle_f); break;
+      case 11: WB_SP_LAUNCH(11, float2, ctxp->d_twiddle_f); break;
+      case 12: WB_SP_LAUNCH(12, float2, ctxp->d_twiddle_f); break;
+      default: WB_SP_LAUNCH(0, float2, ctxp->d_twiddle_f); break;
+    }
   }
 #undef WB_SP_LAUNCH
   WB_LAUNCH_CHECK(); kt3.stop();
