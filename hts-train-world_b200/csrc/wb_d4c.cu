@@ -26,7 +26,6 @@ namespace {
 
 constexpr int kHanning = 1, kBlackman = 2;
 constexpr int kMaxBands = 8;
-constexpr int kVP = 9;        // power values per thread kept in registers during selection
 
 __device__ __forceinline__ int d4c_hwl(double ratio, int fs, double f0) {
   return matlab_round(div_rn(div_rn(mul_rn(ratio, (double)fs), f0), 2.0));   // d4c.cpp:55-56
@@ -128,115 +127,134 @@ __global__ void d4c_main_count_kernel(const double* __restrict__ f0, const doubl
   counts[f] = 3LL * (2LL * d4c_hwl(4.0, fs, fmax(kFloorF0D4C, v)) + 1);
 }
 
-// Exact sum of everything below the K-th largest of the thread-distributed non-negative
-// values pa / pb (two independent sets; entry j of a thread is valid when bit j of `valid` is
-// set).  MSB-first radix selection on the IEEE bit patterns (order-isomorphic to the values
-// for non-negative doubles) with 12-bit digits: every pass histograms the digit of the keys
-// that still match the prefix into shared memory (`hist`, 2 x 4096 ints, carved out of the FFT
-// buffer, which is idle here), locates the bin that holds the K-th largest with one block-wide
-// suffix scan and narrows the prefix.  The loop ends as soon as all keys matching the prefix
-// belong to the top set (always the case once a single candidate is left), typically after
-// 2-3 passes instead of the 63 one-bit passes of a bitwise search.
-// Result: low[s] = sum of the (count - K) smallest values, tot[s] = sum of all.
-// the FFT buffer doubles as the selection histogram (2 x 4096 ints = 2048 double2 slots)
-__host__ __device__ constexpr int d4c_cbuf_slots(int nd) { return cpad_size(nd) > 2048 ? cpad_size(nd) : 2048; }
-constexpr int kSelDigitBits = 12;
-constexpr int kSelBins = 1 << kSelDigitBits;
+// ---- coarse aperiodicity working set ---------------------------------------------------------
+// The band spectra (GetCoarseAperiodicity :192-223) are computed in FP32: each is the FFT of
+// a Nuttall-windowed slice of the static group delay, and only the ratio
+// (sum of all but the boundary+1 largest powers) / (sum of all powers) is used, so an FFT
+// error of 2^-24 relative to the largest bin moves the aperiodicity by ~1e-7 (tolerance 1e-4).
+// Layout inside the [cbuf | pw] region (bytes): [0, fb) FP32 FFT buffer, reused as the
+// selection histograms [0, nbands * 2048 * 4); then nbands power arrays of Hd + 4 floats.
+constexpr int kSelBins = 2048;          // 11-bit digits of the 31-bit float keys
+constexpr int kMaxSets = 6;
+__host__ __device__ constexpr int d4c_band_p_off(int nd, int nbands) {
+  return ((cpad_size(nd) * 8 > nbands * kSelBins * 4 ? cpad_size(nd) * 8 : nbands * kSelBins * 4) + 15) & ~15;
+}
+__host__ __device__ constexpr int d4c_cbuf_slots(int nd, int nbands) {   // double2 slots of cbuf
+  const int need = d4c_band_p_off(nd, nbands) + nbands * (nd / 2 + 4) * 4 - (nd / 2 + 8) * 8;   // pw follows cbuf
+  const int need_slots = (need + 15) / 16;
+  return cpad_size(nd) > need_slots ? cpad_size(nd) : need_slots;
+}
 
 struct SelectScratch {
-  unsigned long long wsum[32];
-  int digit[2], above[2], cand[2];
+  unsigned long long wsum[2][32];
+  int digit[kMaxSets], above[kMaxSets], cand[kMaxSets];
 };
 
-__device__ __forceinline__ void select_low_sums(const double (&pa)[kVP], const double (&pb)[kVP],
-                                                unsigned valid, int K, int* hist, SelectScratch* sc,
-                                                double* red, double (&low)[2], double (&tot)[2]) {
-  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
-  unsigned long long pre[2] = {0ull, 0ull};          // decided high bits of the K-th largest key
-  unsigned long long mask_hi = 0ull;                 // which bits of `pre` are decided
-  int k_rem[2] = {K, K};
-  bool done[2] = {false, false};
-  const int bins_per_thread = kSelBins / T;          // T in {256, 512}
-  // bin b = t * bins_per_thread + q lives at [q * T + t]: a thread's own bins are conflict-free
-  const int bpt_shift = 31 - __clz(bins_per_thread);
-  auto hslot = [=](int bin) { return (bin & (bins_per_thread - 1)) * T + (bin >> bpt_shift); };
-  for (int shift = 63 - kSelDigitBits; ; shift -= kSelDigitBits) {
+// Exact sum of everything below the K-th largest of each of `nsets` arrays of n non-negative
+// floats (P + s * pstride).  MSB-first radix selection on the IEEE bit patterns (order-
+// isomorphic to the values for non-negative floats) with 11-bit digits: every pass histograms
+// the digit of the keys that still match the decided prefix, finds the bin holding the K-th
+// largest with one block-wide suffix scan (all sets packed into two 64-bit words, 21 bits
+// each) and narrows the prefix.  A set is finished as soon as all keys matching its prefix
+// belong to the top set (always true once one candidate is left): 2 passes typically, 3 at
+// most -- instead of the reference's std::sort of every band (25 % of its CPU time).
+// Result: low[s] = sum of the (n - K) smallest values, tot[s] = sum of all (both in FP64).
+template <int T>
+__device__ __forceinline__ void select_low_sums(const float* __restrict__ P, int pstride, int nsets, int n,
+                                                int K, int* hist, SelectScratch* sc, double* red,
+                                                double* low, double* tot) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int nw = T >> 5, BPT = kSelBins / T;
+  // bin b = t * BPT + q lives at [q * T + t]: a thread's own bins are conflict-free
+  auto hslot = [](unsigned bin) { return (int)((bin & (BPT - 1)) * T + (bin / BPT)); };
+  unsigned pre[kMaxSets], mask_hi = 0u;
+  int k_rem[kMaxSets];
+  bool done[kMaxSets];
+#pragma unroll
+  for (int s = 0; s < kMaxSets; ++s) { pre[s] = 0u; k_rem[s] = K; done[s] = s >= nsets; }
+  for (int shift = 31 - 11; ; shift -= 11) {
     const int sh = shift < 0 ? 0 : shift;
-    const int width = shift < 0 ? kSelDigitBits + shift : kSelDigitBits;
-    const int nbins = 1 << width;
-    const unsigned long long dmask = (unsigned long long)(nbins - 1);
-    for (int i = tid; i < 2 * kSelBins / 4; i += T) reinterpret_cast<int4*>(hist)[i] = make_int4(0, 0, 0, 0);
+    const unsigned dmask = (1u << (shift < 0 ? 11 + shift : 11)) - 1u;
+    for (int i = tid; i < nsets * kSelBins / 4; i += T) reinterpret_cast<int4*>(hist)[i] = make_int4(0, 0, 0, 0);
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < kVP; ++j) {
-      if (!((valid >> j) & 1u)) continue;
-      const unsigned long long ka = (unsigned long long)__double_as_longlong(pa[j]);
-      const unsigned long long kb = (unsigned long long)__double_as_longlong(pb[j]);
-      if (!done[0] && (ka & mask_hi) == pre[0]) atomicAdd(&hist[hslot((int)((ka >> sh) & dmask))], 1);
-      if (!done[1] && (kb & mask_hi) == pre[1]) atomicAdd(&hist[kSelBins + hslot((int)((kb >> sh) & dmask))], 1);
+    for (int s = 0; s < kMaxSets; ++s) {
+      if (done[s]) continue;
+      const float* __restrict__ ps = P + s * pstride;
+      for (int k = tid; k < n; k += T) {
+        const unsigned key = __float_as_uint(ps[k]);
+        if ((key & mask_hi) == pre[s]) atomicAdd(&hist[s * kSelBins + hslot((key >> sh) & dmask)], 1);
+      }
     }
     __syncthreads();
-    // counts of this thread's bins; thread t owns bins [t * bpt, (t + 1) * bpt) of both sets
-    const int b_lo = tid * bins_per_thread;
-    unsigned int mine[2] = {0u, 0u};
-    for (int q = 0; q < bins_per_thread; ++q) { mine[0] += hist[q * T + tid]; mine[1] += hist[kSelBins + q * T + tid]; }
-    // suffix sum over threads (bins above mine), both sets packed in one 64-bit word
-    const unsigned long long v = (unsigned long long)mine[0] | ((unsigned long long)mine[1] << 32);
-    unsigned long long inc = v;
+    // per-thread bin totals, suffix-summed over threads; 3 sets x 21 bits per 64-bit word
+    unsigned mine[kMaxSets];
+    unsigned long long v[2] = {0ull, 0ull};
+#pragma unroll
+    for (int s = 0; s < kMaxSets; ++s) {
+      mine[s] = 0u;
+      if (done[s]) continue;
+#pragma unroll
+      for (int q = 0; q < BPT; ++q) mine[s] += hist[s * kSelBins + q * T + tid];
+      v[s / 3] |= (unsigned long long)mine[s] << (21 * (s % 3));
+    }
+    unsigned long long inc[2] = {v[0], v[1]};
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long t = __shfl_down_sync(0xffffffffu, inc, o);
-      if (lane + o < 32) inc += t;
+      const unsigned long long t0 = __shfl_down_sync(0xffffffffu, inc[0], o);
+      const unsigned long long t1 = __shfl_down_sync(0xffffffffu, inc[1], o);
+      if (lane + o < 32) { inc[0] += t0; inc[1] += t1; }
     }
-    if (lane == 0) sc->wsum[wid] = inc;
+    if (lane == 0) { sc->wsum[0][wid] = inc[0]; sc->wsum[1][wid] = inc[1]; }
     __syncthreads();
-    unsigned long long above = inc - v;
-    for (int w = wid + 1; w < nw; ++w) above += sc->wsum[w];
-    const unsigned int ab[2] = {(unsigned int)(above & 0xffffffffull), (unsigned int)(above >> 32)};
+    unsigned long long above[2] = {inc[0] - v[0], inc[1] - v[1]};
+    for (int w = wid + 1; w < nw; ++w) { above[0] += sc->wsum[0][w]; above[1] += sc->wsum[1][w]; }
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kMaxSets; ++s) {
       if (done[s]) continue;
-      if ((int)ab[s] < k_rem[s] && k_rem[s] <= (int)(ab[s] + mine[s])) {   // the K-th largest is in my bins
-        int acc = (int)ab[s];
-        for (int q = bins_per_thread - 1; q >= 0; --q) {
+      const int ab = (int)((above[s / 3] >> (21 * (s % 3))) & 0x1fffffull);
+      if (ab < k_rem[s] && k_rem[s] <= ab + (int)mine[s]) {      // the K-th largest is in my bins
+        int acc = ab;
+        for (int q = BPT - 1; q >= 0; --q) {
           const int h = hist[s * kSelBins + q * T + tid];
-          if (acc < k_rem[s] && k_rem[s] <= acc + h) { sc->digit[s] = b_lo + q; sc->above[s] = acc; sc->cand[s] = h; break; }
+          if (acc < k_rem[s] && k_rem[s] <= acc + h) { sc->digit[s] = tid * BPT + q; sc->above[s] = acc; sc->cand[s] = h; break; }
           acc += h;
         }
       }
     }
     __syncthreads();
     mask_hi |= dmask << sh;
+    bool all_done = true;
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kMaxSets; ++s) {
       if (done[s]) continue;
-      pre[s] |= (unsigned long long)sc->digit[s] << sh;
+      pre[s] |= (unsigned)sc->digit[s] << sh;
       k_rem[s] -= sc->above[s];
       if (sc->cand[s] == k_rem[s]) done[s] = true;   // every key with this prefix is in the top set
+      all_done = all_done && done[s];
     }
-    if ((done[0] && done[1]) || sh == 0) break;
+    if (all_done || sh == 0) break;
   }
   // top set = keys whose decided bits are >= pre; when the digits ran out with ties left
   // (!done), only k_rem copies of the value `pre` belong to it.
-  double acc[3] = {0.0, 0.0, 0.0};
-  double acc2[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-  for (int j = 0; j < kVP; ++j) {
-    if (!((valid >> j) & 1u)) continue;
-    const unsigned long long ka = (unsigned long long)__double_as_longlong(pa[j]) & mask_hi;
-    const unsigned long long kb = (unsigned long long)__double_as_longlong(pb[j]) & mask_hi;
-    acc[0] += pa[j]; if (ka < pre[0]) acc[1] += pa[j]; if (!done[0] && ka == pre[0]) acc[2] += 1.0;
-    acc2[0] += pb[j]; if (kb < pre[1]) acc2[1] += pb[j]; if (!done[1] && kb == pre[1]) acc2[2] += 1.0;
+  for (int s = 0; s < nsets; ++s) {
+    const float* __restrict__ ps = P + s * pstride;
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int k = tid; k < n; k += T) {
+      const float pv = ps[k];
+      const unsigned key = __float_as_uint(pv) & mask_hi;
+      acc[0] += pv;
+      if (key < pre[s]) acc[1] += pv;
+      if (!done[s] && key == pre[s]) acc[2] += 1.0;
+    }
+    block_sum<3>(acc, red);
+    tot[s] = acc[0];
+    low[s] = acc[1];
+    if (!done[s]) low[s] += (acc[2] - (double)k_rem[s]) * (double)__uint_as_float(pre[s]);
   }
-  block_sum<3>(acc, red);
-  block_sum<3>(acc2, red);
-  tot[0] = acc[0]; tot[1] = acc2[0];
-  low[0] = acc[1]; low[1] = acc2[1];
-  if (!done[0]) low[0] += (acc[2] - (double)k_rem[0]) * __longlong_as_double((long long)pre[0]);
-  if (!done[1]) low[1] += (acc2[2] - (double)k_rem[1]) * __longlong_as_double((long long)pre[1]);
 }
 
-// dynamic shared memory: [ cbuf: cpad_size(Nd) double2 | cen: Hd+8 | pw: Hd+8 | red: 96 |
+// dynamic shared memory: [ cen: Hd+8 | cbuf: d4c_cbuf_slots double2 | pw: Hd+8 | red: 96 |
 //                          SelectScratch | coarse: kMaxBands+2 ]
 template <int LOG2ND, int THREADS>    // LOG2ND 0: size given at run time (c.log2nd)
 __global__ void __launch_bounds__(THREADS, 2)
@@ -244,15 +262,16 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
                 const double* __restrict__ f0_in, const double* __restrict__ ap0,
                 const long long* __restrict__ rng_off, const long long* __restrict__ lt_totals,
                 const uint32_t* __restrict__ randn_tab, const double2* __restrict__ tw,
-                const double* __restrict__ nuttall, D4CConst c, double* __restrict__ ap_out) {
+                const float2* __restrict__ twf, const double* __restrict__ nuttall, D4CConst c,
+                double* __restrict__ ap_out) {
   extern __shared__ double2 smem2[];
   const int log2nd = LOG2ND > 0 ? LOG2ND : c.log2nd;
   constexpr int LMD = LOG2ND > 0 ? LOG2ND - 1 : 0;
   const int Nd = 1 << log2nd, Hd = Nd >> 1;
-  double2* cbuf = smem2;
+  double* cen = reinterpret_cast<double*>(smem2);
+  double2* cbuf = reinterpret_cast<double2*>(cen + Hd + 8);
   double* cbufd = reinterpret_cast<double*>(cbuf);
-  double* cen = reinterpret_cast<double*>(cbuf + d4c_cbuf_slots(Nd));
-  double* pw = cen + Hd + 8;
+  double* pw = reinterpret_cast<double*>(cbuf + d4c_cbuf_slots(Nd, c.nbands));
   double* red = pw + Hd + 8;
   SelectScratch* sc = reinterpret_cast<SelectScratch*>(red + 96);
   double* coarse = reinterpret_cast<double*>(sc + 1);
@@ -335,46 +354,39 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
   for (int k = tid; k <= Hd; k += T) cen[k] -= pw[k];
   __syncthreads();
 
-  // ---- GetCoarseAperiodicity (:192-223): two bands per complex FFT -------------------------------
-  const int hw = c.window_length / 2;
-  unsigned valid = 0;
-#pragma unroll
-  for (int j = 0; j < kVP; ++j) if (tid + j * T <= Hd) valid |= 1u << j;
-  for (int b0 = 0; b0 < c.nbands; b0 += 2) {
-    const bool two = b0 + 1 < c.nbands;
-    const int ca = c.centers[b0] - hw, cb = two ? c.centers[b0 + 1] - hw : 0;
-    for (int i = tid; i < Nd; i += T) {
-      double2 z = make_double2(0.0, 0.0);
-      if (i < c.window_length) {
-        const double w = nuttall[i];
-        z.x = cen[ca + i] * w;
-        if (two) z.y = cen[cb + i] * w;
+  // ---- GetCoarseAperiodicity (:192-223): two bands per complex FP32 FFT, one selection for all --
+  {
+    const int hw = c.window_length / 2;
+    float2* fb = reinterpret_cast<float2*>(cbuf);
+    float* P = reinterpret_cast<float*>(reinterpret_cast<char*>(cbuf) + d4c_band_p_off(Nd, c.nbands));
+    const int pstride = Hd + 4;
+    for (int b0 = 0; b0 < c.nbands; b0 += 2) {
+      const bool two = b0 + 1 < c.nbands;
+      const int ca = c.centers[b0] - hw, cb = two ? c.centers[b0 + 1] - hw : 0;
+      for (int i = tid; i < Nd; i += T) {
+        float2 z = make_float2(0.f, 0.f);
+        if (i < c.window_length) {
+          const double w = nuttall[i];
+          z.x = static_cast<float>(cen[ca + i] * w);
+          if (two) z.y = static_cast<float>(cen[cb + i] * w);
+        }
+        fb[cslot(i)] = z;
       }
-      cbuf[cslot(i)] = z;
-    }
-    fft_dit<LOG2ND, false, THREADS>(cbuf, log2nd, tw);
-    double pa[kVP], pb[kVP];
-#pragma unroll
-    for (int j = 0; j < kVP; ++j) {
-      pa[j] = 0.0; pb[j] = 0.0;
-      const int k = tid + j * T;
-      if (k <= Hd) {
-        const double2 A = cbuf[cpad(k)];
-        const double2 B = cbuf[cpad((Nd - k) & (Nd - 1))];
-        const double xr = 0.5 * (A.x + B.x), xi = 0.5 * (A.y - B.y);
-        const double yr = 0.5 * (A.y + B.y), yi = 0.5 * (B.x - A.x);
-        pa[j] = xr * xr + xi * xi;
-        pb[j] = yr * yr + yi * yi;
+      fft_dit<LOG2ND, false, THREADS, 4>(fb, log2nd, twf);
+      for (int k = tid; k <= Hd; k += T) {
+        const float2 A = fb[cpad(k)];
+        const float2 B = fb[cpad((Nd - k) & (Nd - 1))];
+        const float xr = 0.5f * (A.x + B.x), xi = 0.5f * (A.y - B.y);
+        const float yr = 0.5f * (A.y + B.y), yi = 0.5f * (B.x - A.x);
+        P[b0 * pstride + k] = xr * xr + xi * xi;
+        if (two) P[(b0 + 1) * pstride + k] = yr * yr + yi * yi;
       }
+      __syncthreads();
     }
-    double low[2], tot[2];
-    __syncthreads();                                   // everyone has read cbuf: reuse it as the histogram
-    select_low_sums(pa, pb, valid, c.sel_boundary + 1, reinterpret_cast<int*>(cbuf), sc, red, low, tot);
-    if (tid == 0) {
-      coarse[1 + b0] = fmin(0.0, 10.0 * log10(low[0] / tot[0]) + (cur_f0 - 100.0) / 50.0);
-      if (two) coarse[2 + b0] = fmin(0.0, 10.0 * log10(low[1] / tot[1]) + (cur_f0 - 100.0) / 50.0);
-    }
-    __syncthreads();
+    double low[kMaxSets], tot[kMaxSets];
+    select_low_sums<THREADS>(P, pstride, c.nbands, Hd + 1, c.sel_boundary + 1, reinterpret_cast<int*>(cbuf), sc, red, low, tot);
+    if (tid < c.nbands)
+      coarse[1 + tid] = fmin(0.0, 10.0 * log10(low[tid] / tot[tid]) + (cur_f0 - 100.0) / 50.0);
   }
   if (tid == 0) { coarse[0] = -60.0; coarse[c.nbands + 1] = -kMySafeGuardMinimum; }
   __syncthreads();
@@ -416,7 +428,7 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
   c.log2lt = 0; while ((1 << c.log2lt) < nlt) ++c.log2lt;
   if (c.log2nd > 13 || c.log2nd < 6) { set_error("D4C: unsupported sampling rate %d", fs); return false; }
   c.nbands = static_cast<int>(fmin(kUpperLimit, fs / 2.0 - kFrequencyInterval) / kFrequencyInterval);  // :351-353
-  if (c.nbands < 1 || c.nbands > kMaxBands) { set_error("D4C: unsupported number of bands %d (fs %d)", c.nbands, fs); return false; }
+  if (c.nbands < 1 || c.nbands > kMaxBands || c.nbands > kMaxSets) { set_error("D4C: unsupported number of bands %d (fs %d)", c.nbands, fs); return false; }
   c.window_length = static_cast<int>(kFrequencyInterval * nd / fs) * 2 + 1;                         // :356-357
   c.sel_boundary = matlab_round(nd * 8.0 / c.window_length);                                        // :196-197
   for (int i = 0; i < c.nbands; ++i)
@@ -482,16 +494,15 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
   if (!need_randn()) return false;
   {
     const int hd = nd / 2;
-    const size_t smem = d4c_cbuf_slots(nd) * sizeof(double2) + (size_t)(2 * (hd + 8) + 96) * sizeof(double) +
+    const size_t smem = d4c_cbuf_slots(nd, c.nbands) * sizeof(double2) + (size_t)(2 * (hd + 8) + 96) * sizeof(double) +
                         sizeof(SelectScratch) + (kMaxBands + 2) * sizeof(double);
     const int threads = (nd > 4096 || getenv("WB_D4C_T512")) ? 512 : 256;
-    if (hd / threads + 1 > kVP) { set_error("D4C: fft size %d too large", nd); return false; }
     KernelTimer kt2("d4c_main_kernel");
 #define WB_D4C_LAUNCH(L, TH)                                                                                        \
   do {                                                                                                              \
     WB_CUDA_OR_RETURN(cudaFuncSetAttribute(d4c_main_kernel<L, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
     d4c_main_kernel<L, TH><<<total_frames, TH, smem, st>>>(u, frame_utt, frame_t, f0, d_ap0.p, offs_main.p, tot_lt.p, ctxp->d_randn, \
-                                                           ctxp->d_twiddle, d_win.p, c, ap);                         \
+                                                           ctxp->d_twiddle, ctxp->d_twiddle_f, d_win.p, c, ap);                         \
   } while (0)
     if (threads == 512 && c.log2nd == 12) WB_D4C_LAUNCH(12, 512);
     else if (threads == 512) WB_D4C_LAUNCH(0, 512);
