@@ -34,11 +34,11 @@ __global__ void cheaptrick_count_kernel(const double* __restrict__ f0, int total
 
 // dynamic shared memory: [ buf: cpad_size(N/2) double2 | aux: N + 16 doubles | red: 96 doubles ]
 template <int LOG2N>      // 0: size given at run time (log2n_rt)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __restrict__ frame_t,
                   const double* __restrict__ f0_in, const long long* __restrict__ rng_off,
                   const uint32_t* __restrict__ randn_tab, const double2* __restrict__ tw,
-                  int fs, int log2n_rt, double q1, double f0_floor, double* __restrict__ sp_out) {
+                  const float2* __restrict__ twf, int fs, int log2n_rt, double q1, double f0_floor, double* __restrict__ sp_out) {
   extern __shared__ double2 smem2[];
   const int log2n = LOG2N > 0 ? LOG2N : log2n_rt;
   constexpr int LM = LOG2N > 0 ? LOG2N - 1 : 0;
@@ -104,18 +104,18 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
   for (int i = tid; i < W; i += T) bufd[rfft_in_slot(i, log2m)] -= aux[i] * coef;
 
   // ---- GetPowerSpectrum (:64-82) -----------------------------------------------------------
-  fft_dit<LM, false, 256>(buf, log2m, tw);
+  fft_dit<LM, false, 256, 4>(buf, log2m, tw);
   for (int k = tid; k <= half; k += T) {
     const double2 X = rfft_bin(buf, log2m, k, tw);
     aux[k] = X.x * X.x + X.y * X.y;
   }
   __syncthreads();
   // DCCorrection (common.cpp:56-75)
-  const double df = (double)fs / N;                 // exact: N is a power of two
+  const double inv_df = (double)N / fs;
   {
     const int upper_limit = 2 + static_cast<int>(mul_rn(f0c, (double)N) / fs);
     for (int i = tid; i < upper_limit - 1; i += T)
-      bufd[i] = interp1q_at(f0c, -df, aux, upper_limit + 1, mul_rn((double)i, (double)fs) / N);
+      bufd[i] = interp1q_at(f0c, -inv_df, aux, upper_limit + 1, mul_rn((double)i, (double)fs) / N);
     __syncthreads();
     for (int i = tid; i < upper_limit - 1; i += T) aux[i] += bufd[i];
     __syncthreads();
@@ -137,8 +137,8 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
     const uint32_t* __restrict__ rn2 = rn + W;
     for (int k = tid; k <= half; k += T) {
       const double fa = add_rn(mul_rn((double)k / N, (double)fs), -width / 2.0);
-      const double low = interp1q_at(origin_axis, df, bufd, len, fa);
-      const double high = interp1q_at(origin_axis, df, bufd, len, add_rn(fa, width));
+      const double low = interp1q_at(origin_axis, inv_df, bufd, len, fa);
+      const double high = interp1q_at(origin_axis, inv_df, bufd, len, add_rn(fa, width));
       const double sm = (high - low) / width;
       // AddInfinitesimalNoise (:147-151) then log (:38-39)
       aux[k] = log(sm + fabs(randn_from_u32(rn2[k])) * kEps);
@@ -146,26 +146,36 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
   }
   __syncthreads();
   // ---- SmoothingWithRecovery (:22-57) ---------------------------------------------------------
-  for (int i = tid; i < N; i += T) bufd[rfft_in_slot(i, log2m)] = aux[i <= half ? i : N - i];
-  fft_dit<LM, false, 256>(buf, log2m, tw);
-  for (int k = tid; k <= half; k += T) {
-    const double re = rfft_bin(buf, log2m, k, tw).x;
-    double lifter = 1.0, comp = (1.0 - 2.0 * q1) + 2.0 * q1;
-    if (k > 0) {
-      const double quefrency = (double)k / fs;
-      const double a = kPi * f0c * quefrency;
-      lifter = sin(a) / a;
-      comp = (1.0 - 2.0 * q1) + 2.0 * q1 * cos(2.0 * kPi * quefrency * f0c);
+  // Both transforms act on the LOG spectrum (|values| <= ~40) and its cepstrum; in FP32 their
+  // error is ~1e-5 nepers, i.e. 1e-4 dB against the 0.01 dB tolerance, so they run in FP32
+  // (half the shared-memory traffic, twice the FMA rate).  exp() is taken in FP64.
+  {
+    float2* fb = reinterpret_cast<float2*>(buf);
+    float* fbs = reinterpret_cast<float*>(buf);
+    for (int i = tid; i < N; i += T) fbs[rfft_in_slot(i, log2m)] = static_cast<float>(aux[i <= half ? i : N - i]);
+    fft_dit<LM, false, 256, 4>(fb, log2m, twf);
+    float* lif = reinterpret_cast<float*>(aux);         // liftered cepstrum, real
+    __syncthreads();                                     // everyone has read aux
+    for (int k = tid; k <= half; k += T) {
+      const float re = rfft_bin(fb, log2m, k, twf).x;
+      double lifter = 1.0, comp = (1.0 - 2.0 * q1) + 2.0 * q1;
+      if (k > 0) {
+        const double quefrency = (double)k / fs;
+        double sn, cs;
+        sincospi(f0c * quefrency, &sn, &cs);             // sin(pi f0 q), cos(pi f0 q)
+        lifter = sn / (kPi * f0c * quefrency);
+        comp = (1.0 - 2.0 * q1) + 2.0 * q1 * (2.0 * cs * cs - 1.0);   // cos(2 pi f0 q)
+      }
+      lif[k] = static_cast<float>(re * lifter * comp / N);
     }
-    aux[k] = re * lifter * comp / N;
+    __syncthreads();
+    for (int k = tid; k < half; k += T) {
+      const float2 z = c2r_pack(make_float2(lif[k], 0.f), make_float2(lif[half - k], 0.f), k, log2m, twf);
+      fb[cpad(brev(k, log2m))] = z;
+    }
+    fft_dit<LM, true, 256, 4>(fb, log2m, twf);
+    for (int k = tid; k <= half; k += T) out[k] = exp(static_cast<double>(fbs[rfft_out_slot(k)]));
   }
-  __syncthreads();
-  for (int k = tid; k < half; k += T) {
-    const double2 z = c2r_pack(make_double2(aux[k], 0.0), make_double2(aux[half - k], 0.0), k, log2m, tw);
-    buf[cpad(brev(k, log2m))] = z;
-  }
-  fft_dit<LM, true, 256>(buf, log2m, tw);
-  for (int k = tid; k <= half; k += T) out[k] = exp(bufd[rfft_out_slot(k)]);
 }
 
 bool cheaptrick_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
@@ -198,7 +208,7 @@ bool cheaptrick_run(const UttView& u, int fs, int total_frames, const int* frame
 #define WB_CT_LAUNCH(L)                                                                                             \
   do {                                                                                                              \
     WB_CUDA_OR_RETURN(cudaFuncSetAttribute(cheaptrick_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
-    cheaptrick_kernel<L><<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0, offs.p, c->d_randn, c->d_twiddle, fs, log2n, q1, f0_floor, sp); \
+    cheaptrick_kernel<L><<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0, offs.p, c->d_randn, c->d_twiddle, c->d_twiddle_f, fs, log2n, q1, f0_floor, sp); \
   } while (0)
   switch (log2n) {
     case 10: WB_CT_LAUNCH(10); break;

@@ -178,9 +178,12 @@ __device__ __forceinline__ void block_inclusive_scan(double* a, int n, double* r
 
 // interp1Q (W/src/matlabfunctions.cpp:220-241) for one query: uniform grid starting at x0
 // with step dx, n samples in y; delta_y[n-1] is defined as 0 by the reference.
-__device__ __forceinline__ double interp1q_at(double x0, double dx, const double* y, int n,
+// The base index is found by multiplying with 1 / dx instead of dividing: when that moves the
+// truncation across an integer the fraction is ~0 or ~1 and the interpolant is continuous, so
+// the result changes by rounding noise only.
+__device__ __forceinline__ double interp1q_at(double x0, double inv_dx, const double* y, int n,
                                               double xi) {
-  const double r = div_rn(add_rn(xi, -x0), dx);
+  const double r = add_rn(xi, -x0) * inv_dx;
   int base = static_cast<int>(r);
   const double frac = r - base;
   base = max(0, min(n - 1, base));                 // memory guard only (UB in the reference)

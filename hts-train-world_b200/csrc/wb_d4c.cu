@@ -53,10 +53,20 @@ __device__ __forceinline__ int windowed_waveform(const double* __restrict__ x, i
   const int origin = matlab_round(add_rn(mul_rn(position, (double)fs), 0.001));
   const double ang_step = kPi * 2.0 * f0 / (ratio * fs);
   double s[2] = {0.0, 0.0};
+  // cos(a_i), a_i = (i - hwl) * ang_step, i = tid + j T: one sincos per thread for j = 0, then
+  // the angle-addition recurrence with the block-uniform step T * ang_step (<= 16 steps, so
+  // the accumulated rounding stays below 1e-15); cos(2a) = 2 cos^2(a) - 1.
+  double cs, sn, cs_step, sn_step;
+  sincos((double)(tid - hwl) * ang_step, &sn, &cs);
+  sincos((double)T * ang_step, &sn_step, &cs_step);
   for (int i = tid; i < W; i += T) {
-    const double a = (double)(i - hwl) * ang_step;      // pi * (2 (i - hwl) / ratio / fs) * f0
-    const double w = window_type == kHanning ? 0.5 * cos(a) + 0.5
-                                             : 0.42 + 0.5 * cos(a) + 0.08 * cos(a * 2);
+    const double w = window_type == kHanning ? 0.5 * cs + 0.5
+                                             : 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);
+    {
+      const double c2 = cs * cs_step - sn * sn_step;
+      sn = sn * cs_step + cs * sn_step;
+      cs = c2;
+    }
     const int idx = min(x_len - 1, max(0, origin + i - hwl));
     const double wave = x[idx] * w + randn_from_u32(rn[i]) * kMySafeGuardMinimum;
     base[wslot(i)] = wave;
@@ -256,7 +266,7 @@ __device__ __forceinline__ void select_low_sums(const float* __restrict__ P, int
 
 // dynamic shared memory: [ cen: Hd+8 | cbuf: d4c_cbuf_slots double2 | pw: Hd+8 | red: 96 |
 //                          SelectScratch | coarse: kMaxBands+2 ]
-template <int LOG2ND, int THREADS>    // LOG2ND 0: size given at run time (c.log2nd)
+template <int LOG2ND, int THREADS, int MAXK = 3>    // LOG2ND 0: size given at run time (c.log2nd)
 __global__ void __launch_bounds__(THREADS, 2)
 d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __restrict__ frame_t,
                 const double* __restrict__ f0_in, const double* __restrict__ ap0,
@@ -314,7 +324,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
       if (i < W) { const double v = cbuf[cslot(i)].x / sq; z = make_double2(v, v * (i + 1.0)); }
       cbuf[cslot(i)] = z;
     }
-    fft_dit<LOG2ND, false, THREADS>(cbuf, log2nd, tw);
+    fft_dit<LOG2ND, false, THREADS, MAXK>(cbuf, log2nd, tw);
     for (int k = tid; k <= Hd; k += T) {
       const double2 A = cbuf[cpad(k)];
       const double2 B = cbuf[cpad((Nd - k) & (Nd - 1))];
@@ -337,7 +347,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
     const int W = windowed_waveform(x, x_len, c.fs, cur_f0, t_pos, kHanning, 4.0,
                                     rn + 2 * (size_t)W4, cbufd, pwslot, pvslot, red);
     for (int i = W + tid; i < Nd; i += T) cbufd[rfft_in_slot(i, log2m)] = 0.0;
-    fft_dit<LMD, false, THREADS>(cbuf, log2m, tw);
+    fft_dit<LMD, false, THREADS, MAXK>(cbuf, log2m, tw);
     for (int k = tid; k <= Hd; k += T) {
       const double2 X = rfft_bin(cbuf, log2m, k, tw);
       pw[k] = X.x * X.x + X.y * X.y;
@@ -498,16 +508,16 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
                         sizeof(SelectScratch) + (kMaxBands + 2) * sizeof(double);
     const int threads = (nd > 4096 || getenv("WB_D4C_T512")) ? 512 : 256;
     KernelTimer kt2("d4c_main_kernel");
-#define WB_D4C_LAUNCH(L, TH)                                                                                        \
+#define WB_D4C_LAUNCH(L, TH, ...)                                                                                   \
   do {                                                                                                              \
-    WB_CUDA_OR_RETURN(cudaFuncSetAttribute(d4c_main_kernel<L, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
-    d4c_main_kernel<L, TH><<<total_frames, TH, smem, st>>>(u, frame_utt, frame_t, f0, d_ap0.p, offs_main.p, tot_lt.p, ctxp->d_randn, \
+    WB_CUDA_OR_RETURN(cudaFuncSetAttribute(d4c_main_kernel<L, TH, ##__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
+    d4c_main_kernel<L, TH, ##__VA_ARGS__><<<total_frames, TH, smem, st>>>(u, frame_utt, frame_t, f0, d_ap0.p, offs_main.p, tot_lt.p, ctxp->d_randn, \
                                                            ctxp->d_twiddle, ctxp->d_twiddle_f, d_win.p, c, ap);                         \
   } while (0)
     if (threads == 512 && c.log2nd == 12) WB_D4C_LAUNCH(12, 512);
     else if (threads == 512) WB_D4C_LAUNCH(0, 512);
-    else if (c.log2nd == 12) WB_D4C_LAUNCH(12, 256);
-    else if (c.log2nd == 11) WB_D4C_LAUNCH(11, 256);
+    else if (c.log2nd == 12) WB_D4C_LAUNCH(12, 256, 4);      // radix-16 passes: 3 instead of 4 round trips
+    else if (c.log2nd == 11) WB_D4C_LAUNCH(11, 256, 4);
     else WB_D4C_LAUNCH(0, 256);
 #undef WB_D4C_LAUNCH
     WB_LAUNCH_CHECK(); kt2.stop();

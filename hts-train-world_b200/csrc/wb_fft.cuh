@@ -166,11 +166,11 @@ __device__ __noinline__ void fft_dit_rt(C* s, int log2n, const C* __restrict__ t
   }
 }
 
-// LOG2N > 0: compile-time size; LOG2N == 0: the run-time value log2n_rt (radix-8 passes).
+// LOG2N > 0: compile-time size; LOG2N == 0: the run-time value log2n_rt.
 template <int LOG2N, bool INV, int THREADS, int MAXK = 3, typename C>
 __device__ __forceinline__ void fft_dit(C* s, int log2n_rt, const C* __restrict__ tw) {
   if constexpr (LOG2N > 0) fft_dit_fixed<LOG2N, INV, THREADS, MAXK>(s, tw);
-  else fft_dit_rt<INV, THREADS, 3>(s, log2n_rt, tw);
+  else fft_dit_rt<INV, THREADS, MAXK>(s, log2n_rt, tw);
 }
 
 // ---- real transforms on top of a half-size complex FFT -----------------------------------

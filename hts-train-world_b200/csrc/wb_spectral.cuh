@@ -9,10 +9,10 @@ namespace wb {
 // tmp: scratch of >= 2 + f0*N/fs doubles.  Ends with __syncthreads().
 __device__ __forceinline__ void dc_correction(double* spec, double* tmp, double f0, int fs, int N) {
   const int T = blockDim.x, tid = threadIdx.x;
-  const double df = (double)fs / N;
+  const double inv_df = (double)N / fs;
   const int upper_limit = min(N / 2 - 1, 2 + static_cast<int>(mul_rn(f0, (double)N) / fs));
   for (int i = tid; i < upper_limit - 1; i += T)
-    tmp[i] = interp1q_at(f0, -df, spec, upper_limit + 1, mul_rn((double)i, (double)fs) / N);
+    tmp[i] = interp1q_at(f0, -inv_df, spec, upper_limit + 1, mul_rn((double)i, (double)fs) / N);
   __syncthreads();
   for (int i = tid; i < upper_limit - 1; i += T) spec[i] += tmp[i];
   __syncthreads();
@@ -31,7 +31,7 @@ __device__ __forceinline__ void linear_smoothing(const double* in, double* out, 
   const int half = N / 2;
   const int boundary = smoothing_boundary(width, fs, N);
   const int len = half + 2 * boundary + 1;
-  const double df = (double)fs / N;
+  const double inv_df = (double)N / fs;
   for (int i = tid; i < len; i += T) {
     double v;
     if (i < boundary) v = in[boundary - i];
@@ -44,8 +44,8 @@ __device__ __forceinline__ void linear_smoothing(const double* in, double* out, 
   const double origin_axis = -(boundary - 0.5) * fs / N;
   for (int k = tid; k <= half; k += T) {
     const double fa = add_rn(mul_rn((double)k / N, (double)fs), -width / 2.0);
-    const double low = interp1q_at(origin_axis, df, cum, len, fa);
-    const double high = interp1q_at(origin_axis, df, cum, len, add_rn(fa, width));
+    const double low = interp1q_at(origin_axis, inv_df, cum, len, fa);
+    const double high = interp1q_at(origin_axis, inv_df, cum, len, add_rn(fa, width));
     out[k] = (high - low) / width;
   }
   __syncthreads();

@@ -38,10 +38,14 @@ __global__ void stonemask_maxfft_kernel(const double* __restrict__ f0, int n, in
 
 struct Bins { double power, numer; };
 
-__device__ __forceinline__ Bins stonemask_bin(const double2* cbuf, int nfft, int k) {
+// The packed transform runs in FP32: the harmonic bins FixF0 reads are the strongest of the
+// frame, their 2^-24 relative error moves the amplitude-weighted instantaneous frequency by
+// < 1e-6 relative (tolerance 1e-4).  Windows and all later arithmetic stay in FP64.
+__device__ __forceinline__ Bins stonemask_bin(const float2* cbuf, int nfft, int k) {
   k = max(0, min(nfft / 2, k));                    // memory guard (UB in the reference beyond N/2)
-  const double2 A = cbuf[cpad(k)];
-  const double2 B = cbuf[cpad((nfft - k) & (nfft - 1))];
+  const float2 Af = cbuf[cpad(k)];
+  const float2 Bf = cbuf[cpad((nfft - k) & (nfft - 1))];
+  const double2 A = make_double2(Af.x, Af.y), B = make_double2(Bf.x, Bf.y);
   Bins r;
   const double re = 0.5 * (A.x + B.x), im = 0.5 * (A.y - B.y);
   const double dre = 0.5 * (A.y + B.y), dim = 0.5 * (B.x - A.x);
@@ -51,7 +55,7 @@ __device__ __forceinline__ Bins stonemask_bin(const double2* cbuf, int nfft, int
 }
 
 // FixF0 (:96-117), evaluated by one thread
-__device__ double stonemask_fix_f0(const double2* cbuf, int nfft, int fs, double initial_f0, int nh) {
+__device__ double stonemask_fix_f0(const float2* cbuf, int nfft, int fs, double initial_f0, int nh) {
   double numerator = 0.0, denominator = 0.0;
   for (int i = 0; i < nh; ++i) {
     const int index = matlab_round(mul_rn(div_rn(mul_rn(initial_f0, (double)nfft), (double)fs), (double)(i + 1)));
@@ -66,17 +70,17 @@ __device__ double stonemask_fix_f0(const double2* cbuf, int nfft, int fs, double
   return numerator / (denominator + kMySafeGuardMinimum);
 }
 
-// dynamic shared memory: [ cbuf: cpad_size(max fft) double2 | win: max_fft/2 + 8 doubles ]
+// dynamic shared memory: [ cbuf: cpad_size(max fft) float2 | win: max_fft/2 + 8 doubles ]
 __global__ void __launch_bounds__(256)
 stonemask_kernel(UttView u, const int* __restrict__ frame_utt, const double* __restrict__ frame_t,
-                 const double* __restrict__ f0_in, const double2* __restrict__ tw, int fs,
+                 const double* __restrict__ f0_in, const float2* __restrict__ tw, int fs,
                  int max_log2fft, double* __restrict__ f0_out) {
   extern __shared__ double2 smem2[];
   const int f = blockIdx.x;
   const double f0 = f0_in[f];
   if (!stonemask_in_range(f0, fs)) { if (threadIdx.x == 0) f0_out[f] = 0.0; return; }
-  double2* cbuf = smem2;
-  double* win = reinterpret_cast<double*>(cbuf + cpad_size(1 << max_log2fft));
+  float2* cbuf = reinterpret_cast<float2*>(smem2);
+  double* win = reinterpret_cast<double*>(cbuf + ((cpad_size(1 << max_log2fft) + 1) & ~1));
   const int tid = threadIdx.x, T = blockDim.x;
   const int utt = frame_utt[f];
   const double* __restrict__ x = u.x + u.x_off[utt];
@@ -98,7 +102,7 @@ stonemask_kernel(UttView u, const int* __restrict__ frame_utt, const double* __r
   __syncthreads();
   // GetDiffWindow + GetSpectra, packed
   for (int i = tid; i < nfft; i += T) {
-    double2 z = make_double2(0.0, 0.0);
+    float2 z = make_float2(0.f, 0.f);
     if (i < W) {
       const double base_time = div_rn((double)(i - hwl), (double)fs);
       const int index_raw = matlab_round(mul_rn(add_rn(t_pos, base_time), (double)fs));
@@ -108,11 +112,11 @@ stonemask_kernel(UttView u, const int* __restrict__ frame_utt, const double* __r
       if (i == 0) dw = -win[1] / 2.0;
       else if (i == W - 1) dw = win[W - 2] / 2.0;
       else dw = -(win[i + 1] - win[i - 1]) / 2.0;
-      z = make_double2(xv * win[i], xv * dw);
+      z = make_float2(static_cast<float>(xv * win[i]), static_cast<float>(xv * dw));
     }
     cbuf[cpad(brev(i, log2fft))] = z;
   }
-  fft_dit<0, false, 256>(cbuf, log2fft, tw);
+  fft_dit<0, false, 256, 4>(cbuf, log2fft, tw);
   if (tid == 0) {
     // GetTentativeF0 (:122-131) and the 20 % sanity check of GetRefinedF0 (:203-204)
     double mean_f0 = 0.0;
@@ -141,11 +145,11 @@ bool stonemask_run(const UttView& u, int fs, int total_frames, const int* frame_
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
   if (h_max < 3) h_max = 3;
   if (h_max > 13) { set_error("StoneMask: FFT size 2^%d not supported", h_max); return false; }
-  const size_t smem = cpad_size(1 << h_max) * sizeof(double2) + ((size_t)(1 << h_max) / 2 + 8) * sizeof(double);
+  const size_t smem = ((cpad_size(1 << h_max) + 1) & ~1) * sizeof(float2) + ((size_t)(1 << h_max) / 2 + 8) * sizeof(double);
   if (smem > c->smem_optin) { set_error("StoneMask: needs %zu bytes of shared memory", smem); return false; }
   WB_CUDA_OR_RETURN(cudaFuncSetAttribute(stonemask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
   KernelTimer kt1("stonemask_kernel");
-  stonemask_kernel<<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0_in, c->d_twiddle, fs, h_max, f0_out);
+  stonemask_kernel<<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0_in, c->d_twiddle_f, fs, h_max, f0_out);
   WB_LAUNCH_CHECK(); kt1.stop();
   return true;
 }

@@ -58,15 +58,34 @@ __device__ __forceinline__ double coarse_vuv_at(const double* __restrict__ f0, i
   return a * 2 - b;                                   // :238-239
 }
 
-// Time base: WRITE = false counts pulses, WRITE = true stores them.
+// Upper bound on the number of pulses of an utterance: a pulse needs the phase to advance by
+// 2 pi, and inside a frame interval the interpolated f0 never exceeds the larger knot (or the
+// 500 Hz default of unvoiced samples), so pulses <= sum_k max(f_k, f_k+1, 500) * frame_period + 2.
+__global__ void synth_pulse_bound_kernel(const double* __restrict__ f0_all, const int* __restrict__ f_off,
+                                         const int* __restrict__ f_len, SynthConst c, int* __restrict__ bound) {
+  __shared__ double red[96];
+  const int u = blockIdx.x;
+  const double* __restrict__ f0 = f0_all + f_off[u];
+  const int n = f_len[u];
+  double v[1] = {0.0};
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const double a = coarse_f0_at(f0, n, k, c.lowest_f0), b = coarse_f0_at(f0, n, k + 1, c.lowest_f0);
+    v[0] += fmax(fmax(fabs(a), fabs(b)), kDefaultF0);
+  }
+  block_sum<1>(v, red);
+  if (threadIdx.x == 0) bound[u] = static_cast<int>(v[0] * c.frame_period_s * 1.001) + 4;
+}
+
+// Time base: WRITE = false counts pulses, WRITE = true stores them (and counts).
 template <bool WRITE>
 __global__ void __launch_bounds__(512)
 synth_timebase_kernel(const double* __restrict__ f0_all, const int* __restrict__ f_off,
                       const int* __restrict__ f_len, const int* __restrict__ y_len_all, SynthConst c,
                       int* __restrict__ pulse_count, const int* __restrict__ pulse_off,
-                      int* __restrict__ p_index, double* __restrict__ p_shift,
+                      const int* __restrict__ pulse_cap, int* __restrict__ p_index, double* __restrict__ p_shift,
                       unsigned char* __restrict__ p_vuv, int* __restrict__ p_utt) {
   __shared__ double inc_s[512];
+  __shared__ double tot_s[512];
   __shared__ int wcnt[32];
   __shared__ double carry_phase, last_wrap_prev;
   __shared__ int carry_cnt;
@@ -110,12 +129,24 @@ synth_timebase_kernel(const double* __restrict__ f0_all, const int* __restrict__
     inc_s[tid] = inc;
     __syncthreads();
     if (tid == 0) {
+      // batches of 8: the loads of a batch are issued together (input and output arrays are
+      // distinct, so nothing orders them behind the previous batch's stores) and only the
+      // eight dependent DADDs are serial
+      const double* __restrict__ in = inc_s;
+      double* __restrict__ outp = tot_s;
       double run = carry_phase;
-#pragma unroll 8
-      for (int q = 0; q < T; ++q) { run = add_rn(run, inc_s[q]); inc_s[q] = run; }
+      for (int q = 0; q < T; q += 8) {
+        double v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r] = in[q + r];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { run = add_rn(run, v[r]); v[r] = run; }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) outp[q + r] = v[r];
+      }
     }
     __syncthreads();
-    const double total = inc_s[tid];
+    const double total = tot_s[tid];
     const double wrap = fmod(total, kTwoPi);                            // :251,254
     wrap_s[tid + 1] = wrap;
     vuv_s[tid + 1] = vuv;
@@ -137,7 +168,7 @@ synth_timebase_kernel(const double* __restrict__ f0_all, const int* __restrict__
     int before = carry_cnt;
     for (int w = 0; w < wid; ++w) before += wcnt[w];
     const int pos = before + __popc(bal & ((1u << lane) - 1u));
-    if (WRITE && is_pulse) {
+    if (WRITE && is_pulse && pos < pulse_cap[u]) {
       const int o = base_out + pos;
       p_index[o] = j;
       const double yy1 = y1 - kTwoPi;                                   // :271-274
@@ -148,7 +179,7 @@ synth_timebase_kernel(const double* __restrict__ f0_all, const int* __restrict__
     }
     __syncthreads();
     if (tid == T - 1) {
-      carry_phase = total;     // == inc_s[T-1], the running sum after this chunk
+      carry_phase = total;     // == tot_s[T-1], the running sum after this chunk
       last_wrap_prev = wrap;
       int tot = 0;
       for (int w = 0; w < nw; ++w) tot += wcnt[w];
@@ -157,7 +188,7 @@ synth_timebase_kernel(const double* __restrict__ f0_all, const int* __restrict__
     if (tid == 0) vuv_s[0] = vuv_s[T];   // vuv of the chunk's last sample, for the straddling pair
     __syncthreads();
   }
-  if (!WRITE && tid == 0) pulse_count[u] = carry_cnt;
+  if (tid == 0) pulse_count[u] = carry_cnt;
 }
 
 // ---- pulse classification -------------------------------------------------------------------
@@ -184,7 +215,7 @@ __global__ void synth_classify_kernel(const double* __restrict__ ap_all, const i
                                       int total_p, SynthConst c, int* __restrict__ cnt2,
                                       int* __restrict__ list_per, int* __restrict__ list_aper) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= total_p) return;
+  if (p >= total_p || p_utt[p] < 0) return;
   bool periodic = false;
   if (p_vuv[p]) {
     const int u = p_utt[p];
@@ -474,28 +505,27 @@ bool synthesis_run(Batch* b, const int* y_len) {
   c.lowest_f0 = b->fs / N + 1.0;                    // integer division, W/src/synthesis.cpp:359
   c.f0_max_len = b->max_f_len;
 
-  DevBuf<int> d_cnt, d_poff;
-  if (!d_cnt.alloc(n_utt) || !d_poff.alloc(n_utt)) return false;
-  KernelTimer kt1("synth_timebase_kernel");
-  synth_timebase_kernel<false><<<n_utt, 512, 0, st>>>(b->f0.p, b->f_off.p, b->f_len.p, b->y_len.p, c, d_cnt.p,
-                                                      nullptr, nullptr, nullptr, nullptr, nullptr);
-  WB_LAUNCH_CHECK(); kt1.stop();
-  std::vector<int> h_cnt(n_utt), h_poff(n_utt);
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_cnt.data(), d_cnt.p, n_utt * sizeof(int), cudaMemcpyDeviceToHost, st), false);
+  // pulse time base: one pass into per-utterance regions sized by a cheap upper bound
+  DevBuf<int> d_cnt, d_poff, d_cap;
+  if (!d_cnt.alloc(n_utt) || !d_poff.alloc(n_utt) || !d_cap.alloc(n_utt)) return false;
+  synth_pulse_bound_kernel<<<n_utt, 128, 0, st>>>(b->f0.p, b->f_off.p, b->f_len.p, c, d_cap.p);
+  WB_LAUNCH_CHECK();
+  std::vector<int> h_cap(n_utt), h_cnt(n_utt), h_poff(n_utt);
+  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_cap.data(), d_cap.p, n_utt * sizeof(int), cudaMemcpyDeviceToHost, st), false);
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
   long long total_p = 0;
   int max_y = 0;
-  for (int u = 0; u < n_utt; ++u) { h_poff[u] = (int)total_p; total_p += h_cnt[u]; max_y = std::max(max_y, y_len[u]); }
+  for (int u = 0; u < n_utt; ++u) { h_poff[u] = (int)total_p; total_p += h_cap[u]; max_y = std::max(max_y, y_len[u]); }
   if (total_p > 0x7fffffffLL) { set_error("Synthesis: too many pulses"); return false; }
-  if (total_p == 0) return true;
   if (!ensure_randn((size_t)max_y + 16)) return false;
   DevBuf<int> p_index, p_utt;
   DevBuf<double> p_shift, d_rem;
   DevBuf<unsigned char> p_vuv;
   if (!p_index.alloc(total_p) || !p_utt.alloc(total_p) || !p_shift.alloc(total_p) || !p_vuv.alloc(total_p) || !d_rem.alloc(N)) return false;
   WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_poff.p, h_poff.data(), n_utt * sizeof(int), cudaMemcpyHostToDevice, st), false);
+  WB_CUDA_OR_RETURN(cudaMemsetAsync(p_utt.p, 0xff, (size_t)total_p * sizeof(int), st), false);   // -1 = unused slot
   KernelTimer kt2("synth_timebase_kernel");
-  synth_timebase_kernel<true><<<n_utt, 512, 0, st>>>(b->f0.p, b->f_off.p, b->f_len.p, b->y_len.p, c, nullptr, d_poff.p,
+  synth_timebase_kernel<true><<<n_utt, 256, 0, st>>>(b->f0.p, b->f_off.p, b->f_len.p, b->y_len.p, c, d_cnt.p, d_poff.p, d_cap.p,
                                                      p_index.p, p_shift.p, p_vuv.p, p_utt.p);
   WB_LAUNCH_CHECK(); kt2.stop();
   // GetDCRemover (:322-334)
@@ -517,9 +547,13 @@ bool synthesis_run(Batch* b, const int* y_len) {
   WB_LAUNCH_CHECK();
   int h_cnt2[2] = {0, 0};
   WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_cnt2, d_cnt2.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st), false);
+  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_cnt.data(), d_cnt.p, n_utt * sizeof(int), cudaMemcpyDeviceToHost, st), false);
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  for (int u = 0; u < n_utt; ++u)
+    if (h_cnt[u] > h_cap[u]) { set_error("Synthesis: utterance %d has %d pulses, bound was %d", u, h_cnt[u], h_cap[u]); return false; }
   const int n_per = h_cnt2[0], n_aper = h_cnt2[1];
   const unsigned n_items = (unsigned)(n_per + (n_aper + 1) / 2);
+  if (n_items == 0) return true;
   static const bool fp64 = getenv("WB_SYNTH_FP64") != nullptr;      // debugging aid: all four transforms in FP64
   const size_t smem = 2 * cpad_size(N) * (fp64 ? sizeof(double2) : sizeof(float2)) + 96 * sizeof(double);
   if (N / 2 / 256 + 1 > 9) { set_error("Synthesis: fft_size %d too large for the register fold", N); return false; }
