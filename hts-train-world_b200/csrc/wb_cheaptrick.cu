@@ -152,7 +152,7 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
   {
     float2* fb = reinterpret_cast<float2*>(buf);
     float* fbs = reinterpret_cast<float*>(buf);
-    for (int i = tid; i < N; i += T) fbs[rfft_in_slot(i, log2m)] = static_cast<float>(aux[i <= half ? i : N - i]);
+    for (int i = tid; i < N; i += T) fbs[rfft_in_slot_f(i, log2m)] = static_cast<float>(aux[i <= half ? i : N - i]);
     fft_dit<LM, false, 256, 4>(fb, log2m, twf);
     float* lif = reinterpret_cast<float*>(aux);         // liftered cepstrum, real
     __syncthreads();                                     // everyone has read aux
@@ -171,10 +171,10 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
     __syncthreads();
     for (int k = tid; k < half; k += T) {
       const float2 z = c2r_pack(make_float2(lif[k], 0.f), make_float2(lif[half - k], 0.f), k, log2m, twf);
-      fb[cpad(brev(k, log2m))] = z;
+      fb[cpadf(brev(k, log2m))] = z;
     }
     fft_dit<LM, true, 256, 4>(fb, log2m, twf);
-    for (int k = tid; k <= half; k += T) out[k] = exp(static_cast<double>(fbs[rfft_out_slot(k)]));
+    for (int k = tid; k <= half; k += T) out[k] = exp(static_cast<double>(fbs[rfft_out_slot_f(k)]));
   }
 }
 

@@ -380,12 +380,12 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
           z.x = static_cast<float>(cen[ca + i] * w);
           if (two) z.y = static_cast<float>(cen[cb + i] * w);
         }
-        fb[cslot(i)] = z;
+        fb[cpadf(brev(i, log2nd))] = z;
       }
       fft_dit<LOG2ND, false, THREADS, 4>(fb, log2nd, twf);
       for (int k = tid; k <= Hd; k += T) {
-        const float2 A = fb[cpad(k)];
-        const float2 B = fb[cpad((Nd - k) & (Nd - 1))];
+        const float2 A = fb[cpadf(k)];
+        const float2 B = fb[cpadf((Nd - k) & (Nd - 1))];
         const float xr = 0.5f * (A.x + B.x), xi = 0.5f * (A.y - B.y);
         const float yr = 0.5f * (A.y + B.y), yi = 0.5f * (B.x - A.x);
         P[b0 * pstride + k] = xr * xr + xi * xi;

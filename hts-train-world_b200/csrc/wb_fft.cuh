@@ -30,6 +30,13 @@ namespace wb {
 // output permutations (strides 2^(log2n-3) * {0,4,2,6,1,5,3,7}) for every size 2^6 .. 2^13.
 __host__ __device__ __forceinline__ constexpr int cpad(int c) { return c + (c >> 3) + (c >> 6) + (c >> 9); }
 __host__ __device__ constexpr int cpad_size(int n) { return n + (n >> 3) + (n >> 6) + (n >> 9) + 4; }
+// 8-byte elements (float2): 16 slots per 128-byte wavefront, so the skew is one element every
+// 16, 256 and 4096; conflict-free for the radix-16 / radix-8 first pass, for later passes whose
+// stage is >= 4 (16 consecutive lanes) and for the bit-reversed permutations.
+__host__ __device__ __forceinline__ constexpr int cpadf(int c) { return c + (c >> 4) + (c >> 8) + (c >> 12); }
+template <typename C> __host__ __device__ __forceinline__ constexpr int cpadT(int c) {
+  return sizeof(C) == 16 ? cpad(c) : cpadf(c);
+}
 __device__ __forceinline__ int brev(int c, int log2n) {
   return static_cast<int>(__brev(static_cast<unsigned>(c)) >> (32 - log2n));
 }
@@ -89,10 +96,10 @@ __device__ __forceinline__ void fft_pass(C* __restrict__ s, const C* __restrict_
     if (NB % THREADS != 0 && b >= NB) break;
     const int j = FIRST ? 0 : (b & ((1 << STAGE) - 1));
     const int base = FIRST ? (b << K) : (((b >> STAGE) << (STAGE + K)) + j);
-    C* __restrict__ sb = s + cpad(base);
+    C* __restrict__ sb = s + cpadT<C>(base);
     C v[R];
 #pragma unroll
-    for (int m = 0; m < R; ++m) v[m] = sb[cpad(m << STAGE)];
+    for (int m = 0; m < R; ++m) v[m] = sb[cpadT<C>(m << STAGE)];
     C w[K];
     if (!FIRST) {
 #pragma unroll
@@ -116,7 +123,7 @@ __device__ __forceinline__ void fft_pass(C* __restrict__ s, const C* __restrict_
       }
     }
 #pragma unroll
-    for (int m = 0; m < R; ++m) sb[cpad(m << STAGE)] = v[m];
+    for (int m = 0; m < R; ++m) sb[cpadT<C>(m << STAGE)] = v[m];
   }
 }
 
@@ -184,8 +191,8 @@ __device__ __forceinline__ C rfft_bin(const C* s, int log2m, int k, const C* __r
     const C z0 = s[0];
     return mk2(k == 0 ? z0.x + z0.y : z0.x - z0.y, static_cast<R>(0));
   }
-  const C A = s[cpad(k)];
-  const C B = cconj(s[cpad(M - k)]);
+  const C A = s[cpadT<C>(k)];
+  const C B = cconj(s[cpadT<C>(M - k)]);
   const R h = static_cast<R>(0.5);
   const C E = mk2(h * (A.x + B.x), h * (A.y + B.y));
   const C O = mk2(h * (A.x - B.x), h * (A.y - B.y));
@@ -202,6 +209,9 @@ __device__ __forceinline__ int rfft_in_slot(int i, int log2m) {
 __device__ __forceinline__ int rfft_out_slot(int i) {   // natural order after c2r
   return 2 * cpad(i >> 1) + (i & 1);
 }
+// the same for float2 buffers
+__device__ __forceinline__ int rfft_in_slot_f(int i, int log2m) { return 2 * cpadf(brev(i >> 1, log2m)) + (i & 1); }
+__device__ __forceinline__ int rfft_out_slot_f(int i) { return 2 * cpadf(i >> 1) + (i & 1); }
 
 // Inverse (c2r): for k in [0, N/2) compute the packed element from X[k] and X[N/2 - k]
 // and store it at slot brev(k); then fft_dit<true>; real sample i is at rfft_out_slot(i).

@@ -43,8 +43,8 @@ struct Bins { double power, numer; };
 // < 1e-6 relative (tolerance 1e-4).  Windows and all later arithmetic stay in FP64.
 __device__ __forceinline__ Bins stonemask_bin(const float2* cbuf, int nfft, int k) {
   k = max(0, min(nfft / 2, k));                    // memory guard (UB in the reference beyond N/2)
-  const float2 Af = cbuf[cpad(k)];
-  const float2 Bf = cbuf[cpad((nfft - k) & (nfft - 1))];
+  const float2 Af = cbuf[cpadf(k)];
+  const float2 Bf = cbuf[cpadf((nfft - k) & (nfft - 1))];
   const double2 A = make_double2(Af.x, Af.y), B = make_double2(Bf.x, Bf.y);
   Bins r;
   const double re = 0.5 * (A.x + B.x), im = 0.5 * (A.y - B.y);
@@ -114,7 +114,7 @@ stonemask_kernel(UttView u, const int* __restrict__ frame_utt, const double* __r
       else dw = -(win[i + 1] - win[i - 1]) / 2.0;
       z = make_float2(static_cast<float>(xv * win[i]), static_cast<float>(xv * dw));
     }
-    cbuf[cpad(brev(i, log2fft))] = z;
+    cbuf[cpadf(brev(i, log2fft))] = z;
   }
   fft_dit<0, false, 256, 4>(cbuf, log2fft, tw);
   if (tid == 0) {

@@ -340,6 +340,33 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
   const ChanInfo c0 = chan_info(pa, p_index, p_utt, p_vuv, pulse_off, pulse_cnt, f_off, f_len, y_len_all, randn_tab, c, N);
   const ChanInfo c1 = per_item ? c0 : chan_info(pb, p_index, p_utt, p_vuv, pulse_off, pulse_cnt, f_off, f_len, y_len_all, randn_tab, c, N);
 
+  // The sp / ap rows of the pulse(s) are needed first; ask L2 for them now and transform the
+  // noise (which only needs the randn table) while they are in flight.
+  {
+    const int lines = ((half + 1) * 8 + 127) / 128;
+    const int n_rows = (per_item || pb < 0) ? 4 : 8;
+    for (int i = tid; i < n_rows * lines; i += T) {
+      const int r = i / lines;
+      const ChanInfo& ci = r < 4 ? c0 : c1;
+      const size_t row = ci.row0 + ((r & 1) ? ci.fr_ceil : ci.fr_floor);
+      const char* ptr = reinterpret_cast<const char*>(((r & 2) ? ap_all : sp_all) + row * (half + 1)) + (size_t)(i % lines) * 128;
+      asm volatile("prefetch.global.L2 [%0];" :: "l"(ptr));
+    }
+  }
+  // ---- noise of both channels (:19-33) -----------------------------------------------------------
+  {
+    double s2[2] = {0.0, 0.0};
+    if (!per_item) for (int i = tid; i < c0.noise_size; i += T) s2[0] += randn_from_u32(c0.rn[i]);
+    for (int i = tid; i < c1.noise_size; i += T) s2[1] += randn_from_u32(c1.rn[i]);
+    block_sum<2>(s2, red);
+    const double av0 = s2[0] / c0.noise_raw, av1 = s2[1] / c1.noise_raw;
+    for (int i = tid; i < N; i += T) {
+      const R n0 = (!per_item && i < c0.noise_size) ? static_cast<R>(randn_from_u32(c0.rn[i]) - av0) : static_cast<R>(0);
+      const R n1 = i < c1.noise_size ? static_cast<R>(randn_from_u32(c1.rn[i]) - av1) : static_cast<R>(0);
+      nzb[cpadT<C>(brev(i, log2n))] = mk2(n0, n1);
+    }
+  }
+  fft_dit<LOG2N, false, T, 4>(nzb, log2n, tw);       // C
   // ---- log spectra (:45-51, :115-117), written as the even extension in bit-reversed order ----
   for (int k = tid; k <= half; k += T) {
     R l0 = 0, l1 = 0;
@@ -356,23 +383,9 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
       }
     }
     const C z = mk2(l0, l1);
-    cbuf[cpad(brev(k, log2n))] = z;
-    if (k > 0 && k < half) cbuf[cpad(brev(N - k, log2n))] = z;
+    cbuf[cpadT<C>(brev(k, log2n))] = z;
+    if (k > 0 && k < half) cbuf[cpadT<C>(brev(N - k, log2n))] = z;
   }
-  // ---- noise of both channels (:19-33) -----------------------------------------------------------
-  {
-    double s2[2] = {0.0, 0.0};
-    if (!per_item) for (int i = tid; i < c0.noise_size; i += T) s2[0] += randn_from_u32(c0.rn[i]);
-    for (int i = tid; i < c1.noise_size; i += T) s2[1] += randn_from_u32(c1.rn[i]);
-    block_sum<2>(s2, red);
-    const double av0 = s2[0] / c0.noise_raw, av1 = s2[1] / c1.noise_raw;
-    for (int i = tid; i < N; i += T) {
-      const R n0 = (!per_item && i < c0.noise_size) ? static_cast<R>(randn_from_u32(c0.rn[i]) - av0) : static_cast<R>(0);
-      const R n1 = i < c1.noise_size ? static_cast<R>(randn_from_u32(c1.rn[i]) - av1) : static_cast<R>(0);
-      nzb[cpad(brev(i, log2n))] = mk2(n0, n1);
-    }
-  }
-  fft_dit<LOG2N, false, T, 4>(nzb, log2n, tw);       // C
   fft_dit<LOG2N, false, T, 4>(cbuf, log2n, tw);      // A
   // ---- fold the cepstra (common.cpp:194-206) -----------------------------------------------------
   {
@@ -382,7 +395,7 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
       const int i = tid + q * T;
       C z = mk2(static_cast<R>(0), static_cast<R>(0));
       if (i <= half) {
-        z = cbuf[cpad(i)];
+        z = cbuf[cpadT<C>(i)];
         if (i > 0 && i < half) { z.x *= 2; z.y *= 2; }
       }
       keep[q] = z;
@@ -391,9 +404,9 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
 #pragma unroll
     for (int q = 0; q < kQ; ++q) {
       const int i = tid + q * T;
-      if (i <= half) cbuf[cpad(brev(i, log2n))] = keep[q];
+      if (i <= half) cbuf[cpadT<C>(brev(i, log2n))] = keep[q];
     }
-    for (int i = half + 1 + tid; i < N; i += T) cbuf[cpad(brev(i, log2n))] = mk2(static_cast<R>(0), static_cast<R>(0));
+    for (int i = half + 1 + tid; i < N; i += T) cbuf[cpadT<C>(brev(i, log2n))] = mk2(static_cast<R>(0), static_cast<R>(0));
   }
   fft_dit<LOG2N, false, T, 4>(cbuf, log2n, tw);      // B
   // ---- minimum-phase spectra, time shift / noise product (:56-65, :88-100, :120-131) ------------
@@ -409,8 +422,8 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
       y1[q] = y0[q];
       if (k > half) continue;
       const int km = (N - k) & (N - 1);
-      const C A = cbuf[cpad(k)], B = cbuf[cpad(km)];
-      const C Zn = nzb[cpad(k)], Zm = nzb[cpad(km)];
+      const C A = cbuf[cpadT<C>(k)], B = cbuf[cpadT<C>(km)];
+      const C Zn = nzb[cpadT<C>(k)], Zm = nzb[cpadT<C>(km)];
       // S0 = (A + conj B)/2, S1 = (A - conj B)/(2i); likewise for the noise spectra
       const R s0r = hlf * (A.x + B.x), s0i = hlf * (A.y - B.y);
       const R s1r = hlf * (A.y + B.y), s1i = hlf * (B.x - A.x);
@@ -438,21 +451,21 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
       if (k > half) continue;
       C a = y0[q], b = y1[q];
       if (k == 0 || k == half) { a.y = 0; b.y = 0; }
-      cbuf[cpad(brev(k, log2n))] = mk2(a.x - b.y, a.y + b.x);
-      if (k > 0 && k < half) cbuf[cpad(brev(N - k, log2n))] = mk2(a.x + b.y, b.x - a.y);
+      cbuf[cpadT<C>(brev(k, log2n))] = mk2(a.x - b.y, a.y + b.x);
+      if (k > 0 && k < half) cbuf[cpadT<C>(brev(N - k, log2n))] = mk2(a.x + b.y, b.x - a.y);
     }
   }
   fft_dit<LOG2N, true, T, 4>(cbuf, log2n, tw);       // D
   // ---- fftshift, RemoveDCComponent (:73-82), mix (:214-217), overlap-add (:376-383) -------------
   if (per_item) {
     double dc[1] = {0.0};
-    for (int i = tid; i < half; i += T) dc[0] += cbuf[cpad(i)].x;        // shifted [N/2, N) = raw [0, N/2)
+    for (int i = tid; i < half; i += T) dc[0] += cbuf[cpadT<C>(i)].x;        // shifted [N/2, N) = raw [0, N/2)
     block_sum<1>(dc, red);
     const double sqrt_noise = sqrt((double)c0.noise_raw);
     double* __restrict__ y = y_all + y_off[c0.utt];
     for (int jj = tid; jj < N; jj += T) {
       const int raw = jj < half ? jj + half : jj - half;                 // fftshift
-      const C v = cbuf[cpad(raw)];
+      const C v = cbuf[cpadT<C>(raw)];
       const double pr = jj < half ? -dc[0] * dc_remover[jj] : (double)v.x - dc[0] * dc_remover[jj];
       const double r = (pr * sqrt_noise + (double)v.y) / N;
       const int oi = jj + c0.index - half + 1;
@@ -463,7 +476,7 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
     double* __restrict__ yb = y_all + y_off[c1.utt];
     for (int jj = tid; jj < N; jj += T) {
       const int raw = jj < half ? jj + half : jj - half;
-      const C v = cbuf[cpad(raw)];
+      const C v = cbuf[cpadT<C>(raw)];
       const int oa = jj + c0.index - half + 1;
       if (oa >= 0 && oa <= c0.y_len - 1) atomicAdd(&ya[oa], (double)v.x / N);
       if (pb >= 0) {
