@@ -22,12 +22,12 @@
 #include <vector>
 #include "wb_batch.h"
 #include "wb_fft.cuh"
+#include "wb_zerocross.cuh"
 
 namespace wb {
 namespace {
 
 constexpr int kMaxDioBands = 16;
-constexpr int kZcChunk = 2048;       // sample pairs per CTA in the zero-crossing kernels
 
 struct DioFilterBank {
   int nb = 0;
@@ -38,28 +38,6 @@ struct DioFilterBank {
   DevBuf<double2> G;                 // [nb][bn/2 + 1] spectra of the causal combined filters
   double boundary_f0[kMaxDioBands];
 };
-
-// ---- host: build the combined filters and their spectra ------------------------------------------
-void host_fft(std::vector<double>& re, std::vector<double>& im) {   // in-place radix-2, forward
-  const size_t n = re.size();
-  for (size_t i = 1, j = 0; i < n; ++i) {
-    size_t bit = n >> 1;
-    for (; j & bit; bit >>= 1) j ^= bit;
-    j ^= bit;
-    if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
-  }
-  for (size_t len = 2; len <= n; len <<= 1) {
-    const long double ang = -2.0L * 3.14159265358979323846264338327950288L / len;
-    for (size_t i = 0; i < n; i += len)
-      for (size_t k = 0; k < len / 2; ++k) {
-        const double wr = (double)cosl(ang * k), wi = (double)sinl(ang * k);
-        const size_t a = i + k, b = i + k + len / 2;
-        const double xr = re[b] * wr - im[b] * wi, xi = re[b] * wi + im[b] * wr;
-        re[b] = re[a] - xr; im[b] = im[a] - xi;
-        re[a] += xr; im[a] += xi;
-      }
-  }
-}
 
 bool build_filter_bank(double actual_fs, const DioParams& p, DioFilterBank* fb) {
   fb->nb = 1 + static_cast<int>(log(p.f0_ceil / p.f0_floor) / kLog2 * p.channels_in_octave);   // :582-583
@@ -129,184 +107,6 @@ __global__ void dio_mean_kernel(const double* __restrict__ x_all, const long lon
   for (int i = threadIdx.x; i < n; i += blockDim.x) v[0] += x[i];
   block_sum<1>(v, red);
   if (threadIdx.x == 0) mean[u] = v[0] / y_len[u];
-}
-
-// ---- overlap-save filtering: one CTA per (block, utterance) ---------------------------------------
-// dynamic shared memory: [ xs: cpad_size(bn/2) double2 | ws: cpad_size(bn/2) double2 ]
-template <int LOG2BN>     // 0: block size given at run time (c.log2bn)
-__global__ void __launch_bounds__(256)
-dio_filter_kernel(const double* __restrict__ x_all, const long long* __restrict__ x_off,
-                  const int* __restrict__ x_len, const int* __restrict__ y_len_all,
-                  const int* __restrict__ fft_mask_all, const double* __restrict__ mean_all,
-                  const long long* __restrict__ F_off, const double2* __restrict__ G,
-                  const double2* __restrict__ tw, DioConst c, int utt0, double* __restrict__ F) {
-  extern __shared__ double2 smem2[];
-  const int u = utt0 + blockIdx.y;
-  const int y_len = y_len_all[u];
-  const int n0 = blockIdx.x * c.V;
-  if (n0 >= y_len) return;
-  constexpr int LM = LOG2BN > 0 ? LOG2BN - 1 : 0;
-  const int log2m = LOG2BN > 0 ? LOG2BN - 1 : c.log2bn - 1, M = 1 << log2m;
-  double2* xs = smem2;
-  double2* ws = smem2 + cpad_size(M);
-  double* xsd = reinterpret_cast<double*>(xs);
-  double* wsd = reinterpret_cast<double*>(ws);
-  const int tid = threadIdx.x, T = blockDim.x;
-  const double* __restrict__ x = x_all + x_off[u];
-  const int xl = x_len[u];
-  const int mask = fft_mask_all[u];
-  const double mean = mean_all[u];
-  // input block: ypad[(n0 - D + i) mod FS]
-  for (int i = tid; i < c.bn; i += T) {
-    const int m = (n0 - c.D + i) & mask;
-    double v = 0.0;
-    if (m < y_len) v = (m < xl ? x[m] : 0.0) - mean;
-    xsd[rfft_in_slot(i, log2m)] = v;
-  }
-  fft_dit<LM, false, 256>(xs, log2m, tw);
-  // half spectrum in place: slot k = X[k] (k < M), slot 0 = (X[0], X[M])
-  for (int k = tid; k <= M / 2; k += T) {
-    if (k == 0) {
-      const double2 z0 = xs[0];
-      xs[0] = make_double2(z0.x + z0.y, z0.x - z0.y);
-    } else {
-      const double2 a = rfft_bin(xs, log2m, k, tw);
-      const double2 b = rfft_bin(xs, log2m, M - k, tw);
-      xs[cpad(k)] = a;
-      xs[cpad(M - k)] = b;
-    }
-  }
-  __syncthreads();
-  const int n_out = min(c.V, y_len - n0);
-  double* __restrict__ Fu = F + F_off[u - utt0];
-  for (int b = 0; b < c.nb; ++b) {
-    const double2* __restrict__ Gb = G + (size_t)b * (M + 1);
-    for (int k = tid; k <= M / 2; k += T) {
-      if (k == 0) {
-        const double2 x0 = xs[0];
-        const double2 y0 = make_double2(x0.x * Gb[0].x, 0.0), yM = make_double2(x0.y * Gb[M].x, 0.0);
-        ws[cpad(brev(0, log2m))] = c2r_pack(y0, yM, 0, log2m, tw);
-      } else {
-        const double2 yk = cmul(xs[cpad(k)], Gb[k]);
-        const double2 ym = cmul(xs[cpad(M - k)], Gb[M - k]);
-        ws[cpad(brev(k, log2m))] = c2r_pack(yk, ym, k, log2m, tw);
-        if (k != M - k) ws[cpad(brev(M - k, log2m))] = c2r_pack(ym, yk, M - k, log2m, tw);
-      }
-    }
-    fft_dit<LM, true, 256>(ws, log2m, tw);
-    const int shift = c.D + 2 * c.hal[b] + c.hN;       // filtered_b[n] = conv[n - n0 + shift]
-    double* __restrict__ dst = Fu + (size_t)b * y_len + n0;
-    for (int i = tid; i < n_out; i += T) dst[i] = wsd[rfft_out_slot(i + shift)];
-    __syncthreads();
-  }
-}
-
-// ---- zero crossings ------------------------------------------------------------------------------
-// Event types on the filtered signal s (GetFourZeroCrossingIntervals :402-435):
-//   0 negative-going  s[i] > 0 >= s[i+1]            1 positive-going  -s
-//   2 peaks           d[i] = s[i+1] - s[i], d[i] > 0 >= d[i+1]      3 dips  -d
-__device__ __forceinline__ bool zc_event(double a, double b) { return 0.0 < a && b <= 0.0; }
-__device__ __forceinline__ double zc_fine(int e, double a, double b) {   // :376-379
-  return add_rn((double)e, -div_rn(a, add_rn(b, -a)));
-}
-
-template <bool WRITE>
-__global__ void __launch_bounds__(256)
-dio_zc_kernel(const double* __restrict__ F, const long long* __restrict__ F_off,
-              const int* __restrict__ y_len_all, int nb, int utt0, int n_chunks_max,
-              int* __restrict__ counts,              // [lists][n_chunks_max] (count pass: out; write: exclusive offsets)
-              const long long* __restrict__ list_off, double* __restrict__ edges) {
-  __shared__ int wcnt[4][8];
-  __shared__ int run[4];
-  const int ub = blockIdx.y;                         // local utterance * nb + band
-  const int u_local = ub / nb, b = ub % nb;
-  const int y_len = y_len_all[utt0 + u_local];
-  const int chunk = blockIdx.x;
-  const int i0 = chunk * kZcChunk;
-  if (i0 >= y_len - 1) {
-    if (!WRITE && threadIdx.x < 4) counts[((size_t)ub * 4 + threadIdx.x) * n_chunks_max + chunk] = 0;
-    return;
-  }
-  const double* __restrict__ s = F + F_off[u_local] + (size_t)b * y_len;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid < 4) run[tid] = WRITE ? counts[((size_t)ub * 4 + tid) * n_chunks_max + chunk] : 0;
-  __syncthreads();
-  for (int it = 0; it < kZcChunk / 256; ++it) {
-    const int i = i0 + it * 256 + tid;
-    bool ev[4] = {false, false, false, false};
-    double fine[4] = {0.0, 0.0, 0.0, 0.0};
-    if (i < y_len - 1) {
-      const double s0 = s[i], s1 = s[i + 1];
-      ev[0] = zc_event(s0, s1);
-      ev[1] = zc_event(-s0, -s1);
-      if (WRITE && ev[0]) fine[0] = zc_fine(i + 1, s0, s1);
-      if (WRITE && ev[1]) fine[1] = zc_fine(i + 1, -s0, -s1);
-      if (i < y_len - 2) {
-        const double s2 = s[i + 2];
-        const double d0 = add_rn(s1, -s0), d1 = add_rn(s2, -s1);
-        ev[2] = zc_event(d0, d1);
-        ev[3] = zc_event(-d0, -d1);
-        if (WRITE && ev[2]) fine[2] = zc_fine(i + 1, d0, d1);
-        if (WRITE && ev[3]) fine[3] = zc_fine(i + 1, -d0, -d1);
-      }
-    }
-    unsigned bal[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      bal[t] = __ballot_sync(0xffffffffu, ev[t]);
-      if (lane == 0) wcnt[t][wid] = __popc(bal[t]);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      if (WRITE && ev[t]) {
-        int pos = run[t];
-        for (int w = 0; w < wid; ++w) pos += wcnt[t][w];
-        pos += __popc(bal[t] & ((1u << lane) - 1u));
-        edges[list_off[(size_t)ub * 4 + t] + pos] = fine[t];
-      }
-    }
-    __syncthreads();
-    if (tid < 4) {
-      int tot = 0;
-      for (int w = 0; w < 8; ++w) tot += wcnt[tid][w];
-      run[tid] += tot;
-    }
-    __syncthreads();
-  }
-  if (!WRITE && tid < 4) counts[((size_t)ub * 4 + tid) * n_chunks_max + chunk] = run[tid];
-}
-
-// one thread per list: exclusive scan over chunks (in place), list totals out
-__global__ void dio_zc_scan_kernel(int* __restrict__ counts, int n_lists, int n_chunks_max,
-                                   int* __restrict__ totals) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= n_lists) return;
-  int* c = counts + (size_t)l * n_chunks_max;
-  int acc = 0;
-  for (int i = 0; i < n_chunks_max; ++i) { const int v = c[i]; c[i] = acc; acc += v; }
-  totals[l] = acc;
-}
-
-// interp1 (matlabfunctions.cpp:157-182) of interval-F0 at time t; knots are the mid-points of
-// consecutive edges: loc_i = (e_i + e_{i+1}) / 2 / fs, val_i = fs / (e_{i+1} - e_i), i < n_int.
-__device__ __forceinline__ double zc_loc(const double* __restrict__ e, int i, double fs) {
-  return div_rn(div_rn(add_rn(e[i], e[i + 1]), 2.0), fs);
-}
-__device__ __forceinline__ double zc_val(const double* __restrict__ e, int i, double fs) {
-  return div_rn(fs, add_rn(e[i + 1], -e[i]));
-}
-__device__ double zc_interp(const double* __restrict__ e, int n_int, double fs, double t) {
-  int lo = 0, hi = n_int;                 // upper_bound: first knot with loc > t
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (zc_loc(e, mid, fs) <= t) lo = mid + 1; else hi = mid;
-  }
-  const int k = max(1, min(n_int - 1, lo));
-  const double x0 = zc_loc(e, k - 1, fs), x1 = zc_loc(e, k, fs);
-  const double y0 = zc_val(e, k - 1, fs), y1 = zc_val(e, k, fs);
-  const double sfrac = div_rn(add_rn(t, -x0), add_rn(x1, -x0));
-  return add_rn(y0, mul_rn(sfrac, add_rn(y1, -y0)));
 }
 
 // candidates and scores per (utterance, band, frame)  (:441-508, :549-572)
@@ -493,8 +293,16 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
   WB_LAUNCH_CHECK();
 
   const size_t smem = 2 * cpad_size(c.bn / 2) * sizeof(double2);
-  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(dio_filter_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
-  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(dio_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(ols_filter_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(ols_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+
+  OlsConst oc = {c.nb, c.bn, c.log2bn, c.D, c.V};
+  std::vector<int> h_shift(c.nb);
+  for (int i = 0; i < c.nb; ++i) h_shift[i] = c.D + 2 * c.hal[i] + c.hN;
+  DevBuf<int> d_shift;
+  if (!d_shift.alloc(c.nb)) return false;
+  WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_shift.p, h_shift.data(), c.nb * sizeof(int), cudaMemcpyHostToDevice, st), false);
+  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
 
   // sub-batches bounded by the size of the filtered-signal scratch (nb * y_len doubles per utterance)
   const size_t kMaxScratchDoubles = (size_t)2 << 30;           // 16 GiB
@@ -525,16 +333,16 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
     WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_foff.p, h_foff.data(), nu * sizeof(long long), cudaMemcpyHostToDevice, st), false);
     KernelTimer kt1("dio_filter_kernel");
     if (c.log2bn == 13)
-      dio_filter_kernel<13><<<dim3(n_blocks, nu), 256, smem, st>>>(b->x.p, b->x_off.p, b->x_len.p, d_ylen.p, d_mask.p, d_mean.p,
-                                                            d_foff.p, fb->G.p, ctxp->d_twiddle, c, u0, d_F.p);
+      ols_filter_kernel<13><<<dim3(n_blocks, nu), 256, smem, st>>>(b->x.p, b->x_off.p, b->x_len.p, d_ylen.p, d_mask.p, d_mean.p,
+                                                            d_foff.p, fb->G.p, ctxp->d_twiddle, oc, d_shift.p, u0, d_F.p);
     else
-      dio_filter_kernel<0><<<dim3(n_blocks, nu), 256, smem, st>>>(b->x.p, b->x_off.p, b->x_len.p, d_ylen.p, d_mask.p, d_mean.p,
-                                                            d_foff.p, fb->G.p, ctxp->d_twiddle, c, u0, d_F.p);
+      ols_filter_kernel<0><<<dim3(n_blocks, nu), 256, smem, st>>>(b->x.p, b->x_off.p, b->x_len.p, d_ylen.p, d_mask.p, d_mean.p,
+                                                            d_foff.p, fb->G.p, ctxp->d_twiddle, oc, d_shift.p, u0, d_F.p);
     WB_LAUNCH_CHECK(); kt1.stop();
     KernelTimer kt2("dio_zc_kernel");
-    dio_zc_kernel<false><<<dim3(n_chunks, nu * c.nb), 256, 0, st>>>(d_F.p, d_foff.p, d_ylen.p, c.nb, u0, n_chunks, d_counts.p, nullptr, nullptr);
+    zc_kernel<false><<<dim3(n_chunks, nu * c.nb), 256, 0, st>>>(d_F.p, d_foff.p, d_ylen.p, c.nb, u0, n_chunks, d_counts.p, nullptr, nullptr);
     WB_LAUNCH_CHECK(); kt2.stop();
-    dio_zc_scan_kernel<<<(n_lists + 127) / 128, 128, 0, st>>>(d_counts.p, n_lists, n_chunks, d_ltot.p);
+    zc_scan_kernel<<<(n_lists + 127) / 128, 128, 0, st>>>(d_counts.p, n_lists, n_chunks, d_ltot.p);
     WB_LAUNCH_CHECK();
     std::vector<int> h_ltot(n_lists);
     WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_ltot.data(), d_ltot.p, n_lists * sizeof(int), cudaMemcpyDeviceToHost, st), false);
@@ -545,7 +353,7 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
     if (!d_edges.alloc((size_t)etot + 2)) return false;
     WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_loff.p, h_loff.data(), n_lists * sizeof(long long), cudaMemcpyHostToDevice, st), false);
     KernelTimer kt3("dio_zc_kernel");
-    dio_zc_kernel<true><<<dim3(n_chunks, nu * c.nb), 256, 0, st>>>(d_F.p, d_foff.p, d_ylen.p, c.nb, u0, n_chunks, d_counts.p, d_loff.p, d_edges.p);
+    zc_kernel<true><<<dim3(n_chunks, nu * c.nb), 256, 0, st>>>(d_F.p, d_foff.p, d_ylen.p, c.nb, u0, n_chunks, d_counts.p, d_loff.p, d_edges.p);
     WB_LAUNCH_CHECK(); kt3.stop();
     int max_f = 0;
     for (int u = u0; u < u1; ++u) max_f = std::max(max_f, b->h_f_len[u]);

@@ -49,6 +49,41 @@ def test_stonemask_golden(wb, name):
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_harvest_golden(wb, name):
+    """Harvest (W/src/harvest.cpp:1223), F0 range 71-800 Hz, against the reference's output."""
+    g = load_golden(name)
+    t, f0 = wb.harvest(_x(g), int(g["fs"]))
+    assert np.array_equal(t, g["t"])
+    assert M.vuv_agreement(g["f0_harvest"], f0) >= M.TOL_VUV_AGREEMENT
+    assert M.f0_rel_error(g["f0_harvest"], f0) <= M.TOL_F0_REL
+
+
+def test_harvest_batch_and_1ms(wb, reference_lib):
+    """Ragged batch through the extension API, and the frame_period == 1 ms path (:1230-1235)."""
+    from hts_train_world_b200 import signals
+    fs = 48000
+    pcms = [signals.make_utterance(40 + i, fs, duration=d)[0].numpy() for i, d in enumerate([0.8, 2.1, 0.3])]
+    c = wb.Corpus(fs, [len(p) for p in pcms])
+    c.upload_pcm16(np.concatenate(pcms))
+    c.harvest()
+    f0 = c.f0()
+    agree, n = 0.0, 0
+    for u, p in enumerate(pcms):
+        x = p.astype(np.float64) / 32768.0
+        _, fr = reference_lib.harvest(x, fs)
+        sl = c.frames_of(u)
+        agree += M.vuv_agreement(fr, f0[sl]) * len(fr)
+        n += len(fr)
+        assert M.f0_rel_error(fr, f0[sl]) <= M.TOL_F0_REL
+    assert agree / n >= M.TOL_VUV_AGREEMENT
+    c.close()
+    x = pcms[0].astype(np.float64) / 32768.0
+    _, fr = reference_lib.harvest(x, fs, frame_period=1.0)
+    _, f1 = wb.harvest(x, fs, frame_period=1.0)
+    assert M.vuv_agreement(fr, f1) >= M.TOL_VUV_AGREEMENT and M.f0_rel_error(fr, f1) <= M.TOL_F0_REL
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
 def test_cheaptrick_golden(wb, name):
     g = load_golden(name)
     sp = wb.cheaptrick(_x(g), int(g["fs"]), g["t"], g["f0"])
