@@ -289,14 +289,14 @@ def ours_arm(args):
 
     def step_resident():
         c.set_pcm16_device(pcm_dev)
-        c.analyze()
+        c.analyze(f0=args.f0)
         c.synthesis()
         return reduce_stats(c.lf0_stats())
 
     def step_e2e():
         nonlocal y_host
         c.upload_pcm16(pcm_host)
-        c.analyze()
+        c.analyze(f0=args.f0)
         c.synthesis()
         if y_host is None:
             y_host = torch.empty(int(wb.lib().wb200_batch_total_y(c._h)), dtype=torch.int16).pin_memory()
@@ -342,7 +342,8 @@ def ours_arm(args):
     kernel_ms = {k: wb.kernel_time(k) for k in
                  ["d4c_main_kernel", "d4c_lovetrain_kernel", "cheaptrick_kernel", "synth_pulse_kernel",
                   "synth_timebase_kernel", "stonemask_kernel", "dio_filter_kernel", "dio_zc_kernel",
-                  "dio_candidates_kernel", "dio_fix_kernel"]}
+                  "dio_candidates_kernel", "dio_fix_kernel", "harvest_iir_kernel", "harvest_filter_kernel",
+                  "harvest_zc_kernel", "harvest_refine_kernel", "harvest_fix_kernel", "harvest_smooth_kernel"]}
     wb.kernel_timing(False)
     stage_ms = wb.stage_times()
     clk = clocks.stop(t0, t1) if rank == 0 else None
@@ -411,8 +412,9 @@ def ours_arm(args):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%d-utterance synthetic 48 kHz corpus per GPU (%.0f s audio, %d frames), 5 ms "
-                               "frames, fft_size %d: Dio+StoneMask+CheapTrick+D4C+Synthesis + lf0 statistics"
-                               % (len(lengths), audio_s, c.total_frames, c.fft_size),
+                               "frames, fft_size %d: %s+CheapTrick+D4C+Synthesis + lf0 statistics"
+                               % (len(lengths), audio_s, c.total_frames, c.fft_size,
+                                  "Harvest" if args.f0 == "harvest" else "Dio+StoneMask"),
                    "fs": FS, "frame_period_ms": FRAME_PERIOD, "utterances_per_gpu": len(lengths),
                    "parallelism": "utterance-sharded x%d, no hot-path collective" % world,
                    "l2": "inputs larger than L2 (%.0f MB PCM, GBs of intermediates per step)" % (h2d / 1e6)},
@@ -462,6 +464,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--utts", type=int, default=1132, help="utterances per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--f0", default="dio", choices=["dio", "harvest"], help="F0 estimator (harvest = BASELINE config 3)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

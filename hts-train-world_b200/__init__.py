@@ -346,11 +346,14 @@ class Corpus:
             p = y_lengths.ctypes.data_as(_ip)
         _check(lib().wb200_batch_synthesis(self._h, p), "batch synthesis")
 
-    def analyze(self, threshold=0.0):
+    def analyze(self, threshold=0.0, f0="dio"):
         """Dio -> StoneMask -> CheapTrick -> D4C with the analysis tool's options
-        (W/test/analysis.cpp:93-203)."""
-        self.dio()
-        self.stonemask()
+        (W/test/analysis.cpp:93-203); f0="harvest" swaps the F0 estimator (BASELINE config 3)."""
+        if f0 == "harvest":
+            self.harvest()
+        else:
+            self.dio()
+            self.stonemask()
         self.cheaptrick()
         self.d4c(threshold=threshold)
 

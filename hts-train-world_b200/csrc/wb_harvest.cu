@@ -228,33 +228,11 @@ __device__ __forceinline__ double harvest_overlapped(const double* __restrict__ 
   return base_u[(size_t)src * max_base + j];
 }
 
-// ---- 4. refinement: one warp per (frame, slot) (:433-631) ----------------------------------------
-__global__ void __launch_bounds__(256)
-harvest_refine_kernel(const double* __restrict__ y_all, const long long* __restrict__ y_off,
-                      const int* __restrict__ y_len_all, const double* __restrict__ mean_all,
-                      const double* __restrict__ base, const int* __restrict__ g_off,
-                      const int* __restrict__ g_len, const int* __restrict__ nc_utt,
-                      const long long* __restrict__ cand_off, int max_base, HarvestConst c, int n_utt,
-                      const int* __restrict__ work_utt, const long long* __restrict__ work_first,
-                      long long total_work, double* __restrict__ cand, double* __restrict__ score) {
-  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (wid >= total_work) return;
-  // which utterance: binary search over the prefix of (frames * slots)
-  int lo = 0, hi = n_utt - 1;
-  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (work_first[mid] <= wid) lo = mid; else hi = mid - 1; }
-  const int u = lo;
-  (void)work_utt;
-  const int nc = nc_utt[u], slots = nc * kOverlap, n_fr = g_len[u];
-  const long long local = wid - work_first[u];
-  const int k = (int)(local / slots), s = (int)(local - (long long)k * slots);
-  const double* __restrict__ base_u = base + (size_t)g_off[u] * max_base;
-  const double f0c = harvest_overlapped(base_u, max_base, nc, n_fr, k, s);
-  const size_t o = cand_off[u] + (size_t)k * slots + s;
-  if (!(f0c > 0.0)) { if (lane == 0) { cand[o] = 0.0; score[o] = 0.0; } return; }
-  const double* __restrict__ y = y_all + y_off[u];
-  const int y_len = y_len_all[u];
-  const double mean = mean_all[u];
+// ---- 4. refinement: one warp per 1 ms frame, looping over its non-zero candidates (:433-631) ------
+// GetRefinedF0 for one candidate, evaluated by a full warp; lane 0 returns the result.
+__device__ __forceinline__ void harvest_refine_one(const double* __restrict__ y, int y_len, double mean,
+                                                   const HarvestConst& c, int k, double f0c, int lane,
+                                                   double* refined_out, double* score_out) {
   const double fs = c.actual_fs;
   const double pos = div_rn((double)k, 1000.0);
   const int hwl = static_cast<int>(add_rn(div_rn(mul_rn(1.5, fs), f0c), 1.0));          // :586
@@ -268,10 +246,14 @@ harvest_refine_kernel(const double* __restrict__ y_all, const long long* __restr
 #pragma unroll
   for (int h = 0; h < 6; ++h)
     bins[h] = matlab_round(mul_rn(div_rn(mul_rn(f0c, (double)nfft), fs), (double)(h + 1)));   // :513
-  // window phase: a_n = 2 pi tmp_n / wlen, tmp_n = (basic_index + n - 1) / fs - pos (:447-452)
+  // window phase a_n = 2 pi tmp_n / wlen, tmp_n = (basic_index + n - 1) / fs - pos (:447-452): linear
+  // in n, so one sincos for n = lane and angle-addition steps of 32 samples; the neighbours needed
+  // by the differentiated window are one more angle addition (+- one sample).
   const double dstep = 2.0 * kPi / (wlen * fs);
-  double cd, sd;
+  double cd, sd, c32, s32, cs, sn;
   sincos(dstep, &sd, &cd);
+  sincos(32.0 * dstep, &s32, &c32);
+  sincos(2.0 * kPi * add_rn(div_rn(basic_index + lane - 1.0, fs), -pos) / wlen, &sn, &cs);
   double acc[6][4];
 #pragma unroll
   for (int h = 0; h < 6; ++h) { acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.0; }
@@ -284,18 +266,19 @@ harvest_refine_kernel(const double* __restrict__ y_all, const long long* __restr
     sincospi(-2.0 * m0 / nfft, &ps[h], &pc[h]);
     sincospi(-2.0 * m1 / nfft, &qs[h], &qc[h]);
   }
-  auto blackman = [](double cs) { return 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0); };
+  auto blackman = [](double cv) { return 0.42 + 0.5 * cv + 0.08 * (2.0 * cv * cv - 1.0); };
   for (int n = lane; n < W; n += 32) {
-    const double tmp = add_rn(div_rn(basic_index + n - 1.0, fs), -pos);
-    double cs, sn;
-    sincos(2.0 * kPi * tmp / wlen, &sn, &cs);
     const double w = blackman(cs);
-    // neighbours by angle addition: a_{n+-1} = a_n +- dstep
     const double w_next = blackman(cs * cd - sn * sd), w_prev = blackman(cs * cd + sn * sd);
     double dw;                                                       // GetDiffWindow (:459-465)
     if (n == 0) dw = -w_next / 2.0;
     else if (n == W - 1) dw = w_prev / 2.0;
     else dw = -(w_next - w_prev) / 2.0;
+    {
+      const double t = cs * c32 - sn * s32;
+      sn = sn * c32 + cs * s32;
+      cs = t;
+    }
     const int idx = max(0, min(y_len - 1, basic_index + n - 1));
     const double xv = y[idx] - mean;
     const double xm = xv * w, xd = xv * dw;
@@ -312,26 +295,52 @@ harvest_refine_kernel(const double* __restrict__ y_all, const long long* __restr
   for (int h = 0; h < 6; ++h)
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc[h][q] = warp_sum(acc[h][q]);
-  if (lane == 0) {
-    double numerator = 0.0, denominator = 0.0, sc = 0.0;             // FixF0 (:504-536)
-    for (int h = 0; h < nh; ++h) {
-      const double re = acc[h][0], im = acc[h][1], dre = acc[h][2], dim = acc[h][3];
-      const double power = re * re + im * im;
-      const double numer = re * dim - im * dre;
-      const int index = bins[h];
-      const double inst = power == 0.0 ? 0.0
-          : add_rn(div_rn(mul_rn((double)index, fs), (double)nfft),
-                   div_rn(div_rn(mul_rn(div_rn(numer, power), fs), 2.0), kPi));
-      const double amp = sqrt(power);
-      numerator += amp * inst;
-      denominator += amp * (h + 1.0);
-      sc += fabs((inst / (h + 1.0) - f0c) / f0c);
-    }
-    double refined = numerator / (denominator + kMySafeGuardMinimum);
-    double rscore = 1.0 / (sc / nh + kMySafeGuardMinimum);
-    if (refined < c.f0_floor || refined > c.f0_ceil || rscore < 2.5) { refined = 0.0; rscore = 0.0; }   // :598-602
-    cand[o] = refined;
-    score[o] = rscore;
+  double numerator = 0.0, denominator = 0.0, sc = 0.0;             // FixF0 (:504-536)
+  for (int h = 0; h < nh; ++h) {
+    const double re = acc[h][0], im = acc[h][1], dre = acc[h][2], dim = acc[h][3];
+    const double power = re * re + im * im;
+    const double numer = re * dim - im * dre;
+    const int index = bins[h];
+    const double inst = power == 0.0 ? 0.0
+        : add_rn(div_rn(mul_rn((double)index, fs), (double)nfft),
+                 div_rn(div_rn(mul_rn(div_rn(numer, power), fs), 2.0), kPi));
+    const double amp = sqrt(power);
+    numerator += amp * inst;
+    denominator += amp * (h + 1.0);
+    sc += fabs((inst / (h + 1.0) - f0c) / f0c);
+  }
+  double refined = numerator / (denominator + kMySafeGuardMinimum);
+  double rscore = 1.0 / (sc / nh + kMySafeGuardMinimum);
+  if (refined < c.f0_floor || refined > c.f0_ceil || rscore < 2.5) { refined = 0.0; rscore = 0.0; }   // :598-602
+  *refined_out = refined;
+  *score_out = rscore;
+}
+
+__global__ void __launch_bounds__(256, 2)
+harvest_refine_kernel(const double* __restrict__ y_all, const long long* __restrict__ y_off,
+                      const int* __restrict__ y_len_all, const double* __restrict__ mean_all,
+                      const double* __restrict__ base, const int* __restrict__ g_off,
+                      const int* __restrict__ g_len, const int* __restrict__ nc_utt,
+                      const long long* __restrict__ cand_off, int max_base, HarvestConst c, int n_utt,
+                      long long total_frames, double* __restrict__ cand, double* __restrict__ score) {
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= total_frames) return;
+  int lo = 0, hi = n_utt - 1;                       // utterance of this 1 ms frame
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (g_off[mid] <= wid) lo = mid; else hi = mid - 1; }
+  const int u = lo;
+  const int nc = nc_utt[u], slots = nc * kOverlap, n_fr = g_len[u];
+  const int k = (int)(wid - g_off[u]);
+  const double* __restrict__ base_u = base + (size_t)g_off[u] * max_base;
+  const double* __restrict__ y = y_all + y_off[u];
+  const int y_len = y_len_all[u];
+  const double mean = mean_all[u];
+  const size_t o = cand_off[u] + (size_t)k * slots;
+  for (int s = 0; s < slots; ++s) {
+    const double f0c = harvest_overlapped(base_u, max_base, nc, n_fr, k, s);
+    double refined = 0.0, rscore = 0.0;
+    if (f0c > 0.0) harvest_refine_one(y, y_len, mean, c, k, f0c, lane, &refined, &rscore);
+    if (lane == 0) { cand[o + s] = refined; score[o + s] = rscore; }
   }
 }
 
@@ -850,10 +859,9 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
   if (ctot > 0) {
     {
       KernelTimer kt("harvest_refine_kernel");
-      const long long threads = ctot * 32;
+      const long long threads = gtot * 32;
       harvest_refine_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_y.p, d_yoff.p, d_ylen.p, d_mean.p, d_base.p, d_goff.p, d_glen.p,
-                                                                              d_nc.p, d_coff.p, max_base, c, n_utt, nullptr, d_wfirst.p, ctot,
-                                                                              d_cand.p, d_score.p);
+                                                                              d_nc.p, d_coff.p, max_base, c, n_utt, gtot, d_cand.p, d_score.p);
       WB_LAUNCH_CHECK(); kt.stop();
     }
     harvest_unreliable_kernel<<<(unsigned)((ctot + 255) / 256), 256, 0, st>>>(d_cand.p, d_score.p, d_glen.p, d_nc.p, d_coff.p, n_utt, d_wfirst.p,
