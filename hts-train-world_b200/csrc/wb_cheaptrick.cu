@@ -67,41 +67,42 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
   }
 
   // ---- GetWindowedWaveform (:112-142) ---------------------------------------------------
+  // w_i = 0.5 cos(theta_i) + 0.5 with theta_i = (i - hwl) pi f0 / (1.5 fs): one sincos per thread,
+  // then angle-addition steps of T samples.  The reference normalises w by sqrt(sum w^2), adds
+  // the dither and removes the weighted mean; all four sums come from ONE block reduction:
+  //   wave_i = x_i w_i / norm + d_i,   coef = sum(wave) / sum(w / norm) = (Sx + Sd norm) / Sw.
   const int origin = matlab_round(add_rn(mul_rn(t_pos, (double)fs), 0.001));
-  double acc[3];
-  acc[0] = 0.0;
-  for (int i = tid; i < W; i += T) {
-    const double position = div_rn(div_rn((double)(i - hwl), 1.5), (double)fs);
-    const double w = 0.5 * cos(kPi * position * f0c) + 0.5;
-    aux[i] = w;
-    acc[0] += w * w;
-  }
   {
-    double v1[1] = {acc[0]};
-    block_sum<1>(v1, red);
-    acc[0] = v1[0];
-  }
-  const double norm = sqrt(acc[0]);
-  double s1 = 0.0, s2 = 0.0;
-  for (int i = tid; i < N; i += T) {
-    double wave = 0.0;
-    if (i < W) {
-      const double w = aux[i] / norm;
-      aux[i] = w;
+    const double ang_step = kPi * f0c / (1.5 * fs);
+    double cs, sn, cs_step, sn_step;
+    sincos((double)(tid - hwl) * ang_step, &sn, &cs);
+    sincos((double)T * ang_step, &sn_step, &cs_step);
+    double sums[4] = {0.0, 0.0, 0.0, 0.0};            // Sww, Sw, Sx, Sd
+    for (int i = tid; i < W; i += T) {
+      const double w = 0.5 * cs + 0.5;
+      {
+        const double c2 = cs * cs_step - sn * sn_step;
+        sn = sn * cs_step + cs * sn_step;
+        cs = c2;
+      }
       const int idx = min(x_len - 1, max(0, origin + i - hwl));
-      wave = x[idx] * w + randn_from_u32(rn[i]) * kMySafeGuardMinimum;
-      s1 += wave;
-      s2 += w;
+      const double xw = x[idx] * w;
+      aux[i] = w;
+      bufd[rfft_in_slot(i, log2m)] = xw;
+      sums[0] += w * w; sums[1] += w; sums[2] += xw;
+      sums[3] += randn_from_u32(rn[i]) * kMySafeGuardMinimum;
     }
-    bufd[rfft_in_slot(i, log2m)] = wave;
+    block_sum<4>(sums, red);
+    const double inv_norm = 1.0 / sqrt(sums[0]);
+    const double coef = (sums[2] + sums[3] / inv_norm) / sums[1];
+    for (int i = tid; i < N; i += T) {
+      const int slot = rfft_in_slot(i, log2m);
+      double wave = 0.0;
+      if (i < W)
+        wave = bufd[slot] * inv_norm + randn_from_u32(rn[i]) * kMySafeGuardMinimum - aux[i] * inv_norm * coef;
+      bufd[slot] = wave;
+    }
   }
-  {
-    double v2[2] = {s1, s2};
-    block_sum<2>(v2, red);
-    s1 = v2[0]; s2 = v2[1];
-  }
-  const double coef = s1 / s2;
-  for (int i = tid; i < W; i += T) bufd[rfft_in_slot(i, log2m)] -= aux[i] * coef;
 
   // ---- GetPowerSpectrum (:64-82) -----------------------------------------------------------
   fft_dit<LM, false, 256, 4>(buf, log2m, tw);
@@ -141,7 +142,8 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
       const double high = interp1q_at(origin_axis, inv_df, bufd, len, add_rn(fa, width));
       const double sm = (high - low) / width;
       // AddInfinitesimalNoise (:147-151) then log (:38-39)
-      aux[k] = log(sm + fabs(randn_from_u32(rn2[k])) * kEps);
+      // the logarithm feeds the FP32 liftering transforms: FP32 accuracy is all that survives
+      aux[k] = logf(static_cast<float>(sm + fabs(randn_from_u32(rn2[k])) * kEps));
     }
   }
   __syncthreads();
@@ -158,15 +160,15 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
     __syncthreads();                                     // everyone has read aux
     for (int k = tid; k <= half; k += T) {
       const float re = rfft_bin(fb, log2m, k, twf).x;
-      double lifter = 1.0, comp = (1.0 - 2.0 * q1) + 2.0 * q1;
+      float lifter = 1.f, comp = 1.f;
       if (k > 0) {
-        const double quefrency = (double)k / fs;
-        double sn, cs;
-        sincospi(f0c * quefrency, &sn, &cs);             // sin(pi f0 q), cos(pi f0 q)
-        lifter = sn / (kPi * f0c * quefrency);
-        comp = (1.0 - 2.0 * q1) + 2.0 * q1 * (2.0 * cs * cs - 1.0);   // cos(2 pi f0 q)
+        const float fq = static_cast<float>(f0c * ((double)k / fs));    // f0 * quefrency
+        float sn, cs;
+        sincospif(fq, &sn, &cs);                         // sin(pi f0 q), cos(pi f0 q)
+        lifter = sn / (static_cast<float>(kPi) * fq);
+        comp = static_cast<float>(1.0 - 2.0 * q1) + static_cast<float>(2.0 * q1) * (2.f * cs * cs - 1.f);   // cos(2 pi f0 q)
       }
-      lif[k] = static_cast<float>(re * lifter * comp / N);
+      lif[k] = re * lifter * comp * (1.f / N);
     }
     __syncthreads();
     for (int k = tid; k < half; k += T) {
@@ -203,7 +205,7 @@ bool cheaptrick_run(const UttView& u, int fs, int total_frames, const int* frame
   long long mx = 0;
   for (long long v : h_tot) mx = v > mx ? v : mx;
   if (!ensure_randn((size_t)mx)) return false;
-  const size_t smem = cpad_size(fft_size / 2) * sizeof(double2) + (fft_size + 16 + 96) * sizeof(double);
+  const size_t smem = cpad_size(fft_size / 2) * sizeof(double2) + (fft_size + 16 + 128) * sizeof(double);
   KernelTimer kt1("cheaptrick_kernel");
 #define WB_CT_LAUNCH(L)                                                                                             \
   do {                                                                                                              \
