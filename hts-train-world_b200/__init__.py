@@ -120,6 +120,13 @@ def lib():
         "wb200_batch_get_y_pcm16": (i32, [vp, vp]),
         "wb200_batch_device_ptr": (vp, [vp, C.c_char_p]),
         "wb200_batch_lf0_stats": (i32, [vp, _dp]),
+        "wb200_batch_code": (i32, [vp, i32, i32]),
+        "wb200_batch_get_coded": (i32, [vp, vp, vp, vp]),
+        "wb200_batch_decode_mgc": (i32, [vp, i32, i32, vp]),
+        "wb200_batch_feature_stats": (i32, [vp, _dp]),
+        "GetNumberOfAperiodicities": (i32, [i32]),
+        "CodeSpectralEnvelope": (None, [_dpp, i32, i32, i32, i32, _dpp]),
+        "DecodeSpectralEnvelope": (None, [_dpp, i32, i32, i32, i32, _dpp]),
         "wb200_sync": (i32, []),
     }
     for name, (res, args) in sigs.items():
@@ -270,6 +277,20 @@ def synthesis(f0, sp, ap, fft_size, frame_period, fs, y_length=None):
     return _nan_check(y, "Synthesis")
 
 
+def code_spectral_envelope(sp, fs, fft_size, number_of_dimensions):
+    sp = np.ascontiguousarray(sp, np.float64)
+    out = np.zeros((sp.shape[0], number_of_dimensions))
+    lib().CodeSpectralEnvelope(_rows(sp), sp.shape[0], fs, fft_size, number_of_dimensions, _rows(out))
+    return _nan_check(out, "CodeSpectralEnvelope")
+
+
+def decode_spectral_envelope(coded, fs, fft_size):
+    coded = np.ascontiguousarray(coded, np.float64)
+    out = np.zeros((coded.shape[0], fft_size // 2 + 1))
+    lib().DecodeSpectralEnvelope(_rows(coded), coded.shape[0], fs, fft_size, coded.shape[1], _rows(out))
+    return _nan_check(out, "DecodeSpectralEnvelope")
+
+
 # ---------------------------------------------------------------------------------------------
 # the batched path
 # ---------------------------------------------------------------------------------------------
@@ -401,6 +422,30 @@ class Corpus:
             out = np.zeros(n, np.int16)
         ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
         _check(lib().wb200_batch_get_y_pcm16(self._h, ptr), "get_y_pcm16")
+        return out
+
+    def code(self, mgc_dim=50, bap_dim=24):
+        """The analysis tool's float32 lf0 / mgc / bap (W/test/analysis.cpp:293-390); dimensions as
+        data/Makefile.in:214 passes them (MGCORDER + 1 = 50, 24 aperiodicity coefficients)."""
+        self.mgc_dim, self.bap_dim = int(mgc_dim), int(bap_dim)
+        _check(lib().wb200_batch_code(self._h, self.mgc_dim, self.bap_dim), "batch code")
+
+    def coded(self):
+        lf0 = np.zeros(self.total_frames, np.float32)
+        mgc = np.zeros((self.total_frames, self.mgc_dim), np.float32)
+        bap = np.zeros((self.total_frames, self.bap_dim), np.float32)
+        _check(lib().wb200_batch_get_coded(self._h, lf0.ctypes.data, mgc.ctypes.data, bap.ctypes.data), "get_coded")
+        return lf0, mgc, bap
+
+    def decode_mgc(self, fft_size, mgc):
+        mgc = np.ascontiguousarray(mgc, np.float32)
+        self.fft_size = int(fft_size)
+        _check(lib().wb200_batch_decode_mgc(self._h, self.fft_size, mgc.shape[1], mgc.ctypes.data), "decode_mgc")
+
+    def feature_stats(self):
+        """[(1 + mgc_dim), 3] = {count, sum, sum of squares}: row 0 voiced lf0, rows 1.. mgc dims."""
+        out = np.zeros((1 + self.mgc_dim, 3))
+        _check(lib().wb200_batch_feature_stats(self._h, _ptr(out)), "feature_stats")
         return out
 
     def lf0_stats(self):

@@ -256,6 +256,37 @@ void Harvest(const double* x, int x_length, int fs, const HarvestOption* option,
   if (!ok) fill_nan(f0, n);
 }
 
+int GetNumberOfAperiodicities(int fs) {              // W/src/codec.cpp:211-214
+  return static_cast<int>(fmin(kUpperLimit, fs / 2.0 - kFrequencyInterval) / kFrequencyInterval);
+}
+
+// rows <-> coded through the device codec; host code only gathers / scatters the double** rows
+static void codec_host(const double* const* in, int f0_length, int fs, int fft_size, int ndim, bool encode,
+                       double** out) {
+  if (f0_length <= 0) return;
+  const int cols_in = encode ? fft_size / 2 + 1 : ndim, cols_out = encode ? ndim : fft_size / 2 + 1;
+  std::vector<double> flat_in((size_t)f0_length * cols_in), flat_out((size_t)f0_length * cols_out, kNaN);
+  for (int i = 0; i < f0_length; ++i) memcpy(flat_in.data() + (size_t)i * cols_in, in[i], cols_in * sizeof(double));
+  Context* c = ctx();
+  DevBuf<double> d_in, d_out;
+  bool ok = c && d_in.alloc(flat_in.size()) && d_out.alloc(flat_out.size()) &&
+            WB_CUDA(cudaMemcpyAsync(d_in.p, flat_in.data(), flat_in.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (ok) ok = encode ? codec_encode_run(d_in.p, f0_length, fs, fft_size, ndim, 1.0, 0.0, 0.0, d_out.p)
+                      : codec_decode_run(d_in.p, f0_length, fs, fft_size, ndim, d_out.p);
+  ok = ok && WB_CUDA(cudaMemcpyAsync(flat_out.data(), d_out.p, flat_out.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream)) &&
+       WB_CUDA(cudaStreamSynchronize(c->stream));
+  if (!ok) std::fill(flat_out.begin(), flat_out.end(), kNaN);
+  scatter_rows(flat_out, f0_length, cols_out, out);
+}
+void CodeSpectralEnvelope(const double* const* spectrogram, int f0_length, int fs, int fft_size,
+                          int number_of_dimensions, double** coded_spectral_envelope) {
+  codec_host(spectrogram, f0_length, fs, fft_size, number_of_dimensions, true, coded_spectral_envelope);
+}
+void DecodeSpectralEnvelope(const double* const* coded_spectral_envelope, int f0_length, int fs, int fft_size,
+                            int number_of_dimensions, double** spectrogram) {
+  codec_host(coded_spectral_envelope, f0_length, fs, fft_size, number_of_dimensions, false, spectrogram);
+}
+
 // =============================================================================================
 // extension API
 // =============================================================================================
@@ -488,6 +519,51 @@ void* wb200_batch_device_ptr(wb200_batch* h, const char* which) {
   if (w == "ap") return b.ap.p;
   if (w == "y") return b.y.p;
   return nullptr;
+}
+int wb200_batch_code(wb200_batch* h, int mgc_dim, int bap_dim) {
+  if (!ctx()) return 1;
+  return batch_code_features(&h->b, mgc_dim, bap_dim) ? 0 : 1;
+}
+int wb200_batch_get_coded(wb200_batch* h, float* lf0, float* mgc, float* bap) {
+  Batch& b = h->b;
+  const size_t F = (size_t)b.total_frames;
+  if (lf0 && d2h(lf0, b.lf0.p, F * sizeof(float))) return 1;
+  if (mgc && d2h(mgc, b.mgc.p, F * b.mgc_dim * sizeof(float))) return 1;
+  if (bap && d2h(bap, b.bap.p, F * b.bap_dim * sizeof(float))) return 1;
+  return 0;
+}
+__global__ void mgc_unscale_kernel(const float* __restrict__ mgc, long long n, int ndim, double* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = (double)mgc[i] - ((i % ndim) == 0 ? 12.0 : 0.0);           // undo c0 + 12 (analysis.cpp:307)
+}
+__global__ void sp_unscale_kernel(double* __restrict__ sp, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) sp[i] *= 1e-4;                                            // undo sp * 1e4 (analysis.cpp:297)
+}
+int wb200_batch_decode_mgc(wb200_batch* h, int fft_size, int mgc_dim, const float* host_mgc) {
+  Context* c = ctx();
+  if (!c) return 1;
+  Batch& b = h->b;
+  const long long F = b.total_frames, n = F * mgc_dim, ns = F * (fft_size / 2 + 1);
+  DevBuf<float> d_f;
+  DevBuf<double> d_c;
+  if (!d_f.alloc((size_t)n) || !d_c.alloc((size_t)n) || !b.sp.alloc((size_t)ns)) return 1;
+  b.fft_size = fft_size;
+  if (F == 0) return 0;
+  if (!WB_CUDA(cudaMemcpyAsync(d_f.p, host_mgc, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream))) return 1;
+  mgc_unscale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_f.p, n, mgc_dim, d_c.p);
+  WB_LAUNCH_CHECK();
+  if (!codec_decode_run(d_c.p, (int)F, b.fs, fft_size, mgc_dim, b.sp.p)) return 1;
+  sp_unscale_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(b.sp.p, ns);
+  WB_LAUNCH_CHECK();
+  return WB_CUDA(cudaStreamSynchronize(c->stream)) ? 0 : 1;
+}
+int wb200_batch_lf0_stats(wb200_batch* h, double* out3);
+int wb200_batch_feature_stats(wb200_batch* h, double* out) {
+  if (!ctx()) return 1;
+  if (!batch_feature_stats(&h->b, out)) return 1;
+  return wb200_batch_lf0_stats(h, out);                                 // row 0: voiced lf0
 }
 int wb200_batch_lf0_stats(wb200_batch* h, double* out3) {
   Context* c = ctx();

@@ -34,6 +34,9 @@ struct Batch {
   DevBuf<double> f0_raw, f0;           // [total_frames]
   int fft_size = 0;                    // CheapTrick / Synthesis size
   DevBuf<double> sp, ap;               // [total_frames][fft_size/2+1]
+  // coded features of the analysis tool (W/test/analysis.cpp:293-390), float32 like its files
+  int mgc_dim = 0, bap_dim = 0;
+  DevBuf<float> lf0, mgc, bap;         // [total_frames], [total_frames][mgc_dim], [total_frames][bap_dim]
   // synthesis
   std::vector<long long> h_y_off;
   std::vector<int> h_y_len;
@@ -71,6 +74,13 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
 bool synthesis_run(Batch* b, const int* y_len);
 struct HarvestParams { double f0_floor, f0_ceil, frame_period; };
 bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out);
+
+// mel-DCT codec (wb_codec.cu): rows [n_frames][fft_size/2+1] <-> coded [n_frames][ndim], device pointers
+bool codec_encode_run(const double* d_rows, int n_frames, int fs, int fft_size, int ndim, double scale,
+                      double zero_floor, double c0_add, double* d_out);
+bool codec_decode_run(const double* d_coded, int n_frames, int fs, int fft_size, int ndim, double* d_rows);
+bool batch_code_features(Batch* b, int mgc_dim, int bap_dim);
+bool batch_feature_stats(Batch* b, double* h_out);
 
 // generic helper: exclusive prefix sum of counts within each utterance's frame range.
 // out[f] = sum of counts[g] for g in [f_off[u], f); totals[u] = sum over the utterance.

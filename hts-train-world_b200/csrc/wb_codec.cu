@@ -1,0 +1,289 @@
+// world-b200: mel-DCT coding / decoding of spectral envelopes (the analysis tool's codec tail).
+//
+// Reference: W/src/codec.cpp — CodeSpectralEnvelope :266-295, CodeOneFrame :122-134, DCTForCodec
+// :72-88, GetParametersForCoding :161-179, DecodeSpectralEnvelope :297-324, DecodeOneFrame
+// :139-156, IDCTForCodec :93-117, GetParametersForDecoding :184-209; interp1
+// W/src/matlabfunctions.cpp:157-182.  The tool-level scalings (sp x 1e4, zero -> 1e-4, c0 + 12;
+// ap x 1e4, c0 - 9.21034; lf0 = log f0, 0 stays 0; float32 outputs) are W/test/analysis.cpp
+// :293-390.
+//
+// One CTA per frame: the row is read once from HBM, log / interp1 onto the mel grid / DCT (one
+// real FFT of fft_size/2 points) happen in shared memory, and only number_of_dimensions values
+// go back -- 20x less device-to-host traffic than the raw double rows.  The interp1 segment
+// index and weight of every mel point depend only on (fs, fft_size) and come from a table
+// computed once on the host with the reference's histc semantics.
+#include <math.h>
+#include <algorithm>
+#include <map>
+#include <vector>
+#include "wb_batch.h"
+#include "wb_fft.cuh"
+
+namespace wb {
+namespace {
+
+constexpr double kM0 = 1127.01048, kF0mel = 700.0, kFloorFrequency = 40.0, kCeilFrequency = 20000.0;
+inline double freq_to_mel(double f) { return kM0 * log(f / kF0mel + 1.0); }
+inline double mel_to_freq(double m) { return kF0mel * (exp(m / kM0) - 1.0); }
+
+struct CodecTables {
+  int fs = 0, fft_size = 0, ndim = 0, max_dim = 0, log2max = 0;
+  DevBuf<int> enc_idx;        // [max_dim] lower knot (0-based) of every mel point
+  DevBuf<double> enc_s;       // [max_dim] interpolation weight
+  DevBuf<double2> enc_w;      // [ndim] DCT weights (:169-174)
+  DevBuf<int> dec_idx;        // [fft_size/2 + 1] lower knot in the (max_dim + 2)-point mel spectrum
+  DevBuf<double> dec_s;
+  DevBuf<double2> dec_w;      // [ndim] IDCT weights (:193-197)
+};
+
+// interp1 segment of one query: k = clamp(upper_bound(x, xi), 1, n - 1),
+// s = (xi - x[k-1]) / (x[k] - x[k-1]).  Returns k - 1.
+int interp_segment(const std::vector<double>& x, double xi, double* s) {
+  const int n = (int)x.size();
+  int k = (int)(std::upper_bound(x.begin(), x.end(), xi) - x.begin());
+  k = std::max(1, std::min(n - 1, k));
+  *s = (xi - x[k - 1]) / (x[k] - x[k - 1]);
+  return k - 1;
+}
+
+std::map<std::vector<int>, CodecTables*> g_codec;
+
+CodecTables* codec_tables(int fs, int fft_size, int ndim) {
+  const std::vector<int> key = {fs, fft_size, ndim};
+  auto it = g_codec.find(key);
+  if (it != g_codec.end()) return it->second;
+  const int max_dim = fft_size / 2;
+  int log2max = 0;
+  while ((1 << log2max) < max_dim) ++log2max;
+  if ((1 << log2max) != max_dim || log2max < 4 || log2max > 13 || ndim < 1 || ndim > max_dim) {
+    set_error("codec: unsupported fft_size %d / dimensions %d", fft_size, ndim);
+    return nullptr;
+  }
+  CodecTables* t = new CodecTables();
+  t->fs = fs; t->fft_size = fft_size; t->ndim = ndim; t->max_dim = max_dim; t->log2max = log2max;
+  const double floor_mel = freq_to_mel(kFloorFrequency);
+  const double ceil_mel = freq_to_mel(std::min(fs / 2.0, kCeilFrequency));
+  // ---- coding: knots = mel(bin frequencies); the reference leaves the last of its fft_size/2+1
+  // knots uninitialised, it is never reached by the mel grid -> +inf here
+  std::vector<double> knots(max_dim + 1);
+  for (int i = 0; i < max_dim; ++i) knots[i] = freq_to_mel(static_cast<double>(i) * fs / fft_size);
+  knots[max_dim] = HUGE_VAL;
+  std::vector<int> idx(max_dim);
+  std::vector<double> s(max_dim);
+  for (int i = 0; i < max_dim; ++i) {
+    const double mel = (ceil_mel - floor_mel) * i / max_dim + floor_mel;
+    idx[i] = interp_segment(knots, mel, &s[i]);
+    if (idx[i] + 1 >= max_dim) { idx[i] = max_dim - 2; s[i] = (mel - knots[max_dim - 2]) / (knots[max_dim - 1] - knots[max_dim - 2]); }
+  }
+  std::vector<double2> w(ndim), wd(ndim);
+  for (int i = 0; i < ndim; ++i) {
+    w[i] = make_double2(2.0 * cos(i * kPi / fft_size) / sqrt((double)fft_size), 2.0 * sin(i * kPi / fft_size) / sqrt((double)fft_size));
+    wd[i] = make_double2(cos(i * kPi / fft_size) * sqrt((double)fft_size), sin(i * kPi / fft_size) * sqrt((double)fft_size));
+  }
+  w[0].x /= sqrt(2.0);
+  wd[0].x /= sqrt(2.0);
+  // ---- decoding: knots in Hz = {0, mel_to_freq(grid), fs/2}, queries = bin frequencies
+  std::vector<double> dk(max_dim + 2);
+  dk[0] = 0.0;
+  for (int i = 0; i < max_dim; ++i) dk[i + 1] = mel_to_freq((ceil_mel - floor_mel) * i / max_dim + floor_mel);
+  dk[max_dim + 1] = fs / 2.0;
+  std::vector<int> didx(fft_size / 2 + 1);
+  std::vector<double> ds(fft_size / 2 + 1);
+  for (int i = 0; i <= fft_size / 2; ++i) didx[i] = interp_segment(dk, static_cast<double>(i) * fs / fft_size, &ds[i]);
+  bool ok = t->enc_idx.alloc(max_dim) && t->enc_s.alloc(max_dim) && t->enc_w.alloc(ndim) &&
+            t->dec_idx.alloc(didx.size()) && t->dec_s.alloc(ds.size()) && t->dec_w.alloc(ndim);
+  ok = ok && WB_CUDA(cudaMemcpy(t->enc_idx.p, idx.data(), max_dim * sizeof(int), cudaMemcpyHostToDevice)) &&
+       WB_CUDA(cudaMemcpy(t->enc_s.p, s.data(), max_dim * sizeof(double), cudaMemcpyHostToDevice)) &&
+       WB_CUDA(cudaMemcpy(t->enc_w.p, w.data(), ndim * sizeof(double2), cudaMemcpyHostToDevice)) &&
+       WB_CUDA(cudaMemcpy(t->dec_idx.p, didx.data(), didx.size() * sizeof(int), cudaMemcpyHostToDevice)) &&
+       WB_CUDA(cudaMemcpy(t->dec_s.p, ds.data(), ds.size() * sizeof(double), cudaMemcpyHostToDevice)) &&
+       WB_CUDA(cudaMemcpy(t->dec_w.p, wd.data(), ndim * sizeof(double2), cudaMemcpyHostToDevice));
+  if (!ok) { delete t; return nullptr; }
+  g_codec[key] = t;
+  return t;
+}
+
+// dynamic shared memory: [ buf: cpad_size(max_dim/2) double2 | logsp: max_dim + 2 doubles ]
+// out[f][d] = DCT coefficient d of frame f (+ c0_add on d = 0).  scale multiplies the row first;
+// a scaled value of exactly 0 becomes zero_floor (W/test/analysis.cpp:297-301); pass 0 to disable.
+__global__ void __launch_bounds__(128)
+codec_encode_kernel(const double* __restrict__ rows, int half, int log2max, const int* __restrict__ idx,
+                    const double* __restrict__ s, const double2* __restrict__ weight, int ndim, double scale,
+                    double zero_floor, double c0_add, const double2* __restrict__ tw, double* __restrict__ out) {
+  extern __shared__ double2 smem2[];
+  const int max_dim = 1 << log2max, M = max_dim >> 1, log2m = log2max - 1;
+  double2* buf = smem2;
+  double* bufd = reinterpret_cast<double*>(buf);
+  double* logsp = reinterpret_cast<double*>(buf + cpad_size(M));
+  const int tid = threadIdx.x, T = 128;
+  const size_t f = blockIdx.x;
+  const double* __restrict__ row = rows + f * (half + 1);
+  for (int k = tid; k < max_dim; k += T) {        // bins 0 .. max_dim-1 are all interp1 ever reads
+    double v = row[k] * scale;
+    if (zero_floor != 0.0 && v == 0.0) v = zero_floor;
+    logsp[k] = log(v);
+  }
+  __syncthreads();
+  // mel spectrum j -> DCT input position (:75-79): even j -> j/2, odd j -> max_dim - 1 - (j-1)/2
+  for (int j = tid; j < max_dim; j += T) {
+    const int k = idx[j];
+    const double y0 = logsp[k];
+    const double v = add_rn(y0, mul_rn(s[j], add_rn(logsp[k + 1], -y0)));
+    const int pos = (j & 1) ? (max_dim - 1 - (j >> 1)) : (j >> 1);
+    bufd[rfft_in_slot(pos, log2m)] = v;
+  }
+  fft_dit<0, false, 128, 3>(buf, log2m, tw);
+  const double normalization = sqrt((double)max_dim);
+  for (int d = tid; d < ndim; d += T) {
+    const double2 X = rfft_bin(buf, log2m, d, tw);
+    const double2 w = weight[d];
+    double v = (X.x * w.x - X.y * w.y) / normalization;
+    if (d == 0) v += c0_add;
+    out[f * ndim + d] = v;
+  }
+}
+
+// dynamic shared memory: [ buf: cpad_size(max_dim) double2 | mel: max_dim + 2 doubles ]
+__global__ void __launch_bounds__(128)
+codec_decode_kernel(const double* __restrict__ coded, int half, int log2max, const int* __restrict__ idx,
+                    const double* __restrict__ s, const double2* __restrict__ weight, int ndim,
+                    const double2* __restrict__ tw, double* __restrict__ rows) {
+  extern __shared__ double2 smem2[];
+  const int max_dim = 1 << log2max;
+  double2* buf = smem2;
+  double* mel = reinterpret_cast<double*>(buf + cpad_size(max_dim));
+  const int tid = threadIdx.x, T = 128;
+  const size_t f = blockIdx.x;
+  const double normalization = sqrt((double)max_dim);
+  for (int i = tid; i < max_dim; i += T) {        // IDCTForCodec (:93-106)
+    double2 z = make_double2(0.0, 0.0);
+    if (i < ndim) {
+      const double c = coded[f * ndim + i];
+      z = make_double2(c * weight[i].x * normalization, -c * weight[i].y * normalization);
+    }
+    buf[cpad(brev(i, log2max))] = z;
+  }
+  // the reference's backward c2c wrapper returns conj(sum_j x_j e^{-2 pi i j k / n}) (W/src/fft.cpp
+  // :36-46); only the real part is used, which equals the real part of the forward transform
+  fft_dit<0, false, 128, 3>(buf, log2max, tw);
+  for (int i = tid; i < max_dim / 2; i += T) {    // (:110-116)
+    mel[1 + i * 2] = buf[cpad(i)].x;
+    mel[1 + i * 2 + 1] = buf[cpad(max_dim - i - 1)].x;
+  }
+  __syncthreads();
+  if (tid == 0) { mel[0] = mel[1]; mel[max_dim + 1] = mel[max_dim]; }
+  __syncthreads();
+  for (int k = tid; k <= half; k += T) {          // DecodeOneFrame (:150-154)
+    const int q = idx[k];
+    const double y0 = mel[q];
+    const double v = add_rn(y0, mul_rn(s[k], add_rn(mel[q + 1], -y0)));
+    rows[f * (half + 1) + k] = exp(v / max_dim);
+  }
+}
+
+__global__ void lf0_kernel(const double* __restrict__ f0, int n, float* __restrict__ lf0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) lf0[i] = f0[i] != 0.0 ? static_cast<float>(log(f0[i])) : 0.f;     // ToLF0, analysis.cpp:216-224
+}
+
+__global__ void coded_to_float_kernel(const double* __restrict__ in, long long n, int ndim, int clamp_c0,
+                                      float* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = in[i];
+  if (clamp_c0 && (i % ndim) == 0 && v > 0 && v < 1e-4) v = 0;                  // analysis.cpp:349-351
+  out[i] = static_cast<float>(v);
+}
+
+// per-dimension {count, sum, sum of squares} of a [frames][ndim] float matrix
+__global__ void feature_stats_kernel(const float* __restrict__ m, int n_frames, int ndim, double* __restrict__ out3) {
+  __shared__ double red[96];
+  const int d = blockIdx.y;
+  double v[3] = {0.0, 0.0, 0.0};
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n_frames; f += gridDim.x * blockDim.x) {
+    const double x = m[(size_t)f * ndim + d];
+    v[0] += 1.0; v[1] += x; v[2] += x * x;
+  }
+  block_sum<3>(v, red);
+  if (threadIdx.x == 0) { atomicAdd(&out3[d * 3], v[0]); atomicAdd(&out3[d * 3 + 1], v[1]); atomicAdd(&out3[d * 3 + 2], v[2]); }
+}
+
+}  // namespace
+
+bool codec_encode_run(const double* d_rows, int n_frames, int fs, int fft_size, int ndim, double scale,
+                      double zero_floor, double c0_add, double* d_out) {
+  Context* c = ctx();
+  if (!c) return false;
+  if (n_frames <= 0) return true;
+  CodecTables* t = codec_tables(fs, fft_size, ndim);
+  if (!t) return false;
+  const size_t smem = cpad_size(t->max_dim / 2) * sizeof(double2) + (t->max_dim + 2) * sizeof(double);
+  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(codec_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+  KernelTimer kt("codec_encode_kernel");
+  codec_encode_kernel<<<n_frames, 128, smem, c->stream>>>(d_rows, fft_size / 2, t->log2max, t->enc_idx.p, t->enc_s.p, t->enc_w.p, ndim,
+                                                         scale, zero_floor, c0_add, c->d_twiddle, d_out);
+  WB_LAUNCH_CHECK(); kt.stop();
+  return true;
+}
+
+bool codec_decode_run(const double* d_coded, int n_frames, int fs, int fft_size, int ndim, double* d_rows) {
+  Context* c = ctx();
+  if (!c) return false;
+  if (n_frames <= 0) return true;
+  CodecTables* t = codec_tables(fs, fft_size, ndim);
+  if (!t) return false;
+  const size_t smem = cpad_size(t->max_dim) * sizeof(double2) + (t->max_dim + 2) * sizeof(double);
+  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(codec_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+  KernelTimer kt("codec_decode_kernel");
+  codec_decode_kernel<<<n_frames, 128, smem, c->stream>>>(d_coded, fft_size / 2, t->log2max, t->dec_idx.p, t->dec_s.p, t->dec_w.p, ndim,
+                                                         c->d_twiddle, d_rows);
+  WB_LAUNCH_CHECK(); kt.stop();
+  return true;
+}
+
+// the analysis tool's coded outputs (W/test/analysis.cpp:293-390) for a whole batch
+bool batch_code_features(Batch* b, int mgc_dim, int bap_dim) {
+  Context* c = ctx();
+  if (!c) return false;
+  if (!b->sp.p || !b->ap.p || b->fft_size <= 0) { set_error("code: CheapTrick and D4C have not been run"); return false; }
+  const int F = b->total_frames;
+  DevBuf<double> tmp;
+  if (!tmp.alloc((size_t)F * std::max(mgc_dim, bap_dim)) || !b->lf0.alloc(F) || !b->mgc.alloc((size_t)F * mgc_dim) ||
+      !b->bap.alloc((size_t)F * bap_dim))
+    return false;
+  b->mgc_dim = mgc_dim; b->bap_dim = bap_dim;
+  if (F == 0) return true;
+  cudaStream_t st = c->stream;
+  lf0_kernel<<<(F + 255) / 256, 256, 0, st>>>(b->f0.p, F, b->lf0.p);
+  WB_LAUNCH_CHECK();
+  if (!codec_encode_run(b->sp.p, F, b->fs, b->fft_size, mgc_dim, 1e4, 0.0001, 12.0, tmp.p)) return false;
+  long long n = (long long)F * mgc_dim;
+  coded_to_float_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tmp.p, n, mgc_dim, 0, b->mgc.p);
+  WB_LAUNCH_CHECK();
+  if (!codec_encode_run(b->ap.p, F, b->fs, b->fft_size, bap_dim, 1e4, 0.0, -9.210340, tmp.p)) return false;
+  n = (long long)F * bap_dim;
+  coded_to_float_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tmp.p, n, bap_dim, 1, b->bap.p);
+  WB_LAUNCH_CHECK();
+  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  return true;
+}
+
+bool batch_feature_stats(Batch* b, double* h_out) {   // [(1 + mgc_dim)][3]: lf0 (voiced frames), then mgc
+  Context* c = ctx();
+  if (!c) return false;
+  if (!b->mgc.p) { set_error("stats: features have not been coded"); return false; }
+  const int F = b->total_frames, nd = b->mgc_dim;
+  DevBuf<double> d;
+  if (!d.alloc((size_t)(nd + 1) * 3)) return false;
+  cudaStream_t st = c->stream;
+  WB_CUDA_OR_RETURN(cudaMemsetAsync(d.p, 0, (size_t)(nd + 1) * 3 * sizeof(double), st), false);
+  if (F > 0) {
+    feature_stats_kernel<<<dim3(64, nd), 256, 0, st>>>(b->mgc.p, F, nd, d.p + 3);
+    WB_LAUNCH_CHECK();
+  }
+  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_out, d.p, (size_t)(nd + 1) * 3 * sizeof(double), cudaMemcpyDeviceToHost, st), false);
+  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  return true;
+}
+
+}  // namespace wb

@@ -14,6 +14,7 @@
 #define WORLD_B200_H_
 #include <stdint.h>
 #include "world/cheaptrick.h"
+#include "world/codec.h"
 #include "world/d4c.h"
 #include "world/dio.h"
 #include "world/harvest.h"
@@ -92,6 +93,19 @@ WORLD_API void *wb200_batch_device_ptr(wb200_batch *b, const char *which);
 /* corpus statistics of voiced log-f0 over the batch: out = {count, sum, sum of squares};
  * the per-GPU partials that the NCCL all-reduce combines */
 WORLD_API int wb200_batch_lf0_stats(wb200_batch *b, double *out3);
+/* ---- the analysis tool's coded outputs (W/test/analysis.cpp:293-390) for the whole batch ------
+ * lf0 = log f0 (0 stays 0); mgc = CodeSpectralEnvelope(sp * 1e4, mgc_dim) with c0 + 12;
+ * bap = CodeSpectralEnvelope(ap * 1e4, bap_dim) with c0 - 9.21034; all float32 like the tool's files.
+ * Needs CheapTrick and D4C results in the batch. */
+WORLD_API int wb200_batch_code(wb200_batch *b, int mgc_dim, int bap_dim);
+WORLD_API int wb200_batch_get_coded(wb200_batch *b, float *host_lf0, float *host_mgc, float *host_bap);
+/* decode mgc back into the batch's spectrogram (DecodeSpectralEnvelope, then the inverse of the
+ * tool's scalings): the entry of Synthesis-only runs that start from float32 mgc files */
+WORLD_API int wb200_batch_decode_mgc(wb200_batch *b, int fft_size, int mgc_dim, const float *host_mgc);
+/* per-GPU partials of the corpus statistics: out[(1 + mgc_dim)][3] = {count, sum, sum of squares}
+ * of voiced lf0 (row 0) and of every mgc dimension over all frames (rows 1..mgc_dim); the NCCL
+ * all-reduce of these rows gives the corpus mean / variance */
+WORLD_API int wb200_batch_feature_stats(wb200_batch *b, double *out);
 /* block until everything queued on the library stream has finished */
 WORLD_API int wb200_sync(void);
 

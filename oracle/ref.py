@@ -85,6 +85,11 @@ def bind_world_api(lib):
     lib.InitializeHarvestOption.argtypes = [C.POINTER(HarvestOption)]
     lib.GetSamplesForHarvest.argtypes = [C.c_int, C.c_int, C.c_double]
     lib.GetSamplesForHarvest.restype = C.c_int
+    if hasattr(lib, "CodeSpectralEnvelope"):
+        lib.CodeSpectralEnvelope.argtypes = [_dpp, C.c_int, C.c_int, C.c_int, C.c_int, _dpp]
+        lib.CodeSpectralEnvelope.restype = None
+        lib.DecodeSpectralEnvelope.argtypes = [_dpp, C.c_int, C.c_int, C.c_int, C.c_int, _dpp]
+        lib.DecodeSpectralEnvelope.restype = None
     return lib
 
 
@@ -173,6 +178,32 @@ class WorldLib:
         self.lib.Synthesis(_ptr(f0), len(f0), _rows(sp), _rows(ap), fft_size,
                            float(frame_period), fs, y_length, _ptr(y))
         return y
+
+    # ---- codec (W/src/codec.cpp:266-324) and the tool's coded outputs (W/test/analysis.cpp:293-390) --
+    def code_spectral_envelope(self, sp, fs, fft_size, ndim):
+        sp = np.ascontiguousarray(sp, np.float64)
+        out = np.zeros((sp.shape[0], ndim))
+        self.lib.CodeSpectralEnvelope(_rows(sp), sp.shape[0], fs, fft_size, ndim, _rows(out))
+        return out
+
+    def decode_spectral_envelope(self, coded, fs, fft_size):
+        coded = np.ascontiguousarray(coded, np.float64)
+        out = np.zeros((coded.shape[0], fft_size // 2 + 1))
+        self.lib.DecodeSpectralEnvelope(_rows(coded), coded.shape[0], fs, fft_size, coded.shape[1], _rows(out))
+        return out
+
+    def tool_features(self, f0, sp, ap, fs, fft_size, mgc_dim=50, bap_dim=24):
+        """float32 lf0 / mgc / bap exactly as the analysis tool writes them."""
+        s = sp * 1e4
+        s[s == 0.0] = 0.0001
+        mgc = self.code_spectral_envelope(s, fs, fft_size, mgc_dim)
+        mgc[:, 0] += 12.0
+        bap = self.code_spectral_envelope(ap * 1e4, fs, fft_size, bap_dim)
+        bap[:, 0] -= 9.210340
+        tiny = (bap[:, 0] > 0) & (bap[:, 0] < 1e-4)
+        bap[tiny, 0] = 0
+        lf0 = np.where(f0 != 0, np.log(np.where(f0 != 0, f0, 1.0)), 0.0)
+        return lf0.astype(np.float32), mgc.astype(np.float32), bap.astype(np.float32)
 
     # ---- the tool's whole analysis (W/test/analysis.cpp:243-398 without the codec tail) --
     def analyze(self, x, fs, frame_period=5.0, threshold=0.0):

@@ -182,6 +182,57 @@ def test_batch_equals_single_calls(wb, reference_lib):
     c.close()
 
 
+# ---- codec tail -----------------------------------------------------------------
+@pytest.mark.parametrize("name", ["synthetic48k_u7", "synthetic16k_u11", "vaiueo2d"])
+def test_codec_against_reference(wb, reference_lib, name):
+    """CodeSpectralEnvelope / DecodeSpectralEnvelope (W/src/codec.cpp:266-324) through the C ABI."""
+    g = load_golden(name)
+    x, fs = _x(g), int(g["fs"])
+    o = reference_lib.analyze(x, fs)
+    for ndim in (50, 24):
+        ref_c = reference_lib.code_spectral_envelope(o["sp"] * 1e4, fs, o["fft_size"], ndim)
+        our_c = wb.code_spectral_envelope(o["sp"] * 1e4, fs, o["fft_size"], ndim)
+        assert np.max(np.abs(our_c - ref_c)) <= 1e-9 * max(1.0, np.max(np.abs(ref_c)))
+        ref_d = reference_lib.decode_spectral_envelope(ref_c, fs, o["fft_size"])
+        our_d = wb.decode_spectral_envelope(ref_c, fs, o["fft_size"])
+        assert M.lsd_db(ref_d, our_d)[1] <= 1e-6
+
+
+def test_batch_coded_features_and_stats(wb, reference_lib):
+    """float32 lf0 / mgc / bap of the analysis tool for a ragged batch, the statistics partials the
+    NCCL reduce combines, and the decode -> Synthesis entry of config 4."""
+    from hts_train_world_b200 import signals
+    fs = 48000
+    pcms = [signals.make_utterance(60 + i, fs, duration=d)[0].numpy() for i, d in enumerate([0.7, 1.3])]
+    c = wb.Corpus(fs, [len(p) for p in pcms])
+    c.upload_pcm16(np.concatenate(pcms))
+    refs = [reference_lib.analyze(p.astype(np.float64) / 32768.0, fs) for p in pcms]
+    # inject the reference's f0 / sp / ap so only the codec is under test
+    c.set_f0(np.concatenate([r["f0"] for r in refs]))
+    c.set_sp_ap(refs[0]["fft_size"], np.concatenate([r["sp"] for r in refs]), np.concatenate([r["ap"] for r in refs]))
+    c.code(50, 24)
+    lf0, mgc, bap = c.coded()
+    want = [reference_lib.tool_features(r["f0"], r["sp"], r["ap"], fs, r["fft_size"]) for r in refs]
+    wl, wm, wbp = (np.concatenate([w[i] for w in want]) for i in range(3))
+    assert np.array_equal(lf0, wl)
+    assert np.max(np.abs(mgc - wm)) <= 2e-6 * np.max(np.abs(wm))
+    assert np.max(np.abs(bap - wbp)) <= 2e-6 * max(1.0, np.max(np.abs(wbp)))
+    st = c.feature_stats()
+    v = wl[wl != 0].astype(np.float64)
+    assert st[0, 0] == len(v) and np.isclose(st[0, 1], np.log(np.concatenate([r["f0"] for r in refs])[wl != 0]).sum())
+    assert np.all(st[1:, 0] == len(wl))
+    assert np.allclose(st[1:, 1], mgc.astype(np.float64).sum(axis=0), rtol=1e-9)
+    assert np.allclose(st[1:, 2], (mgc.astype(np.float64) ** 2).sum(axis=0), rtol=1e-9)
+    # decode the float32 mgc back into the batch and compare with the reference's decode
+    c.decode_mgc(refs[0]["fft_size"], mgc)
+    sp_dec = c.sp()
+    m = wm.astype(np.float64).copy()
+    m[:, 0] -= 12.0
+    ref_dec = reference_lib.decode_spectral_envelope(m, fs, refs[0]["fft_size"]) * 1e-4
+    assert M.lsd_db(ref_dec, sp_dec)[1] <= 1e-4
+    c.close()
+
+
 # ---- edge cases ------------------------------------------------------------------------------------
 def test_all_unvoiced_and_digital_silence(wb, reference_lib):
     fs = 16000
