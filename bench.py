@@ -38,6 +38,7 @@ FS = 48000
 FRAME_PERIOD = 5.0
 METRIC = "xRT (audio s/s) WORLD analysis+synthesis, 48 kHz 5 ms"
 UNIT = "audio_s/s"
+MGC_DIM, BAP_DIM = 50, 24       # MGCORDER + 1 and the tool's default (data/Makefile.in:214, analysis.cpp:324-328)
 
 
 # =================================================================================================
@@ -63,8 +64,8 @@ def _worker_main(conn, opt):
             conn.send(len(cache))
             continue
         # "run": Dio -> StoneMask -> CheapTrick -> D4C -> Synthesis with the analysis tool's options
-        # (W/test/analysis.cpp:93-203, W/test/synth.cpp:259); per-stage seconds are returned
-        acc = np.zeros(5)
+        # (W/test/analysis.cpp:93-203, W/test/synth.cpp:259) and the tool's codec tail (:293-358); per-stage seconds
+        acc = np.zeros(6)
         for u in utts:
             x = cache[u]
             t = [time.perf_counter()]
@@ -74,6 +75,7 @@ def _worker_main(conn, opt):
             n = sp.shape[1] * 2 - 2
             ap = R.d4c(x, FS, tp, f0, n, threshold=0.0); t.append(time.perf_counter())
             R.synthesis(f0, sp, ap, n, FRAME_PERIOD, FS); t.append(time.perf_counter())
+            R.tool_features(f0, sp, ap, FS, n, MGC_DIM, BAP_DIM); t.append(time.perf_counter())
             acc += np.diff(t)
         conn.send(acc)
 
@@ -130,7 +132,7 @@ def run_reference_pass(pool, utts, passes):
     from hts_train_world_b200 import signals
     audio = sum(signals.utterance_params(u)["T"] for u in utts)
     pool.prepare(utts)          # synthetic signals are generated untimed, inside each worker
-    times, stages = [], np.zeros(5)
+    times, stages = [], np.zeros(6)
     for _ in range(passes):
         dt, st = pool.run(utts)
         times.append(dt)
@@ -164,11 +166,11 @@ def reference_arm(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "1132-utterance synthetic 48 kHz corpus, 5 ms frames, fft_size 2048: "
-                               "Dio+StoneMask+CheapTrick+D4C+Synthesis (bounded sample per step)",
+                               "Dio+StoneMask+CheapTrick+D4C+codec+Synthesis (bounded sample per step)",
                    "fs": FS, "frame_period_ms": FRAME_PERIOD, "utterances_per_step": len(utts)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "stage_cpu_seconds": dict(zip(["dio", "stonemask", "cheaptrick", "d4c", "synthesis"],
+        "stage_cpu_seconds": dict(zip(["dio", "stonemask", "cheaptrick", "d4c", "synthesis", "codec"],
                                       [float(s) for s in stages])),
         "gpu_launches": 0,
     }
@@ -279,6 +281,9 @@ def ours_arm(args):
     c = wb.Corpus(FS, lengths, FRAME_PERIOD)
     y_host = None
     f0_host = torch.empty(c.total_frames, dtype=torch.float64).pin_memory()
+    lf0_host = torch.empty(c.total_frames, dtype=torch.float32).pin_memory()
+    mgc_host = torch.empty((c.total_frames, MGC_DIM), dtype=torch.float32).pin_memory()
+    bap_host = torch.empty((c.total_frames, BAP_DIM), dtype=torch.float32).pin_memory()
 
     def reduce_stats(st):
         if world > 1:
@@ -290,19 +295,23 @@ def ours_arm(args):
     def step_resident():
         c.set_pcm16_device(pcm_dev)
         c.analyze(f0=args.f0)
+        c.code(MGC_DIM, BAP_DIM)
         c.synthesis()
-        return reduce_stats(c.lf0_stats())
+        return reduce_stats(c.feature_stats())
 
     def step_e2e():
         nonlocal y_host
         c.upload_pcm16(pcm_host)
         c.analyze(f0=args.f0)
+        c.code(MGC_DIM, BAP_DIM)
         c.synthesis()
         if y_host is None:
             y_host = torch.empty(int(wb.lib().wb200_batch_total_y(c._h)), dtype=torch.int16).pin_memory()
         c.y_pcm16(y_host)
+        wb._check(wb.lib().wb200_batch_get_coded(c._h, lf0_host.data_ptr(), mgc_host.data_ptr(), bap_host.data_ptr()),
+                  "get_coded")
         wb._check(wb.lib().wb200_batch_get_f0(c._h, wb.C.cast(f0_host.data_ptr(), wb._dp), 1), "get_f0")
-        return reduce_stats(c.lf0_stats())
+        return reduce_stats(c.feature_stats())
 
     def barrier():
         if world > 1:
@@ -343,18 +352,26 @@ def ours_arm(args):
                  ["d4c_main_kernel", "d4c_lovetrain_kernel", "cheaptrick_kernel", "synth_pulse_kernel",
                   "synth_timebase_kernel", "stonemask_kernel", "dio_filter_kernel", "dio_zc_kernel",
                   "dio_candidates_kernel", "dio_fix_kernel", "harvest_iir_kernel", "harvest_filter_kernel",
-                  "harvest_zc_kernel", "harvest_refine_kernel", "harvest_fix_kernel", "harvest_smooth_kernel"]}
+                  "harvest_zc_kernel", "harvest_refine_kernel", "harvest_fix_kernel", "harvest_smooth_kernel",
+                  "codec_encode_kernel"]}
     wb.kernel_timing(False)
     stage_ms = wb.stage_times()
     clk = clocks.stop(t0, t1) if rank == 0 else None
-    value = audio_s * world * args.steps / (ms * 1e-3)
+    if world > 1:
+        ta = torch.tensor([audio_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ta)
+        audio_total = float(ta[0])
+    else:
+        audio_total = audio_s
+    value = audio_total * args.steps / (ms * 1e-3)
 
     # ---- end to end from host memory --------------------------------------------------------------
     step_e2e()
     ms_e, wall_e, _, _ = timed(step_e2e, args.steps)
-    e2e_value = audio_s * world * args.steps / (max(ms_e, wall_e) * 1e-3)
+    e2e_value = audio_total * args.steps / (max(ms_e, wall_e) * 1e-3)
     h2d = pcm_host.numel() * 2
-    d2h = y_host.numel() * 2 + f0_host.numel() * 8 + 24
+    d2h = y_host.numel() * 2 + f0_host.numel() * 8 + (lf0_host.numel() + mgc_host.numel() + bap_host.numel()) * 4 + \
+        (1 + MGC_DIM) * 24
 
     # ---- roofline of the dominant kernel --------------------------------------------------------------
     f0 = f0_host.numpy().copy()
@@ -412,7 +429,7 @@ def ours_arm(args):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%d-utterance synthetic 48 kHz corpus per GPU (%.0f s audio, %d frames), 5 ms "
-                               "frames, fft_size %d: %s+CheapTrick+D4C+Synthesis + lf0 statistics"
+                               "frames, fft_size %d: %s+CheapTrick+D4C+codec+Synthesis + lf0/mgc statistics"
                                % (len(lengths), audio_s, c.total_frames, c.fft_size,
                                   "Harvest" if args.f0 == "harvest" else "Dio+StoneMask"),
                    "fs": FS, "frame_period_ms": FRAME_PERIOD, "utterances_per_gpu": len(lengths),
@@ -420,7 +437,8 @@ def ours_arm(args):
                    "l2": "inputs larger than L2 (%.0f MB PCM, GBs of intermediates per step)" % (h2d / 1e6)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": max(ms_e, wall_e) / args.steps,
-                "result": "16-bit resynthesised waveform + f0 contour + lf0 statistics; sp/ap stay in HBM"},
+                "result": "the analysis tool's float32 lf0/mgc/bap + f0 + 16-bit resynthesised waveform + lf0/mgc statistics; "
+                          "sp/ap stay in HBM"},
         "gpu_launches": int(launches),
         "wall_ms_per_step": wall / args.steps,
         "stage_ms": stage_ms,
@@ -428,7 +446,8 @@ def ours_arm(args):
         "kernels": kernels,
         "peaks": {"fp64_tflops_measured": fp64_peak, "fp32_tflops_measured": fp32_peak, "hbm_gbs": hbm_peak},
         "clocks": clk,
-        "lf0_stats": corpus.merge_stats([stats]),
+        "lf0_stats": corpus.merge_stats([stats[0]]),
+        "mgc0_stats": corpus.merge_stats([stats[1]]),
         "gen_seconds": t_gen,
     }
 
@@ -443,7 +462,7 @@ def ours_arm(args):
                 "value": audio / times[0], "unit": UNIT, "cores": cores, "kind": "reference",
                 "sample": "%d utterances (ids 0..%d, %.1f s audio), one pass, one process per core, reference "
                           "sources compiled -O3" % (len(utts), len(utts) - 1, audio),
-                "stage_cpu_seconds": dict(zip(["dio", "stonemask", "cheaptrick", "d4c", "synthesis"],
+                "stage_cpu_seconds": dict(zip(["dio", "stonemask", "cheaptrick", "d4c", "synthesis", "codec"],
                                               [float(s) for s in stages]))}
         else:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
