@@ -113,3 +113,18 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(root, f)).read()
                 assert not pat.search(src), "%s references the oracle" % f
+
+
+def test_reference_tools_link_against_the_library():
+    """The reference's unmodified analysis / synth tools, linked against libworld_b200.so instead
+    of libworld.a (oracle/Makefile `tools`), load and reach their own argument check."""
+    import subprocess
+    bin_dir = os.path.join(ROOT, "oracle", "_ref")
+    if os.path.isdir("/root/reference/externs/WORLD_v2/test"):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "tools"], check=True, capture_output=True)
+    for tool in ("analysis_b200", "synth_b200"):
+        p = os.path.join(bin_dir, tool)
+        if not os.path.exists(p):
+            pytest.skip(p + " not built and /root/reference is absent")
+        r = subprocess.run([p], capture_output=True, text=True)
+        assert "sage" in (r.stdout + r.stderr)            # "Usage: ..." / "usage" from the tool itself

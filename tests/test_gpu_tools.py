@@ -1,0 +1,84 @@
+"""GPU: the reference's OWN command-line tools (externs/WORLD_v2/test/analysis.cpp, synth.cpp —
+compiled unmodified by oracle/Makefile `tools`) linked against libworld_b200.so instead of
+libworld.a, run next to the same tools linked against the reference library.  This is the
+drop-in claim of BASELINE.json's north_star at the level data/Makefile.in:214 uses it."""
+import os
+import subprocess
+import wave
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from oracle import metrics as M
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _tool(name):
+    p = os.path.join(BIN, name)
+    if not os.path.exists(p):
+        pytest.skip("%s not built (make -C oracle tools, needs /root/reference)" % p)
+    return p
+
+
+def _write_wav(path, pcm, fs):
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(fs)
+        w.writeframes(pcm.astype("<i2").tobytes())
+
+
+def _read_wav(path):
+    with wave.open(path, "rb") as w:
+        return np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").astype(np.float64)
+
+
+def _run(args):
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name", ["arctic_a0001", "synthetic48k_u7"])
+def test_analysis_tool_is_a_drop_in(tmp_path, name):
+    g = load_golden(name)
+    fs, fft = int(g["fs"]), int(g["fft_size"])
+    wav = str(tmp_path / "in.wav")
+    _write_wav(wav, g["pcm"], fs)
+    out = {}
+    for tag in ("ref", "b200"):
+        files = [str(tmp_path / ("%s.%s" % (tag, e))) for e in ("lf0", "mgc", "bap")]
+        # data/Makefile.in:214: analysis wav lf0 mgc bap 5 FFTLEN MGCDIM  (bap dimension defaults to 24)
+        _run([_tool("analysis_" + tag), wav] + files + ["5", str(fft), "50"])
+        out[tag] = [np.fromfile(f, np.float32).astype(np.float64) for f in files]
+    lf0_r, mgc_r, bap_r = out["ref"]
+    lf0_b, mgc_b, bap_b = out["b200"]
+    assert len(lf0_r) == len(lf0_b) == len(g["f0"]) and len(mgc_r) == len(mgc_b) == 50 * len(lf0_r)
+    assert len(bap_r) == len(bap_b) == 24 * len(lf0_r)
+    f0_r, f0_b = np.where(lf0_r != 0, np.exp(lf0_r), 0.0), np.where(lf0_b != 0, np.exp(lf0_b), 0.0)
+    assert M.vuv_agreement(f0_r, f0_b) >= M.TOL_VUV_AGREEMENT
+    assert M.f0_rel_error(f0_r, f0_b) <= M.TOL_F0_REL
+    same = (f0_r > 0) == (f0_b > 0)
+    rows = np.repeat(same, 50)
+    # 0.01 dB of log spectral distance is 1.15e-3 nepers per bin; the orthonormal DCT keeps that norm
+    assert np.max(np.abs(mgc_r[rows] - mgc_b[rows])) <= 1.15e-3 * np.sqrt(fft / 2)
+    assert np.max(np.abs(bap_r[np.repeat(same, 24)] - bap_b[np.repeat(same, 24)])) <= 1.15e-3 * np.sqrt(fft / 2)
+
+
+def test_synth_tool_is_a_drop_in(tmp_path):
+    g = load_golden("synthetic16k_u11")
+    fs, fft = int(g["fs"]), int(g["fft_size"])
+    wav = str(tmp_path / "in.wav")
+    _write_wav(wav, g["pcm"], fs)
+    raw = [str(tmp_path / ("ref.%s" % e)) for e in ("f0", "sp", "ap")]
+    _run([_tool("analysis_ref"), wav] + raw + ["5", str(fft)])          # uncompressed float32 f0 / sp / ap
+    ys = {}
+    for tag in ("ref", "b200"):
+        o = str(tmp_path / ("%s.wav" % tag))
+        _run([_tool("synth_" + tag)] + raw + [o, "5", str(fft), str(fs)])
+        ys[tag] = _read_wav(o)
+    assert len(ys["ref"]) == len(ys["b200"]) > 0
+    assert np.max(np.abs(ys["ref"] - ys["b200"])) <= 1.0            # 16-bit truncation of values 1e-6 apart
+    assert M.snr_db(ys["ref"], ys["b200"]) >= M.TOL_SNR_DB
