@@ -283,7 +283,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
   double* cbufd = reinterpret_cast<double*>(cbuf);
   double* pw = reinterpret_cast<double*>(cbuf + d4c_cbuf_slots(Nd, c.nbands));
   double* red = pw + Hd + 8;
-  SelectScratch* sc = reinterpret_cast<SelectScratch*>(red + 96);
+  SelectScratch* sc = reinterpret_cast<SelectScratch*>(red + 160);
   double* coarse = reinterpret_cast<double*>(sc + 1);
   const int tid = threadIdx.x;
   constexpr int T = THREADS;
@@ -311,18 +311,46 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
   for (int side = 0; side < 2; ++side) {
     const double pos = add_rn(t_pos, side == 0 ? -0.25 / cur_f0 : 0.25 / cur_f0);
     __syncthreads();                                    // previous readers of cbuf are done
-    auto cw = [log2nd](int i) { return 2 * cpad(brev(i, log2nd)); };
-    auto cv = [log2nd](int i) { return 2 * cpad(brev(i, log2nd)) + 1; };
-    const int W = windowed_waveform(x, x_len, c.fs, cur_f0, pos, kBlackman, 4.0,
-                                    rn + (size_t)side * W4, cbufd, cw, cv, red);
-    double pwr[1] = {0.0};
-    for (int i = tid; i < W; i += T) { const double v = cbuf[cslot(i)].x; pwr[0] += v * v; }
-    block_sum<1>(pwr, red);
-    const double sq = sqrt(pwr[0]);
-    for (int i = tid; i < Nd; i += T) {
-      double2 z = make_double2(0.0, 0.0);
-      if (i < W) { const double v = cbuf[cslot(i)].x / sq; z = make_double2(v, v * (i + 1.0)); }
-      cbuf[cslot(i)] = z;
+    // windowed waveform (d4c.cpp:52-84), mean removal and unit-energy normalisation (:95-100) with a
+    // single block reduction: with S1 = sum(wave), Sw = sum(w), S2 = sum(wave^2), Sxw = sum(wave w),
+    // Sww = sum(w^2):  coef = S1 / Sw,  energy of (wave - w coef) = S2 - 2 coef Sxw + coef^2 Sww.
+    const int hwl4 = d4c_hwl(4.0, c.fs, cur_f0);
+    const int W = 2 * hwl4 + 1;
+    {
+      const int origin = matlab_round(add_rn(mul_rn(pos, (double)c.fs), 0.001));
+      const double ang_step = kPi * 2.0 * cur_f0 / (4.0 * c.fs);
+      const uint32_t* __restrict__ rns = rn + (size_t)side * W4;
+      double cs, sn, cs_step, sn_step;
+      sincos((double)(tid - hwl4) * ang_step, &sn, &cs);
+      sincos((double)T * ang_step, &sn_step, &cs_step);
+      double sums[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      for (int i = tid; i < W; i += T) {
+        const double w = 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);
+        {
+          const double c2 = cs * cs_step - sn * sn_step;
+          sn = sn * cs_step + cs * sn_step;
+          cs = c2;
+        }
+        const int idx = min(x_len - 1, max(0, origin + i - hwl4));
+        const double wave = x[idx] * w + randn_from_u32(rns[i]) * kMySafeGuardMinimum;
+        cbuf[cslot(i)] = make_double2(wave, w);
+        sums[0] += wave; sums[1] += w; sums[2] += wave * wave; sums[3] += wave * w; sums[4] += w * w;
+      }
+      block_sum<5>(sums, red);
+      const double coef = sums[0] / sums[1];
+      double energy = sums[2] - 2.0 * coef * sums[3] + coef * coef * sums[4];
+      if (!(energy > 1e-8 * sums[2])) {                 // DC-dominated frame: the expansion cancels, sum directly
+        double e[1] = {0.0};
+        for (int i = tid; i < W; i += T) { const double2 z = cbuf[cslot(i)]; const double v = z.x - z.y * coef; e[0] += v * v; }
+        block_sum<1>(e, red);
+        energy = e[0];
+      }
+      const double inv_sq = 1.0 / sqrt(energy);
+      for (int i = tid; i < Nd; i += T) {
+        double2 z = make_double2(0.0, 0.0);
+        if (i < W) { const double2 q = cbuf[cslot(i)]; const double v = (q.x - q.y * coef) * inv_sq; z = make_double2(v, v * (i + 1.0)); }
+        cbuf[cslot(i)] = z;
+      }
     }
     fft_dit<LOG2ND, false, THREADS, MAXK>(cbuf, log2nd, tw);
     for (int k = tid; k <= Hd; k += T) {
@@ -504,7 +532,7 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
   if (!need_randn()) return false;
   {
     const int hd = nd / 2;
-    const size_t smem = d4c_cbuf_slots(nd, c.nbands) * sizeof(double2) + (size_t)(2 * (hd + 8) + 96) * sizeof(double) +
+    const size_t smem = d4c_cbuf_slots(nd, c.nbands) * sizeof(double2) + (size_t)(2 * (hd + 8) + 160) * sizeof(double) +
                         sizeof(SelectScratch) + (kMaxBands + 2) * sizeof(double);
     const int threads = (nd > 4096 || getenv("WB_D4C_T512")) ? 512 : 256;
     KernelTimer kt2("d4c_main_kernel");
