@@ -82,3 +82,45 @@ def test_synth_tool_is_a_drop_in(tmp_path):
     assert len(ys["ref"]) == len(ys["b200"]) > 0
     assert np.max(np.abs(ys["ref"] - ys["b200"])) <= 1.0            # 16-bit truncation of values 1e-6 apart
     assert M.snr_db(ys["ref"], ys["b200"]) >= M.TOL_SNR_DB
+
+
+def test_corpus_driver_writes_the_tools_files(tmp_path):
+    """hts-train-world_b200/driver.py = the `features:` loop of data/Makefile.in:121-242: same
+    float32 lf0 / mgc / bap files as the reference tool run file by file, clip check included."""
+    from hts_train_world_b200 import driver, signals
+    import hts_train_world_b200 as wb
+    wb.init(0)
+    fs = 16000
+    raw_dir = tmp_path / "raw"
+    raw_dir.mkdir()
+    names = []
+    for i, d in enumerate([0.6, 1.1, 0.4]):
+        pcm = signals.make_utterance(80 + i, fs, duration=d)[0].numpy()
+        pcm.astype("<i2").tofile(str(raw_dir / ("utt%d.raw" % i)))
+        names.append(("utt%d" % i, pcm))
+    clipped = names[0][1].copy()
+    clipped[100] = 32767
+    clipped.astype("<i2").tofile(str(raw_dir / "clipped.raw"))
+    (raw_dir / "empty.raw").write_bytes(b"")
+    paths = sorted(str(p) for p in raw_dir.glob("*.raw"))
+    rep = driver.extract_features(paths, str(tmp_path), fs=fs, log=lambda *_: None)
+    assert sorted(rep["skipped"]) == ["clipped", "empty"] and sorted(rep["done"]) == ["utt0", "utt1", "utt2"]
+    assert not (tmp_path / "lf0" / "clipped.lf0").exists()
+    n_voiced = 0
+    for base, pcm in names:
+        wav = str(tmp_path / (base + ".wav"))
+        _write_wav(wav, pcm, fs)
+        ref = [str(tmp_path / ("ref_%s.%s" % (base, e))) for e in ("lf0", "mgc", "bap")]
+        _run([_tool("analysis_ref"), wav] + ref + ["5", "1024", "50"])
+        lf0_r, mgc_r, bap_r = (np.fromfile(f, np.float32).astype(np.float64) for f in ref)
+        lf0_b = np.fromfile(str(tmp_path / "lf0" / (base + ".lf0")), np.float32).astype(np.float64)
+        mgc_b = np.fromfile(str(tmp_path / "mgc" / (base + ".mgc")), np.float32).astype(np.float64)
+        bap_b = np.fromfile(str(tmp_path / "bap" / (base + ".bap")), np.float32).astype(np.float64)
+        assert len(lf0_b) == len(lf0_r) and len(mgc_b) == len(mgc_r) and len(bap_b) == len(bap_r)
+        same = (lf0_r != 0) == (lf0_b != 0)
+        assert same.mean() >= 0.99
+        assert np.max(np.abs(np.exp(lf0_b[same & (lf0_r != 0)]) / np.exp(lf0_r[same & (lf0_r != 0)]) - 1)) <= M.TOL_F0_REL
+        assert np.max(np.abs(mgc_r[np.repeat(same, 50)] - mgc_b[np.repeat(same, 50)])) <= 1.15e-3 * np.sqrt(512)
+        assert np.max(np.abs(bap_r[np.repeat(same, 24)] - bap_b[np.repeat(same, 24)])) <= 1.15e-3 * np.sqrt(512)
+        n_voiced += int((lf0_b != 0).sum())
+    assert rep["stats"][0, 0] == n_voiced

@@ -118,3 +118,14 @@ def test_stats_allreduce_world_size_2_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert "rank %d ok" % r in o
+
+
+def test_driver_host_rules():
+    """clip check of data/Makefile.in:127-129 and FFTLEN of configure.ac:540-549."""
+    from hts_train_world_b200 import driver
+    ok = np.array([1, -5, 32766, -32767], np.int16)
+    assert driver.passes_clip_check(ok)
+    assert not driver.passes_clip_check(np.array([0, 32767], np.int16))
+    assert not driver.passes_clip_check(np.array([-32768, 3], np.int16))
+    assert not driver.passes_clip_check(np.zeros(0, np.int16))
+    assert [driver.fftlen_for(fs) for fs in (16000, 22050, 44100, 48000)] == [1024, 1024, 2048, 2048]
