@@ -11,6 +11,7 @@
 // randn: the reference draws (2*hwl+1) + (N/2+1) variates per frame, in frame order
 // (SURVEY Appendix A1).  A per-utterance exclusive scan of those counts gives each frame its
 // offset into the precomputed randn table, so the dither is bit-identical to the reference.
+#include <stdlib.h>
 #include "wb_batch.h"
 #include "wb_fft.cuh"
 
@@ -33,8 +34,8 @@ __global__ void cheaptrick_count_kernel(const double* __restrict__ f0, int total
 }
 
 // dynamic shared memory: [ buf: cpad_size(N/2) double2 | aux: N + 16 doubles | red: 96 doubles ]
-template <int LOG2N>      // 0: size given at run time (log2n_rt)
-__global__ void __launch_bounds__(256, 3)
+template <int LOG2N, int THREADS>      // LOG2N 0: size given at run time (log2n_rt)
+__global__ void __launch_bounds__(THREADS, 768 / THREADS)
 cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __restrict__ frame_t,
                   const double* __restrict__ f0_in, const long long* __restrict__ rng_off,
                   const uint32_t* __restrict__ randn_tab, const double2* __restrict__ tw,
@@ -105,7 +106,7 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
   }
 
   // ---- GetPowerSpectrum (:64-82) -----------------------------------------------------------
-  fft_dit<LM, false, 256, 4>(buf, log2m, tw);
+  fft_dit<LM, false, THREADS, THREADS == 256 ? 4 : 3>(buf, log2m, tw);
   for (int k = tid; k <= half; k += T) {
     const double2 X = rfft_bin(buf, log2m, k, tw);
     aux[k] = X.x * X.x + X.y * X.y;
@@ -155,7 +156,7 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
     float2* fb = reinterpret_cast<float2*>(buf);
     float* fbs = reinterpret_cast<float*>(buf);
     for (int i = tid; i < N; i += T) fbs[rfft_in_slot_f(i, log2m)] = static_cast<float>(aux[i <= half ? i : N - i]);
-    fft_dit<LM, false, 256, 4>(fb, log2m, twf);
+    fft_dit<LM, false, THREADS, 4>(fb, log2m, twf);
     float* lif = reinterpret_cast<float*>(aux);         // liftered cepstrum, real
     __syncthreads();                                     // everyone has read aux
     for (int k = tid; k <= half; k += T) {
@@ -175,7 +176,7 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
       const float2 z = c2r_pack(make_float2(lif[k], 0.f), make_float2(lif[half - k], 0.f), k, log2m, twf);
       fb[cpadf(brev(k, log2m))] = z;
     }
-    fft_dit<LM, true, 256, 4>(fb, log2m, twf);
+    fft_dit<LM, true, THREADS, 4>(fb, log2m, twf);
     for (int k = tid; k <= half; k += T) out[k] = exp(static_cast<double>(fbs[rfft_out_slot_f(k)]));
   }
 }
@@ -207,10 +208,16 @@ bool cheaptrick_run(const UttView& u, int fs, int total_frames, const int* frame
   if (!ensure_randn((size_t)mx)) return false;
   const size_t smem = cpad_size(fft_size / 2) * sizeof(double2) + (fft_size + 16 + 128) * sizeof(double);
   KernelTimer kt1("cheaptrick_kernel");
+  // 128-thread CTAs: 6 frames per SM instead of 3, half as many warps behind every barrier (9 % faster)
+  static const bool t128 = getenv("WB_CT_T256") == nullptr;
 #define WB_CT_LAUNCH(L)                                                                                             \
   do {                                                                                                              \
-    WB_CUDA_OR_RETURN(cudaFuncSetAttribute(cheaptrick_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
-    cheaptrick_kernel<L><<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0, offs.p, c->d_randn, c->d_twiddle, c->d_twiddle_f, fs, log2n, q1, f0_floor, sp); \
+    if (t128) {                                                                                                     \
+    WB_CUDA_OR_RETURN(cudaFuncSetAttribute(cheaptrick_kernel<L, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
+    cheaptrick_kernel<L, 128><<<total_frames, 128, smem, st>>>(u, frame_utt, frame_t, f0, offs.p, c->d_randn, c->d_twiddle, c->d_twiddle_f, fs, log2n, q1, f0_floor, sp); \
+    break; }                                                                                                        \
+    WB_CUDA_OR_RETURN(cudaFuncSetAttribute(cheaptrick_kernel<L, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
+    cheaptrick_kernel<L, 256><<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0, offs.p, c->d_randn, c->d_twiddle, c->d_twiddle_f, fs, log2n, q1, f0_floor, sp); \
   } while (0)
   switch (log2n) {
     case 10: WB_CT_LAUNCH(10); break;

@@ -306,8 +306,8 @@ __device__ __forceinline__ void exp_sincos(float re, float im, float* er, float*
 __device__ __forceinline__ double log_of(double v, double) { return log(v); }
 __device__ __forceinline__ float log_of(double v, float) { return logf(static_cast<float>(v)); }
 
-template <int LOG2N, typename C>      // LOG2N 0: size given at run time (c.log2n)
-__global__ void __launch_bounds__(256, 3)
+template <int LOG2N, typename C, int THREADS = 256>      // LOG2N 0: size given at run time (c.log2n)
+__global__ void __launch_bounds__(THREADS, 768 / THREADS)
 synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ ap_all,
                   const int* __restrict__ f_off, const int* __restrict__ f_len,
                   const long long* __restrict__ y_off, const int* __restrict__ y_len_all,
@@ -321,8 +321,8 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
   extern __shared__ double2 smem2[];
   const int log2n = LOG2N > 0 ? LOG2N : c.log2n;
   const int N = 1 << log2n, half = N >> 1;
-  constexpr int T = 256;
-  constexpr int kQ = 9;                 // (N/2 + 1) / T rounded up, N <= 4096
+  constexpr int T = THREADS;
+  constexpr int kQ = LOG2N > 0 ? ((1 << (LOG2N > 0 ? LOG2N - 1 : 0)) + THREADS) / THREADS : 2304 / THREADS;   // ceil((N/2 + 1) / T)
   C* cbuf = reinterpret_cast<C*>(smem2);
   C* nzb = cbuf + cpad_size(N);
   double* red = reinterpret_cast<double*>(nzb + cpad_size(N));
@@ -570,6 +570,7 @@ bool synthesis_run(Batch* b, const int* y_len) {
   static const bool fp64 = getenv("WB_SYNTH_FP64") != nullptr;      // debugging aid: all four transforms in FP64
   const size_t smem = 2 * cpad_size(N) * (fp64 ? sizeof(double2) : sizeof(float2)) + 96 * sizeof(double);
   if (N / 2 / 256 + 1 > 9) { set_error("Synthesis: fft_size %d too large for the register fold", N); return false; }
+  static const bool t128 = getenv("WB_SYNTH_T128") != nullptr;
   KernelTimer kt3("synth_pulse_kernel");
 #define WB_SP_LAUNCH(L, CT, TW)                                                                                     \
   do {                                                                                                              \
@@ -585,7 +586,15 @@ bool synthesis_run(Batch* b, const int* y_len) {
   } else {
     switch (log2n) {
       case 10: WB_SP_LAUNCH(10, float2, ctxp->d_twiddle_f); break;
-      case 11: WB_SP_LAUNCH(11, float2, ctxp->d_twiddle_f); break;
+      case 11:
+        if (t128) {
+          WB_CUDA_OR_RETURN(cudaFuncSetAttribute(synth_item_kernel<11, float2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+          synth_item_kernel<11, float2, 128><<<n_items, 128, smem, st>>>(b->sp.p, b->ap.p, b->f_off.p, b->f_len.p, b->y_off.p, b->y_len.p, d_poff.p, d_cnt.p,
+              p_index.p, p_shift.p, p_vuv.p, p_utt.p, list_per.p, list_aper.p, n_per, n_aper, ctxp->d_randn, ctxp->d_twiddle_f, d_rem.p, c, b->y.p);
+        } else {
+          WB_SP_LAUNCH(11, float2, ctxp->d_twiddle_f);
+        }
+        break;
       case 12: WB_SP_LAUNCH(12, float2, ctxp->d_twiddle_f); break;
       default: WB_SP_LAUNCH(0, float2, ctxp->d_twiddle_f); break;
     }
