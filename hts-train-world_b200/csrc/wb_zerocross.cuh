@@ -44,14 +44,20 @@ __device__ __forceinline__ double zc_fine(int e, double a, double b) {   // :376
   return add_rn((double)e, -div_rn(a, add_rn(b, -a)));
 }
 
+// One CTA scans kZcChunk sample pairs of one (utterance, band).  Events keep the order of the
+// sample index: thread t looks at samples i0 + k * 256 + t (k = 0..7, coalesced), all eight
+// rounds are evaluated first, the per-(round, type, warp) event counts go to shared memory and
+// ONE barrier later every event knows its slot (prefix over rounds and warps + ballot prefix
+// inside the warp).  WRITE = false only counts.
 template <bool WRITE>
 static __global__ void __launch_bounds__(256)
 zc_kernel(const double* __restrict__ F, const long long* __restrict__ F_off,
               const int* __restrict__ y_len_all, int nb, int utt0, int n_chunks_max,
               int* __restrict__ counts,              // [lists][n_chunks_max] (count pass: out; write: exclusive offsets)
               const long long* __restrict__ list_off, double* __restrict__ edges) {
-  __shared__ int wcnt[4][8];
-  __shared__ int run[4];
+  constexpr int kRounds = kZcChunk / 256;
+  __shared__ int wcnt[kRounds][4][8];
+  __shared__ unsigned lpre_s[WRITE ? kRounds : 1][256];
   const int ub = blockIdx.y;                         // local utterance * nb + band
   const int u_local = ub / nb, b = ub % nb;
   const int y_len = y_len_all[utt0 + u_local];
@@ -63,52 +69,60 @@ zc_kernel(const double* __restrict__ F, const long long* __restrict__ F_off,
   }
   const double* __restrict__ s = F + F_off[u_local] + (size_t)b * y_len;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid < 4) run[tid] = WRITE ? counts[((size_t)ub * 4 + tid) * n_chunks_max + chunk] : 0;
-  __syncthreads();
-  for (int it = 0; it < kZcChunk / 256; ++it) {
-    const int i = i0 + it * 256 + tid;
+  unsigned evbits = 0;                               // bit (4 k + t): event of type t in round k
+#pragma unroll
+  for (int k = 0; k < kRounds; ++k) {
+    const int i = i0 + k * 256 + tid;
     bool ev[4] = {false, false, false, false};
-    double fine[4] = {0.0, 0.0, 0.0, 0.0};
     if (i < y_len - 1) {
       const double s0 = s[i], s1 = s[i + 1];
       ev[0] = zc_event(s0, s1);
       ev[1] = zc_event(-s0, -s1);
-      if (WRITE && ev[0]) fine[0] = zc_fine(i + 1, s0, s1);
-      if (WRITE && ev[1]) fine[1] = zc_fine(i + 1, -s0, -s1);
       if (i < y_len - 2) {
         const double s2 = s[i + 2];
         const double d0 = add_rn(s1, -s0), d1 = add_rn(s2, -s1);
         ev[2] = zc_event(d0, d1);
         ev[3] = zc_event(-d0, -d1);
-        if (WRITE && ev[2]) fine[2] = zc_fine(i + 1, d0, d1);
-        if (WRITE && ev[3]) fine[3] = zc_fine(i + 1, -d0, -d1);
       }
     }
-    unsigned bal[4];
+    unsigned pre = 0;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      bal[t] = __ballot_sync(0xffffffffu, ev[t]);
-      if (lane == 0) wcnt[t][wid] = __popc(bal[t]);
+      const unsigned bal = __ballot_sync(0xffffffffu, ev[t]);
+      if (lane == 0) wcnt[k][t][wid] = __popc(bal);
+      if (ev[t]) evbits |= 1u << (4 * k + t);
+      pre |= (unsigned)__popc(bal & ((1u << lane) - 1u)) << (8 * t);   // events of lower lanes (<= 31)
     }
-    __syncthreads();
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      if (WRITE && ev[t]) {
-        int pos = run[t];
-        for (int w = 0; w < wid; ++w) pos += wcnt[t][w];
-        pos += __popc(bal[t] & ((1u << lane) - 1u));
-        edges[list_off[(size_t)ub * 4 + t] + pos] = fine[t];
-      }
-    }
-    __syncthreads();
-    if (tid < 4) {
-      int tot = 0;
-      for (int w = 0; w < 8; ++w) tot += wcnt[tid][w];
-      run[tid] += tot;
-    }
-    __syncthreads();
+    if (WRITE) lpre_s[k][tid] = pre;
   }
-  if (!WRITE && tid < 4) counts[((size_t)ub * 4 + tid) * n_chunks_max + chunk] = run[tid];
+  __syncthreads();
+  if (tid < 4) {                                     // exclusive prefix over (round, warp), in place
+    int acc = WRITE ? counts[((size_t)ub * 4 + tid) * n_chunks_max + chunk] : 0;
+    for (int k = 0; k < kRounds; ++k)
+      for (int w = 0; w < 8; ++w) { const int v = wcnt[k][tid][w]; wcnt[k][tid][w] = acc; acc += v; }
+    if (!WRITE) counts[((size_t)ub * 4 + tid) * n_chunks_max + chunk] = acc;
+  }
+  if (!WRITE) return;
+  __syncthreads();
+  if (evbits == 0) return;
+#pragma unroll 1
+  for (int k = 0; k < kRounds; ++k) {
+    const unsigned e4 = (evbits >> (4 * k)) & 0xfu;
+    if (e4 == 0) continue;
+    const int i = i0 + k * 256 + tid;
+    const double s0 = s[i], s1 = s[i + 1];
+    const double s2 = i < y_len - 2 ? s[i + 2] : 0.0;
+    const double d0 = add_rn(s1, -s0), d1 = add_rn(s2, -s1);
+    const unsigned pre = lpre_s[k][tid];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (!((e4 >> t) & 1u)) continue;
+      const int pos = wcnt[k][t][wid] + (int)((pre >> (8 * t)) & 0xffu);
+      const double fine = t == 0 ? zc_fine(i + 1, s0, s1) : t == 1 ? zc_fine(i + 1, -s0, -s1)
+                        : t == 2 ? zc_fine(i + 1, d0, d1) : zc_fine(i + 1, -d0, -d1);
+      edges[list_off[(size_t)ub * 4 + t] + pos] = fine;
+    }
+  }
 }
 
 // one thread per list: exclusive scan over chunks (in place), list totals out
