@@ -82,6 +82,10 @@ bool codec_decode_run(const double* d_coded, int n_frames, int fs, int fft_size,
 bool batch_code_features(Batch* b, int mgc_dim, int bap_dim);
 bool batch_feature_stats(Batch* b, double* h_out);
 
+// zero-phase IIR decimation of every utterance (wb_harvest.cu), used by Dio when option.speed > 1
+bool decimate_run(const Batch* b, int r, const std::vector<int>& want_len, DevBuf<double>* y,
+                  DevBuf<long long>* y_off, DevBuf<int>* y_len, std::vector<int>* out_len);
+
 // generic helper: exclusive prefix sum of counts within each utterance's frame range.
 // out[f] = sum of counts[g] for g in [f_off[u], f); totals[u] = sum over the utterance.
 bool segmented_exclusive_scan(const long long* counts, const int* f_off, const int* f_len,

@@ -252,7 +252,6 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
   const int n_utt = b->n_utt;
   if (n_utt == 0) return true;
   const int ratio = std::max(std::min(p.speed, 12), 1);
-  if (ratio != 1) { set_error("Dio: option.speed = %d (decimation) is not implemented yet; the analysis tool uses 1", p.speed); return false; }
   const double actual_fs = (double)b->fs / ratio;
   const std::vector<double> key = {actual_fs, p.f0_floor, p.f0_ceil, p.channels_in_octave};
   DioFilterBank* fb = nullptr;
@@ -289,7 +288,19 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
   WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_ylen.p, h_ylen.data(), n_utt * sizeof(int), cudaMemcpyHostToDevice, st), false);
   WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_mask.p, h_mask.data(), n_utt * sizeof(int), cudaMemcpyHostToDevice, st), false);
   WB_CUDA_OR_RETURN(cudaMemsetAsync(d_f0_out, 0, (size_t)TF * sizeof(double), st), false);
-  dio_mean_kernel<<<n_utt, 256, 0, st>>>(b->x.p, b->x_off.p, b->x_len.p, d_ylen.p, d_mean.p);
+  // the signal the bands are computed from: x itself, or its decimated copy when speed > 1 (:69-71)
+  const double* xin = b->x.p;
+  const long long* xin_off = b->x_off.p;
+  const int* xin_len = b->x_len.p;
+  DevBuf<double> d_dec;
+  DevBuf<long long> d_dec_off;
+  DevBuf<int> d_dec_len;
+  if (ratio != 1) {
+    std::vector<int> got;
+    if (!decimate_run(b, ratio, h_ylen, &d_dec, &d_dec_off, &d_dec_len, &got)) return false;
+    xin = d_dec.p; xin_off = d_dec_off.p; xin_len = d_dec_len.p;
+  }
+  dio_mean_kernel<<<n_utt, 256, 0, st>>>(xin, xin_off, xin_len, d_ylen.p, d_mean.p);
   WB_LAUNCH_CHECK();
 
   const size_t smem = 2 * cpad_size(c.bn / 2) * sizeof(double2);
@@ -333,10 +344,10 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
     WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_foff.p, h_foff.data(), nu * sizeof(long long), cudaMemcpyHostToDevice, st), false);
     KernelTimer kt1("dio_filter_kernel");
     if (c.log2bn == 13)
-      ols_filter_kernel<13><<<dim3(n_blocks, nu), 256, smem, st>>>(b->x.p, b->x_off.p, b->x_len.p, d_ylen.p, d_mask.p, d_mean.p,
+      ols_filter_kernel<13><<<dim3(n_blocks, nu), 256, smem, st>>>(xin, xin_off, xin_len, d_ylen.p, d_mask.p, d_mean.p,
                                                             d_foff.p, fb->G.p, ctxp->d_twiddle, oc, d_shift.p, u0, d_F.p);
     else
-      ols_filter_kernel<0><<<dim3(n_blocks, nu), 256, smem, st>>>(b->x.p, b->x_off.p, b->x_len.p, d_ylen.p, d_mask.p, d_mean.p,
+      ols_filter_kernel<0><<<dim3(n_blocks, nu), 256, smem, st>>>(xin, xin_off, xin_len, d_ylen.p, d_mask.p, d_mean.p,
                                                             d_foff.p, fb->G.p, ctxp->d_twiddle, oc, d_shift.p, u0, d_F.p);
     WB_LAUNCH_CHECK(); kt1.stop();
     KernelTimer kt2("dio_zc_kernel");

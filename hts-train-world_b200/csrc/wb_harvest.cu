@@ -686,6 +686,48 @@ bool build_harvest_bank(double actual_fs, double f0_floor, double f0_ceil, Harve
 
 }  // namespace
 
+// decimate() of W/src/matlabfunctions.cpp:184-210 for every utterance of the batch (no edge
+// extension: lag = 0), as Dio uses it when option.speed > 1 (W/src/dio.cpp:69-71).  out_len[u] =
+// min(want_len[u], number of values the reference's loop writes); the caller treats the rest as 0.
+bool decimate_run(const Batch* b, int r, const std::vector<int>& want_len, DevBuf<double>* y,
+                  DevBuf<long long>* y_off, DevBuf<int>* y_len, std::vector<int>* out_len) {
+  Context* ctxp = ctx();
+  if (!ctxp) return false;
+  cudaStream_t st = ctxp->stream;
+  const int n_utt = b->n_utt;
+  HarvestConst c;
+  c.fs = b->fs; c.r = r; c.nch = 0; c.lag = 0; c.actual_fs = (double)b->fs / r; c.f0_floor = c.f0_ceil = 0.0;
+  if (!decimate_coefficients(r, c.a, c.b)) { set_error("decimate: unsupported ratio %d", r); return false; }
+  std::vector<long long> h_yoff(n_utt), h_boff(n_utt);
+  out_len->resize(n_utt);
+  long long ytot = 0, btot = 0;
+  int max_M = 0;
+  for (int u = 0; u < n_utt; ++u) {
+    const int L = b->h_x_len[u];
+    if (L < 20) { set_error("decimate: utterance %d is too short (%d samples)", u, L); return false; }
+    const int nout = (L - 1) / r + 1, nbeg = r - r * nout + L;
+    const int written = (L + 9 - nbeg + r - 1) / r;                  // trips of the loop at :205-206
+    (*out_len)[u] = std::min(want_len[u], written);
+    h_yoff[u] = ytot; ytot += ((*out_len)[u] + 1) & ~1;
+    h_boff[u] = btot; btot += (L + 18 + 1) & ~1;
+    max_M = std::max(max_M, L + 18);
+  }
+  DevBuf<double> d_B;
+  DevBuf<long long> d_boff;
+  if (!y->alloc(ytot + 2) || !y_off->alloc(n_utt) || !y_len->alloc(n_utt) || !d_B.alloc(btot) || !d_boff.alloc(n_utt)) return false;
+  WB_CUDA_OR_RETURN(cudaMemcpyAsync(y_off->p, h_yoff.data(), n_utt * sizeof(long long), cudaMemcpyHostToDevice, st), false);
+  WB_CUDA_OR_RETURN(cudaMemcpyAsync(y_len->p, out_len->data(), n_utt * sizeof(int), cudaMemcpyHostToDevice, st), false);
+  WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_boff.p, h_boff.data(), n_utt * sizeof(long long), cudaMemcpyHostToDevice, st), false);
+  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  const int n_chunks = (max_M + kIirChunk - 1) / kIirChunk;
+  harvest_iir_fwd_kernel<<<dim3((n_chunks + 63) / 64, n_utt), 64, 0, st>>>(b->x.p, b->x_off.p, b->x_len.p, d_boff.p, c, n_chunks, d_B.p);
+  WB_LAUNCH_CHECK();
+  harvest_iir_bwd_kernel<<<dim3((n_chunks + 63) / 64, n_utt), 64, 0, st>>>(d_B.p, d_boff.p, b->x_len.p, y_off->p, y_len->p, c, n_chunks, y->p);
+  WB_LAUNCH_CHECK();
+  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);                // d_B dies with this scope
+  return true;
+}
+
 bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
   Context* ctxp = ctx();
   if (!ctxp) return false;

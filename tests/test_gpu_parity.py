@@ -40,6 +40,18 @@ def test_dio_golden(wb, name):
     assert M.f0_rel_error(g["f0_raw"], f0) <= M.TOL_F0_REL
 
 
+@pytest.mark.parametrize("fs,speed", [(48000, 2), (48000, 6), (48000, 12), (16000, 4), (16000, 11)])
+def test_dio_with_decimation(wb, reference_lib, fs, speed):
+    """DioOption.speed > 1: zero-phase IIR decimation (W/src/matlabfunctions.cpp:184-210) first."""
+    from hts_train_world_b200 import signals
+    x = signals.pcm_to_double(signals.make_utterance(31, fs, duration=1.6)[0])
+    t_ref, f_ref = reference_lib.dio(x, fs, speed=speed)
+    t, f0 = wb.dio(x, fs, speed=speed)
+    assert np.array_equal(t, t_ref)
+    assert M.vuv_agreement(f_ref, f0) >= M.TOL_VUV_AGREEMENT
+    assert M.f0_rel_error(f_ref, f0) <= M.TOL_F0_REL
+
+
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
 def test_stonemask_golden(wb, name):
     g = load_golden(name)
