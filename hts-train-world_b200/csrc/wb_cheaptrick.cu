@@ -74,11 +74,23 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
   //   wave_i = x_i w_i / norm + d_i,   coef = sum(wave) / sum(w / norm) = (Sx + Sd norm) / Sw.
   const int origin = matlab_round(add_rn(mul_rn(t_pos, (double)fs), 0.001));
   {
+    // stage the sample window with one TMA bulk copy into aux (where the window coefficients will
+    // overwrite it in place); frames whose window crosses an utterance edge gather with clamping
+    __shared__ uint64_t mbar;
+    int a0 = 0, n_stage = 0;
+    const bool staged = bulk_window_range(origin - hwl, W, x_len, N + 16, &a0, &n_stage);
+    double* waux = aux + (staged ? (origin - hwl) - a0 : 0);     // sample / coefficient i lives at waux[i]
+    if (staged) {
+      if (tid == 0) mbar_init(&mbar, 1);
+      __syncthreads();
+      if (tid == 0) bulk_load_issue(aux, x + a0, (unsigned)n_stage * 8u, &mbar);
+    }
     const double ang_step = kPi * f0c / (1.5 * fs);
     double cs, sn, cs_step, sn_step;
     sincos((double)(tid - hwl) * ang_step, &sn, &cs);
     sincos((double)T * ang_step, &sn_step, &cs_step);
     double sums[4] = {0.0, 0.0, 0.0, 0.0};            // Sww, Sw, Sx, Sd
+    if (staged) mbar_wait(&mbar, 0);
     for (int i = tid; i < W; i += T) {
       const double w = 0.5 * cs + 0.5;
       {
@@ -86,9 +98,9 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
         sn = sn * cs_step + cs * sn_step;
         cs = c2;
       }
-      const int idx = min(x_len - 1, max(0, origin + i - hwl));
-      const double xw = x[idx] * w;
-      aux[i] = w;
+      const double xv = staged ? waux[i] : x[min(x_len - 1, max(0, origin + i - hwl))];
+      const double xw = xv * w;
+      waux[i] = w;
       bufd[rfft_in_slot(i, log2m)] = xw;
       sums[0] += w * w; sums[1] += w; sums[2] += xw;
       sums[3] += randn_from_u32(rn[i]) * kMySafeGuardMinimum;
@@ -100,7 +112,7 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
       const int slot = rfft_in_slot(i, log2m);
       double wave = 0.0;
       if (i < W)
-        wave = bufd[slot] * inv_norm + randn_from_u32(rn[i]) * kMySafeGuardMinimum - aux[i] * inv_norm * coef;
+        wave = bufd[slot] * inv_norm + randn_from_u32(rn[i]) * kMySafeGuardMinimum - waux[i] * inv_norm * coef;
       bufd[slot] = wave;
     }
   }

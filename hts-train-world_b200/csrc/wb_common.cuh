@@ -176,6 +176,42 @@ __device__ __forceinline__ void block_inclusive_scan(double* a, int n, double* r
   __syncthreads();
 }
 
+// ---- TMA bulk copy (cp.async.bulk; UBLKCP in SASS) ------------------------------------------------
+// A frame's sample window is a contiguous range of the utterance: one elected thread asks the
+// TMA unit to copy it into shared memory and arms an mbarrier with the byte count; the other
+// threads meanwhile compute window coefficients and wait on the barrier only when they need the
+// samples.  Source and destination must be 16-byte aligned and the size a multiple of 16 bytes.
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load_issue(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// Window [g0, g0 + W) of an utterance of x_len samples whose base pointer is 16-byte aligned:
+// can it be staged with one bulk copy into `cap` doubles?  If so returns true and the aligned
+// range [*a0, *a0 + *n); sample g0 + i then sits at staging[(g0 - *a0) + i].
+__device__ __forceinline__ bool bulk_window_range(int g0, int W, int x_len, int cap, int* a0, int* n) {
+  if (g0 < 0 || g0 + W > x_len) return false;      // the reference clamps indices at the edges: gather path
+  *a0 = g0 & ~1;
+  *n = ((g0 + W + 1) & ~1) - *a0;                 // may include the (allocated) pad sample after x_len
+  return *n <= cap;
+}
+
 // interp1Q (W/src/matlabfunctions.cpp:220-241) for one query: uniform grid starting at x0
 // with step dx, n samples in y; delta_y[n-1] is defined as 0 by the reference.
 // The base index is found by multiplying with 1 / dx instead of dividing: when that moves the
