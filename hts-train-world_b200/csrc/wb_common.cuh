@@ -187,6 +187,8 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_load_issue(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+  // order earlier generic-proxy accesses of the destination before the async-proxy write
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_addr(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_addr(bar)) : "memory");

@@ -46,7 +46,8 @@ template <typename WS, typename VS>
 __device__ __forceinline__ int windowed_waveform(const double* __restrict__ x, int x_len, int fs,
                                                  double f0, double position, int window_type,
                                                  double ratio, const uint32_t* __restrict__ rn,
-                                                 double* base, WS wslot, VS vslot, double* red) {
+                                                 double* base, WS wslot, VS vslot, double* red,
+                                                 const double* staged = nullptr) {
   const int T = blockDim.x, tid = threadIdx.x;
   const int hwl = d4c_hwl(ratio, fs, f0);
   const int W = 2 * hwl + 1;
@@ -67,8 +68,8 @@ __device__ __forceinline__ int windowed_waveform(const double* __restrict__ x, i
       sn = sn * cs_step + cs * sn_step;
       cs = c2;
     }
-    const int idx = min(x_len - 1, max(0, origin + i - hwl));
-    const double wave = x[idx] * w + randn_from_u32(rn[i]) * kMySafeGuardMinimum;
+    const double xv = staged ? staged[i] : x[min(x_len - 1, max(0, origin + i - hwl))];
+    const double wave = xv * w + randn_from_u32(rn[i]) * kMySafeGuardMinimum;
     base[wslot(i)] = wave;
     base[vslot(i)] = w;
     s[0] += wave;
@@ -307,6 +308,23 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
   }
   auto cslot = [log2nd](int i) { return cpad(brev(i, log2nd)); };
 
+  // The three sample windows of the frame (two centroids, power spectrum) are staged into the
+  // idle `pw` array by TMA bulk copies, each issued one phase ahead so that it lands while the
+  // previous window is being transformed; windows that cross an utterance edge (the reference
+  // clamps the index there) or exceed the staging area fall back to a clamped gather.
+  __shared__ uint64_t mbar;
+  const int hwl_w = d4c_hwl(4.0, c.fs, cur_f0);
+  auto window_origin = [&](int which) {                 // 0 / 1: centroid sides, 2: power spectrum
+    const double pos = which == 2 ? t_pos : add_rn(t_pos, which == 0 ? -0.25 / cur_f0 : 0.25 / cur_f0);
+    return matlab_round(add_rn(mul_rn(pos, (double)c.fs), 0.001)) - hwl_w;
+  };
+  int st_a0 = 0, st_n = 0;
+  bool st_ok = bulk_window_range(window_origin(0), W4, x_len, Hd + 8, &st_a0, &st_n);
+  unsigned st_parity = 0;
+  if (tid == 0) mbar_init(&mbar, 1);
+  __syncthreads();
+  if (st_ok && tid == 0) bulk_load_issue(pw, x + st_a0, (unsigned)st_n * 8u, &mbar);
+
   // ---- GetStaticCentroid (:125-142): two centroids, each one packed complex FFT ----------------
   for (int side = 0; side < 2; ++side) {
     const double pos = add_rn(t_pos, side == 0 ? -0.25 / cur_f0 : 0.25 / cur_f0);
@@ -324,6 +342,9 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
       sincos((double)(tid - hwl4) * ang_step, &sn, &cs);
       sincos((double)T * ang_step, &sn_step, &cs_step);
       double sums[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      const bool staged = st_ok;
+      const double* xs = pw + (window_origin(side) - st_a0);
+      if (staged) { mbar_wait(&mbar, st_parity); st_parity ^= 1u; }
       for (int i = tid; i < W; i += T) {
         const double w = 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);
         {
@@ -331,12 +352,14 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
           sn = sn * cs_step + cs * sn_step;
           cs = c2;
         }
-        const int idx = min(x_len - 1, max(0, origin + i - hwl4));
-        const double wave = x[idx] * w + randn_from_u32(rns[i]) * kMySafeGuardMinimum;
+        const double xv = staged ? xs[i] : x[min(x_len - 1, max(0, origin + i - hwl4))];
+        const double wave = xv * w + randn_from_u32(rns[i]) * kMySafeGuardMinimum;
         cbuf[cslot(i)] = make_double2(wave, w);
         sums[0] += wave; sums[1] += w; sums[2] += wave * wave; sums[3] += wave * w; sums[4] += w * w;
       }
-      block_sum<5>(sums, red);
+      block_sum<5>(sums, red);                          // (its barriers also mean: every thread is done with pw)
+      st_ok = bulk_window_range(window_origin(side + 1), W4, x_len, Hd + 8, &st_a0, &st_n);
+      if (st_ok && tid == 0) bulk_load_issue(pw, x + st_a0, (unsigned)st_n * 8u, &mbar);   // next window
       const double coef = sums[0] / sums[1];
       double energy = sums[2] - 2.0 * coef * sums[3] + coef * coef * sums[4];
       if (!(energy > 1e-8 * sums[2])) {                 // DC-dominated frame: the expansion cancels, sum directly
@@ -361,7 +384,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
     }
   }
   __syncthreads();
-  dc_correction(cen, pw, cur_f0, c.fs, Nd);
+  dc_correction(cen, cbufd, cur_f0, c.fs, Nd);        // cbuf is idle here; pw holds the staged power-spectrum window
 
   // ---- GetSmoothedPowerSpectrum (:148-164) ----------------------------------------------------
   {
@@ -372,8 +395,10 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
     auto pwslot = [log2m](int i) { return rfft_in_slot(i, log2m); };
     auto pvslot = [vbase](int i) { return vbase + i; };
     __syncthreads();                                    // centroid readers of cbuf are done
+    if (st_ok) mbar_wait(&mbar, st_parity);
     const int W = windowed_waveform(x, x_len, c.fs, cur_f0, t_pos, kHanning, 4.0,
-                                    rn + 2 * (size_t)W4, cbufd, pwslot, pvslot, red);
+                                    rn + 2 * (size_t)W4, cbufd, pwslot, pvslot, red,
+                                    st_ok ? pw + (window_origin(2) - st_a0) : nullptr);
     for (int i = W + tid; i < Nd; i += T) cbufd[rfft_in_slot(i, log2m)] = 0.0;
     fft_dit<LMD, false, THREADS, MAXK>(cbuf, log2m, tw);
     for (int k = tid; k <= Hd; k += T) {
