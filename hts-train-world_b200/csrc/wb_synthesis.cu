@@ -86,6 +86,7 @@ synth_timebase_kernel(const double* __restrict__ f0_all, const int* __restrict__
                       unsigned char* __restrict__ p_vuv, int* __restrict__ p_utt) {
   __shared__ double inc_s[512];
   __shared__ double tot_s[512];
+  __shared__ long long wsum_s[32];
   __shared__ int wcnt[32];
   __shared__ double carry_phase, last_wrap_prev;
   __shared__ int carry_cnt;
@@ -126,24 +127,55 @@ synth_timebase_kernel(const double* __restrict__ f0_all, const int* __restrict__
     // scan moves pulses by one sample.  One thread walks the chunk sequentially (the loads
     // are independent, only the DADD chain is serial: ~T x 8 cycles per chunk, all utterances
     // in flight at once); everything else in this kernel stays parallel.
+    // Exact parallel form: while the running sum s stays inside one binade [2^e, 2^(e+1)], every
+    // IEEE addition is  s <- s + rn_u(a)  with u = ulp = 2^(e-52) and rn_u = round-to-nearest
+    // multiple of u (s is a multiple of u, so the rounding does not depend on s unless a / u ends
+    // in exactly .5).  In units of u the chunk is then an INTEGER prefix sum -- associative, so a
+    // warp-shuffle scan reproduces the sequential result bit for bit.  Chunks that see a tie, leave
+    // the binade (the sum doubles ~20 times per utterance) or start from 0 take the sequential walk.
     inc_s[tid] = inc;
+    const double s0 = carry_phase;
+    bool slow = !(s0 > 0.0);
+    long long r = 0, s0int = 0;
+    int e = 0;
+    if (!slow) {
+      e = ilogb(s0);
+      const double m = scalbn(inc, 52 - e);
+      const double rr = rint(m);
+      slow = fabs(m - rr) == 0.5 || !(m < 4503599627370496.0);
+      r = static_cast<long long>(rr);
+      s0int = static_cast<long long>(scalbn(s0, 52 - e));
+    }
+    long long pre = r;                                   // inclusive scan over the CTA
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += t;
+    }
+    if (lane == 31) wsum_s[wid] = pre;
     __syncthreads();
-    if (tid == 0) {
-      // batches of 8: the loads of a batch are issued together (input and output arrays are
-      // distinct, so nothing orders them behind the previous batch's stores) and only the
-      // eight dependent DADDs are serial
-      const double* __restrict__ in = inc_s;
-      double* __restrict__ outp = tot_s;
-      double run = carry_phase;
-      for (int q = 0; q < T; q += 8) {
-        double v[8];
+    for (int w = 0; w < wid; ++w) pre += wsum_s[w];
+    slow = slow || (s0int + pre > 9007199254740992LL) || (s0int + pre < 4503599627370496LL);   // left the binade
+    if (__syncthreads_or(slow)) {
+      if (tid == 0) {
+        // batches of 8: the loads of a batch are issued together (input and output arrays are
+        // distinct, so nothing orders them behind the previous batch's stores) and only the
+        // eight dependent DADDs are serial
+        const double* __restrict__ in = inc_s;
+        double* __restrict__ outp = tot_s;
+        double run = carry_phase;
+        for (int q = 0; q < T; q += 8) {
+          double v[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) v[r] = in[q + r];
+          for (int r8 = 0; r8 < 8; ++r8) v[r8] = in[q + r8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) { run = add_rn(run, v[r]); v[r] = run; }
+          for (int r8 = 0; r8 < 8; ++r8) { run = add_rn(run, v[r8]); v[r8] = run; }
 #pragma unroll
-        for (int r = 0; r < 8; ++r) outp[q + r] = v[r];
+          for (int r8 = 0; r8 < 8; ++r8) outp[q + r8] = v[r8];
+        }
       }
+    } else {
+      tot_s[tid] = scalbn(static_cast<double>(s0int + pre), e - 52);
     }
     __syncthreads();
     const double total = tot_s[tid];
