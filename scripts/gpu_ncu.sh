@@ -4,7 +4,7 @@
 set -x
 mkdir -p gpurun_out
 SMALL="python bench.py --utts ${UTTS:-64} --steps 1 --warmup 1 --no-cpu-baseline"
-KRE='regex:dio_|d4c_|cheaptrick|synth_|stonemask|seg_scan|pcm16|lf0_stats|default_frames|randn_table|harvest|ols_filter|zc_'
+KRE='regex:dio_|d4c_|cheaptrick|synth_|stonemask|seg_scan|pcm16|lf0_stats|default_frames|randn_table|harvest|ols_filter|zc_|codec'
 HEAVY="regex:${HEAVY:-d4c_main|synth_pulse|cheaptrick_kernel|stonemask_kernel|lovetrain|dio_filter}"
 timeout 600 $SMALL > gpurun_out/plain_small.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KRE" -c 400 --csv --log-file gpurun_out/launches.csv $SMALL > gpurun_out/ncu_small.log 2>&1 &&
