@@ -38,6 +38,7 @@ FS = 48000
 FRAME_PERIOD = 5.0
 METRIC = "xRT (audio s/s) WORLD analysis+synthesis, 48 kHz 5 ms"
 UNIT = "audio_s/s"
+E2E_PARTS = int(os.environ.get("WB_E2E_PARTS", "2"))    # pipelined sub-batches of the end-to-end leg
 MGC_DIM, BAP_DIM = 50, 24       # MGCORDER + 1 and the tool's default (data/Makefile.in:214, analysis.cpp:324-328)
 
 
@@ -279,7 +280,6 @@ def ours_arm(args):
     audio_s = sum(lengths) / float(FS)
 
     c = wb.Corpus(FS, lengths, FRAME_PERIOD)
-    y_host = None
     f0_host = torch.empty(c.total_frames, dtype=torch.float64).pin_memory()
     lf0_host = torch.empty(c.total_frames, dtype=torch.float32).pin_memory()
     mgc_host = torch.empty((c.total_frames, MGC_DIM), dtype=torch.float32).pin_memory()
@@ -299,19 +299,39 @@ def ours_arm(args):
         c.synthesis()
         return reduce_stats(c.feature_stats())
 
+    # ---- end to end: the shard goes through the public batch API in E2E_PARTS pipelined sub-batches.
+    # Uploads run on the library's upload stream one sub-batch ahead, the coded features and the 16-bit
+    # waveform leave on its download stream while the next sub-batch computes.
+    n_parts = max(1, min(E2E_PARTS, len(lengths)))
+    bounds = [len(lengths) * i // n_parts for i in range(n_parts + 1)]
+    parts = []
+    s_off = f_off_ = y_off_ = 0
+    for i in range(n_parts):
+        ls = lengths[bounds[i]:bounds[i + 1]]
+        cp = wb.Corpus(FS, ls, FRAME_PERIOD)
+        ns, nf = sum(ls), cp.total_frames
+        ny = sum(int((int(f) - 1) * FRAME_PERIOD / 1000.0 * FS) + 1 for f in cp.f_len)     # W/test/synth.cpp:259
+        parts.append(dict(c=cp, s=(s_off, s_off + ns), f=(f_off_, f_off_ + nf), y=(y_off_, y_off_ + ny)))
+        s_off, f_off_, y_off_ = s_off + ns, f_off_ + nf, y_off_ + ny
+    y_host = torch.empty(y_off_, dtype=torch.int16).pin_memory()
+
     def step_e2e():
-        nonlocal y_host
-        c.upload_pcm16(pcm_host)
-        c.analyze(f0=args.f0)
-        c.code(MGC_DIM, BAP_DIM)
-        c.synthesis()
-        if y_host is None:
-            y_host = torch.empty(int(wb.lib().wb200_batch_total_y(c._h)), dtype=torch.int16).pin_memory()
-        c.y_pcm16(y_host)
-        wb._check(wb.lib().wb200_batch_get_coded(c._h, lf0_host.data_ptr(), mgc_host.data_ptr(), bap_host.data_ptr()),
-                  "get_coded")
-        wb._check(wb.lib().wb200_batch_get_f0(c._h, wb.C.cast(f0_host.data_ptr(), wb._dp), 1), "get_f0")
-        return reduce_stats(c.feature_stats())
+        st = np.zeros((1 + MGC_DIM, 3))
+        parts[0]["c"].upload_pcm16_async(pcm_host[parts[0]["s"][0]:parts[0]["s"][1]])
+        for i, p in enumerate(parts):
+            if i + 1 < len(parts):
+                q = parts[i + 1]
+                q["c"].upload_pcm16_async(pcm_host[q["s"][0]:q["s"][1]])
+            cp, (fa, fb), (ya, yb) = p["c"], p["f"], p["y"]
+            cp.analyze(f0=args.f0)
+            cp.code(MGC_DIM, BAP_DIM)
+            cp.coded_async(lf0_host[fa:fb], mgc_host[fa:fb], bap_host[fa:fb])
+            cp.synthesis()
+            cp.y_pcm16_async(y_host[ya:yb])
+            wb._check(wb.lib().wb200_batch_get_f0(cp._h, wb.C.cast(f0_host[fa:fb].data_ptr(), wb._dp), 1), "get_f0")
+            st += cp.feature_stats()
+        wb.sync()                               # every asynchronous copy has landed
+        return reduce_stats(st)
 
     def barrier():
         if world > 1:
@@ -366,6 +386,7 @@ def ours_arm(args):
     value = audio_total * args.steps / (ms * 1e-3)
 
     # ---- end to end from host memory --------------------------------------------------------------
+    step_e2e()
     step_e2e()
     ms_e, wall_e, _, _ = timed(step_e2e, args.steps)
     e2e_value = audio_total * args.steps / (max(ms_e, wall_e) * 1e-3)
@@ -436,7 +457,8 @@ def ours_arm(args):
                    "parallelism": "utterance-sharded x%d, no hot-path collective" % world,
                    "l2": "inputs larger than L2 (%.0f MB PCM, GBs of intermediates per step)" % (h2d / 1e6)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": max(ms_e, wall_e) / args.steps,
+                "ms_per_step": max(ms_e, wall_e) / args.steps, "pipelined_sub_batches": n_parts,
+                "device_ms_per_step": ms_e / args.steps, "wall_ms_per_step": wall_e / args.steps,
                 "result": "the analysis tool's float32 lf0/mgc/bap + f0 + 16-bit resynthesised waveform + lf0/mgc statistics; "
                           "sp/ap stay in HBM"},
         "gpu_launches": int(launches),
@@ -470,6 +492,8 @@ def ours_arm(args):
     if rank == 0:
         print(json.dumps(line))
     c.close()
+    for p in parts:
+        p["c"].close()
     if world > 1:
         dist.destroy_process_group()
     return 0

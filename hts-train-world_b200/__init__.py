@@ -101,6 +101,8 @@ def lib():
         "wb200_batch_total_samples": (i64, [vp]),
         "wb200_batch_frame_layout": (i32, [vp, _ip, _ip]),
         "wb200_batch_upload_pcm16": (i32, [vp, vp]),
+        "wb200_batch_upload_pcm16_async": (i32, [vp, vp]),
+        "wb200_batch_get_y_pcm16_async": (i32, [vp, vp]),
         "wb200_batch_upload_f64": (i32, [vp, vp]),
         "wb200_batch_set_pcm16_device": (i32, [vp, vp]),
         "wb200_batch_dio": (i32, [vp, C.POINTER(DioOption)]),
@@ -122,6 +124,7 @@ def lib():
         "wb200_batch_lf0_stats": (i32, [vp, _dp]),
         "wb200_batch_code": (i32, [vp, i32, i32]),
         "wb200_batch_get_coded": (i32, [vp, vp, vp, vp]),
+        "wb200_batch_get_coded_async": (i32, [vp, vp, vp, vp]),
         "wb200_batch_decode_mgc": (i32, [vp, i32, i32, vp]),
         "wb200_batch_feature_stats": (i32, [vp, _dp]),
         "GetNumberOfAperiodicities": (i32, [i32]),
@@ -329,6 +332,20 @@ class Corpus:
         ptr = pcm.data_ptr() if hasattr(pcm, "data_ptr") else pcm.ctypes.data
         _check(lib().wb200_batch_upload_pcm16(self._h, ptr), "upload_pcm16")
         self._keep = pcm
+
+    def upload_pcm16_async(self, pcm):
+        """Pinned int16 tensor / array; the copy overlaps whatever is running (another batch)."""
+        ptr = pcm.data_ptr() if hasattr(pcm, "data_ptr") else pcm.ctypes.data
+        _check(lib().wb200_batch_upload_pcm16_async(self._h, ptr), "upload_pcm16_async")
+        self._keep = pcm
+
+    def y_pcm16_async(self, out):
+        ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+        _check(lib().wb200_batch_get_y_pcm16_async(self._h, ptr), "get_y_pcm16_async")
+
+    def coded_async(self, lf0, mgc, bap):
+        _check(lib().wb200_batch_get_coded_async(self._h, *(a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+                                                            for a in (lf0, mgc, bap))), "get_coded_async")
 
     def set_pcm16_device(self, dev_tensor):
         _check(lib().wb200_batch_set_pcm16_device(self._h, dev_tensor.data_ptr()), "set_pcm16_device")

@@ -12,8 +12,30 @@ using namespace wb;
 
 struct wb200_batch {
   Batch b;
-  DevBuf<int16_t> pcm_stage;
+  DevBuf<int16_t> pcm_stage, pcm_out;
+  DevBuf<long long> src_off, out_off;   // per-utterance offsets inside the packed 16-bit input / output
+  cudaEvent_t upload_done = nullptr;     // recorded on the upload stream by wb200_batch_upload_pcm16_async
+  bool upload_pending = false;
+  ~wb200_batch() { if (upload_done) cudaEventDestroy(upload_done); }
 };
+
+namespace {
+bool ensure_copy_streams(Context* c) {
+  if (!c->copy_stream) {
+    if (!WB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) ||
+        !WB_CUDA(cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking)) ||
+        !WB_CUDA(cudaEventCreateWithFlags(&c->copy_event, cudaEventDisableTiming)))
+      return false;
+  }
+  return true;
+}
+// every stage that reads the samples first waits (on the device) for an asynchronous upload
+bool wait_upload(wb200_batch* h) {
+  if (!h->upload_pending) return true;
+  h->upload_pending = false;
+  return WB_CUDA(cudaStreamWaitEvent(ctx()->stream, h->upload_done, 0));
+}
+}  // namespace
 
 namespace {
 
@@ -56,14 +78,21 @@ __global__ void pcm16_to_double_kernel(const int16_t* __restrict__ pcm, const lo
     d[i] = static_cast<double>(s[i]) / 32768.0;
 }
 
-__global__ void y_to_pcm16_kernel(const double* __restrict__ y, long long n, int16_t* __restrict__ out) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  // W/test/audioio.cpp:115-170: (short)(MyMax(-32768, MyMin(32767, (int)(x * 32767))))
-  double v = y[i] * 32767.0;
-  int iv = (v != v) ? 0 : (v > 2147483000.0 ? 2147483000 : (v < -2147483000.0 ? -2147483000 : (int)v));
-  iv = max(-32768, min(32767, iv));
-  out[i] = (int16_t)iv;
+// y (utterances 16-byte aligned) -> 16-bit samples, utterances back to back (one D2H copy later)
+__global__ void y_to_pcm16_kernel(const double* __restrict__ y, const long long* __restrict__ y_off,
+                                  const long long* __restrict__ out_off, const int* __restrict__ y_len,
+                                  int16_t* __restrict__ out) {
+  const int u = blockIdx.y;
+  const int n = y_len[u];
+  const double* __restrict__ src = y + y_off[u];
+  int16_t* __restrict__ dst = out + out_off[u];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    // W/test/audioio.cpp:115-170: (short)(MyMax(-32768, MyMin(32767, (int)(x * 32767))))
+    const double v = src[i] * 32767.0;
+    int iv = (v != v) ? 0 : (v > 2147483000.0 ? 2147483000 : (v < -2147483000.0 ? -2147483000 : (int)v));
+    iv = max(-32768, min(32767, iv));
+    dst[i] = (int16_t)iv;
+  }
 }
 
 __global__ void lf0_stats_kernel(const double* __restrict__ f0, int n, double* __restrict__ out3) {
@@ -314,7 +343,10 @@ double wb200_measure_fma_peak(int fp64) { return measure_fma_peak(fp64 != 0); }
 int wb200_sync(void) {
   Context* c = ctx();
   if (!c) return 1;
-  return WB_CUDA(cudaStreamSynchronize(c->stream)) ? 0 : 1;
+  bool ok = WB_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->copy_stream) ok = WB_CUDA(cudaStreamSynchronize(c->copy_stream)) && ok;
+  if (c->upload_stream) ok = WB_CUDA(cudaStreamSynchronize(c->upload_stream)) && ok;
+  return ok ? 0 : 1;
 }
 int wb200_randn_stream(double* out, long long n) {
   Context* c = ctx();
@@ -339,7 +371,7 @@ wb200_batch* wb200_batch_create(int fs, double frame_period, int n_utt, const in
 }
 void wb200_batch_destroy(wb200_batch* h) {
   if (!h) return;
-  if (ctx()) cudaStreamSynchronize(ctx()->stream);
+  if (ctx()) wb200_sync();             // library, upload and download streams
   delete h;
 }
 int wb200_batch_total_frames(const wb200_batch* h) { return h->b.total_frames; }
@@ -375,6 +407,36 @@ int wb200_batch_upload_pcm16(wb200_batch* h, const int16_t* host_pcm) {
   if (!WB_CUDA(cudaMemcpyAsync(h->pcm_stage.p, host_pcm, (size_t)n * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream))) return 1;
   return convert_pcm(h, h->pcm_stage.p);
 }
+// Asynchronous variant: the copy and the int16 -> double conversion run on the upload stream, so
+// they overlap whatever the library stream is computing (the previous batch); the stages of THIS
+// batch wait for it on the device.  host_pcm must be pinned and stay valid until the first stage
+// of this batch has been launched.
+int wb200_batch_upload_pcm16_async(wb200_batch* h, const int16_t* host_pcm) {
+  Context* c = ctx();
+  if (!c || !ensure_copy_streams(c)) return 1;
+  Batch& b = h->b;
+  const long long n = wb200_batch_total_samples(h);
+  if (!h->upload_done && !WB_CUDA(cudaEventCreateWithFlags(&h->upload_done, cudaEventDisableTiming))) return 1;
+  if (!h->pcm_stage.p || !h->src_off.p) {            // first use: allocate on the library stream, once
+    std::vector<long long> src(b.n_utt > 0 ? b.n_utt : 1);
+    long long o = 0;
+    for (int u = 0; u < b.n_utt; ++u) { src[u] = o; o += b.h_x_len[u]; }
+    if (!h->pcm_stage.alloc((size_t)n + 1) || !h->src_off.alloc(b.n_utt)) return 1;
+    if (!WB_CUDA(cudaMemcpyAsync(h->src_off.p, src.data(), b.n_utt * sizeof(long long), cudaMemcpyHostToDevice, c->stream)) ||
+        !WB_CUDA(cudaStreamSynchronize(c->stream)))
+      return 1;
+  }
+  // x may still be read by work queued on the library stream: order the upload behind it
+  if (!WB_CUDA(cudaEventRecord(c->copy_event, c->stream)) || !WB_CUDA(cudaStreamWaitEvent(c->upload_stream, c->copy_event, 0))) return 1;
+  if (n > 0) {
+    if (!WB_CUDA(cudaMemcpyAsync(h->pcm_stage.p, host_pcm, (size_t)n * sizeof(int16_t), cudaMemcpyHostToDevice, c->upload_stream))) return 1;
+    pcm16_to_double_kernel<<<dim3(64, b.n_utt), 256, 0, c->upload_stream>>>(h->pcm_stage.p, h->src_off.p, b.x_off.p, b.x_len.p, b.x.p);
+    WB_LAUNCH_CHECK();
+  }
+  if (!WB_CUDA(cudaEventRecord(h->upload_done, c->upload_stream))) return 1;
+  h->upload_pending = true;
+  return 0;
+}
 int wb200_batch_set_pcm16_device(wb200_batch* h, const int16_t* dev_pcm) {
   if (!ctx()) return 1;
   return convert_pcm(h, dev_pcm);
@@ -394,25 +456,25 @@ int wb200_batch_upload_f64(wb200_batch* h, const double* host_x) {
 }
 
 int wb200_batch_dio(wb200_batch* h, const DioOption* o) {
-  if (!ctx()) return 1;
+  if (!ctx() || !wait_upload(h)) return 1;
   DioParams p = {o->f0_floor, o->f0_ceil, o->channels_in_octave, o->frame_period, o->speed, o->allowed_range};
   StageTimer t(&g_times.dio);
   return dio_run(&h->b, p, h->b.f0_raw.p) ? 0 : 1;
 }
 int wb200_batch_stonemask(wb200_batch* h) {
-  if (!ctx()) return 1;
+  if (!ctx() || !wait_upload(h)) return 1;
   Batch& b = h->b;
   StageTimer t(&g_times.stonemask);
   return stonemask_run(b.view(), b.fs, b.total_frames, b.frame_utt.p, b.frame_t.p, b.f0_raw.p, b.f0.p) ? 0 : 1;
 }
 int wb200_batch_harvest(wb200_batch* h, const HarvestOption* o) {
-  if (!ctx()) return 1;
+  if (!ctx() || !wait_upload(h)) return 1;
   HarvestParams p = {o->f0_floor, o->f0_ceil, o->frame_period};
   StageTimer t(&g_times.harvest);
   return harvest_run(&h->b, p, h->b.f0.p) ? 0 : 1;
 }
 int wb200_batch_cheaptrick(wb200_batch* h, const CheapTrickOption* o) {
-  if (!ctx()) return 1;
+  if (!ctx() || !wait_upload(h)) return 1;
   Batch& b = h->b;
   b.fft_size = o->fft_size;
   if (!b.sp.alloc((size_t)b.total_frames * (o->fft_size / 2 + 1))) return 1;
@@ -420,7 +482,7 @@ int wb200_batch_cheaptrick(wb200_batch* h, const CheapTrickOption* o) {
   return cheaptrick_run(b.view(), b.fs, b.total_frames, b.frame_utt.p, b.frame_t.p, b.f0.p, o->fft_size, o->q1, b.sp.p) ? 0 : 1;
 }
 int wb200_batch_d4c(wb200_batch* h, int fft_size, const D4COption* o) {
-  if (!ctx()) return 1;
+  if (!ctx() || !wait_upload(h)) return 1;
   Batch& b = h->b;
   b.fft_size = fft_size;
   if (!b.ap.alloc((size_t)b.total_frames * (fft_size / 2 + 1))) return 1;
@@ -496,18 +558,41 @@ int wb200_batch_get_y_pcm16(wb200_batch* h, int16_t* out) {
   Context* c = ctx();
   Batch& b = h->b;
   if (!c || !b.y.p) { set_error("synthesis has not been run"); return 1; }
-  DevBuf<int16_t> tmp;
-  if (!tmp.alloc((size_t)b.total_y)) return 1;
-  y_to_pcm16_kernel<<<(unsigned)((b.total_y + 255) / 256), 256, 0, c->stream>>>(b.y.p, b.total_y, tmp.p);
-  WB_LAUNCH_CHECK();
+  const long long n = wb200_batch_total_y(h);
+  std::vector<long long> cum(b.n_utt > 0 ? b.n_utt : 1);
   long long o = 0;
-  for (int u = 0; u < b.n_utt; ++u) {
-    if (b.h_y_len[u] > 0 &&
-        !WB_CUDA(cudaMemcpyAsync(out + o, tmp.p + b.h_y_off[u], (size_t)b.h_y_len[u] * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream)))
+  for (int u = 0; u < b.n_utt; ++u) { cum[u] = o; o += b.h_y_len[u]; }
+  DevBuf<long long> d_cum;
+  if (!h->pcm_out.alloc((size_t)n + 1) || !d_cum.alloc(b.n_utt)) return 1;
+  if (b.n_utt == 0 || n == 0) return 0;
+  if (!WB_CUDA(cudaMemcpyAsync(d_cum.p, cum.data(), b.n_utt * sizeof(long long), cudaMemcpyHostToDevice, c->stream))) return 1;
+  y_to_pcm16_kernel<<<dim3(64, b.n_utt), 256, 0, c->stream>>>(b.y.p, b.y_off.p, d_cum.p, b.y_len.p, h->pcm_out.p);
+  WB_LAUNCH_CHECK();
+  return (WB_CUDA(cudaMemcpyAsync(out, h->pcm_out.p, (size_t)n * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream)) &&
+          WB_CUDA(cudaStreamSynchronize(c->stream))) ? 0 : 1;
+}
+// The conversion runs on the library stream (after Synthesis), the copy on the download stream:
+// it overlaps the next batch's computation.  `out` must be pinned; valid after wb200_sync().
+int wb200_batch_get_y_pcm16_async(wb200_batch* h, int16_t* out) {
+  Context* c = ctx();
+  Batch& b = h->b;
+  if (!c || !b.y.p) { set_error("synthesis has not been run"); return 1; }
+  if (!ensure_copy_streams(c)) return 1;
+  const long long n = wb200_batch_total_y(h);
+  if (b.n_utt == 0 || n == 0) return 0;
+  if (!h->pcm_out.p || !h->out_off.p) {
+    std::vector<long long> cum(b.n_utt);
+    long long o = 0;
+    for (int u = 0; u < b.n_utt; ++u) { cum[u] = o; o += b.h_y_len[u]; }
+    if (!h->pcm_out.alloc((size_t)n + 1) || !h->out_off.alloc(b.n_utt)) return 1;
+    if (!WB_CUDA(cudaMemcpyAsync(h->out_off.p, cum.data(), b.n_utt * sizeof(long long), cudaMemcpyHostToDevice, c->stream)) ||
+        !WB_CUDA(cudaStreamSynchronize(c->stream)))
       return 1;
-    o += b.h_y_len[u];
   }
-  return WB_CUDA(cudaStreamSynchronize(c->stream)) ? 0 : 1;
+  y_to_pcm16_kernel<<<dim3(64, b.n_utt), 256, 0, c->stream>>>(b.y.p, b.y_off.p, h->out_off.p, b.y_len.p, h->pcm_out.p);
+  WB_LAUNCH_CHECK();
+  return (WB_CUDA(cudaEventRecord(c->copy_event, c->stream)) && WB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_event, 0)) &&
+          WB_CUDA(cudaMemcpyAsync(out, h->pcm_out.p, (size_t)n * sizeof(int16_t), cudaMemcpyDeviceToHost, c->copy_stream))) ? 0 : 1;
 }
 void* wb200_batch_device_ptr(wb200_batch* h, const char* which) {
   Batch& b = h->b;
@@ -531,6 +616,23 @@ int wb200_batch_get_coded(wb200_batch* h, float* lf0, float* mgc, float* bap) {
   if (mgc && d2h(mgc, b.mgc.p, F * b.mgc_dim * sizeof(float))) return 1;
   if (bap && d2h(bap, b.bap.p, F * b.bap_dim * sizeof(float))) return 1;
   return 0;
+}
+// Same copies on a second stream, ordered after everything queued so far on the library stream;
+// they run while later stages (Synthesis) compute.  Host buffers must be pinned and stay valid
+// until wb200_sync() returns.
+int wb200_batch_get_coded_async(wb200_batch* h, float* lf0, float* mgc, float* bap) {
+  Context* c = ctx();
+  if (!c) return 1;
+  Batch& b = h->b;
+  if (!b.mgc.p) { set_error("features have not been coded"); return 1; }
+  if (!ensure_copy_streams(c)) return 1;
+  const size_t F = (size_t)b.total_frames;
+  bool ok = WB_CUDA(cudaEventRecord(c->copy_event, c->stream)) &&
+            WB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_event, 0));
+  if (ok && lf0) ok = WB_CUDA(cudaMemcpyAsync(lf0, b.lf0.p, F * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+  if (ok && mgc) ok = WB_CUDA(cudaMemcpyAsync(mgc, b.mgc.p, F * b.mgc_dim * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+  if (ok && bap) ok = WB_CUDA(cudaMemcpyAsync(bap, b.bap.p, F * b.bap_dim * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+  return ok ? 0 : 1;
 }
 __global__ void mgc_unscale_kernel(const float* __restrict__ mgc, long long n, int ndim, double* __restrict__ out) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;

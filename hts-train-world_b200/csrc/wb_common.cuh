@@ -47,6 +47,9 @@ extern unsigned long long g_launch_count;   // kernels launched by this library
 struct Context {
   int device = -1;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;    // device-to-host copies that overlap later stages (lazily created)
+  cudaStream_t upload_stream = nullptr;  // host-to-device copies of the NEXT batch while this one computes
+  cudaEvent_t copy_event = nullptr;
   double2* d_twiddle = nullptr;          // [kTwN/2 + 1]
   float2* d_twiddle_f = nullptr;         // the same table rounded to FP32
   uint32_t* d_randn = nullptr;           // randn table: variate k = d_randn[k] / 2^28 - 6

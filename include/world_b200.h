@@ -66,6 +66,9 @@ WORLD_API int wb200_batch_frame_layout(const wb200_batch *b, int *f_off, int *f_
 WORLD_API int wb200_batch_upload_pcm16(wb200_batch *b, const int16_t *host_pcm);
 WORLD_API int wb200_batch_upload_f64(wb200_batch *b, const double *host_x);
 WORLD_API int wb200_batch_set_pcm16_device(wb200_batch *b, const int16_t *dev_pcm);
+/* asynchronous upload on a second stream: overlaps the computation of another batch; the stages
+ * of this batch wait for it on the device.  host_pcm must be pinned. */
+WORLD_API int wb200_batch_upload_pcm16_async(wb200_batch *b, const int16_t *host_pcm);
 
 /* ---- stages (each = the reference function of the same name over the whole batch) -------- */
 WORLD_API int wb200_batch_dio(wb200_batch *b, const DioOption *option);        /* -> raw f0 */
@@ -88,6 +91,8 @@ WORLD_API int wb200_batch_y_layout(const wb200_batch *b, long long *y_off, int *
 WORLD_API int wb200_batch_get_y(wb200_batch *b, double *host_y);     /* back to back */
 /* 16-bit output as the reference's wavwrite: trunc(y * 32767) clamped (W/test/audioio.cpp:115-170) */
 WORLD_API int wb200_batch_get_y_pcm16(wb200_batch *b, int16_t *host_pcm);
+/* asynchronous variant on a download stream (pinned `host_pcm`, valid after wb200_sync()) */
+WORLD_API int wb200_batch_get_y_pcm16_async(wb200_batch *b, int16_t *host_pcm);
 /* device pointers for zero-copy consumers: which = "x","f0_raw","f0","sp","ap","y" */
 WORLD_API void *wb200_batch_device_ptr(wb200_batch *b, const char *which);
 /* corpus statistics of voiced log-f0 over the batch: out = {count, sum, sum of squares};
@@ -99,6 +104,9 @@ WORLD_API int wb200_batch_lf0_stats(wb200_batch *b, double *out3);
  * Needs CheapTrick and D4C results in the batch. */
 WORLD_API int wb200_batch_code(wb200_batch *b, int mgc_dim, int bap_dim);
 WORLD_API int wb200_batch_get_coded(wb200_batch *b, float *host_lf0, float *host_mgc, float *host_bap);
+/* the same copies queued on a second stream so that they overlap the stages launched afterwards
+ * (Synthesis); the (pinned) host buffers are valid after wb200_sync() */
+WORLD_API int wb200_batch_get_coded_async(wb200_batch *b, float *host_lf0, float *host_mgc, float *host_bap);
 /* decode mgc back into the batch's spectrogram (DecodeSpectralEnvelope, then the inverse of the
  * tool's scalings): the entry of Synthesis-only runs that start from float32 mgc files */
 WORLD_API int wb200_batch_decode_mgc(wb200_batch *b, int fft_size, int mgc_dim, const float *host_mgc);
