@@ -258,7 +258,19 @@ def ours_arm(args):
             cpu_pool = ReferencePool(host_cores(), True)    # forked before CUDA is initialised; idle until the end
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout at the first collective; stdout carries ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     wb.init(local)
     stream = torch.cuda.Stream()
     wb.set_stream(stream.cuda_stream)
