@@ -304,6 +304,29 @@ def test_short_inputs(wb, reference_lib):
     assert M.ap_abs_error(o["ap"], wb.d4c(x, fs, t, o["f0"], o["fft_size"])) <= M.TOL_AP_ABS
 
 
+def test_empty_batch_and_long_utterance(wb, reference_lib):
+    """n_utt = 0 is a no-op; a 10 s utterance (Dio's reference FFT would be 2^19 points,
+    SURVEY.md 8 table) matches the reference through every stage."""
+    c = wb.Corpus(48000, [])
+    c.analyze()
+    assert c.total_frames == 0 and c.f0().size == 0
+    c.close()
+    from hts_train_world_b200 import signals
+    fs = 48000
+    x = signals.pcm_to_double(signals.make_utterance(77, fs, duration=10.0)[0])
+    o = reference_lib.analyze(x, fs)
+    t, f0r = wb.dio(x, fs)
+    f0 = wb.stonemask(x, fs, t, f0r)
+    assert M.vuv_agreement(o["f0"], f0) >= M.TOL_VUV_AGREEMENT and M.f0_rel_error(o["f0"], f0) <= M.TOL_F0_REL
+    assert M.lsd_db(o["sp"], wb.cheaptrick(x, fs, o["t"], o["f0"]))[1] <= M.TOL_LSD_DB
+    assert M.ap_abs_error(o["ap"], wb.d4c(x, fs, o["t"], o["f0"], o["fft_size"])) <= M.TOL_AP_ABS
+    y_ref = reference_lib.synthesis(o["f0"], o["sp"], o["ap"], o["fft_size"], 5.0, fs)
+    assert M.snr_db(y_ref, wb.synthesis(o["f0"], o["sp"], o["ap"], o["fft_size"], 5.0, fs)) >= M.TOL_SNR_DB
+    _, fh_ref = reference_lib.harvest(x, fs)
+    _, fh = wb.harvest(x, fs)
+    assert M.vuv_agreement(fh_ref, fh) >= M.TOL_VUV_AGREEMENT and M.f0_rel_error(fh_ref, fh) <= M.TOL_F0_REL
+
+
 def test_f0_extremes(wb, reference_lib):
     """f0 at the StoneMask / CheapTrick / D4C floors and at 800 Hz."""
     fs = 48000
