@@ -106,11 +106,14 @@ CodecTables* codec_tables(int fs, int fft_size, int ndim) {
 // dynamic shared memory: [ buf: cpad_size(max_dim/2) double2 | logsp: max_dim + 2 doubles ]
 // out[f][d] = DCT coefficient d of frame f (+ c0_add on d = 0).  scale multiplies the row first;
 // a scaled value of exactly 0 becomes zero_floor (W/test/analysis.cpp:297-301); pass 0 to disable.
+template <int LOG2MAX>     // log2(fft_size / 2); 0: given at run time
 __global__ void __launch_bounds__(128)
-codec_encode_kernel(const double* __restrict__ rows, int half, int log2max, const int* __restrict__ idx,
+codec_encode_kernel(const double* __restrict__ rows, int half, int log2max_rt, const int* __restrict__ idx,
                     const double* __restrict__ s, const double2* __restrict__ weight, int ndim, double scale,
                     double zero_floor, double c0_add, const double2* __restrict__ tw, double* __restrict__ out) {
   extern __shared__ double2 smem2[];
+  const int log2max = LOG2MAX > 0 ? LOG2MAX : log2max_rt;
+  constexpr int LM = LOG2MAX > 0 ? LOG2MAX - 1 : 0;
   const int max_dim = 1 << log2max, M = max_dim >> 1, log2m = log2max - 1;
   double2* buf = smem2;
   double* bufd = reinterpret_cast<double*>(buf);
@@ -132,7 +135,7 @@ codec_encode_kernel(const double* __restrict__ rows, int half, int log2max, cons
     const int pos = (j & 1) ? (max_dim - 1 - (j >> 1)) : (j >> 1);
     bufd[rfft_in_slot(pos, log2m)] = v;
   }
-  fft_dit<0, false, 128, 3>(buf, log2m, tw);
+  fft_dit<LM, false, 128, 3>(buf, log2m, tw);
   const double normalization = sqrt((double)max_dim);
   for (int d = tid; d < ndim; d += T) {
     const double2 X = rfft_bin(buf, log2m, d, tw);
@@ -218,10 +221,19 @@ bool codec_encode_run(const double* d_rows, int n_frames, int fs, int fft_size, 
   CodecTables* t = codec_tables(fs, fft_size, ndim);
   if (!t) return false;
   const size_t smem = cpad_size(t->max_dim / 2) * sizeof(double2) + (t->max_dim + 2) * sizeof(double);
-  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(codec_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
   KernelTimer kt("codec_encode_kernel");
-  codec_encode_kernel<<<n_frames, 128, smem, c->stream>>>(d_rows, fft_size / 2, t->log2max, t->enc_idx.p, t->enc_s.p, t->enc_w.p, ndim,
-                                                         scale, zero_floor, c0_add, c->d_twiddle, d_out);
+#define WB_ENC_LAUNCH(L)                                                                                            \
+  do {                                                                                                              \
+    WB_CUDA_OR_RETURN(cudaFuncSetAttribute(codec_encode_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
+    codec_encode_kernel<L><<<n_frames, 128, smem, c->stream>>>(d_rows, fft_size / 2, t->log2max, t->enc_idx.p, t->enc_s.p, t->enc_w.p, ndim, \
+                                                              scale, zero_floor, c0_add, c->d_twiddle, d_out);     \
+  } while (0)
+  switch (t->log2max) {
+    case 9: WB_ENC_LAUNCH(9); break;
+    case 10: WB_ENC_LAUNCH(10); break;
+    default: WB_ENC_LAUNCH(0); break;
+  }
+#undef WB_ENC_LAUNCH
   WB_LAUNCH_CHECK(); kt.stop();
   return true;
 }

@@ -96,8 +96,8 @@ stonemask_kernel(UttView u, const int* __restrict__ frame_utt, const double* __r
     const double base_time = div_rn((double)(i - hwl), (double)fs);
     const int index_raw = matlab_round(mul_rn(add_rn(t_pos, base_time), (double)fs));
     const double tmp = add_rn(div_rn(index_raw - 1.0, (double)fs), -t_pos);
-    win[i] = 0.42 + 0.5 * cos(div_rn(mul_rn(2.0 * kPi, tmp), wlen)) +
-             0.08 * cos(div_rn(mul_rn(4.0 * kPi, tmp), wlen));
+    const double cs = cos(div_rn(mul_rn(2.0 * kPi, tmp), wlen));
+    win[i] = 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);        // cos(2a) = 2 cos^2(a) - 1
   }
   __syncthreads();
   // GetDiffWindow + GetSpectra, packed
