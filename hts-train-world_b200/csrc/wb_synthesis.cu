@@ -332,11 +332,14 @@ __device__ __forceinline__ void envelope_at(const ChanInfo& ci, const double* __
 __device__ __forceinline__ void exp_sincos(double re, double im, double* er, double* ei) {
   const double e = exp(re); double sn, cs; sincos(im, &sn, &cs); *er = e * cs; *ei = e * sn;
 }
+// FP32 channel: hardware approximations (MUFU.EX2 / SIN / COS / LG2, ~2^-21 relative); |im| is a
+// minimum-phase angle of a few radians at most, far inside the accurate range of __sincosf.  The
+// resynthesis stays > 100 dB above the error (tests: tolerance 60 dB).
 __device__ __forceinline__ void exp_sincos(float re, float im, float* er, float* ei) {
-  const float e = expf(re); float sn, cs; sincosf(im, &sn, &cs); *er = e * cs; *ei = e * sn;
+  const float e = __expf(re); float sn, cs; __sincosf(im, &sn, &cs); *er = e * cs; *ei = e * sn;
 }
 __device__ __forceinline__ double log_of(double v, double) { return log(v); }
-__device__ __forceinline__ float log_of(double v, float) { return logf(static_cast<float>(v)); }
+__device__ __forceinline__ float log_of(double v, float) { return __logf(static_cast<float>(v)); }
 
 template <int LOG2N, typename C, int THREADS = 256>      // LOG2N 0: size given at run time (c.log2n)
 __global__ void __launch_bounds__(THREADS, 768 / THREADS)
