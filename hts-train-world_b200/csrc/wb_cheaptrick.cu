@@ -221,7 +221,7 @@ bool cheaptrick_run(const UttView& u, int fs, int total_frames, const int* frame
   const size_t smem = cpad_size(fft_size / 2) * sizeof(double2) + (fft_size + 16 + 128) * sizeof(double);
   KernelTimer kt1("cheaptrick_kernel");
   // 128-thread CTAs: 6 frames per SM instead of 3, half as many warps behind every barrier (9 % faster)
-  static const bool t128 = getenv("WB_CT_T256") == nullptr;
+  const bool t128 = true;
 #define WB_CT_LAUNCH(L)                                                                                             \
   do {                                                                                                              \
     if (t128) {                                                                                                     \

@@ -559,7 +559,7 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
     const int hd = nd / 2;
     const size_t smem = d4c_cbuf_slots(nd, c.nbands) * sizeof(double2) + (size_t)(2 * (hd + 8) + 160) * sizeof(double) +
                         sizeof(SelectScratch) + (kMaxBands + 2) * sizeof(double);
-    const int threads = (nd > 4096 || getenv("WB_D4C_T512")) ? 512 : 256;
+    const int threads = nd > 4096 ? 512 : 256;
     KernelTimer kt2("d4c_main_kernel");
 #define WB_D4C_LAUNCH(L, TH, ...)                                                                                   \
   do {                                                                                                              \
@@ -567,8 +567,7 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
     d4c_main_kernel<L, TH, ##__VA_ARGS__><<<total_frames, TH, smem, st>>>(u, frame_utt, frame_t, f0, d_ap0.p, offs_main.p, tot_lt.p, ctxp->d_randn, \
                                                            ctxp->d_twiddle, ctxp->d_twiddle_f, d_win.p, c, ap);                         \
   } while (0)
-    if (threads == 512 && c.log2nd == 12) WB_D4C_LAUNCH(12, 512);
-    else if (threads == 512) WB_D4C_LAUNCH(0, 512);
+    if (threads == 512) WB_D4C_LAUNCH(0, 512);
     else if (c.log2nd == 12) WB_D4C_LAUNCH(12, 256, 4);      // radix-16 passes: 3 instead of 4 round trips
     else if (c.log2nd == 11) WB_D4C_LAUNCH(11, 256, 4);
     else WB_D4C_LAUNCH(0, 256);

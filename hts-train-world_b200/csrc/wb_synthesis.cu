@@ -605,7 +605,6 @@ bool synthesis_run(Batch* b, const int* y_len) {
   static const bool fp64 = getenv("WB_SYNTH_FP64") != nullptr;      // debugging aid: all four transforms in FP64
   const size_t smem = 2 * cpad_size(N) * (fp64 ? sizeof(double2) : sizeof(float2)) + 96 * sizeof(double);
   if (N / 2 / 256 + 1 > 9) { set_error("Synthesis: fft_size %d too large for the register fold", N); return false; }
-  static const bool t128 = getenv("WB_SYNTH_T128") != nullptr;
   KernelTimer kt3("synth_pulse_kernel");
 #define WB_SP_LAUNCH(L, CT, TW)                                                                                     \
   do {                                                                                                              \
@@ -621,15 +620,7 @@ bool synthesis_run(Batch* b, const int* y_len) {
   } else {
     switch (log2n) {
       case 10: WB_SP_LAUNCH(10, float2, ctxp->d_twiddle_f); break;
-      case 11:
-        if (t128) {
-          WB_CUDA_OR_RETURN(cudaFuncSetAttribute(synth_item_kernel<11, float2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
-          synth_item_kernel<11, float2, 128><<<n_items, 128, smem, st>>>(b->sp.p, b->ap.p, b->f_off.p, b->f_len.p, b->y_off.p, b->y_len.p, d_poff.p, d_cnt.p,
-              p_index.p, p_shift.p, p_vuv.p, p_utt.p, list_per.p, list_aper.p, n_per, n_aper, ctxp->d_randn, ctxp->d_twiddle_f, d_rem.p, c, b->y.p);
-        } else {
-          WB_SP_LAUNCH(11, float2, ctxp->d_twiddle_f);
-        }
-        break;
+      case 11: WB_SP_LAUNCH(11, float2, ctxp->d_twiddle_f); break;
       case 12: WB_SP_LAUNCH(12, float2, ctxp->d_twiddle_f); break;
       default: WB_SP_LAUNCH(0, float2, ctxp->d_twiddle_f); break;
     }
