@@ -477,6 +477,11 @@ def ours_arm(args):
         "wall_ms_per_step": wall / args.steps,
         "stage_ms": stage_ms,
         "roofline": roof,
+        # the same kernel against the memory roofline (it is nowhere near it: the frame lives in shared memory)
+        "roofline_hbm": {"bound": "hbm", "achieved": dcnt["bytes"] / dsec / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": dcnt["bytes"] / dsec / 1e9 / hbm_peak, "traffic": roof.get("traffic"), "kernel": dom},
+        "dtype_note": "FP64 wherever a cancellation follows (power spectra, cumulative sums, group delay, time base); "
+                      "FP32 transforms for log spectra / cepstra / noise / band slices (DESIGN.md section 4)",
         "kernels": kernels,
         "peaks": {"fp64_tflops_measured": fp64_peak, "fp32_tflops_measured": fp32_peak, "hbm_gbs": hbm_peak},
         "clocks": clk,
