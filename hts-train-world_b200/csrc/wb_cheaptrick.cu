@@ -126,10 +126,11 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
   __syncthreads();
   // DCCorrection (common.cpp:56-75)
   const double inv_df = (double)N / fs;
+  const double inv_n = 1.0 / N;                 // N is a power of two: x * inv_n == x / N exactly
   {
     const int upper_limit = 2 + static_cast<int>(mul_rn(f0c, (double)N) / fs);
     for (int i = tid; i < upper_limit - 1; i += T)
-      bufd[i] = interp1q_at(f0c, -inv_df, aux, upper_limit + 1, mul_rn((double)i, (double)fs) / N);
+      bufd[i] = interp1q_at(f0c, -inv_df, aux, upper_limit + 1, mul_rn((double)i, (double)fs) * inv_n);
     __syncthreads();
     for (int i = tid; i < upper_limit - 1; i += T) aux[i] += bufd[i];
     __syncthreads();
@@ -142,18 +143,19 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
     if (i < boundary) v = aux[boundary - i];
     else if (i < half + boundary) v = aux[i - boundary];
     else v = aux[half - (i - (half + boundary))];
-    bufd[i] = mul_rn(v, (double)fs) / N;
+    bufd[i] = mul_rn(v, (double)fs) * inv_n;
   }
   __syncthreads();
   block_inclusive_scan(bufd, len, red);
   {
     const double origin_axis = -(boundary - 0.5) * fs / N;
+    const double inv_width = 1.0 / width;
     const uint32_t* __restrict__ rn2 = rn + W;
     for (int k = tid; k <= half; k += T) {
-      const double fa = add_rn(mul_rn((double)k / N, (double)fs), -width / 2.0);
+      const double fa = add_rn(mul_rn((double)k * inv_n, (double)fs), -width / 2.0);
       const double low = interp1q_at(origin_axis, inv_df, bufd, len, fa);
       const double high = interp1q_at(origin_axis, inv_df, bufd, len, add_rn(fa, width));
-      const double sm = (high - low) / width;
+      const double sm = (high - low) * inv_width;
       // AddInfinitesimalNoise (:147-151) then log (:38-39)
       // the logarithm feeds the FP32 liftering transforms: FP32 accuracy is all that survives
       aux[k] = logf(static_cast<float>(sm + fabs(randn_from_u32(rn2[k])) * kEps));
