@@ -40,6 +40,35 @@ _ip = C.POINTER(C.c_int)
 _lib = None
 
 
+CMP_MAX_STREAMS, CMP_MAX_WINDOWS, CMP_MAX_WIN_SIZE = 8, 4, 15
+CMP_SRC = {"host": 0, "mgc": 1, "lf0": 2, "bap": 3}
+
+
+class CmpStream(C.Structure):          # include/world_b200.h: wb200_cmp_stream
+    _fields_ = [("source", C.c_int), ("dim", C.c_int), ("host_data", C.c_void_p), ("n_win", C.c_int),
+                ("win_size", C.c_int * CMP_MAX_WINDOWS),
+                ("win_coef", (C.c_double * CMP_MAX_WIN_SIZE) * CMP_MAX_WINDOWS)]
+
+
+# data/win/{mgc,lf0,bap,vib}.win[123] of the reference: static, delta, delta-delta
+DEFAULT_WINDOWS = ((1.0,), (-0.5, 0.0, 0.5), (1.0, -2.0, 1.0))
+
+
+def parse_window_file(text):
+    """One data/win/*.win file: "size c1 ... csize" on its first line (data/scripts/window.pl:63-66)."""
+    tok = text.split("\n")[0].split()
+    size = int(float(tok[0]))
+    return tuple(float(v) for v in tok[1:1 + size])
+
+
+def htk_header(n_frames, samp_freq, frame_shift, byte_per_frame, kind=9):
+    """The 12 bytes data/scripts/addhtkheader.pl puts in front of a cmp file."""
+    out = (C.c_ubyte * 12)()
+    _check(lib().wb200_htk_header(int(n_frames), int(samp_freq), int(frame_shift), int(byte_per_frame), int(kind), out),
+           "htk_header")
+    return bytes(out)
+
+
 class WorldB200Error(RuntimeError):
     pass
 
@@ -127,6 +156,11 @@ def lib():
         "wb200_batch_get_coded_async": (i32, [vp, vp, vp, vp]),
         "wb200_batch_decode_mgc": (i32, [vp, i32, i32, vp]),
         "wb200_batch_feature_stats": (i32, [vp, _dp]),
+        "wb200_batch_compose_cmp": (i32, [vp, C.POINTER(CmpStream), i32]),
+        "wb200_batch_cmp_dim": (i32, [vp]),
+        "wb200_batch_get_cmp": (i32, [vp, vp]),
+        "wb200_batch_cmp_stats": (i32, [vp, _dp]),
+        "wb200_htk_header": (i32, [i32, i32, i32, i32, i32, C.POINTER(C.c_ubyte)]),
         "GetNumberOfAperiodicities": (i32, [i32]),
         "CodeSpectralEnvelope": (None, [_dpp, i32, i32, i32, i32, _dpp]),
         "DecodeSpectralEnvelope": (None, [_dpp, i32, i32, i32, i32, _dpp]),
@@ -463,6 +497,46 @@ class Corpus:
         """[(1 + mgc_dim), 3] = {count, sum, sum of squares}: row 0 voiced lf0, rows 1.. mgc dims."""
         out = np.zeros((1 + self.mgc_dim, 3))
         _check(lib().wb200_batch_feature_stats(self._h, _ptr(out)), "feature_stats")
+        return out
+
+    def compose_cmp(self, streams=("mgc", "lf0", "bap"), windows=None):
+        """The `cmp` target of data/Makefile.in:276-321 for the whole batch: every stream extended by
+        its delta windows (data/scripts/window.pl) and merged side by side.  `streams`: names of the
+        batch's own coded features ("mgc", "lf0", "bap") or (name, array[total_frames, dim]) pairs
+        for streams computed on the host (Extract.py's lf0 / vib).  `windows`: one tuple of
+        coefficient tuples per stream (default data/win/*.win[123]).  Returns [total_frames, cmp_dim]
+        float32."""
+        n = len(streams)
+        arr = (CmpStream * n)()
+        keep = []
+        for i, st in enumerate(streams):
+            wins = DEFAULT_WINDOWS if windows is None else windows[i]
+            if isinstance(st, str):
+                arr[i].source, arr[i].dim, arr[i].host_data = CMP_SRC[st], 0, None
+            else:
+                data = np.ascontiguousarray(st[1], np.float32)
+                data = data.reshape(self.total_frames, data.shape[1] if data.ndim == 2 else 1)
+                keep.append(data)
+                arr[i].source, arr[i].dim, arr[i].host_data = CMP_SRC["host"], data.shape[1], data.ctypes.data
+            if len(wins) > CMP_MAX_WINDOWS:
+                raise WorldB200Error("at most %d windows per stream" % CMP_MAX_WINDOWS)
+            arr[i].n_win = len(wins)
+            for w, coef in enumerate(wins):
+                if len(coef) > CMP_MAX_WIN_SIZE:
+                    raise WorldB200Error("window longer than %d taps" % CMP_MAX_WIN_SIZE)
+                arr[i].win_size[w] = len(coef)
+                for k, v in enumerate(coef):
+                    arr[i].win_coef[w][k] = float(v)
+        _check(lib().wb200_batch_compose_cmp(self._h, arr, n), "compose_cmp")
+        self.cmp_dim = int(lib().wb200_batch_cmp_dim(self._h))
+        out = np.zeros((self.total_frames, self.cmp_dim), np.float32)
+        _check(lib().wb200_batch_get_cmp(self._h, out.ctypes.data), "get_cmp")
+        return out
+
+    def cmp_stats(self):
+        """[cmp_dim, 3] = {count, sum, sum of squares} of every cmp column (per-GPU partials)."""
+        out = np.zeros((self.cmp_dim, 3))
+        _check(lib().wb200_batch_cmp_stats(self._h, _ptr(out)), "cmp_stats")
         return out
 
     def lf0_stats(self):

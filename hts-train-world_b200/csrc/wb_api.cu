@@ -10,6 +10,11 @@
 
 using namespace wb;
 
+namespace wb {
+bool batch_compose_cmp(Batch* b, const wb200_cmp_stream* streams, int n_streams);   // wb_cmp.cu
+bool batch_cmp_stats(Batch* b, double* h_out);
+}
+
 struct wb200_batch {
   Batch b;
   DevBuf<int16_t> pcm_stage, pcm_out;
@@ -660,6 +665,29 @@ int wb200_batch_decode_mgc(wb200_batch* h, int fft_size, int mgc_dim, const floa
   sp_unscale_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(b.sp.p, ns);
   WB_LAUNCH_CHECK();
   return WB_CUDA(cudaStreamSynchronize(c->stream)) ? 0 : 1;
+}
+int wb200_batch_compose_cmp(wb200_batch* h, const wb200_cmp_stream* streams, int n_streams) {
+  if (!ctx()) return 1;
+  return batch_compose_cmp(&h->b, streams, n_streams) ? 0 : 1;
+}
+int wb200_batch_cmp_dim(const wb200_batch* h) { return h->b.cmp_dim; }
+int wb200_batch_get_cmp(wb200_batch* h, float* out) {
+  return d2h(out, h->b.cmp.p, (size_t)h->b.total_frames * h->b.cmp_dim * sizeof(float));
+}
+int wb200_batch_cmp_stats(wb200_batch* h, double* out) {
+  if (!ctx()) return 1;
+  return batch_cmp_stats(&h->b, out) ? 0 : 1;
+}
+// data/scripts/addhtkheader.pl: pack("l", nframe) pack("l", 10000000 * frameshift / samprate)
+// pack("s", byte) pack("s", type); host arithmetic only (12 bytes per utterance).
+int wb200_htk_header(int n_frames, int samp_freq, int frame_shift, int byte_per_frame, int kind,
+                     unsigned char* out12) {
+  if (!out12 || samp_freq <= 0) return 1;
+  const int32_t nf = n_frames;
+  const int32_t shift = (int32_t)(10000000.0 * frame_shift / samp_freq);
+  const int16_t bytes = (int16_t)byte_per_frame, type = (int16_t)kind;
+  memcpy(out12, &nf, 4); memcpy(out12 + 4, &shift, 4); memcpy(out12 + 8, &bytes, 2); memcpy(out12 + 10, &type, 2);
+  return 0;
 }
 int wb200_batch_lf0_stats(wb200_batch* h, double* out3);
 int wb200_batch_feature_stats(wb200_batch* h, double* out) {

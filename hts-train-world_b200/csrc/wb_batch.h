@@ -37,6 +37,9 @@ struct Batch {
   // coded features of the analysis tool (W/test/analysis.cpp:293-390), float32 like its files
   int mgc_dim = 0, bap_dim = 0;
   DevBuf<float> lf0, mgc, bap;         // [total_frames], [total_frames][mgc_dim], [total_frames][bap_dim]
+  // training observation vectors (data/Makefile.in:276-321): statics + delta windows of every stream
+  int cmp_dim = 0;
+  DevBuf<float> cmp;                   // [total_frames][cmp_dim]
   // synthesis
   std::vector<long long> h_y_off;
   std::vector<int> h_y_len;

@@ -43,6 +43,7 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
   extern __shared__ double2 smem2[];
   const int log2n = LOG2N > 0 ? LOG2N : log2n_rt;
   constexpr int LM = LOG2N > 0 ? LOG2N - 1 : 0;
+  constexpr int TWL = LOG2N > 0 ? LOG2N : kTwLog2;       // compact twiddle tables of this size, or the master tables
   const int N = 1 << log2n, M = N >> 1, log2m = log2n - 1, half = M;   // half = N/2
   double2* buf = smem2;
   double* bufd = reinterpret_cast<double*>(buf);
@@ -118,9 +119,9 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
   }
 
   // ---- GetPowerSpectrum (:64-82) -----------------------------------------------------------
-  fft_dit<LM, false, THREADS, THREADS == 256 ? 4 : 3>(buf, log2m, tw);
+  fft_dit<LM, false, THREADS, THREADS == 256 ? 4 : 3, TWL>(buf, log2m, tw);
   for (int k = tid; k <= half; k += T) {
-    const double2 X = rfft_bin(buf, log2m, k, tw);
+    const double2 X = rfft_bin<TWL>(buf, log2m, k, tw);
     aux[k] = X.x * X.x + X.y * X.y;
   }
   __syncthreads();
@@ -170,11 +171,11 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
     float2* fb = reinterpret_cast<float2*>(buf);
     float* fbs = reinterpret_cast<float*>(buf);
     for (int i = tid; i < N; i += T) fbs[rfft_in_slot_f(i, log2m)] = static_cast<float>(aux[i <= half ? i : N - i]);
-    fft_dit<LM, false, THREADS, 4>(fb, log2m, twf);
+    fft_dit<LM, false, THREADS, 4, TWL>(fb, log2m, twf);
     float* lif = reinterpret_cast<float*>(aux);         // liftered cepstrum, real
     __syncthreads();                                     // everyone has read aux
     for (int k = tid; k <= half; k += T) {
-      const float re = rfft_bin(fb, log2m, k, twf).x;
+      const float re = rfft_bin<TWL>(fb, log2m, k, twf).x;
       float lifter = 1.f, comp = 1.f;
       if (k > 0) {
         const float fq = static_cast<float>(f0c * ((double)k / fs));    // f0 * quefrency
@@ -187,10 +188,10 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
     }
     __syncthreads();
     for (int k = tid; k < half; k += T) {
-      const float2 z = c2r_pack(make_float2(lif[k], 0.f), make_float2(lif[half - k], 0.f), k, log2m, twf);
+      const float2 z = c2r_pack<TWL>(make_float2(lif[k], 0.f), make_float2(lif[half - k], 0.f), k, log2m, twf);
       fb[cpadf(brev(k, log2m))] = z;
     }
-    fft_dit<LM, true, THREADS, 4>(fb, log2m, twf);
+    fft_dit<LM, true, THREADS, 4, TWL>(fb, log2m, twf);
     for (int k = tid; k <= half; k += T) out[k] = exp(static_cast<double>(fbs[rfft_out_slot_f(k)]));
   }
 }
@@ -228,10 +229,10 @@ bool cheaptrick_run(const UttView& u, int fs, int total_frames, const int* frame
   do {                                                                                                              \
     if (t128) {                                                                                                     \
     WB_CUDA_OR_RETURN(cudaFuncSetAttribute(cheaptrick_kernel<L, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
-    cheaptrick_kernel<L, 128><<<total_frames, 128, smem, st>>>(u, frame_utt, frame_t, f0, offs.p, c->d_randn, c->d_twiddle, c->d_twiddle_f, fs, log2n, q1, f0_floor, sp); \
+    cheaptrick_kernel<L, 128><<<total_frames, 128, smem, st>>>(u, frame_utt, frame_t, f0, offs.p, c->d_randn, L > 0 ? c->tw_c(L > 0 ? L : 4) : c->d_twiddle, L > 0 ? c->tw_cf(L > 0 ? L : 4) : c->d_twiddle_f, fs, log2n, q1, f0_floor, sp); \
     break; }                                                                                                        \
     WB_CUDA_OR_RETURN(cudaFuncSetAttribute(cheaptrick_kernel<L, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
-    cheaptrick_kernel<L, 256><<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0, offs.p, c->d_randn, c->d_twiddle, c->d_twiddle_f, fs, log2n, q1, f0_floor, sp); \
+    cheaptrick_kernel<L, 256><<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0, offs.p, c->d_randn, L > 0 ? c->tw_c(L > 0 ? L : 4) : c->d_twiddle, L > 0 ? c->tw_cf(L > 0 ? L : 4) : c->d_twiddle_f, fs, log2n, q1, f0_floor, sp); \
   } while (0)
   switch (log2n) {
     case 10: WB_CT_LAUNCH(10); break;

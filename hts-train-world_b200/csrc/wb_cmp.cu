@@ -1,0 +1,146 @@
+// world-b200: composing the training observation vectors ("cmp") on the device.
+//
+// Reference: data/Makefile.in:276-321 (the WORLD branch of the `cmp` target) — per utterance
+//   perl scripts/window.pl DIM stream.f32 win1 win2 win3 > tmp.stream     (data/scripts/window.pl)
+//   merge +f -s 0 -l ... -L ...  tmp.mgc < tmp.lf0 ... > tmp.cmp            (streams side by side)
+//   perl scripts/addhtkheader.pl SAMPFREQ FRAMESHIFT BYTEPERFRAME 9 tmp.cmp (data/scripts/addhtkheader.pl)
+// Here: one kernel writes every (frame, window, dimension) element of every stream straight
+// into its column of the [total_frames][cmp_dim] float32 matrix, so the windowed streams never
+// exist on their own.  The arithmetic follows window.pl literally: the float32 statics are
+// widened to double, the taps are accumulated in double in the order k = -nlr .. nlr starting
+// from 0.0, frame indices are clamped to the utterance, and an element becomes -1.0e10 (the
+// "ignore value" of window.pl:55) when any tap that lies between the first and the last non-zero
+// coefficient of the window reads -1.0e10.  The result is rounded to float32 once (pack "f").
+// The kernel is a pure HBM stream: 4 bytes written per element, the statics come from L2.
+#include "../../include/world_b200.h"
+#include "wb_batch.h"
+
+namespace wb {
+
+namespace {
+
+constexpr double kIgnoreValue = -1.0e+10;     // window.pl:55
+
+// one (stream, window) pair = `dim` adjacent columns of the cmp frame
+struct CmpSegment {
+  const float* src;        // [total_frames][dim] statics (device)
+  int dim, col0, nlr;
+  int chk_lo, chk_hi;      // taps (0-based, 0 .. 2 nlr) between the first and last non-zero coefficient
+  double coef[WB200_CMP_MAX_WIN_SIZE];
+};
+
+__global__ void __launch_bounds__(256)
+cmp_compose_kernel(const CmpSegment* __restrict__ segs, const int* __restrict__ frame_utt,
+                   const int* __restrict__ f_off, const int* __restrict__ f_len, int total_frames,
+                   int cmp_dim, float* __restrict__ out) {
+  const CmpSegment& s = segs[blockIdx.y];
+  const long long n = (long long)total_frames * s.dim;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(e / s.dim), j = (int)(e - (long long)f * s.dim);
+    const int u = frame_utt[f];
+    const int first = f_off[u], T = f_len[u], t = f - first;
+    double acc = 0.0;
+    bool boundary = false;
+    for (int k = -s.nlr; k <= s.nlr; ++k) {
+      const int l = min(T - 1, max(0, t + k));                         // window.pl:95-103 / :111-119
+      const double v = (double)s.src[(size_t)(first + l) * s.dim + j];
+      const int tap = k + s.nlr;
+      if (tap >= s.chk_lo && tap <= s.chk_hi && v == kIgnoreValue) boundary = true;
+      acc = __dadd_rn(acc, __dmul_rn(s.coef[tap], v));                  // no contraction: perl adds a rounded product
+    }
+    out[(size_t)f * cmp_dim + s.col0 + j] = (float)(boundary ? kIgnoreValue : acc);
+  }
+}
+
+// per-column {count, sum, sum of squares} of a [frames][ndim] float matrix (all columns in one launch)
+__global__ void cmp_stats_kernel(const float* __restrict__ m, int n_frames, int ndim, double* __restrict__ out3) {
+  __shared__ double red[96];
+  const int d = blockIdx.y;
+  double v[3] = {0.0, 0.0, 0.0};
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n_frames; f += gridDim.x * blockDim.x) {
+    const double x = m[(size_t)f * ndim + d];
+    v[0] += 1.0; v[1] += x; v[2] += x * x;
+  }
+  block_sum<3>(v, red);
+  if (threadIdx.x == 0) { atomicAdd(&out3[d * 3], v[0]); atomicAdd(&out3[d * 3 + 1], v[1]); atomicAdd(&out3[d * 3 + 2], v[2]); }
+}
+
+}  // namespace
+
+bool batch_compose_cmp(Batch* b, const wb200_cmp_stream* streams, int n_streams) {
+  Context* c = ctx();
+  if (!c) return false;
+  if (n_streams < 1 || n_streams > WB200_CMP_MAX_STREAMS) { set_error("cmp: %d streams (1..%d supported)", n_streams, WB200_CMP_MAX_STREAMS); return false; }
+  const int F = b->total_frames;
+  std::vector<CmpSegment> segs;
+  std::vector<DevBuf<float>> staged(n_streams);
+  int col = 0;
+  for (int s = 0; s < n_streams; ++s) {
+    const wb200_cmp_stream& st = streams[s];
+    const float* src = nullptr;
+    int dim = st.dim;
+    switch (st.source) {
+      case WB200_CMP_SRC_MGC: src = b->mgc.p; dim = b->mgc_dim; break;
+      case WB200_CMP_SRC_LF0: src = b->lf0.p; dim = 1; break;
+      case WB200_CMP_SRC_BAP: src = b->bap.p; dim = b->bap_dim; break;
+      case WB200_CMP_SRC_HOST:
+        if (!st.host_data || dim < 1) { set_error("cmp: stream %d has no data", s); return false; }
+        if (!staged[s].alloc((size_t)F * dim + 1)) return false;
+        if (F > 0) WB_CUDA_OR_RETURN(cudaMemcpyAsync(staged[s].p, st.host_data, (size_t)F * dim * sizeof(float), cudaMemcpyHostToDevice, c->stream), false);
+        src = staged[s].p;
+        break;
+      default: set_error("cmp: stream %d: unknown source %d", s, st.source); return false;
+    }
+    if (!src || dim < 1) { set_error("cmp: stream %d: features have not been coded (wb200_batch_code)", s); return false; }
+    if (st.n_win < 1 || st.n_win > WB200_CMP_MAX_WINDOWS) { set_error("cmp: stream %d: %d windows (1..%d supported)", s, st.n_win, WB200_CMP_MAX_WINDOWS); return false; }
+    for (int w = 0; w < st.n_win; ++w) {
+      const int size = st.win_size[w];
+      if (size < 1 || size > WB200_CMP_MAX_WIN_SIZE || size % 2 != 1) {      // window.pl:83-85 dies on even sizes
+        set_error("cmp: stream %d window %d: size %d (must be odd, <= %d)", s, w, size, WB200_CMP_MAX_WIN_SIZE);
+        return false;
+      }
+      CmpSegment g;
+      g.src = src; g.dim = dim; g.col0 = col; g.nlr = (size - 1) / 2;
+      for (int i = 0; i < WB200_CMP_MAX_WIN_SIZE; ++i) g.coef[i] = i < size ? st.win_coef[w][i] : 0.0;
+      g.chk_lo = 0; g.chk_hi = size - 1;                                     // window.pl:70-81
+      while (g.chk_lo < size && g.coef[g.chk_lo] == 0.0) ++g.chk_lo;
+      while (g.chk_hi >= 0 && g.coef[g.chk_hi] == 0.0) --g.chk_hi;
+      segs.push_back(g);
+      col += dim;
+    }
+  }
+  b->cmp_dim = col;
+  if (!b->cmp.alloc((size_t)F * col + 1)) return false;
+  if (F == 0) return true;
+  DevBuf<CmpSegment> d_segs;
+  if (!d_segs.alloc(segs.size())) return false;
+  WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_segs.p, segs.data(), segs.size() * sizeof(CmpSegment), cudaMemcpyHostToDevice, c->stream), false);
+  {
+    KernelTimer kt("cmp_compose_kernel");
+    cmp_compose_kernel<<<dim3(148 * 4, (unsigned)segs.size()), 256, 0, c->stream>>>(d_segs.p, b->frame_utt.p, b->f_off.p, b->f_len.p, F, col, b->cmp.p);
+    WB_LAUNCH_CHECK(); kt.stop();
+  }
+  // the host vectors (segs, staged uploads) must outlive the copies queued above
+  WB_CUDA_OR_RETURN(cudaStreamSynchronize(c->stream), false);
+  return true;
+}
+
+bool batch_cmp_stats(Batch* b, double* h_out) {   // [cmp_dim][3]
+  Context* c = ctx();
+  if (!c) return false;
+  if (!b->cmp.p || b->cmp_dim < 1) { set_error("cmp stats: wb200_batch_compose_cmp has not been run"); return false; }
+  const int F = b->total_frames, nd = b->cmp_dim;
+  DevBuf<double> d;
+  if (!d.alloc((size_t)nd * 3)) return false;
+  cudaStream_t st = c->stream;
+  WB_CUDA_OR_RETURN(cudaMemsetAsync(d.p, 0, (size_t)nd * 3 * sizeof(double), st), false);
+  if (F > 0) {
+    cmp_stats_kernel<<<dim3(32, nd), 256, 0, st>>>(b->cmp.p, F, nd, d.p);
+    WB_LAUNCH_CHECK();
+  }
+  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_out, d.p, (size_t)nd * 3 * sizeof(double), cudaMemcpyDeviceToHost, st), false);
+  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  return true;
+}
+
+}  // namespace wb

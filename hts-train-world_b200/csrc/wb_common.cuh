@@ -52,6 +52,15 @@ struct Context {
   cudaEvent_t copy_event = nullptr;
   double2* d_twiddle = nullptr;          // [kTwN/2 + 1]
   float2* d_twiddle_f = nullptr;         // the same table rounded to FP32
+  // compact copies of the same values for one transform size each: table L holds
+  // exp(-2 pi i k / 2^L), k = 0 .. 2^(L-1), contiguous, so the entries one FFT touches share
+  // cache lines (the master table spreads them 2^(15-L) entries apart and they fall out of the
+  // small L1 that is left beside 220 KB of shared memory).  L = 4 .. kTwLog2.
+  double2* d_twiddle_c = nullptr;
+  float2* d_twiddle_cf = nullptr;
+  static size_t tw_c_offset(int L) { return ((size_t)1 << (L - 1)) + 2 * (size_t)L; }   // entries before table L
+  const double2* tw_c(int L) const { return d_twiddle_c + tw_c_offset(L); }
+  const float2* tw_cf(int L) const { return d_twiddle_cf + tw_c_offset(L); }
   uint32_t* d_randn = nullptr;           // randn table: variate k = d_randn[k] / 2^28 - 6
   size_t randn_count = 0;
   int sm_count = 0;
@@ -112,8 +121,12 @@ __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
 
+// W/src/matlabfunctions.cpp:276: (double)v / 268435456.0 - 6.0.  Both operations are exact in
+// double (v < 2^32), so is this form: the integer is placed in the mantissa of 2^52 + v and one
+// FMA removes the offset, scales by 2^-28 and subtracts 6 -- no 64-bit integer conversion.
 __device__ __forceinline__ double randn_from_u32(uint32_t v) {
-  return static_cast<double>(v) / 268435456.0 - 6.0;   // W/src/matlabfunctions.cpp:276
+  const double biased = __hiloint2double(0x43300000, static_cast<int>(v));      // 2^52 + v
+  return fma(biased, 3.7252902984619140625e-09, -(16777216.0 + 6.0));          // 2^-28, 2^52 * 2^-28 = 2^24
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -263,6 +263,23 @@ Context* ctx() {
                           cudaMemcpyHostToDevice))) {
     g_ctx_failed = true; return nullptr;
   }
+  {   // compact per-size tables: table L = every 2^(kTwLog2-L)-th entry of the master table
+    std::vector<double2> twc(Context::tw_c_offset(kTwLog2 + 1));
+    std::vector<float2> twcf(twc.size());
+    for (int L = 4; L <= kTwLog2; ++L) {
+      const size_t off = Context::tw_c_offset(L);
+      for (int k = 0; k <= (1 << (L - 1)); ++k) {
+        twc[off + k] = tw[(size_t)k << (kTwLog2 - L)];
+        twcf[off + k] = twf[(size_t)k << (kTwLog2 - L)];
+      }
+    }
+    if (!WB_CUDA(cudaMalloc((void**)&g_ctx.d_twiddle_c, twc.size() * sizeof(double2))) ||
+        !WB_CUDA(cudaMemcpy(g_ctx.d_twiddle_c, twc.data(), twc.size() * sizeof(double2), cudaMemcpyHostToDevice)) ||
+        !WB_CUDA(cudaMalloc((void**)&g_ctx.d_twiddle_cf, twcf.size() * sizeof(float2))) ||
+        !WB_CUDA(cudaMemcpy(g_ctx.d_twiddle_cf, twcf.data(), twcf.size() * sizeof(float2), cudaMemcpyHostToDevice))) {
+      g_ctx_failed = true; return nullptr;
+    }
+  }
   g_ctx_ok = true;
   return &g_ctx;
 }

@@ -35,6 +35,7 @@ struct D4CConst {
   int fs, log2nd, log2lt, nbands, window_length, sel_boundary;
   int lt_b0, lt_b1, lt_b2;
   int out_half;              // fft_size/2 of the output axis
+  int exit_after;            // EXPERIMENT: phase timing
   double threshold;
   int centers[kMaxBands];
 };
@@ -101,6 +102,7 @@ d4c_lovetrain_kernel(UttView u, const int* __restrict__ frame_utt, const double*
   const double f0 = f0_in[f];
   if (f0 == 0.0) { if (threadIdx.x == 0) ap0_out[f] = 0.0; return; }
   constexpr int LM = LOG2LT > 0 ? LOG2LT - 1 : 0;
+  constexpr int TWL = LOG2LT > 0 ? LOG2LT : kTwLog2;     // compact twiddle table of this size, or the master table
   const int log2m = LOG2LT > 0 ? LOG2LT - 1 : c.log2lt - 1;
   const int M = 1 << log2m, N = M << 1;
   double2* buf = smem2;
@@ -117,10 +119,10 @@ d4c_lovetrain_kernel(UttView u, const int* __restrict__ frame_utt, const double*
   const int W = windowed_waveform(x, u.x_len[utt], c.fs, cur_f0, frame_t[f], kBlackman, 3.0,
                                   randn_tab + rng_off[f], bufd, wslot, vslot, red);
   for (int i = W + tid; i < N; i += T) bufd[rfft_in_slot(i, log2m)] = 0.0;
-  fft_dit<LM, false, 256>(buf, log2m, tw);
+  fft_dit<LM, false, 256, 3, TWL>(buf, log2m, tw);
   double s[2] = {0.0, 0.0};
   for (int k = c.lt_b0 + 1 + tid; k <= c.lt_b2; k += T) {
-    const double2 X = rfft_bin(buf, log2m, k, tw);
+    const double2 X = rfft_bin<TWL>(buf, log2m, k, tw);
     const double p = X.x * X.x + X.y * X.y;
     if (k <= c.lt_b1) s[0] += p;
     s[1] += p;
@@ -265,6 +267,102 @@ __device__ __forceinline__ void select_low_sums(const float* __restrict__ P, int
   }
 }
 
+// The same quantity for ONE array held in the registers of ONE warp (compile-time sizes): the
+// K-th largest key is found by an MSB-first binary search on the bit pattern, each step one
+// register sweep (key >= candidate) plus a warp reduction -- no shared memory, no atomics and no
+// block barriers, so the bands of a frame are selected concurrently by different warps.  The
+// search stops as soon as exactly K keys lie at or above the candidate (then they are the top
+// set); otherwise it ends with T = the K-th largest key and the low set receives its surplus
+// copies of T.
+template <int NPL>     // keys per lane: ceil(n / 32)
+__device__ __forceinline__ void warp_select_low_sum(const float* __restrict__ P, int n, int K,
+                                                    double* low, double* tot) {
+  const int lane = threadIdx.x & 31;
+  unsigned key[NPL];
+#pragma unroll
+  for (int j = 0; j < NPL; ++j) {
+    const int k = lane + 32 * j;
+    key[j] = k < n ? __float_as_uint(P[k]) : 0u;
+  }
+  unsigned mx = 0u;
+#pragma unroll
+  for (int j = 0; j < NPL; ++j) mx = max(mx, key[j]);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  unsigned T = 0u;
+  int at_or_above = 32 * NPL;                 // keys >= T
+  for (int bit = 31 - __clz(mx | 1u); bit >= 0; --bit) {      // higher bits: no key reaches the candidate
+    const unsigned cand = T | (1u << bit);
+    int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < NPL; ++j)              // one compare and one predicated increment per key
+      asm("{.reg .pred p; setp.ge.u32 p, %1, %2; @p add.s32 %0, %0, 1;}" : "+r"(c[j & 7]) : "r"(key[j]), "r"(cand));
+    const int cnt = __reduce_add_sync(0xffffffffu, ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7])));
+    if (cnt >= K) {
+      T = cand;
+      at_or_above = cnt;
+      if (cnt == K) break;
+    }
+  }
+  double a_tot = 0.0, a_low = 0.0;
+#pragma unroll
+  for (int j = 0; j < NPL; ++j) {
+    const double v = (double)__uint_as_float(key[j]);
+    a_tot += v;
+    if (key[j] < T) a_low += v;
+  }
+  a_tot = warp_sum(a_tot);
+  a_low = warp_sum(a_low);
+  *tot = a_tot;
+  *low = a_low + (double)(at_or_above - K) * (double)__uint_as_float(T);
+}
+
+// First radix-16 pass of the band transform fused with its input: the Nuttall-windowed slice has
+// window_length <= 3 * Nd/16 non-zero samples, so of the 16 inputs x[il + r Nd/16] of a
+// first-pass group only r = 0, 1 (and r = 2 for the first few il) are non-zero and the 16-point
+// DFT collapses to  out[q] = x0 + x1 w^q + x2 w^2q,  w = exp(-2 pi i / 16).  The zero fill, the
+// bit-reversed scatter and the first pass's loads disappear; the later passes run unchanged.
+// Element .x of every point carries band a, .y band b (two real sequences per transform).
+template <int LOG2N, int THREADS>
+__device__ __forceinline__ void band_fft_pruned(float2* __restrict__ fb, const double* __restrict__ cen, int ca,
+                                                int cb, bool two, const double* __restrict__ nuttall, int wl,
+                                                const float2* __restrict__ twf) {
+  static_assert(fft_plan<LOG2N, 4>::k_of(0) == 4, "first pass must be radix-16");
+  constexpr int G = 1 << (LOG2N - 4);
+  // lane <-> il: the reads of cen are linear and the stores land on slots brev(il) + q, the same
+  // conflict-free bit-reversed scatter as a plain input permutation
+  for (int il = threadIdx.x; il < G; il += THREADS) {
+    const int g = brev(il, LOG2N - 4);
+    float2 x[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int i = il + r * G;
+      x[r] = make_float2(0.f, 0.f);
+      if (i < wl) {
+        const double w = nuttall[i];
+        x[r].x = static_cast<float>(cen[ca + i] * w);
+        if (two) x[r].y = static_cast<float>(cen[cb + i] * w);
+      }
+    }
+    float2* __restrict__ sb = fb + cpadf(g << 4);
+    const bool has2 = il + 2 * G < wl;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float2 t = rot16<false>(x[1], q);
+      float2 lo = cadd(x[0], t), hi = csub(x[0], t);
+      if (has2) {                                  // w^(2q) = w^(2(q+8)); for 2q >= 8 it is -w^(2q-8)
+        float2 u = rot16<false>(x[2], (2 * q) & 7);
+        if (2 * q >= 8) u = make_float2(-u.x, -u.y);
+        lo = cadd(lo, u);
+        hi = cadd(hi, u);
+      }
+      sb[cpadf(q)] = lo;
+      sb[cpadf(q + 8)] = hi;
+    }
+  }
+  __syncthreads();
+  fft_run_passes<LOG2N, 4, 1, false, THREADS, LOG2N>(fb, twf);
+}
+
 // dynamic shared memory: [ cen: Hd+8 | cbuf: d4c_cbuf_slots double2 | pw: Hd+8 | red: 96 |
 //                          SelectScratch | coarse: kMaxBands+2 ]
 template <int LOG2ND, int THREADS, int MAXK = 3>    // LOG2ND 0: size given at run time (c.log2nd)
@@ -278,6 +376,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
   extern __shared__ double2 smem2[];
   const int log2nd = LOG2ND > 0 ? LOG2ND : c.log2nd;
   constexpr int LMD = LOG2ND > 0 ? LOG2ND - 1 : 0;
+  constexpr int TWL = LOG2ND > 0 ? LOG2ND : kTwLog2;     // compact twiddle tables of this size, or the master tables
   const int Nd = 1 << log2nd, Hd = Nd >> 1;
   double* cen = reinterpret_cast<double*>(smem2);
   double2* cbuf = reinterpret_cast<double2*>(cen + Hd + 8);
@@ -375,7 +474,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
         cbuf[cslot(i)] = z;
       }
     }
-    fft_dit<LOG2ND, false, THREADS, MAXK>(cbuf, log2nd, tw);
+    fft_dit<LOG2ND, false, THREADS, MAXK, TWL>(cbuf, log2nd, tw);
     for (int k = tid; k <= Hd; k += T) {
       const double2 A = cbuf[cpad(k)];
       const double2 B = cbuf[cpad((Nd - k) & (Nd - 1))];
@@ -384,6 +483,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
     }
   }
   __syncthreads();
+  if (c.exit_after == 1) return;
   dc_correction(cen, cbufd, cur_f0, c.fs, Nd);        // cbuf is idle here; pw holds the staged power-spectrum window
 
   // ---- GetSmoothedPowerSpectrum (:148-164) ----------------------------------------------------
@@ -400,15 +500,17 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
                                     rn + 2 * (size_t)W4, cbufd, pwslot, pvslot, red,
                                     st_ok ? pw + (window_origin(2) - st_a0) : nullptr);
     for (int i = W + tid; i < Nd; i += T) cbufd[rfft_in_slot(i, log2m)] = 0.0;
-    fft_dit<LMD, false, THREADS, MAXK>(cbuf, log2m, tw);
+    fft_dit<LMD, false, THREADS, MAXK, TWL>(cbuf, log2m, tw);
     for (int k = tid; k <= Hd; k += T) {
-      const double2 X = rfft_bin(cbuf, log2m, k, tw);
+      const double2 X = rfft_bin<TWL>(cbuf, log2m, k, tw);
       pw[k] = X.x * X.x + X.y * X.y;
     }
     __syncthreads();
     dc_correction(pw, cbufd, cur_f0, c.fs, Nd);
+    if (c.exit_after == 2) return;
     linear_smoothing(pw, pw, cbufd, red, cur_f0, c.fs, Nd);
   }
+  if (c.exit_after == 3) return;
   // ---- GetStaticGroupDelay (:170-186) ------------------------------------------------------------
   for (int k = tid; k <= Hd; k += T) cen[k] = cen[k] / pw[k];
   __syncthreads();
@@ -416,6 +518,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
   linear_smoothing(cen, pw, cbufd, red, cur_f0, c.fs, Nd);
   for (int k = tid; k <= Hd; k += T) cen[k] -= pw[k];
   __syncthreads();
+  if (c.exit_after == 4) return;
 
   // ---- GetCoarseAperiodicity (:192-223): two bands per complex FP32 FFT, one selection for all --
   {
@@ -426,16 +529,25 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
     for (int b0 = 0; b0 < c.nbands; b0 += 2) {
       const bool two = b0 + 1 < c.nbands;
       const int ca = c.centers[b0] - hw, cb = two ? c.centers[b0 + 1] - hw : 0;
-      for (int i = tid; i < Nd; i += T) {
-        float2 z = make_float2(0.f, 0.f);
-        if (i < c.window_length) {
-          const double w = nuttall[i];
-          z.x = static_cast<float>(cen[ca + i] * w);
-          if (two) z.y = static_cast<float>(cen[cb + i] * w);
+      bool pruned = false;
+      if constexpr (LOG2ND >= 8) {
+        if (c.window_length <= 3 * (Nd >> 4)) {      // block-uniform
+          band_fft_pruned<LOG2ND, THREADS>(fb, cen, ca, cb, two, nuttall, c.window_length, twf);
+          pruned = true;
         }
-        fb[cpadf(brev(i, log2nd))] = z;
       }
-      fft_dit<LOG2ND, false, THREADS, 4>(fb, log2nd, twf);
+      if (!pruned) {
+        for (int i = tid; i < Nd; i += T) {
+          float2 z = make_float2(0.f, 0.f);
+          if (i < c.window_length) {
+            const double w = nuttall[i];
+            z.x = static_cast<float>(cen[ca + i] * w);
+            if (two) z.y = static_cast<float>(cen[cb + i] * w);
+          }
+          fb[cpadf(brev(i, log2nd))] = z;
+        }
+        fft_dit<LOG2ND, false, THREADS, 4, TWL>(fb, log2nd, twf);
+      }
       for (int k = tid; k <= Hd; k += T) {
         const float2 A = fb[cpadf(k)];
         const float2 B = fb[cpadf((Nd - k) & (Nd - 1))];
@@ -446,13 +558,24 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
       }
       __syncthreads();
     }
-    double low[kMaxSets], tot[kMaxSets];
-    select_low_sums<THREADS>(P, pstride, c.nbands, Hd + 1, c.sel_boundary + 1, reinterpret_cast<int*>(cbuf), sc, red, low, tot);
-    if (tid < c.nbands)
-      coarse[1 + tid] = fmin(0.0, 10.0 * log10(low[tid] / tot[tid]) + (cur_f0 - 100.0) / 50.0);
+    if (c.exit_after == 5) return;
+    if constexpr (LOG2ND > 0) {                    // one warp per band, keys in registers
+      constexpr int NPL = ((1 << (LOG2ND - 1)) + 1 + 31) / 32;
+      for (int b = tid >> 5; b < c.nbands; b += THREADS / 32) {
+        double low, tot;
+        warp_select_low_sum<NPL>(P + b * pstride, Hd + 1, c.sel_boundary + 1, &low, &tot);
+        if ((tid & 31) == 0) coarse[1 + b] = fmin(0.0, 10.0 * log10(low / tot) + (cur_f0 - 100.0) / 50.0);
+      }
+    } else {
+      double low[kMaxSets], tot[kMaxSets];
+      select_low_sums<THREADS>(P, pstride, c.nbands, Hd + 1, c.sel_boundary + 1, reinterpret_cast<int*>(cbuf), sc, red, low, tot);
+      if (tid < c.nbands)
+        coarse[1 + tid] = fmin(0.0, 10.0 * log10(low[tid] / tot[tid]) + (cur_f0 - 100.0) / 50.0);
+    }
   }
   if (tid == 0) { coarse[0] = -60.0; coarse[c.nbands + 1] = -kMySafeGuardMinimum; }
   __syncthreads();
+  if (c.exit_after == 6) return;
   // ---- GetAperiodicity (:325-333): interp1 over {0, 3k, ..., fs/2} then 10^(dB/20) ---------------
   const int nk = c.nbands + 2;
   const int N_out = 2 * c.out_half;
@@ -485,6 +608,7 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
   c.fs = fs;
   c.threshold = threshold;
   c.out_half = fft_size / 2;
+  c.exit_after = getenv("WB_D4C_EXIT") ? atoi(getenv("WB_D4C_EXIT")) : 0;
   const int nd = static_cast<int>(pow(2.0, 1.0 + static_cast<int>(log(4.0 * fs / kFloorF0D4C + 1) / kLog2)));  // d4c.cpp:344-346
   const int nlt = static_cast<int>(pow(2.0, 1.0 + static_cast<int>(log(3.0 * fs / 40.0 + 1) / kLog2)));        // :261-262
   c.log2nd = 0; while ((1 << c.log2nd) < nd) ++c.log2nd;
@@ -538,7 +662,7 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
 #define WB_LT_LAUNCH(L)                                                                                             \
   do {                                                                                                              \
     WB_CUDA_OR_RETURN(cudaFuncSetAttribute(d4c_lovetrain_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
-    d4c_lovetrain_kernel<L><<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0, offs_lt.p, ctxp->d_randn, ctxp->d_twiddle, c, d_ap0.p); \
+    d4c_lovetrain_kernel<L><<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0, offs_lt.p, ctxp->d_randn, L > 0 ? ctxp->tw_c(L > 0 ? L : 4) : ctxp->d_twiddle, c, d_ap0.p); \
   } while (0)
     switch (c.log2lt) {
       case 11: WB_LT_LAUNCH(11); break;
@@ -565,7 +689,7 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
   do {                                                                                                              \
     WB_CUDA_OR_RETURN(cudaFuncSetAttribute(d4c_main_kernel<L, TH, ##__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
     d4c_main_kernel<L, TH, ##__VA_ARGS__><<<total_frames, TH, smem, st>>>(u, frame_utt, frame_t, f0, d_ap0.p, offs_main.p, tot_lt.p, ctxp->d_randn, \
-                                                           ctxp->d_twiddle, ctxp->d_twiddle_f, d_win.p, c, ap);                         \
+                                                           L > 0 ? ctxp->tw_c(L > 0 ? L : 4) : ctxp->d_twiddle, L > 0 ? ctxp->tw_cf(L > 0 ? L : 4) : ctxp->d_twiddle_f, d_win.p, c, ap);                         \
   } while (0)
     if (threads == 512) WB_D4C_LAUNCH(0, 512);
     else if (c.log2nd == 12) WB_D4C_LAUNCH(12, 256, 4);      // radix-16 passes: 3 instead of 4 round trips

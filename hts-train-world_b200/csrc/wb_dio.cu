@@ -345,7 +345,7 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
     KernelTimer kt1("dio_filter_kernel");
     if (c.log2bn == 13)
       ols_filter_kernel<13><<<dim3(n_blocks, nu), 256, smem, st>>>(xin, xin_off, xin_len, d_ylen.p, d_mask.p, d_mean.p,
-                                                            d_foff.p, fb->G.p, ctxp->d_twiddle, oc, d_shift.p, u0, d_F.p);
+                                                            d_foff.p, fb->G.p, ctxp->tw_c(13), oc, d_shift.p, u0, d_F.p);
     else
       ols_filter_kernel<0><<<dim3(n_blocks, nu), 256, smem, st>>>(xin, xin_off, xin_len, d_ylen.p, d_mask.p, d_mean.p,
                                                             d_foff.p, fb->G.p, ctxp->d_twiddle, oc, d_shift.p, u0, d_F.p);

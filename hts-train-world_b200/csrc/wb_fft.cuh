@@ -84,7 +84,7 @@ __device__ __forceinline__ C rot16(C v, int e16) {
 //
 // cpad() is additive over non-overlapping bit fields: the group base has zeros where
 // (m << STAGE) lives, hence cpad(base + (m << STAGE)) = cpad(base) + cpad(m << STAGE).
-template <int K, bool INV, int LOG2N, int STAGE, int THREADS, typename C>
+template <int K, bool INV, int LOG2N, int STAGE, int THREADS, int TWL = kTwLog2, typename C>
 __device__ __forceinline__ void fft_pass(C* __restrict__ s, const C* __restrict__ tw) {
   constexpr int R = 1 << K;
   constexpr bool FIRST = STAGE == 0;
@@ -104,7 +104,7 @@ __device__ __forceinline__ void fft_pass(C* __restrict__ s, const C* __restrict_
     if (!FIRST) {
 #pragma unroll
       for (int t = 0; t < K; ++t) {
-        w[t] = __ldg(&tw[j << (kTwLog2 - STAGE - t - 1)]);
+        w[t] = __ldg(&tw[j << (TWL - STAGE - t - 1)]);
         if (INV) w[t].y = -w[t].y;
       }
     }
@@ -135,23 +135,23 @@ template <int LOG2N, int MAXK> struct fft_plan {
   __host__ __device__ static constexpr int stage_of(int p) { return p * base + (p < extra ? p : extra); }
 };
 
-template <int LOG2N, int MAXK, int PASS, bool INV, int THREADS, typename C>
+template <int LOG2N, int MAXK, int PASS, bool INV, int THREADS, int TWL = kTwLog2, typename C>
 __device__ __forceinline__ void fft_run_passes(C* s, const C* __restrict__ tw) {
   using plan = fft_plan<LOG2N, MAXK>;
   if constexpr (PASS < plan::P) {
-    fft_pass<plan::k_of(PASS), INV, LOG2N, plan::stage_of(PASS), THREADS>(s, tw);
+    fft_pass<plan::k_of(PASS), INV, LOG2N, plan::stage_of(PASS), THREADS, TWL>(s, tw);
     __syncthreads();
-    fft_run_passes<LOG2N, MAXK, PASS + 1, INV, THREADS>(s, tw);
+    fft_run_passes<LOG2N, MAXK, PASS + 1, INV, THREADS, TWL>(s, tw);
   }
 }
 
 // In-place complex FFT of 2^LOG2N points held in shared memory at padded slots.
 // Input: element c stored at slot brev(c, LOG2N).  Output: slot k = X[k].
 // Starts and ends with __syncthreads().
-template <int LOG2N, bool INV, int THREADS, int MAXK, typename C>
+template <int LOG2N, bool INV, int THREADS, int MAXK, int TWL = kTwLog2, typename C>
 __device__ __forceinline__ void fft_dit_fixed(C* s, const C* __restrict__ tw) {
   __syncthreads();
-  fft_run_passes<LOG2N, MAXK, 0, INV, THREADS>(s, tw);
+  fft_run_passes<LOG2N, MAXK, 0, INV, THREADS, TWL>(s, tw);
 }
 
 // Size chosen at run time (block-uniform): sizes 2^3 .. 2^13.
@@ -173,17 +173,18 @@ __device__ __noinline__ void fft_dit_rt(C* s, int log2n, const C* __restrict__ t
   }
 }
 
-// LOG2N > 0: compile-time size; LOG2N == 0: the run-time value log2n_rt.
-template <int LOG2N, bool INV, int THREADS, int MAXK = 3, typename C>
+// LOG2N > 0: compile-time size; LOG2N == 0: the run-time value log2n_rt (master table only).
+// TWL: `tw` holds exp(-2 pi i k / 2^TWL) -- the master table (kTwLog2) or a compact one.
+template <int LOG2N, bool INV, int THREADS, int MAXK = 3, int TWL = kTwLog2, typename C>
 __device__ __forceinline__ void fft_dit(C* s, int log2n_rt, const C* __restrict__ tw) {
-  if constexpr (LOG2N > 0) fft_dit_fixed<LOG2N, INV, THREADS, MAXK>(s, tw);
-  else fft_dit_rt<INV, THREADS, MAXK>(s, log2n_rt, tw);
+  if constexpr (LOG2N > 0) fft_dit_fixed<LOG2N, INV, THREADS, MAXK, TWL>(s, tw);
+  else { static_assert(LOG2N > 0 || TWL == kTwLog2, "run-time sizes use the master table"); fft_dit_rt<INV, THREADS, MAXK>(s, log2n_rt, tw); }
 }
 
 // ---- real transforms on top of a half-size complex FFT -----------------------------------
 // Forward: pack x[2n] + i x[2n+1] into element n (slot brev(n)), run fft_dit<false> with
 // log2m = log2(N) - 1, then rfft_bin(k) returns X[k] for k in [0, N/2].
-template <typename C>
+template <int TWL = kTwLog2, typename C>
 __device__ __forceinline__ C rfft_bin(const C* s, int log2m, int k, const C* __restrict__ tw) {
   using R = scalar_t<C>;
   const int M = 1 << log2m;
@@ -196,7 +197,7 @@ __device__ __forceinline__ C rfft_bin(const C* s, int log2m, int k, const C* __r
   const R h = static_cast<R>(0.5);
   const C E = mk2(h * (A.x + B.x), h * (A.y + B.y));
   const C O = mk2(h * (A.x - B.x), h * (A.y - B.y));
-  const C w = __ldg(&tw[k << (kTwLog2 - log2m - 1)]);
+  const C w = __ldg(&tw[k << (TWL - log2m - 1)]);
   const C t = cmul(w, O);
   return mk2(E.x + t.y, E.y - t.x);     // E - i w O
 }
@@ -215,14 +216,14 @@ __device__ __forceinline__ int rfft_out_slot_f(int i) { return 2 * cpadf(i >> 1)
 
 // Inverse (c2r): for k in [0, N/2) compute the packed element from X[k] and X[N/2 - k]
 // and store it at slot brev(k); then fft_dit<true>; real sample i is at rfft_out_slot(i).
-template <typename C>
+template <int TWL = kTwLog2, typename C>
 __device__ __forceinline__ C c2r_pack(C Xk, C XMk, int k, int log2m, const C* __restrict__ tw) {
   if (k == 0)   // Xk = X[0], XMk = X[N/2]; imaginary parts ignored like W/src/fft.cpp:27-29
     return mk2(Xk.x + XMk.x, Xk.x - XMk.x);
   const C B = cconj(XMk);
   const C S = cadd(Xk, B);
   const C D = csub(Xk, B);
-  C w = __ldg(&tw[k << (kTwLog2 - log2m - 1)]);
+  C w = __ldg(&tw[k << (TWL - log2m - 1)]);
   w.y = -w.y;                                     // w^{-k}
   const C t = cmul(w, D);
   return mk2(S.x - t.y, S.y + t.x);      // S + i w^{-k} D

@@ -843,7 +843,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
       // the decimated signals play the role of Dio's x: offsets d_yoff, length = y_len for both "x" and "y"
       if (hb->log2bn == 11)
         ols_filter_kernel<11><<<dim3(n_blocks, nu), 256, smem, st>>>(d_y.p, d_yoff.p, d_ylen.p, d_ylen.p, d_mask.p, d_mean.p, d_foff.p,
-                                                                    hb->G.p, ctxp->d_twiddle, oc, hb->shift.p, u0, d_F.p);
+                                                                    hb->G.p, ctxp->tw_c(11), oc, hb->shift.p, u0, d_F.p);
       else
         ols_filter_kernel<0><<<dim3(n_blocks, nu), 256, smem, st>>>(d_y.p, d_yoff.p, d_ylen.p, d_ylen.p, d_mask.p, d_mean.p, d_foff.p,
                                                                    hb->G.p, ctxp->d_twiddle, oc, hb->shift.p, u0, d_F.p);

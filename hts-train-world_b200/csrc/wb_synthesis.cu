@@ -353,6 +353,7 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
                   const uint32_t* __restrict__ randn_tab, const C* __restrict__ tw,
                   const double* __restrict__ dc_remover, SynthConst c, double* __restrict__ y_all) {
   using R = scalar_t<C>;
+  constexpr int TWL = LOG2N > 0 ? LOG2N : kTwLog2;       // compact twiddle table of this size, or the master table
   extern __shared__ double2 smem2[];
   const int log2n = LOG2N > 0 ? LOG2N : c.log2n;
   const int N = 1 << log2n, half = N >> 1;
@@ -401,7 +402,7 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
       nzb[cpadT<C>(brev(i, log2n))] = mk2(n0, n1);
     }
   }
-  fft_dit<LOG2N, false, T, 4>(nzb, log2n, tw);       // C
+  fft_dit<LOG2N, false, T, 4, TWL>(nzb, log2n, tw);       // C
   // ---- log spectra (:45-51, :115-117), written as the even extension in bit-reversed order ----
   for (int k = tid; k <= half; k += T) {
     R l0 = 0, l1 = 0;
@@ -421,7 +422,7 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
     cbuf[cpadT<C>(brev(k, log2n))] = z;
     if (k > 0 && k < half) cbuf[cpadT<C>(brev(N - k, log2n))] = z;
   }
-  fft_dit<LOG2N, false, T, 4>(cbuf, log2n, tw);      // A
+  fft_dit<LOG2N, false, T, 4, TWL>(cbuf, log2n, tw);      // A
   // ---- fold the cepstra (common.cpp:194-206) -----------------------------------------------------
   {
     C keep[kQ];
@@ -443,7 +444,7 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
     }
     for (int i = half + 1 + tid; i < N; i += T) cbuf[cpadT<C>(brev(i, log2n))] = mk2(static_cast<R>(0), static_cast<R>(0));
   }
-  fft_dit<LOG2N, false, T, 4>(cbuf, log2n, tw);      // B
+  fft_dit<LOG2N, false, T, 4, TWL>(cbuf, log2n, tw);      // B
   // ---- minimum-phase spectra, time shift / noise product (:56-65, :88-100, :120-131) ------------
   {
     const double coefficient = per_item
@@ -490,7 +491,7 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
       if (k > 0 && k < half) cbuf[cpadT<C>(brev(N - k, log2n))] = mk2(a.x + b.y, b.x - a.y);
     }
   }
-  fft_dit<LOG2N, true, T, 4>(cbuf, log2n, tw);       // D
+  fft_dit<LOG2N, true, T, 4, TWL>(cbuf, log2n, tw);       // D
   // ---- fftshift, RemoveDCComponent (:73-82), mix (:214-217), overlap-add (:376-383) -------------
   if (per_item) {
     double dc[1] = {0.0};
@@ -614,14 +615,14 @@ bool synthesis_run(Batch* b, const int* y_len) {
   } while (0)
   if (fp64) {
     switch (log2n) {
-      case 11: WB_SP_LAUNCH(11, double2, ctxp->d_twiddle); break;
+      case 11: WB_SP_LAUNCH(11, double2, ctxp->tw_c(11)); break;
       default: WB_SP_LAUNCH(0, double2, ctxp->d_twiddle); break;
     }
   } else {
     switch (log2n) {
-      case 10: WB_SP_LAUNCH(10, float2, ctxp->d_twiddle_f); break;
-      case 11: WB_SP_LAUNCH(11, float2, ctxp->d_twiddle_f); break;
-      case 12: WB_SP_LAUNCH(12, float2, ctxp->d_twiddle_f); break;
+      case 10: WB_SP_LAUNCH(10, float2, ctxp->tw_cf(10)); break;
+      case 11: WB_SP_LAUNCH(11, float2, ctxp->tw_cf(11)); break;
+      case 12: WB_SP_LAUNCH(12, float2, ctxp->tw_cf(12)); break;
       default: WB_SP_LAUNCH(0, float2, ctxp->d_twiddle_f); break;
     }
   }

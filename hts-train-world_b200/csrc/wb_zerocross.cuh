@@ -184,6 +184,7 @@ ols_filter_kernel(const double* __restrict__ x_all, const long long* __restrict_
   const int n0 = blockIdx.x * c.V;
   if (n0 >= y_len) return;
   constexpr int LM = LOG2BN > 0 ? LOG2BN - 1 : 0;
+  constexpr int TWL = LOG2BN > 0 ? LOG2BN : kTwLog2;     // compact twiddle table of this size, or the master table
   const int log2m = LOG2BN > 0 ? LOG2BN - 1 : c.log2bn - 1, M = 1 << log2m;
   double2* xs = smem2;
   double2* ws = smem2 + cpad_size(M);
@@ -201,15 +202,15 @@ ols_filter_kernel(const double* __restrict__ x_all, const long long* __restrict_
     if (m < y_len) v = (m < xl ? x[m] : 0.0) - mean;
     xsd[rfft_in_slot(i, log2m)] = v;
   }
-  fft_dit<LM, false, 256, 4>(xs, log2m, tw);
+  fft_dit<LM, false, 256, 4, TWL>(xs, log2m, tw);
   // half spectrum in place: slot k = X[k] (k < M), slot 0 = (X[0], X[M])
   for (int k = tid; k <= M / 2; k += T) {
     if (k == 0) {
       const double2 z0 = xs[0];
       xs[0] = make_double2(z0.x + z0.y, z0.x - z0.y);
     } else {
-      const double2 a = rfft_bin(xs, log2m, k, tw);
-      const double2 b = rfft_bin(xs, log2m, M - k, tw);
+      const double2 a = rfft_bin<TWL>(xs, log2m, k, tw);
+      const double2 b = rfft_bin<TWL>(xs, log2m, M - k, tw);
       xs[cpad(k)] = a;
       xs[cpad(M - k)] = b;
     }
@@ -223,15 +224,15 @@ ols_filter_kernel(const double* __restrict__ x_all, const long long* __restrict_
       if (k == 0) {
         const double2 x0 = xs[0];
         const double2 y0 = make_double2(x0.x * Gb[0].x, 0.0), yM = make_double2(x0.y * Gb[M].x, 0.0);
-        ws[cpad(brev(0, log2m))] = c2r_pack(y0, yM, 0, log2m, tw);
+        ws[cpad(brev(0, log2m))] = c2r_pack<TWL>(y0, yM, 0, log2m, tw);
       } else {
         const double2 yk = cmul(xs[cpad(k)], Gb[k]);
         const double2 ym = cmul(xs[cpad(M - k)], Gb[M - k]);
-        ws[cpad(brev(k, log2m))] = c2r_pack(yk, ym, k, log2m, tw);
-        if (k != M - k) ws[cpad(brev(M - k, log2m))] = c2r_pack(ym, yk, M - k, log2m, tw);
+        ws[cpad(brev(k, log2m))] = c2r_pack<TWL>(yk, ym, k, log2m, tw);
+        if (k != M - k) ws[cpad(brev(M - k, log2m))] = c2r_pack<TWL>(ym, yk, M - k, log2m, tw);
       }
     }
-    fft_dit<LM, true, 256, 4>(ws, log2m, tw);
+    fft_dit<LM, true, 256, 4, TWL>(ws, log2m, tw);
     const int shift = shift_all[b];                    // filtered_b[n] = conv[n - n0 + shift]
     double* __restrict__ dst = Fu + (size_t)b * y_len + n0;
     for (int i = tid; i < n_out; i += T) dst[i] = wsd[rfft_out_slot(i + shift)];

@@ -114,6 +114,35 @@ WORLD_API int wb200_batch_decode_mgc(wb200_batch *b, int fft_size, int mgc_dim, 
  * of voiced lf0 (row 0) and of every mgc dimension over all frames (rows 1..mgc_dim); the NCCL
  * all-reduce of these rows gives the corpus mean / variance */
 WORLD_API int wb200_batch_feature_stats(wb200_batch *b, double *out);
+/* ---- training observation vectors (data/Makefile.in:276-321, the `cmp` target) ----------------
+ * Every stream (mgc, lf0, bap, and any stream computed on the host such as the two-dimensional
+ * lf0 and vib of data/scripts/Extract.py) is extended by its delta windows exactly as
+ * data/scripts/window.pl does (double accumulation, frames clamped to the utterance, -1.0e10 as
+ * the ignore value) and written side by side, in the order given, into one float32 matrix
+ * [total_frames][cmp_dim] — the `merge` chain of the Makefile.  Window files data/win/*.win[123]
+ * hold "size c1 c2 ... csize"; pass those numbers in win_size / win_coef. */
+#define WB200_CMP_MAX_STREAMS 8
+#define WB200_CMP_MAX_WINDOWS 4
+#define WB200_CMP_MAX_WIN_SIZE 15
+enum { WB200_CMP_SRC_HOST = 0, WB200_CMP_SRC_MGC = 1, WB200_CMP_SRC_LF0 = 2, WB200_CMP_SRC_BAP = 3 };
+typedef struct {
+  int source;                 /* WB200_CMP_SRC_*: host_data, or the batch's own coded features */
+  int dim;                    /* static dimensionality (ignored for the batch's own features) */
+  const float *host_data;     /* [total_frames][dim] statics, utterances back to back (SRC_HOST) */
+  int n_win;                  /* NMGCWIN / NLF0WIN / NBAPWIN / NVIBWIN */
+  int win_size[WB200_CMP_MAX_WINDOWS];
+  double win_coef[WB200_CMP_MAX_WINDOWS][WB200_CMP_MAX_WIN_SIZE];
+} wb200_cmp_stream;
+WORLD_API int wb200_batch_compose_cmp(wb200_batch *b, const wb200_cmp_stream *streams, int n_streams);
+WORLD_API int wb200_batch_cmp_dim(const wb200_batch *b);           /* floats per frame */
+WORLD_API int wb200_batch_get_cmp(wb200_batch *b, float *host_cmp); /* [total_frames][cmp_dim] */
+/* per-GPU partials {count, sum, sum of squares} of every cmp column: out[cmp_dim][3] */
+WORLD_API int wb200_batch_cmp_stats(wb200_batch *b, double *out);
+/* the 12-byte HTK header of data/scripts/addhtkheader.pl: int32 nframe, int32 frame shift in
+ * 100 ns units (10000000 * frame_shift / samp_freq, truncated), int16 bytes per frame, int16
+ * parameter kind (9 = USER), native byte order */
+WORLD_API int wb200_htk_header(int n_frames, int samp_freq, int frame_shift, int byte_per_frame,
+                               int kind, unsigned char *out12);
 /* block until everything queued on the library stream has finished */
 WORLD_API int wb200_sync(void);
 
