@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include "wb_batch.h"
 #include "wb_fft.cuh"
+#include "wb_spectral.cuh"
 
 namespace wb {
 
@@ -139,15 +140,17 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
   // ---- LinearSmoothing (common.cpp:77-111), width = f0 * 2 / 3 ------------------------------
   const double width = f0c * 2.0 / 3.0;
   const int len = half + 2 * boundary + 1;
-  for (int i = tid; i < len; i += T) {
-    double v;
-    if (i < boundary) v = aux[boundary - i];
-    else if (i < half + boundary) v = aux[i - boundary];
-    else v = aux[half - (i - (half + boundary))];
-    bufd[i] = mul_rn(v, (double)fs) * inv_n;
+  if (!mirrored_cumsum<9>(aux, bufd, red, half, boundary, fs, inv_n)) {
+    for (int i = tid; i < len; i += T) {
+      double v;
+      if (i < boundary) v = aux[boundary - i];
+      else if (i < half + boundary) v = aux[i - boundary];
+      else v = aux[half - (i - (half + boundary))];
+      bufd[i] = mul_rn(v, (double)fs) * inv_n;
+    }
+    __syncthreads();
+    block_inclusive_scan(bufd, len, red);
   }
-  __syncthreads();
-  block_inclusive_scan(bufd, len, red);
   {
     const double origin_axis = -(boundary - 0.5) * fs / N;
     const double inv_width = 1.0 / width;

@@ -58,7 +58,7 @@ struct Context {
   // small L1 that is left beside 220 KB of shared memory).  L = 4 .. kTwLog2.
   double2* d_twiddle_c = nullptr;
   float2* d_twiddle_cf = nullptr;
-  static size_t tw_c_offset(int L) { return ((size_t)1 << (L - 1)) + 2 * (size_t)L; }   // entries before table L
+  __host__ __device__ static size_t tw_c_offset(int L) { return ((size_t)1 << (L - 1)) + 2 * (size_t)L; }   // entries before table L
   const double2* tw_c(int L) const { return d_twiddle_c + tw_c_offset(L); }
   const float2* tw_cf(int L) const { return d_twiddle_cf + tw_c_offset(L); }
   uint32_t* d_randn = nullptr;           // randn table: variate k = d_randn[k] / 2^28 - 6

@@ -173,6 +173,19 @@ __device__ __noinline__ void fft_dit_rt(C* s, int log2n, const C* __restrict__ t
   }
 }
 
+// Run-time size with the compact tables: `tw_c_base` is the start of the concatenated per-size
+// tables (Context::d_twiddle_c / d_twiddle_cf); every case picks its own table.
+template <bool INV, int THREADS, int MAXK, typename C>
+__device__ __noinline__ void fft_dit_rt_compact(C* s, int log2n, const C* __restrict__ tw_c_base) {
+#define WB_FFT_CASE(L) case L: fft_dit_fixed<L, INV, THREADS, MAXK, L>(s, tw_c_base + Context::tw_c_offset(L)); break;
+  switch (log2n) {
+    WB_FFT_CASE(4) WB_FFT_CASE(5) WB_FFT_CASE(6) WB_FFT_CASE(7) WB_FFT_CASE(8) WB_FFT_CASE(9)
+    WB_FFT_CASE(10) WB_FFT_CASE(11) WB_FFT_CASE(12) WB_FFT_CASE(13)
+    default: break;
+  }
+#undef WB_FFT_CASE
+}
+
 // LOG2N > 0: compile-time size; LOG2N == 0: the run-time value log2n_rt (master table only).
 // TWL: `tw` holds exp(-2 pi i k / 2^TWL) -- the master table (kTwLog2) or a compact one.
 template <int LOG2N, bool INV, int THREADS, int MAXK = 3, int TWL = kTwLog2, typename C>

@@ -23,26 +23,76 @@ __device__ __forceinline__ int smoothing_boundary(double width, int fs, int N) {
   return static_cast<int>(mul_rn(width, (double)N) / fs) + 1;
 }
 
+// cum[0..len) = running sum of the mirrored, df-scaled spectrum (LinearSmoothing :86-97):
+// element i of the mirrored axis is in[boundary - i], in[i - boundary] or in[half - (i - (half +
+// boundary))].  Every thread gathers its contiguous chunk (<= PER elements) straight from `in`
+// into registers, sums it there, the chunk totals are scanned with warp shuffles and the
+// finished values are stored once -- no mirrored copy and no second read-modify-write pass.
+// Returns false (nothing written) when len > blockDim.x * PER; the caller then takes the generic
+// path.  `in` must be complete on entry; ends with __syncthreads().
+template <int PER>
+__device__ __forceinline__ bool mirrored_cumsum(const double* in, double* cum, double* red, int half,
+                                                int boundary, int fs, double inv_n) {
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int len = half + 2 * boundary + 1;
+  const int per = (len + T - 1) / T;
+  if (per > PER) return false;
+  const int lo = tid * per;
+  double v[PER];
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = lo + j;
+    if (j < per && i < len) {
+      const int src = i < boundary ? boundary - i : i < half + boundary ? i - boundary : half - (i - (half + boundary));
+      s += mul_rn(in[src], (double)fs) * inv_n;
+    }
+    v[j] = s;
+  }
+  const int lane = tid & 31, wid = tid >> 5;
+  double inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();                       // `red` may still be read by an earlier reduction
+  if (lane == 31) red[wid] = inc;
+  __syncthreads();
+  double offset = inc - s;               // exclusive within the warp
+  for (int w = 0; w < wid; ++w) offset += red[w];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = lo + j;
+    if (j < per && i < len) cum[i] = v[j] + offset;
+  }
+  __syncthreads();
+  return true;
+}
+
 // Rectangular smoothing of in[0..N/2] with the given width (Hz) -> out[0..N/2]; out may
 // alias in.  cum: scratch of >= N/2 + 2*boundary + 1 doubles; red: >= 33 doubles.
 // Must be entered by all threads with `in` complete (caller syncs); ends with __syncthreads().
-__device__ __forceinline__ void linear_smoothing(const double* in, double* out, double* cum,
-                                                 double* red, double width, int fs, int N) {
+// Not inlined: D4C calls it three times per frame and the kernels are instruction-cache bound.
+static __device__ __noinline__ void linear_smoothing(const double* in, double* out, double* cum,
+                                              double* red, double width, int fs, int N) {
   const int T = blockDim.x, tid = threadIdx.x;
   const int half = N / 2;
   const int boundary = smoothing_boundary(width, fs, N);
   const int len = half + 2 * boundary + 1;
   const double inv_df = (double)N / fs;
   const double inv_n = 1.0 / N;                 // N is a power of two: x * inv_n == x / N exactly
-  for (int i = tid; i < len; i += T) {
-    double v;
-    if (i < boundary) v = in[boundary - i];
-    else if (i < half + boundary) v = in[i - boundary];
-    else v = in[half - (i - (half + boundary))];
-    cum[i] = mul_rn(v, (double)fs) * inv_n;
+  if (!mirrored_cumsum<9>(in, cum, red, half, boundary, fs, inv_n)) {
+    for (int i = tid; i < len; i += T) {
+      double v;
+      if (i < boundary) v = in[boundary - i];
+      else if (i < half + boundary) v = in[i - boundary];
+      else v = in[half - (i - (half + boundary))];
+      cum[i] = mul_rn(v, (double)fs) * inv_n;
+    }
+    __syncthreads();
+    block_inclusive_scan(cum, len, red);
   }
-  __syncthreads();
-  block_inclusive_scan(cum, len, red);
   const double origin_axis = -(boundary - 0.5) * fs / N;
   const double inv_width = 1.0 / width;
   for (int k = tid; k <= half; k += T) {

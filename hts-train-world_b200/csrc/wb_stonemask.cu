@@ -70,7 +70,7 @@ __device__ double stonemask_fix_f0(const float2* cbuf, int nfft, int fs, double 
   return numerator / (denominator + kMySafeGuardMinimum);
 }
 
-// dynamic shared memory: [ cbuf: cpad_size(max fft) float2 | win: max_fft/2 + 8 doubles ]
+// dynamic shared memory: [ cbuf: cpad_size(max fft) float2 | win: max_fft/2 + 8 doubles | idx: max_fft/2 ints ]
 __global__ void __launch_bounds__(256)
 stonemask_kernel(UttView u, const int* __restrict__ frame_utt, const double* __restrict__ frame_t,
                  const double* __restrict__ f0_in, const float2* __restrict__ tw, int fs,
@@ -91,12 +91,18 @@ stonemask_kernel(UttView u, const int* __restrict__ frame_utt, const double* __r
   const int log2fft = stonemask_log2fft(hwl);
   const int nfft = 1 << log2fft;
   const double wlen = div_rn(add_rn(mul_rn(2.0, (double)hwl), 1.0), (double)fs);   // :189
-  // GetBaseIndex + GetMainWindow
+  // GetBaseIndex + GetMainWindow.  index_raw decides which sample is read, so it is formed with the
+  // reference's own roundings (one exact division per sample) and kept for the second pass; the
+  // argument of the cosine only shapes the window, there the two divisions become multiplications
+  // by reciprocals (the window moves by ~1e-14 relative).
+  int* idx_s = reinterpret_cast<int*>(win + (1 << max_log2fft) / 2 + 8);
+  const double inv_fs = 1.0 / fs, two_pi_over_wlen = 2.0 * kPi / wlen;
   for (int i = tid; i < W; i += T) {
     const double base_time = div_rn((double)(i - hwl), (double)fs);
     const int index_raw = matlab_round(mul_rn(add_rn(t_pos, base_time), (double)fs));
-    const double tmp = add_rn(div_rn(index_raw - 1.0, (double)fs), -t_pos);
-    const double cs = cos(div_rn(mul_rn(2.0 * kPi, tmp), wlen));
+    idx_s[i] = max(0, min(x_len - 1, index_raw - 1));
+    const double tmp = (index_raw - 1.0) * inv_fs - t_pos;
+    const double cs = cos(tmp * two_pi_over_wlen);
     win[i] = 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);        // cos(2a) = 2 cos^2(a) - 1
   }
   __syncthreads();
@@ -104,10 +110,7 @@ stonemask_kernel(UttView u, const int* __restrict__ frame_utt, const double* __r
   for (int i = tid; i < nfft; i += T) {
     float2 z = make_float2(0.f, 0.f);
     if (i < W) {
-      const double base_time = div_rn((double)(i - hwl), (double)fs);
-      const int index_raw = matlab_round(mul_rn(add_rn(t_pos, base_time), (double)fs));
-      const int idx = max(0, min(x_len - 1, index_raw - 1));
-      const double xv = x[idx];
+      const double xv = x[idx_s[i]];
       double dw;
       if (i == 0) dw = -win[1] / 2.0;
       else if (i == W - 1) dw = win[W - 2] / 2.0;
@@ -116,7 +119,7 @@ stonemask_kernel(UttView u, const int* __restrict__ frame_utt, const double* __r
     }
     cbuf[cpadf(brev(i, log2fft))] = z;
   }
-  fft_dit<0, false, 256, 4>(cbuf, log2fft, tw);
+  fft_dit_rt_compact<false, 256, 4>(cbuf, log2fft, tw);      // tw: base of the compact FP32 tables
   if (tid == 0) {
     // GetTentativeF0 (:122-131) and the 20 % sanity check of GetRefinedF0 (:203-204)
     double mean_f0 = 0.0;
@@ -145,11 +148,11 @@ bool stonemask_run(const UttView& u, int fs, int total_frames, const int* frame_
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
   if (h_max < 3) h_max = 3;
   if (h_max > 13) { set_error("StoneMask: FFT size 2^%d not supported", h_max); return false; }
-  const size_t smem = ((cpad_size(1 << h_max) + 1) & ~1) * sizeof(float2) + ((size_t)(1 << h_max) / 2 + 8) * sizeof(double);
+  const size_t smem = ((cpad_size(1 << h_max) + 1) & ~1) * sizeof(float2) + ((size_t)(1 << h_max) / 2 + 8) * sizeof(double) + ((size_t)(1 << h_max) / 2) * sizeof(int);
   if (smem > c->smem_optin) { set_error("StoneMask: needs %zu bytes of shared memory", smem); return false; }
   WB_CUDA_OR_RETURN(cudaFuncSetAttribute(stonemask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
   KernelTimer kt1("stonemask_kernel");
-  stonemask_kernel<<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0_in, c->d_twiddle_f, fs, h_max, f0_out);
+  stonemask_kernel<<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0_in, c->d_twiddle_cf, fs, h_max, f0_out);
   WB_LAUNCH_CHECK(); kt1.stop();
   return true;
 }
