@@ -145,6 +145,7 @@ def lib():
         "wb200_batch_get_sp": (i32, [vp, vp]),
         "wb200_batch_get_ap": (i32, [vp, vp]),
         "wb200_batch_set_sp_ap": (i32, [vp, i32, _dp, _dp]),
+        "wb200_batch_set_params_f32": (i32, [vp, i32, vp, vp, vp]),
         "wb200_batch_total_y": (i64, [vp]),
         "wb200_batch_y_layout": (i32, [vp, C.POINTER(i64), _ip]),
         "wb200_batch_get_y": (i32, [vp, vp]),
@@ -454,6 +455,15 @@ class Corpus:
         sp, ap = (np.ascontiguousarray(a, np.float64) for a in (sp, ap))
         self.fft_size = int(fft_size)
         _check(lib().wb200_batch_set_sp_ap(self._h, self.fft_size, _ptr(sp), _ptr(ap)), "set_sp_ap")
+
+    def set_params_f32(self, fft_size, f0, sp, ap):
+        """float32 f0 / sp / ap as the synth tool reads them (W/test/synth.cpp:160-190); numpy arrays or
+        pinned torch tensors."""
+        self.fft_size = int(fft_size)
+        ptr = lambda a: None if a is None else (a.data_ptr() if hasattr(a, "data_ptr") else np.ascontiguousarray(a, np.float32).ctypes.data)
+        keep = [None if a is None or hasattr(a, "data_ptr") else np.ascontiguousarray(a, np.float32) for a in (f0, sp, ap)]
+        ptrs = [ptr(k if k is not None else a) for k, a in zip(keep, (f0, sp, ap))]
+        _check(lib().wb200_batch_set_params_f32(self._h, self.fft_size, *ptrs), "set_params_f32")
 
     def y_layout(self):
         off = np.zeros(self.n_utt, np.int64)

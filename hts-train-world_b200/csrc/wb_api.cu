@@ -536,6 +536,31 @@ int wb200_batch_set_sp_ap(wb200_batch* h, int fft_size, const double* sp, const 
   if (!b.sp.alloc(n) || !b.ap.alloc(n)) return 1;
   return h2d(b.sp.p, sp, n * sizeof(double)) || h2d(b.ap.p, ap, n * sizeof(double));
 }
+__global__ void widen_f32_kernel(const float* __restrict__ in, long long n, double* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (double)in[i];                                              // ToDouble, W/test/synth.cpp:66-70
+}
+int wb200_batch_set_params_f32(wb200_batch* h, int fft_size, const float* f0, const float* sp, const float* ap) {
+  Context* c = ctx();
+  if (!c) return 1;
+  Batch& b = h->b;
+  if (fft_size < 32 || (fft_size & (fft_size - 1))) { set_error("set_params_f32: fft_size %d", fft_size); return 1; }
+  b.fft_size = fft_size;
+  const size_t F = (size_t)b.total_frames, n = F * (fft_size / 2 + 1);
+  DevBuf<float> stage;
+  if (!b.sp.alloc(n) || !b.ap.alloc(n) || !stage.alloc(n + 1)) return 1;
+  if (F == 0) return 0;
+  const float* src[3] = {f0, sp, ap};
+  double* dst[3] = {b.f0.p, b.sp.p, b.ap.p};
+  const size_t cnt[3] = {F, n, n};
+  for (int k = 0; k < 3; ++k) {
+    if (!src[k]) continue;
+    if (!WB_CUDA(cudaMemcpyAsync(stage.p, src[k], cnt[k] * sizeof(float), cudaMemcpyHostToDevice, c->stream))) return 1;
+    widen_f32_kernel<<<148 * 8, 256, 0, c->stream>>>(stage.p, (long long)cnt[k], dst[k]);
+    WB_LAUNCH_CHECK();
+  }
+  return WB_CUDA(cudaStreamSynchronize(c->stream)) ? 0 : 1;
+}
 long long wb200_batch_total_y(const wb200_batch* h) {
   long long s = 0;
   for (int v : h->b.h_y_len) s += v;

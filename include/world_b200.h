@@ -86,6 +86,11 @@ WORLD_API int wb200_batch_get_sp(wb200_batch *b, double *host_sp);   /* [frames]
 WORLD_API int wb200_batch_get_ap(wb200_batch *b, double *host_ap);
 WORLD_API int wb200_batch_set_sp_ap(wb200_batch *b, int fft_size, const double *host_sp,
                                     const double *host_ap);
+/* the synth tool's raw parameter files (W/test/synth.cpp:160-190, spec_dimension == 0): float32
+ * f0 [frames] and sp / ap [frames][fft_size/2+1], widened to double on the device (ToDouble).
+ * The host buffers may be pinned; the entry of Synthesis-only runs (BASELINE config 4). */
+WORLD_API int wb200_batch_set_params_f32(wb200_batch *b, int fft_size, const float *host_f0,
+                                         const float *host_sp, const float *host_ap);
 WORLD_API long long wb200_batch_total_y(const wb200_batch *b);
 WORLD_API int wb200_batch_y_layout(const wb200_batch *b, long long *y_off, int *y_len);
 WORLD_API int wb200_batch_get_y(wb200_batch *b, double *host_y);     /* back to back */

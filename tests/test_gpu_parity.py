@@ -381,3 +381,30 @@ def test_full_size_properties(wb):
         assert np.array_equal(s.ap(), ap[sl])
         s.close()
     c.close()
+
+
+@pytest.mark.gpu
+def test_synthesis_from_float32_parameter_files(wb, reference_lib):
+    """BASELINE config 4 entry: the synth tool's raw float32 f0 / sp / ap (W/test/synth.cpp:160-190,
+    spec_dimension == 0) go through wb200_batch_set_params_f32; the waveform must match the
+    reference's Synthesis fed the same widened values (SNR >= 60 dB, north_star)."""
+    gs = [load_golden(n) for n in ("synthetic16k_u11", "arctic_a0001")]
+    fs = int(gs[0]["fs"])
+    assert all(int(g["fs"]) == fs for g in gs)
+    refs = [reference_lib.analyze(_x(g), fs) for g in gs]
+    fft = refs[0]["fft_size"]
+    c = wb.Corpus(fs, [len(g["pcm"]) for g in gs])
+    f0 = np.concatenate([r["f0"] for r in refs]).astype(np.float32)
+    sp = np.concatenate([r["sp"] for r in refs]).astype(np.float32)
+    ap = np.concatenate([r["ap"] for r in refs]).astype(np.float32)
+    c.set_params_f32(fft, f0, sp, ap)
+    c.synthesis()
+    y = c.y()
+    off, ln = c.y_layout()
+    for u, r in enumerate(refs):
+        sl = c.frames_of(u)
+        want = reference_lib.synthesis(f0[sl].astype(np.float64), sp[sl].astype(np.float64), ap[sl].astype(np.float64),
+                                       fft, 5.0, fs)
+        got = y[off[u]:off[u] + ln[u]]
+        assert len(got) == len(want)
+        assert M.snr_db(want, got) >= 60.0
