@@ -80,7 +80,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out);
 
 // mel-DCT codec (wb_codec.cu): rows [n_frames][fft_size/2+1] <-> coded [n_frames][ndim], device pointers
 bool codec_encode_run(const double* d_rows, int n_frames, int fs, int fft_size, int ndim, double scale,
-                      double zero_floor, double c0_add, double* d_out);
+                      double zero_floor, double c0_add, double* d_out, bool f32log = false);
 bool codec_decode_run(const double* d_coded, int n_frames, int fs, int fft_size, int ndim, double* d_rows);
 bool batch_code_features(Batch* b, int mgc_dim, int bap_dim);
 bool batch_feature_stats(Batch* b, double* h_out);

@@ -106,7 +106,11 @@ CodecTables* codec_tables(int fs, int fft_size, int ndim) {
 // dynamic shared memory: [ buf: cpad_size(max_dim/2) double2 | logsp: max_dim + 2 doubles ]
 // out[f][d] = DCT coefficient d of frame f (+ c0_add on d = 0).  scale multiplies the row first;
 // a scaled value of exactly 0 becomes zero_floor (W/test/analysis.cpp:297-301); pass 0 to disable.
-template <int LOG2MAX>     // log2(fft_size / 2); 0: given at run time
+// F32LOG: the logarithm of every bin is taken in FP32 (1 ulp, ~1e-6 absolute on log spectra of
+// magnitude <= 20) -- the batch path, whose outputs are the tool's float32 files (the coefficients
+// move by < 1e-6, their own float32 spacing is 1e-6 at c0 ~ 14); the drop-in CodeSpectralEnvelope,
+// which returns doubles, keeps the FP64 logarithm.
+template <int LOG2MAX, bool F32LOG = false>     // LOG2MAX = log2(fft_size / 2); 0: given at run time
 __global__ void __launch_bounds__(128)
 codec_encode_kernel(const double* __restrict__ rows, int half, int log2max_rt, const int* __restrict__ idx,
                     const double* __restrict__ s, const double2* __restrict__ weight, int ndim, double scale,
@@ -114,6 +118,7 @@ codec_encode_kernel(const double* __restrict__ rows, int half, int log2max_rt, c
   extern __shared__ double2 smem2[];
   const int log2max = LOG2MAX > 0 ? LOG2MAX : log2max_rt;
   constexpr int LM = LOG2MAX > 0 ? LOG2MAX - 1 : 0;
+  constexpr int TWL = LOG2MAX > 0 ? LOG2MAX : kTwLog2;   // compact twiddle table of this size, or the master table
   const int max_dim = 1 << log2max, M = max_dim >> 1, log2m = log2max - 1;
   double2* buf = smem2;
   double* bufd = reinterpret_cast<double*>(buf);
@@ -124,7 +129,7 @@ codec_encode_kernel(const double* __restrict__ rows, int half, int log2max_rt, c
   for (int k = tid; k < max_dim; k += T) {        // bins 0 .. max_dim-1 are all interp1 ever reads
     double v = row[k] * scale;
     if (zero_floor != 0.0 && v == 0.0) v = zero_floor;
-    logsp[k] = log(v);
+    logsp[k] = F32LOG ? static_cast<double>(logf(static_cast<float>(v))) : log(v);
   }
   __syncthreads();
   // mel spectrum j -> DCT input position (:75-79): even j -> j/2, odd j -> max_dim - 1 - (j-1)/2
@@ -135,10 +140,10 @@ codec_encode_kernel(const double* __restrict__ rows, int half, int log2max_rt, c
     const int pos = (j & 1) ? (max_dim - 1 - (j >> 1)) : (j >> 1);
     bufd[rfft_in_slot(pos, log2m)] = v;
   }
-  fft_dit<LM, false, 128, 3>(buf, log2m, tw);
+  fft_dit<LM, false, 128, 3, TWL>(buf, log2m, tw);
   const double normalization = sqrt((double)max_dim);
   for (int d = tid; d < ndim; d += T) {
-    const double2 X = rfft_bin(buf, log2m, d, tw);
+    const double2 X = rfft_bin<TWL>(buf, log2m, d, tw);
     const double2 w = weight[d];
     double v = (X.x * w.x - X.y * w.y) / normalization;
     if (d == 0) v += c0_add;
@@ -214,7 +219,7 @@ __global__ void feature_stats_kernel(const float* __restrict__ m, int n_frames, 
 }  // namespace
 
 bool codec_encode_run(const double* d_rows, int n_frames, int fs, int fft_size, int ndim, double scale,
-                      double zero_floor, double c0_add, double* d_out) {
+                      double zero_floor, double c0_add, double* d_out, bool f32log) {
   Context* c = ctx();
   if (!c) return false;
   if (n_frames <= 0) return true;
@@ -222,16 +227,16 @@ bool codec_encode_run(const double* d_rows, int n_frames, int fs, int fft_size, 
   if (!t) return false;
   const size_t smem = cpad_size(t->max_dim / 2) * sizeof(double2) + (t->max_dim + 2) * sizeof(double);
   KernelTimer kt("codec_encode_kernel");
-#define WB_ENC_LAUNCH(L)                                                                                            \
+#define WB_ENC_LAUNCH(L, F)                                                                                         \
   do {                                                                                                              \
-    WB_CUDA_OR_RETURN(cudaFuncSetAttribute(codec_encode_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
-    codec_encode_kernel<L><<<n_frames, 128, smem, c->stream>>>(d_rows, fft_size / 2, t->log2max, t->enc_idx.p, t->enc_s.p, t->enc_w.p, ndim, \
-                                                              scale, zero_floor, c0_add, c->d_twiddle, d_out);     \
+    WB_CUDA_OR_RETURN(cudaFuncSetAttribute(codec_encode_kernel<L, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
+    codec_encode_kernel<L, F><<<n_frames, 128, smem, c->stream>>>(d_rows, fft_size / 2, t->log2max, t->enc_idx.p, t->enc_s.p, t->enc_w.p, ndim, \
+                                                              scale, zero_floor, c0_add, L > 0 ? c->tw_c(L > 0 ? L : 4) : c->d_twiddle, d_out);     \
   } while (0)
   switch (t->log2max) {
-    case 9: WB_ENC_LAUNCH(9); break;
-    case 10: WB_ENC_LAUNCH(10); break;
-    default: WB_ENC_LAUNCH(0); break;
+    case 9: if (f32log) WB_ENC_LAUNCH(9, true); else WB_ENC_LAUNCH(9, false); break;
+    case 10: if (f32log) WB_ENC_LAUNCH(10, true); else WB_ENC_LAUNCH(10, false); break;
+    default: WB_ENC_LAUNCH(0, false); break;
   }
 #undef WB_ENC_LAUNCH
   WB_LAUNCH_CHECK(); kt.stop();
@@ -268,11 +273,11 @@ bool batch_code_features(Batch* b, int mgc_dim, int bap_dim) {
   cudaStream_t st = c->stream;
   lf0_kernel<<<(F + 255) / 256, 256, 0, st>>>(b->f0.p, F, b->lf0.p);
   WB_LAUNCH_CHECK();
-  if (!codec_encode_run(b->sp.p, F, b->fs, b->fft_size, mgc_dim, 1e4, 0.0001, 12.0, tmp.p)) return false;
+  if (!codec_encode_run(b->sp.p, F, b->fs, b->fft_size, mgc_dim, 1e4, 0.0001, 12.0, tmp.p, true)) return false;
   long long n = (long long)F * mgc_dim;
   coded_to_float_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tmp.p, n, mgc_dim, 0, b->mgc.p);
   WB_LAUNCH_CHECK();
-  if (!codec_encode_run(b->ap.p, F, b->fs, b->fft_size, bap_dim, 1e4, 0.0, -9.210340, tmp.p)) return false;
+  if (!codec_encode_run(b->ap.p, F, b->fs, b->fft_size, bap_dim, 1e4, 0.0, -9.210340, tmp.p, true)) return false;
   n = (long long)F * bap_dim;
   coded_to_float_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tmp.p, n, bap_dim, 1, b->bap.p);
   WB_LAUNCH_CHECK();

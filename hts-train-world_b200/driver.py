@@ -12,7 +12,13 @@ all-reduced over the ranks at the end.
   python hts-train-world_b200/driver.py --raw-dir data/raw --out-dir data --fs 48000 [--f0 harvest]
   torchrun --nproc-per-node 8 hts-train-world_b200/driver.py ...     # utterance-sharded, NCCL stats
 
-Extract.py's vibrato stream (:215) is singing-voice specific and stays outside.
+With --cmp the `cmp:` target (:244-321) runs in the same pass while the features are still in
+HBM: every stream is extended by its delta windows (data/scripts/window.pl, data/win/*.win[123]),
+the streams are merged side by side (mgc | lf0 | bap) and written with the 12-byte HTK header of
+data/scripts/addhtkheader.pl as cmp/<base>.cmp; the per-column {count, sum, sum of squares} of the
+cmp matrix join the all-reduce.  Extract.py's label-driven streams (the second lf0 dimension and
+vib, :215) are singing-voice specific and stay outside; a caller that has them passes
+them to Corpus.compose_cmp as host streams.
 """
 import argparse
 import glob
@@ -45,12 +51,15 @@ def passes_clip_check(pcm):
 
 
 def extract_features(raw_paths, out_dir, fs=48000, frame_period_ms=5.0, mgc_dim=50, bap_dim=24,
-                     f0="dio", batch_seconds=4000.0, rank=0, world=1, log=print):
-    """Returns dict(done=[...], skipped=[...], failed={base: [streams]}, stats=[(1+mgc_dim), 3])."""
+                     f0="dio", batch_seconds=4000.0, rank=0, world=1, log=print, cmp=False, windows=None):
+    """Returns dict(done=[...], skipped=[...], failed={base: [streams]}, stats=[(1+mgc_dim), 3]
+    and, with cmp=True, cmp_stats=[cmp_dim, 3])."""
     import hts_train_world_b200 as wb
     from hts_train_world_b200 import corpus
-    for d in ("lf0", "mgc", "bap"):
+    for d in ("lf0", "mgc", "bap") + (("cmp",) if cmp else ()):
         os.makedirs(os.path.join(out_dir, d), exist_ok=True)
+    frame_shift = int(round(frame_period_ms * fs / 1000.0))     # FRAMESHIFT in samples
+    cmp_stats = None
     sizes = [os.path.getsize(p) // 2 for p in raw_paths]
     mine = corpus.shard_utterances(sizes, rank, world)
     report = dict(done=[], skipped=[], failed={})
@@ -58,7 +67,7 @@ def extract_features(raw_paths, out_dir, fs=48000, frame_period_ms=5.0, mgc_dim=
     batch, batch_audio = [], 0.0
 
     def flush():
-        nonlocal batch, batch_audio
+        nonlocal batch, batch_audio, cmp_stats
         if not batch:
             return
         names, pcms = zip(*batch)
@@ -68,6 +77,11 @@ def extract_features(raw_paths, out_dir, fs=48000, frame_period_ms=5.0, mgc_dim=
         c.code(mgc_dim, bap_dim)
         lf0, mgc, bap = c.coded()
         stats[:] += c.feature_stats()
+        cmp_rows = None
+        if cmp:
+            cmp_rows = c.compose_cmp(("mgc", "lf0", "bap"), windows)
+            st = c.cmp_stats()
+            cmp_stats = st if cmp_stats is None else cmp_stats + st
         for u, base in enumerate(names):
             sl = c.frames_of(u)
             bad = []
@@ -79,6 +93,11 @@ def extract_features(raw_paths, out_dir, fs=48000, frame_period_ms=5.0, mgc_dim=
                 arr.astype("<f4").tofile(os.path.join(out_dir, stream, "%s.%s" % (base, stream)))
             if bad:
                 report["failed"][base] = bad
+            elif cmp:                                    # data/Makefile.in:284: only when every stream exists
+                rows = cmp_rows[sl]
+                with open(os.path.join(out_dir, "cmp", base + ".cmp"), "wb") as f:
+                    f.write(wb.htk_header(rows.shape[0], fs, frame_shift, 4 * rows.shape[1], 9))
+                    f.write(rows.astype("<f4").tobytes())
             report["done"].append(base)
         c.close()
         batch, batch_audio = [], 0.0
@@ -97,14 +116,23 @@ def extract_features(raw_paths, out_dir, fs=48000, frame_period_ms=5.0, mgc_dim=
             flush()
     flush()
     import torch.distributed as dist
+    if cmp and cmp_stats is None:                        # a rank without utterances still joins the reduce
+        dims = [(mgc_dim, 0), (1, 1), (bap_dim, 2)]
+        cmp_stats = np.zeros((sum(d * (3 if windows is None else len(windows[i])) for d, i in dims), 3))
     if dist.is_available() and dist.is_initialized():
         import torch
-        t = torch.as_tensor(stats)
+        parts = [stats] + ([cmp_stats] if cmp else [])
+        t = torch.as_tensor(np.concatenate(parts))       # one all-reduce for all partials
         if dist.get_backend() == "nccl":
             t = t.cuda()
         dist.all_reduce(t)
-        stats = t.cpu().numpy()
+        t = t.cpu().numpy()
+        stats = t[:stats.shape[0]]
+        if cmp:
+            cmp_stats = t[stats.shape[0]:]
     report["stats"] = stats
+    if cmp:
+        report["cmp_stats"] = cmp_stats
     return report
 
 
@@ -117,6 +145,8 @@ def main():
     ap.add_argument("--mgc-order", type=int, default=49)
     ap.add_argument("--bap-dim", type=int, default=24)
     ap.add_argument("--f0", default="dio", choices=["dio", "harvest"])
+    ap.add_argument("--cmp", action="store_true", help="also compose cmp/<base>.cmp (delta windows + HTK header)")
+    ap.add_argument("--win-dir", default=None, help="directory with {mgc,lf0,bap}.win[123] (default: static, delta, delta-delta)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -130,11 +160,19 @@ def main():
     wb.init(local)
     fp = 5.0 if args.frameshift is None else args.frameshift * 1000.0 / args.fs
     paths = sorted(glob.glob(os.path.join(args.raw_dir, "*.raw")))
+    windows = None
+    if args.win_dir:
+        windows = [tuple(wb.parse_window_file(open(os.path.join(args.win_dir, "%s.win%d" % (s, i))).read())
+                         for i in (1, 2, 3) if os.path.exists(os.path.join(args.win_dir, "%s.win%d" % (s, i))))
+                   for s in ("mgc", "lf0", "bap")]
     rep = extract_features(paths, args.out_dir, args.fs, fp, args.mgc_order + 1, args.bap_dim, args.f0,
-                           rank=rank, world=world, log=(print if rank == 0 else (lambda *_: None)))
+                           rank=rank, world=world, log=(print if rank == 0 else (lambda *_: None)),
+                           cmp=args.cmp, windows=windows)
     if rank == 0:
         st = rep["stats"]
         summary = dict(lf0=corpus.merge_stats([st[0]]), mgc=[corpus.merge_stats([r]) for r in st[1:]])
+        if args.cmp:
+            summary["cmp"] = [corpus.merge_stats([r]) for r in rep["cmp_stats"]]
         json.dump(summary, open(os.path.join(args.out_dir, "world_b200_stats.json"), "w"), indent=1)
         print("done: %d utterances on rank 0, %d skipped (clip check), %d with NaN streams"
               % (len(rep["done"]), len(rep["skipped"]), len(rep["failed"])))

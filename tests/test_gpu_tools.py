@@ -124,3 +124,38 @@ def test_corpus_driver_writes_the_tools_files(tmp_path):
         assert np.max(np.abs(bap_r[np.repeat(same, 24)] - bap_b[np.repeat(same, 24)])) <= 1.15e-3 * np.sqrt(512)
         n_voiced += int((lf0_b != 0).sum())
     assert rep["stats"][0, 0] == n_voiced
+
+
+@pytest.mark.gpu
+def test_corpus_driver_composes_cmp_files(tmp_path):
+    """`cmp:` target of data/Makefile.in:244-321 inside the driver: cmp/<base>.cmp = HTK header
+    (addhtkheader.pl) + [mgc | lf0 | bap] x (static, delta, delta-delta) (window.pl), equal bit for
+    bit to the oracle composition of the lf0 / mgc / bap files written in the same run."""
+    from hts_train_world_b200 import driver, signals
+    from oracle import cmp_np
+    import hts_train_world_b200 as wb
+    wb.init(0)
+    fs = 16000
+    raw_dir = tmp_path / "raw"
+    raw_dir.mkdir()
+    for i, d in enumerate([0.5, 0.8]):
+        signals.make_utterance(90 + i, fs, duration=d)[0].numpy().astype("<i2").tofile(str(raw_dir / ("u%d.raw" % i)))
+    paths = sorted(str(p) for p in raw_dir.glob("*.raw"))
+    rep = driver.extract_features(paths, str(tmp_path), fs=fs, log=lambda *_: None, cmp=True)
+    total = 0
+    acc = np.zeros((3 * 75, 2))
+    for base in ("u0", "u1"):
+        lf0 = np.fromfile(str(tmp_path / "lf0" / (base + ".lf0")), np.float32).reshape(-1, 1)
+        mgc = np.fromfile(str(tmp_path / "mgc" / (base + ".mgc")), np.float32).reshape(-1, 50)
+        bap = np.fromfile(str(tmp_path / "bap" / (base + ".bap")), np.float32).reshape(-1, 24)
+        want = cmp_np.compose_cmp([mgc, lf0, bap])
+        blob = (tmp_path / "cmp" / (base + ".cmp")).read_bytes()
+        assert blob[:12] == cmp_np.htk_header(len(lf0), fs, 80, 4 * want.shape[1], 9)     # FRAMESHIFT = 80 at 16 kHz / 5 ms
+        got = np.frombuffer(blob[12:], "<f4").reshape(len(lf0), -1)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        total += len(lf0)
+        acc[:, 0] += want.astype(np.float64).sum(axis=0)
+        acc[:, 1] += (want.astype(np.float64) ** 2).sum(axis=0)
+    st = rep["cmp_stats"]
+    assert st.shape == (225, 3) and np.all(st[:, 0] == total)
+    assert np.allclose(st[:, 1], acc[:, 0], rtol=1e-10, atol=1e-7) and np.allclose(st[:, 2], acc[:, 1], rtol=1e-10)
