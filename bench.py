@@ -326,23 +326,41 @@ def ours_arm(args):
         parts.append(dict(c=cp, s=(s_off, s_off + ns), f=(f_off_, f_off_ + nf), y=(y_off_, y_off_ + ny)))
         s_off, f_off_, y_off_ = s_off + ns, f_off_ + nf, y_off_ + ny
     y_host = torch.empty(y_off_, dtype=torch.int16).pin_memory()
+    # Steps follow each other like the batches of a long corpus run: the first sub-batch of the next
+    # step is uploaded while the last one of this step computes, and the results of a step land in one
+    # of two sets of pinned host buffers while the next step already runs (a consumer has one step of
+    # time to take them).  Nothing is skipped: every step uploads its PCM and downloads all its
+    # results inside the timed region; the statistics are read synchronously every sub-batch.
+    out_sets = [dict(f0=f0_host, lf0=lf0_host, mgc=mgc_host, bap=bap_host, y=y_host)]
+    out_sets.append({k: torch.empty_like(v).pin_memory() for k, v in out_sets[0].items()})
+    e2e_state = dict(step=0, prefetched=False)
 
-    def step_e2e():
+    def upload_part(q):
+        q["c"].upload_pcm16_async(pcm_host[q["s"][0]:q["s"][1]])
+
+    def step_e2e(more_to_come=True):
         st = np.zeros((1 + MGC_DIM, 3))
-        parts[0]["c"].upload_pcm16_async(pcm_host[parts[0]["s"][0]:parts[0]["s"][1]])
+        o = out_sets[e2e_state["step"] % 2]
+        e2e_state["step"] += 1
+        if not e2e_state["prefetched"]:
+            upload_part(parts[0])
+        e2e_state["prefetched"] = False
         for i, p in enumerate(parts):
             if i + 1 < len(parts):
-                q = parts[i + 1]
-                q["c"].upload_pcm16_async(pcm_host[q["s"][0]:q["s"][1]])
+                upload_part(parts[i + 1])
+            elif more_to_come:
+                upload_part(parts[0])               # first sub-batch of the next step
+                e2e_state["prefetched"] = True
             cp, (fa, fb), (ya, yb) = p["c"], p["f"], p["y"]
             cp.analyze(f0=args.f0)
             cp.code(MGC_DIM, BAP_DIM)
-            cp.coded_async(lf0_host[fa:fb], mgc_host[fa:fb], bap_host[fa:fb])
+            cp.coded_async(o["lf0"][fa:fb], o["mgc"][fa:fb], o["bap"][fa:fb])
             cp.synthesis()
-            cp.y_pcm16_async(y_host[ya:yb])
-            wb._check(wb.lib().wb200_batch_get_f0(cp._h, wb.C.cast(f0_host[fa:fb].data_ptr(), wb._dp), 1), "get_f0")
+            cp.y_pcm16_async(o["y"][ya:yb])
+            wb._check(wb.lib().wb200_batch_get_f0(cp._h, wb.C.cast(o["f0"][fa:fb].data_ptr(), wb._dp), 1), "get_f0")
             st += cp.feature_stats()
-        wb.sync()                               # every asynchronous copy has landed
+        if not more_to_come:
+            wb.sync()                           # every asynchronous copy has landed
         return reduce_stats(st)
 
     def barrier():
@@ -399,8 +417,14 @@ def ours_arm(args):
 
     # ---- end to end from host memory --------------------------------------------------------------
     step_e2e()
-    step_e2e()
-    ms_e, wall_e, _, _ = timed(step_e2e, args.steps)
+    step_e2e(more_to_come=False)
+    e2e_calls = dict(n=0)
+
+    def step_e2e_timed():
+        e2e_calls["n"] += 1
+        return step_e2e(more_to_come=e2e_calls["n"] < args.steps)
+
+    ms_e, wall_e, _, _ = timed(step_e2e_timed, args.steps)
     e2e_value = audio_total * args.steps / (max(ms_e, wall_e) * 1e-3)
     h2d = pcm_host.numel() * 2
     d2h = y_host.numel() * 2 + f0_host.numel() * 8 + (lf0_host.numel() + mgc_host.numel() + bap_host.numel()) * 4 + \
@@ -470,6 +494,7 @@ def ours_arm(args):
                    "l2": "inputs larger than L2 (%.0f MB PCM, GBs of intermediates per step)" % (h2d / 1e6)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": max(ms_e, wall_e) / args.steps, "pipelined_sub_batches": n_parts,
+                "pipelined_across_steps": "the next step's first upload overlaps this step's last sub-batch; results land in double-buffered pinned host memory",
                 "device_ms_per_step": ms_e / args.steps, "wall_ms_per_step": wall_e / args.steps,
                 "result": "the analysis tool's float32 lf0/mgc/bap + f0 + 16-bit resynthesised waveform + lf0/mgc statistics; "
                           "sp/ap stay in HBM"},

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(THREADS, 768 / THREADS)
 cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __restrict__ frame_t,
                   const double* __restrict__ f0_in, const long long* __restrict__ rng_off,
                   const uint32_t* __restrict__ randn_tab, const double2* __restrict__ tw,
-                  const float2* __restrict__ twf, int fs, int log2n_rt, double q1, double f0_floor, double* __restrict__ sp_out, int exit_after) {
+                  const float2* __restrict__ twf, int fs, int log2n_rt, double q1, double f0_floor, double* __restrict__ sp_out) {
   extern __shared__ double2 smem2[];
   const int log2n = LOG2N > 0 ? LOG2N : log2n_rt;
   constexpr int LM = LOG2N > 0 ? LOG2N - 1 : 0;
@@ -118,8 +118,6 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
       bufd[slot] = wave;
     }
   }
-
-  if (exit_after == 1) return;
   // ---- GetPowerSpectrum (:64-82) -----------------------------------------------------------
   fft_dit<LM, false, THREADS, THREADS == 256 ? 4 : 3, TWL>(buf, log2m, tw);
   for (int k = tid; k <= half; k += T) {
@@ -127,7 +125,6 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
     aux[k] = X.x * X.x + X.y * X.y;
   }
   __syncthreads();
-  if (exit_after == 2) return;
   // DCCorrection (common.cpp:56-75)
   const double inv_df = (double)N / fs;
   const double inv_n = 1.0 / N;                 // N is a power of two: x * inv_n == x / N exactly
@@ -168,7 +165,6 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
     }
   }
   __syncthreads();
-  if (exit_after == 3) return;
   // ---- SmoothingWithRecovery (:22-57) ---------------------------------------------------------
   // Both transforms act on the LOG spectrum (|values| <= ~40) and its cepstrum; in FP32 their
   // error is ~1e-5 nepers, i.e. 1e-4 dB against the 0.01 dB tolerance, so they run in FP32
@@ -178,7 +174,6 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
     float* fbs = reinterpret_cast<float*>(buf);
     for (int i = tid; i < N; i += T) fbs[rfft_in_slot_f(i, log2m)] = static_cast<float>(aux[i <= half ? i : N - i]);
     fft_dit<LM, false, THREADS, 4, TWL>(fb, log2m, twf);
-    if (exit_after == 4) return;
     float* lif = reinterpret_cast<float*>(aux);         // liftered cepstrum, real
     __syncthreads();                                     // everyone has read aux
     for (int k = tid; k <= half; k += T) {
@@ -198,9 +193,7 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
       const float2 z = c2r_pack<TWL>(make_float2(lif[k], 0.f), make_float2(lif[half - k], 0.f), k, log2m, twf);
       fb[cpadf(brev(k, log2m))] = z;
     }
-    if (exit_after == 5) return;
     fft_dit<LM, true, THREADS, 4, TWL>(fb, log2m, twf);
-    if (exit_after == 6) return;
     for (int k = tid; k <= half; k += T) out[k] = exp(static_cast<double>(fbs[rfft_out_slot_f(k)]));
   }
 }
@@ -234,15 +227,14 @@ bool cheaptrick_run(const UttView& u, int fs, int total_frames, const int* frame
   KernelTimer kt1("cheaptrick_kernel");
   // 128-thread CTAs: 6 frames per SM instead of 3, half as many warps behind every barrier (9 % faster)
   const bool t128 = true;
-  const int exit_after = getenv("WB_CT_EXIT") ? atoi(getenv("WB_CT_EXIT")) : 0;   // EXPERIMENT
 #define WB_CT_LAUNCH(L)                                                                                             \
   do {                                                                                                              \
     if (t128) {                                                                                                     \
     WB_CUDA_OR_RETURN(cudaFuncSetAttribute(cheaptrick_kernel<L, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
-    cheaptrick_kernel<L, 128><<<total_frames, 128, smem, st>>>(u, frame_utt, frame_t, f0, offs.p, c->d_randn, L > 0 ? c->tw_c(L > 0 ? L : 4) : c->d_twiddle, L > 0 ? c->tw_cf(L > 0 ? L : 4) : c->d_twiddle_f, fs, log2n, q1, f0_floor, sp, exit_after); \
+    cheaptrick_kernel<L, 128><<<total_frames, 128, smem, st>>>(u, frame_utt, frame_t, f0, offs.p, c->d_randn, L > 0 ? c->tw_c(L > 0 ? L : 4) : c->d_twiddle, L > 0 ? c->tw_cf(L > 0 ? L : 4) : c->d_twiddle_f, fs, log2n, q1, f0_floor, sp); \
     break; }                                                                                                        \
     WB_CUDA_OR_RETURN(cudaFuncSetAttribute(cheaptrick_kernel<L, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false); \
-    cheaptrick_kernel<L, 256><<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0, offs.p, c->d_randn, L > 0 ? c->tw_c(L > 0 ? L : 4) : c->d_twiddle, L > 0 ? c->tw_cf(L > 0 ? L : 4) : c->d_twiddle_f, fs, log2n, q1, f0_floor, sp, exit_after); \
+    cheaptrick_kernel<L, 256><<<total_frames, 256, smem, st>>>(u, frame_utt, frame_t, f0, offs.p, c->d_randn, L > 0 ? c->tw_c(L > 0 ? L : 4) : c->d_twiddle, L > 0 ? c->tw_cf(L > 0 ? L : 4) : c->d_twiddle_f, fs, log2n, q1, f0_floor, sp); \
   } while (0)
   switch (log2n) {
     case 10: WB_CT_LAUNCH(10); break;

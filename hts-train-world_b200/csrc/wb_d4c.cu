@@ -35,15 +35,16 @@ struct D4CConst {
   int fs, log2nd, log2lt, nbands, window_length, sel_boundary;
   int lt_b0, lt_b1, lt_b2;
   int out_half;              // fft_size/2 of the output axis
-  int exit_after;            // EXPERIMENT: phase timing
   double threshold;
   int centers[kMaxBands];
 };
 
 // windowed waveform with dither and weighted-mean removal (d4c.cpp:52-84).  Sample i is
-// written to base[wslot(i)], its window value to base[vslot(i)] (scratch).  Returns W.
-// Contains block syncs; on return every thread has finished its own slots only.
-template <typename WS, typename VS>
+// written to base[wslot(i)].  STORE_W: its window value goes to base[vslot(i)] (scratch) for the
+// mean-removal sweep; otherwise that sweep re-runs the same recurrence (bit-identical values) and
+// no scratch is needed.  Returns W.  Contains block syncs; on return every thread has finished
+// its own slots only.
+template <bool STORE_W, typename WS, typename VS>
 __device__ __forceinline__ int windowed_waveform(const double* __restrict__ x, int x_len, int fs,
                                                  double f0, double position, int window_type,
                                                  double ratio, const uint32_t* __restrict__ rn,
@@ -58,12 +59,15 @@ __device__ __forceinline__ int windowed_waveform(const double* __restrict__ x, i
   // cos(a_i), a_i = (i - hwl) * ang_step, i = tid + j T: one sincos per thread for j = 0, then
   // the angle-addition recurrence with the block-uniform step T * ang_step (<= 16 steps, so
   // the accumulated rounding stays below 1e-15); cos(2a) = 2 cos^2(a) - 1.
-  double cs, sn, cs_step, sn_step;
-  sincos((double)(tid - hwl) * ang_step, &sn, &cs);
+  double cs0, sn0, cs_step, sn_step;
+  sincos((double)(tid - hwl) * ang_step, &sn0, &cs0);
   sincos((double)T * ang_step, &sn_step, &cs_step);
+  auto window_at = [&](double cs) {
+    return window_type == kHanning ? 0.5 * cs + 0.5 : 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);
+  };
+  double cs = cs0, sn = sn0;
   for (int i = tid; i < W; i += T) {
-    const double w = window_type == kHanning ? 0.5 * cs + 0.5
-                                             : 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);
+    const double w = window_at(cs);
     {
       const double c2 = cs * cs_step - sn * sn_step;
       sn = sn * cs_step + cs * sn_step;
@@ -72,13 +76,23 @@ __device__ __forceinline__ int windowed_waveform(const double* __restrict__ x, i
     const double xv = staged ? staged[i] : x[min(x_len - 1, max(0, origin + i - hwl))];
     const double wave = xv * w + randn_from_u32(rn[i]) * kMySafeGuardMinimum;
     base[wslot(i)] = wave;
-    base[vslot(i)] = w;
+    if (STORE_W) base[vslot(i)] = w;
     s[0] += wave;
     s[1] += w;
   }
   block_sum<2>(s, red);
   const double coef = s[0] / s[1];
-  for (int i = tid; i < W; i += T) base[wslot(i)] -= base[vslot(i)] * coef;
+  if (STORE_W) {
+    for (int i = tid; i < W; i += T) base[wslot(i)] -= base[vslot(i)] * coef;
+  } else {
+    cs = cs0; sn = sn0;
+    for (int i = tid; i < W; i += T) {
+      base[wslot(i)] -= window_at(cs) * coef;
+      const double c2 = cs * cs_step - sn * sn_step;
+      sn = sn * cs_step + cs * sn_step;
+      cs = c2;
+    }
+  }
   return W;
 }
 
@@ -107,17 +121,17 @@ d4c_lovetrain_kernel(UttView u, const int* __restrict__ frame_utt, const double*
   const int M = 1 << log2m, N = M << 1;
   double2* buf = smem2;
   double* bufd = reinterpret_cast<double*>(buf);
-  // layout: [ buf: 2*cpad_size(M) doubles | window scratch: N + 8 doubles | red: 96 ]
+  // layout: [ buf: 2*cpad_size(M) doubles | red: 96 ]
   const int vbase = 2 * cpad_size(M);
-  double* red = bufd + vbase + N + 8;
+  double* red = bufd + vbase;
   const int tid = threadIdx.x, T = blockDim.x;
   const int utt = frame_utt[f];
   const double* __restrict__ x = u.x + u.x_off[utt];
   const double cur_f0 = fmax(f0, 40.0);
   auto wslot = [log2m](int i) { return rfft_in_slot(i, log2m); };
   auto vslot = [vbase](int i) { return vbase + i; };
-  const int W = windowed_waveform(x, u.x_len[utt], c.fs, cur_f0, frame_t[f], kBlackman, 3.0,
-                                  randn_tab + rng_off[f], bufd, wslot, vslot, red);
+  const int W = windowed_waveform<false>(x, u.x_len[utt], c.fs, cur_f0, frame_t[f], kBlackman, 3.0,
+                                         randn_tab + rng_off[f], bufd, wslot, vslot, red);
   for (int i = W + tid; i < N; i += T) bufd[rfft_in_slot(i, log2m)] = 0.0;
   fft_dit<LM, false, 256, 3, TWL>(buf, log2m, tw);
   double s[2] = {0.0, 0.0};
@@ -468,13 +482,30 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
         energy = e[0];
       }
       const double inv_sq = 1.0 / sqrt(energy);
-      for (int i = tid; i < Nd; i += T) {
-        double2 z = make_double2(0.0, 0.0);
-        if (i < W) { const double2 q = cbuf[cslot(i)]; const double v = (q.x - q.y * coef) * inv_sq; z = make_double2(v, v * (i + 1.0)); }
-        cbuf[cslot(i)] = z;
+      if constexpr (LOG2ND > 0) {
+        // mean removal, normalisation, the (n + 1) factor of the second sequence and the zero padding
+        // happen while the first pass loads its own slots (the block reductions above are the barrier
+        // behind the window loop); slots beyond the window are not even read
+        using plan = fft_plan<LOG2ND, MAXK>;
+        constexpr int K0 = plan::k_of(0);
+        auto load = [&](int base, int m) {
+          const int i = brev(base, LOG2ND) | (brev(m, K0) << (LOG2ND - K0));     // element index of slot base + m
+          double2 z = make_double2(0.0, 0.0);
+          if (i < W) { const double2 q = cbuf[cpad(base) + cpad(m)]; const double v = (q.x - q.y * coef) * inv_sq; z = make_double2(v, v * (i + 1.0)); }
+          return z;
+        };
+        fft_first_pass_from<K0, false, LOG2ND, THREADS>(cbuf, load);
+        __syncthreads();
+        fft_run_passes<LOG2ND, MAXK, 1, false, THREADS, TWL>(cbuf, tw);
+      } else {
+        for (int i = tid; i < Nd; i += T) {
+          double2 z = make_double2(0.0, 0.0);
+          if (i < W) { const double2 q = cbuf[cslot(i)]; const double v = (q.x - q.y * coef) * inv_sq; z = make_double2(v, v * (i + 1.0)); }
+          cbuf[cslot(i)] = z;
+        }
+        fft_dit<LOG2ND, false, THREADS, MAXK, TWL>(cbuf, log2nd, tw);
       }
     }
-    fft_dit<LOG2ND, false, THREADS, MAXK, TWL>(cbuf, log2nd, tw);
     for (int k = tid; k <= Hd; k += T) {
       const double2 A = cbuf[cpad(k)];
       const double2 B = cbuf[cpad((Nd - k) & (Nd - 1))];
@@ -483,7 +514,6 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
     }
   }
   __syncthreads();
-  if (c.exit_after == 1) return;
   dc_correction(cen, cbufd, cur_f0, c.fs, Nd);        // cbuf is idle here; pw holds the staged power-spectrum window
 
   // ---- GetSmoothedPowerSpectrum (:148-164) ----------------------------------------------------
@@ -496,7 +526,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
     auto pvslot = [vbase](int i) { return vbase + i; };
     __syncthreads();                                    // centroid readers of cbuf are done
     if (st_ok) mbar_wait(&mbar, st_parity);
-    const int W = windowed_waveform(x, x_len, c.fs, cur_f0, t_pos, kHanning, 4.0,
+    const int W = windowed_waveform<true>(x, x_len, c.fs, cur_f0, t_pos, kHanning, 4.0,
                                     rn + 2 * (size_t)W4, cbufd, pwslot, pvslot, red,
                                     st_ok ? pw + (window_origin(2) - st_a0) : nullptr);
     for (int i = W + tid; i < Nd; i += T) cbufd[rfft_in_slot(i, log2m)] = 0.0;
@@ -507,10 +537,8 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
     }
     __syncthreads();
     dc_correction(pw, cbufd, cur_f0, c.fs, Nd);
-    if (c.exit_after == 2) return;
     linear_smoothing(pw, pw, cbufd, red, cur_f0, c.fs, Nd);
   }
-  if (c.exit_after == 3) return;
   // ---- GetStaticGroupDelay (:170-186) ------------------------------------------------------------
   for (int k = tid; k <= Hd; k += T) cen[k] = cen[k] / pw[k];
   __syncthreads();
@@ -518,7 +546,6 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
   linear_smoothing(cen, pw, cbufd, red, cur_f0, c.fs, Nd);
   for (int k = tid; k <= Hd; k += T) cen[k] -= pw[k];
   __syncthreads();
-  if (c.exit_after == 4) return;
 
   // ---- GetCoarseAperiodicity (:192-223): two bands per complex FP32 FFT, one selection for all --
   {
@@ -558,7 +585,6 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
       }
       __syncthreads();
     }
-    if (c.exit_after == 5) return;
     if constexpr (LOG2ND > 0) {                    // one warp per band, keys in registers
       constexpr int NPL = ((1 << (LOG2ND - 1)) + 1 + 31) / 32;
       for (int b = tid >> 5; b < c.nbands; b += THREADS / 32) {
@@ -575,7 +601,6 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
   }
   if (tid == 0) { coarse[0] = -60.0; coarse[c.nbands + 1] = -kMySafeGuardMinimum; }
   __syncthreads();
-  if (c.exit_after == 6) return;
   // ---- GetAperiodicity (:325-333): interp1 over {0, 3k, ..., fs/2} then 10^(dB/20) ---------------
   const int nk = c.nbands + 2;
   const int N_out = 2 * c.out_half;
@@ -608,7 +633,6 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
   c.fs = fs;
   c.threshold = threshold;
   c.out_half = fft_size / 2;
-  c.exit_after = getenv("WB_D4C_EXIT") ? atoi(getenv("WB_D4C_EXIT")) : 0;
   const int nd = static_cast<int>(pow(2.0, 1.0 + static_cast<int>(log(4.0 * fs / kFloorF0D4C + 1) / kLog2)));  // d4c.cpp:344-346
   const int nlt = static_cast<int>(pow(2.0, 1.0 + static_cast<int>(log(3.0 * fs / 40.0 + 1) / kLog2)));        // :261-262
   c.log2nd = 0; while ((1 << c.log2nd) < nd) ++c.log2nd;
@@ -657,7 +681,7 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
   if (!need_randn()) return false;
   {
     const int nl = 1 << c.log2lt;
-    const size_t smem = (size_t)(2 * cpad_size(nl / 2) + nl + 8 + 96) * sizeof(double);
+    const size_t smem = (size_t)(2 * cpad_size(nl / 2) + 96) * sizeof(double);
     KernelTimer kt1("d4c_lovetrain_kernel");
 #define WB_LT_LAUNCH(L)                                                                                             \
   do {                                                                                                              \

@@ -103,8 +103,17 @@ __global__ void dio_mean_kernel(const double* __restrict__ x_all, const long lon
   const int u = blockIdx.x;
   const double* __restrict__ x = x_all + x_off[u];
   const int n = x_len[u];
-  double v[1] = {0.0};
-  for (int i = threadIdx.x; i < n; i += blockDim.x) v[0] += x[i];
+  // one CTA per utterance: keep eight loads in flight per thread, the latency of a dependent
+  // load-add chain is what this kernel costs (the mean only shifts the DC the low-cut filter removes)
+  double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  const int T = blockDim.x;
+  int i = threadIdx.x;
+  for (; i + 7 * T < n; i += 8 * T) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] += x[i + q * T];
+  }
+  for (; i < n; i += T) a[0] += x[i];
+  double v[1] = {((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]))};
   block_sum<1>(v, red);
   if (threadIdx.x == 0) mean[u] = v[0] / y_len[u];
 }
@@ -300,7 +309,7 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
     if (!decimate_run(b, ratio, h_ylen, &d_dec, &d_dec_off, &d_dec_len, &got)) return false;
     xin = d_dec.p; xin_off = d_dec_off.p; xin_len = d_dec_len.p;
   }
-  dio_mean_kernel<<<n_utt, 256, 0, st>>>(xin, xin_off, xin_len, d_ylen.p, d_mean.p);
+  dio_mean_kernel<<<n_utt, 1024, 0, st>>>(xin, xin_off, xin_len, d_ylen.p, d_mean.p);
   WB_LAUNCH_CHECK();
 
   const size_t smem = 2 * cpad_size(c.bn / 2) * sizeof(double2);

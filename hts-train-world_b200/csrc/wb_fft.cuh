@@ -127,6 +127,42 @@ __device__ __forceinline__ void fft_pass(C* __restrict__ s, const C* __restrict_
   }
 }
 
+// First pass with the input produced on the fly: load(slot) returns the element that belongs in
+// `slot` (element index brev(slot)), e.g. a normalised / zero-padded value computed from what the
+// slot currently holds -- a separate sweep over the whole buffer and its barrier disappear.  The
+// group of a thread is its own 2^K consecutive slots, so reading and writing them needs no
+// synchronisation beyond "the producers of the slots are done".
+template <int K, bool INV, int LOG2N, int THREADS, typename C, typename LOAD>
+__device__ __forceinline__ void fft_first_pass_from(C* __restrict__ s, LOAD load) {
+  constexpr int R = 1 << K;
+  constexpr int NB = 1 << (LOG2N - K);
+  constexpr int ITERS = (NB + THREADS - 1) / THREADS;
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int b = threadIdx.x + it * THREADS;
+    if (NB % THREADS != 0 && b >= NB) break;
+    const int base = b << K;
+    C* __restrict__ sb = s + cpadT<C>(base);
+    C v[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) v[m] = load(base, m);
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+      const int span = 1 << t;
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        if (m & span) continue;
+        const C x = rot16<INV>(v[m + span], (m & (span - 1)) * (8 >> t));
+        const C a = v[m];
+        v[m] = cadd(a, x);
+        v[m + span] = csub(a, x);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < R; ++m) sb[cpadT<C>(m)] = v[m];
+  }
+}
+
 // Pass schedule: P = ceil(LOG2N / MAXK) passes, the first LOG2N % P of them one stage larger.
 template <int LOG2N, int MAXK> struct fft_plan {
   static constexpr int P = (LOG2N + MAXK - 1) / MAXK;

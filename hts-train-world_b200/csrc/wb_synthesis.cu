@@ -27,7 +27,6 @@ namespace {
 constexpr double kTwoPi = 2.0 * kPi;
 
 struct SynthConst {
-  int exit_after;   // EXPERIMENT
   int fs, log2n, f0_max_len;
   double frame_period_s;   // seconds
   double lowest_f0;
@@ -79,20 +78,20 @@ __global__ void synth_pulse_bound_kernel(const double* __restrict__ f0_all, cons
 
 // Time base: WRITE = false counts pulses, WRITE = true stores them (and counts).
 template <bool WRITE>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 synth_timebase_kernel(const double* __restrict__ f0_all, const int* __restrict__ f_off,
                       const int* __restrict__ f_len, const int* __restrict__ y_len_all, SynthConst c,
                       int* __restrict__ pulse_count, const int* __restrict__ pulse_off,
                       const int* __restrict__ pulse_cap, int* __restrict__ p_index, double* __restrict__ p_shift,
                       unsigned char* __restrict__ p_vuv, int* __restrict__ p_utt) {
-  __shared__ double inc_s[512];
-  __shared__ double tot_s[512];
+  __shared__ double inc_s[1024];
+  __shared__ double tot_s[1024];
   __shared__ long long wsum_s[32];
   __shared__ int wcnt[32];
   __shared__ double carry_phase, last_wrap_prev;
   __shared__ int carry_cnt;
-  __shared__ double wrap_s[512 + 1];
-  __shared__ unsigned char vuv_s[512 + 1];
+  __shared__ double wrap_s[1024 + 1];
+  __shared__ unsigned char vuv_s[1024 + 1];
   const int u = blockIdx.x;
   const double* __restrict__ f0 = f0_all + f_off[u];
   const int n_frames = f_len[u];
@@ -403,9 +402,7 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
       nzb[cpadT<C>(brev(i, log2n))] = mk2(n0, n1);
     }
   }
-  if (c.exit_after == 1) return;
   fft_dit<LOG2N, false, T, 4, TWL>(nzb, log2n, tw);       // C
-  if (c.exit_after == 2) return;
   // ---- log spectra (:45-51, :115-117), written as the even extension in bit-reversed order ----
   for (int k = tid; k <= half; k += T) {
     R l0 = 0, l1 = 0;
@@ -425,9 +422,7 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
     cbuf[cpadT<C>(brev(k, log2n))] = z;
     if (k > 0 && k < half) cbuf[cpadT<C>(brev(N - k, log2n))] = z;
   }
-  if (c.exit_after == 3) return;
   fft_dit<LOG2N, false, T, 4, TWL>(cbuf, log2n, tw);      // A
-  if (c.exit_after == 4) return;
   // ---- fold the cepstra (common.cpp:194-206) -----------------------------------------------------
   {
     C keep[kQ];
@@ -450,7 +445,6 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
     for (int i = half + 1 + tid; i < N; i += T) cbuf[cpadT<C>(brev(i, log2n))] = mk2(static_cast<R>(0), static_cast<R>(0));
   }
   fft_dit<LOG2N, false, T, 4, TWL>(cbuf, log2n, tw);      // B
-  if (c.exit_after == 5) return;
   // ---- minimum-phase spectra, time shift / noise product (:56-65, :88-100, :120-131) ------------
   {
     const double coefficient = per_item
@@ -497,9 +491,7 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
       if (k > 0 && k < half) cbuf[cpadT<C>(brev(N - k, log2n))] = mk2(a.x + b.y, b.x - a.y);
     }
   }
-  if (c.exit_after == 6) return;
   fft_dit<LOG2N, true, T, 4, TWL>(cbuf, log2n, tw);       // D
-  if (c.exit_after == 7) return;
   // ---- fftshift, RemoveDCComponent (:73-82), mix (:214-217), overlap-add (:376-383) -------------
   if (per_item) {
     double dc[1] = {0.0};
@@ -557,7 +549,6 @@ bool synthesis_run(Batch* b, const int* y_len) {
 
   SynthConst c;
   c.fs = b->fs;
-  c.exit_after = getenv("WB_SY_EXIT") ? atoi(getenv("WB_SY_EXIT")) : 0;
   c.log2n = log2n;
   c.frame_period_s = b->frame_period / 1000.0;
   c.lowest_f0 = b->fs / N + 1.0;                    // integer division, W/src/synthesis.cpp:359
@@ -584,8 +575,9 @@ bool synthesis_run(Batch* b, const int* y_len) {
   WB_CUDA_OR_RETURN(cudaMemsetAsync(p_utt.p, 0xff, (size_t)total_p * sizeof(int), st), false);   // -1 = unused slot
   KernelTimer kt2("synth_timebase_kernel");
   // one CTA walks one utterance chunk by chunk (the phase accumulation is sequential across chunks):
-  // its latency, not the throughput, sets the time, so small batches get twice as wide chunks
-  const int tb_threads = n_utt <= 4 * ctxp->sm_count ? 512 : 256;
+  // the number of chunks sets the latency of an utterance, so the chunks are as wide as the batch
+  // allows without queueing CTAs behind each other (measured: 1024 threads lose at 1 132 utterances)
+  const int tb_threads = n_utt <= 2 * ctxp->sm_count ? 1024 : n_utt <= 4 * ctxp->sm_count ? 512 : 256;
   synth_timebase_kernel<true><<<n_utt, tb_threads, 0, st>>>(b->f0.p, b->f_off.p, b->f_len.p, b->y_len.p, c, d_cnt.p, d_poff.p, d_cap.p,
                                                      p_index.p, p_shift.p, p_vuv.p, p_utt.p);
   WB_LAUNCH_CHECK(); kt2.stop();
