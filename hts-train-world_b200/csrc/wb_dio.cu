@@ -313,7 +313,7 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
   WB_LAUNCH_CHECK();
 
   const size_t smem = 2 * cpad_size(c.bn / 2) * sizeof(double2);
-  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(ols_filter_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(ols_filter_kernel<13, 512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
   WB_CUDA_OR_RETURN(cudaFuncSetAttribute(ols_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
 
   OlsConst oc = {c.nb, c.bn, c.log2bn, c.D, c.V};
@@ -352,8 +352,10 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
       return false;
     WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_foff.p, h_foff.data(), nu * sizeof(long long), cudaMemcpyHostToDevice, st), false);
     KernelTimer kt1("dio_filter_kernel");
+    // 150 KB of shared memory per block leave one CTA per SM: 512 threads (16 warps) hide the latency of
+    // the multiply / pack / store sweeps even though only 256 of them own a radix-16 group (-16 %)
     if (c.log2bn == 13)
-      ols_filter_kernel<13><<<dim3(n_blocks, nu), 256, smem, st>>>(xin, xin_off, xin_len, d_ylen.p, d_mask.p, d_mean.p,
+      ols_filter_kernel<13, 512, 4><<<dim3(n_blocks, nu), 512, smem, st>>>(xin, xin_off, xin_len, d_ylen.p, d_mask.p, d_mean.p,
                                                             d_foff.p, fb->G.p, ctxp->tw_c(13), oc, d_shift.p, u0, d_F.p);
     else
       ols_filter_kernel<0><<<dim3(n_blocks, nu), 256, smem, st>>>(xin, xin_off, xin_len, d_ylen.p, d_mask.p, d_mean.p,

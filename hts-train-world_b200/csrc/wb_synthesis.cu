@@ -341,8 +341,8 @@ __device__ __forceinline__ void exp_sincos(float re, float im, float* er, float*
 __device__ __forceinline__ double log_of(double v, double) { return log(v); }
 __device__ __forceinline__ float log_of(double v, float) { return __logf(static_cast<float>(v)); }
 
-template <int LOG2N, typename C, int THREADS = 256>      // LOG2N 0: size given at run time (c.log2n)
-__global__ void __launch_bounds__(THREADS, 768 / THREADS)
+template <int LOG2N, typename C, int THREADS = 256, int MINB = (sizeof(C) == 8 ? 1024 : 768) / THREADS>      // LOG2N 0: size given at run time (c.log2n)
+__global__ void __launch_bounds__(THREADS, MINB)
 synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ ap_all,
                   const int* __restrict__ f_off, const int* __restrict__ f_len,
                   const long long* __restrict__ y_off, const int* __restrict__ y_len_all,

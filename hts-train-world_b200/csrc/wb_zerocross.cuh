@@ -170,8 +170,8 @@ __device__ inline double zc_interp(const double* __restrict__ e, int n_int, doub
 struct OlsConst { int nb, bn, log2bn, D, V; };
 
 // dynamic shared memory: [ xs: cpad_size(bn/2) double2 | ws: cpad_size(bn/2) double2 ]
-template <int LOG2BN>     // 0: block size given at run time (c.log2bn)
-static __global__ void __launch_bounds__(256)
+template <int LOG2BN, int THREADS = 256, int MAXK = 4>     // LOG2BN 0: block size given at run time (c.log2bn)
+static __global__ void __launch_bounds__(THREADS)
 ols_filter_kernel(const double* __restrict__ x_all, const long long* __restrict__ x_off,
                   const int* __restrict__ x_len, const int* __restrict__ y_len_all,
                   const int* __restrict__ fft_mask_all, const double* __restrict__ mean_all,
@@ -202,7 +202,7 @@ ols_filter_kernel(const double* __restrict__ x_all, const long long* __restrict_
     if (m < y_len) v = (m < xl ? x[m] : 0.0) - mean;
     xsd[rfft_in_slot(i, log2m)] = v;
   }
-  fft_dit<LM, false, 256, 4, TWL>(xs, log2m, tw);
+  fft_dit<LM, false, THREADS, MAXK, TWL>(xs, log2m, tw);
   // half spectrum in place: slot k = X[k] (k < M), slot 0 = (X[0], X[M])
   for (int k = tid; k <= M / 2; k += T) {
     if (k == 0) {
@@ -232,7 +232,7 @@ ols_filter_kernel(const double* __restrict__ x_all, const long long* __restrict_
         if (k != M - k) ws[cpad(brev(M - k, log2m))] = c2r_pack<TWL>(ym, yk, M - k, log2m, tw);
       }
     }
-    fft_dit<LM, true, 256, 4, TWL>(ws, log2m, tw);
+    fft_dit<LM, true, THREADS, MAXK, TWL>(ws, log2m, tw);
     const int shift = shift_all[b];                    // filtered_b[n] = conv[n - n0 + shift]
     double* __restrict__ dst = Fu + (size_t)b * y_len + n0;
     for (int i = tid; i < n_out; i += T) dst[i] = wsd[rfft_out_slot(i + shift)];
