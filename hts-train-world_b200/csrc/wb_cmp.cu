@@ -29,26 +29,47 @@ struct CmpSegment {
   double coef[WB200_CMP_MAX_WIN_SIZE];
 };
 
+// Warps walk frames (grid-stride), lanes are the columns of the merged frame: a warp stores 32
+// consecutive floats of one row and reads runs of consecutive statics, so both sides of this
+// pure HBM stream are coalesced.  The (stream, window) segment of every column comes
+// from a table in shared memory.
 __global__ void __launch_bounds__(256)
-cmp_compose_kernel(const CmpSegment* __restrict__ segs, const int* __restrict__ frame_utt,
+cmp_compose_kernel(const CmpSegment* __restrict__ segs, int n_segs, const int* __restrict__ frame_utt,
                    const int* __restrict__ f_off, const int* __restrict__ f_len, int total_frames,
                    int cmp_dim, float* __restrict__ out) {
-  const CmpSegment& s = segs[blockIdx.y];
-  const long long n = (long long)total_frames * s.dim;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-    const int f = (int)(e / s.dim), j = (int)(e - (long long)f * s.dim);
+  extern __shared__ unsigned char smem_raw[];
+  CmpSegment* sg = reinterpret_cast<CmpSegment*>(smem_raw);
+  unsigned char* col_seg = smem_raw + (size_t)n_segs * sizeof(CmpSegment);
+  for (int i = threadIdx.x; i < n_segs * (int)(sizeof(CmpSegment) / 4); i += blockDim.x)
+    reinterpret_cast<int*>(sg)[i] = reinterpret_cast<const int*>(segs)[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < cmp_dim; c += blockDim.x) {
+    int k = 0;
+    while (k + 1 < n_segs && c >= sg[k + 1].col0) ++k;
+    col_seg[c] = (unsigned char)k;
+  }
+  __syncthreads();
+  // one warp per frame row: eight rows are in flight per CTA, which hides the dependent look-ups
+  // (frame -> utterance -> frame range) behind the streams of the other warps
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int f = blockIdx.x * wpb + (threadIdx.x >> 5); f < total_frames; f += gridDim.x * wpb) {
     const int u = frame_utt[f];
     const int first = f_off[u], T = f_len[u], t = f - first;
-    double acc = 0.0;
-    bool boundary = false;
-    for (int k = -s.nlr; k <= s.nlr; ++k) {
-      const int l = min(T - 1, max(0, t + k));                         // window.pl:95-103 / :111-119
-      const double v = (double)s.src[(size_t)(first + l) * s.dim + j];
-      const int tap = k + s.nlr;
-      if (tap >= s.chk_lo && tap <= s.chk_hi && v == kIgnoreValue) boundary = true;
-      acc = __dadd_rn(acc, __dmul_rn(s.coef[tap], v));                  // no contraction: perl adds a rounded product
+#pragma unroll 4
+    for (int c = lane; c < cmp_dim; c += 32) {
+      const CmpSegment& s = sg[col_seg[c]];
+      const int j = c - s.col0;
+      double acc = 0.0;
+      bool boundary = false;
+      for (int k = -s.nlr; k <= s.nlr; ++k) {
+        const int l = min(T - 1, max(0, t + k));                         // window.pl:95-103 / :111-119
+        const double v = (double)s.src[(size_t)(first + l) * s.dim + j];
+        const int tap = k + s.nlr;
+        if (tap >= s.chk_lo && tap <= s.chk_hi && v == kIgnoreValue) boundary = true;
+        acc = __dadd_rn(acc, __dmul_rn(s.coef[tap], v));                  // no contraction: perl adds a rounded product
+      }
+      out[(size_t)f * cmp_dim + c] = (float)(boundary ? kIgnoreValue : acc);
     }
-    out[(size_t)f * cmp_dim + s.col0 + j] = (float)(boundary ? kIgnoreValue : acc);
   }
 }
 
@@ -117,7 +138,8 @@ bool batch_compose_cmp(Batch* b, const wb200_cmp_stream* streams, int n_streams)
   WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_segs.p, segs.data(), segs.size() * sizeof(CmpSegment), cudaMemcpyHostToDevice, c->stream), false);
   {
     KernelTimer kt("cmp_compose_kernel");
-    cmp_compose_kernel<<<dim3(148 * 4, (unsigned)segs.size()), 256, 0, c->stream>>>(d_segs.p, b->frame_utt.p, b->f_off.p, b->f_len.p, F, col, b->cmp.p);
+    const size_t smem = segs.size() * sizeof(CmpSegment) + (size_t)col + 16;
+    cmp_compose_kernel<<<c->sm_count * 8, 256, smem, c->stream>>>(d_segs.p, (int)segs.size(), b->frame_utt.p, b->f_off.p, b->f_len.p, F, col, b->cmp.p);
     WB_LAUNCH_CHECK(); kt.stop();
   }
   // the host vectors (segs, staged uploads) must outlive the copies queued above
