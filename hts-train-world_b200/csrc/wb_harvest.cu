@@ -232,6 +232,7 @@ __device__ __forceinline__ double harvest_overlapped(const double* __restrict__ 
 // GetRefinedF0 for one candidate, evaluated by a full warp; lane 0 returns the result.
 __device__ __forceinline__ void harvest_refine_one(const double* __restrict__ y, int y_len, double mean,
                                                    const HarvestConst& c, int k, double f0c, int lane,
+                                                   const double2* __restrict__ tw_c_base,
                                                    double* refined_out, double* score_out) {
   const double fs = c.actual_fs;
   const double pos = div_rn((double)k, 1000.0);
@@ -258,13 +259,21 @@ __device__ __forceinline__ void harvest_refine_one(const double* __restrict__ y,
 #pragma unroll
   for (int h = 0; h < 6; ++h) { acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.0; }
   // phasors e^{-2 pi i bin n / nfft} for n = lane, advanced by 32 samples per iteration
+  // (start and step come from the compact twiddle table of size nfft: exp(-2 pi i m / nfft) for
+  // m <= nfft/2, negated for the other half turn -- twelve table loads instead of twelve sincospi)
   double pc[6], ps[6], qc[6], qs[6];
+  {
+    const double2* __restrict__ tw = tw_c_base + Context::tw_c_offset(log2fft);
+    const int nhalf = nfft >> 1;
 #pragma unroll
-  for (int h = 0; h < 6; ++h) {
-    const int m0 = (int)(((long long)bins[h] * lane) & (nfft - 1));
-    const int m1 = (int)(((long long)bins[h] * 32) & (nfft - 1));
-    sincospi(-2.0 * m0 / nfft, &ps[h], &pc[h]);
-    sincospi(-2.0 * m1 / nfft, &qs[h], &qc[h]);
+    for (int h = 0; h < 6; ++h) {
+      const int m0 = (int)(((long long)bins[h] * lane) & (nfft - 1));
+      const int m1 = (int)(((long long)bins[h] * 32) & (nfft - 1));
+      double2 a = __ldg(&tw[m0 & (nhalf - 1)]), b = __ldg(&tw[m1 & (nhalf - 1)]);
+      if (m0 & nhalf) { a.x = -a.x; a.y = -a.y; }
+      if (m1 & nhalf) { b.x = -b.x; b.y = -b.y; }
+      pc[h] = a.x; ps[h] = a.y; qc[h] = b.x; qs[h] = b.y;
+    }
   }
   auto blackman = [](double cv) { return 0.42 + 0.5 * cv + 0.08 * (2.0 * cv * cv - 1.0); };
   for (int n = lane; n < W; n += 32) {
@@ -291,10 +300,60 @@ __device__ __forceinline__ void harvest_refine_one(const double* __restrict__ y,
       pc[h] = t;
     }
   }
+  // 24 sums over the warp by recursive halving: at every step a lane keeps half of its values and
+  // hands the other half to its partner, so 12 + 6 + 3 values cross instead of 24 per step; the
+  // last three values are finished with plain butterflies.  Lane (4 g + q') ends up with ... no
+  // particular owner is needed: the totals are broadcast back below.
+  {
+    double v[24];
 #pragma unroll
-  for (int h = 0; h < 6; ++h)
+    for (int h = 0; h < 6; ++h)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) acc[h][q] = warp_sum(acc[h][q]);
+      for (int q = 0; q < 4; ++q) v[4 * h + q] = acc[h][q];
+    // step 1 (partner lane ^ 16): keep 12
+    double a12[12];
+    {
+      const bool up = lane & 16;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        const double send = up ? v[i] : v[12 + i];
+        const double keep = up ? v[12 + i] : v[i];
+        a12[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+    }
+    double a6[6];
+    {
+      const bool up = lane & 8;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const double send = up ? a12[i] : a12[6 + i];
+        const double keep = up ? a12[6 + i] : a12[i];
+        a6[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+    }
+    double a3[3];
+    {
+      const bool up = lane & 4;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double send = up ? a6[i] : a6[3 + i];
+        const double keep = up ? a6[3 + i] : a6[i];
+        a3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      a3[i] += __shfl_xor_sync(0xffffffffu, a3[i], 2);
+      a3[i] += __shfl_xor_sync(0xffffffffu, a3[i], 1);
+    }
+    // lane group g = (lane >> 2) & 7 = (bit16, bit8, bit4) holds values  12 b16 + 6 b8 + 3 b4 + {0,1,2}
+#pragma unroll
+    for (int idx = 0; idx < 24; ++idx) {
+      const int b16 = idx / 12, r12 = idx % 12, b8 = r12 / 6, r6 = r12 % 6, b4 = r6 / 3, i = r6 % 3;
+      const int src = (b16 << 4) | (b8 << 3) | (b4 << 2);
+      acc[idx >> 2][idx & 3] = __shfl_sync(0xffffffffu, a3[i], src);
+    }
+  }
   double numerator = 0.0, denominator = 0.0, sc = 0.0;             // FixF0 (:504-536)
   for (int h = 0; h < nh; ++h) {
     const double re = acc[h][0], im = acc[h][1], dre = acc[h][2], dim = acc[h][3];
@@ -322,7 +381,8 @@ harvest_refine_kernel(const double* __restrict__ y_all, const long long* __restr
                       const double* __restrict__ base, const int* __restrict__ g_off,
                       const int* __restrict__ g_len, const int* __restrict__ nc_utt,
                       const long long* __restrict__ cand_off, int max_base, HarvestConst c, int n_utt,
-                      long long total_frames, double* __restrict__ cand, double* __restrict__ score) {
+                      long long total_frames, const double2* __restrict__ tw_c_base,
+                      double* __restrict__ cand, double* __restrict__ score) {
   const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wid >= total_frames) return;
@@ -339,7 +399,7 @@ harvest_refine_kernel(const double* __restrict__ y_all, const long long* __restr
   for (int s = 0; s < slots; ++s) {
     const double f0c = harvest_overlapped(base_u, max_base, nc, n_fr, k, s);
     double refined = 0.0, rscore = 0.0;
-    if (f0c > 0.0) harvest_refine_one(y, y_len, mean, c, k, f0c, lane, &refined, &rscore);
+    if (f0c > 0.0) harvest_refine_one(y, y_len, mean, c, k, f0c, lane, tw_c_base, &refined, &rscore);
     if (lane == 0) { cand[o + s] = refined; score[o + s] = rscore; }
   }
 }
@@ -903,7 +963,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
       KernelTimer kt("harvest_refine_kernel");
       const long long threads = gtot * 32;
       harvest_refine_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_y.p, d_yoff.p, d_ylen.p, d_mean.p, d_base.p, d_goff.p, d_glen.p,
-                                                                              d_nc.p, d_coff.p, max_base, c, n_utt, gtot, d_cand.p, d_score.p);
+                                                                              d_nc.p, d_coff.p, max_base, c, n_utt, gtot, ctxp->d_twiddle_c, d_cand.p, d_score.p);
       WB_LAUNCH_CHECK(); kt.stop();
     }
     harvest_unreliable_kernel<<<(unsigned)((ctot + 255) / 256), 256, 0, st>>>(d_cand.p, d_score.p, d_glen.p, d_nc.p, d_coff.p, n_utt, d_wfirst.p,
