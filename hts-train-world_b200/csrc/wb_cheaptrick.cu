@@ -87,10 +87,10 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
       __syncthreads();
       if (tid == 0) bulk_load_issue(aux, x + a0, (unsigned)n_stage * 8u, &mbar);
     }
-    const double ang_step = kPi * f0c / (1.5 * fs);
+    const double turn_step = f0c / (1.5 * fs);                   // angle step in units of pi
     double cs, sn, cs_step, sn_step;
-    sincos((double)(tid - hwl) * ang_step, &sn, &cs);
-    sincos((double)T * ang_step, &sn_step, &cs_step);
+    sincospi((double)(tid - hwl) * turn_step, &sn, &cs);
+    sincospi((double)T * turn_step, &sn_step, &cs_step);
     double sums[4] = {0.0, 0.0, 0.0, 0.0};            // Sww, Sw, Sx, Sd
     if (staged) mbar_wait(&mbar, 0);
     for (int i = tid; i < W; i += T) {

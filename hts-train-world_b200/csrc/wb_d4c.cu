@@ -54,14 +54,14 @@ __device__ __forceinline__ int windowed_waveform(const double* __restrict__ x, i
   const int hwl = d4c_hwl(ratio, fs, f0);
   const int W = 2 * hwl + 1;
   const int origin = matlab_round(add_rn(mul_rn(position, (double)fs), 0.001));
-  const double ang_step = kPi * 2.0 * f0 / (ratio * fs);
+  const double turn_step = 2.0 * f0 / (ratio * fs);          // angle step in units of pi (sincospi: no range reduction)
   double s[2] = {0.0, 0.0};
   // cos(a_i), a_i = (i - hwl) * ang_step, i = tid + j T: one sincos per thread for j = 0, then
   // the angle-addition recurrence with the block-uniform step T * ang_step (<= 16 steps, so
   // the accumulated rounding stays below 1e-15); cos(2a) = 2 cos^2(a) - 1.
   double cs0, sn0, cs_step, sn_step;
-  sincos((double)(tid - hwl) * ang_step, &sn0, &cs0);
-  sincos((double)T * ang_step, &sn_step, &cs_step);
+  sincospi((double)(tid - hwl) * turn_step, &sn0, &cs0);
+  sincospi((double)T * turn_step, &sn_step, &cs_step);
   auto window_at = [&](double cs) {
     return window_type == kHanning ? 0.5 * cs + 0.5 : 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);
   };
@@ -449,11 +449,11 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
     const int W = 2 * hwl4 + 1;
     {
       const int origin = matlab_round(add_rn(mul_rn(pos, (double)c.fs), 0.001));
-      const double ang_step = kPi * 2.0 * cur_f0 / (4.0 * c.fs);
+      const double turn_step = 2.0 * cur_f0 / (4.0 * c.fs);   // angle step in units of pi
       const uint32_t* __restrict__ rns = rn + (size_t)side * W4;
       double cs, sn, cs_step, sn_step;
-      sincos((double)(tid - hwl4) * ang_step, &sn, &cs);
-      sincos((double)T * ang_step, &sn_step, &cs_step);
+      sincospi((double)(tid - hwl4) * turn_step, &sn, &cs);
+      sincospi((double)T * turn_step, &sn_step, &cs_step);
       double sums[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
       const bool staged = st_ok;
       const double* xs = pw + (window_origin(side) - st_a0);

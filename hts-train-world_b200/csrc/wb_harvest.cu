@@ -250,11 +250,11 @@ __device__ __forceinline__ void harvest_refine_one(const double* __restrict__ y,
   // window phase a_n = 2 pi tmp_n / wlen, tmp_n = (basic_index + n - 1) / fs - pos (:447-452): linear
   // in n, so one sincos for n = lane and angle-addition steps of 32 samples; the neighbours needed
   // by the differentiated window are one more angle addition (+- one sample).
-  const double dstep = 2.0 * kPi / (wlen * fs);
+  const double dturn = 2.0 / (wlen * fs);                            // angle step in units of pi
   double cd, sd, c32, s32, cs, sn;
-  sincos(dstep, &sd, &cd);
-  sincos(32.0 * dstep, &s32, &c32);
-  sincos(2.0 * kPi * add_rn(div_rn(basic_index + lane - 1.0, fs), -pos) / wlen, &sn, &cs);
+  sincospi(dturn, &sd, &cd);
+  sincospi(32.0 * dturn, &s32, &c32);
+  sincospi(2.0 * add_rn(div_rn(basic_index + lane - 1.0, fs), -pos) / wlen, &sn, &cs);
   double acc[6][4];
 #pragma unroll
   for (int h = 0; h < 6; ++h) { acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.0; }
