@@ -76,65 +76,84 @@ __global__ void synth_pulse_bound_kernel(const double* __restrict__ f0_all, cons
   if (threadIdx.x == 0) bound[u] = static_cast<int>(v[0] * c.frame_period_s * 1.001) + 4;
 }
 
-// Time base: WRITE = false counts pulses, WRITE = true stores them (and counts).
-template <bool WRITE>
-__global__ void __launch_bounds__(1024)
-synth_timebase_kernel(const double* __restrict__ f0_all, const int* __restrict__ f_off,
-                      const int* __restrict__ f_len, const int* __restrict__ y_len_all, SynthConst c,
-                      int* __restrict__ pulse_count, const int* __restrict__ pulse_off,
-                      const int* __restrict__ pulse_cap, int* __restrict__ p_index, double* __restrict__ p_shift,
-                      unsigned char* __restrict__ p_vuv, int* __restrict__ p_utt) {
-  __shared__ double inc_s[1024];
-  __shared__ double tot_s[1024];
-  __shared__ long long wsum_s[32];
-  __shared__ int wcnt[32];
-  __shared__ double carry_phase, last_wrap_prev;
-  __shared__ int carry_cnt;
-  __shared__ double wrap_s[1024 + 1];
-  __shared__ unsigned char vuv_s[1024 + 1];
-  const int u = blockIdx.x;
+// ---- time base (GetTimeBase :287-320, GetPulseLocationsForTimeBase :242-285) -------------------------
+// Three steps.  Only the middle one is sequential, and it is reduced to the bare running sum:
+//   (1) synth_inc_kernel     per sample, fully parallel: interpolated f0 / vuv -> phase increment
+//   (2) synth_phase_kernel   one CTA per utterance: total_phase[i] = total_phase[i-1] + inc[i]
+//   (3) synth_pulses_kernel  per sample pair, fully parallel: wrap, pulse detection; ordered
+//                            compaction by count / scan / write over 1024-sample chunks
+// so the latency of an utterance is ~280 light chunk iterations instead of ~1100 heavy ones.
+constexpr int kTbChunk = 1024;
+
+__global__ void __launch_bounds__(256)
+synth_inc_kernel(const double* __restrict__ f0_all, const int* __restrict__ f_off,
+                 const int* __restrict__ f_len, const int* __restrict__ y_len_all,
+                 const long long* __restrict__ y_off, SynthConst c, double* __restrict__ inc_all,
+                 unsigned char* __restrict__ vuv_all) {
+  const int u = blockIdx.y;
+  const int y_len = y_len_all[u];
+  if (blockIdx.x * kTbChunk >= y_len) return;
   const double* __restrict__ f0 = f0_all + f_off[u];
   const int n_frames = f_len[u];
-  const int y_len = y_len_all[u];
-  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
   const int n_knots = n_frames + 1;
   const double fp = c.frame_period_s;
-  if (tid == 0) { carry_phase = 0.0; carry_cnt = 0; last_wrap_prev = 0.0; }
-  __syncthreads();
-  const int base_out = WRITE ? pulse_off[u] : 0;
-  // sample i needs wrap[i] and wrap[i+1]; process chunks of T samples, keeping the previous
-  // chunk's last sample for the pair that straddles the chunk boundary.
-  for (int base = 0; base < y_len; base += T) {
+  const size_t off = (size_t)y_off[u];
+  // four samples per thread: four independent chains of exact divisions in flight (a CTA per 256
+  // samples was bound by the latency of one chain and by the launch rate of a million tiny CTAs)
+#pragma unroll
+  for (int q = 0; q < kTbChunk / 256; ++q) {
+    const int i = blockIdx.x * kTbChunk + q * 256 + threadIdx.x;
+    if (i >= y_len) continue;
+    const double t = (double)i / (double)c.fs;                       // :227-228
+    const int k = uniform_segment(t, fp, n_knots);
+    const double x0 = mul_rn((double)(k - 1), fp), x1 = mul_rn((double)k, fp);
+    const double s = div_rn(add_rn(t, -x0), add_rn(x1, -x0));
+    const double fa = coarse_f0_at(f0, n_frames, k - 1, c.lowest_f0), fb = coarse_f0_at(f0, n_frames, k, c.lowest_f0);
+    const double va = coarse_vuv_at(f0, n_frames, k - 1, c.lowest_f0), vb = coarse_vuv_at(f0, n_frames, k, c.lowest_f0);
+    double fi = add_rn(fa, mul_rn(s, add_rn(fb, -fa)));
+    const double vi = add_rn(va, mul_rn(s, add_rn(vb, -va)));
+    const unsigned char vuv = vi > 0.5 ? 1 : 0;                       // :305-309
+    if (!vuv) fi = kDefaultF0;
+    inc_all[off + i] = div_rn(mul_rn(kTwoPi, fi), (double)c.fs);      // :250,253
+    vuv_all[off + i] = vuv;
+  }
+}
+
+// total_phase[i] = total_phase[i-1] + inc[i] (:252-253) must be accumulated in exactly the
+// reference's order: with fs / 500 Hz an integer (48 kHz, 16 kHz) every unvoiced pulse sits on a
+// wrap-around that is decided by the rounding of this running sum, so a tree-shaped floating-point
+// scan moves pulses by one sample.
+// Exact parallel form: while the running sum s stays inside one binade [2^e, 2^(e+1)], every
+// IEEE addition is  s <- s + rn_u(a)  with u = ulp = 2^(e-52) and rn_u = round-to-nearest
+// multiple of u (s is a multiple of u, so the rounding does not depend on s unless a / u ends
+// in exactly .5).  In units of u the chunk is then an INTEGER prefix sum -- associative, so a
+// warp-shuffle scan reproduces the sequential result bit for bit.  Chunks that see a tie, leave
+// the binade (the sum doubles ~20 times per utterance) or start from 0 take a sequential walk
+// by one thread (loads in batches of eight, only the dependent DADDs are serial).
+__global__ void __launch_bounds__(kTbChunk)
+synth_phase_kernel(const double* __restrict__ inc_all, const long long* __restrict__ y_off,
+                   const int* __restrict__ y_len_all, double* __restrict__ tot_all) {
+  __shared__ double inc_s[kTbChunk];
+  __shared__ double tot_s[kTbChunk];
+  // double-buffered by chunk parity: a chunk's values are read after its second barrier while the
+  // next chunk already writes the other set before its first one -- two barriers per chunk suffice
+  __shared__ long long wsum_s[2][32];     // inclusive warp totals, then (warp 0) exclusive warp offsets
+  __shared__ int wslow_s[2][32];
+  __shared__ long long chunk_total_s[2];
+  __shared__ int chunk_slow_s[2];
+  const int u = blockIdx.x;
+  const int y_len = y_len_all[u];
+  const size_t off = (size_t)y_off[u];
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
+  double carry = 0.0;                      // running sum before this chunk, the same in every thread
+  double inc_next = tid < y_len ? inc_all[off + tid] : 0.0;
+  int par = 0;
+  for (int base = 0; base < y_len; base += T, par ^= 1) {
     const int i = base + tid;
-    double inc = 0.0;
-    unsigned char vuv = 0;
-    if (i < y_len) {
-      const double t = (double)i / (double)c.fs;                       // :227-228
-      const int k = uniform_segment(t, fp, n_knots);
-      const double x0 = mul_rn((double)(k - 1), fp), x1 = mul_rn((double)k, fp);
-      const double s = div_rn(add_rn(t, -x0), add_rn(x1, -x0));
-      const double fa = coarse_f0_at(f0, n_frames, k - 1, c.lowest_f0), fb = coarse_f0_at(f0, n_frames, k, c.lowest_f0);
-      const double va = coarse_vuv_at(f0, n_frames, k - 1, c.lowest_f0), vb = coarse_vuv_at(f0, n_frames, k, c.lowest_f0);
-      double fi = add_rn(fa, mul_rn(s, add_rn(fb, -fa)));
-      const double vi = add_rn(va, mul_rn(s, add_rn(vb, -va)));
-      vuv = vi > 0.5 ? 1 : 0;                                           // :305-309
-      if (!vuv) fi = kDefaultF0;
-      inc = div_rn(mul_rn(kTwoPi, fi), (double)c.fs);                   // :250,253
-    }
-    // total_phase[i] = total_phase[i-1] + inc[i] (:252-253) must be accumulated in exactly the
-    // reference's order: with fs / 500 Hz an integer (48 kHz, 16 kHz) every unvoiced pulse sits
-    // on a wrap-around that is decided by the rounding of this running sum, so a tree-shaped
-    // scan moves pulses by one sample.  One thread walks the chunk sequentially (the loads
-    // are independent, only the DADD chain is serial: ~T x 8 cycles per chunk, all utterances
-    // in flight at once); everything else in this kernel stays parallel.
-    // Exact parallel form: while the running sum s stays inside one binade [2^e, 2^(e+1)], every
-    // IEEE addition is  s <- s + rn_u(a)  with u = ulp = 2^(e-52) and rn_u = round-to-nearest
-    // multiple of u (s is a multiple of u, so the rounding does not depend on s unless a / u ends
-    // in exactly .5).  In units of u the chunk is then an INTEGER prefix sum -- associative, so a
-    // warp-shuffle scan reproduces the sequential result bit for bit.  Chunks that see a tie, leave
-    // the binade (the sum doubles ~20 times per utterance) or start from 0 take the sequential walk.
-    inc_s[tid] = inc;
-    const double s0 = carry_phase;
+    const double inc = inc_next;
+    if (i + T < y_len) inc_next = inc_all[off + i + T];          // the next chunk's load is in flight during this one
+    else inc_next = 0.0;
+    const double s0 = carry;
     bool slow = !(s0 > 0.0);
     long long r = 0, s0int = 0;
     int e = 0;
@@ -146,81 +165,160 @@ synth_timebase_kernel(const double* __restrict__ f0_all, const int* __restrict__
       r = static_cast<long long>(rr);
       s0int = static_cast<long long>(scalbn(s0, 52 - e));
     }
-    long long pre = r;                                   // inclusive scan over the CTA
+    long long pre = r;                                   // inclusive scan inside the warp
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const long long t = __shfl_up_sync(0xffffffffu, pre, o);
       if (lane >= o) pre += t;
     }
-    if (lane == 31) wsum_s[wid] = pre;
+    const bool warp_slow = __any_sync(0xffffffffu, slow);
+    if (lane == 31) { wsum_s[par][wid] = pre; wslow_s[par][wid] = warp_slow; }
     __syncthreads();
-    for (int w = 0; w < wid; ++w) pre += wsum_s[w];
-    slow = slow || (s0int + pre > 9007199254740992LL) || (s0int + pre < 4503599627370496LL);   // left the binade
-    if (__syncthreads_or(slow)) {
+    if (wid == 0) {                                      // scan of the warp totals, chunk total, slow flag
+      const long long wv = lane < nw ? wsum_s[par][lane] : 0;
+      long long winc = wv;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+      }
+      const bool any_slow = __any_sync(0xffffffffu, lane < nw && wslow_s[par][lane] != 0);
+      wsum_s[par][lane] = winc - wv;                     // exclusive offset of warp `lane`
+      if (lane == 31) {
+        chunk_total_s[par] = winc;
+        // the sums are non-decreasing (inc >= 0): the chunk stays inside the binade iff its end does
+        chunk_slow_s[par] = any_slow || (s0int + winc > 9007199254740992LL) || (s0int + winc < 4503599627370496LL);
+      }
+    }
+    __syncthreads();
+    double total;
+    if (chunk_slow_s[par]) {                             // block-uniform
+      inc_s[tid] = inc;
+      __syncthreads();
       if (tid == 0) {
-        // batches of 8: the loads of a batch are issued together (input and output arrays are
-        // distinct, so nothing orders them behind the previous batch's stores) and only the
-        // eight dependent DADDs are serial
-        const double* __restrict__ in = inc_s;
-        double* __restrict__ outp = tot_s;
-        double run = carry_phase;
+        double run = carry;
         for (int q = 0; q < T; q += 8) {
           double v[8];
 #pragma unroll
-          for (int r8 = 0; r8 < 8; ++r8) v[r8] = in[q + r8];
+          for (int r8 = 0; r8 < 8; ++r8) v[r8] = inc_s[q + r8];
 #pragma unroll
           for (int r8 = 0; r8 < 8; ++r8) { run = add_rn(run, v[r8]); v[r8] = run; }
 #pragma unroll
-          for (int r8 = 0; r8 < 8; ++r8) outp[q + r8] = v[r8];
+          for (int r8 = 0; r8 < 8; ++r8) tot_s[q + r8] = v[r8];
         }
       }
+      __syncthreads();
+      total = tot_s[tid];
+      carry = tot_s[T - 1];
+      __syncthreads();                                   // tot_s / inc_s are rewritten by the next slow chunk
     } else {
-      tot_s[tid] = scalbn(static_cast<double>(s0int + pre), e - 52);
+      total = scalbn(static_cast<double>(s0int + pre + wsum_s[par][wid]), e - 52);
+      carry = scalbn(static_cast<double>(s0int + chunk_total_s[par]), e - 52);
     }
-    __syncthreads();
-    const double total = tot_s[tid];
-    const double wrap = fmod(total, kTwoPi);                            // :251,254
-    wrap_s[tid + 1] = wrap;
-    vuv_s[tid + 1] = vuv;
-    if (tid == 0) { wrap_s[0] = last_wrap_prev; }
-    __syncthreads();
-    // pair (j, j+1) with j = base + tid - 1: both wraps are now in shared memory
-    const int j = base + tid - 1;
-    bool is_pulse = false;
-    double y1 = 0.0, y2 = 0.0;
-    if (j >= 0 && j + 1 < y_len) {
-      y1 = wrap_s[tid];
-      y2 = wrap_s[tid + 1];
-      is_pulse = fabs(y2 - y1) > kPi;                                   // :255,259
+    if (i < y_len) tot_all[off + i] = total;
+  }
+}
+
+// fmod(x, 2 pi) for 0 <= x < 2^20, exact like the C library's: with n = floor(x / 2 pi) (possibly off
+// by one) the residual x - n * y is a multiple of ulp(y) = 2^-50 and smaller than 8 in magnitude,
+// so it is representable and the FMA delivers it without rounding; one exact +- y repairs n.
+__device__ __forceinline__ double fmod_two_pi(double x) {
+  if (!(x >= 0.0 && x < 1048576.0)) return fmod(x, kTwoPi);
+  const double n = floor(x * (1.0 / kTwoPi));
+  double r = fma(-n, kTwoPi, x);
+  if (r < 0.0) r += kTwoPi;
+  else if (r >= kTwoPi) r -= kTwoPi;
+  return r;
+}
+
+// Pulses: sample pair (j, j+1) holds one when the wrapped phase jumps by more than pi (:255-259).
+// One CTA per 1024-pair chunk of one utterance.  WRITE = false stores the chunk's pulse count;
+// after synth_pulse_scan_kernel turned the counts into exclusive offsets, WRITE = true stores the
+// pulses in sample order.
+template <bool WRITE>
+__global__ void __launch_bounds__(256)
+synth_pulses_kernel(const double* __restrict__ tot_all, const unsigned char* __restrict__ vuv_all,
+                    const long long* __restrict__ y_off, const int* __restrict__ y_len_all, SynthConst c,
+                    int n_chunks_max, int* __restrict__ counts, const int* __restrict__ pulse_off,
+                    const int* __restrict__ pulse_cap, int* __restrict__ p_index,
+                    double* __restrict__ p_shift, unsigned char* __restrict__ p_vuv, int* __restrict__ p_utt) {
+  __shared__ double first_s[8 + 1];         // wrapped phase of the first sample of every warp (+ of the next chunk)
+  __shared__ int wcnt[8];
+  const int u = blockIdx.y, chunk = blockIdx.x;
+  const int y_len = y_len_all[u];
+  const int j0 = chunk * kTbChunk;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (j0 + 1 >= y_len) {                                  // no pair starts in this chunk
+    if (!WRITE && tid == 0) counts[(size_t)u * n_chunks_max + chunk] = 0;
+    return;
+  }
+  const size_t off = (size_t)y_off[u];
+  const int jb = j0 + 4 * tid;                            // this thread: samples jb .. jb + 3 (and the pair into jb + 4)
+  double w[5];
+  if (jb + 3 < y_len) {                                   // 32-byte aligned: utterance offsets are even, jb is a multiple of 4
+    const double2 a = *reinterpret_cast<const double2*>(tot_all + off + jb);
+    const double2 b2 = *reinterpret_cast<const double2*>(tot_all + off + jb + 2);
+    w[0] = fmod_two_pi(a.x); w[1] = fmod_two_pi(a.y); w[2] = fmod_two_pi(b2.x); w[3] = fmod_two_pi(b2.y);   // :251,254
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[q] = jb + q < y_len ? fmod_two_pi(tot_all[off + jb + q]) : 0.0;
+  }
+  if (lane == 0) first_s[wid] = w[0];
+  if (tid == 255) first_s[8] = j0 + kTbChunk < y_len ? fmod_two_pi(tot_all[off + j0 + kTbChunk]) : 0.0;
+  w[4] = __shfl_down_sync(0xffffffffu, w[0], 1);
+  __syncthreads();
+  if (lane == 31) w[4] = first_s[wid + 1];
+  unsigned mask = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (jb + q + 1 < y_len && fabs(w[q + 1] - w[q]) > kPi) mask |= 1u << q;                                  // :255,259
+  const int cnt = __popc(mask);
+  int inc_scan = cnt;                                     // inclusive scan of the per-thread counts inside the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc_scan, o);
+    if (lane >= o) inc_scan += t;
+  }
+  if (lane == 31) wcnt[wid] = inc_scan;
+  __syncthreads();
+  if (!WRITE) {
+    if (tid == 0) {
+      int tot = 0;
+#pragma unroll
+      for (int wq = 0; wq < 8; ++wq) tot += wcnt[wq];
+      counts[(size_t)u * n_chunks_max + chunk] = tot;
     }
-    // compaction
-    const unsigned bal = __ballot_sync(0xffffffffu, is_pulse);
-    if (lane == 0) wcnt[wid] = __popc(bal);
-    __syncthreads();
-    int before = carry_cnt;
-    for (int w = 0; w < wid; ++w) before += wcnt[w];
-    const int pos = before + __popc(bal & ((1u << lane) - 1u));
-    if (WRITE && is_pulse && pos < pulse_cap[u]) {
-      const int o = base_out + pos;
+    return;
+  }
+  if (mask == 0) return;
+  int pos = counts[(size_t)u * n_chunks_max + chunk] + (inc_scan - cnt);
+  for (int wq = 0; wq < wid; ++wq) pos += wcnt[wq];
+  const int cap = pulse_cap[u], base_out = pulse_off[u];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (!((mask >> q) & 1u)) continue;
+    if (pos < cap) {
+      const int o = base_out + pos, j = jb + q;
       p_index[o] = j;
-      const double yy1 = y1 - kTwoPi;                                   // :271-274
-      const double xx = -yy1 / (y2 - yy1);
+      const double yy1 = w[q] - kTwoPi;                                   // :271-274
+      const double xx = -yy1 / (w[q + 1] - yy1);
       p_shift[o] = xx / c.fs;
-      p_vuv[o] = vuv_s[tid];                                           // vuv of sample j
+      p_vuv[o] = vuv_all[off + j];
       p_utt[o] = u;
     }
-    __syncthreads();
-    if (tid == T - 1) {
-      carry_phase = total;     // == tot_s[T-1], the running sum after this chunk
-      last_wrap_prev = wrap;
-      int tot = 0;
-      for (int w = 0; w < nw; ++w) tot += wcnt[w];
-      carry_cnt += tot;
-    }
-    if (tid == 0) vuv_s[0] = vuv_s[T];   // vuv of the chunk's last sample, for the straddling pair
-    __syncthreads();
+    ++pos;
   }
-  if (tid == 0) pulse_count[u] = carry_cnt;
+}
+
+// one thread per utterance: exclusive scan of the chunk counts in place, total -> pulse_count
+__global__ void synth_pulse_scan_kernel(int* __restrict__ counts, int n_utt, int n_chunks_max,
+                                        int* __restrict__ pulse_count) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_utt) return;
+  int* cu = counts + (size_t)u * n_chunks_max;
+  int acc = 0;
+  for (int k = 0; k < n_chunks_max; ++k) { const int v = cu[k]; cu[k] = acc; acc += v; }
+  pulse_count[u] = acc;
 }
 
 // ---- pulse classification -------------------------------------------------------------------
@@ -582,14 +680,30 @@ bool synthesis_run(Batch* b, const int* y_len) {
   if (!p_index.alloc(total_p) || !p_utt.alloc(total_p) || !p_shift.alloc(total_p) || !p_vuv.alloc(total_p) || !d_rem.alloc(N)) return false;
   WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_poff.p, h_poff.data(), n_utt * sizeof(int), cudaMemcpyHostToDevice, st), false);
   WB_CUDA_OR_RETURN(cudaMemsetAsync(p_utt.p, 0xff, (size_t)total_p * sizeof(int), st), false);   // -1 = unused slot
-  KernelTimer kt2("synth_timebase_kernel");
-  // one CTA walks one utterance chunk by chunk (the phase accumulation is sequential across chunks):
-  // the number of chunks sets the latency of an utterance, so the chunks are as wide as the batch
-  // allows without queueing CTAs behind each other (measured: 1024 threads lose at 1 132 utterances)
-  const int tb_threads = n_utt <= 2 * ctxp->sm_count ? 1024 : n_utt <= 4 * ctxp->sm_count ? 512 : 256;
-  synth_timebase_kernel<true><<<n_utt, tb_threads, 0, st>>>(b->f0.p, b->f_off.p, b->f_len.p, b->y_len.p, c, d_cnt.p, d_poff.p, d_cap.p,
-                                                     p_index.p, p_shift.p, p_vuv.p, p_utt.p);
-  WB_LAUNCH_CHECK(); kt2.stop();
+  {
+    const int n_chunks_max = (max_y + kTbChunk - 1) / kTbChunk + 1;
+    DevBuf<double> d_inc, d_tot;
+    DevBuf<unsigned char> d_vuv;
+    DevBuf<int> d_counts;
+    if (!d_inc.alloc((size_t)b->total_y + 1) || !d_tot.alloc((size_t)b->total_y + 1) || !d_vuv.alloc((size_t)b->total_y + 1) ||
+        !d_counts.alloc((size_t)n_utt * n_chunks_max))
+      return false;
+    KernelTimer kt2("synth_timebase_kernel");               // all five launches of the time base
+    synth_inc_kernel<<<dim3((max_y + kTbChunk - 1) / kTbChunk, n_utt), 256, 0, st>>>(b->f0.p, b->f_off.p, b->f_len.p, b->y_len.p, b->y_off.p, c,
+                                                                      d_inc.p, d_vuv.p);
+    WB_LAUNCH_CHECK();
+    synth_phase_kernel<<<n_utt, kTbChunk, 0, st>>>(d_inc.p, b->y_off.p, b->y_len.p, d_tot.p);
+    WB_LAUNCH_CHECK();
+    synth_pulses_kernel<false><<<dim3(n_chunks_max, n_utt), 256, 0, st>>>(d_tot.p, d_vuv.p, b->y_off.p, b->y_len.p, c, n_chunks_max,
+        d_counts.p, d_poff.p, d_cap.p, p_index.p, p_shift.p, p_vuv.p, p_utt.p);
+    WB_LAUNCH_CHECK();
+    synth_pulse_scan_kernel<<<(n_utt + 127) / 128, 128, 0, st>>>(d_counts.p, n_utt, n_chunks_max, d_cnt.p);
+    WB_LAUNCH_CHECK();
+    synth_pulses_kernel<true><<<dim3(n_chunks_max, n_utt), 256, 0, st>>>(d_tot.p, d_vuv.p, b->y_off.p, b->y_len.p, c, n_chunks_max,
+        d_counts.p, d_poff.p, d_cap.p, p_index.p, p_shift.p, p_vuv.p, p_utt.p);
+    WB_LAUNCH_CHECK(); kt2.stop();
+    // the scratch is released in stream order when this scope ends (stream-ordered pool)
+  }
   // GetDCRemover (:322-334)
   std::vector<double> rem(N);
   double dc_component = 0.0;
