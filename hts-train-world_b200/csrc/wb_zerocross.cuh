@@ -96,11 +96,27 @@ zc_kernel(const double* __restrict__ F, const long long* __restrict__ F_off,
     if (WRITE) lpre_s[k][tid] = pre;
   }
   __syncthreads();
-  if (tid < 4) {                                     // exclusive prefix over (round, warp), in place
-    int acc = WRITE ? counts[((size_t)ub * 4 + tid) * n_chunks_max + chunk] : 0;
-    for (int k = 0; k < kRounds; ++k)
-      for (int w = 0; w < 8; ++w) { const int v = wcnt[k][tid][w]; wcnt[k][tid][w] = acc; acc += v; }
-    if (!WRITE) counts[((size_t)ub * 4 + tid) * n_chunks_max + chunk] = acc;
+  {
+    // exclusive prefix over (round, warp) of every type, in place: the 4 x 64 counters are one per
+    // thread (type = tid / 64, entry = round * 8 + warp), scanned with shuffles inside each warp and
+    // joined across the two warps of a type -- four threads walking 64 entries each kept the other
+    // 252 waiting for ~2000 cycles per CTA
+    static_assert(kRounds * 8 == 64, "one counter per thread of a 256-thread CTA");
+    __shared__ int half_tot[4];
+    const int ty = tid >> 6, idx = tid & 63;
+    const int v = wcnt[idx >> 3][ty][idx & 7];
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (idx == 31) half_tot[ty] = inc;
+    __syncthreads();
+    const int first_half = half_tot[ty];
+    const int base = WRITE ? counts[((size_t)ub * 4 + ty) * n_chunks_max + chunk] : 0;
+    wcnt[idx >> 3][ty][idx & 7] = base + (inc - v) + (idx >= 32 ? first_half : 0);
+    if (!WRITE && idx == 63) counts[((size_t)ub * 4 + ty) * n_chunks_max + chunk] = inc + first_half;
   }
   if (!WRITE) return;
   __syncthreads();
