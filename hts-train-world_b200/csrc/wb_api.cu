@@ -24,9 +24,12 @@ struct wb200_batch {
   // recorded on the download stream after the asynchronous result copies of this batch: the next
   // pass over the same batch object must not overwrite lf0 / mgc / bap / the 16-bit staging before
   // those copies have read them (a caller that pipelines batches back to back never calls wb200_sync)
-  cudaEvent_t download_done = nullptr;
-  bool download_pending = false;
-  ~wb200_batch() { if (upload_done) cudaEventDestroy(upload_done); if (download_done) cudaEventDestroy(download_done); }
+  cudaEvent_t download_done[2] = {nullptr, nullptr};     // [0] coded features (lf0 / mgc / bap), [1] 16-bit waveform staging
+  bool download_pending[2] = {false, false};
+  ~wb200_batch() {
+    if (upload_done) cudaEventDestroy(upload_done);
+    for (cudaEvent_t e : download_done) if (e) cudaEventDestroy(e);
+  }
 };
 
 namespace {
@@ -39,20 +42,19 @@ bool ensure_copy_streams(Context* c) {
   }
   return true;
 }
-bool wait_downloads(wb200_batch* h) {
-  if (!h->download_pending) return true;
-  h->download_pending = false;
-  return WB_CUDA(cudaStreamWaitEvent(ctx()->stream, h->download_done, 0));
+enum { kDlCoded = 0, kDlWave = 1 };
+bool wait_downloads(wb200_batch* h, int which) {        // the buffer `which` is about to be rewritten
+  if (!h->download_pending[which]) return true;
+  h->download_pending[which] = false;
+  return WB_CUDA(cudaStreamWaitEvent(ctx()->stream, h->download_done[which], 0));
 }
-bool mark_downloads(wb200_batch* h) {
-  if (!h->download_done && !WB_CUDA(cudaEventCreateWithFlags(&h->download_done, cudaEventDisableTiming))) return false;
-  h->download_pending = true;
-  return WB_CUDA(cudaEventRecord(h->download_done, ctx()->copy_stream));
+bool mark_downloads(wb200_batch* h, int which) {
+  if (!h->download_done[which] && !WB_CUDA(cudaEventCreateWithFlags(&h->download_done[which], cudaEventDisableTiming))) return false;
+  h->download_pending[which] = true;
+  return WB_CUDA(cudaEventRecord(h->download_done[which], ctx()->copy_stream));
 }
-// every stage that reads the samples first waits (on the device) for an asynchronous upload and
-// for result copies of the previous pass over this batch that are still in flight
+// every stage that reads the samples first waits (on the device) for an asynchronous upload
 bool wait_upload(wb200_batch* h) {
-  if (!wait_downloads(h)) return false;
   if (!h->upload_pending) return true;
   h->upload_pending = false;
   return WB_CUDA(cudaStreamWaitEvent(ctx()->stream, h->upload_done, 0));
@@ -613,6 +615,7 @@ int wb200_batch_get_y_pcm16(wb200_batch* h, int16_t* out) {
   if (!h->pcm_out.alloc((size_t)n + 1) || !d_cum.alloc(b.n_utt)) return 1;
   if (b.n_utt == 0 || n == 0) return 0;
   if (!WB_CUDA(cudaMemcpyAsync(d_cum.p, cum.data(), b.n_utt * sizeof(long long), cudaMemcpyHostToDevice, c->stream))) return 1;
+  if (!wait_downloads(h, kDlWave)) return 1;
   y_to_pcm16_kernel<<<dim3(64, b.n_utt), 256, 0, c->stream>>>(b.y.p, b.y_off.p, d_cum.p, b.y_len.p, h->pcm_out.p);
   WB_LAUNCH_CHECK();
   return (WB_CUDA(cudaMemcpyAsync(out, h->pcm_out.p, (size_t)n * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream)) &&
@@ -636,12 +639,12 @@ int wb200_batch_get_y_pcm16_async(wb200_batch* h, int16_t* out) {
         !WB_CUDA(cudaStreamSynchronize(c->stream)))
       return 1;
   }
-  if (!wait_downloads(h)) return 1;
+  if (!wait_downloads(h, kDlWave)) return 1;           // the previous pass's copy may still read pcm_out
   y_to_pcm16_kernel<<<dim3(64, b.n_utt), 256, 0, c->stream>>>(b.y.p, b.y_off.p, h->out_off.p, b.y_len.p, h->pcm_out.p);
   WB_LAUNCH_CHECK();
   return (WB_CUDA(cudaEventRecord(c->copy_event, c->stream)) && WB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_event, 0)) &&
           WB_CUDA(cudaMemcpyAsync(out, h->pcm_out.p, (size_t)n * sizeof(int16_t), cudaMemcpyDeviceToHost, c->copy_stream)) &&
-          mark_downloads(h)) ? 0 : 1;
+          mark_downloads(h, kDlWave)) ? 0 : 1;
 }
 void* wb200_batch_device_ptr(wb200_batch* h, const char* which) {
   Batch& b = h->b;
@@ -655,7 +658,7 @@ void* wb200_batch_device_ptr(wb200_batch* h, const char* which) {
   return nullptr;
 }
 int wb200_batch_code(wb200_batch* h, int mgc_dim, int bap_dim) {
-  if (!ctx() || !wait_downloads(h)) return 1;
+  if (!ctx() || !wait_downloads(h, kDlCoded)) return 1;   // the previous pass's copies may still read lf0 / mgc / bap
   return batch_code_features(&h->b, mgc_dim, bap_dim) ? 0 : 1;
 }
 int wb200_batch_get_coded(wb200_batch* h, float* lf0, float* mgc, float* bap) {
@@ -681,7 +684,7 @@ int wb200_batch_get_coded_async(wb200_batch* h, float* lf0, float* mgc, float* b
   if (ok && lf0) ok = WB_CUDA(cudaMemcpyAsync(lf0, b.lf0.p, F * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
   if (ok && mgc) ok = WB_CUDA(cudaMemcpyAsync(mgc, b.mgc.p, F * b.mgc_dim * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
   if (ok && bap) ok = WB_CUDA(cudaMemcpyAsync(bap, b.bap.p, F * b.bap_dim * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
-  return ok && mark_downloads(h) ? 0 : 1;
+  return ok && mark_downloads(h, kDlCoded) ? 0 : 1;
 }
 __global__ void mgc_unscale_kernel(const float* __restrict__ mgc, long long n, int ndim, double* __restrict__ out) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
