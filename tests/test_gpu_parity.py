@@ -408,3 +408,54 @@ def test_synthesis_from_float32_parameter_files(wb, reference_lib):
         got = y[off[u]:off[u] + ln[u]]
         assert len(got) == len(want)
         assert M.snr_db(want, got) >= 60.0
+
+
+@pytest.mark.gpu
+def test_back_to_back_passes_with_asynchronous_copies(wb):
+    """A long corpus run re-uses its batch objects without ever calling wb200_sync(): uploads on the
+    upload stream, result copies on the download stream, stages on the library stream.  Three passes
+    over the same batch object (different inputs in turn) must deliver, in double-buffered pinned host
+    memory, exactly what the synchronous calls deliver -- i.e. a pass never overwrites a buffer that an
+    in-flight copy of the previous pass still reads."""
+    import torch
+    from hts_train_world_b200 import signals
+    fs = 16000
+    sets = []
+    for seed in (21, 22):
+        pcm = [signals.make_utterance(seed + 10 * k, fs, duration=0.7)[0] for k in range(2)]
+        sets.append(torch.cat(pcm).pin_memory())
+    lengths = [len(sets[0]) // 2, len(sets[0]) - len(sets[0]) // 2]
+    assert len(sets[1]) == len(sets[0])
+    c = wb.Corpus(fs, lengths)
+    F = c.total_frames
+    want = []
+    for s in sets:                                     # synchronous reference results
+        c.upload_pcm16(s.numpy())
+        c.analyze()
+        c.code(50, 24)
+        c.synthesis()
+        want.append((c.coded(), c.y_pcm16().copy()))
+    n_y = len(want[0][1])
+    bufs = [dict(lf0=torch.empty(F, dtype=torch.float32).pin_memory(), mgc=torch.empty((F, 50), dtype=torch.float32).pin_memory(),
+                 bap=torch.empty((F, 24), dtype=torch.float32).pin_memory(), y=torch.empty(n_y, dtype=torch.int16).pin_memory())
+            for _ in range(2)]
+    order = [0, 1, 0, 1]
+    c.upload_pcm16_async(sets[order[0]])
+    for it, k in enumerate(order):
+        c.analyze()
+        b = bufs[it % 2]
+        c.code(50, 24)
+        c.coded_async(b["lf0"], b["mgc"], b["bap"])
+        c.synthesis()
+        c.y_pcm16_async(b["y"])
+        if it + 1 < len(order):
+            c.upload_pcm16_async(sets[order[it + 1]])  # ordered behind the stages queued so far
+    wb.sync()
+    for it in (len(order) - 2, len(order) - 1):        # the last two passes own the two buffer sets
+        b, ((lf0, mgc, bap), y) = bufs[it % 2], want[order[it]]
+        assert np.array_equal(b["lf0"].numpy(), lf0), it
+        assert np.array_equal(b["mgc"].numpy(), mgc), it
+        assert np.array_equal(b["bap"].numpy(), bap), it
+        # the overlap-add uses floating-point atomics: the last bit of y depends on their order, which can
+        # move a truncated 16-bit sample by one step
+        assert np.max(np.abs(b["y"].numpy().astype(np.int32) - y.astype(np.int32))) <= 1, it
