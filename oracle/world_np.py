@@ -2,7 +2,8 @@
 externs/WORLD_v2 (W/ below), written from the reference's sources as an independent second
 oracle.  Only tests/ may import this module; the product never does.
 
-Pinned: tests/test_oracle_np.py checks every function here against the golden vectors in
+Pinned: tests/test_oracle_np.py checks every function here (Dio, StoneMask, CheapTrick, D4C,
+Synthesis, codec; Harvest is checked against the compiled reference only) against the golden vectors in
 tests/golden/ (produced by the compiled, unmodified reference) — F0 within 1e-6 relative,
 spectral envelope within 1e-6 dB, aperiodicity within 1e-7, resynthesis > 100 dB SNR; the
 differences are numpy's FFT versus the reference's Ooura FFT.  The strongest oracle remains
@@ -144,6 +145,128 @@ def cheaptrick(x, fs, t, f0, q1=-0.15, fft_size=None):
         env = np.fft.irfft(cep * lifter * comp, N)[:half + 1]      # irfft includes the 1/N of :49
         out[i] = np.exp(env)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Dio (W/src/dio.cpp), speed = 1 (the tool's setting; decimation is checked against the compiled
+# reference only)
+# ---------------------------------------------------------------------------------------------
+kMaximumValue = 100000.0
+kLog2 = 0.69314718055994529
+
+
+def _low_cut_filter(N, fft_size):
+    """DesignLowCutFilter :40-53, including its in-place shifts (the second one reads past N into
+    the zeroed area)."""
+    f = np.zeros(fft_size)
+    i = np.arange(1, N + 1)
+    f[:N] = 0.5 - 0.5 * np.cos(i * 2.0 * kPi / (N + 1))
+    f[:N] = -f[:N] / f[:N].sum()
+    h = (N - 1) // 2
+    f[fft_size - h:fft_size] = f[:h]
+    f[:N] = f[h:h + N].copy()          # every read index is above its write index: same as the loop
+    f[0] += 1.0
+    return f
+
+
+def _zero_crossing_engine(sig, n, fs):
+    """ZeroCrossingEngine :357-393 on sig[0..n): (interval_locations, intervals), empty if < 2 edges."""
+    s = sig[:n]
+    edges = np.nonzero((0.0 < s[:-1]) & (s[1:] <= 0.0))[0] + 1
+    if len(edges) < 2:
+        return np.zeros(0), np.zeros(0)
+    fine = edges - s[edges - 1] / (s[edges] - s[edges - 1])
+    return (fine[:-1] + fine[1:]) / 2.0 / fs, fs / (fine[1:] - fine[:-1])
+
+
+def _dio_band(Y, fft_size, y_length, fs, boundary_f0, f0_floor, f0_ceil, t):
+    """GetF0CandidateFromRawEvent :523-541 -> (candidate, score) of one band."""
+    hal = matlab_round(fs / boundary_f0 / 2.0)
+    lpf = np.zeros(fft_size)                                              # GetFilteredSignal :296-343
+    lpf[:4 * hal] = nuttall(4 * hal)
+    conv = np.fft.irfft(Y * np.fft.rfft(lpf), fft_size) * fft_size       # c2r is unnormalised
+    sig = conv[2 * hal:2 * hal + y_length].copy()
+    sets = []                                                             # GetFourZeroCrossingIntervals :402-435
+    sets.append(_zero_crossing_engine(sig, y_length, fs))
+    sig = -sig
+    sets.append(_zero_crossing_engine(sig, y_length, fs))
+    sig[:y_length - 1] = sig[:y_length - 1] - sig[1:y_length]
+    sets.append(_zero_crossing_engine(sig, y_length - 1, fs))
+    sig[:y_length - 1] = -sig[:y_length - 1]
+    sets.append(_zero_crossing_engine(sig, y_length - 1, fs))
+    F = len(t)
+    if any(len(v) - 2 <= 0 for _, v in sets):                             # CheckEvent :484-493
+        return np.zeros(F), np.full(F, kMaximumValue)
+    ip = np.array([interp1(loc, val, t) for loc, val in sets])            # :498-512
+    cand = (ip[0] + ip[1] + ip[2] + ip[3]) / 4.0                          # GetF0CandidateContourSub :441-465
+    score = np.sqrt(((ip - cand) ** 2).sum(axis=0) / 3.0)
+    bad = (cand > boundary_f0) | (cand < boundary_f0 / 2.0) | (cand > f0_ceil) | (cand < f0_floor)
+    cand[bad] = 0.0
+    score[bad] = kMaximumValue
+    return cand, score
+
+
+def _select_best_f0(cur, past, cands, j, allowed):                       # SelectBestF0 :190-209
+    ref = (cur * 3.0 - past) / 2.0
+    err = np.abs(ref - cands[:, j])
+    best = cands[int(np.argmin(err)), j]                                   # first minimum wins
+    if abs(1.0 - best / ref) > allowed:
+        return 0.0
+    return best
+
+
+def dio(x, fs, frame_period=5.0, f0_floor=71.0, f0_ceil=800.0, channels_in_octave=2.0, allowed_range=0.1):
+    """Dio :642-647 / DioGeneralBody :578-634 with speed 1 -> (temporal_positions, f0)."""
+    x = np.asarray(x, float)
+    x_length = len(x)
+    nb = 1 + int(math.log(f0_ceil / f0_floor) / kLog2 * channels_in_octave)           # :582-586
+    boundary = [f0_floor * 2.0 ** ((i + 1) / channels_in_octave) for i in range(nb)]
+    y_length = 1 + x_length                                                            # :590 (speed 1)
+    fft_size = _pow2_above(y_length + 4 * int(1.0 + fs / boundary[0] / 2.0))          # :592-593
+    y = np.zeros(fft_size)                                                             # GetSpectrumForEstimation :60-106
+    y[:x_length] = x
+    y[:y_length] -= y[:y_length].sum() / y_length
+    Y = np.fft.rfft(y) * np.fft.rfft(_low_cut_filter(matlab_round(fs / 50.0) * 2 + 1, fft_size))
+    F = int(1000.0 * x_length / fs / frame_period) + 1                                 # GetSamplesForDIO :638-640
+    t = np.arange(F) * frame_period / 1000.0
+    cands, scores = np.zeros((nb, F)), np.zeros((nb, F))
+    for b in range(nb):                                                                # GetF0CandidatesAndScores :549-572
+        c, sc = _dio_band(Y, fft_size, y_length, float(fs), boundary[b], f0_floor, f0_ceil, t)
+        cands[b], scores[b] = c, sc / (c + kMySafeGuardMinimum)
+    best = cands[np.argmin(scores, axis=0), np.arange(F)]                              # GetBestF0Contour :112-126 (first minimum)
+    # FixF0Contour :259-289
+    vrm = int(0.5 + 1000.0 / frame_period / f0_floor) * 2 + 1
+    f0 = np.zeros(F)
+    if F <= vrm:
+        return t, f0                                 # the reference returns without writing f0 at all
+    base = np.zeros(F)                                                                 # FixStep1 :132-150
+    base[vrm:F - vrm] = best[vrm:F - vrm]
+    s1 = np.zeros(F)
+    i = np.arange(vrm, F)
+    ok = np.abs((base[i] - base[i - 1]) / (kMySafeGuardMinimum + base[i])) < allowed_range
+    s1[i] = np.where(ok, base[i], 0.0)
+    s2 = s1.copy()                                                                     # FixStep2 :156-169
+    center = (vrm - 1) // 2
+    for i in range(center, F - center):
+        if (s1[i - center:i + center + 1] == 0).any():
+            s2[i] = 0.0
+    neg = [i - 1 for i in range(1, F) if s2[i] == 0 and s2[i - 1] != 0]                # GetNumberOfVoicedSections :174-184
+    pos = [i for i in range(1, F) if s2[i - 1] == 0 and s2[i] != 0]
+    s3 = s2.copy()                                                                     # FixStep3 :215-231
+    for k, start in enumerate(neg):
+        limit = F - 1 if k == len(neg) - 1 else neg[k + 1]
+        for j in range(start, limit):
+            s3[j + 1] = _select_best_f0(s3[j], s3[j - 1], cands, j + 1, allowed_range)
+            if s3[j + 1] == 0:
+                break
+    s4 = s3.copy()                                                                     # FixStep4 :237-253
+    for k in range(len(pos) - 1, -1, -1):
+        limit = 1 if k == 0 else pos[k - 1]
+        for j in range(pos[k], limit, -1):
+            s4[j - 1] = _select_best_f0(s4[j], s4[j + 1], cands, j - 1, allowed_range)
+            if s4[j - 1] == 0:
+                break
+    return t, s4
 
 
 # ---------------------------------------------------------------------------------------------

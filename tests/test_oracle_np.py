@@ -33,6 +33,23 @@ def test_interp1_extrapolates_like_the_reference(wnp):
     assert np.allclose(wnp.interp1(x, y, [-1.0, 0.0, 0.5, 1.0, 2.0, 3.0, 4.0]), [-10, 0, 5, 10, 20, 30, 40])
 
 
+@pytest.mark.parametrize("name", ["arctic_a0001", "vaiueo2d", "synthetic48k_u7", "synthetic16k_u11"])
+def test_dio(wnp, name):
+    """The numpy restatement of Dio (W/src/dio.cpp, speed 1) against the golden raw F0 of the compiled
+    reference: every voicing decision equal, F0 to FFT rounding (numpy's FFT vs Ooura's)."""
+    g = load_golden(name)
+    t, f0 = wnp.dio(_x(g), int(g["fs"]))
+    assert np.array_equal(t, g["t"])
+    assert M.vuv_agreement(g["f0_raw"], f0) == 1.0
+    assert M.f0_rel_error(g["f0_raw"], f0) <= 1e-9
+
+
+def test_dio_short_input_is_left_unwritten(wnp):
+    # FixF0Contour returns before writing f0 when there are <= 7 frames (W/src/dio.cpp:266); the oracle yields zeros
+    t, f0 = wnp.dio(np.sin(np.arange(400) * 0.1), 16000)
+    assert len(t) == 6 and not f0.any()
+
+
 @pytest.mark.parametrize("name", ["vaiueo2d", "synthetic16k_u11"])
 def test_stonemask_and_cheaptrick(wnp, name):
     g = load_golden(name)
