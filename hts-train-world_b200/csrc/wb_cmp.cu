@@ -73,17 +73,25 @@ cmp_compose_kernel(const CmpSegment* __restrict__ segs, int n_segs, const int* _
   }
 }
 
-// per-column {count, sum, sum of squares} of a [frames][ndim] float matrix (all columns in one launch)
-__global__ void cmp_stats_kernel(const float* __restrict__ m, int n_frames, int ndim, double* __restrict__ out3) {
-  __shared__ double red[96];
-  const int d = blockIdx.y;
-  double v[3] = {0.0, 0.0, 0.0};
-  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n_frames; f += gridDim.x * blockDim.x) {
-    const double x = m[(size_t)f * ndim + d];
-    v[0] += 1.0; v[1] += x; v[2] += x * x;
+// per-column {count, sum, sum of squares} of a [frames][ndim] float matrix, read as one contiguous
+// stream: the CTA has R * ndim threads and the grid stride is a multiple of ndim, so a thread always
+// meets the same column; the R threads of a column are joined in shared memory.
+__global__ void __launch_bounds__(1024)
+cmp_stats_kernel(const float* __restrict__ m, long long n_elems, int ndim, double* __restrict__ out3) {
+  extern __shared__ double sh[];                    // [3][blockDim.x]
+  const int T = blockDim.x, tid = threadIdx.x;      // T % ndim == 0
+  double c = 0.0, s = 0.0, q = 0.0;
+  for (long long i = blockIdx.x * (long long)T + tid; i < n_elems; i += (long long)gridDim.x * T) {
+    const double x = m[i];
+    c += 1.0; s += x; q += x * x;
   }
-  block_sum<3>(v, red);
-  if (threadIdx.x == 0) { atomicAdd(&out3[d * 3], v[0]); atomicAdd(&out3[d * 3 + 1], v[1]); atomicAdd(&out3[d * 3 + 2], v[2]); }
+  sh[tid] = c; sh[T + tid] = s; sh[2 * T + tid] = q;
+  __syncthreads();
+  if (tid < ndim) {
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int t = tid; t < T; t += ndim) { v[0] += sh[t]; v[1] += sh[T + t]; v[2] += sh[2 * T + t]; }
+    atomicAdd(&out3[tid * 3], v[0]); atomicAdd(&out3[tid * 3 + 1], v[1]); atomicAdd(&out3[tid * 3 + 2], v[2]);
+  }
 }
 
 }  // namespace
@@ -157,7 +165,9 @@ bool batch_cmp_stats(Batch* b, double* h_out) {   // [cmp_dim][3]
   cudaStream_t st = c->stream;
   WB_CUDA_OR_RETURN(cudaMemsetAsync(d.p, 0, (size_t)nd * 3 * sizeof(double), st), false);
   if (F > 0) {
-    cmp_stats_kernel<<<dim3(32, nd), 256, 0, st>>>(b->cmp.p, F, nd, d.p);
+    if (nd > 1024) { set_error("cmp stats: %d columns (<= 1024 supported)", nd); return false; }
+    const int threads = nd * (256 / nd > 0 ? 256 / nd : 1);
+    cmp_stats_kernel<<<c->sm_count * 4, threads, 3 * threads * sizeof(double), st>>>(b->cmp.p, (long long)F * nd, nd, d.p);
     WB_LAUNCH_CHECK();
   }
   WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_out, d.p, (size_t)nd * 3 * sizeof(double), cudaMemcpyDeviceToHost, st), false);
