@@ -60,7 +60,10 @@ def build(force=False, verbose=False):
             for _ in ex.map(lambda j: _compile(*j), jobs):
                 pass
     if jobs or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs
+        # -Bsymbolic-functions: calls between the library's own exported functions (the helpers of
+        # wb_compat.cu call interp1Q, fft_execute, ...) bind inside the library, so a host program
+        # that happens to define a function of the same name cannot interpose them
+        cmd = [NVCC, "-shared", "-Xlinker", "-Bsymbolic-functions", "-o", LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stderr[-4000:])

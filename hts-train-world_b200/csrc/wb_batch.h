@@ -89,6 +89,9 @@ bool batch_feature_stats(Batch* b, double* h_out);
 bool decimate_run(const Batch* b, int r, const std::vector<int>& want_len, DevBuf<double>* y,
                   DevBuf<long long>* y_off, DevBuf<int>* y_len, std::vector<int>* out_len);
 
+// a[3], b[2] of the 3rd-order decimation filter for ratio r = 2..12 (W/src/matlabfunctions.cpp:29-112)
+bool decimate_filter_coefficients(int r, double* a, double* b);
+
 // generic helper: exclusive prefix sum of counts within each utterance's frame range.
 // out[f] = sum of counts[g] for g in [f_off[u], f); totals[u] = sum over the utterance.
 bool segmented_exclusive_scan(const long long* counts, const int* f_off, const int* f_len,

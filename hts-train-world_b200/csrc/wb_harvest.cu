@@ -746,6 +746,9 @@ bool build_harvest_bank(double actual_fs, double f0_floor, double f0_ceil, Harve
 
 }  // namespace
 
+// the filter table above for the host-side decimate() of wb_compat.cu
+bool decimate_filter_coefficients(int r, double* a, double* b) { return decimate_coefficients(r, a, b); }
+
 // decimate() of W/src/matlabfunctions.cpp:184-210 for every utterance of the batch (no edge
 // extension: lag = 0), as Dio uses it when option.speed > 1 (W/src/dio.cpp:69-71).  out_len[u] =
 // min(want_len[u], number of values the reference's loop writes); the caller treats the rest as 0.
