@@ -352,13 +352,17 @@ def ours_arm(args):
                 upload_part(parts[0])               # first sub-batch of the next step
                 e2e_state["prefetched"] = True
             cp, (fa, fb), (ya, yb) = p["c"], p["f"], p["y"]
+            # The synchronous reads (f0, statistics) come BEFORE the bulk asynchronous copies are
+            # queued: a read issued behind a bulk copy waits in the device-to-host copy engine's
+            # queue for that copy's whole PCIe time, and the host cannot launch the next stage
+            # meanwhile (that was the 15 ms per step the end-to-end leg lost, profiles/README.md).
             cp.analyze(f0=args.f0)
+            wb._check(wb.lib().wb200_batch_get_f0(cp._h, wb.C.cast(o["f0"][fa:fb].data_ptr(), wb._dp), 1), "get_f0")
             cp.code(MGC_DIM, BAP_DIM)
+            st += cp.feature_stats()
             cp.coded_async(o["lf0"][fa:fb], o["mgc"][fa:fb], o["bap"][fa:fb])
             cp.synthesis()
             cp.y_pcm16_async(o["y"][ya:yb])
-            wb._check(wb.lib().wb200_batch_get_f0(cp._h, wb.C.cast(o["f0"][fa:fb].data_ptr(), wb._dp), 1), "get_f0")
-            st += cp.feature_stats()
         if not more_to_come:
             wb.sync()                           # every asynchronous copy has landed
         return reduce_stats(st)

@@ -218,8 +218,7 @@ bool cheaptrick_run(const UttView& u, int fs, int total_frames, const int* frame
   WB_LAUNCH_CHECK();
   if (!segmented_exclusive_scan(counts.p, u.f_off, u.f_len, u.n_utt, offs.p, totals.p)) return false;
   std::vector<long long> h_tot(u.n_utt);
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_tot.data(), totals.p, u.n_utt * sizeof(long long), cudaMemcpyDeviceToHost, st), false);
-  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  if (!read_back(h_tot.data(), totals.p, u.n_utt * sizeof(long long))) return false;
   long long mx = 0;
   for (long long v : h_tot) mx = v > mx ? v : mx;
   if (!ensure_randn((size_t)mx)) return false;

@@ -170,8 +170,7 @@ bool batch_cmp_stats(Batch* b, double* h_out) {   // [cmp_dim][3]
     cmp_stats_kernel<<<c->sm_count * 4, threads, 3 * threads * sizeof(double), st>>>(b->cmp.p, (long long)F * nd, nd, d.p);
     WB_LAUNCH_CHECK();
   }
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_out, d.p, (size_t)nd * 3 * sizeof(double), cudaMemcpyDeviceToHost, st), false);
-  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  if (!read_back(h_out, d.p, (size_t)nd * 3 * sizeof(double))) return false;
   return true;
 }
 

@@ -311,8 +311,7 @@ bool batch_feature_stats(Batch* b, double* h_out) {   // [(1 + mgc_dim)][3]: lf0
     feature_stats_kernel<<<c->sm_count * 4, threads, 3 * threads * sizeof(double), st>>>(b->mgc.p, (long long)F * nd, nd, d.p + 3);
     WB_LAUNCH_CHECK();
   }
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_out, d.p, (size_t)(nd + 1) * 3 * sizeof(double), cudaMemcpyDeviceToHost, st), false);
-  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  if (!read_back(h_out, d.p, (size_t)(nd + 1) * 3 * sizeof(double))) return false;
   return true;
 }
 

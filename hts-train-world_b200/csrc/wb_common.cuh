@@ -68,6 +68,13 @@ struct Context {
 };
 Context* ctx();                           // lazily initialised; nullptr on failure
 bool ensure_randn(size_t count);          // grow the randn table to >= count variates
+// Small device -> host read-back on the library stream, complete on return (per-utterance totals,
+// counters, statistics partials: the values the host needs to size the next launch).  bytes is a
+// multiple of 4.  A cudaMemcpyAsync here would queue on the device-to-host copy engine BEHIND any
+// bulk result copy another stream has in flight (hundreds of MB of features / waveform in a
+// pipelined run) and stall the compute stream for that copy's whole PCIe time; instead a small
+// kernel stores the words into mapped pinned host memory, which involves no copy engine.
+bool read_back(void* h_dst, const void* d_src, size_t bytes);
 
 // Optional per-kernel device timing (CUDA events on the library stream around one launch).
 // Off by default; bench.py switches it on to measure the dominant kernel live.

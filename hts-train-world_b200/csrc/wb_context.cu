@@ -325,6 +325,46 @@ bool ensure_randn(size_t count) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// read_back: device words -> mapped pinned host memory by a kernel (see wb_common.cuh)
+// ---------------------------------------------------------------------------------------------
+__global__ void read_back_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, size_t n_words) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
+static std::mutex g_rb_mutex;
+static void* g_rb_host = nullptr;          // cudaHostAlloc(Mapped)
+static uint32_t* g_rb_dev = nullptr;       // the same memory as the device sees it
+static size_t g_rb_cap = 0;
+
+bool read_back(void* h_dst, const void* d_src, size_t bytes) {
+  Context* c = ctx();
+  if (!c) return false;
+  if (bytes & 3) { set_error("read_back: %zu bytes is not a multiple of 4", bytes); return false; }
+  std::lock_guard<std::mutex> lock(g_rb_mutex);
+  if (bytes > g_rb_cap) {
+    size_t cap = (size_t)1 << 16;
+    while (cap < bytes) cap <<= 1;
+    if (g_rb_host) { cudaFreeHost(g_rb_host); g_rb_host = nullptr; g_rb_dev = nullptr; g_rb_cap = 0; }
+    if (!WB_CUDA(cudaHostAlloc(&g_rb_host, cap, cudaHostAllocMapped))) { g_rb_host = nullptr; return false; }
+    if (!WB_CUDA(cudaHostGetDevicePointer((void**)&g_rb_dev, g_rb_host, 0))) {
+      cudaFreeHost(g_rb_host); g_rb_host = nullptr; g_rb_dev = nullptr;
+      return false;
+    }
+    g_rb_cap = cap;
+  }
+  if (bytes > 0) {
+    const size_t n_words = bytes / 4;
+    const unsigned blocks = (unsigned)std::min<size_t>((n_words + 255) / 256, (size_t)c->sm_count);
+    read_back_kernel<<<blocks, 256, 0, c->stream>>>(static_cast<const uint32_t*>(d_src), g_rb_dev, n_words);
+    WB_LAUNCH_CHECK();
+  }
+  if (!WB_CUDA(cudaStreamSynchronize(c->stream))) return false;
+  if (bytes > 0) memcpy(h_dst, g_rb_host, bytes);
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // segmented exclusive scan over the frames of each utterance (one CTA per utterance)
 // ---------------------------------------------------------------------------------------------
 __global__ void seg_scan_kernel(const long long* __restrict__ counts, const int* __restrict__ f_off,

@@ -675,8 +675,7 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
   d4c_lt_count_kernel<<<nblk, 256, 0, st>>>(f0, total_frames, fs, counts.p);
   WB_LAUNCH_CHECK();
   if (!segmented_exclusive_scan(counts.p, u.f_off, u.f_len, u.n_utt, offs_lt.p, tot_lt.p)) return false;
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_lt.data(), tot_lt.p, u.n_utt * sizeof(long long), cudaMemcpyDeviceToHost, st), false);
-  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  if (!read_back(h_lt.data(), tot_lt.p, u.n_utt * sizeof(long long))) return false;
   std::fill(h_main.begin(), h_main.end(), 0);
   if (!need_randn()) return false;
   {
@@ -700,8 +699,7 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
   d4c_main_count_kernel<<<nblk, 256, 0, st>>>(f0, d_ap0.p, total_frames, fs, threshold, counts.p);
   WB_LAUNCH_CHECK();
   if (!segmented_exclusive_scan(counts.p, u.f_off, u.f_len, u.n_utt, offs_main.p, tot_main.p)) return false;
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_main.data(), tot_main.p, u.n_utt * sizeof(long long), cudaMemcpyDeviceToHost, st), false);
-  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  if (!read_back(h_main.data(), tot_main.p, u.n_utt * sizeof(long long))) return false;
   if (!need_randn()) return false;
   {
     const int hd = nd / 2;

@@ -367,8 +367,7 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
     zc_scan_kernel<<<(n_lists + 127) / 128, 128, 0, st>>>(d_counts.p, n_lists, n_chunks, d_ltot.p);
     WB_LAUNCH_CHECK();
     std::vector<int> h_ltot(n_lists);
-    WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_ltot.data(), d_ltot.p, n_lists * sizeof(int), cudaMemcpyDeviceToHost, st), false);
-    WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+    if (!read_back(h_ltot.data(), d_ltot.p, n_lists * sizeof(int))) return false;
     std::vector<long long> h_loff(n_lists);
     long long etot = 0;
     for (int l = 0; l < n_lists; ++l) { h_loff[l] = etot; etot += h_ltot[l]; }

@@ -920,8 +920,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
       WB_LAUNCH_CHECK(); kt.stop();
     }
     std::vector<int> h_ltot(n_lists);
-    WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_ltot.data(), d_ltot.p, n_lists * sizeof(int), cudaMemcpyDeviceToHost, st), false);
-    WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+    if (!read_back(h_ltot.data(), d_ltot.p, n_lists * sizeof(int))) return false;
     std::vector<long long> h_loff(n_lists);
     long long etot = 0;
     for (int l = 0; l < n_lists; ++l) { h_loff[l] = etot; etot += h_ltot[l]; }
@@ -944,8 +943,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
 
   // ---- 4. refinement of the overlapped candidates --------------------------------------------------------
   std::vector<int> h_nc(n_utt);
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_nc.data(), d_nc.p, n_utt * sizeof(int), cudaMemcpyDeviceToHost, st), false);
-  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  if (!read_back(h_nc.data(), d_nc.p, n_utt * sizeof(int))) return false;
   std::vector<long long> h_coff(n_utt), h_wfirst(n_utt);
   long long ctot = 0;
   for (int u = 0; u < n_utt; ++u) {
@@ -980,8 +978,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
   harvest_fix_a_kernel<<<n_utt, 256, 0, st>>>(d_cand2.p, d_score2.p, d_goff.p, d_glen.p, d_nc.p, d_coff.p, d_tmp1.p, d_tmp2.p, d_bl.p, d_nsec.p);
   WB_LAUNCH_CHECK();
   std::vector<int> h_nsec(n_utt);
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_nsec.data(), d_nsec.p, n_utt * sizeof(int), cudaMemcpyDeviceToHost, st), false);
-  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  if (!read_back(h_nsec.data(), d_nsec.p, n_utt * sizeof(int))) return false;
   {
     std::vector<long long> h_mcoff(n_utt);
     long long mtot = 0;
@@ -1001,8 +998,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
   WB_CUDA_OR_RETURN(cudaMemsetAsync(d_tmp2.p, 0, (size_t)gtot * sizeof(double), st), false);
   harvest_sections_kernel<<<n_utt, 32, 0, st>>>(d_tmp1.p, d_goff.p, d_glen.p, d_bl.p, d_nsec.p);
   WB_LAUNCH_CHECK();
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_nsec.data(), d_nsec.p, n_utt * sizeof(int), cudaMemcpyDeviceToHost, st), false);
-  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  if (!read_back(h_nsec.data(), d_nsec.p, n_utt * sizeof(int))) return false;
   {
     std::vector<int> h_sfirst(n_utt);
     std::vector<long long> h_soff(n_utt);

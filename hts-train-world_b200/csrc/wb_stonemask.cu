@@ -144,8 +144,7 @@ bool stonemask_run(const UttView& u, int fs, int total_frames, const int* frame_
   stonemask_maxfft_kernel<<<std::min(1024, (total_frames + 255) / 256), 256, 0, st>>>(f0_in, total_frames, fs, d_max.p);
   WB_LAUNCH_CHECK();
   int h_max = 0;
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(&h_max, d_max.p, sizeof(int), cudaMemcpyDeviceToHost, st), false);
-  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  if (!read_back(&h_max, d_max.p, sizeof(int))) return false;
   if (h_max < 3) h_max = 3;
   if (h_max > 13) { set_error("StoneMask: FFT size 2^%d not supported", h_max); return false; }
   const size_t smem = ((cpad_size(1 << h_max) + 1) & ~1) * sizeof(float2) + ((size_t)(1 << h_max) / 2 + 8) * sizeof(double) + ((size_t)(1 << h_max) / 2) * sizeof(int);

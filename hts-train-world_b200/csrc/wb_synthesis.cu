@@ -667,8 +667,7 @@ bool synthesis_run(Batch* b, const int* y_len) {
   synth_pulse_bound_kernel<<<n_utt, 128, 0, st>>>(b->f0.p, b->f_off.p, b->f_len.p, c, d_cap.p);
   WB_LAUNCH_CHECK();
   std::vector<int> h_cap(n_utt), h_cnt(n_utt), h_poff(n_utt);
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_cap.data(), d_cap.p, n_utt * sizeof(int), cudaMemcpyDeviceToHost, st), false);
-  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  if (!read_back(h_cap.data(), d_cap.p, n_utt * sizeof(int))) return false;
   long long total_p = 0;
   int max_y = 0;
   for (int u = 0; u < n_utt; ++u) { h_poff[u] = (int)total_p; total_p += h_cap[u]; max_y = std::max(max_y, y_len[u]); }
@@ -722,9 +721,8 @@ bool synthesis_run(Batch* b, const int* y_len) {
                                                                           p_utt.p, (int)total_p, c, d_cnt2.p, list_per.p, list_aper.p);
   WB_LAUNCH_CHECK();
   int h_cnt2[2] = {0, 0};
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_cnt2, d_cnt2.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st), false);
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(h_cnt.data(), d_cnt.p, n_utt * sizeof(int), cudaMemcpyDeviceToHost, st), false);
-  WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  if (!read_back(h_cnt2, d_cnt2.p, 2 * sizeof(int))) return false;
+  if (!read_back(h_cnt.data(), d_cnt.p, n_utt * sizeof(int))) return false;
   for (int u = 0; u < n_utt; ++u)
     if (h_cnt[u] > h_cap[u]) { set_error("Synthesis: utterance %d has %d pulses, bound was %d", u, h_cnt[u], h_cap[u]); return false; }
   const int n_per = h_cnt2[0], n_aper = h_cnt2[1];
