@@ -31,8 +31,10 @@ void set_error(const char* fmt, ...) {
   fprintf(stderr, "[world_b200] error: %s\n", buf);
 }
 const char* last_error() {
+  static thread_local std::string snapshot;   // the caller's pointer stays valid if another thread reports meanwhile
   std::lock_guard<std::mutex> lock(g_err_mutex);
-  return g_err.c_str();
+  snapshot = g_err;
+  return snapshot.c_str();
 }
 bool check_cuda(cudaError_t e, const char* what, const char* file, int line) {
   if (e == cudaSuccess) return true;
