@@ -22,6 +22,7 @@ distance in dB, tolerance 0.01).  tests/test_precision_budget.py pins the conclu
 rely on; profiles/README.md ("Precision budget") holds the table of the last run.
 """
 import argparse
+import contextlib
 import math
 import os
 import sys
@@ -131,6 +132,55 @@ def cheaptrick_variant(x, fs, t, f0, power32=False):
         np.fft.rfft = real
 
 
+@contextlib.contextmanager
+def single_precision_ffts(select=lambda kind, a, n: True):
+    """numpy.fft.{rfft, irfft, fft} compute in single precision for the calls `select` accepts."""
+    orig = {k: getattr(np.fft, k) for k in ("rfft", "irfft", "fft")}
+
+    def wrap(kind):
+        f = orig[kind]
+
+        def g(a, n=None, *args, **kw):
+            a = np.asarray(a)
+            if not select(kind, a, n):
+                return f(a, n, *args, **kw)
+            r = f(a.astype(np.complex64 if np.iscomplexobj(a) else np.float32), n, *args, **kw)
+            return r.astype(np.complex128 if np.iscomplexobj(r) else np.float64)
+        return g
+    for k in orig:
+        setattr(np.fft, k, wrap(k))
+    try:
+        yield
+    finally:
+        for k, f in orig.items():
+            setattr(np.fft, k, f)
+
+
+def kernels_fp32_choices(x, fs, t, f0):
+    """The FP32 transforms the kernels run TODAY, emulated one stage at a time
+    on the oracle: StoneMask's spectra, CheapTrick's two liftering transforms, Synthesis' four
+    transforms.  -> the north_star metrics of each against the all-double oracle."""
+    from oracle import metrics as M
+    fft_size = W.cheaptrick_fft_size(fs)
+    out = {}
+    f0_raw = W.dio(x, fs)[1] if f0 is None else f0
+    ref = W.stonemask(x, fs, t, f0_raw)
+    with single_precision_ffts():
+        new = W.stonemask(x, fs, t, f0_raw)
+    out["stonemask: V/UV agreement"] = M.vuv_agreement(ref, new)
+    out["stonemask: F0 relative error (tol 1e-4)"] = M.f0_rel_error(ref, new)
+    sp = W.cheaptrick(x, fs, t, ref)
+    with single_precision_ffts(lambda kind, a, n: kind == "irfft" or (kind == "rfft" and (n is None or len(a) == n))):
+        sp32 = W.cheaptrick(x, fs, t, ref)
+    out["cheaptrick lifter: LSD dB (tol 0.01)"] = M.lsd_db(sp, sp32)[1]
+    ap = W.d4c(x, fs, t, ref, fft_size, threshold=0.0)
+    y = W.synthesis(ref, sp, ap, fft_size, 5.0, fs)
+    with single_precision_ffts():
+        y32 = W.synthesis(ref, sp, ap, fft_size, 5.0, fs)
+    out["synthesis: SNR dB (tol >= 60)"] = M.snr_db(y, y32)
+    return out
+
+
 def _contour(x, fs):
     t, f0 = W.dio(x, fs)
     return t, W.stonemask(x, fs, t, f0)
@@ -210,7 +260,14 @@ def run(quick=False, variants=VARIANTS):
 if __name__ == "__main__":
     a = argparse.ArgumentParser()
     a.add_argument("--quick", action="store_true")
+    a.add_argument("--kernels", action="store_true", help="the FP32 choices of today's kernels on the hard inputs")
     args = a.parse_args()
+    if args.kernels:
+        for name, x, fs, t, f0 in cases(False)[:4]:
+            print(name)
+            for k, v in kernels_fp32_choices(x, fs, t, f0).items():
+                print("    %-44s %.4g" % (k, v))
+        sys.exit(0)
     for case, r in run(args.quick).items():
         print("%s  [%s]" % (case, r.pop("frames")))
         for k, v in r.items():

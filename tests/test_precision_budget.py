@@ -8,7 +8,9 @@ What the kernels rely on, and what this file keeps true:
     upper bands are empty (16 kHz speech delivered at 48 kHz -- the bands at 9-15 kHz hold
     quantisation noise 90 dB below the peak) their FP32 versions break the 1e-4 tolerance, although
     the bench corpus (noise floor at -34 dB) would never show it;
-  * LoveTrain's transform (:225-250) is a candidate for FP32: ap0 moves by < 1e-7.
+  * LoveTrain's transform (:225-250) is a candidate for FP32: ap0 moves by < 1e-7;
+  * the FP32 transforms of the other kernels (StoneMask's spectra, CheapTrick's liftering pair,
+    Synthesis' four transforms) stay four to six orders inside their tolerances on the same input.
 """
 import numpy as np
 import pytest
@@ -57,3 +59,12 @@ def test_bench_corpus_alone_would_not_show_it():
     res = PS.run(quick=True, variants=[("all", dict(centroid="c32", power32=True, band32=True, lt32=True))])
     for case, r in res.items():
         assert r["all"] < 1e-5, case
+
+
+def test_fp32_transforms_of_the_other_kernels_hold_on_the_hard_input(band_limited):
+    x, fs, t, f0 = band_limited
+    r = PS.kernels_fp32_choices(x, fs, t, f0)
+    assert r["stonemask: V/UV agreement"] == 1.0
+    assert r["stonemask: F0 relative error (tol 1e-4)"] < 1e-6
+    assert r["cheaptrick lifter: LSD dB (tol 0.01)"] < 1e-4
+    assert r["synthesis: SNR dB (tol >= 60)"] > 100.0
