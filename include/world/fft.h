@@ -10,18 +10,20 @@ WORLD_BEGIN_C_DECLS
 #define FFT_FORWARD 1
 #define FFT_BACKWARD 2
 #define FFT_ESTIMATE 3
-typedef double fft_complex[2];
+typedef double fft_complex[2];   /* (re, im) */
+/* Field order and types are the reference's (the struct travels by value); what the work arrays
+ * hold is private to the implementation. */
 typedef struct {
-  int n;
-  int sign;
-  unsigned int flags;
-  fft_complex *c_in;
-  double *in;
-  fft_complex *c_out;
-  double *out;
-  double *input; /* work buffer, 2 n doubles */
-  int *ip;       /* bit-reversal table, n ints */
-  double *w;     /* twiddle table, 5 n / 4 doubles */
+  int n;               /* transform length (a power of two) */
+  int sign;            /* FFT_FORWARD / FFT_BACKWARD */
+  unsigned int flags;  /* FFT_ESTIMATE, ignored */
+  fft_complex *c_in;   /* complex input, or NULL (r2c) */
+  double *in;          /* real input, or NULL */
+  fft_complex *c_out;  /* complex output, or NULL (c2r) */
+  double *out;         /* real output, or NULL */
+  double *input;       /* work buffer, 2 n doubles */
+  int *ip;             /* bit-reversal table, n ints */
+  double *w;           /* twiddle table, 5 n / 4 doubles */
 } fft_plan;
 /* replaces W/src/fft.cpp:76-97: c2c; FFT_FORWARD computes DFT(conj(in)), FFT_BACKWARD
  * n * IDFT(conj(in)) (the reference's conventions, W/src/fft.cpp:36-45,61-71) */
