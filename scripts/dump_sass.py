@@ -18,7 +18,7 @@ WANT = {
     "stonemask_kernel": r"stonemask_kernelE",
     "ols_filter_kernel<13>": r"wb_dio.*ols_filter_kernelILi13E|ols_filter_kernelILi13E",
     "harvest_refine_kernel": r"harvest_refine_kernelE",
-    "codec_encode_kernel": r"codec_encode_kernelE",
+    "codec_encode_kernel<10,fp32 log>": r"codec_encode_kernelILi10ELb1E",
 }
 syms = subprocess.run(["cuobjdump", "-elf", LIB], capture_output=True, text=True).stdout
 names = sorted(set(re.findall(r"\.text\.(_Z\w+)", syms)))
