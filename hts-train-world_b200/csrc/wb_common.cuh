@@ -12,6 +12,13 @@
 #include <stdint.h>
 #include <stdio.h>
 
+// dynamic shared memory of a kernel (tests/emu runs the kernels on the CPU, one CTA at a time)
+#ifdef WB_HOST_EMU
+#define WB_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(::wbemu::dyn_smem)
+#else
+#define WB_DYN_SMEM(T, name) extern __shared__ T name[]
+#endif
+
 namespace wb {
 
 // ---- constants of the reference (W/src/world/constantnumbers.h) -------------------------
@@ -115,7 +122,7 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
 };
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(WB_HOST_EMU)
 // ---- small device helpers ----------------------------------------------------------------
 // matlab_round (W/src/matlabfunctions.cpp:212-214): half away from zero via truncation.
 __host__ __device__ __forceinline__ int matlab_round(double x) {
@@ -204,6 +211,17 @@ __device__ __forceinline__ void block_inclusive_scan(double* a, int n, double* r
 // TMA unit to copy it into shared memory and arms an mbarrier with the byte count; the other
 // threads meanwhile compute window coefficients and wait on the barrier only when they need the
 // samples.  Source and destination must be 16-byte aligned and the size a multiple of 16 bytes.
+#ifdef WB_HOST_EMU
+// CPU emulation: the copy is done by the issuing thread, the barrier word counts completed phases
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned) { __atomic_store_n(bar, 0ull, __ATOMIC_SEQ_CST); }
+__device__ __forceinline__ void bulk_load_issue(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+  memcpy(smem_dst, gsrc, bytes);
+  __atomic_fetch_add(bar, 1ull, __ATOMIC_SEQ_CST);
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  while ((__atomic_load_n(bar, __ATOMIC_SEQ_CST) & 1ull) == parity) ::wbemu::yield();
+}
+#else
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
@@ -227,6 +245,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       "DONE_%=:\n"
       "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
+#endif  // WB_HOST_EMU
 // Window [g0, g0 + W) of an utterance of x_len samples whose base pointer is 16-byte aligned:
 // can it be staged with one bulk copy into `cap` doubles?  If so returns true and the aligned
 // range [*a0, *a0 + *n); sample g0 + i then sits at staging[(g0 - *a0) + i].

@@ -111,7 +111,7 @@ d4c_lovetrain_kernel(UttView u, const int* __restrict__ frame_utt, const double*
                      const double* __restrict__ f0_in, const long long* __restrict__ rng_off,
                      const uint32_t* __restrict__ randn_tab, const double2* __restrict__ tw,
                      D4CConst c, double* __restrict__ ap0_out) {
-  extern __shared__ double2 smem2[];
+  WB_DYN_SMEM(double2, smem2);
   const int f = blockIdx.x;
   const double f0 = f0_in[f];
   if (f0 == 0.0) { if (threadIdx.x == 0) ap0_out[f] = 0.0; return; }
@@ -309,7 +309,11 @@ __device__ __forceinline__ void warp_select_low_sum(const float* __restrict__ P,
     int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int j = 0; j < NPL; ++j)              // one compare and one predicated increment per key
+#ifdef WB_HOST_EMU
+      c[j & 7] += key[j] >= cand;
+#else
       asm("{.reg .pred p; setp.ge.u32 p, %1, %2; @p add.s32 %0, %0, 1;}" : "+r"(c[j & 7]) : "r"(key[j]), "r"(cand));
+#endif
     const int cnt = __reduce_add_sync(0xffffffffu, ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7])));
     if (cnt >= K) {
       T = cand;
@@ -387,7 +391,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
                 const uint32_t* __restrict__ randn_tab, const double2* __restrict__ tw,
                 const float2* __restrict__ twf, const double* __restrict__ nuttall, D4CConst c,
                 double* __restrict__ ap_out) {
-  extern __shared__ double2 smem2[];
+  WB_DYN_SMEM(double2, smem2);
   const int log2nd = LOG2ND > 0 ? LOG2ND : c.log2nd;
   constexpr int LMD = LOG2ND > 0 ? LOG2ND - 1 : 0;
   constexpr int TWL = LOG2ND > 0 ? LOG2ND : kTwLog2;     // compact twiddle tables of this size, or the master tables
@@ -622,6 +626,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
 
 }  // namespace
 
+#ifndef WB_HOST_EMU      // the launcher; tests/emu has its own
 bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
              const double* frame_t, const double* f0, int fft_size, double threshold,
              double* ap) {
@@ -723,5 +728,6 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
   return true;
 }
+#endif  // WB_HOST_EMU
 
 }  // namespace wb

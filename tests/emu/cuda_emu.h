@@ -1,0 +1,107 @@
+// TEST INFRASTRUCTURE: a minimal CUDA-on-CPU shim, enough to run the D4C kernels of
+// hts-train-world_b200/csrc/wb_d4c.cu one CTA at a time (every CUDA thread is an OS thread,
+// __syncthreads() a barrier, warp shuffles an exchange through a per-warp slot array).  It finds
+// index / layout / logic errors of a kernel before it has seen a GPU; it says nothing about
+// races, bank conflicts or speed.  g++ -std=c++20 -DWB_HOST_EMU.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#include <barrier>
+#include <memory>
+#include <thread>
+#include <vector>
+
+namespace wbemu {
+struct Dim { unsigned x = 1, y = 1, z = 1; };
+inline thread_local Dim t_idx;
+inline Dim b_idx, b_dim, g_dim;
+alignas(16) inline unsigned char dyn_smem[256 * 1024];
+inline std::unique_ptr<std::barrier<>> block_bar;
+inline std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
+inline uint64_t xchg[64][32];
+inline void yield() { std::this_thread::yield(); }
+inline void syncthreads() { block_bar->arrive_and_wait(); }
+
+template <typename T, typename SRC>
+inline T exchange(T v, SRC src_of_lane) {
+  static_assert(sizeof(T) <= 8, "shuffle of <= 8 bytes");
+  const int w = t_idx.x >> 5, lane = t_idx.x & 31;
+  uint64_t raw = 0;
+  memcpy(&raw, &v, sizeof(T));
+  xchg[w][lane] = raw;
+  warp_bar[w]->arrive_and_wait();
+  const int src = src_of_lane(lane);
+  T r = v;
+  if (src >= 0 && src < 32) memcpy(&r, &xchg[w][src], sizeof(T));
+  warp_bar[w]->arrive_and_wait();
+  return r;
+}
+template <typename T> inline T shfl_xor(T v, int o) { return exchange(v, [o](int l) { return l ^ o; }); }
+template <typename T> inline T shfl_up(T v, int o) { return exchange(v, [o](int l) { return l - o; }); }
+template <typename T> inline T shfl_down(T v, int o) { return exchange(v, [o](int l) { return l + o; }); }
+template <typename T, typename OP> inline T reduce(T v, OP op) {
+  for (int o = 16; o > 0; o >>= 1) v = op(v, shfl_xor(v, o));
+  return v;
+}
+
+// run `body()` as a grid of CTAs of `threads` threads, one CTA at a time
+template <typename F>
+inline void launch(const std::vector<int>& blocks, int grid, int threads, F body) {
+  b_dim.x = threads;
+  g_dim.x = grid;
+  block_bar = std::make_unique<std::barrier<>>(threads);
+  warp_bar.clear();
+  for (int w = 0; w < (threads + 31) / 32; ++w) warp_bar.push_back(std::make_unique<std::barrier<>>(32));
+  for (int b : blocks) {
+    b_idx.x = b;
+    std::vector<std::thread> th;
+    for (int i = 0; i < threads; ++i)
+      th.emplace_back([i, &body]() { t_idx.x = i; body(); });
+    for (auto& t : th) t.join();
+  }
+}
+}  // namespace wbemu
+
+#undef __shared__
+#define __shared__ static
+#undef __launch_bounds__
+#define __launch_bounds__(...)
+#undef __noinline__
+#define __noinline__
+#undef __forceinline__
+#define __forceinline__ inline
+#define threadIdx (::wbemu::t_idx)
+#define blockIdx (::wbemu::b_idx)
+#define blockDim (::wbemu::b_dim)
+#define gridDim (::wbemu::g_dim)
+#define __syncthreads() ::wbemu::syncthreads()
+#define __shfl_xor_sync(m, v, o) ::wbemu::shfl_xor((v), (o))
+#define __shfl_up_sync(m, v, o) ::wbemu::shfl_up((v), (o))
+#define __shfl_down_sync(m, v, o) ::wbemu::shfl_down((v), (o))
+#define __reduce_add_sync(m, v) ::wbemu::reduce((v), [](auto a, auto b) { return a + b; })
+#define __reduce_max_sync(m, v) ::wbemu::reduce((v), [](auto a, auto b) { return a > b ? a : b; })
+#define __ldg(p) (*(p))
+inline unsigned __brev(unsigned v) {
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i);
+  return r;
+}
+inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __ddiv_rn(double a, double b) { return a / b; }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+inline double __hiloint2double(int hi, int lo) {
+  const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+  double d; memcpy(&d, &u, 8); return d;
+}
+inline void sincospi(double a, double* s, double* c) {
+  const long double x = 3.14159265358979323846264338327950288L * (long double)a;
+  *s = (double)sinl(x); *c = (double)cosl(x);
+}
+using std::max;
+using std::min;
