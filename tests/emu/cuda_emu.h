@@ -46,9 +46,12 @@ template <typename T, typename OP> inline T reduce(T v, OP op) {
   return v;
 }
 
-// run `body()` as a grid of CTAs of `threads` threads, one CTA at a time
+// run `body()` as a grid of CTAs of `threads` threads, one CTA at a time.  smem_bytes = the dynamic
+// shared memory the launcher would request: the 4 KB behind it hold a canary, and a kernel that
+// writes past its allocation is counted in smem_overruns.
+inline int smem_overruns = 0;
 template <typename F>
-inline void launch(const std::vector<int>& blocks, int grid, int threads, F body) {
+inline void launch(const std::vector<int>& blocks, int grid, int threads, size_t smem_bytes, F body) {
   b_dim.x = threads;
   g_dim.x = grid;
   block_bar = std::make_unique<std::barrier<>>(threads);
@@ -56,10 +59,13 @@ inline void launch(const std::vector<int>& blocks, int grid, int threads, F body
   for (int w = 0; w < (threads + 31) / 32; ++w) warp_bar.push_back(std::make_unique<std::barrier<>>(32));
   for (int b : blocks) {
     b_idx.x = b;
+    memset(dyn_smem + smem_bytes, 0xA5, 4096);
     std::vector<std::thread> th;
     for (int i = 0; i < threads; ++i)
       th.emplace_back([i, &body]() { t_idx.x = i; body(); });
     for (auto& t : th) t.join();
+    for (int i = 0; i < 4096; ++i)
+      if (dyn_smem[smem_bytes + i] != 0xA5) { ++smem_overruns; break; }
   }
 }
 }  // namespace wbemu

@@ -57,6 +57,18 @@ extern "C" int emu_d4c(const double* x, int x_len, int fs, const double* t, cons
   const int f_off = 0;
   UttView u{xs.data(), &x_off, &x_len, &f_off, &F, 1};
   std::vector<int> frame_utt(F, 0);
+  // dynamic shared memory exactly as d4c_run requests it
+  const int hd = nd / 2, nl = 1 << c.log2lt;
+  const size_t smem_lt = (size_t)(2 * cpad_size(nl / 2) + 96) * sizeof(double);
+  const size_t smem_main = d4c_cbuf_slots(nd, c.nbands) * sizeof(double2) + (size_t)(2 * (hd + 8) + 160) * sizeof(double) +
+                           sizeof(SelectScratch) + (kMaxBands + 2) * sizeof(double);
+#ifdef WB_D4C_HAS_SPLIT
+  const size_t smem_lt32 = (size_t)((cpadf(nl / 2) + 4 + 1) & ~1) * sizeof(float2) + 96 * sizeof(double);
+  const size_t smem_gd = (size_t)(2 * (hd + 8) + 160) * sizeof(double) + (size_t)cpad_size(hd) * sizeof(double2);
+  const size_t smem_tail = (size_t)d4c_tail_fb_slots(nd) * sizeof(float2) + (size_t)((c.nbands * (hd + 1) + 1) & ~1) * sizeof(float) +
+                           (kMaxBands + 2) * sizeof(double);
+#endif
+  wbemu::smem_overruns = 0;
   // LoveTrain
   std::vector<long long> offs_lt(F), offs_main(F);
   long long tot_lt = 0, tot_main = 0;
@@ -86,10 +98,10 @@ extern "C" int emu_d4c(const double* x, int x_len, int fs, const double* t, cons
 #endif
   if (mode & 2) {
 #ifdef WB_D4C_HAS_SPLIT
-    wbemu::launch(lt_rows, F, 256, [&]() { d4c_lovetrain32_kernel<12>(u, frame_utt.data(), t, f0, offs_lt.data(), randn_tab.data(), twf.data(), c, ap0.data()); });
+    wbemu::launch(lt_rows, F, 256, smem_lt32, [&]() { d4c_lovetrain32_kernel<12>(u, frame_utt.data(), t, f0, offs_lt.data(), randn_tab.data(), twf.data(), c, ap0.data()); });
 #endif
   } else {
-    wbemu::launch(lt_rows, F, 256, [&]() { d4c_lovetrain_kernel<12>(u, frame_utt.data(), t, f0, offs_lt.data(), randn_tab.data(), tw.data(), c, ap0.data()); });
+    wbemu::launch(lt_rows, F, 256, smem_lt, [&]() { d4c_lovetrain_kernel<12>(u, frame_utt.data(), t, f0, offs_lt.data(), randn_tab.data(), tw.data(), c, ap0.data()); });
   }
   if (!(threshold > 0.0))
     for (int f = 0; f < F; ++f) if (f0[f] != 0.0 && ap0[f] == 0.0) ap0[f] = 1.0;      // not launched: passes `ap0 <= threshold`
@@ -102,14 +114,14 @@ extern "C" int emu_d4c(const double* x, int x_len, int fs, const double* t, cons
   if (mode & 1) {
 #ifdef WB_D4C_HAS_SPLIT
     std::vector<float> slices((size_t)F * c.nbands * c.window_length, 0.f);
-    wbemu::launch(sel, F, 256, [&]() { d4c_gd_kernel<12, 256>(u, frame_utt.data(), t, f0, ap0.data(), offs_main.data(), &tot_lt, randn_tab.data(), tw.data(), win.data(), c, slices.data()); });
-    wbemu::launch(sel, F, 256, [&]() { d4c_tail_kernel<12, 256>(f0, ap0.data(), slices.data(), twf.data(), c, ap.data()); });
+    wbemu::launch(sel, F, 256, smem_gd, [&]() { d4c_gd_kernel<12, 256>(u, frame_utt.data(), t, f0, ap0.data(), offs_main.data(), &tot_lt, randn_tab.data(), tw.data(), win.data(), c, slices.data()); });
+    wbemu::launch(sel, F, 256, smem_tail, [&]() { d4c_tail_kernel<12, 256>(f0, ap0.data(), slices.data(), twf.data(), c, ap.data()); });
 #endif
   } else {
-    wbemu::launch(sel, F, 256, [&]() { d4c_main_kernel<12, 256, 4>(u, frame_utt.data(), t, f0, ap0.data(), offs_main.data(), &tot_lt, randn_tab.data(), tw.data(), twf.data(), win.data(), c, ap.data()); });
+    wbemu::launch(sel, F, 256, smem_main, [&]() { d4c_main_kernel<12, 256, 4>(u, frame_utt.data(), t, f0, ap0.data(), offs_main.data(), &tot_lt, randn_tab.data(), tw.data(), twf.data(), win.data(), c, ap.data()); });
   }
   if (ap0_out) memcpy(ap0_out, ap0.data(), F * sizeof(double));
   for (int r = 0; r < n_rows; ++r)
     memcpy(ap_rows + (size_t)r * (c.out_half + 1), ap.data() + (size_t)rows[r] * (c.out_half + 1), (c.out_half + 1) * sizeof(double));
-  return 0;
+  return wbemu::smem_overruns ? 4 : 0;                                 // 4: a kernel wrote past its shared-memory allocation
 }
