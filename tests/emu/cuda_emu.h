@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 #include <barrier>
 #include <memory>
@@ -22,7 +23,14 @@ inline std::unique_ptr<std::barrier<>> block_bar;
 inline std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
 inline uint64_t xchg[64][32];
 inline void yield() { std::this_thread::yield(); }
-inline void syncthreads() { block_bar->arrive_and_wait(); }
+// WBEMU_SKIP_BARRIER=n drops the n-th __syncthreads() of every CTA (all threads skip the same one):
+// the self-test of the race check (tests/emu/README.md) -- ThreadSanitizer must then report a race.
+inline thread_local int barrier_no = 0;
+inline int skip_barrier = getenv("WBEMU_SKIP_BARRIER") ? atoi(getenv("WBEMU_SKIP_BARRIER")) : -1;
+inline void syncthreads() {
+  if (barrier_no++ == skip_barrier) return;
+  block_bar->arrive_and_wait();
+}
 
 template <typename T, typename SRC>
 inline T exchange(T v, SRC src_of_lane) {
@@ -62,7 +70,7 @@ inline void launch(const std::vector<int>& blocks, int grid, int threads, size_t
     memset(dyn_smem + smem_bytes, 0xA5, 4096);
     std::vector<std::thread> th;
     for (int i = 0; i < threads; ++i)
-      th.emplace_back([i, &body]() { t_idx.x = i; body(); });
+      th.emplace_back([i, &body]() { t_idx.x = i; barrier_no = 0; body(); });
     for (auto& t : th) t.join();
     for (int i = 0; i < 4096; ++i)
       if (dyn_smem[smem_bytes + i] != 0xA5) { ++smem_overruns; break; }

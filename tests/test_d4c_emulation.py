@@ -84,3 +84,44 @@ def test_long_windows_edges_and_threshold(emu, reference_lib):
     for mode in modes(has_split):
         ap, _ = run(lib, x, fs, t, g["f0"], n, rows, mode, threshold=0.85)
         assert M.ap_abs_error(ref[rows], ap) <= 1e-6, mode
+
+
+def test_no_data_races_under_thread_sanitizer(tmp_path, reference_lib):
+    """Barrier placement: the emulated kernels (256 OS threads per CTA, __syncthreads = a barrier)
+    run under ThreadSanitizer -- a missing __syncthreads is a data race between two threads of the
+    CTA and is reported with the source line of the kernel.  Frames: a long window (f0 75 Hz: gather
+    path, folding halves), a staged one, a normal voiced frame, the last frame (utterance edge).
+    The detector is shown to be live first: with one barrier dropped (WBEMU_SKIP_BARRIER) it must
+    report.  (The TMA copy is a memcpy here: proxy fences are outside what this can see.)"""
+    if not shutil.which("g++") or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    exe = str(tmp_path / "d4c_tsan")
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-DWB_HOST_EMU",
+                        "-I" + CUDA_INC, "-I" + os.path.join(ROOT, "include"),
+                        "-I" + os.path.join(ROOT, "hts-train-world_b200", "csrc"), "-x", "c++",
+                        os.path.join(EMU, "d4c_emu.cpp"), os.path.join(EMU, "d4c_emu_main.cpp"), "-o", exe, "-lpthread"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("no ThreadSanitizer runtime: " + r.stderr[-200:])
+    g = load_golden("synthetic48k_u7")
+    x, t, f0 = _x(g), g["t"].astype(np.float64), g["f0"].astype(np.float64).copy()
+    f0[0], f0[1], f0[-1] = 75.0, 100.0, 120.0
+    rows = np.array([0, 1, int(np.nonzero(g["f0"] > 0)[0][10]), len(f0) - 1], dtype=np.int32)
+    x.tofile(tmp_path / "x.f64"); t.tofile(tmp_path / "t.f64"); f0.tofile(tmp_path / "f0.f64"); rows.tofile(tmp_path / "rows.i32")
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0")
+
+    def tsan(mode, threshold, skip=None):
+        e = dict(env, WBEMU_SKIP_BARRIER=str(skip)) if skip is not None else env
+        p = subprocess.run([exe, str(tmp_path), str(mode), str(threshold)], capture_output=True, text=True, env=e, timeout=900)
+        if "unexpected memory mapping" in p.stderr:
+            pytest.skip("ThreadSanitizer cannot map its shadow memory here")
+        return p.returncode, p.stderr.count("WARNING: ThreadSanitizer")
+
+    assert tsan(0, 0.0, skip=20)[1] > 0                    # the detector sees a dropped barrier
+    has_split = "WB_D4C_HAS_SPLIT" in open(os.path.join(ROOT, "hts-train-world_b200", "csrc", "wb_d4c.cu")).read()
+    for mode, thr in [(0, 0.0), (0, 0.85)] + ([(1, 0.0), (3, 0.85)] if has_split else []):
+        rc, warnings = tsan(mode, thr)
+        assert (rc, warnings) == (0, 0), (mode, thr)
+        ap = np.fromfile(tmp_path / "ap.f64").reshape(len(rows), -1)
+        ref = reference_lib.d4c(x, int(g["fs"]), t, f0, int(g["fft_size"]), threshold=thr)
+        assert M.ap_abs_error(ref[rows], ap) <= 1e-6, (mode, thr)
