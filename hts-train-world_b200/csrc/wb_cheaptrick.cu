@@ -41,7 +41,7 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
                   const double* __restrict__ f0_in, const long long* __restrict__ rng_off,
                   const uint32_t* __restrict__ randn_tab, const double2* __restrict__ tw,
                   const float2* __restrict__ twf, int fs, int log2n_rt, double q1, double f0_floor, double* __restrict__ sp_out) {
-  extern __shared__ double2 smem2[];
+  WB_DYN_SMEM(double2, smem2);
   const int log2n = LOG2N > 0 ? LOG2N : log2n_rt;
   constexpr int LM = LOG2N > 0 ? LOG2N - 1 : 0;
   constexpr int TWL = LOG2N > 0 ? LOG2N : kTwLog2;       // compact twiddle tables of this size, or the master tables
@@ -198,6 +198,7 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
   }
 }
 
+#ifndef WB_HOST_EMU      // the launcher; tests/emu has its own
 bool cheaptrick_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
                     const double* frame_t, const double* f0, int fft_size, double q1,
                     double* sp) {
@@ -247,5 +248,7 @@ bool cheaptrick_run(const UttView& u, int fs, int total_frames, const int* frame
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
   return true;
 }
+
+#endif  // WB_HOST_EMU
 
 }  // namespace wb

@@ -1,0 +1,50 @@
+// TEST INFRASTRUCTURE: stand-alone driver of tests/emu/{d4c,cheaptrick}_emu.cpp for the
+// ThreadSanitizer builds (an instrumented executable is simpler to run than an instrumented library
+// inside python).  Reads <dir>/{x,t,f0}.f64 and <dir>/rows.i32 (48 kHz, fft_size 2048):
+//   emu_main <dir> <mode> <threshold>      D4C (default build): writes <dir>/ap.f64
+//   emu_main <dir>                         CheapTrick (-DEMU_CHEAPTRICK): writes <dir>/sp.f64
+// and exits with the harness's return code.
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+extern "C" int emu_cheaptrick(const double* x, int x_len, int fs, const double* t, const double* f0, int F, int fft_size,
+                              double q1, const int* rows, int n_rows, double* sp_rows);
+extern "C" int emu_d4c(const double* x, int x_len, int fs, const double* t, const double* f0, int F, int fft_size,
+                       double threshold, int mode, const int* rows, int n_rows, double* ap_rows, double* ap0_out);
+template <typename T>
+static std::vector<T> slurp(const std::string& path) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) { perror(path.c_str()); exit(90); }
+  fseek(f, 0, SEEK_END);
+  const long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<T> v(n / sizeof(T));
+  if (fread(v.data(), 1, n, f) != (size_t)n) exit(91);
+  fclose(f);
+  return v;
+}
+static void dump(const std::string& path, const std::vector<double>& v) {
+  FILE* f = fopen(path.c_str(), "wb");
+  fwrite(v.data(), sizeof(double), v.size(), f);
+  fclose(f);
+}
+int main(int argc, char** argv) {
+  if (argc < 2) return 92;
+  const std::string dir = argv[1];
+  const auto x = slurp<double>(dir + "/x.f64"), t = slurp<double>(dir + "/t.f64"), f0 = slurp<double>(dir + "/f0.f64");
+  const auto rows = slurp<int>(dir + "/rows.i32");
+  std::vector<double> out(rows.size() * 1025);
+#ifdef EMU_CHEAPTRICK
+  const int rc = emu_cheaptrick(x.data(), (int)x.size(), 48000, t.data(), f0.data(), (int)f0.size(), 2048, -0.15, rows.data(),
+                                (int)rows.size(), out.data());
+  dump(dir + "/sp.f64", out);
+#else
+  if (argc < 4) return 92;
+  std::vector<double> ap0(f0.size());
+  const int rc = emu_d4c(x.data(), (int)x.size(), 48000, t.data(), f0.data(), (int)f0.size(), 2048, atof(argv[3]), atoi(argv[2]),
+                         rows.data(), (int)rows.size(), out.data(), ap0.data());
+  dump(dir + "/ap.f64", out);
+#endif
+  return rc;
+}

@@ -1,5 +1,5 @@
-"""CPU: the D4C kernels of hts-train-world_b200/csrc/wb_d4c.cu, compiled for the CPU by the
-CUDA-on-CPU shim of tests/emu/ (every CUDA thread an OS thread, one CTA at a time), against the
+"""CPU: the D4C kernels of hts-train-world_b200/csrc/wb_d4c.cu and the CheapTrick kernel of
+wb_cheaptrick.cu, compiled for the CPU by the CUDA-on-CPU shim of tests/emu/ (every CUDA thread an OS thread, one CTA at a time), against the
 golden vectors and the compiled reference.  It checks the SOURCE of the kernels -- indices, layouts,
 barrier placement as far as logic goes -- without a GPU; the GPU parity tests check the binaries.
 
@@ -35,6 +35,15 @@ def emu(tmp_path_factory):
     lib = C.CDLL(so)
     src = open(os.path.join(ROOT, "hts-train-world_b200", "csrc", "wb_d4c.cu")).read()
     return lib, "WB_D4C_HAS_SPLIT" in src
+
+
+def _build(src, out, extra=()):
+    if not shutil.which("g++") or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    return subprocess.run(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-DWB_HOST_EMU", "-I" + CUDA_INC,
+                           "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "hts-train-world_b200", "csrc"),
+                           "-x", "c++"] + [os.path.join(EMU, f) for f in src] + ["-o", out, "-lpthread"] + list(extra),
+                          capture_output=True, text=True)
 
 
 def run(lib, x, fs, t, f0, fft_size, rows, mode, threshold=0.0):
@@ -99,7 +108,7 @@ def test_no_data_races_under_thread_sanitizer(tmp_path, reference_lib):
     r = subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-DWB_HOST_EMU",
                         "-I" + CUDA_INC, "-I" + os.path.join(ROOT, "include"),
                         "-I" + os.path.join(ROOT, "hts-train-world_b200", "csrc"), "-x", "c++",
-                        os.path.join(EMU, "d4c_emu.cpp"), os.path.join(EMU, "d4c_emu_main.cpp"), "-o", exe, "-lpthread"],
+                        os.path.join(EMU, "d4c_emu.cpp"), os.path.join(EMU, "emu_main.cpp"), "-o", exe, "-lpthread"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         pytest.skip("no ThreadSanitizer runtime: " + r.stderr[-200:])
@@ -125,3 +134,42 @@ def test_no_data_races_under_thread_sanitizer(tmp_path, reference_lib):
         ap = np.fromfile(tmp_path / "ap.f64").reshape(len(rows), -1)
         ref = reference_lib.d4c(x, int(g["fs"]), t, f0, int(g["fft_size"]), threshold=thr)
         assert M.ap_abs_error(ref[rows], ap) <= 1e-6, (mode, thr)
+
+
+def test_cheaptrick_kernel_source(tmp_path, reference_lib):
+    """cheaptrick_kernel<11, 128> (FP64 power spectrum, FP32 liftering pair) against the golden rows
+    and, on long windows / utterance edges / unvoiced frames, against the compiled reference; then the
+    same frames under ThreadSanitizer."""
+    so = str(tmp_path / "libct_emu.so")
+    assert _build(["cheaptrick_emu.cpp"], so, ["-fPIC", "-shared"]).returncode == 0
+    lib = C.CDLL(so)
+    g = load_golden("synthetic48k_u7")
+    x, fs, t, n = _x(g), int(g["fs"]), g["t"].astype(np.float64), int(g["fft_size"])
+
+    def ct(f0, rows):
+        f0 = np.ascontiguousarray(f0, dtype=np.float64)
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        out = np.zeros((len(rows), n // 2 + 1))
+        rc = lib.emu_cheaptrick(x.ctypes.data_as(dp), len(x), fs, t.ctypes.data_as(dp), f0.ctypes.data_as(dp), len(f0), n,
+                                C.c_double(-0.15), rows.ctypes.data_as(ip), len(rows), out.ctypes.data_as(dp))
+        assert rc == 0
+        return out
+    rows = g["rows"][::3]
+    assert M.lsd_db(g["sp_rows"][::3].astype(np.float64), ct(g["f0"], rows))[1] <= 1e-4      # float32 fixture rows
+    f0 = np.where(np.arange(len(t)) % 3 == 0, 71.5, np.where(np.arange(len(t)) % 3 == 1, 0.0, 640.0))
+    rows = [0, 1, 2, 150, 151, 152, len(t) - 3, len(t) - 2, len(t) - 1]
+    ref = reference_lib.cheaptrick(x, fs, t, f0)
+    assert M.lsd_db(ref[rows], ct(f0, rows))[1] <= 1e-4
+    exe = str(tmp_path / "ct_tsan")
+    if _build(["cheaptrick_emu.cpp", "emu_main.cpp"], exe, ["-g", "-fsanitize=thread", "-DEMU_CHEAPTRICK"]).returncode != 0:
+        pytest.skip("no ThreadSanitizer runtime")
+    x.tofile(tmp_path / "x.f64"); t.tofile(tmp_path / "t.f64"); f0.tofile(tmp_path / "f0.f64")
+    np.array(rows, dtype=np.int32).tofile(tmp_path / "rows.i32")
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0")
+    p = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, env=env, timeout=900)
+    if "unexpected memory mapping" in p.stderr:
+        pytest.skip("ThreadSanitizer cannot map its shadow memory here")
+    assert (p.returncode, p.stderr.count("WARNING: ThreadSanitizer")) == (0, 0), p.stderr[:2000]
+    assert M.lsd_db(ref[rows], np.fromfile(tmp_path / "sp.f64").reshape(len(rows), -1))[1] <= 1e-4
+    p = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, env=dict(env, WBEMU_SKIP_BARRIER="12"), timeout=900)
+    assert p.stderr.count("WARNING: ThreadSanitizer") > 0          # the detector is live
