@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256)
 stonemask_kernel(UttView u, const int* __restrict__ frame_utt, const double* __restrict__ frame_t,
                  const double* __restrict__ f0_in, const float2* __restrict__ tw, int fs,
                  int max_log2fft, double* __restrict__ f0_out) {
-  extern __shared__ double2 smem2[];
+  WB_DYN_SMEM(double2, smem2);
   const int f = blockIdx.x;
   const double f0 = f0_in[f];
   if (!stonemask_in_range(f0, fs)) { if (threadIdx.x == 0) f0_out[f] = 0.0; return; }
@@ -132,6 +132,7 @@ stonemask_kernel(UttView u, const int* __restrict__ frame_utt, const double* __r
 
 }  // namespace
 
+#ifndef WB_HOST_EMU      // the launcher; tests/emu has its own
 bool stonemask_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
                    const double* frame_t, const double* f0_in, double* f0_out) {
   Context* c = ctx();
@@ -155,5 +156,7 @@ bool stonemask_run(const UttView& u, int fs, int total_frames, const int* frame_
   WB_LAUNCH_CHECK(); kt1.stop();
   return true;
 }
+
+#endif  // WB_HOST_EMU
 
 }  // namespace wb

@@ -121,5 +121,10 @@ inline void sincospif(float a, float* s, float* c) {
   const double x = 3.14159265358979323846 * (double)a;
   *s = (float)sin(x); *c = (float)cos(x);
 }
+inline int atomicMax(int* p, int v) {
+  int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
 using std::max;
 using std::min;

@@ -3,6 +3,7 @@
 // inside python).  Reads <dir>/{x,t,f0}.f64 and <dir>/rows.i32 (48 kHz, fft_size 2048):
 //   emu_main <dir> <mode> <threshold>      D4C (default build): writes <dir>/ap.f64
 //   emu_main <dir>                         CheapTrick (-DEMU_CHEAPTRICK): writes <dir>/sp.f64
+//   emu_main <dir> <fs>                    StoneMask (-DEMU_STONEMASK): f0.f64 = raw F0, writes <dir>/f0_refined.f64
 // and exits with the harness's return code.
 #include <cstdio>
 #include <cstdlib>
@@ -10,6 +11,8 @@
 #include <vector>
 extern "C" int emu_cheaptrick(const double* x, int x_len, int fs, const double* t, const double* f0, int F, int fft_size,
                               double q1, const int* rows, int n_rows, double* sp_rows);
+extern "C" int emu_stonemask(const double* x, int x_len, int fs, const double* t, const double* f0, int F, const int* rows,
+                             int n_rows, double* f0_rows);
 extern "C" int emu_d4c(const double* x, int x_len, int fs, const double* t, const double* f0, int F, int fft_size,
                        double threshold, int mode, const int* rows, int n_rows, double* ap_rows, double* ap0_out);
 template <typename T>
@@ -35,7 +38,13 @@ int main(int argc, char** argv) {
   const auto x = slurp<double>(dir + "/x.f64"), t = slurp<double>(dir + "/t.f64"), f0 = slurp<double>(dir + "/f0.f64");
   const auto rows = slurp<int>(dir + "/rows.i32");
   std::vector<double> out(rows.size() * 1025);
-#ifdef EMU_CHEAPTRICK
+#if defined(EMU_STONEMASK)
+  if (argc < 3) return 92;
+  out.resize(rows.size());
+  const int rc = emu_stonemask(x.data(), (int)x.size(), atoi(argv[2]), t.data(), f0.data(), (int)f0.size(), rows.data(),
+                               (int)rows.size(), out.data());
+  dump(dir + "/f0_refined.f64", out);
+#elif defined(EMU_CHEAPTRICK)
   const int rc = emu_cheaptrick(x.data(), (int)x.size(), 48000, t.data(), f0.data(), (int)f0.size(), 2048, -0.15, rows.data(),
                                 (int)rows.size(), out.data());
   dump(dir + "/sp.f64", out);

@@ -1,5 +1,5 @@
-"""CPU: the D4C kernels of hts-train-world_b200/csrc/wb_d4c.cu and the CheapTrick kernel of
-wb_cheaptrick.cu, compiled for the CPU by the CUDA-on-CPU shim of tests/emu/ (every CUDA thread an OS thread, one CTA at a time), against the
+"""CPU: the D4C kernels of hts-train-world_b200/csrc/wb_d4c.cu, the CheapTrick kernel of
+wb_cheaptrick.cu and the StoneMask kernel of wb_stonemask.cu, compiled for the CPU by the CUDA-on-CPU shim of tests/emu/ (every CUDA thread an OS thread, one CTA at a time), against the
 golden vectors and the compiled reference.  It checks the SOURCE of the kernels -- indices, layouts,
 barrier placement as far as logic goes -- without a GPU; the GPU parity tests check the binaries.
 
@@ -173,3 +173,33 @@ def test_cheaptrick_kernel_source(tmp_path, reference_lib):
     assert M.lsd_db(ref[rows], np.fromfile(tmp_path / "sp.f64").reshape(len(rows), -1))[1] <= 1e-4
     p = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, env=dict(env, WBEMU_SKIP_BARRIER="12"), timeout=900)
     assert p.stderr.count("WARNING: ThreadSanitizer") > 0          # the detector is live
+
+
+@pytest.mark.parametrize("name", ["synthetic48k_u7", "arctic_a0001", "vaiueo2d"])
+def test_stonemask_kernel_source(tmp_path, name):
+    """stonemask_kernel (run-time transform sizes, FP32 spectra) on the golden raw F0 of three
+    sampling rates: voicing identical, refined F0 within 2e-6; the 48 kHz case again under
+    ThreadSanitizer."""
+    so = str(tmp_path / "libsm_emu.so")
+    assert _build(["stonemask_emu.cpp"], so, ["-fPIC", "-shared"]).returncode == 0
+    lib = C.CDLL(so)
+    g = load_golden(name)
+    x, fs, t, f0r = _x(g), int(g["fs"]), g["t"].astype(np.float64), g["f0_raw"].astype(np.float64)
+    rows = np.arange(0, len(t), 3, dtype=np.int32)
+    out = np.zeros(len(rows))
+    assert lib.emu_stonemask(x.ctypes.data_as(dp), len(x), fs, t.ctypes.data_as(dp), f0r.ctypes.data_as(dp), len(t),
+                             rows.ctypes.data_as(ip), len(rows), out.ctypes.data_as(dp)) == 0
+    ref = g["f0"][rows]
+    assert M.vuv_agreement(ref, out) == 1.0 and M.f0_rel_error(ref, out) <= 2e-6
+    if name != "synthetic48k_u7":
+        return
+    exe = str(tmp_path / "sm_tsan")
+    if _build(["stonemask_emu.cpp", "emu_main.cpp"], exe, ["-g", "-fsanitize=thread", "-DEMU_STONEMASK"]).returncode != 0:
+        pytest.skip("no ThreadSanitizer runtime")
+    x.tofile(tmp_path / "x.f64"); t.tofile(tmp_path / "t.f64"); f0r.tofile(tmp_path / "f0.f64"); rows[::4].copy().tofile(tmp_path / "rows.i32")
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0")
+    p = subprocess.run([exe, str(tmp_path), str(fs)], capture_output=True, text=True, env=env, timeout=900)
+    if "unexpected memory mapping" in p.stderr:
+        pytest.skip("ThreadSanitizer cannot map its shadow memory here")
+    assert (p.returncode, p.stderr.count("WARNING: ThreadSanitizer")) == (0, 0), p.stderr[:2000]
+    assert M.f0_rel_error(ref[::4], np.fromfile(tmp_path / "f0_refined.f64")) <= 2e-6
