@@ -7,6 +7,7 @@ single precision) and reports the aperiodicity error against the all-double run,
 precision change in a kernel can be judged BEFORE it is written:
 
     python tests/precision_study.py [--quick]        # 12 signals, ~45 s
+    python tests/precision_study.py --kernels        # the FP32 transforms today's kernels use, on the hard inputs
 
 Variants of the centroid pair (GetCentroid :90-119; X = FFT(v), Xt = FFT((n + 1) v)):
   f64        : the reference arithmetic
