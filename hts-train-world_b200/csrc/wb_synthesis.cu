@@ -452,7 +452,7 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
                   const double* __restrict__ dc_remover, SynthConst c, double* __restrict__ y_all) {
   using R = scalar_t<C>;
   constexpr int TWL = LOG2N > 0 ? LOG2N : kTwLog2;       // compact twiddle table of this size, or the master table
-  extern __shared__ double2 smem2[];
+  WB_DYN_SMEM(double2, smem2);
   const int log2n = LOG2N > 0 ? LOG2N : c.log2n;
   const int N = 1 << log2n, half = N >> 1;
   constexpr int T = THREADS;
@@ -484,7 +484,9 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
       const ChanInfo& ci = r < 4 ? c0 : c1;
       const size_t row = ci.row0 + ((r & 1) ? ci.fr_ceil : ci.fr_floor);
       const char* ptr = reinterpret_cast<const char*>(((r & 2) ? ap_all : sp_all) + row * (half + 1)) + (size_t)(i % lines) * 128;
+#ifndef WB_HOST_EMU
       asm volatile("prefetch.global.L2 [%0];" :: "l"(ptr));
+#endif
     }
   }
   // ---- noise of both channels (:19-33) -----------------------------------------------------------
@@ -632,6 +634,7 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
 
 }  // namespace
 
+#ifndef WB_HOST_EMU      // the launcher; tests/emu has its own
 bool synthesis_run(Batch* b, const int* y_len) {
   Context* ctxp = ctx();
   if (!ctxp) return false;
@@ -756,5 +759,7 @@ bool synthesis_run(Batch* b, const int* y_len) {
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
   return true;
 }
+
+#endif  // WB_HOST_EMU
 
 }  // namespace wb

@@ -76,6 +76,19 @@ inline void launch(const std::vector<int>& blocks, int grid, int threads, size_t
       if (dyn_smem[smem_bytes + i] != 0xA5) { ++smem_overruns; break; }
   }
 }
+// a whole 2-D grid, x fastest
+template <typename F>
+inline void launch_grid(int gx, int gy, int threads, size_t smem_bytes, F body) {
+  g_dim.y = gy;
+  for (int y = 0; y < gy; ++y) {
+    b_idx.y = y;
+    std::vector<int> xs(gx);
+    for (int i = 0; i < gx; ++i) xs[i] = i;
+    launch(xs, gx, threads, smem_bytes, body);
+  }
+  b_idx.y = 0;
+  g_dim.y = 1;
+}
 }  // namespace wbemu
 
 #undef __shared__
@@ -120,6 +133,23 @@ inline void sincospi(double a, double* s, double* c) {
 inline void sincospif(float a, float* s, float* c) {
   const double x = 3.14159265358979323846 * (double)a;
   *s = (float)sin(x); *c = (float)cos(x);
+}
+#define __any_sync(m, pred) (::wbemu::reduce((int)((pred) ? 1 : 0), [](int a, int b) { return a | b; }) != 0)
+#define __ballot_sync(m, pred) ::wbemu::reduce((unsigned)((pred) ? (1u << (::wbemu::t_idx.x & 31)) : 0u), [](unsigned a, unsigned b) { return a | b; })
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline void __sincosf(float a, float* s, float* c) { *s = sinf(a); *c = cosf(a); }
+inline float __logf(float a) { return logf(a); }
+inline float __expf(float a) { return expf(a); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline double atomicAdd(double* p, double v) {
+  uint64_t old = __atomic_load_n(reinterpret_cast<uint64_t*>(p), __ATOMIC_SEQ_CST), neu;
+  double d;
+  do {
+    memcpy(&d, &old, 8);
+    const double sum = d + v;
+    memcpy(&neu, &sum, 8);
+  } while (!__atomic_compare_exchange_n(reinterpret_cast<uint64_t*>(p), &old, neu, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+  return d;
 }
 inline int atomicMax(int* p, int v) {
   int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);

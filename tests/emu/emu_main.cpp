@@ -4,6 +4,7 @@
 //   emu_main <dir> <mode> <threshold>      D4C (default build): writes <dir>/ap.f64
 //   emu_main <dir>                         CheapTrick (-DEMU_CHEAPTRICK): writes <dir>/sp.f64
 //   emu_main <dir> <fs>                    StoneMask (-DEMU_STONEMASK): f0.f64 = raw F0, writes <dir>/f0_refined.f64
+//   emu_main <dir>                         Synthesis (-DEMU_SYNTHESIS): f0.f64, sp.f64, ap.f64 (1025 bins), writes <dir>/y.f64
 // and exits with the harness's return code.
 #include <cstdio>
 #include <cstdlib>
@@ -13,6 +14,8 @@ extern "C" int emu_cheaptrick(const double* x, int x_len, int fs, const double* 
                               double q1, const int* rows, int n_rows, double* sp_rows);
 extern "C" int emu_stonemask(const double* x, int x_len, int fs, const double* t, const double* f0, int F, const int* rows,
                              int n_rows, double* f0_rows);
+extern "C" int emu_synthesis(const double* f0, int F, const double* sp, const double* ap, int fft_size, double frame_period_ms,
+                             int fs, int y_length, double* y_out);
 extern "C" int emu_d4c(const double* x, int x_len, int fs, const double* t, const double* f0, int F, int fft_size,
                        double threshold, int mode, const int* rows, int n_rows, double* ap_rows, double* ap0_out);
 template <typename T>
@@ -35,10 +38,22 @@ static void dump(const std::string& path, const std::vector<double>& v) {
 int main(int argc, char** argv) {
   if (argc < 2) return 92;
   const std::string dir = argv[1];
+#ifdef EMU_SYNTHESIS
+  {
+    const auto f0 = slurp<double>(dir + "/f0.f64"), sp = slurp<double>(dir + "/sp.f64"), ap = slurp<double>(dir + "/ap.f64");
+    const int F = (int)f0.size(), y_length = static_cast<int>((F - 1) * 5.0 / 1000.0 * 48000) + 1;
+    std::vector<double> y(y_length);
+    const int rc = emu_synthesis(f0.data(), F, sp.data(), ap.data(), 2048, 5.0, 48000, y_length, y.data());
+    dump(dir + "/y.f64", y);
+    return rc;
+  }
+#endif
   const auto x = slurp<double>(dir + "/x.f64"), t = slurp<double>(dir + "/t.f64"), f0 = slurp<double>(dir + "/f0.f64");
   const auto rows = slurp<int>(dir + "/rows.i32");
   std::vector<double> out(rows.size() * 1025);
-#if defined(EMU_STONEMASK)
+#if defined(EMU_SYNTHESIS)
+  const int rc = 0;
+#elif defined(EMU_STONEMASK)
   if (argc < 3) return 92;
   out.resize(rows.size());
   const int rc = emu_stonemask(x.data(), (int)x.size(), atoi(argv[2]), t.data(), f0.data(), (int)f0.size(), rows.data(),

@@ -1,5 +1,6 @@
 """CPU: the D4C kernels of hts-train-world_b200/csrc/wb_d4c.cu, the CheapTrick kernel of
-wb_cheaptrick.cu and the StoneMask kernel of wb_stonemask.cu, compiled for the CPU by the CUDA-on-CPU shim of tests/emu/ (every CUDA thread an OS thread, one CTA at a time), against the
+wb_cheaptrick.cu, the StoneMask kernel of wb_stonemask.cu and the seven Synthesis kernels of
+wb_synthesis.cu, compiled for the CPU by the CUDA-on-CPU shim of tests/emu/ (every CUDA thread an OS thread, one CTA at a time), against the
 golden vectors and the compiled reference.  It checks the SOURCE of the kernels -- indices, layouts,
 barrier placement as far as logic goes -- without a GPU; the GPU parity tests check the binaries.
 
@@ -203,3 +204,37 @@ def test_stonemask_kernel_source(tmp_path, name):
         pytest.skip("ThreadSanitizer cannot map its shadow memory here")
     assert (p.returncode, p.stderr.count("WARNING: ThreadSanitizer")) == (0, 0), p.stderr[:2000]
     assert M.f0_rel_error(ref[::4], np.fromfile(tmp_path / "f0_refined.f64")) <= 2e-6
+
+
+def test_synthesis_kernels_source(tmp_path, reference_lib):
+    """The whole Synthesis chain (pulse bound, increments, running phase, pulse count / scan / write,
+    classification, synth_item_kernel<11, float2>) on 0.75 s of the 48 kHz fixture, fed the compiled
+    reference's f0 / sp / ap: resynthesis SNR against the reference (the FP32 channel gives ~120 dB,
+    tolerance 60), then the same run under ThreadSanitizer (the overlap-add uses atomics)."""
+    so = str(tmp_path / "libsyn_emu.so")
+    assert _build(["synthesis_emu.cpp"], so, ["-fPIC", "-shared"]).returncode == 0
+    lib = C.CDLL(so)
+    g = load_golden("synthetic48k_u7")
+    fs = int(g["fs"])
+    o = reference_lib.analyze(_x(g)[:36000], fs)
+    f0, sp, ap = (np.ascontiguousarray(o[k], dtype=np.float64) for k in ("f0", "sp", "ap"))
+    assert 0 < np.count_nonzero(f0) < len(f0)                       # voiced and unvoiced pulses
+    n = int(o["fft_size"])
+    ylen = int((len(f0) - 1) * 5.0 / 1000.0 * fs) + 1
+    y_ref = reference_lib.synthesis(f0, sp, ap, n, 5.0, fs)[:ylen]
+    y = np.zeros(ylen)
+    assert lib.emu_synthesis(f0.ctypes.data_as(dp), len(f0), sp.ctypes.data_as(dp), ap.ctypes.data_as(dp), n, C.c_double(5.0), fs,
+                             ylen, y.ctypes.data_as(dp)) == 0
+    assert M.snr_db(y_ref, y) >= 100.0
+    exe = str(tmp_path / "syn_tsan")
+    if _build(["synthesis_emu.cpp", "emu_main.cpp"], exe, ["-g", "-fsanitize=thread", "-DEMU_SYNTHESIS"]).returncode != 0:
+        pytest.skip("no ThreadSanitizer runtime")
+    k = 60                                                             # 0.3 s: enough pulses of both kinds
+    f0[:k].tofile(tmp_path / "f0.f64"); sp[:k].tofile(tmp_path / "sp.f64"); ap[:k].tofile(tmp_path / "ap.f64")
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0")
+    p = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, env=env, timeout=1500)
+    if "unexpected memory mapping" in p.stderr:
+        pytest.skip("ThreadSanitizer cannot map its shadow memory here")
+    assert (p.returncode, p.stderr.count("WARNING: ThreadSanitizer")) == (0, 0), p.stderr[:3000]
+    yk = np.fromfile(tmp_path / "y.f64")
+    assert M.snr_db(reference_lib.synthesis(f0[:k], sp[:k], ap[:k], n, 5.0, fs)[:len(yk)], yk) >= 100.0
