@@ -111,11 +111,19 @@ struct DevBuf {
     if (count <= n && p) return true;
     release();
     if (count == 0) count = 1;
+#ifdef WB_HOST_EMU      // tests/emu: "device" memory is host memory
+    p = static_cast<T*>(calloc(count, sizeof(T)));
+    n = p ? count : 0;
+    return p != nullptr;
+  }
+  void release() { free(p); p = nullptr; n = 0; }
+#else
     if (!WB_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), pool_stream()))) { p = nullptr; n = 0; return false; }
     n = count;
     return true;
   }
   void release() { if (p) cudaFreeAsync(p, pool_stream()); p = nullptr; n = 0; }
+#endif
   ~DevBuf() { release(); }
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;

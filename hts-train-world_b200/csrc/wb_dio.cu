@@ -254,6 +254,7 @@ std::map<std::vector<double>, DioFilterBank*> g_banks;   // keyed by (actual_fs,
 
 }  // namespace
 
+#ifndef WB_HOST_EMU      // the launcher; tests/emu has its own
 bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
   Context* ctxp = ctx();
   if (!ctxp) return false;
@@ -392,5 +393,7 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
   }
   return true;
 }
+
+#endif  // WB_HOST_EMU
 
 }  // namespace wb

@@ -194,7 +194,7 @@ ols_filter_kernel(const double* __restrict__ x_all, const long long* __restrict_
                   const long long* __restrict__ F_off, const double2* __restrict__ G,
                   const double2* __restrict__ tw, OlsConst c, const int* __restrict__ shift_all, int utt0,
                   double* __restrict__ F) {
-  extern __shared__ double2 smem2[];
+  WB_DYN_SMEM(double2, smem2);
   const int u = utt0 + blockIdx.y;
   const int y_len = y_len_all[u];
   const int n0 = blockIdx.x * c.V;

@@ -4,6 +4,7 @@
 //   emu_main <dir> <mode> <threshold>      D4C (default build): writes <dir>/ap.f64
 //   emu_main <dir>                         CheapTrick (-DEMU_CHEAPTRICK): writes <dir>/sp.f64
 //   emu_main <dir> <fs>                    StoneMask (-DEMU_STONEMASK): f0.f64 = raw F0, writes <dir>/f0_refined.f64
+//   emu_main <dir>                         Dio (-DEMU_DIO): x.f64 only, writes <dir>/f0_raw.f64
 //   emu_main <dir>                         Synthesis (-DEMU_SYNTHESIS): f0.f64, sp.f64, ap.f64 (1025 bins), writes <dir>/y.f64
 // and exits with the harness's return code.
 #include <cstdio>
@@ -16,6 +17,8 @@ extern "C" int emu_stonemask(const double* x, int x_len, int fs, const double* t
                              int n_rows, double* f0_rows);
 extern "C" int emu_synthesis(const double* f0, int F, const double* sp, const double* ap, int fft_size, double frame_period_ms,
                              int fs, int y_length, double* y_out);
+extern "C" int emu_dio(const double* x, int x_len, int fs, double f0_floor, double f0_ceil, double channels_in_octave,
+                       double frame_period, double allowed_range, double* f0_out);
 extern "C" int emu_d4c(const double* x, int x_len, int fs, const double* t, const double* f0, int F, int fft_size,
                        double threshold, int mode, const int* rows, int n_rows, double* ap_rows, double* ap0_out);
 template <typename T>
@@ -38,6 +41,15 @@ static void dump(const std::string& path, const std::vector<double>& v) {
 int main(int argc, char** argv) {
   if (argc < 2) return 92;
   const std::string dir = argv[1];
+#ifdef EMU_DIO
+  {
+    const auto x = slurp<double>(dir + "/x.f64");
+    std::vector<double> f0(static_cast<int>(1000.0 * x.size() / 48000 / 5.0) + 1);
+    const int rc = emu_dio(x.data(), (int)x.size(), 48000, 71.0, 800.0, 2.0, 5.0, 0.1, f0.data());
+    dump(dir + "/f0_raw.f64", f0);
+    return rc;
+  }
+#endif
 #ifdef EMU_SYNTHESIS
   {
     const auto f0 = slurp<double>(dir + "/f0.f64"), sp = slurp<double>(dir + "/sp.f64"), ap = slurp<double>(dir + "/ap.f64");
@@ -51,7 +63,7 @@ int main(int argc, char** argv) {
   const auto x = slurp<double>(dir + "/x.f64"), t = slurp<double>(dir + "/t.f64"), f0 = slurp<double>(dir + "/f0.f64");
   const auto rows = slurp<int>(dir + "/rows.i32");
   std::vector<double> out(rows.size() * 1025);
-#if defined(EMU_SYNTHESIS)
+#if defined(EMU_SYNTHESIS) || defined(EMU_DIO)
   const int rc = 0;
 #elif defined(EMU_STONEMASK)
   if (argc < 3) return 92;

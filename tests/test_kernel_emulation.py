@@ -1,6 +1,6 @@
 """CPU: the D4C kernels of hts-train-world_b200/csrc/wb_d4c.cu, the CheapTrick kernel of
-wb_cheaptrick.cu, the StoneMask kernel of wb_stonemask.cu and the seven Synthesis kernels of
-wb_synthesis.cu, compiled for the CPU by the CUDA-on-CPU shim of tests/emu/ (every CUDA thread an OS thread, one CTA at a time), against the
+wb_cheaptrick.cu, the StoneMask kernel of wb_stonemask.cu, the seven Synthesis kernels of
+wb_synthesis.cu and the Dio kernels of wb_dio.cu / wb_zerocross.cuh, compiled for the CPU by the CUDA-on-CPU shim of tests/emu/ (every CUDA thread an OS thread, one CTA at a time), against the
 golden vectors and the compiled reference.  It checks the SOURCE of the kernels -- indices, layouts,
 barrier placement as far as logic goes -- without a GPU; the GPU parity tests check the binaries.
 
@@ -238,3 +238,39 @@ def test_synthesis_kernels_source(tmp_path, reference_lib):
     assert (p.returncode, p.stderr.count("WARNING: ThreadSanitizer")) == (0, 0), p.stderr[:3000]
     yk = np.fromfile(tmp_path / "y.f64")
     assert M.snr_db(reference_lib.synthesis(f0[:k], sp[:k], ap[:k], n, 5.0, fs)[:len(yk)], yk) >= 100.0
+
+
+def test_dio_kernels_source(tmp_path, reference_lib):
+    """The Dio chain (mean, overlap-save band filters, zero-crossing count / scan / write with the
+    one-barrier ballot compaction, candidates, best contour + FixF0Contour) on 0.4 s of the 48 kHz
+    fixture against the compiled reference: voicing identical, raw F0 to 1e-12; a shorter excerpt
+    again under ThreadSanitizer."""
+    so = str(tmp_path / "libdio_emu.so")
+    assert _build(["dio_emu.cpp"], so, ["-fPIC", "-shared"]).returncode == 0
+    lib = C.CDLL(so)
+    g = load_golden("synthetic48k_u7")
+    fs = int(g["fs"])
+    x = np.ascontiguousarray(_x(g)[9600:9600 + 19200])
+
+    def dio(sig):
+        out = np.zeros(int(1000.0 * len(sig) / fs / 5.0) + 1)
+        assert lib.emu_dio(sig.ctypes.data_as(dp), len(sig), fs, C.c_double(71.0), C.c_double(800.0), C.c_double(2.0),
+                           C.c_double(5.0), C.c_double(0.1), out.ctypes.data_as(dp)) == 0
+        return out
+    ref = reference_lib.dio(x, fs)[1]
+    out = dio(x)
+    assert np.count_nonzero(ref) > 10
+    assert M.vuv_agreement(ref, out) == 1.0 and M.f0_rel_error(ref, out) <= 1e-12
+    exe = str(tmp_path / "dio_tsan")
+    if _build(["dio_emu.cpp", "emu_main.cpp"], exe, ["-g", "-fsanitize=thread", "-DEMU_DIO"]).returncode != 0:
+        pytest.skip("no ThreadSanitizer runtime")
+    xs = np.ascontiguousarray(x[:9600])
+    xs.tofile(tmp_path / "x.f64")
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0")
+    p = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, env=env, timeout=1800)
+    if "unexpected memory mapping" in p.stderr:
+        pytest.skip("ThreadSanitizer cannot map its shadow memory here")
+    assert (p.returncode, p.stderr.count("WARNING: ThreadSanitizer")) == (0, 0), p.stderr[:3000]
+    refs = reference_lib.dio(xs, fs)[1]
+    outs = np.fromfile(tmp_path / "f0_raw.f64")
+    assert M.vuv_agreement(refs, outs) == 1.0 and M.f0_rel_error(refs, outs) <= 1e-12
