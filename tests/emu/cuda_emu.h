@@ -65,16 +65,28 @@ inline void launch(const std::vector<int>& blocks, int grid, int threads, size_t
   block_bar = std::make_unique<std::barrier<>>(threads);
   warp_bar.clear();
   for (int w = 0; w < (threads + 31) / 32; ++w) warp_bar.push_back(std::make_unique<std::barrier<>>(32));
-  for (int b : blocks) {
-    b_idx.x = b;
-    memset(dyn_smem + smem_bytes, 0xA5, 4096);
-    std::vector<std::thread> th;
-    for (int i = 0; i < threads; ++i)
-      th.emplace_back([i, &body]() { t_idx.x = i; barrier_no = 0; body(); });
-    for (auto& t : th) t.join();
-    for (int i = 0; i < 4096; ++i)
-      if (dyn_smem[smem_bytes + i] != 0xA5) { ++smem_overruns; break; }
-  }
+  // the CTA's threads are created once per launch and walk the list of CTAs together (thread 0
+  // switches blockIdx and checks the canary between two rendezvous)
+  std::barrier<> cta_bar(threads);
+  auto worker = [&](int i) {
+    t_idx.x = i;
+    for (size_t k = 0; k < blocks.size(); ++k) {
+      if (i == 0) {
+        b_idx.x = blocks[k];
+        memset(dyn_smem + smem_bytes, 0xA5, 4096);
+      }
+      cta_bar.arrive_and_wait();
+      barrier_no = 0;
+      body();
+      cta_bar.arrive_and_wait();
+      if (i == 0)
+        for (int q = 0; q < 4096; ++q)
+          if (dyn_smem[smem_bytes + q] != 0xA5) { ++smem_overruns; break; }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int i = 0; i < threads; ++i) th.emplace_back(worker, i);
+  for (auto& t : th) t.join();
 }
 // a whole 2-D grid, x fastest
 template <typename F>

@@ -70,10 +70,10 @@ def modes(has_split):
 def test_kernels_match_the_golden_rows(emu):
     lib, has_split = emu
     g = load_golden("synthetic48k_u7")
-    rows = g["rows"][::3]
+    rows = g["rows"][::6]
     for mode in modes(has_split):
         ap, _ = run(lib, _x(g), int(g["fs"]), g["t"], g["f0"], int(g["fft_size"]), rows, mode)
-        assert M.ap_abs_error(g["ap_rows"][::3].astype(np.float64), ap) <= 1e-6, mode
+        assert M.ap_abs_error(g["ap_rows"][::6].astype(np.float64), ap) <= 1e-6, mode
 
 
 def test_long_windows_edges_and_threshold(emu, reference_lib):
@@ -84,12 +84,12 @@ def test_long_windows_edges_and_threshold(emu, reference_lib):
     g = load_golden("synthetic48k_u7")
     x, fs, t, n = _x(g), int(g["fs"]), g["t"], int(g["fft_size"])
     f0 = np.where(np.arange(len(t)) % 2 == 0, 75.0, 100.0)
-    rows = [0, 1, 2, 3, 150, 151, len(t) - 2, len(t) - 1]
+    rows = [0, 1, 150, 151, len(t) - 2, len(t) - 1]
     ref = reference_lib.d4c(x, fs, t, f0, n, threshold=0.0)
     for mode in modes(has_split):
         ap, _ = run(lib, x, fs, t, f0, n, rows, mode)
         assert M.ap_abs_error(ref[rows], ap) <= 1e-6, mode
-    rows = list(range(100, 130))
+    rows = list(range(100, 130, 3))
     ref = reference_lib.d4c(x, fs, t, g["f0"], n, threshold=0.85)
     for mode in modes(has_split):
         ap, _ = run(lib, x, fs, t, g["f0"], n, rows, mode, threshold=0.85)
@@ -208,7 +208,7 @@ def test_stonemask_kernel_source(tmp_path, name):
 
 def test_synthesis_kernels_source(tmp_path, reference_lib):
     """The whole Synthesis chain (pulse bound, increments, running phase, pulse count / scan / write,
-    classification, synth_item_kernel<11, float2>) on 0.75 s of the 48 kHz fixture, fed the compiled
+    classification, synth_item_kernel<11, float2>) on 0.5 s of the 48 kHz fixture, fed the compiled
     reference's f0 / sp / ap: resynthesis SNR against the reference (the FP32 channel gives ~120 dB,
     tolerance 60), then the same run under ThreadSanitizer (the overlap-add uses atomics)."""
     so = str(tmp_path / "libsyn_emu.so")
@@ -216,7 +216,7 @@ def test_synthesis_kernels_source(tmp_path, reference_lib):
     lib = C.CDLL(so)
     g = load_golden("synthetic48k_u7")
     fs = int(g["fs"])
-    o = reference_lib.analyze(_x(g)[:36000], fs)
+    o = reference_lib.analyze(_x(g)[12000:36000], fs)
     f0, sp, ap = (np.ascontiguousarray(o[k], dtype=np.float64) for k in ("f0", "sp", "ap"))
     assert 0 < np.count_nonzero(f0) < len(f0)                       # voiced and unvoiced pulses
     n = int(o["fft_size"])
@@ -229,7 +229,7 @@ def test_synthesis_kernels_source(tmp_path, reference_lib):
     exe = str(tmp_path / "syn_tsan")
     if _build(["synthesis_emu.cpp", "emu_main.cpp"], exe, ["-g", "-fsanitize=thread", "-DEMU_SYNTHESIS"]).returncode != 0:
         pytest.skip("no ThreadSanitizer runtime")
-    k = 60                                                             # 0.3 s: enough pulses of both kinds
+    k = 40                                                             # 0.2 s: enough pulses of both kinds
     f0[:k].tofile(tmp_path / "f0.f64"); sp[:k].tofile(tmp_path / "sp.f64"); ap[:k].tofile(tmp_path / "ap.f64")
     env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0")
     p = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, env=env, timeout=1500)
@@ -242,7 +242,7 @@ def test_synthesis_kernels_source(tmp_path, reference_lib):
 
 def test_dio_kernels_source(tmp_path, reference_lib):
     """The Dio chain (mean, overlap-save band filters, zero-crossing count / scan / write with the
-    one-barrier ballot compaction, candidates, best contour + FixF0Contour) on 0.4 s of the 48 kHz
+    one-barrier ballot compaction, candidates, best contour + FixF0Contour) on 0.3 s of the 48 kHz
     fixture against the compiled reference: voicing identical, raw F0 to 1e-12; a shorter excerpt
     again under ThreadSanitizer."""
     so = str(tmp_path / "libdio_emu.so")
@@ -250,7 +250,7 @@ def test_dio_kernels_source(tmp_path, reference_lib):
     lib = C.CDLL(so)
     g = load_golden("synthetic48k_u7")
     fs = int(g["fs"])
-    x = np.ascontiguousarray(_x(g)[9600:9600 + 19200])
+    x = np.ascontiguousarray(_x(g)[9600:9600 + 14400])
 
     def dio(sig):
         out = np.zeros(int(1000.0 * len(sig) / fs / 5.0) + 1)
@@ -264,7 +264,7 @@ def test_dio_kernels_source(tmp_path, reference_lib):
     exe = str(tmp_path / "dio_tsan")
     if _build(["dio_emu.cpp", "emu_main.cpp"], exe, ["-g", "-fsanitize=thread", "-DEMU_DIO"]).returncode != 0:
         pytest.skip("no ThreadSanitizer runtime")
-    xs = np.ascontiguousarray(x[:9600])
+    xs = np.ascontiguousarray(x[:7200])
     xs.tofile(tmp_path / "x.f64")
     env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0")
     p = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, env=env, timeout=1800)
