@@ -239,6 +239,117 @@ def build_shard(args, rank, world):
     return ids, [lengths[i] for i in ids]
 
 
+def verify_against_reference(wb, c, ids, pcm_host, lengths, k):
+    """-> the five north_star metrics over k utterances of the resident batch `c` (worst case of each)."""
+    from oracle import metrics as M
+    from oracle import ref
+    if not os.path.exists(ref.ref_path()):
+        return {"unavailable": "oracle/_ref/libworld_ref.so was not built"}
+    R = ref.load()
+    n = len(lengths)
+    pick = sorted(set(int(round(i * (n - 1) / max(1, k - 1))) for i in range(k))) if n > 1 else [0]
+    offs = np.concatenate([[0], np.cumsum(lengths)])
+    res = {"vuv_agreement": 1.0, "f0_rel_error": 0.0, "lsd_db_max": 0.0, "ap_abs_error": 0.0, "snr_db": 1e9}
+    fft = c.fft_size
+    for u in pick:
+        x = pcm_host[int(offs[u]):int(offs[u + 1])].numpy().astype(np.float64) / 32768.0
+        o = c.utterance(u)
+        tp, f0r = R.dio(x, FS, frame_period=FRAME_PERIOD)
+        f0_ref = R.stonemask(x, FS, tp, f0r)
+        res["vuv_agreement"] = min(res["vuv_agreement"], M.vuv_agreement(f0_ref, o["f0"]))
+        res["f0_rel_error"] = max(res["f0_rel_error"], M.f0_rel_error(f0_ref, o["f0"]))
+        sp_ref = R.cheaptrick(x, FS, tp, o["f0"])
+        ap_ref = R.d4c(x, FS, tp, o["f0"], fft, threshold=0.0)
+        res["lsd_db_max"] = max(res["lsd_db_max"], M.lsd_db(sp_ref, o["sp"])[1])
+        res["ap_abs_error"] = max(res["ap_abs_error"], M.ap_abs_error(ap_ref, o["ap"]))
+        y_ref = R.synthesis(o["f0"], o["sp"], o["ap"], fft, FRAME_PERIOD, FS)
+        res["snr_db"] = min(res["snr_db"], M.snr_db(y_ref, o["y"]))
+    res = {a: float(b) for a, b in res.items()}
+    res["within_tolerance"] = bool(res["vuv_agreement"] >= M.TOL_VUV_AGREEMENT and res["f0_rel_error"] <= M.TOL_F0_REL and
+                                   res["lsd_db_max"] <= M.TOL_LSD_DB and res["ap_abs_error"] <= M.TOL_AP_ABS and
+                                   res["snr_db"] >= M.TOL_SNR_DB)
+    res["tolerances"] = {"vuv_agreement": M.TOL_VUV_AGREEMENT, "f0_rel_error": M.TOL_F0_REL, "lsd_db_max": M.TOL_LSD_DB,
+                         "ap_abs_error": M.TOL_AP_ABS, "snr_db": M.TOL_SNR_DB}
+    res["utterances"] = [int(ids[u]) for u in pick]
+    res["how"] = ("f0 / sp / ap / y of these utterances read back from the batch the timed region processed; reference = "
+                  "oracle/_ref (unmodified WORLD_v2); CheapTrick, D4C and Synthesis compared stage by stage on identical inputs")
+    return res
+
+
+def other_configs(wb, c, args, audio_s, pcm_dev, lengths, stream):
+    """BASELINE.json configs[0], [2], [3] measured in the same run (configs[1] is the headline line,
+    configs[4] is this bench under torchrun).  Device-timed with CUDA events on the library stream."""
+    import torch
+    out = {}
+
+    def dev_timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    # configs[3]: Synthesis only, f0 / sp / ap of the batch already in HBM; the batch is resynthesised
+    # ceil(10 h / batch) times back to back inside one timed region
+    passes = max(1, int(math.ceil(36000.0 / audio_s)))
+    t0 = time.perf_counter()
+    ms = dev_timed(lambda: [c.synthesis() for _ in range(passes)], 1, 1)
+    out["config4_synthesis_only"] = {
+        "workload": "Synthesis only: %d passes over the %d-utterance batch = %.2f h of 48 kHz audio, f0/sp/ap (double) resident in HBM"
+                    % (passes, len(lengths), passes * audio_s / 3600.0),
+        "value": passes * audio_s / (ms * 1e-3), "unit": UNIT, "ms_total": ms, "wall_s": time.perf_counter() - t0}
+    # configs[2]: the Harvest F0 path (71-800 Hz) instead of Dio + StoneMask on the same corpus
+    if args.f0 != "harvest":
+        def step_h():
+            c.set_pcm16_device(pcm_dev)
+            c.analyze(f0="harvest")
+            c.code(MGC_DIM, BAP_DIM)
+            c.synthesis()
+            c.feature_stats()
+        try:
+            wb.kernel_timing(True)
+            wb.kernel_times_reset()
+            ms = dev_timed(step_h, 2, 1)
+            hk = {k: wb.kernel_time(k) for k in ["harvest_iir_kernel", "harvest_filter_kernel", "harvest_zc_kernel",
+                                                 "harvest_refine_kernel", "harvest_fix_kernel", "harvest_smooth_kernel"]}
+            wb.kernel_timing(False)
+            out["config3_harvest"] = {
+                "workload": "%d-utterance corpus, Harvest (71-800 Hz) + CheapTrick + D4C + codec + Synthesis + statistics" % len(lengths),
+                "value": audio_s / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "harvest_stage_ms": wb.stage_times()["harvest"],
+                "kernels_ms_per_step": {k: v[0] / 3.0 for k, v in hk.items() if v[1]}}
+        except Exception as e:          # e.g. out of memory for the band signals of a very large batch
+            out["config3_harvest"] = {"error": str(e)[:300]}
+    # configs[0]: one 3 s 16 kHz utterance through the drop-in C API, host buffers, one call per stage
+    try:
+        from hts_train_world_b200 import signals
+        x = signals.pcm_to_double(signals.make_utterance(11, 16000, duration=3.0)[0])
+
+        def chain():
+            tp, f0r = wb.dio(x, 16000)
+            f0 = wb.stonemask(x, 16000, tp, f0r)
+            sp = wb.cheaptrick(x, 16000, tp, f0)
+            ap = wb.d4c(x, 16000, tp, f0, 1024, threshold=0.0)
+            wb.synthesis(f0, sp, ap, 1024, 5.0, 16000)
+        for _ in range(3):
+            chain()
+        ts = []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            chain()
+            ts.append(time.perf_counter() - t0)
+        out["config1_dropin"] = {"workload": "single 3 s synthetic 16 kHz utterance, drop-in C API, host buffers, one call per stage",
+                                 "value": 3.0 / min(ts), "unit": UNIT, "ms_total": 1e3 * min(ts)}
+    except Exception as e:
+        out["config1_dropin"] = {"error": str(e)[:300]}
+    return out
+
+
+
 def ours_arm(args):
     import torch
     import torch.distributed as dist
@@ -403,7 +514,7 @@ def ours_arm(args):
     ms, wall, stats, (t0, t1) = timed(step_resident, args.steps)
     launches = wb.launch_count() - n0
     kernel_ms = {k: wb.kernel_time(k) for k in
-                 ["d4c_main_kernel", "d4c_lovetrain_kernel", "cheaptrick_kernel", "synth_pulse_kernel",
+                 ["d4c_main_kernel", "d4c_gd_kernel", "d4c_tail_kernel", "d4c_lovetrain_kernel", "cheaptrick_kernel", "synth_pulse_kernel",
                   "synth_timebase_kernel", "stonemask_kernel", "dio_filter_kernel", "dio_zc_kernel",
                   "dio_candidates_kernel", "dio_fix_kernel", "harvest_iir_kernel", "harvest_filter_kernel",
                   "harvest_zc_kernel", "harvest_refine_kernel", "harvest_fix_kernel", "harvest_smooth_kernel",
@@ -434,48 +545,72 @@ def ours_arm(args):
     d2h = y_host.numel() * 2 + f0_host.numel() * 8 + (lf0_host.numel() + mgc_host.numel() + bap_host.numel()) * 4 + \
         (1 + MGC_DIM) * 24
 
+    # ---- parity of the timed configuration (--verify K) ------------------------------------------------
+    # K utterances of the batch the timed region just processed are pulled out of HBM (f0, sp, ap of the
+    # resident leg's last step, y of its Synthesis) and compared with the compiled reference: F0 against
+    # the reference's own Dio + StoneMask chain; CheapTrick / D4C / Synthesis stage by stage, the reference
+    # fed the same upstream values our stage saw -- north_star's five metrics.
+    parity = None
+    if rank == 0 and args.verify > 0 and args.f0 == "dio":
+        parity = verify_against_reference(wb, c, ids, pcm_host, lengths, args.verify)
+
+    # ---- the other BASELINE.json configurations (rank 0, N = 1) -------------------------------------------
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        configs = other_configs(wb, c, args, audio_s, pcm_dev, lengths, stream)
+
     # ---- roofline of the dominant kernel --------------------------------------------------------------
     f0 = f0_host.numpy().copy()
     voiced = f0 > 0
     pv = float((f0[voiced] * FRAME_PERIOD / 1000.0).sum())
     pu = float((~voiced).sum() * 500.0 * FRAME_PERIOD / 1000.0)
-    counts = roofline.stage_counts(FS, f0, sum(lengths), pv, pu, fft_size=c.fft_size, n_utt=len(lengths))
+    counts = roofline.stage_counts(FS, f0, sum(lengths), pv, pu, fft_size=c.fft_size, n_utt=len(lengths),
+                                   lovetrain_fp32=wb.build_info().get("lovetrain_fp32", False))
     fp64_peak = wb.fma_peak_tflops(True)
     fp32_peak = wb.fma_peak_tflops(False)
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    kmap = {"d4c_main_kernel": "d4c_main", "d4c_lovetrain_kernel": "d4c_lovetrain",
-            "cheaptrick_kernel": "cheaptrick", "synth_pulse_kernel": "synthesis",
-            "stonemask_kernel": "stonemask", "dio_filter_kernel": "dio"}
+    kmap = {"d4c_main_kernel": "d4c_main", "d4c_gd_kernel": "d4c_gd", "d4c_tail_kernel": "d4c_tail",
+            "d4c_lovetrain_kernel": "d4c_lovetrain", "cheaptrick_kernel": "cheaptrick",
+            "synth_pulse_kernel": "synthesis", "stonemask_kernel": "stonemask", "dio_filter_kernel": "dio",
+            "codec_encode_kernel": "codec"}
+    # Every kernel against the peak of the precision it EXECUTES in (roofline.py splits the algorithmic
+    # FLOPs of each kernel into its FP64 and FP32 part): bound time = flops64 / peak64 + flops32 / peak32,
+    # or the compulsory bytes over the HBM bandwidth when that is longer.
     kernels = {}
     for k, (tot_ms, n) in kernel_ms.items():
         if n == 0:
             continue
         ent = {"ms_per_launch": tot_ms / n, "launches_per_step": n / args.steps}
-        if k in kmap:
+        if k in kmap and kmap[k] in counts:
             cnt = counts[kmap[k]]
-            per_launch_s = tot_ms * 1e-3 / args.steps      # all launches of this kernel in one step
-            ent["tflops"] = cnt["flops"] / per_launch_s / 1e12
-            ent["gbs"] = cnt["bytes"] / per_launch_s / 1e9
-            ent["frac_fp64"] = ent["tflops"] / fp64_peak if fp64_peak else None
-            ent["frac_hbm"] = ent["gbs"] / hbm_peak
+            per_step_s = tot_ms * 1e-3 / args.steps        # all launches of this kernel in one step
+            t_roof, bound = roofline.roof_seconds(cnt, fp64_peak, fp32_peak, hbm_peak)
+            ent.update({"tflops": cnt["flops"] / per_step_s / 1e12, "fp32_share_of_flops": cnt.get("flops32", 0.0) / cnt["flops"],
+                        "gbs": cnt["bytes"] / per_step_s / 1e9, "bound": bound, "frac": t_roof / per_step_s,
+                        "frac_hbm": cnt["bytes"] / per_step_s / 1e9 / hbm_peak})
         kernels[k] = ent
     dom = max((k for k in kernels if k in kmap), key=lambda k: kernel_ms[k][0])
     dcnt = counts[kmap[dom]]
     dsec = kernel_ms[dom][0] * 1e-3 / args.steps
-    t_flop, t_byte = dcnt["flops"] / (fp64_peak * 1e12), dcnt["bytes"] / (hbm_peak * 1e9)
-    if t_flop >= t_byte:
-        roof = {"bound": "fp64", "achieved": dcnt["flops"] / dsec / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                "peak_source": "measured live: FP64 FMA micro-benchmark on this GPU (nominal 37.2)"}
-    else:
+    t_roof, bound = roofline.roof_seconds(dcnt, fp64_peak, fp32_peak, hbm_peak)
+    if bound == "hbm":
         roof = {"bound": "hbm", "achieved": dcnt["bytes"] / dsec / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}
+    else:
+        # `peak` is the rate at which THIS kernel's precision mix would run with every pipe it uses at its
+        # measured FMA peak: flops / (flops64 / peak64 + flops32 / peak32); an all-FP64 kernel gets peak64.
+        roof = {"bound": bound, "achieved": dcnt["flops"] / dsec / 1e12, "peak": dcnt["flops"] / t_roof / 1e12,
+                "unit": "TFLOP/s",
+                "peak_source": "measured live on this GPU: FMA micro-benchmarks, FP64 %.2f and FP32 %.2f TFLOP/s (nominal 37.2 / 74.4), "
+                               "weighted by the kernel's FP64 / FP32 split of algorithmic FLOPs" % (fp64_peak, fp32_peak)}
     roof.update({"frac": roof["achieved"] / roof["peak"], "traffic": None, "kernel": dom,
-                 "algorithmic_flops_per_launch": dcnt["flops"], "algorithmic_bytes_per_launch": dcnt["bytes"],
+                 "algorithmic_flops_per_launch": dcnt["flops"], "algorithmic_fp32_flops_per_launch": dcnt.get("flops32", 0.0),
+                 "algorithmic_bytes_per_launch": dcnt["bytes"],
                  "units_per_launch": dcnt["units"], "ms_per_launch": dsec * 1e3,
                  "share_of_step": kernel_ms[dom][0] / ms,
-                 "note": "every stage of this path is bound by the CUDA-core FP64 pipe, not HBM or tensor "
+                 "note": "every stage of this path is bound by the CUDA-core floating-point pipes, not HBM or tensor "
                          "cores (SURVEY.md 8d); hbm fraction of the same kernel: %.4f" %
                          (dcnt["bytes"] / dsec / 1e9 / hbm_peak)})
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -484,6 +619,17 @@ def ours_arm(args):
             roof["traffic"] = json.load(open(tp)).get(dom)
         except Exception:
             pass
+    # the whole step: sum of the algorithmic work of every stage over the step time
+    step_keys = ["dio", "stonemask", "cheaptrick", "d4c", "codec", "synthesis"] if args.f0 != "harvest" else \
+        ["cheaptrick", "d4c", "codec", "synthesis"]
+    step_cnt = {"flops": sum(counts[k]["flops"] for k in step_keys), "flops32": sum(counts[k].get("flops32", 0.0) for k in step_keys),
+                "bytes": sum(counts[k]["bytes"] for k in step_keys)}
+    t_step_roof, step_bound = roofline.roof_seconds(step_cnt, fp64_peak, fp32_peak, hbm_peak)
+    step_s = ms * 1e-3 / args.steps
+    roofline_step = {"bound": step_bound, "achieved": step_cnt["flops"] / step_s / 1e12, "peak": step_cnt["flops"] / t_step_roof / 1e12,
+                     "unit": "TFLOP/s", "frac": t_step_roof / step_s, "algorithmic_flops": step_cnt["flops"],
+                     "algorithmic_fp32_flops": step_cnt["flops32"], "algorithmic_bytes": step_cnt["bytes"],
+                     "stages": step_keys, "flops_per_audio_s": step_cnt["flops"] / audio_s}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -506,9 +652,12 @@ def ours_arm(args):
         "wall_ms_per_step": wall / args.steps,
         "stage_ms": stage_ms,
         "roofline": roof,
+        "roofline_step": roofline_step,
         # the same kernel against the memory roofline (it is nowhere near it: the frame lives in shared memory)
         "roofline_hbm": {"bound": "hbm", "achieved": dcnt["bytes"] / dsec / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": dcnt["bytes"] / dsec / 1e9 / hbm_peak, "traffic": roof.get("traffic"), "kernel": dom},
+        "parity": parity,
+        "configs": configs,
         "dtype_note": "FP64 wherever a cancellation follows (power spectra, cumulative sums, group delay, time base); "
                       "FP32 transforms for log spectra / cepstra / noise / band slices (DESIGN.md section 4)",
         "kernels": kernels,
@@ -553,6 +702,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--utts", type=int, default=1132, help="utterances per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", type=int, default=3, help="utterances of the timed batch checked against the compiled reference")
+    ap.add_argument("--no-configs", action="store_true", help="skip the legs of BASELINE configs 1, 3 and 4")
     ap.add_argument("--f0", default="dio", choices=["dio", "harvest"], help="F0 estimator (harvest = BASELINE config 3)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -124,6 +124,7 @@ def lib():
         "wb200_kernel_times_reset": (None, []),
         "wb200_kernel_time": (i32, [C.c_char_p, _dp, C.POINTER(i64)]),
         "wb200_measure_fma_peak": (f64, [i32]),
+        "wb200_option": (i32, [C.c_char_p]),
         "wb200_batch_create": (vp, [i32, f64, i32, _ip]),
         "wb200_batch_destroy": (None, [vp]),
         "wb200_batch_total_frames": (i32, [vp]),
@@ -150,6 +151,7 @@ def lib():
         "wb200_batch_y_layout": (i32, [vp, C.POINTER(i64), _ip]),
         "wb200_batch_get_y": (i32, [vp, vp]),
         "wb200_batch_get_y_pcm16": (i32, [vp, vp]),
+        "wb200_batch_get_utterance": (i32, [vp, i32, vp, vp, vp, vp, vp]),
         "wb200_batch_device_ptr": (vp, [vp, C.c_char_p]),
         "wb200_batch_lf0_stats": (i32, [vp, _dp]),
         "wb200_batch_code": (i32, [vp, i32, i32]),
@@ -218,6 +220,12 @@ def kernel_time(name):
     ms, n = C.c_double(0.0), C.c_longlong(0)
     lib().wb200_kernel_time(name.encode(), C.byref(ms), C.byref(n))
     return ms.value, n.value
+
+
+def build_info():
+    """Run-time switches of the library that change what a kernel executes (bench.py's roofline needs
+    to know the precision of each transform)."""
+    return {"lovetrain_fp32": bool(lib().wb200_option(b"lovetrain_fp32")), "d4c_split": bool(lib().wb200_option(b"d4c_split"))}
 
 
 def fma_peak_tflops(fp64=True):
@@ -464,6 +472,24 @@ class Corpus:
         keep = [None if a is None or hasattr(a, "data_ptr") else np.ascontiguousarray(a, np.float32) for a in (f0, sp, ap)]
         ptrs = [ptr(k if k is not None else a) for k, a in zip(keep, (f0, sp, ap))]
         _check(lib().wb200_batch_set_params_f32(self._h, self.fft_size, *ptrs), "set_params_f32")
+
+    def utterance(self, u, want=("f0_raw", "f0", "sp", "ap", "y")):
+        """One utterance's slice of the results as a dict (spot checks of a corpus-sized batch)."""
+        n, H = int(self.f_len[u]), (self.fft_size or 0) // 2 + 1
+        out = {}
+        if "f0_raw" in want:
+            out["f0_raw"] = np.zeros(n)
+        if "f0" in want:
+            out["f0"] = np.zeros(n)
+        if "sp" in want:
+            out["sp"] = np.zeros((n, H))
+        if "ap" in want:
+            out["ap"] = np.zeros((n, H))
+        if "y" in want:
+            out["y"] = np.zeros(int(self.y_layout()[1][u]))
+        p = [out[k].ctypes.data if k in out else None for k in ("f0_raw", "f0", "sp", "ap", "y")]
+        _check(lib().wb200_batch_get_utterance(self._h, int(u), *p), "get_utterance")
+        return out
 
     def y_layout(self):
         off = np.zeros(self.n_utt, np.int64)

@@ -19,6 +19,7 @@ struct wb200_batch {
   Batch b;
   DevBuf<int16_t> pcm_stage, pcm_out;
   DevBuf<long long> src_off, out_off;   // per-utterance offsets inside the packed 16-bit input / output
+  std::vector<int> out_layout;          // the y_len[] that out_off / pcm_out were built for
   cudaEvent_t upload_done = nullptr;     // recorded on the upload stream by wb200_batch_upload_pcm16_async
   bool upload_pending = false;
   // recorded on the download stream after the asynchronous result copies of this batch: the next
@@ -364,6 +365,7 @@ int wb200_kernel_time(const char* name, double* ms_total, long long* launches) {
   return kernel_time_query(name, ms_total, launches) ? 0 : 1;
 }
 double wb200_measure_fma_peak(int fp64) { return measure_fma_peak(fp64 != 0); }
+int wb200_option(const char* name) { return name ? option(name) : 0; }
 int wb200_sync(void) {
   Context* c = ctx();
   if (!c) return 1;
@@ -603,20 +605,34 @@ int wb200_batch_get_y(wb200_batch* h, double* out) {
   }
   return WB_CUDA(cudaStreamSynchronize(c->stream)) ? 0 : 1;
 }
+// 16-bit staging of the waveform: pcm_out and the per-utterance output offsets are (re)built whenever
+// the y layout of the last Synthesis call differs from the one they were built for (y_lengths is a
+// per-call argument of wb200_batch_synthesis).  An asynchronous copy of the previous pass may still
+// read pcm_out, so the library stream first waits for it -- before the buffer can be re-allocated.
+static bool prepare_pcm_out(wb200_batch* h, long long n) {
+  Context* c = ctx();
+  Batch& b = h->b;
+  if (!wait_downloads(h, kDlWave)) return false;
+  if (h->pcm_out.p && h->out_off.p && h->out_layout == b.h_y_len && h->pcm_out.n >= (size_t)n + 1) return true;
+  std::vector<long long> cum(b.n_utt > 0 ? b.n_utt : 1);
+  long long o = 0;
+  for (int u = 0; u < b.n_utt; ++u) { cum[u] = o; o += b.h_y_len[u]; }
+  if (!h->pcm_out.alloc((size_t)n + 1) || !h->out_off.alloc(b.n_utt)) return false;
+  if (b.n_utt > 0 &&
+      (!WB_CUDA(cudaMemcpyAsync(h->out_off.p, cum.data(), b.n_utt * sizeof(long long), cudaMemcpyHostToDevice, c->stream)) ||
+       !WB_CUDA(cudaStreamSynchronize(c->stream))))            // cum is a host temporary
+    return false;
+  h->out_layout = b.h_y_len;
+  return true;
+}
 int wb200_batch_get_y_pcm16(wb200_batch* h, int16_t* out) {
   Context* c = ctx();
   Batch& b = h->b;
   if (!c || !b.y.p) { set_error("synthesis has not been run"); return 1; }
   const long long n = wb200_batch_total_y(h);
-  std::vector<long long> cum(b.n_utt > 0 ? b.n_utt : 1);
-  long long o = 0;
-  for (int u = 0; u < b.n_utt; ++u) { cum[u] = o; o += b.h_y_len[u]; }
-  DevBuf<long long> d_cum;
-  if (!h->pcm_out.alloc((size_t)n + 1) || !d_cum.alloc(b.n_utt)) return 1;
   if (b.n_utt == 0 || n == 0) return 0;
-  if (!WB_CUDA(cudaMemcpyAsync(d_cum.p, cum.data(), b.n_utt * sizeof(long long), cudaMemcpyHostToDevice, c->stream))) return 1;
-  if (!wait_downloads(h, kDlWave)) return 1;
-  y_to_pcm16_kernel<<<dim3(64, b.n_utt), 256, 0, c->stream>>>(b.y.p, b.y_off.p, d_cum.p, b.y_len.p, h->pcm_out.p);
+  if (!prepare_pcm_out(h, n)) return 1;
+  y_to_pcm16_kernel<<<dim3(64, b.n_utt), 256, 0, c->stream>>>(b.y.p, b.y_off.p, h->out_off.p, b.y_len.p, h->pcm_out.p);
   WB_LAUNCH_CHECK();
   return (WB_CUDA(cudaMemcpyAsync(out, h->pcm_out.p, (size_t)n * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream)) &&
           WB_CUDA(cudaStreamSynchronize(c->stream))) ? 0 : 1;
@@ -630,21 +646,31 @@ int wb200_batch_get_y_pcm16_async(wb200_batch* h, int16_t* out) {
   if (!ensure_copy_streams(c)) return 1;
   const long long n = wb200_batch_total_y(h);
   if (b.n_utt == 0 || n == 0) return 0;
-  if (!h->pcm_out.p || !h->out_off.p) {
-    std::vector<long long> cum(b.n_utt);
-    long long o = 0;
-    for (int u = 0; u < b.n_utt; ++u) { cum[u] = o; o += b.h_y_len[u]; }
-    if (!h->pcm_out.alloc((size_t)n + 1) || !h->out_off.alloc(b.n_utt)) return 1;
-    if (!WB_CUDA(cudaMemcpyAsync(h->out_off.p, cum.data(), b.n_utt * sizeof(long long), cudaMemcpyHostToDevice, c->stream)) ||
-        !WB_CUDA(cudaStreamSynchronize(c->stream)))
-      return 1;
-  }
-  if (!wait_downloads(h, kDlWave)) return 1;           // the previous pass's copy may still read pcm_out
+  if (!prepare_pcm_out(h, n)) return 1;                // also: the previous pass's copy may still read pcm_out
   y_to_pcm16_kernel<<<dim3(64, b.n_utt), 256, 0, c->stream>>>(b.y.p, b.y_off.p, h->out_off.p, b.y_len.p, h->pcm_out.p);
   WB_LAUNCH_CHECK();
   return (WB_CUDA(cudaEventRecord(c->copy_event, c->stream)) && WB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_event, 0)) &&
           WB_CUDA(cudaMemcpyAsync(out, h->pcm_out.p, (size_t)n * sizeof(int16_t), cudaMemcpyDeviceToHost, c->copy_stream)) &&
           mark_downloads(h, kDlWave)) ? 0 : 1;
+}
+// one utterance's slice of every result (any pointer may be NULL)
+int wb200_batch_get_utterance(wb200_batch* h, int utt, double* f0_raw, double* f0, double* sp, double* ap, double* y) {
+  Context* c = ctx();
+  Batch& b = h->b;
+  if (!c) return 1;
+  if (utt < 0 || utt >= b.n_utt) { set_error("get_utterance: utterance %d of %d", utt, b.n_utt); return 1; }
+  const size_t fo = (size_t)b.h_f_off[utt], fl = (size_t)b.h_f_len[utt], H = (size_t)(b.fft_size / 2 + 1);
+  struct { double* dst; const double* src; size_t n; } parts[5] = {
+      {f0_raw, b.f0_raw.p ? b.f0_raw.p + fo : nullptr, fl}, {f0, b.f0.p ? b.f0.p + fo : nullptr, fl},
+      {sp, b.sp.p ? b.sp.p + fo * H : nullptr, fl * H}, {ap, b.ap.p ? b.ap.p + fo * H : nullptr, fl * H},
+      {y, b.y.p && (size_t)utt < b.h_y_len.size() ? b.y.p + b.h_y_off[utt] : nullptr,
+       (size_t)utt < b.h_y_len.size() ? (size_t)b.h_y_len[utt] : 0}};
+  for (auto& q : parts) {
+    if (!q.dst || q.n == 0) continue;
+    if (!q.src) { set_error("get_utterance: result not available (stage not run?)"); return 1; }
+    if (!WB_CUDA(cudaMemcpyAsync(q.dst, q.src, q.n * sizeof(double), cudaMemcpyDeviceToHost, c->stream))) return 1;
+  }
+  return WB_CUDA(cudaStreamSynchronize(c->stream)) ? 0 : 1;
 }
 void* wb200_batch_device_ptr(wb200_batch* h, const char* which) {
   Batch& b = h->b;

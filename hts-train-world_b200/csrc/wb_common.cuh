@@ -92,6 +92,7 @@ struct KernelTimer {
   const char* name_;
   cudaEvent_t e0_ = nullptr, e1_ = nullptr;
 };
+int option(const char* name);           // run-time switch (wb_context.cu), 0 / 1
 double measure_fma_peak(bool fp64);       // TFLOP/s of the CUDA-core FMA pipe, measured
 void set_stream(cudaStream_t s);          // run everything on a caller-owned stream
 void kernel_timing_enable(bool on);

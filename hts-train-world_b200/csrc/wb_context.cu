@@ -206,6 +206,28 @@ static double fma_peak(Context* c) {
   cudaFree(d);
   return best;
 }
+// Run-time switches (read once from the environment; `1` / `0` override the default).  They select
+// between kernels that compute the same result -- A/B measurements, and bench.py's roofline needs to
+// know which precision ran.
+int option(const char* name) {
+  struct Opt { const char* name; const char* env; int def; int val; };
+  static Opt opts[] = {
+      {"d4c_split", "WB_D4C_SPLIT", 0, -1},            // D4C as FP64 group-delay kernel + FP32 tail kernel (3 CTAs / SM each)
+      {"lovetrain_fp32", "WB_D4C_LT32", 0, -1},        // LoveTrain's transform in FP32
+  };
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  for (Opt& o : opts) {
+    if (strcmp(o.name, name) != 0) continue;
+    if (o.val < 0) {
+      const char* e = getenv(o.env);
+      o.val = e ? (e[0] != '0' && e[0] != '\0') : o.def;
+    }
+    return o.val;
+  }
+  return 0;
+}
+
 double measure_fma_peak(bool fp64) {
   Context* c = ctx();
   if (!c) return 0.0;

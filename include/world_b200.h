@@ -45,6 +45,9 @@ WORLD_API int wb200_kernel_time(const char *name, double *ms_total, long long *l
 /* measured CUDA-core FMA peak in TFLOP/s (fp64 != 0: double, else float) — the roofline
  * denominator of SURVEY.md 8(d) */
 WORLD_API double wb200_measure_fma_peak(int fp64);
+/* state (0 / 1) of a run-time switch of the library: "d4c_split", "lovetrain_fp32" (environment
+ * WB_D4C_SPLIT / WB_D4C_LT32 = 0 | 1 override the defaults); unknown names give 0 */
+WORLD_API int wb200_option(const char *name);
 /* first `n` values of the randn table as doubles (test hook: must equal the reference's
  * randn() stream after randn_reseed(), W/src/matlabfunctions.cpp:247-277) */
 WORLD_API int wb200_randn_stream(double *out, long long n);
@@ -98,6 +101,10 @@ WORLD_API int wb200_batch_get_y(wb200_batch *b, double *host_y);     /* back to 
 WORLD_API int wb200_batch_get_y_pcm16(wb200_batch *b, int16_t *host_pcm);
 /* asynchronous variant on a download stream (pinned `host_pcm`, valid after wb200_sync()) */
 WORLD_API int wb200_batch_get_y_pcm16_async(wb200_batch *b, int16_t *host_pcm);
+/* one utterance's slice of the results (any pointer may be NULL): f0_raw / f0 [f_len], sp / ap
+ * [f_len][fft_size/2+1], y [y_len] -- spot checks of a corpus-sized batch without copying all of it */
+WORLD_API int wb200_batch_get_utterance(wb200_batch *b, int utt, double *host_f0_raw, double *host_f0,
+                                        double *host_sp, double *host_ap, double *host_y);
 /* device pointers for zero-copy consumers: which = "x","f0_raw","f0","sp","ap","y" */
 WORLD_API void *wb200_batch_device_ptr(wb200_batch *b, const char *which);
 /* corpus statistics of voiced log-f0 over the batch: out = {count, sum, sum of squares};

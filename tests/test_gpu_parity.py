@@ -459,3 +459,75 @@ def test_back_to_back_passes_with_asynchronous_copies(wb):
         # the overlap-add uses floating-point atomics: the last bit of y depends on their order, which can
         # move a truncated 16-bit sample by one step
         assert np.max(np.abs(b["y"].numpy().astype(np.int32) - y.astype(np.int32))) <= 1, it
+
+
+# ---- sampling rates whose transform sizes / band counts no other test reaches ----------------------
+# fs -> (CheapTrick N, D4C internal size, LoveTrain size, aperiodicity bands):
+#    8 000 -> ( 512,  1024,  1024, 0)   run-time-size templates, no band at all (W/src/d4c.cpp:351-353)
+#   24 000 -> (1024,  2048,  2048, 3)   odd band count: the last band transform carries one band
+#   32 000 -> (2048,  4096,  4096, 4)
+#   44 100 -> (2048,  4096,  4096, 5)
+#   96 000 -> (4096,  8192,  8192, 5)   512-thread D4C launch + histogram selection, run-time LoveTrain size
+@pytest.mark.parametrize("fs", [8000, 24000, 32000, 44100, 96000])
+def test_other_sampling_rates(wb, reference_lib, fs):
+    """Every stage against the compiled reference, each fed the reference's upstream outputs
+    (W/src/d4c.cpp:344-357, W/src/cheaptrick.cpp:191-194 give the sizes above)."""
+    from hts_train_world_b200 import signals
+    x = signals.pcm_to_double(signals.make_utterance(50 + fs // 1000, fs, duration=0.9)[0])
+    o = reference_lib.analyze(x, fs)
+    t, f0r = wb.dio(x, fs)
+    assert np.array_equal(t, o["t"])
+    assert M.vuv_agreement(o["f0_raw"], f0r) >= M.TOL_VUV_AGREEMENT
+    assert M.f0_rel_error(o["f0_raw"], f0r) <= M.TOL_F0_REL
+    f0 = wb.stonemask(x, fs, o["t"], o["f0_raw"])
+    assert M.vuv_agreement(o["f0"], f0) >= M.TOL_VUV_AGREEMENT
+    assert M.f0_rel_error(o["f0"], f0) <= M.TOL_F0_REL
+    assert np.count_nonzero(o["f0"]) > 20
+    sp = wb.cheaptrick(x, fs, o["t"], o["f0"])
+    assert sp.shape == o["sp"].shape
+    assert M.lsd_db(o["sp"], sp)[1] <= M.TOL_LSD_DB
+    ap = wb.d4c(x, fs, o["t"], o["f0"], o["fft_size"])            # threshold 0, the analysis tool's setting
+    assert M.ap_abs_error(o["ap"], ap) <= M.TOL_AP_ABS
+    if fs >= 16000:   # below 15.8 kHz the reference's LoveTrain reads uninitialised memory (d4c.cpp:243-246)
+        ap_ref = reference_lib.d4c(x, fs, o["t"], o["f0"], o["fft_size"], threshold=0.85)
+        assert M.ap_abs_error(ap_ref, wb.d4c(x, fs, o["t"], o["f0"], o["fft_size"], threshold=0.85)) <= M.TOL_AP_ABS
+    y_ref = reference_lib.synthesis(o["f0"], o["sp"], o["ap"], o["fft_size"], 5.0, fs)
+    y = wb.synthesis(o["f0"], o["sp"], o["ap"], o["fft_size"], 5.0, fs)
+    assert M.snr_db(y_ref, y) >= M.TOL_SNR_DB
+    _, fh_ref = reference_lib.harvest(x, fs)
+    _, fh = wb.harvest(x, fs)
+    assert M.vuv_agreement(fh_ref, fh) >= M.TOL_VUV_AGREEMENT and M.f0_rel_error(fh_ref, fh) <= M.TOL_F0_REL
+
+
+# ---- the inputs the precision study (tests/precision_study.py, profiles/README.md) calls decisive ----
+def _hard_inputs():
+    from scipy.signal import resample_poly
+    from hts_train_world_b200 import signals
+    g = load_golden("arctic_a0001")
+    x16 = _x(g)[:32000]
+    out = {"band_limited": np.round(np.clip(resample_poly(x16, 3, 1), -1, 1) * 32767.0) / 32768.0}
+    x = signals.pcm_to_double(signals.make_utterance(3, 48000, duration=1.2)[0])
+    out["dc_offset"] = x * 0.5 + 0.3
+    out["quiet_7bit"] = np.round(x * 32768.0 / 256.0) / 32768.0
+    return out
+
+
+@pytest.mark.parametrize("case", ["band_limited", "dc_offset", "quiet_7bit"])
+def test_hard_inputs(wb, reference_lib, case):
+    """16 kHz real speech delivered at 48 kHz (the aperiodicity bands at 9-15 kHz hold quantisation
+    noise 90 dB below the peak: the input on which single-precision centroid / power-spectrum
+    transforms miss the tolerance), a DC offset of 0.3 and a recording at -48 dB: every stage that
+    runs a single-precision transform (StoneMask, CheapTrick liftering, D4C bands, Synthesis) plus
+    Dio, against the compiled reference fed the reference's upstream outputs."""
+    x, fs = _hard_inputs()[case], 48000
+    o = reference_lib.analyze(x, fs)
+    t, f0_raw = wb.dio(x, fs)
+    assert M.vuv_agreement(o["f0_raw"], f0_raw) >= M.TOL_VUV_AGREEMENT and M.f0_rel_error(o["f0_raw"], f0_raw) <= M.TOL_F0_REL
+    f0 = wb.stonemask(x, fs, o["t"], o["f0_raw"])
+    assert M.vuv_agreement(o["f0"], f0) >= M.TOL_VUV_AGREEMENT and M.f0_rel_error(o["f0"], f0) <= M.TOL_F0_REL
+    assert M.lsd_db(o["sp"], wb.cheaptrick(x, fs, o["t"], o["f0"]))[1] <= M.TOL_LSD_DB
+    assert M.ap_abs_error(o["ap"], wb.d4c(x, fs, o["t"], o["f0"], o["fft_size"])) <= M.TOL_AP_ABS
+    ap_ref = reference_lib.d4c(x, fs, o["t"], o["f0"], o["fft_size"], threshold=0.85)
+    assert M.ap_abs_error(ap_ref, wb.d4c(x, fs, o["t"], o["f0"], o["fft_size"], threshold=0.85)) <= M.TOL_AP_ABS
+    y_ref = reference_lib.synthesis(o["f0"], o["sp"], o["ap"], o["fft_size"], 5.0, fs)
+    assert M.snr_db(y_ref, wb.synthesis(o["f0"], o["sp"], o["ap"], o["fft_size"], 5.0, fs)) >= M.TOL_SNR_DB
