@@ -14,6 +14,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libworld_b200.so")
+if os.environ.get("WB200_LIB"):          # an experimental build of the same sources (build.py --variant): A/B measurements
+    LIB_PATH = os.path.join(_HERE, os.environ["WB200_LIB"]) if not os.path.isabs(os.environ["WB200_LIB"]) else os.environ["WB200_LIB"]
 
 
 class DioOption(C.Structure):          # W/src/world/dio.h:16-23

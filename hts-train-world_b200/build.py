@@ -44,7 +44,23 @@ def _compile(src, obj, log):
     return obj
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant / defines: an experimental build with extra -D flags into libworld_b200_<variant>.so
+    (loaded instead of the default library when WB200_LIB points at it: A/B measurements)."""
+    global FLAGS
+    bdir, lib = BUILD, LIB
+    flags_saved = FLAGS
+    if variant:
+        bdir = os.path.join(BUILD, variant)
+        lib = os.path.join(HERE, "libworld_b200_%s.so" % variant)
+        FLAGS = FLAGS + ["-D" + d for d in defines]
+    try:
+        return _build(force, verbose, bdir, lib)
+    finally:
+        FLAGS = flags_saved
+
+
+def _build(force, verbose, BUILD, LIB):
     os.makedirs(BUILD, exist_ok=True)
     srcs = _sources()
     dep_m = _deps_mtime()
@@ -73,4 +89,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
+    # python build.py [--force] [--variant NAME -DFLAG ...]
+    var = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    build(force="--force" in sys.argv, verbose=True, variant=var, defines=[a[2:] for a in sys.argv if a.startswith("-D")])

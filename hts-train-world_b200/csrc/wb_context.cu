@@ -213,7 +213,8 @@ int option(const char* name) {
   struct Opt { const char* name; const char* env; int def; int val; };
   static Opt opts[] = {
       {"d4c_split", "WB_D4C_SPLIT", 0, -1},            // D4C as FP64 group-delay kernel + FP32 tail kernel (3 CTAs / SM each)
-      {"lovetrain_fp32", "WB_D4C_LT32", 0, -1},        // LoveTrain's transform in FP32
+      {"lovetrain_fp32", "WB_D4C_LT32", 1, -1},        // LoveTrain's transform in FP32
+      {"stonemask_dft", "WB_STONEMASK_DFT", 1, -1},    // StoneMask: direct evaluation of the <= 8 bins (0: packed FP32 FFT)
   };
   static std::mutex mu;
   std::lock_guard<std::mutex> lock(mu);

@@ -335,7 +335,7 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
     std::vector<long long> h_foff;
     while (u1 < n_utt) {
       const size_t need = (size_t)c.nb * h_ylen[u1] + 8;
-      if (u1 > u0 && tot + need > kMaxScratchDoubles) break;
+      if (u1 > u0 && (tot + need > kMaxScratchDoubles || (long long)(u1 - u0 + 1) * c.nb > 65535)) break;   // grid.y of the per-(utterance, band) kernels
       h_foff.push_back((long long)tot);
       tot += need;
       max_y = std::max(max_y, h_ylen[u1]);

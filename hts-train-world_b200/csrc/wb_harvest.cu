@@ -881,7 +881,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
     std::vector<long long> h_foff, h_roff;
     while (u1 < n_utt) {
       const size_t need = (size_t)c.nch * h_ylen[u1] + 8;
-      if (u1 > u0 && tot + need > kMaxScratchDoubles) break;
+      if (u1 > u0 && (tot + need > kMaxScratchDoubles || (long long)(u1 - u0 + 1) * c.nch > 65535)) break;   // grid.y of the per-(utterance, channel) kernels
       h_foff.push_back((long long)tot);
       h_roff.push_back((long long)rtot);
       tot += need;

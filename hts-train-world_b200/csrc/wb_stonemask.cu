@@ -130,6 +130,158 @@ stonemask_kernel(UttView u, const int* __restrict__ frame_utt, const double* __r
   }
 }
 
+
+// ---- direct evaluation of the harmonic bins (default path) ------------------------------------------
+// FixF0 reads at most 2 + 6 bins of the two spectra, so no transform is needed at all: one WARP owns a
+// frame and evaluates  X_w[k] = sum_n x_n w_n e^{-2 pi i k n / N}  and the same sum with the
+// differentiated window for the bins FixF0 asks for -- lane l takes samples l, l + 32, ...; the
+// phasor of every bin advances by a fixed rotation (32 samples) per iteration, its start and step come
+// from the compact twiddle table of size N (exact to 1 ulp); everything is FP64.  ~80 FP64 operations
+// per sample for the two passes (2 bins, then 6 bins around the tentative F0) against ~170 for the
+// packed FFT plus one libm cos per sample, and no shared memory or block barrier.
+//
+// Window phase (GetMainWindow :33-43): a_n = 2 pi ((index_raw[n] - 1) / fs - t) / wlen with
+// index_raw[n] = round((t + (n - hwl) / fs) fs) (:24-28).  When t fs is not within 1e-6 of a
+// half-integer every index_raw[n] is r0 + n (the rounding cannot flip), a_n is linear in n and one
+// sincospi per lane plus angle-addition steps of 32 samples give the whole window (|error| < 1e-14);
+// the +-1 neighbours of the differentiated window (:49-55) are one more angle addition.  Otherwise
+// (44.1 / 22.05 kHz: t fs is a half-integer on every other frame) each sample's own index_raw and
+// those of its two neighbours are formed with the reference's roundings and the phase is taken
+// from them directly.
+template <int NH, bool linear>
+__device__ __forceinline__ double stonemask_fix_f0_dft(const double* __restrict__ x, int x_len, int fs, double t_pos,
+                                                       int hwl, int log2fft, double wlen, int r0,
+                                                       double initial_f0, int lane,
+                                                       const double2* __restrict__ tw_c_base) {
+  const int W = 2 * hwl + 1, nfft = 1 << log2fft, nhalf = nfft >> 1;
+  int bins[NH];
+  double pc[NH], ps[NH], qc[NH], qs[NH], acc[NH][4];
+  {
+    const double2* __restrict__ tw = tw_c_base + Context::tw_c_offset(log2fft);
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      bins[h] = matlab_round(mul_rn(div_rn(mul_rn(initial_f0, (double)nfft), (double)fs), (double)(h + 1)));   // :103
+      const int k = max(0, min(nhalf, bins[h]));                 // memory guard (UB in the reference beyond N/2)
+      const int m0 = (int)(((long long)k * lane) & (nfft - 1));
+      const int m1 = (int)(((long long)k * 32) & (nfft - 1));
+      double2 a = __ldg(&tw[m0 & (nhalf - 1)]), b = __ldg(&tw[m1 & (nhalf - 1)]);
+      if (m0 & nhalf) { a.x = -a.x; a.y = -a.y; }
+      if (m1 & nhalf) { b.x = -b.x; b.y = -b.y; }
+      pc[h] = a.x; ps[h] = a.y; qc[h] = b.x; qs[h] = b.y;
+      acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.0;
+    }
+  }
+  auto blackman = [](double cv) { return 0.42 + 0.5 * cv + 0.08 * (2.0 * cv * cv - 1.0); };
+  const double turn_per_sample = 2.0 / (wlen * fs);               // phase step in units of pi
+  auto index_raw = [&](int n) {                                     // :24-28
+    return matlab_round(mul_rn(add_rn(t_pos, div_rn((double)(n - hwl), (double)fs)), (double)fs));
+  };
+  auto window_of_index = [&](int ir) {                              // :38-42 for one sample (slow path)
+    const double tmp = add_rn(div_rn(ir - 1.0, (double)fs), -t_pos);
+    return blackman(cospi(2.0 * tmp / wlen));
+  };
+  double cd = 1.0, sd = 0.0, c32 = 1.0, s32 = 0.0, cs = 1.0, sn = 0.0;
+  if (linear) {
+    sincospi(turn_per_sample, &sd, &cd);
+    sincospi(32.0 * turn_per_sample, &s32, &c32);
+    sincospi(2.0 * add_rn(div_rn(r0 + lane - 1.0, (double)fs), -t_pos) / wlen, &sn, &cs);
+  }
+  for (int n = lane; n < W; n += 32) {
+    double w, w_next, w_prev;
+    int ir;
+    if (linear) {
+      ir = r0 + n;
+      w = blackman(cs);
+      w_next = blackman(cs * cd - sn * sd);
+      w_prev = blackman(cs * cd + sn * sd);
+      const double t = cs * c32 - sn * s32;
+      sn = sn * c32 + cs * s32;
+      cs = t;
+    } else {
+      ir = index_raw(n);
+      w = window_of_index(ir);
+      w_next = n + 1 < W ? window_of_index(index_raw(n + 1)) : 0.0;
+      w_prev = n > 0 ? window_of_index(index_raw(n - 1)) : 0.0;
+    }
+    double dw;                                                      // GetDiffWindow (:49-55)
+    if (n == 0) dw = -w_next / 2.0;
+    else if (n == W - 1) dw = w_prev / 2.0;
+    else dw = -(w_next - w_prev) / 2.0;
+    const double xv = x[max(0, min(x_len - 1, ir - 1))];            // GetSpectra (:67-70)
+    const double xm = xv * w, xd = xv * dw;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      acc[h][0] += xm * pc[h]; acc[h][1] += xm * ps[h];
+      acc[h][2] += xd * pc[h]; acc[h][3] += xd * ps[h];
+      const double t = pc[h] * qc[h] - ps[h] * qs[h];
+      ps[h] = ps[h] * qc[h] + pc[h] * qs[h];
+      pc[h] = t;
+    }
+  }
+  double numerator = 0.0, denominator = 0.0;                         // FixF0 (:96-117)
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    const double re = warp_sum(acc[h][0]), im = warp_sum(acc[h][1]);
+    const double dre = warp_sum(acc[h][2]), dim = warp_sum(acc[h][3]);
+    const double power = re * re + im * im;
+    const double numer = re * dim - im * dre;
+    const double inst = power == 0.0 ? 0.0
+        : add_rn(div_rn(mul_rn((double)bins[h], (double)fs), (double)nfft),
+                 div_rn(div_rn(mul_rn(div_rn(numer, power), (double)fs), 2.0), kPi));
+    const double amp = sqrt(power);
+    numerator += amp * inst;
+    denominator += amp * (h + 1);
+  }
+  return numerator / (denominator + kMySafeGuardMinimum);
+}
+
+// frames whose t fs sits on a half-integer (rare except at 44.1 / 22.05 kHz): out of line, so that its
+// registers do not count against the common path
+__device__ __noinline__ double stonemask_exact_indices(const double* __restrict__ x, int x_len, int fs, double t_pos,
+                                                       int hwl, int log2fft, double wlen, double f0, int lane,
+                                                       const double2* __restrict__ tw_c_base) {
+  const double tentative = stonemask_fix_f0_dft<2, false>(x, x_len, fs, t_pos, hwl, log2fft, wlen, 0, f0, lane, tw_c_base);
+  if (tentative <= 0.0 || tentative > f0 * 2) return 0.0;
+  return stonemask_fix_f0_dft<6, false>(x, x_len, fs, t_pos, hwl, log2fft, wlen, 0, tentative, lane, tw_c_base);
+}
+
+constexpr int kSmWarps = 8;      // frames per CTA
+__global__ void __launch_bounds__(kSmWarps * 32, 2)
+stonemask_dft_kernel(UttView u, const int* __restrict__ frame_utt, const double* __restrict__ frame_t,
+                     const double* __restrict__ f0_in, const double2* __restrict__ tw_c_base, int fs,
+                     int total_frames, double* __restrict__ f0_out) {
+  const int f = blockIdx.x * kSmWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (f >= total_frames) return;
+  const double f0 = f0_in[f];
+  if (!stonemask_in_range(f0, fs)) { if (lane == 0) f0_out[f] = 0.0; return; }
+  const int utt = frame_utt[f];
+  const double* __restrict__ x = u.x + u.x_off[utt];
+  const int x_len = u.x_len[utt];
+  const double t_pos = frame_t[f];
+  const int hwl = stonemask_hwl(f0, fs);
+  const int log2fft = stonemask_log2fft(hwl);
+  const double wlen = div_rn(add_rn(mul_rn(2.0, (double)hwl), 1.0), (double)fs);   // :189
+  // is every index_raw[n] = round(t fs) - hwl + n?  (t + (n - hwl) / fs) fs differs from t fs + (n - hwl)
+  // by a few ulps of t fs (< 1e-9 for any utterance length): the rounding can only flip within that
+  // distance of a half-integer
+  const double p = mul_rn(t_pos, (double)fs);
+  const double fr = p - floor(p);
+  const bool linear = fabs(fr - 0.5) > 1e-6;
+  const int r0 = matlab_round(p) - hwl;
+  double mean_f0 = 0.0;
+  // GetTentativeF0 (:122-131) and the 20 % sanity check of GetRefinedF0 (:203-204)
+  if (linear) {
+    const double tentative = stonemask_fix_f0_dft<2, true>(x, x_len, fs, t_pos, hwl, log2fft, wlen, r0, f0, lane, tw_c_base);
+    if (!(tentative <= 0.0 || tentative > f0 * 2))
+      mean_f0 = stonemask_fix_f0_dft<6, true>(x, x_len, fs, t_pos, hwl, log2fft, wlen, r0, tentative, lane, tw_c_base);
+  } else {
+    mean_f0 = stonemask_exact_indices(x, x_len, fs, t_pos, hwl, log2fft, wlen, f0, lane, tw_c_base);
+  }
+  if (fabs(mean_f0 - f0) / f0 > 0.2) mean_f0 = f0;
+  if (lane == 0) f0_out[f] = mean_f0;
+}
+
 }  // namespace
 
 #ifndef WB_HOST_EMU      // the launcher; tests/emu has its own
@@ -139,6 +291,17 @@ bool stonemask_run(const UttView& u, int fs, int total_frames, const int* frame_
   if (!c) return false;
   if (total_frames <= 0) return true;
   cudaStream_t st = c->stream;
+  if (option("stonemask_dft")) {
+    // largest transform size the bins refer to: f0 just above 40 Hz -> hwl = 1.5 fs / 40 + 1
+    const int w_max = 2 * static_cast<int>(1.5 * fs / kFloorF0StoneMask + 1.0) + 1;
+    int l2 = 0; while ((1 << (l2 + 1)) <= w_max) ++l2;
+    if (2 + l2 > kTwLog2) { set_error("StoneMask: sampling rate %d not supported (bin table 2^%d)", fs, 2 + l2); return false; }
+    KernelTimer kt("stonemask_kernel");
+    stonemask_dft_kernel<<<(total_frames + kSmWarps - 1) / kSmWarps, kSmWarps * 32, 0, st>>>(u, frame_utt, frame_t, f0_in, c->d_twiddle_c, fs,
+                                                                                         total_frames, f0_out);
+    WB_LAUNCH_CHECK(); kt.stop();
+    return true;
+  }
   DevBuf<int> d_max;
   if (!d_max.alloc(1)) return false;
   WB_CUDA_OR_RETURN(cudaMemsetAsync(d_max.p, 0, sizeof(int), st), false);

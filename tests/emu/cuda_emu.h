@@ -142,6 +142,7 @@ inline void sincospi(double a, double* s, double* c) {
   const long double x = 3.14159265358979323846264338327950288L * (long double)a;
   *s = (double)sinl(x); *c = (double)cosl(x);
 }
+inline double cospi(double a) { double s, c; sincospi(a, &s, &c); return c; }
 inline void sincospif(float a, float* s, float* c) {
   const double x = 3.14159265358979323846 * (double)a;
   *s = (float)sin(x); *c = (float)cos(x);

@@ -35,3 +35,31 @@ extern "C" int emu_stonemask(const double* x, int x_len, int fs, const double* t
   for (int r = 0; r < n_rows; ++r) f0_rows[r] = out[rows[r]];
   return wbemu::smem_overruns ? 4 : 0;
 }
+
+// the default path: stonemask_dft_kernel (one warp per frame, direct evaluation of the harmonic bins)
+extern "C" int emu_stonemask_dft(const double* x, int x_len, int fs, const double* t, const double* f0, int F, const int* rows,
+                                 int n_rows, double* f0_rows) {
+  using namespace wb;
+  std::vector<double2> twc(Context::tw_c_offset(kTwLog2 + 1));
+  for (int L = 4; L <= kTwLog2; ++L)
+    for (int k = 0; k <= (1 << (L - 1)); ++k) {
+      const long double a = -2.0L * 3.14159265358979323846264338327950288L * k / (1 << L);
+      twc[Context::tw_c_offset(L) + k] = make_double2((double)cosl(a), (double)sinl(a));
+    }
+  std::vector<double> xs(x, x + x_len);
+  xs.push_back(0.0);
+  xs.push_back(0.0);
+  const long long x_off = 0;
+  const int f_off = 0;
+  UttView u{xs.data(), &x_off, &x_len, &f_off, &F, 1};
+  std::vector<int> frame_utt(F, 0);
+  std::vector<double> out(F, -1.0);
+  std::vector<int> blocks;                                  // the CTAs that hold the requested frames
+  for (int r = 0; r < n_rows; ++r)
+    if (blocks.empty() || blocks.back() != rows[r] / kSmWarps) blocks.push_back(rows[r] / kSmWarps);
+  wbemu::smem_overruns = 0;
+  wbemu::launch(blocks, (F + kSmWarps - 1) / kSmWarps, kSmWarps * 32, 0,
+                [&]() { stonemask_dft_kernel(u, frame_utt.data(), t, f0, twc.data(), fs, F, out.data()); });
+  for (int r = 0; r < n_rows; ++r) f0_rows[r] = out[rows[r]];
+  return wbemu::smem_overruns ? 4 : 0;
+}

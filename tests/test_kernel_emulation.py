@@ -192,6 +192,12 @@ def test_stonemask_kernel_source(tmp_path, name):
                              rows.ctypes.data_as(ip), len(rows), out.ctypes.data_as(dp)) == 0
     ref = g["f0"][rows]
     assert M.vuv_agreement(ref, out) == 1.0 and M.f0_rel_error(ref, out) <= 2e-6
+    # the default path: direct FP64 evaluation of the harmonic bins, one warp per frame (at 22.05 kHz every
+    # other frame position times fs is a half-integer: the exact-index path)
+    out2 = np.zeros(len(rows))
+    assert lib.emu_stonemask_dft(x.ctypes.data_as(dp), len(x), fs, t.ctypes.data_as(dp), f0r.ctypes.data_as(dp), len(t),
+                                 rows.ctypes.data_as(ip), len(rows), out2.ctypes.data_as(dp)) == 0
+    assert M.vuv_agreement(ref, out2) == 1.0 and M.f0_rel_error(ref, out2) <= 1e-9
     if name != "synthetic48k_u7":
         return
     exe = str(tmp_path / "sm_tsan")
