@@ -535,21 +535,8 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
         cbuf[cslot(i)] = make_double2(wave, w);
         sums[0] += wave; sums[1] += w; sums[2] += wave * wave; sums[3] += wave * w; sums[4] += w * w;
       };
-#ifdef WB_RN_PRELOAD
-      // the dither values of the first rounds are requested before the wait for the staged samples:
-      // their L2 latency overlaps the TMA copy instead of sitting inside the loop
-      constexpr int kPre = 6;
-      uint32_t rpre[kPre];
-#pragma unroll
-      for (int q = 0; q < kPre; ++q) { const int i = tid + q * T; rpre[q] = i < W ? rns[i] : 0u; }
-      if (staged) { mbar_wait(&mbar, st_parity); st_parity ^= 1u; }
-#pragma unroll
-      for (int q = 0; q < kPre; ++q) { const int i = tid + q * T; if (i < W) window_sample(i, rpre[q]); }
-      for (int i = tid + kPre * T; i < W; i += T) window_sample(i, rns[i]);
-#else
       if (staged) { mbar_wait(&mbar, st_parity); st_parity ^= 1u; }
       for (int i = tid; i < W; i += T) window_sample(i, rns[i]);
-#endif
       block_sum<5>(sums, red);                          // (its barriers also mean: every thread is done with pw)
       st_ok = bulk_window_range(window_origin(side + 1), W4, x_len, Hd + 8, &st_a0, &st_n);
       if (st_ok && tid == 0) bulk_load_issue(pw, x + st_a0, (unsigned)st_n * 8u, &mbar);   // next window

@@ -316,6 +316,8 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
   const size_t smem = 2 * cpad_size(c.bn / 2) * sizeof(double2);
   WB_CUDA_OR_RETURN(cudaFuncSetAttribute(ols_filter_kernel<13, 512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
   WB_CUDA_OR_RETURN(cudaFuncSetAttribute(ols_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(ols_filter_zc_kernel<13, 512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(ols_filter_zc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
 
   OlsConst oc = {c.nb, c.bn, c.log2bn, c.D, c.V};
   std::vector<int> h_shift(c.nb);
@@ -345,38 +347,77 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
     DevBuf<double> d_F, d_edges;
     DevBuf<long long> d_foff, d_loff;
     DevBuf<int> d_counts, d_ltot;
-    const int n_blocks = (max_y + c.V - 1) / c.V;
-    const int n_chunks = (max_y + kZcChunk - 1) / kZcChunk;
     const int n_lists = nu * c.nb * 4;
-    if (!d_F.alloc(tot) || !d_foff.alloc(nu) || !d_counts.alloc((size_t)n_lists * n_chunks) ||
-        !d_ltot.alloc(n_lists) || !d_loff.alloc(n_lists))
-      return false;
-    WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_foff.p, h_foff.data(), nu * sizeof(long long), cudaMemcpyHostToDevice, st), false);
-    KernelTimer kt1("dio_filter_kernel");
-    // 150 KB of shared memory per block leave one CTA per SM: 512 threads (16 warps) hide the latency of
-    // the multiply / pack / store sweeps even though only 256 of them own a radix-16 group (-16 %)
-    if (c.log2bn == 13)
-      ols_filter_kernel<13, 512, 4><<<dim3(n_blocks, nu), 512, smem, st>>>(xin, xin_off, xin_len, d_ylen.p, d_mask.p, d_mean.p,
-                                                            d_foff.p, fb->G.p, ctxp->tw_c(13), oc, d_shift.p, u0, d_F.p);
-    else
-      ols_filter_kernel<0><<<dim3(n_blocks, nu), 256, smem, st>>>(xin, xin_off, xin_len, d_ylen.p, d_mask.p, d_mean.p,
-                                                            d_foff.p, fb->G.p, ctxp->d_twiddle, oc, d_shift.p, u0, d_F.p);
-    WB_LAUNCH_CHECK(); kt1.stop();
-    KernelTimer kt2("dio_zc_kernel");
-    zc_kernel<false><<<dim3(n_chunks, nu * c.nb), 256, 0, st>>>(d_F.p, d_foff.p, d_ylen.p, c.nb, u0, n_chunks, d_counts.p, nullptr, nullptr);
-    WB_LAUNCH_CHECK(); kt2.stop();
-    zc_scan_kernel<<<(n_lists + 127) / 128, 128, 0, st>>>(d_counts.p, n_lists, n_chunks, d_ltot.p);
-    WB_LAUNCH_CHECK();
-    std::vector<int> h_ltot(n_lists);
-    if (!read_back(h_ltot.data(), d_ltot.p, n_lists * sizeof(int))) return false;
+    if (!d_ltot.alloc(n_lists + 1) || !d_loff.alloc(n_lists)) return false;
+    std::vector<int> h_ltot(n_lists + 1);
     std::vector<long long> h_loff(n_lists);
-    long long etot = 0;
-    for (int l = 0; l < n_lists; ++l) { h_loff[l] = etot; etot += h_ltot[l]; }
-    if (!d_edges.alloc((size_t)etot + 2)) return false;
-    WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_loff.p, h_loff.data(), n_lists * sizeof(long long), cudaMemcpyHostToDevice, st), false);
-    KernelTimer kt3("dio_zc_kernel");
-    zc_kernel<true><<<dim3(n_chunks, nu * c.nb), 256, 0, st>>>(d_F.p, d_foff.p, d_ylen.p, c.nb, u0, n_chunks, d_counts.p, d_loff.p, d_edges.p);
-    WB_LAUNCH_CHECK(); kt3.stop();
+    bool fused_done = false;
+    if (option("dio_fused") && c.V > 64) {
+      // filter + zero crossings in one kernel: the band signals never leave shared memory (wb_zerocross.cuh)
+      OlsConst ocz = oc;
+      ocz.V = c.V - 2;                                        // two-sample halo for the first differences
+      const int n_blocks = (max_y - 1 + ocz.V - 1) / ocz.V;
+      DevBuf<int> d_segcnt, d_segoff;
+      DevBuf<double> d_seg;
+      if (!d_segcnt.alloc((size_t)n_lists * n_blocks) || !d_segoff.alloc((size_t)n_lists * n_blocks) ||
+          !d_seg.alloc((size_t)n_lists * n_blocks * kZcSegCap))
+        return false;
+      WB_CUDA_OR_RETURN(cudaMemsetAsync(d_segcnt.p, 0, (size_t)n_lists * n_blocks * sizeof(int), st), false);
+      WB_CUDA_OR_RETURN(cudaMemsetAsync(d_ltot.p + n_lists, 0, sizeof(int), st), false);
+      {
+        KernelTimer kt1("dio_filter_kernel");
+        if (c.log2bn == 13)
+          ols_filter_zc_kernel<13, 512, 4><<<dim3(n_blocks, nu), 512, smem, st>>>(xin, xin_off, xin_len, d_ylen.p, d_mask.p, d_mean.p, fb->G.p,
+                                                                                 ctxp->tw_c(13), ocz, d_shift.p, u0, n_blocks, kZcSegCap, d_segcnt.p, d_seg.p);
+        else
+          ols_filter_zc_kernel<0><<<dim3(n_blocks, nu), 256, smem, st>>>(xin, xin_off, xin_len, d_ylen.p, d_mask.p, d_mean.p, fb->G.p,
+                                                                        ctxp->d_twiddle, ocz, d_shift.p, u0, n_blocks, kZcSegCap, d_segcnt.p, d_seg.p);
+        WB_LAUNCH_CHECK(); kt1.stop();
+      }
+      zc_seg_scan_kernel<<<(n_lists + 127) / 128, 128, 0, st>>>(d_segcnt.p, n_lists, n_blocks, kZcSegCap, d_segoff.p, d_ltot.p, d_ltot.p + n_lists);
+      WB_LAUNCH_CHECK();
+      if (!read_back(h_ltot.data(), d_ltot.p, (n_lists + 1) * sizeof(int))) return false;
+      if (h_ltot[n_lists] == 0) {                              // no segment overflowed
+        long long etot = 0;
+        for (int l = 0; l < n_lists; ++l) { h_loff[l] = etot; etot += h_ltot[l]; }
+        if (!d_edges.alloc((size_t)etot + 2)) return false;
+        WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_loff.p, h_loff.data(), n_lists * sizeof(long long), cudaMemcpyHostToDevice, st), false);
+        KernelTimer kt3("dio_zc_kernel");
+        zc_seg_gather_kernel<<<n_lists, 128, 0, st>>>(d_segcnt.p, d_segoff.p, d_seg.p, n_blocks, kZcSegCap, d_loff.p, d_edges.p);
+        WB_LAUNCH_CHECK(); kt3.stop();
+        WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);  // h_loff and the segment buffers die with this scope
+        fused_done = true;
+      }
+    }
+    if (!fused_done) {
+      const int n_blocks = (max_y + c.V - 1) / c.V;
+      const int n_chunks = (max_y + kZcChunk - 1) / kZcChunk;
+      if (!d_F.alloc(tot) || !d_foff.alloc(nu) || !d_counts.alloc((size_t)n_lists * n_chunks)) return false;
+      WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_foff.p, h_foff.data(), nu * sizeof(long long), cudaMemcpyHostToDevice, st), false);
+      KernelTimer kt1("dio_filter_kernel");
+      // 150 KB of shared memory per block leave one CTA per SM: 512 threads (16 warps) hide the latency of
+      // the multiply / pack / store sweeps even though only 256 of them own a radix-16 group (-16 %)
+      if (c.log2bn == 13)
+        ols_filter_kernel<13, 512, 4><<<dim3(n_blocks, nu), 512, smem, st>>>(xin, xin_off, xin_len, d_ylen.p, d_mask.p, d_mean.p,
+                                                              d_foff.p, fb->G.p, ctxp->tw_c(13), oc, d_shift.p, u0, d_F.p);
+      else
+        ols_filter_kernel<0><<<dim3(n_blocks, nu), 256, smem, st>>>(xin, xin_off, xin_len, d_ylen.p, d_mask.p, d_mean.p,
+                                                              d_foff.p, fb->G.p, ctxp->d_twiddle, oc, d_shift.p, u0, d_F.p);
+      WB_LAUNCH_CHECK(); kt1.stop();
+      KernelTimer kt2("dio_zc_kernel");
+      zc_kernel<false><<<dim3(n_chunks, nu * c.nb), 256, 0, st>>>(d_F.p, d_foff.p, d_ylen.p, c.nb, u0, n_chunks, d_counts.p, nullptr, nullptr);
+      WB_LAUNCH_CHECK(); kt2.stop();
+      zc_scan_kernel<<<(n_lists + 127) / 128, 128, 0, st>>>(d_counts.p, n_lists, n_chunks, d_ltot.p);
+      WB_LAUNCH_CHECK();
+      if (!read_back(h_ltot.data(), d_ltot.p, n_lists * sizeof(int))) return false;
+      long long etot = 0;
+      for (int l = 0; l < n_lists; ++l) { h_loff[l] = etot; etot += h_ltot[l]; }
+      if (!d_edges.alloc((size_t)etot + 2)) return false;
+      WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_loff.p, h_loff.data(), n_lists * sizeof(long long), cudaMemcpyHostToDevice, st), false);
+      KernelTimer kt3("dio_zc_kernel");
+      zc_kernel<true><<<dim3(n_chunks, nu * c.nb), 256, 0, st>>>(d_F.p, d_foff.p, d_ylen.p, c.nb, u0, n_chunks, d_counts.p, d_loff.p, d_edges.p);
+      WB_LAUNCH_CHECK(); kt3.stop();
+    }
     int max_f = 0;
     for (int u = u0; u < u1; ++u) max_f = std::max(max_f, b->h_f_len[u]);
     if (max_f > 0) {

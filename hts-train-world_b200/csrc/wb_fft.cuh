@@ -102,22 +102,15 @@ __device__ __forceinline__ void fft_pass(C* __restrict__ s, const C* __restrict_
     for (int m = 0; m < R; ++m) v[m] = sb[cpadT<C>(m << STAGE)];
     C w[K];
     if (!FIRST) {
-#ifdef WB_TW_SQUARE
       // one table load per group: w[K-1] = exp(-2 pi i j / 2^(STAGE+K)) is the finest of the K twiddles
-      // and every coarser one is the square of the next finer one (4 flops instead of a load whose
-      // latency the group waits for; the rounding error doubles per squaring: <= 2^(K-1) ulp)
+      // and every coarser one is the square of the next finer one -- 4 flops instead of a load whose
+      // latency the whole group waits for (with ~28 KB of L1 left beside the shared memory the tables
+      // miss; measured -7 % on the step).  The rounding error doubles per squaring: <= 2^(K-1) ulp.
       w[K - 1] = __ldg(&tw[j << (TWL - STAGE - K)]);
       if (INV) w[K - 1].y = -w[K - 1].y;
 #pragma unroll
       for (int t = K - 2; t >= 0; --t)
         w[t] = mk2((w[t + 1].x - w[t + 1].y) * (w[t + 1].x + w[t + 1].y), (w[t + 1].x + w[t + 1].x) * w[t + 1].y);
-#else
-#pragma unroll
-      for (int t = 0; t < K; ++t) {
-        w[t] = __ldg(&tw[j << (TWL - STAGE - t - 1)]);
-        if (INV) w[t].y = -w[t].y;
-      }
-#endif
     }
 #pragma unroll
     for (int t = 0; t < K; ++t) {

@@ -872,6 +872,8 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
   const size_t smem = 2 * cpad_size(hb->bn / 2) * sizeof(double2);
   WB_CUDA_OR_RETURN(cudaFuncSetAttribute(ols_filter_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
   WB_CUDA_OR_RETURN(cudaFuncSetAttribute(ols_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(ols_filter_zc_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+  WB_CUDA_OR_RETURN(cudaFuncSetAttribute(ols_filter_zc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
   const size_t kMaxScratchDoubles = (size_t)2 << 30;           // 16 GiB of filtered signals at a time
   int u0 = 0;
   while (u0 < n_utt) {
@@ -894,42 +896,83 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
     DevBuf<double> d_F, d_edges, d_raw;
     DevBuf<long long> d_foff, d_loff, d_roff;
     DevBuf<int> d_counts, d_ltot;
-    const int n_blocks = (sub_max_y + hb->V - 1) / hb->V;
-    const int n_chunks = (sub_max_y + kZcChunk - 1) / kZcChunk;
     const int n_lists = nu * c.nch * 4;
-    if (!d_F.alloc(tot) || !d_foff.alloc(nu) || !d_roff.alloc(nu) || !d_counts.alloc((size_t)n_lists * n_chunks) ||
-        !d_ltot.alloc(n_lists) || !d_loff.alloc(n_lists) || !d_raw.alloc(rtot))
-      return false;
-    if (!up(d_foff.p, h_foff.data(), nu * sizeof(long long)) || !up(d_roff.p, h_roff.data(), nu * sizeof(long long))) return false;
-    {
-      KernelTimer kt("harvest_filter_kernel");
-      // the decimated signals play the role of Dio's x: offsets d_yoff, length = y_len for both "x" and "y"
-      if (hb->log2bn == 11)
-        ols_filter_kernel<11><<<dim3(n_blocks, nu), 256, smem, st>>>(d_y.p, d_yoff.p, d_ylen.p, d_ylen.p, d_mask.p, d_mean.p, d_foff.p,
-                                                                    hb->G.p, ctxp->tw_c(11), oc, hb->shift.p, u0, d_F.p);
-      else
-        ols_filter_kernel<0><<<dim3(n_blocks, nu), 256, smem, st>>>(d_y.p, d_yoff.p, d_ylen.p, d_ylen.p, d_mask.p, d_mean.p, d_foff.p,
-                                                                   hb->G.p, ctxp->d_twiddle, oc, hb->shift.p, u0, d_F.p);
-      WB_LAUNCH_CHECK(); kt.stop();
-    }
-    {
-      KernelTimer kt("harvest_zc_kernel");
-      zc_kernel<false><<<dim3(n_chunks, nu * c.nch), 256, 0, st>>>(d_F.p, d_foff.p, d_ylen.p, c.nch, u0, n_chunks, d_counts.p, nullptr, nullptr);
-      WB_LAUNCH_CHECK();
-      zc_scan_kernel<<<(n_lists + 127) / 128, 128, 0, st>>>(d_counts.p, n_lists, n_chunks, d_ltot.p);
-      WB_LAUNCH_CHECK(); kt.stop();
-    }
-    std::vector<int> h_ltot(n_lists);
-    if (!read_back(h_ltot.data(), d_ltot.p, n_lists * sizeof(int))) return false;
+    if (!d_roff.alloc(nu) || !d_ltot.alloc(n_lists + 1) || !d_loff.alloc(n_lists) || !d_raw.alloc(rtot)) return false;
+    if (!up(d_roff.p, h_roff.data(), nu * sizeof(long long))) return false;
+    std::vector<int> h_ltot(n_lists + 1);
     std::vector<long long> h_loff(n_lists);
-    long long etot = 0;
-    for (int l = 0; l < n_lists; ++l) { h_loff[l] = etot; etot += h_ltot[l]; }
-    if (!d_edges.alloc((size_t)etot + 2)) return false;
-    if (!up(d_loff.p, h_loff.data(), n_lists * sizeof(long long))) return false;
-    {
-      KernelTimer kt("harvest_zc_kernel");
-      zc_kernel<true><<<dim3(n_chunks, nu * c.nch), 256, 0, st>>>(d_F.p, d_foff.p, d_ylen.p, c.nch, u0, n_chunks, d_counts.p, d_loff.p, d_edges.p);
-      WB_LAUNCH_CHECK(); kt.stop();
+    bool fused_done = false;
+    if (option("harvest_fused") && hb->V > 64) {
+      // band-pass filters + zero crossings in one kernel: the 152 channel signals never leave shared memory
+      constexpr int kCap = 128;                              // events per (list, block): ~1 500 samples at 8 kHz per block
+      OlsConst ocz = oc;
+      ocz.V = hb->V - 2;
+      const int n_blocks = (sub_max_y - 1 + ocz.V - 1) / ocz.V;
+      DevBuf<int> d_segcnt, d_segoff;
+      DevBuf<double> d_seg;
+      if (!d_segcnt.alloc((size_t)n_lists * n_blocks) || !d_segoff.alloc((size_t)n_lists * n_blocks) ||
+          !d_seg.alloc((size_t)n_lists * n_blocks * kCap))
+        return false;
+      WB_CUDA_OR_RETURN(cudaMemsetAsync(d_segcnt.p, 0, (size_t)n_lists * n_blocks * sizeof(int), st), false);
+      WB_CUDA_OR_RETURN(cudaMemsetAsync(d_ltot.p + n_lists, 0, sizeof(int), st), false);
+      {
+        KernelTimer kt("harvest_filter_kernel");
+        if (hb->log2bn == 11)
+          ols_filter_zc_kernel<11><<<dim3(n_blocks, nu), 256, smem, st>>>(d_y.p, d_yoff.p, d_ylen.p, d_ylen.p, d_mask.p, d_mean.p, hb->G.p,
+                                                                         ctxp->tw_c(11), ocz, hb->shift.p, u0, n_blocks, kCap, d_segcnt.p, d_seg.p);
+        else
+          ols_filter_zc_kernel<0><<<dim3(n_blocks, nu), 256, smem, st>>>(d_y.p, d_yoff.p, d_ylen.p, d_ylen.p, d_mask.p, d_mean.p, hb->G.p,
+                                                                        ctxp->d_twiddle, ocz, hb->shift.p, u0, n_blocks, kCap, d_segcnt.p, d_seg.p);
+        WB_LAUNCH_CHECK(); kt.stop();
+      }
+      zc_seg_scan_kernel<<<(n_lists + 127) / 128, 128, 0, st>>>(d_segcnt.p, n_lists, n_blocks, kCap, d_segoff.p, d_ltot.p, d_ltot.p + n_lists);
+      WB_LAUNCH_CHECK();
+      if (!read_back(h_ltot.data(), d_ltot.p, (n_lists + 1) * sizeof(int))) return false;
+      if (h_ltot[n_lists] == 0) {
+        long long etot = 0;
+        for (int l = 0; l < n_lists; ++l) { h_loff[l] = etot; etot += h_ltot[l]; }
+        if (!d_edges.alloc((size_t)etot + 2)) return false;
+        if (!up(d_loff.p, h_loff.data(), n_lists * sizeof(long long))) return false;
+        KernelTimer kt("harvest_zc_kernel");
+        zc_seg_gather_kernel<<<n_lists, 128, 0, st>>>(d_segcnt.p, d_segoff.p, d_seg.p, n_blocks, kCap, d_loff.p, d_edges.p);
+        WB_LAUNCH_CHECK(); kt.stop();
+        WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);  // the segment buffers die with this scope
+        fused_done = true;
+      }
+    }
+    if (!fused_done) {
+      const int n_blocks = (sub_max_y + hb->V - 1) / hb->V;
+      const int n_chunks = (sub_max_y + kZcChunk - 1) / kZcChunk;
+      if (!d_F.alloc(tot) || !d_foff.alloc(nu) || !d_counts.alloc((size_t)n_lists * n_chunks)) return false;
+      if (!up(d_foff.p, h_foff.data(), nu * sizeof(long long))) return false;
+      {
+        KernelTimer kt("harvest_filter_kernel");
+        // the decimated signals play the role of Dio's x: offsets d_yoff, length = y_len for both "x" and "y"
+        if (hb->log2bn == 11)
+          ols_filter_kernel<11><<<dim3(n_blocks, nu), 256, smem, st>>>(d_y.p, d_yoff.p, d_ylen.p, d_ylen.p, d_mask.p, d_mean.p, d_foff.p,
+                                                                      hb->G.p, ctxp->tw_c(11), oc, hb->shift.p, u0, d_F.p);
+        else
+          ols_filter_kernel<0><<<dim3(n_blocks, nu), 256, smem, st>>>(d_y.p, d_yoff.p, d_ylen.p, d_ylen.p, d_mask.p, d_mean.p, d_foff.p,
+                                                                     hb->G.p, ctxp->d_twiddle, oc, hb->shift.p, u0, d_F.p);
+        WB_LAUNCH_CHECK(); kt.stop();
+      }
+      {
+        KernelTimer kt("harvest_zc_kernel");
+        zc_kernel<false><<<dim3(n_chunks, nu * c.nch), 256, 0, st>>>(d_F.p, d_foff.p, d_ylen.p, c.nch, u0, n_chunks, d_counts.p, nullptr, nullptr);
+        WB_LAUNCH_CHECK();
+        zc_scan_kernel<<<(n_lists + 127) / 128, 128, 0, st>>>(d_counts.p, n_lists, n_chunks, d_ltot.p);
+        WB_LAUNCH_CHECK(); kt.stop();
+      }
+      if (!read_back(h_ltot.data(), d_ltot.p, n_lists * sizeof(int))) return false;
+      long long etot = 0;
+      for (int l = 0; l < n_lists; ++l) { h_loff[l] = etot; etot += h_ltot[l]; }
+      if (!d_edges.alloc((size_t)etot + 2)) return false;
+      if (!up(d_loff.p, h_loff.data(), n_lists * sizeof(long long))) return false;
+      {
+        KernelTimer kt("harvest_zc_kernel");
+        zc_kernel<true><<<dim3(n_chunks, nu * c.nch), 256, 0, st>>>(d_F.p, d_foff.p, d_ylen.p, c.nch, u0, n_chunks, d_counts.p, d_loff.p, d_edges.p);
+        WB_LAUNCH_CHECK(); kt.stop();
+      }
     }
     harvest_raw_kernel<<<dim3((sub_max_g + 127) / 128, nu * c.nch), 128, 0, st>>>(d_edges.p, d_loff.p, d_ltot.p, d_goff.p, d_glen.p,
                                                                                 hb->d_boundary.p, c, u0, d_roff.p, d_raw.p);

@@ -257,4 +257,168 @@ ols_filter_kernel(const double* __restrict__ x_all, const long long* __restrict_
 }
 
 
+// ---- band filtering with the zero crossings taken from the block while it is still in shared memory --
+// ols_filter_kernel writes every band signal to HBM (7 x the input for Dio, 152 x for Harvest) and the two
+// zc_kernel passes read all of it back twice.  Here the events of a block are detected right behind the
+// inverse transform of each band: thread t owns `per` consecutive output samples (plus a two-sample
+// halo, so a block owns V - 2 outputs instead of V), marks the four event types in bit masks, one block
+// scan of the packed counts orders them, and the sub-sample positions go to this block's segment of a
+// staging buffer -- seg_cap events per (list, block); a block that finds more only counts them and the
+// caller falls back to the two-pass path for that sub-batch.  A scan over the blocks of each list and a
+// gather then give the same contiguous, ordered edge lists as zc_kernel<true>.
+constexpr int kZcSegCap = 256;      // Dio's capacity (8 192-sample blocks at the full rate); Harvest passes 128
+
+template <int LOG2BN, int THREADS = 256, int MAXK = 4>     // LOG2BN 0: block size given at run time (c.log2bn)
+static __global__ void __launch_bounds__(THREADS)
+ols_filter_zc_kernel(const double* __restrict__ x_all, const long long* __restrict__ x_off,
+                     const int* __restrict__ x_len, const int* __restrict__ y_len_all,
+                     const int* __restrict__ fft_mask_all, const double* __restrict__ mean_all,
+                     const double2* __restrict__ G, const double2* __restrict__ tw, OlsConst c,   // c.V: outputs OWNED per block
+                     const int* __restrict__ shift_all, int utt0, int n_blocks_max, int seg_cap,
+                     int* __restrict__ seg_count,          // [lists][n_blocks_max], zeroed by the caller
+                     double* __restrict__ seg_edges) {     // [lists][n_blocks_max][seg_cap]
+  WB_DYN_SMEM(double2, smem2);
+  __shared__ unsigned long long wtot[THREADS / 32];
+  const int u = utt0 + blockIdx.y;
+  const int y_len = y_len_all[u];
+  const int n0 = blockIdx.x * c.V;
+  if (n0 >= y_len - 1) return;                      // no event can start at the last sample
+  constexpr int LM = LOG2BN > 0 ? LOG2BN - 1 : 0;
+  constexpr int TWL = LOG2BN > 0 ? LOG2BN : kTwLog2;
+  const int log2m = LOG2BN > 0 ? LOG2BN - 1 : c.log2bn - 1, M = 1 << log2m;
+  double2* xs = smem2;
+  double2* ws = smem2 + cpad_size(M);
+  double* xsd = reinterpret_cast<double*>(xs);
+  double* wsd = reinterpret_cast<double*>(ws);
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5;
+  const double* __restrict__ x = x_all + x_off[u];
+  const int xl = x_len[u];
+  const int mask = fft_mask_all[u];
+  const double mean = mean_all[u];
+  for (int i = tid; i < c.bn; i += T) {             // input block: ypad[(n0 - D + i) mod FS]
+    const int m = (n0 - c.D + i) & mask;
+    double v = 0.0;
+    if (m < y_len) v = (m < xl ? x[m] : 0.0) - mean;
+    xsd[rfft_in_slot(i, log2m)] = v;
+  }
+  fft_dit<LM, false, THREADS, MAXK, TWL>(xs, log2m, tw);
+  for (int k = tid; k <= M / 2; k += T) {           // half spectrum in place: slot k = X[k] (k < M), slot 0 = (X[0], X[M])
+    if (k == 0) {
+      const double2 z0 = xs[0];
+      xs[0] = make_double2(z0.x + z0.y, z0.x - z0.y);
+    } else {
+      const double2 a = rfft_bin<TWL>(xs, log2m, k, tw);
+      const double2 b = rfft_bin<TWL>(xs, log2m, M - k, tw);
+      xs[cpad(k)] = a;
+      xs[cpad(M - k)] = b;
+    }
+  }
+  __syncthreads();
+  const int n_own = min(c.V, y_len - 1 - n0);       // samples of this block at which an event may start
+  const int per = (c.V + T - 1) / T;
+  const int lo = min(n_own, tid * per), hi = min(n_own, lo + per);
+  for (int b = 0; b < c.nb; ++b) {
+    const double2* __restrict__ Gb = G + (size_t)b * (M + 1);
+    for (int k = tid; k <= M / 2; k += T) {
+      if (k == 0) {
+        const double2 x0 = xs[0];
+        const double2 y0 = make_double2(x0.x * Gb[0].x, 0.0), yM = make_double2(x0.y * Gb[M].x, 0.0);
+        ws[cpad(brev(0, log2m))] = c2r_pack<TWL>(y0, yM, 0, log2m, tw);
+      } else {
+        const double2 yk = cmul(xs[cpad(k)], Gb[k]);
+        const double2 ym = cmul(xs[cpad(M - k)], Gb[M - k]);
+        ws[cpad(brev(k, log2m))] = c2r_pack<TWL>(yk, ym, k, log2m, tw);
+        if (k != M - k) ws[cpad(brev(M - k, log2m))] = c2r_pack<TWL>(ym, yk, M - k, log2m, tw);
+      }
+    }
+    fft_dit<LM, true, THREADS, MAXK, TWL>(ws, log2m, tw);
+    const int shift = shift_all[b];                 // filtered_b[n0 + i] = conv[i + shift]
+    auto S = [&](int i) { return wsd[rfft_out_slot(i + shift)]; };
+    // events that start at my samples (GetFourZeroCrossingIntervals :402-435): bit (i - lo) of m[type]
+    unsigned m[4] = {0u, 0u, 0u, 0u};
+    if (lo < hi) {
+      double s0 = S(lo), s1 = S(lo + 1);
+      for (int i = lo; i < hi; ++i) {
+        const double s2 = S(i + 2);
+        const unsigned bit = 1u << (i - lo);
+        if (zc_event(s0, s1)) m[0] |= bit;
+        if (zc_event(-s0, -s1)) m[1] |= bit;
+        if (n0 + i < y_len - 2) {
+          const double d0 = add_rn(s1, -s0), d1 = add_rn(s2, -s1);
+          if (zc_event(d0, d1)) m[2] |= bit;
+          if (zc_event(-d0, -d1)) m[3] |= bit;
+        }
+        s0 = s1; s1 = s2;
+      }
+    }
+    // ordered slots: block-wide exclusive scan of the four counts, 16 bits each (a block holds < 2^16 samples)
+    const unsigned long long mine = (unsigned long long)__popc(m[0]) | ((unsigned long long)__popc(m[1]) << 16) |
+                                    ((unsigned long long)__popc(m[2]) << 32) | ((unsigned long long)__popc(m[3]) << 48);
+    unsigned long long inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wtot[wid] = inc;
+    __syncthreads();
+    unsigned long long before = inc - mine;
+    for (int w = 0; w < wid; ++w) before += wtot[w];
+    const size_t list0 = ((size_t)blockIdx.y * c.nb + b) * 4;
+    if (tid == T - 1) {
+      const unsigned long long tot = before + mine;
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        seg_count[(list0 + t) * n_blocks_max + blockIdx.x] = (int)((tot >> (16 * t)) & 0xffffull);
+    }
+#pragma unroll 1
+    for (int t = 0; t < 4; ++t) {
+      unsigned mm = m[t];
+      if (mm == 0u) continue;
+      int pos = (int)((before >> (16 * t)) & 0xffffull);
+      double* __restrict__ seg = seg_edges + ((list0 + t) * n_blocks_max + blockIdx.x) * seg_cap;
+      while (mm) {
+        const int j = __ffs(mm) - 1;
+        mm &= mm - 1u;
+        const int i = lo + j;
+        const double s0 = S(i), s1 = S(i + 1);
+        double a = s0, bb = s1;
+        if (t >= 2) { const double s2 = S(i + 2); a = add_rn(s1, -s0); bb = add_rn(s2, -s1); }
+        if (t & 1) { a = -a; bb = -bb; }
+        if (pos < seg_cap) seg[pos] = zc_fine(n0 + i + 1, a, bb);
+        ++pos;
+      }
+    }
+    __syncthreads();                                // ws and wtot are rewritten by the next band
+  }
+}
+
+// one thread per list: exclusive offsets of its blocks' segments, list total, overflow flag
+static __global__ void zc_seg_scan_kernel(const int* __restrict__ seg_count, int n_lists, int n_blocks_max, int seg_cap,
+                                          int* __restrict__ seg_off, int* __restrict__ totals, int* __restrict__ overflow) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_lists) return;
+  const int* c = seg_count + (size_t)l * n_blocks_max;
+  int* o = seg_off + (size_t)l * n_blocks_max;
+  int acc = 0, over = 0;
+  for (int i = 0; i < n_blocks_max; ++i) { const int v = c[i]; o[i] = acc; acc += v; over |= v > seg_cap; }
+  totals[l] = acc;
+  if (over) atomicOr(overflow, 1);
+}
+
+// one CTA per list: segments -> the contiguous edge list
+static __global__ void __launch_bounds__(128)
+zc_seg_gather_kernel(const int* __restrict__ seg_count, const int* __restrict__ seg_off, const double* __restrict__ seg_edges,
+                     int n_blocks_max, int seg_cap, const long long* __restrict__ list_off, double* __restrict__ edges) {
+  const size_t l = blockIdx.x;
+  double* __restrict__ dst = edges + list_off[l];
+  for (int k = 0; k < n_blocks_max; ++k) {
+    const int n = min(seg_cap, seg_count[l * n_blocks_max + k]);
+    const double* __restrict__ src = seg_edges + (l * n_blocks_max + k) * seg_cap;
+    const int o = seg_off[l * n_blocks_max + k];
+    for (int j = threadIdx.x; j < n; j += blockDim.x) dst[o + j] = src[j];
+  }
+}
+
+
 }  // namespace wb

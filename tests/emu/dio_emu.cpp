@@ -68,6 +68,31 @@ extern "C" int emu_dio(const double* x, int x_len, int fs, double f0_floor, doub
   std::vector<double> edges((size_t)etot + 2, 0.0);
   wbemu::launch_grid(n_chunks, c.nb, 256, 0,
                      [&]() { zc_kernel<true>(Fbuf.data(), &f_off_ll, &y_len, c.nb, 0, n_chunks, counts.data(), loff.data(), edges.data()); });
+  // the default path of the library: zero crossings taken inside the filter kernel (ols_filter_zc_kernel),
+  // block segments -> scan -> gather.  Its edge lists must hold the same events as the two-pass ones.
+  {
+    OlsConst ocz = oc;
+    ocz.V = c.V - 2;
+    const int nbz = (y_len - 1 + ocz.V - 1) / ocz.V;
+    std::vector<int> segcnt((size_t)n_lists * nbz, 0), segoff((size_t)n_lists * nbz, 0), ltot2(n_lists + 1, 0);
+    std::vector<double> seg((size_t)n_lists * nbz * kZcSegCap, -1.0);
+    wbemu::launch_grid(nbz, 1, 512, smem, [&]() {
+      ols_filter_zc_kernel<13, 512, 4>(xs.data(), &x_off, &x_len, &y_len, &mask, &mean, fb.G.p, tw.data(), ocz, shift.data(), 0, nbz, kZcSegCap,
+                                       segcnt.data(), seg.data());
+    });
+    wbemu::launch_grid((n_lists + 127) / 128, 1, 128, 0,
+                       [&]() { zc_seg_scan_kernel(segcnt.data(), n_lists, nbz, kZcSegCap, segoff.data(), ltot2.data(), ltot2.data() + n_lists); });
+    if (ltot2[n_lists] != 0) return 5;                                           // a segment overflowed
+    for (int l = 0; l < n_lists; ++l) if (ltot2[l] != ltot[l]) return 6;
+    std::vector<double> edges2((size_t)etot + 2, 0.0);
+    wbemu::launch_grid(n_lists, 1, 128, 0,
+                       [&]() { zc_seg_gather_kernel(segcnt.data(), segoff.data(), seg.data(), nbz, kZcSegCap, loff.data(), edges2.data()); });
+    // (a sample's block and position inside the block differ between the two partitions, so the transforms
+    // round differently: the sub-sample positions agree to ~1e-12, not bit for bit)
+    for (long long i = 0; i < etot; ++i)
+      if (fabs(edges[i] - edges2[i]) > 1e-9 * (1.0 + fabs(edges[i]))) return 7;
+    edges.swap(edges2);
+  }
   wbemu::launch_grid((TF + 127) / 128, c.nb, 128, 0, [&]() {
     dio_candidates_kernel(edges.data(), loff.data(), ltot.data(), &f_off, &TF, frame_t.data(), c, 0, TF, cand.data(), score.data());
   });

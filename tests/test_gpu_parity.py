@@ -487,8 +487,17 @@ def test_other_sampling_rates(wb, reference_lib, fs):
     assert sp.shape == o["sp"].shape
     assert M.lsd_db(o["sp"], sp)[1] <= M.TOL_LSD_DB
     ap = wb.d4c(x, fs, o["t"], o["f0"], o["fft_size"])            # threshold 0, the analysis tool's setting
-    assert M.ap_abs_error(o["ap"], ap) <= M.TOL_AP_ABS
-    if fs >= 16000:   # below 15.8 kHz the reference's LoveTrain reads uninitialised memory (d4c.cpp:243-246)
+    if fs >= 16000:
+        assert M.ap_abs_error(o["ap"], ap) <= M.TOL_AP_ABS
+    else:
+        # below 15.8 kHz the reference's LoveTrain sums uninitialised heap memory (boundary2 > fft_size / 2,
+        # d4c.cpp:243-246), so WHICH voiced frames pass its gate differs from run to run; the rows of the
+        # frames it did process are defined (knots {0: -60 dB, fs/2: -1e-12 dB}, no band at all) and ours
+        # processes every voiced frame
+        done = o["ap"][:, 0] < 0.5
+        assert M.ap_abs_error(o["ap"][done], ap[done]) <= M.TOL_AP_ABS
+        assert np.all(ap[o["f0"] == 0] == 1.0 - 1e-12) and np.all(ap[o["f0"] > 0][:, 0] < 0.5)
+    if fs >= 16000:
         ap_ref = reference_lib.d4c(x, fs, o["t"], o["f0"], o["fft_size"], threshold=0.85)
         assert M.ap_abs_error(ap_ref, wb.d4c(x, fs, o["t"], o["f0"], o["fft_size"], threshold=0.85)) <= M.TOL_AP_ABS
     y_ref = reference_lib.synthesis(o["f0"], o["sp"], o["ap"], o["fft_size"], 5.0, fs)
