@@ -126,10 +126,22 @@ codec_encode_kernel(const double* __restrict__ rows, int half, int log2max_rt, c
   const int tid = threadIdx.x, T = 128;
   const size_t f = blockIdx.x;
   const double* __restrict__ row = rows + f * (half + 1);
-  for (int k = tid; k < max_dim; k += T) {        // bins 0 .. max_dim-1 are all interp1 ever reads
-    double v = row[k] * scale;
+  auto log_of = [&](double raw) {
+    double v = raw * scale;
     if (zero_floor != 0.0 && v == 0.0) v = zero_floor;
-    logsp[k] = F32LOG ? static_cast<double>(logf(static_cast<float>(v))) : log(v);
+    return F32LOG ? static_cast<double>(logf(static_cast<float>(v))) : log(v);
+  };
+  if constexpr (LOG2MAX > 0) {
+    // the whole row is requested before the first logarithm: one HBM round trip per frame instead of
+    // one per loop iteration (the kernel was bound by the latency of these loads)
+    constexpr int kPer = (1 << LOG2MAX) / 128;
+    double raw[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) raw[j] = row[tid + j * T];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) logsp[tid + j * T] = log_of(raw[j]);
+  } else {
+    for (int k = tid; k < max_dim; k += T) logsp[k] = log_of(row[k]);   // bins 0 .. max_dim-1 are all interp1 ever reads
   }
   __syncthreads();
   // mel spectrum j -> DCT input position (:75-79): even j -> j/2, odd j -> max_dim - 1 - (j-1)/2

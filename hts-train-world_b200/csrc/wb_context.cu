@@ -215,7 +215,8 @@ int option(const char* name) {
       {"d4c_split", "WB_D4C_SPLIT", 0, -1},            // D4C as FP64 group-delay kernel + FP32 tail kernel (3 CTAs / SM each)
       {"lovetrain_fp32", "WB_D4C_LT32", 1, -1},        // LoveTrain's transform in FP32
       {"dio_fused", "WB_DIO_FUSED", 1, -1},            // Dio: zero crossings inside the filter kernel (0: band signals through HBM)
-      {"harvest_fused", "WB_HARVEST_FUSED", 1, -1},    // Harvest: the same for its 152 band-pass channels
+      {"harvest_fused", "WB_HARVEST_FUSED", 1, -1},
+      {"harvest_refine_thread", "WB_HARVEST_REFINE_THREAD", 1, -1},   // Harvest refinement: one thread per candidate (0: one warp)    // Harvest: the same for its 152 band-pass channels
       {"stonemask_dft", "WB_STONEMASK_DFT", 1, -1},    // StoneMask: direct evaluation of the <= 8 bins (0: packed FP32 FFT)
   };
   static std::mutex mu;

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 i=0
 for envs in "$@"; do
   i=$((i+1))
-  env $envs timeout 600 python bench.py --no-cpu-baseline --no-configs --verify 0 --utts ${UTTS:-300} --steps 3 --warmup 2 > gpurun_out/ab_$i.json 2> gpurun_out/ab_$i.err || tail -5 gpurun_out/ab_$i.err
+  env $envs timeout 600 python bench.py --no-cpu-baseline --no-configs --verify 0 ${BENCH_EXTRA} --utts ${UTTS:-300} --steps 3 --warmup 2 > gpurun_out/ab_$i.json 2> gpurun_out/ab_$i.err || tail -5 gpurun_out/ab_$i.err
   python - "$envs" gpurun_out/ab_$i.json <<'PY'
 import json,sys
 d=json.load(open(sys.argv[2]))

@@ -191,7 +191,7 @@ def test_stonemask_kernel_source(tmp_path, name):
     assert lib.emu_stonemask(x.ctypes.data_as(dp), len(x), fs, t.ctypes.data_as(dp), f0r.ctypes.data_as(dp), len(t),
                              rows.ctypes.data_as(ip), len(rows), out.ctypes.data_as(dp)) == 0
     ref = g["f0"][rows]
-    assert M.vuv_agreement(ref, out) == 1.0 and M.f0_rel_error(ref, out) <= 2e-6
+    assert M.vuv_agreement(ref, out) == 1.0 and M.f0_rel_error(ref, out) <= 5e-6     # FP32 transform, twiddles by squaring
     # the default path: direct FP64 evaluation of the harmonic bins, one warp per frame (at 22.05 kHz every
     # other frame position times fs is a half-integer: the exact-index path)
     out2 = np.zeros(len(rows))
@@ -209,7 +209,7 @@ def test_stonemask_kernel_source(tmp_path, name):
     if "unexpected memory mapping" in p.stderr:
         pytest.skip("ThreadSanitizer cannot map its shadow memory here")
     assert (p.returncode, p.stderr.count("WARNING: ThreadSanitizer")) == (0, 0), p.stderr[:2000]
-    assert M.f0_rel_error(ref[::4], np.fromfile(tmp_path / "f0_refined.f64")) <= 2e-6
+    assert M.f0_rel_error(ref[::4], np.fromfile(tmp_path / "f0_refined.f64")) <= 5e-6
 
 
 def test_synthesis_kernels_source(tmp_path, reference_lib):
