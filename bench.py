@@ -315,8 +315,9 @@ def other_configs(wb, c, args, audio_s, pcm_dev, lengths, stream):
             wb.kernel_timing(True)
             wb.kernel_times_reset()
             ms = dev_timed(step_h, 2, 1)
-            hk = {k: wb.kernel_time(k) for k in ["harvest_iir_kernel", "harvest_filter_kernel", "harvest_zc_kernel",
-                                                 "harvest_refine_kernel", "harvest_fix_kernel", "harvest_smooth_kernel"]}
+            hk = {k: wb.kernel_time(k) for k in ["harvest_iir_kernel", "harvest_filter_kernel", "harvest_zc_kernel", "harvest_raw_kernel",
+                                                 "harvest_refine_kernel", "harvest_unreliable_kernel", "harvest_fix_a_kernel",
+                                                 "harvest_fix_kernel", "harvest_smooth_kernel"]}
             wb.kernel_timing(False)
             out["config3_harvest"] = {
                 "workload": "%d-utterance corpus, Harvest (71-800 Hz) + CheapTrick + D4C + codec + Synthesis + statistics" % len(lengths),
@@ -517,7 +518,8 @@ def ours_arm(args):
                  ["d4c_main_kernel", "d4c_gd_kernel", "d4c_tail_kernel", "d4c_lovetrain_kernel", "cheaptrick_kernel", "synth_pulse_kernel",
                   "synth_timebase_kernel", "stonemask_kernel", "dio_filter_kernel", "dio_zc_kernel",
                   "dio_candidates_kernel", "dio_fix_kernel", "harvest_iir_kernel", "harvest_filter_kernel",
-                  "harvest_zc_kernel", "harvest_refine_kernel", "harvest_fix_kernel", "harvest_smooth_kernel",
+                  "harvest_zc_kernel", "harvest_raw_kernel", "harvest_refine_kernel", "harvest_unreliable_kernel",
+                  "harvest_fix_a_kernel", "harvest_fix_kernel", "harvest_smooth_kernel",
                   "codec_encode_kernel"]}
     wb.kernel_timing(False)
     stage_ms = wb.stage_times()

@@ -227,7 +227,7 @@ def kernel_time(name):
 def build_info():
     """Run-time switches of the library that change what a kernel executes (bench.py's roofline needs
     to know the precision of each transform)."""
-    return {"lovetrain_fp32": bool(lib().wb200_option(b"lovetrain_fp32")), "d4c_split": bool(lib().wb200_option(b"d4c_split"))}
+    return {"lovetrain_fp32": bool(lib().wb200_option(b"lovetrain_fp32"))}
 
 
 def fma_peak_tflops(fp64=True):

@@ -212,7 +212,6 @@ static double fma_peak(Context* c) {
 int option(const char* name) {
   struct Opt { const char* name; const char* env; int def; int val; };
   static Opt opts[] = {
-      {"d4c_split", "WB_D4C_SPLIT", 0, -1},            // D4C as FP64 group-delay kernel + FP32 tail kernel (3 CTAs / SM each)
       {"lovetrain_fp32", "WB_D4C_LT32", 1, -1},        // LoveTrain's transform in FP32
       {"dio_fused", "WB_DIO_FUSED", 1, -1},            // Dio: zero crossings inside the filter kernel (0: band signals through HBM)
       {"harvest_fused", "WB_HARVEST_FUSED", 1, -1},

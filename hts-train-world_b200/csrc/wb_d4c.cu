@@ -35,6 +35,7 @@ struct D4CConst {
   int fs, log2nd, log2lt, nbands, window_length, sel_boundary;
   int lt_b0, lt_b1, lt_b2;
   int out_half;              // fft_size/2 of the output axis
+  int band_top;              // highest bin of the group delay any band slice reads
   double threshold;
   int centers[kMaxBands];
 };
@@ -468,7 +469,9 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
       const double x1 = seg <= c.nbands ? seg * kFrequencyInterval : c.fs / 2.0;
       const double s = (xi - x0) / (x1 - x0);
       const double v = add_rn(coarse[seg - 1], mul_rn(s, coarse[seg] - coarse[seg - 1]));
-      out[k] = exp(v * 0.11512925464970228420);        // 10^(v/20) = e^(v ln(10)/20)
+      // 10^(v/20) = e^(v ln(10)/20): the row is an aperiodicity in (0, 1], tolerance 1e-4 absolute -- the
+      // single-precision exponential (1 ulp, 6e-8 relative) costs a quarter of the double one
+      out[k] = static_cast<double>(expf(static_cast<float>(v * 0.11512925464970228420)));
     }
   };
   // fs < 12 kHz: no 3 kHz band fits below fs/2 - 3 kHz (d4c.cpp:351-353), the reference still runs
@@ -486,6 +489,14 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
     return;
   }
   auto cslot = [log2nd](int i) { return cpad(brev(i, log2nd)); };
+  // Nothing above the highest band slice is ever read (at 48 kHz the five bands end at 18 of 24 kHz),
+  // so every per-bin sweep stops at the bin its consumer needs: the group delay up to band_top, the
+  // input of each smoothing its boundary further (smoothing_input_need), all clamped to Nd / 2.
+  const int b_f0 = smoothing_boundary(cur_f0, c.fs, Nd), b_half = smoothing_boundary(cur_f0 / 2.0, c.fs, Nd);
+  const int k_gd = min(Hd, c.band_top);                                       // static group delay
+  const int k_s2 = min(Hd, smoothing_input_need(k_gd, b_f0));                 // first smoothing of the ratio (input of the second)
+  const int k_ratio = min(Hd, smoothing_input_need(k_s2, b_half));            // centroid / power ratio, smoothed power spectrum, centroid
+  const int k_pw = min(Hd, smoothing_input_need(k_ratio, b_f0));              // raw power spectrum
 
   // The three sample windows of the frame (two centroids, power spectrum) are staged into the
   // idle `pw` array by TMA bulk copies, each issued one phase ahead so that it lands while the
@@ -573,7 +584,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
         fft_dit<LOG2ND, false, THREADS, MAXK, TWL>(cbuf, log2nd, tw);
       }
     }
-    for (int k = tid; k <= Hd; k += T) {
+    for (int k = tid; k <= k_ratio; k += T) {
       const double2 A = cbuf[cpad(k)];
       const double2 B = cbuf[cpad((Nd - k) & (Nd - 1))];
       const double cval = 0.5 * (A.x * B.y + A.y * B.x);
@@ -598,20 +609,20 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
                                     st_ok ? pw + (window_origin(2) - st_a0) : nullptr);
     for (int i = W + tid; i < Nd; i += T) cbufd[rfft_in_slot(i, log2m)] = 0.0;
     fft_dit<LMD, false, THREADS, MAXK, TWL>(cbuf, log2m, tw);
-    for (int k = tid; k <= Hd; k += T) {
+    for (int k = tid; k <= k_pw; k += T) {
       const double2 X = rfft_bin<TWL>(cbuf, log2m, k, tw);
       pw[k] = X.x * X.x + X.y * X.y;
     }
     __syncthreads();
     dc_correction(pw, cbufd, cur_f0, c.fs, Nd);
-    linear_smoothing(pw, pw, cbufd, red, cur_f0, c.fs, Nd);
+    linear_smoothing(pw, pw, cbufd, red, cur_f0, c.fs, Nd, k_ratio);
   }
   // ---- GetStaticGroupDelay (:170-186) ------------------------------------------------------------
-  for (int k = tid; k <= Hd; k += T) cen[k] = cen[k] / pw[k];
+  for (int k = tid; k <= k_ratio; k += T) cen[k] = cen[k] / pw[k];
   __syncthreads();
-  linear_smoothing(cen, cen, cbufd, red, cur_f0 / 2.0, c.fs, Nd);
-  linear_smoothing(cen, pw, cbufd, red, cur_f0, c.fs, Nd);
-  for (int k = tid; k <= Hd; k += T) cen[k] -= pw[k];
+  linear_smoothing(cen, cen, cbufd, red, cur_f0 / 2.0, c.fs, Nd, k_s2);
+  linear_smoothing(cen, pw, cbufd, red, cur_f0, c.fs, Nd, k_gd);
+  for (int k = tid; k <= k_gd; k += T) cen[k] -= pw[k];
   __syncthreads();
 
   // ---- GetCoarseAperiodicity (:192-223): two bands per complex FP32 FFT, one selection for all --
@@ -670,333 +681,6 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
 }
 
 
-// ==== split variant: three CTAs per SM =======================================
-#define WB_D4C_HAS_SPLIT 1
-// d4c_gd_kernel   : the FP64 part of d4c_main (centroids, power spectrum, smoothing, group delay)
-//                   with the 2^LOG2ND-point centroid transform done as its two half-size
-//                   decimation-in-frequency halves (even / odd output bins), one after the other in
-//                   ONE half-size buffer; writes the Nuttall-windowed group-delay slices (FP32).
-// d4c_tail_kernel : the FP32 part (band transforms, selection, interp1 row) from those slices.
-// Same arithmetic as d4c_main_kernel except for the order of the butterflies of the centroid
-// transform (radix-2 DIF stage + radix-8 passes instead of radix-16 passes).
-
-// radix-8 first pass on 8 elements given in natural sub-order (z[j] = element i0 + j * M/8) of the
-// group whose slots start at sb: slot m holds element j = brev3(m).
-__device__ __forceinline__ void first_pass8_store(double2* __restrict__ sb, const double2 (&z)[8]) {
-  double2 v[8] = {z[0], z[4], z[2], z[6], z[1], z[5], z[3], z[7]};
-#pragma unroll
-  for (int t = 0; t < 3; ++t) {
-    const int span = 1 << t;
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-      if (m & span) continue;
-      const double2 xx = rot16<false>(v[m + span], (m & (span - 1)) * (8 >> t));
-      const double2 a = v[m];
-      v[m] = cadd(a, xx);
-      v[m + span] = csub(a, xx);
-    }
-  }
-#pragma unroll
-  for (int m = 0; m < 8; ++m) sb[cpad(m)] = v[m];
-}
-
-// dynamic shared memory: [ cen: Hd+8 | cbuf: cpad_size(Hd) double2 | pw: Hd+8 | red: 160 ]
-template <int LOG2ND, int THREADS>
-__global__ void __launch_bounds__(THREADS, 3)
-d4c_gd_kernel(UttView u, const int* __restrict__ frame_utt, const double* __restrict__ frame_t,
-              const double* __restrict__ f0_in, const double* __restrict__ ap0,
-              const long long* __restrict__ rng_off, const long long* __restrict__ lt_totals,
-              const uint32_t* __restrict__ randn_tab, const double2* __restrict__ tw,
-              const double* __restrict__ nuttall, D4CConst c, float* __restrict__ slices) {
-  WB_DYN_SMEM(double2, smem2);
-  constexpr int LM = LOG2ND - 1;              // half-size transforms
-  constexpr int Nd = 1 << LOG2ND, Hd = Nd >> 1, M = Hd, G8 = M >> 3;
-  static_assert(G8 == THREADS, "one radix-8 first-pass group per thread");
-  constexpr int T = THREADS;
-  double* cen = reinterpret_cast<double*>(smem2);
-  double2* cbuf = reinterpret_cast<double2*>(cen + Hd + 8);
-  double* cbufd = reinterpret_cast<double*>(cbuf);
-  double* pw = reinterpret_cast<double*>(cbuf + cpad_size(M));
-  double* red = pw + Hd + 8;
-  const int tid = threadIdx.x;
-  const int f = blockIdx.x;
-  const double f0 = f0_in[f];
-  if (f0 == 0.0 || ap0[f] <= c.threshold) return;     // the tail kernel writes the row
-  const int utt = frame_utt[f];
-  const double* __restrict__ x = u.x + u.x_off[utt];
-  const int x_len = u.x_len[utt];
-  const double t_pos = frame_t[f];
-  const double cur_f0 = fmax(kFloorF0D4C, f0);
-  const uint32_t* __restrict__ rn = randn_tab + lt_totals[utt] + rng_off[f];
-  const int hwl4 = d4c_hwl(4.0, c.fs, cur_f0);
-  const int W = 2 * hwl4 + 1;
-  if (W > Nd || Hd + 2 * smoothing_boundary(cur_f0, c.fs, Nd) + 1 > 2 * cpad_size(M)) return;   // tail: NaN row
-
-  __shared__ uint64_t mbar;
-  auto window_origin = [&](int which) {                 // 0 / 1: centroid sides, 2: power spectrum
-    const double pos = which == 2 ? t_pos : add_rn(t_pos, which == 0 ? -0.25 / cur_f0 : 0.25 / cur_f0);
-    return matlab_round(add_rn(mul_rn(pos, (double)c.fs), 0.001)) - hwl4;
-  };
-  int st_a0 = 0, st_n = 0;
-  bool st_ok = bulk_window_range(window_origin(0), W, x_len, Hd + 8, &st_a0, &st_n);
-  unsigned st_parity = 0;
-  if (tid == 0) mbar_init(&mbar, 1);
-  __syncthreads();
-  if (st_ok && tid == 0) bulk_load_issue(pw, x + st_a0, (unsigned)st_n * 8u, &mbar);
-
-  const double turn_step = 2.0 * cur_f0 / (4.0 * c.fs);       // window angle step in units of pi
-  auto blackman = [](double cs) { return 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0); };
-
-  for (int side = 0; side < 2; ++side) {
-    const int g0 = window_origin(side);                 // global index of window sample 0
-    const uint32_t* __restrict__ rns = rn + (size_t)side * W;
-    const bool staged = st_ok;
-    const bool keep = staged || W <= Hd + 8;            // the windowed samples stay in pw for the two halves
-    double* wv = staged ? pw + (g0 - st_a0) : pw;
-    auto fresh_wave = [&](int i, double w) {            // clamped gather (d4c.cpp:52-84)
-      return x[min(x_len - 1, max(0, g0 + i))] * w + randn_from_u32(rns[i]) * kMySafeGuardMinimum;
-    };
-    __syncthreads();                                    // previous readers of cbuf / pw are done
-    if (staged) { mbar_wait(&mbar, st_parity); st_parity ^= 1u; }
-    // ---- sweep 0: windowed samples (kept in pw) and the five sums of the single-reduction
-    //      mean removal / normalisation (see d4c_main_kernel)
-    double cs0, sn0, cs_t, sn_t;
-    sincospi((double)(tid - hwl4) * turn_step, &sn0, &cs0);
-    sincospi((double)T * turn_step, &sn_t, &cs_t);
-    double sums[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    {
-      double cs = cs0, sn = sn0;
-      for (int i = tid; i < W; i += T) {
-        const double w = blackman(cs);
-        { const double c2 = cs * cs_t - sn * sn_t; sn = sn * cs_t + cs * sn_t; cs = c2; }
-        const double wave = staged ? wv[i] * w + randn_from_u32(rns[i]) * kMySafeGuardMinimum : fresh_wave(i, w);
-        if (keep) wv[i] = wave;
-        sums[0] += wave; sums[1] += w; sums[2] += wave * wave; sums[3] += wave * w; sums[4] += w * w;
-      }
-    }
-    block_sum<5>(sums, red);
-    const double coef = sums[0] / sums[1];
-    double energy = sums[2] - 2.0 * coef * sums[3] + coef * coef * sums[4];
-    if (!(energy > 1e-8 * sums[2])) {                   // DC-dominated frame: the expansion cancels, sum directly
-      double e[1] = {0.0};
-      double cs = cs0, sn = sn0;
-      for (int i = tid; i < W; i += T) {
-        const double w = blackman(cs);
-        { const double c2 = cs * cs_t - sn * sn_t; sn = sn * cs_t + cs * sn_t; cs = c2; }
-        const double v = (keep ? wv[i] : fresh_wave(i, w)) - w * coef;
-        e[0] += v * v;
-      }
-      block_sum<1>(e, red);
-      energy = e[0];
-    }
-    const double inv_sq = 1.0 / sqrt(energy);
-
-    // ---- the two decimation-in-frequency halves of the Nd-point transform of z = v + i (n+1) v
-    const int il = tid;
-    double2* __restrict__ sb = cbuf + cpad(brev(il, LM - 3) << 3);
-    double cs_i, sn_i, cs_g, sn_g;
-    sincospi((double)(il - hwl4) * turn_step, &sn_i, &cs_i);
-    sincospi((double)G8 * turn_step, &sn_g, &cs_g);
-    for (int half = 0; half < 2; ++half) {
-      double2 z[8];
-      double cs = cs_i, sn = sn_i;
-      // (v, (n + 1) v) of window sample i.  The first half turns the kept windowed sample into the
-      // normalised one in place (every thread owns its samples), so the second half only reads it.
-      const bool reuse = keep && half == 1;
-      auto sample = [&](int i) {
-        double v = 0.0;
-        if (reuse) {
-          if (i < W) v = wv[i];
-        } else {
-          if (i < W) {
-            const double w = blackman(cs);
-            v = ((keep ? wv[i] : fresh_wave(i, w)) - w * coef) * inv_sq;
-            if (keep) wv[i] = v;
-          }
-          { const double c2 = cs * cs_g - sn * sn_g; sn = sn * cs_g + cs * sn_g; cs = c2; }
-        }
-        return make_double2(v, v * (i + 1.0));
-      };
-#pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] = sample(il + j * G8);
-      if (W > M) {                                      // block-uniform: windows longer than half the transform fold
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const double2 e = sample(il + (j + 8) * G8);
-          z[j] = half == 0 ? cadd(z[j], e) : csub(z[j], e);
-        }
-      }
-      if (half == 1) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) z[j] = cmul(__ldg(&tw[il + j * G8]), z[j]);      // exp(-2 pi i m / Nd), m < Hd
-      }
-      __syncthreads();                                  // the product loop of the previous half is done with cbuf
-      first_pass8_store(sb, z);
-      __syncthreads();
-      if (half == 1) {                                  // pw is free now: stage the next window behind the passes
-        st_ok = bulk_window_range(window_origin(side + 1), W, x_len, Hd + 8, &st_a0, &st_n);
-        if (st_ok && tid == 0) bulk_load_issue(pw, x + st_a0, (unsigned)st_n * 8u, &mbar);
-      }
-      fft_run_passes<LM, 3, 1, false, THREADS, LOG2ND>(cbuf, tw);
-      // centroid bins of this half: Z[k] and its partner Z[Nd - k] have the same parity
-      if (half == 0) {
-        for (int j = tid; j <= M / 2; j += T) {         // k = 2 j
-          const double2 P = cbuf[cpad(j)];
-          const double2 Q = cbuf[cpad((M - j) & (M - 1))];
-          const double cval = 0.5 * (P.x * Q.y + P.y * Q.x);
-          cen[2 * j] = side == 0 ? cval : cen[2 * j] + cval;
-        }
-      } else {
-        for (int j = tid; j < M / 2; j += T) {          // k = 2 j + 1
-          const double2 P = cbuf[cpad(j)];
-          const double2 Q = cbuf[cpad(M - 1 - j)];
-          const double cval = 0.5 * (P.x * Q.y + P.y * Q.x);
-          cen[2 * j + 1] = side == 0 ? cval : cen[2 * j + 1] + cval;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  dc_correction(cen, cbufd, cur_f0, c.fs, Nd);
-
-  // ---- GetSmoothedPowerSpectrum (:148-164): real transform on the same half-size buffer ----------
-  {
-    auto pwslot = [](int i) { return rfft_in_slot(i, LM); };
-    auto pvslot = [](int i) { return i; };              // unused (STORE_W = false)
-    if (st_ok) mbar_wait(&mbar, st_parity);
-    const int Wp = windowed_waveform<false>(x, x_len, c.fs, cur_f0, t_pos, kHanning, 4.0, rn + 2 * (size_t)W,
-                                            cbufd, pwslot, pvslot, red,
-                                            st_ok ? pw + (window_origin(2) - st_a0) : nullptr);
-    for (int i = Wp + tid; i < Nd; i += T) cbufd[rfft_in_slot(i, LM)] = 0.0;
-    fft_dit<LM, false, THREADS, 3, LOG2ND>(cbuf, LM, tw);
-    for (int k = tid; k <= Hd; k += T) {
-      const double2 X = rfft_bin<LOG2ND>(cbuf, LM, k, tw);
-      pw[k] = X.x * X.x + X.y * X.y;
-    }
-    __syncthreads();
-    dc_correction(pw, cbufd, cur_f0, c.fs, Nd);
-    linear_smoothing(pw, pw, cbufd, red, cur_f0, c.fs, Nd);
-  }
-  // ---- GetStaticGroupDelay (:170-186) ------------------------------------------------------------
-  for (int k = tid; k <= Hd; k += T) cen[k] = cen[k] / pw[k];
-  __syncthreads();
-  linear_smoothing(cen, cen, cbufd, red, cur_f0 / 2.0, c.fs, Nd);
-  linear_smoothing(cen, pw, cbufd, red, cur_f0, c.fs, Nd);
-  // ---- the Nuttall-windowed slice of every band (GetCoarseAperiodicity :204-211), FP32 -----------
-  {
-    const int hw = c.window_length / 2;
-    float* __restrict__ so = slices + (size_t)f * c.nbands * c.window_length;
-    for (int b = 0; b < c.nbands; ++b) {
-      const int ca = c.centers[b] - hw;
-      for (int i = tid; i < c.window_length; i += T)
-        so[b * c.window_length + i] = static_cast<float>((cen[ca + i] - pw[ca + i]) * nuttall[i]);
-    }
-  }
-}
-
-// dynamic shared memory: [ fb: cpadf(Nd-1)+1 float2 (8-byte aligned) | P: nbands * (Hd+1) floats | coarse: kMaxBands+2 ]
-__host__ __device__ constexpr int d4c_tail_fb_slots(int nd) { return (cpadf(nd - 1) + 2) & ~1; }
-template <int LOG2ND, int THREADS>
-__global__ void __launch_bounds__(THREADS, 3)
-d4c_tail_kernel(const double* __restrict__ f0_in, const double* __restrict__ ap0,
-                const float* __restrict__ slices, const float2* __restrict__ twf, D4CConst c,
-                double* __restrict__ ap_out) {
-  WB_DYN_SMEM(double2, smem2);
-  constexpr int Nd = 1 << LOG2ND, Hd = Nd >> 1, G = Nd >> 4;
-  constexpr int T = THREADS;
-  float2* fb = reinterpret_cast<float2*>(smem2);
-  float* P = reinterpret_cast<float*>(fb + d4c_tail_fb_slots(Nd));
-  const int pstride = Hd + 1;
-  double* coarse = reinterpret_cast<double*>(P + ((c.nbands * pstride + 1) & ~1));
-  const int tid = threadIdx.x;
-  const int f = blockIdx.x;
-  double* __restrict__ out = ap_out + (size_t)f * (c.out_half + 1);
-  const double f0 = f0_in[f];
-  if (f0 == 0.0 || ap0[f] <= c.threshold) {           // d4c.cpp:380 + InitializeAperiodicity
-    for (int k = tid; k <= c.out_half; k += T) out[k] = 1.0 - kMySafeGuardMinimum;
-    return;
-  }
-  const double cur_f0 = fmax(kFloorF0D4C, f0);
-  if (2 * d4c_hwl(4.0, c.fs, cur_f0) + 1 > Nd || Hd + 2 * smoothing_boundary(cur_f0, c.fs, Nd) + 1 > 2 * cpad_size(Hd)) {
-    for (int k = tid; k <= c.out_half; k += T) out[k] = __longlong_as_double(0x7ff8000000000000LL);
-    return;
-  }
-  const int wl = c.window_length;
-  const float* __restrict__ sl = slices + (size_t)f * c.nbands * wl;
-  for (int b0 = 0; b0 < c.nbands; b0 += 2) {
-    const bool two = b0 + 1 < c.nbands;
-    const float* __restrict__ sa = sl + b0 * wl;
-    const float* __restrict__ sbnd = sl + (b0 + 1) * wl;
-    // pruned radix-16 first pass (see band_fft_pruned): only inputs r = 0, 1, 2 of a group are non-zero
-    for (int il = tid; il < G; il += T) {
-      const int g = brev(il, LOG2ND - 4);
-      float2 xin[3];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const int i = il + r * G;
-        xin[r] = make_float2(0.f, 0.f);
-        if (i < wl) {
-          xin[r].x = sa[i];
-          if (two) xin[r].y = sbnd[i];
-        }
-      }
-      float2* __restrict__ grp = fb + cpadf(g << 4);
-      const bool has2 = il + 2 * G < wl;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float2 t1 = rot16<false>(xin[1], q);
-        float2 lo = cadd(xin[0], t1), hi = csub(xin[0], t1);
-        if (has2) {
-          float2 t2 = rot16<false>(xin[2], (2 * q) & 7);
-          if (2 * q >= 8) t2 = make_float2(-t2.x, -t2.y);
-          lo = cadd(lo, t2);
-          hi = cadd(hi, t2);
-        }
-        grp[cpadf(q)] = lo;
-        grp[cpadf(q + 8)] = hi;
-      }
-    }
-    __syncthreads();
-    fft_run_passes<LOG2ND, 4, 1, false, THREADS, LOG2ND>(fb, twf);
-    for (int k = tid; k <= Hd; k += T) {
-      const float2 A = fb[cpadf(k)];
-      const float2 B = fb[cpadf((Nd - k) & (Nd - 1))];
-      const float xr = 0.5f * (A.x + B.x), xi = 0.5f * (A.y - B.y);
-      const float yr = 0.5f * (A.y + B.y), yi = 0.5f * (B.x - A.x);
-      P[b0 * pstride + k] = xr * xr + xi * xi;
-      if (two) P[(b0 + 1) * pstride + k] = yr * yr + yi * yi;
-    }
-    __syncthreads();
-  }
-  {                                                 // one warp per band, keys in registers
-    constexpr int NPL = (Hd + 1 + 31) / 32;
-    for (int b = tid >> 5; b < c.nbands; b += THREADS / 32) {
-      double low, tot;
-      warp_select_low_sum<NPL>(P + b * pstride, Hd + 1, c.sel_boundary + 1, &low, &tot);
-      if ((tid & 31) == 0) coarse[1 + b] = fmin(0.0, 10.0 * log10(low / tot) + (cur_f0 - 100.0) / 50.0);
-    }
-  }
-  if (tid == 0) { coarse[0] = -60.0; coarse[c.nbands + 1] = -kMySafeGuardMinimum; }
-  __syncthreads();
-  // ---- GetAperiodicity (:325-333): interp1 over {0, 3k, ..., fs/2} then 10^(dB/20) ---------------
-  const int nk = c.nbands + 2;
-  const int N_out = 2 * c.out_half;
-  for (int k = tid; k <= c.out_half; k += T) {
-    const double xi = mul_rn((double)k, (double)c.fs) / N_out;
-    int seg = 1;
-    while (seg < nk - 1) {
-      const double knot = seg <= c.nbands ? seg * kFrequencyInterval : c.fs / 2.0;
-      if (xi < knot) break;
-      ++seg;
-    }
-    const double x0 = (seg - 1) * kFrequencyInterval;
-    const double x1 = seg <= c.nbands ? seg * kFrequencyInterval : c.fs / 2.0;
-    const double s = (xi - x0) / (x1 - x0);
-    const double v = add_rn(coarse[seg - 1], mul_rn(s, coarse[seg] - coarse[seg - 1]));
-    out[k] = exp(v * 0.11512925464970228420);
-  }
-}
-
 }  // namespace
 
 #ifndef WB_HOST_EMU      // the launcher; tests/emu has its own
@@ -1020,8 +704,11 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
   if (c.nbands < 0 || c.nbands > kMaxBands || c.nbands > kMaxSets) { set_error("D4C: unsupported number of bands %d (fs %d)", c.nbands, fs); return false; }
   c.window_length = static_cast<int>(kFrequencyInterval * nd / fs) * 2 + 1;                         // :356-357
   c.sel_boundary = matlab_round(nd * 8.0 / c.window_length);                                        // :196-197
-  for (int i = 0; i < c.nbands; ++i)
+  c.band_top = 0;
+  for (int i = 0; i < c.nbands; ++i) {
     c.centers[i] = static_cast<int>(kFrequencyInterval * (i + 1) * nd / fs);                        // :204-205
+    c.band_top = std::max(c.band_top, c.centers[i] - c.window_length / 2 + c.window_length - 1);
+  }
   c.lt_b0 = static_cast<int>(ceil(100.0 * nlt / fs));                                               // :267-269
   c.lt_b1 = static_cast<int>(ceil(4000.0 * nlt / fs));
   c.lt_b2 = static_cast<int>(ceil(7900.0 * nlt / fs));
@@ -1090,29 +777,6 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
     const size_t smem = d4c_cbuf_slots(nd, c.nbands) * sizeof(double2) + (size_t)(2 * (hd + 8) + 160) * sizeof(double) +
                         sizeof(SelectScratch) + (kMaxBands + 2) * sizeof(double);
     const int threads = nd > 4096 ? 512 : 256;
-    const bool split = option("d4c_split") != 0;
-    if (split && c.log2nd == 12 && c.window_length <= 3 * (nd >> 4)) {
-      DevBuf<float> slices;
-      if (!slices.alloc((size_t)total_frames * c.nbands * c.window_length)) return false;
-      const size_t smem1 = (size_t)(2 * (hd + 8) + 160) * sizeof(double) + (size_t)cpad_size(hd) * sizeof(double2);
-      const size_t smem2 = (size_t)d4c_tail_fb_slots(nd) * sizeof(float2) + (size_t)((c.nbands * (hd + 1) + 1) & ~1) * sizeof(float) +
-                           (kMaxBands + 2) * sizeof(double);
-      {
-        KernelTimer kg("d4c_gd_kernel");
-        WB_CUDA_OR_RETURN(cudaFuncSetAttribute(d4c_gd_kernel<12, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1), false);
-        d4c_gd_kernel<12, 256><<<total_frames, 256, smem1, st>>>(u, frame_utt, frame_t, f0, d_ap0.p, offs_main.p, tot_lt.p, ctxp->d_randn,
-                                                                ctxp->tw_c(12), d_win.p, c, slices.p);
-        WB_LAUNCH_CHECK(); kg.stop();
-      }
-      {
-        KernelTimer kt("d4c_tail_kernel");
-        WB_CUDA_OR_RETURN(cudaFuncSetAttribute(d4c_tail_kernel<12, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2), false);
-        d4c_tail_kernel<12, 256><<<total_frames, 256, smem2, st>>>(f0, d_ap0.p, slices.p, ctxp->tw_cf(12), c, ap);
-        WB_LAUNCH_CHECK(); kt.stop();
-      }
-      WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
-      return true;
-    }
     KernelTimer kt2("d4c_main_kernel");
 #define WB_D4C_LAUNCH(L, TH, ...)                                                                                   \
   do {                                                                                                              \

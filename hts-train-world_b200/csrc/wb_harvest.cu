@@ -617,7 +617,32 @@ __global__ void harvest_fix_a_kernel(const double* __restrict__ cand, const doub
   }
 }
 
-// phase B: FixStep3 (:976-1004) and FixStep4 (:1009-1032); one warp per utterance, lane 0 walks.
+// SelectBestF0 (:636-650) by a warp: the sequential rule keeps the LAST candidate among those with the
+// smallest relative error <= allowed; lanes scan strided subsets with the same rule and the partial
+// results are joined by (smaller error, then larger index).  Every lane returns the result.
+__device__ __forceinline__ double harvest_select_best_warp(double ref, const double* __restrict__ row, int n, double allowed,
+                                                           int lane) {
+  double best_error = allowed;
+  int best_i = -1;
+  for (int i = lane; i < n; i += 32) {
+    const double t = fabs(ref - row[i]) / ref;
+    if (t > best_error) continue;
+    best_error = t;
+    best_i = i;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double e = __shfl_xor_sync(0xffffffffu, best_error, o);
+    const int i = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (i >= 0 && (best_i < 0 || e < best_error || (e == best_error && i > best_i))) { best_error = e; best_i = i; }
+  }
+  return best_i >= 0 ? row[best_i] : 0.0;
+}
+
+// phase B: FixStep3 (:976-1004) and FixStep4 (:1009-1032); one warp per utterance.  The walk along the
+// contour is sequential by nature (every step depends on the F0 just chosen), but each step's search over
+// the candidate slots, the score look-ups of MergeF0 and the contour copies are spread over the lanes;
+// the scalar bookkeeping (means, boundaries, merge order) stays on lane 0 in the reference's order.
 // mc: [sections][n] scratch of this utterance; chan: pointer permutation for Swap (:828-843).
 __global__ void harvest_fix_b_kernel(const double* __restrict__ cand, const double* __restrict__ score,
                                      const int* __restrict__ g_off, const int* __restrict__ g_len,
@@ -626,6 +651,7 @@ __global__ void harvest_fix_b_kernel(const double* __restrict__ cand, const doub
                                      const long long* __restrict__ mc_off, double* __restrict__ mc_all,
                                      int* __restrict__ chan_all, int* __restrict__ order_all) {
   const int u = blockIdx.x;
+  const int lane = threadIdx.x;
   const int n = g_len[u], off = g_off[u], slots = nc_utt[u] * kOverlap;
   const double* __restrict__ step2 = tmp1 + off;
   double* __restrict__ step3 = tmp2 + off;
@@ -635,39 +661,41 @@ __global__ void harvest_fix_b_kernel(const double* __restrict__ cand, const doub
   double* mc = mc_all + mc_off[u];
   int* chan = chan_all + off;
   int* order = order_all + off;
-  __shared__ int nb_s;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) step3[i] = step2[i];
-  if (threadIdx.x == 0) nb_s = harvest_boundaries(step2, n, bl);
-  __syncthreads();
+  __shared__ int nb_s, nchn_s;
+  for (int i = lane; i < n; i += 32) step3[i] = step2[i];
+  if (lane == 0) nb_s = harvest_boundaries(step2, n, bl);
+  __syncwarp();
   const int nsec = nb_s / 2;
   // GetMultiChannelF0 (:769-781)
   for (int s = 0; s < nsec; ++s)
-    for (int j = threadIdx.x; j < n; j += blockDim.x)
+    for (int j = lane; j < n; j += 32)
       mc[(size_t)s * n + j] = (j >= bl[2 * s] && j <= bl[2 * s + 1]) ? step2[j] : 0.0;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < nsec; ++s) chan[s] = s;
-    // Extend (:867-883) with ExtendF0 (:794-823), in place on mc and bl
-    for (int s = 0; s < nsec; ++s) {
-      double* ext = mc + (size_t)s * n;
-      for (int dir = 0; dir < 2; ++dir) {
-        const int shift = dir == 0 ? 1 : -1;
-        const int origin = dir == 0 ? bl[2 * s + 1] : bl[2 * s];
-        const int last_point = dir == 0 ? min(n - 2, bl[2 * s + 1] + 100) : max(1, bl[2 * s] - 100);
-        double tmp_f0 = ext[origin];
-        int shifted_origin = origin, count = 0;
-        const int distance = abs(last_point - origin);
-        for (int i = 0; i <= distance; ++i) {
-          const int idx = origin + shift * i + shift;
-          const double v = harvest_select_best(tmp_f0, cu + (size_t)idx * slots, slots, 0.18);
-          ext[idx] = v;
-          if (v == 0.0) ++count;
-          else { tmp_f0 = v; count = 0; shifted_origin = idx; }
-          if (count == 4) break;
-        }
-        if (dir == 0) bl[2 * s + 1] = shifted_origin; else bl[2 * s] = shifted_origin;
+  for (int s = lane; s < nsec; s += 32) chan[s] = s;
+  __syncwarp();
+  // Extend (:867-883) with ExtendF0 (:794-823), in place on mc and bl
+  for (int s = 0; s < nsec; ++s) {
+    double* ext = mc + (size_t)s * n;
+    for (int dir = 0; dir < 2; ++dir) {
+      const int shift = dir == 0 ? 1 : -1;
+      const int origin = dir == 0 ? bl[2 * s + 1] : bl[2 * s];
+      const int last_point = dir == 0 ? min(n - 2, bl[2 * s + 1] + 100) : max(1, bl[2 * s] - 100);
+      double tmp_f0 = ext[origin];
+      int shifted_origin = origin, count = 0;
+      const int distance = abs(last_point - origin);
+      __syncwarp();                                                 // bl / ext read by every lane before lane 0 rewrites them
+      for (int i = 0; i <= distance; ++i) {
+        const int idx = origin + shift * i + shift;
+        const double v = harvest_select_best_warp(tmp_f0, cu + (size_t)idx * slots, slots, 0.18, lane);
+        if (lane == 0) ext[idx] = v;
+        if (v == 0.0) ++count;
+        else { tmp_f0 = v; count = 0; shifted_origin = idx; }
+        if (count == 4) break;
       }
+      if (lane == 0) { if (dir == 0) bl[2 * s + 1] = shifted_origin; else bl[2 * s] = shifted_origin; }
+      __syncwarp();
     }
+  }
+  if (lane == 0) {
     // ExtendSub (:845-862); mean_f0 is deliberately not reset between sections (as in the reference)
     int nchn = 0;
     double mean_f0 = 0.0;
@@ -684,47 +712,65 @@ __global__ void harvest_fix_b_kernel(const double* __restrict__ cand, const doub
       }
     }
     if (nchn != 0) {
-      // MergeF0 (:944-971)
       for (int i = 0; i < nchn; ++i) order[i] = i;                  // MakeSortedOrder (:888-901)
       for (int i = 1; i < nchn; ++i)
         for (int j = i - 1; j >= 0; --j) {
           if (bl[order[j] * 2] > bl[order[i] * 2]) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
           else break;
         }
-      const double* ch0 = mc + (size_t)chan[0] * n;
-      for (int i = 0; i < n; ++i) step3[i] = ch0[i];
-      for (int i = 1; i < nchn; ++i) {
-        const int oi = order[i];
-        const double* f2 = mc + (size_t)chan[oi] * n;
-        const int st2 = bl[oi * 2], ed2 = bl[oi * 2 + 1];
-        if (st2 - bl[1] > 0) {
-          for (int j = st2; j <= ed2; ++j) step3[j] = f2[j];
-          bl[0] = st2;
-          bl[1] = ed2;
-        } else {
-          const int st1 = bl[0], ed1 = bl[1];                       // MergeF0Sub (:917-939)
-          if (st1 <= st2 && ed1 >= ed2) { bl[1] = ed1; continue; }
-          double score1 = 0.0, score2 = 0.0;
-          for (int j = st2; j <= ed1; ++j) {
-            double s1 = 0.0, s2 = 0.0;                              // SearchScore (:906-912)
-            const double v1 = step3[j], v2 = f2[j];
-            for (int q = 0; q < slots; ++q) {
-              const double cq = cu[(size_t)j * slots + q], sq = su[(size_t)j * slots + q];
-              if (v1 == cq && s1 < sq) s1 = sq;
-              if (v2 == cq && s2 < sq) s2 = sq;
-            }
-            score1 += s1;
-            score2 += s2;
-          }
-          if (score1 > score2) { for (int j = ed1; j <= ed2; ++j) step3[j] = f2[j]; }
-          else { for (int j = st2; j <= ed2; ++j) step3[j] = f2[j]; }
-          bl[1] = ed2;
-        }
-      }
     }
-    // FixStep4 (:1009-1032), threshold 9; result back into tmp1
-    double* step4 = tmp1 + off;
-    for (int i = 0; i < n; ++i) step4[i] = step3[i];
+    nchn_s = nchn;
+  }
+  __syncwarp();
+  const int nchn = nchn_s;
+  if (nchn != 0) {
+    // MergeF0 (:944-971)
+    const double* ch0 = mc + (size_t)chan[0] * n;
+    for (int i = lane; i < n; i += 32) step3[i] = ch0[i];
+    __syncwarp();
+    // bl[0] / bl[1] double as the merged contour's boundaries exactly as in the reference (which rewrites
+    // boundary_list[0..1] in place, so a later channel whose slot is 0 sees the rewritten values)
+    for (int i = 1; i < nchn; ++i) {
+      const int oi = order[i];
+      const double* f2 = mc + (size_t)chan[oi] * n;
+      const int st2 = bl[oi * 2], ed2 = bl[oi * 2 + 1];
+      const int st1 = bl[0], ed1 = bl[1];
+      __syncwarp();                                                 // every lane has read bl before lane 0 rewrites it
+      if (st2 - ed1 > 0) {
+        for (int j = st2 + lane; j <= ed2; j += 32) step3[j] = f2[j];
+        if (lane == 0) { bl[0] = st2; bl[1] = ed2; }
+      } else if (!(st1 <= st2 && ed1 >= ed2)) {                     // MergeF0Sub (:917-939); otherwise bl[1] stays ed1
+        double score1 = 0.0, score2 = 0.0;
+        for (int j = st2; j <= ed1; ++j) {
+          double s1 = 0.0, s2 = 0.0;                                // SearchScore (:906-912): a maximum, any order
+          const double v1 = step3[j], v2 = f2[j];
+          for (int q = lane; q < slots; q += 32) {
+            const double cq = cu[(size_t)j * slots + q], sq = su[(size_t)j * slots + q];
+            if (v1 == cq && s1 < sq) s1 = sq;
+            if (v2 == cq && s2 < sq) s2 = sq;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            s1 = fmax(s1, __shfl_xor_sync(0xffffffffu, s1, o));
+            s2 = fmax(s2, __shfl_xor_sync(0xffffffffu, s2, o));
+          }
+          score1 += s1;
+          score2 += s2;
+        }
+        __syncwarp();
+        if (score1 > score2) { for (int j = ed1 + lane; j <= ed2; j += 32) step3[j] = f2[j]; }
+        else { for (int j = st2 + lane; j <= ed2; j += 32) step3[j] = f2[j]; }
+        if (lane == 0) bl[1] = ed2;
+      }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  // FixStep4 (:1009-1032), threshold 9; result back into tmp1
+  double* step4 = tmp1 + off;
+  for (int i = lane; i < n; i += 32) step4[i] = step3[i];
+  __syncwarp();
+  if (lane == 0) {
     const int nb4 = harvest_boundaries(step3, n, bl);
     for (int i = 0; i < nb4 / 2 - 1; ++i) {
       const int distance = bl[(i + 1) * 2] - bl[i * 2 + 1] - 1;
@@ -1013,7 +1059,8 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
     bool fused_done = false;
     if (option("harvest_fused") && hb->V > 64) {
       // band-pass filters + zero crossings in one kernel: the 152 channel signals never leave shared memory
-      constexpr int kCap = 128;                              // events per (list, block): ~1 500 samples at 8 kHz per block
+      constexpr int kCap = 256;                              // events per (list, block): a block is ~1 550 samples at 8 kHz (0.19 s), the
+                                                             // highest channel (880 Hz) yields ~170 events of each type in it
       OlsConst ocz = oc;
       ocz.V = hb->V - 2;
       const int n_blocks = (sub_max_y - 1 + ocz.V - 1) / ocz.V;
@@ -1083,12 +1130,13 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
         WB_LAUNCH_CHECK(); kt.stop();
       }
     }
+    KernelTimer ktr("harvest_raw_kernel");
     harvest_raw_kernel<<<dim3((sub_max_g + 127) / 128, nu * c.nch), 128, 0, st>>>(d_edges.p, d_loff.p, d_ltot.p, d_goff.p, d_glen.p,
                                                                                 hb->d_boundary.p, c, u0, d_roff.p, d_raw.p);
     WB_LAUNCH_CHECK();
     harvest_detect_kernel<<<dim3((sub_max_g + 127) / 128, nu), 128, 0, st>>>(d_raw.p, d_roff.p, d_goff.p, d_glen.p, c.nch, max_base, u0,
                                                                            d_base.p, d_nc.p);
-    WB_LAUNCH_CHECK();
+    WB_LAUNCH_CHECK(); ktr.stop();
     WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);      // scratch buffers die with this scope
     u0 = u1;
   }
@@ -1124,16 +1172,18 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
       }
       WB_LAUNCH_CHECK(); kt.stop();
     }
+    KernelTimer ktu("harvest_unreliable_kernel");
     harvest_unreliable_kernel<<<(unsigned)((ctot + 255) / 256), 256, 0, st>>>(d_cand.p, d_score.p, d_glen.p, d_nc.p, d_coff.p, n_utt, d_wfirst.p,
                                                                              ctot, d_cand2.p, d_score2.p);
-    WB_LAUNCH_CHECK();
+    WB_LAUNCH_CHECK(); ktu.stop();
   }
   // ---- 5. contour logic -------------------------------------------------------------------------------------
   // bl_all is indexed by 2 * g_off[u]; the smoothing stage needs 2 * (g_len + 600) entries at most, and
   // sections are at least 1 frame apart, so 2 * g_off[u] + ... stays inside because g_len >= 602 is not
   // guaranteed: use a separate, padded offset table for the smoothing boundaries below.
+  KernelTimer kta("harvest_fix_a_kernel");
   harvest_fix_a_kernel<<<n_utt, 256, 0, st>>>(d_cand2.p, d_score2.p, d_goff.p, d_glen.p, d_nc.p, d_coff.p, d_tmp1.p, d_tmp2.p, d_bl.p, d_nsec.p);
-  WB_LAUNCH_CHECK();
+  WB_LAUNCH_CHECK(); kta.stop();
   std::vector<int> h_nsec(n_utt);
   if (!read_back(h_nsec.data(), d_nsec.p, n_utt * sizeof(int))) return false;
   {

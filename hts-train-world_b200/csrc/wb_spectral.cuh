@@ -32,9 +32,9 @@ __device__ __forceinline__ int smoothing_boundary(double width, int fs, int N) {
 // path.  `in` must be complete on entry; ends with __syncthreads().
 template <int PER>
 __device__ __forceinline__ bool mirrored_cumsum(const double* in, double* cum, double* red, int half,
-                                                int boundary, int fs, double inv_n) {
+                                                int boundary, int fs, double inv_n, int len_limit = 0x7fffffff) {
   const int T = blockDim.x, tid = threadIdx.x;
-  const int len = half + 2 * boundary + 1;
+  const int len = min(half + 2 * boundary + 1, len_limit);      // a prefix of the running sum is all a caller with n_out < half needs
   const int per = (len + T - 1) / T;
   if (per > PER) return false;
   const int lo = tid * per;
@@ -70,19 +70,25 @@ __device__ __forceinline__ bool mirrored_cumsum(const double* in, double* cum, d
   return true;
 }
 
-// Rectangular smoothing of in[0..N/2] with the given width (Hz) -> out[0..N/2]; out may
+// Rectangular smoothing of in[0..N/2] with the given width (Hz) -> out[0..n_out]; out may
 // alias in.  cum: scratch of >= N/2 + 2*boundary + 1 doubles; red: >= 33 doubles.
+// out[k] is a difference of the running sum of the mirrored input at k + boundary - 1/2 -+ width / (2 df),
+// i.e. it reads the sum up to element k + 3 boundary / 2 + 1 and the input up to k + boundary / 2 + 1: a
+// caller that needs only the bins up to n_out < N/2 (D4C: nothing above the highest band is ever used)
+// gets the same values from a prefix -- smoothing_input_need(n_out, boundary) input bins.
 // Must be entered by all threads with `in` complete (caller syncs); ends with __syncthreads().
 // Not inlined: D4C calls it three times per frame and the kernels are instruction-cache bound.
+__host__ __device__ __forceinline__ int smoothing_input_need(int n_out, int boundary) { return n_out + boundary + 3; }
 static __device__ __noinline__ void linear_smoothing(const double* in, double* out, double* cum,
-                                              double* red, double width, int fs, int N) {
+                                              double* red, double width, int fs, int N, int n_out) {
   const int T = blockDim.x, tid = threadIdx.x;
   const int half = N / 2;
   const int boundary = smoothing_boundary(width, fs, N);
-  const int len = half + 2 * boundary + 1;
+  n_out = min(n_out, half);
+  const int len = min(half + 2 * boundary + 1, n_out + 2 * boundary + 3);
   const double inv_df = (double)N / fs;
   const double inv_n = 1.0 / N;                 // N is a power of two: x * inv_n == x / N exactly
-  if (!mirrored_cumsum<9>(in, cum, red, half, boundary, fs, inv_n)) {
+  if (!mirrored_cumsum<9>(in, cum, red, half, boundary, fs, inv_n, len)) {
     for (int i = tid; i < len; i += T) {
       double v;
       if (i < boundary) v = in[boundary - i];
@@ -95,7 +101,7 @@ static __device__ __noinline__ void linear_smoothing(const double* in, double* o
   }
   const double origin_axis = -(boundary - 0.5) * fs / N;
   const double inv_width = 1.0 / width;
-  for (int k = tid; k <= half; k += T) {
+  for (int k = tid; k <= n_out; k += T) {
     const double fa = add_rn(mul_rn((double)k * inv_n, (double)fs), -width / 2.0);
     const double low = interp1q_at(origin_axis, inv_df, cum, len, fa);
     const double high = interp1q_at(origin_axis, inv_df, cum, len, add_rn(fa, width));

@@ -439,6 +439,22 @@ __device__ __forceinline__ void exp_sincos(float re, float im, float* er, float*
 __device__ __forceinline__ double log_of(double v, double) { return log(v); }
 __device__ __forceinline__ float log_of(double v, float) { return __logf(static_cast<float>(v)); }
 
+// Overlap-add (W/src/synthesis.cpp:376-383) with a result that does not depend on the order in which the
+// work items reach a sample: every response value is rounded once to a multiple of 2^-40 and accumulated
+// as a 64-bit integer (integer addition is associative, an atomic double add is not), and one pass at the
+// end converts the sums back.  2^-40 = 9e-13 is 20 dB below the rounding of the FP32 transforms even for a
+// recording at -120 dB; the sums hold |y| < 2^23 (double samples on a 16-bit scale fit), values beyond
+// saturate.
+constexpr double kOlaScale = 1099511627776.0;            // 2^40
+__device__ __forceinline__ void ola_add(double* y, int i, double r) {
+  const double q = fmin(fmax(r * kOlaScale, -4.6e18), 4.6e18);
+  atomicAdd(reinterpret_cast<unsigned long long*>(y) + i, static_cast<unsigned long long>(__double2ll_rn(q)));
+}
+__global__ void synth_ola_finish_kernel(double* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = static_cast<double>(reinterpret_cast<const long long*>(y)[i]) * (1.0 / kOlaScale);
+}
+
 template <int LOG2N, typename C, int THREADS = 256, int MINB = (sizeof(C) == 8 ? 1024 : 768) / THREADS>      // LOG2N 0: size given at run time (c.log2n)
 __global__ void __launch_bounds__(THREADS, MINB)
 synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ ap_all,
@@ -614,7 +630,7 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
       const double pr = jj < half ? -dc[0] * dc_remover[jj] : (double)v.x - dc[0] * dc_remover[jj];
       const double r = (pr * sqrt_noise + (double)v.y) / N;
       const int oi = jj + c0.index - half + 1;
-      if (oi >= 0 && oi <= c0.y_len - 1) atomicAdd(&y[oi], r);
+      if (oi >= 0 && oi <= c0.y_len - 1) ola_add(y, oi, r);
     }
   } else {
     double* __restrict__ ya = y_all + y_off[c0.utt];
@@ -623,10 +639,10 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
       const int raw = jj < half ? jj + half : jj - half;
       const C v = cbuf[cpadT<C>(raw)];
       const int oa = jj + c0.index - half + 1;
-      if (oa >= 0 && oa <= c0.y_len - 1) atomicAdd(&ya[oa], (double)v.x / N);
+      if (oa >= 0 && oa <= c0.y_len - 1) ola_add(ya, oa, (double)v.x / N);
       if (pb >= 0) {
         const int ob = jj + c1.index - half + 1;
-        if (ob >= 0 && ob <= c1.y_len - 1) atomicAdd(&yb[ob], (double)v.y / N);
+        if (ob >= 0 && ob <= c1.y_len - 1) ola_add(yb, ob, (double)v.y / N);
       }
     }
   }
@@ -756,6 +772,8 @@ bool synthesis_run(Batch* b, const int* y_len) {
   }
 #undef WB_SP_LAUNCH
   WB_LAUNCH_CHECK(); kt3.stop();
+  synth_ola_finish_kernel<<<148 * 8, 256, 0, st>>>(b->y.p, b->total_y);      // integer sums -> samples
+  WB_LAUNCH_CHECK();
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
   return true;
 }

@@ -45,8 +45,9 @@ WORLD_API int wb200_kernel_time(const char *name, double *ms_total, long long *l
 /* measured CUDA-core FMA peak in TFLOP/s (fp64 != 0: double, else float) — the roofline
  * denominator of SURVEY.md 8(d) */
 WORLD_API double wb200_measure_fma_peak(int fp64);
-/* state (0 / 1) of a run-time switch of the library: "d4c_split", "lovetrain_fp32" (environment
- * WB_D4C_SPLIT / WB_D4C_LT32 = 0 | 1 override the defaults); unknown names give 0 */
+/* state (0 / 1) of a run-time switch of the library: "lovetrain_fp32", "stonemask_dft", "dio_fused",
+ * "harvest_fused", "harvest_refine_thread" (environment WB_D4C_LT32, WB_STONEMASK_DFT, WB_DIO_FUSED,
+ * WB_HARVEST_FUSED, WB_HARVEST_REFINE_THREAD = 0 | 1 override the defaults); unknown names give 0 */
 WORLD_API int wb200_option(const char *name);
 /* first `n` values of the randn table as doubles (test hook: must equal the reference's
  * randn() stream after randn_reseed(), W/src/matlabfunctions.cpp:247-277) */

@@ -154,6 +154,8 @@ inline void __sincosf(float a, float* s, float* c) { *s = sinf(a); *c = cosf(a);
 inline float __logf(float a) { return logf(a); }
 inline float __expf(float a) { return expf(a); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline long long __double2ll_rn(double v) { return llrint(v); }
 inline double atomicAdd(double* p, double v) {
   uint64_t old = __atomic_load_n(reinterpret_cast<uint64_t*>(p), __ATOMIC_SEQ_CST), neu;
   double d;

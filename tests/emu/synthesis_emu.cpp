@@ -87,6 +87,7 @@ extern "C" int emu_synthesis(const double* f0, int F, const double* sp, const do
                                     p_utt.data(), list_per.data(), list_aper.data(), n_per, n_aper, randn_tab.data(), twf.data(),
                                     rem.data(), c, y.data());
     });
+    wbemu::launch_grid(1, 1, 256, 0, [&]() { synth_ola_finish_kernel(y.data(), (long long)y_length); });   // integer sums -> samples
   }
   memcpy(y_out, y.data(), (size_t)y_length * sizeof(double));
   return wbemu::smem_overruns ? 4 : 0;
