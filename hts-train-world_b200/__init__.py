@@ -161,6 +161,7 @@ def lib():
         "wb200_batch_get_coded_async": (i32, [vp, vp, vp, vp]),
         "wb200_batch_decode_mgc": (i32, [vp, i32, i32, vp]),
         "wb200_batch_feature_stats": (i32, [vp, _dp]),
+        "wb200_batch_gv_stats": (i32, [vp, vp, vp]),
         "wb200_batch_compose_cmp": (i32, [vp, C.POINTER(CmpStream), i32]),
         "wb200_batch_cmp_dim": (i32, [vp]),
         "wb200_batch_get_cmp": (i32, [vp, vp]),
@@ -536,6 +537,15 @@ class Corpus:
         out = np.zeros((1 + self.mgc_dim, 3))
         _check(lib().wb200_batch_feature_stats(self._h, _ptr(out)), "feature_stats")
         return out
+
+    def gv_stats(self):
+        """Global-variance statistics (include/world_b200.h): (per-utterance variances [n_utt][mgc+1+bap],
+        partials [mgc+1+bap][3] over this batch's utterances).  Needs code()."""
+        ncol = self.mgc_dim + 1 + self.bap_dim
+        per = np.zeros((self.n_utt, ncol))
+        part = np.zeros((ncol, 3))
+        _check(lib().wb200_batch_gv_stats(self._h, per.ctypes.data, part.ctypes.data), "gv_stats")
+        return per, part
 
     def compose_cmp(self, streams=("mgc", "lf0", "bap"), windows=None):
         """The `cmp` target of data/Makefile.in:276-321 for the whole batch: every stream extended by

@@ -44,3 +44,17 @@ def allreduce_stats(local3, group=None):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         t = t.cpu()
     return merge_stats([t.numpy()])
+
+
+def merge_gv(partials):
+    """partials: iterable of [dims][3] = {count, sum, sum of squares} of the per-utterance variances
+    (wb200_batch_gv_stats, one per batch / rank) -> (mean[dims], var[dims]): the mean and the variance
+    of the variances over the corpus (stats/gv.var of data/Makefile.in:447-458)."""
+    tot = np.sum(np.asarray(list(partials), np.float64), axis=0)
+    n = np.maximum(tot[:, 0], 1.0)
+    mean = tot[:, 1] / n
+    var = tot[:, 2] / n - mean * mean
+    bad = tot[:, 0] <= 0
+    mean[bad] = np.nan
+    var[bad] = np.nan
+    return mean, var

@@ -762,6 +762,10 @@ int wb200_htk_header(int n_frames, int samp_freq, int frame_shift, int byte_per_
   memcpy(out12, &nf, 4); memcpy(out12 + 4, &shift, 4); memcpy(out12 + 8, &bytes, 2); memcpy(out12 + 10, &type, 2);
   return 0;
 }
+int wb200_batch_gv_stats(wb200_batch* h, double* per_utt, double* partials) {
+  if (!ctx()) return 1;
+  return batch_gv_stats(&h->b, per_utt, partials) ? 0 : 1;
+}
 int wb200_batch_lf0_stats(wb200_batch* h, double* out3);
 int wb200_batch_feature_stats(wb200_batch* h, double* out) {
   if (!ctx()) return 1;

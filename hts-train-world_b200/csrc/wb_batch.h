@@ -84,6 +84,7 @@ bool codec_encode_run(const double* d_rows, int n_frames, int fs, int fft_size, 
 bool codec_decode_run(const double* d_coded, int n_frames, int fs, int fft_size, int ndim, double* d_rows);
 bool batch_code_features(Batch* b, int mgc_dim, int bap_dim);
 bool batch_feature_stats(Batch* b, double* h_out);
+bool batch_gv_stats(Batch* b, double* h_per_utt, double* h_partials);
 
 // zero-phase IIR decimation of every utterance (wb_harvest.cu), used by Dio when option.speed > 1
 bool decimate_run(const Batch* b, int r, const std::vector<int>& want_len, DevBuf<double>* y,

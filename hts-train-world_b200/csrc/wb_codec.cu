@@ -239,6 +239,44 @@ feature_stats_kernel(const float* __restrict__ m, long long n_elems, int ndim, d
   }
 }
 
+
+// ---- global-variance statistics (scripts/Training.pl make_data_gv :1402-1456, data/Makefile.in:447-458) ---
+// For every utterance and every static stream the reference runs `vstat -d -o 2` over the frames of the
+// utterance: per-dimension sum and sum of squares in double, in frame order, variance = E[x^2] - mean^2
+// over the k frames it read; lf0 first loses its unvoiced frames (the "1e+10" filter of :1437).  One CTA per
+// utterance; thread c owns column c of [mgc | lf0 | bap] and walks the frames in order, i.e. the additions
+// happen in vstat's order (neighbouring threads read neighbouring floats of a row: coalesced).
+// out[u][c] = variance (NaN when the stream has no frame: vstat prints nothing, the NaN check of
+// Training.pl:1451 then drops the utterance).
+__global__ void __launch_bounds__(256)
+gv_utterance_kernel(const float* __restrict__ mgc, const float* __restrict__ lf0, const float* __restrict__ bap,
+                    int mgc_dim, int bap_dim, const int* __restrict__ f_off, const int* __restrict__ f_len,
+                    double* __restrict__ out) {
+  const int u = blockIdx.x, ncol = mgc_dim + 1 + bap_dim;
+  const int f0 = f_off[u], n = f_len[u];
+  for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
+    const float* __restrict__ base;
+    int stride;
+    bool msd = false;
+    if (c < mgc_dim) { base = mgc + (size_t)f0 * mgc_dim + c; stride = mgc_dim; }
+    else if (c == mgc_dim) { base = lf0 + f0; stride = 1; msd = true; }
+    else { base = bap + (size_t)f0 * bap_dim + (c - mgc_dim - 1); stride = bap_dim; }
+    double sum = 0.0, sq = 0.0;
+    long long k = 0;
+    for (int i = 0; i < n; ++i) {
+      const float v = base[(size_t)i * stride];
+      if (msd && v == 0.0f) continue;                 // unvoiced: lf0 = 0 here, -1e10 in the reference's files
+      const double x = v;
+      sum = add_rn(sum, x);
+      sq = add_rn(sq, mul_rn(x, x));
+      ++k;
+    }
+    double var = __longlong_as_double(0x7ff8000000000000LL);
+    if (k > 0) { const double mean = sum / k; var = add_rn(sq / k, -mul_rn(mean, mean)); }
+    out[(size_t)u * ncol + c] = var;
+  }
+}
+
 }  // namespace
 
 bool codec_encode_run(const double* d_rows, int n_frames, int fs, int fft_size, int ndim, double scale,
@@ -324,6 +362,41 @@ bool batch_feature_stats(Batch* b, double* h_out) {   // [(1 + mgc_dim)][3]: lf0
     WB_LAUNCH_CHECK();
   }
   if (!read_back(h_out, d.p, (size_t)(nd + 1) * 3 * sizeof(double))) return false;
+  return true;
+}
+
+// per-utterance variances [n_utt][mgc_dim + 1 + bap_dim] (host, doubles) and, per column, the partials
+// {count, sum, sum of squares} over the utterances of this batch of the variances ROUNDED TO FLOAT32 (the
+// reference's tmp.var1 is a float file; data/Makefile.in:451-453 runs vstat over it): the all-reduce of
+// these rows gives stats/gv.var on any number of GPUs.  Utterances whose variance is NaN are not counted.
+bool batch_gv_stats(Batch* b, double* h_per_utt, double* h_partials) {
+  Context* c = ctx();
+  if (!c) return false;
+  if (!b->mgc.p || !b->bap.p || !b->lf0.p) { set_error("gv: features have not been coded (wb200_batch_code)"); return false; }
+  const int ncol = b->mgc_dim + 1 + b->bap_dim;
+  std::vector<double> local((size_t)std::max(1, b->n_utt) * ncol);
+  if (b->n_utt > 0) {
+    DevBuf<double> d;
+    if (!d.alloc((size_t)b->n_utt * ncol)) return false;
+    gv_utterance_kernel<<<b->n_utt, 256, 0, c->stream>>>(b->mgc.p, b->lf0.p, b->bap.p, b->mgc_dim, b->bap_dim, b->f_off.p, b->f_len.p, d.p);
+    WB_LAUNCH_CHECK();
+    if (!WB_CUDA(cudaMemcpyAsync(local.data(), d.p, (size_t)b->n_utt * ncol * sizeof(double), cudaMemcpyDeviceToHost, c->stream)) ||
+        !WB_CUDA(cudaStreamSynchronize(c->stream)))
+      return false;
+  }
+  if (h_per_utt) memcpy(h_per_utt, local.data(), (size_t)b->n_utt * ncol * sizeof(double));
+  if (h_partials) {
+    for (int k = 0; k < ncol; ++k) {
+      double cnt = 0.0, sum = 0.0, sq = 0.0;
+      for (int u = 0; u < b->n_utt; ++u) {              // utterance order = the order of the reference's loop over files
+        const double v = local[(size_t)u * ncol + k];
+        if (v != v) continue;
+        const double x = static_cast<double>(static_cast<float>(v));
+        cnt += 1.0; sum += x; sq += x * x;
+      }
+      h_partials[3 * k] = cnt; h_partials[3 * k + 1] = sum; h_partials[3 * k + 2] = sq;
+    }
+  }
   return true;
 }
 

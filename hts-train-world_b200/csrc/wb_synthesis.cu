@@ -339,30 +339,75 @@ __device__ __forceinline__ PulseFrames pulse_frames(int index, int fs, double fr
 }
 __device__ __forceinline__ double safe_ap(double x) { return fmax(0.001, fmin(0.999999999999, x)); }   // common.h:111-113
 
-__global__ void synth_classify_kernel(const double* __restrict__ ap_all, const int* __restrict__ f_off,
-                                      const int* __restrict__ f_len, const int* __restrict__ p_index,
-                                      const unsigned char* __restrict__ p_vuv, const int* __restrict__ p_utt,
-                                      int total_p, SynthConst c, int* __restrict__ cnt2,
-                                      int* __restrict__ list_per, int* __restrict__ list_aper) {
+// Work lists in PULSE ORDER (count pass, scan, write pass): the two non-periodic pulses that share one
+// complex transform are always the same two, so the waveform does not depend on which thread reached an
+// atomic counter first (the partner's rounding noise leaks into a channel at the 1e-7 level).
+// blk_cnt: [2][n_blocks] -- count pass: events of each kind per CTA; write pass: exclusive offsets.
+template <bool WRITE>
+__global__ void __launch_bounds__(256)
+synth_classify_kernel(const double* __restrict__ ap_all, const int* __restrict__ f_off,
+                      const int* __restrict__ f_len, const int* __restrict__ p_index,
+                      const unsigned char* __restrict__ p_vuv, const int* __restrict__ p_utt,
+                      int total_p, SynthConst c, int* __restrict__ blk_cnt,
+                      int* __restrict__ list_per, int* __restrict__ list_aper) {
+  __shared__ int wc[2][8];
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= total_p || p_utt[p] < 0) return;
-  bool periodic = false;
-  if (p_vuv[p]) {
-    const int u = p_utt[p];
-    const int half = (1 << c.log2n) >> 1;
-    const PulseFrames fr = pulse_frames(p_index[p], c.fs, c.frame_period_s, f_len[u]);
-    const double a0 = safe_ap(ap_all[((size_t)f_off[u] + fr.fr_floor) * (half + 1)]);
-    double ar;
-    if (fr.fr_floor == fr.fr_ceil) ar = a0 * a0;
-    else {
-      const double a1 = safe_ap(ap_all[((size_t)f_off[u] + fr.fr_ceil) * (half + 1)]);
-      const double m = add_rn(mul_rn(1.0 - fr.interp, a0), mul_rn(fr.interp, a1));
-      ar = m * m;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int kind = 0;                                     // 0: unused slot, 1: periodic, 2: non-periodic
+  if (p < total_p && p_utt[p] >= 0) {
+    bool periodic = false;
+    if (p_vuv[p]) {
+      const int u = p_utt[p];
+      const int half = (1 << c.log2n) >> 1;
+      const PulseFrames fr = pulse_frames(p_index[p], c.fs, c.frame_period_s, f_len[u]);
+      const double a0 = safe_ap(ap_all[((size_t)f_off[u] + fr.fr_floor) * (half + 1)]);
+      double ar;
+      if (fr.fr_floor == fr.fr_ceil) ar = a0 * a0;
+      else {
+        const double a1 = safe_ap(ap_all[((size_t)f_off[u] + fr.fr_ceil) * (half + 1)]);
+        const double m = add_rn(mul_rn(1.0 - fr.interp, a0), mul_rn(fr.interp, a1));
+        ar = m * m;
+      }
+      periodic = !(ar > 0.999);
     }
-    periodic = !(ar > 0.999);
+    kind = periodic ? 1 : 2;
   }
-  if (periodic) list_per[atomicAdd(&cnt2[0], 1)] = p;
-  else list_aper[atomicAdd(&cnt2[1], 1)] = p;
+  const unsigned m1 = __ballot_sync(0xffffffffu, kind == 1), m2 = __ballot_sync(0xffffffffu, kind == 2);
+  if (lane == 0) { wc[0][wid] = __popc(m1); wc[1][wid] = __popc(m2); }
+  __syncthreads();
+  if (!WRITE) {
+    if (threadIdx.x < 2) {
+      int t = 0;
+      for (int w = 0; w < 8; ++w) t += wc[threadIdx.x][w];
+      blk_cnt[threadIdx.x * gridDim.x + blockIdx.x] = t;
+    }
+    return;
+  }
+  if (kind == 0) return;
+  const int k = kind - 1;
+  int pos = blk_cnt[k * gridDim.x + blockIdx.x] + __popc((k == 0 ? m1 : m2) & ((1u << lane) - 1u));
+  for (int w = 0; w < wid; ++w) pos += wc[k][w];
+  (k == 0 ? list_per : list_aper)[pos] = p;
+}
+
+// exclusive scan of the two rows of blk_cnt (one warp per row), totals -> cnt2[0..1]
+__global__ void synth_classify_scan_kernel(int* __restrict__ blk_cnt, int n_blocks, int* __restrict__ cnt2) {
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* row = blk_cnt + (size_t)k * n_blocks;
+  int carry = 0;
+  for (int i0 = 0; i0 < n_blocks; i0 += 32) {
+    const int i = i0 + lane;
+    const int v = i < n_blocks ? row[i] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (i < n_blocks) row[i] = carry + inc - v;
+    carry += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (lane == 0) cnt2[k] = carry;
 }
 
 // ---- one work item: two minimum-phase responses through four complex FFTs -----------------
@@ -733,12 +778,20 @@ bool synthesis_run(Batch* b, const int* y_len) {
   for (int i = 0; i < N / 2; ++i) { rem[i] /= dc_component; rem[N - i - 1] = rem[i]; }
   WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_rem.p, rem.data(), N * sizeof(double), cudaMemcpyHostToDevice, st), false);
   // classify the pulses into periodic / non-periodic work lists
-  DevBuf<int> d_cnt2, list_per, list_aper;
-  if (!d_cnt2.alloc(2) || !list_per.alloc(total_p) || !list_aper.alloc(total_p)) return false;
+  DevBuf<int> d_cnt2, list_per, list_aper, d_blk;
+  const int n_cblocks = (int)((total_p + 255) / 256);
+  if (!d_cnt2.alloc(2) || !list_per.alloc(total_p) || !list_aper.alloc(total_p) || !d_blk.alloc(2 * (size_t)std::max(1, n_cblocks))) return false;
   WB_CUDA_OR_RETURN(cudaMemsetAsync(d_cnt2.p, 0, 2 * sizeof(int), st), false);
-  synth_classify_kernel<<<(unsigned)((total_p + 255) / 256), 256, 0, st>>>(b->ap.p, b->f_off.p, b->f_len.p, p_index.p, p_vuv.p,
-                                                                          p_utt.p, (int)total_p, c, d_cnt2.p, list_per.p, list_aper.p);
-  WB_LAUNCH_CHECK();
+  if (n_cblocks > 0) {
+    synth_classify_kernel<false><<<n_cblocks, 256, 0, st>>>(b->ap.p, b->f_off.p, b->f_len.p, p_index.p, p_vuv.p, p_utt.p, (int)total_p, c,
+                                                          d_blk.p, list_per.p, list_aper.p);
+    WB_LAUNCH_CHECK();
+    synth_classify_scan_kernel<<<1, 64, 0, st>>>(d_blk.p, n_cblocks, d_cnt2.p);
+    WB_LAUNCH_CHECK();
+    synth_classify_kernel<true><<<n_cblocks, 256, 0, st>>>(b->ap.p, b->f_off.p, b->f_len.p, p_index.p, p_vuv.p, p_utt.p, (int)total_p, c,
+                                                         d_blk.p, list_per.p, list_aper.p);
+    WB_LAUNCH_CHECK();
+  }
   int h_cnt2[2] = {0, 0};
   if (!read_back(h_cnt2, d_cnt2.p, 2 * sizeof(int))) return false;
   if (!read_back(h_cnt.data(), d_cnt.p, n_utt * sizeof(int))) return false;

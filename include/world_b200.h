@@ -127,6 +127,14 @@ WORLD_API int wb200_batch_decode_mgc(wb200_batch *b, int fft_size, int mgc_dim, 
  * of voiced lf0 (row 0) and of every mgc dimension over all frames (rows 1..mgc_dim); the NCCL
  * all-reduce of these rows gives the corpus mean / variance */
 WORLD_API int wb200_batch_feature_stats(wb200_batch *b, double *out);
+/* global-variance statistics (scripts/Training.pl make_data_gv :1402-1456; data/Makefile.in:447-458): for every
+ * utterance the per-dimension variance over its frames of the static streams [mgc | lf0 (voiced frames) | bap],
+ * computed as SPTK `vstat -d -o 2` does (double sums in frame order, E[x^2] - mean^2); NaN where a stream has
+ * no frame.  per_utt[n_utt][mgc_dim + 1 + bap_dim] (may be NULL); partials[mgc_dim + 1 + bap_dim][3] = {count,
+ * sum, sum of squares} over this batch's utterances of those variances rounded to float32 (the reference's
+ * tmp.var1 is a float file) -- summed over batches / GPUs they give the mean and variance of the variances
+ * (stats/gv.var).  Needs wb200_batch_code. */
+WORLD_API int wb200_batch_gv_stats(wb200_batch *b, double *per_utt, double *partials);
 /* ---- training observation vectors (data/Makefile.in:276-321, the `cmp` target) ----------------
  * Every stream (mgc, lf0, bap, and any stream computed on the host such as the two-dimensional
  * lf0 and vib of data/scripts/Extract.py) is extended by its delta windows exactly as

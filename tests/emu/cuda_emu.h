@@ -49,6 +49,7 @@ inline T exchange(T v, SRC src_of_lane) {
 template <typename T> inline T shfl_xor(T v, int o) { return exchange(v, [o](int l) { return l ^ o; }); }
 template <typename T> inline T shfl_up(T v, int o) { return exchange(v, [o](int l) { return l - o; }); }
 template <typename T> inline T shfl_down(T v, int o) { return exchange(v, [o](int l) { return l + o; }); }
+template <typename T> inline T shfl_idx(T v, int src) { return exchange(v, [src](int) { return src; }); }
 template <typename T, typename OP> inline T reduce(T v, OP op) {
   for (int o = 16; o > 0; o >>= 1) v = op(v, shfl_xor(v, o));
   return v;
@@ -119,6 +120,7 @@ inline void launch_grid(int gx, int gy, int threads, size_t smem_bytes, F body) 
 #define __shfl_xor_sync(m, v, o) ::wbemu::shfl_xor((v), (o))
 #define __shfl_up_sync(m, v, o) ::wbemu::shfl_up((v), (o))
 #define __shfl_down_sync(m, v, o) ::wbemu::shfl_down((v), (o))
+#define __shfl_sync(m, v, src) ::wbemu::shfl_idx((v), (src))
 #define __reduce_add_sync(m, v) ::wbemu::reduce((v), [](auto a, auto b) { return a + b; })
 #define __reduce_max_sync(m, v) ::wbemu::reduce((v), [](auto a, auto b) { return a > b ? a : b; })
 #define __ldg(p) (*(p))

@@ -70,9 +70,17 @@ extern "C" int emu_synthesis(const double* f0, int F, const double* sp, const do
   }
   for (int i = 0; i < N / 2; ++i) { rem[i] /= dc_component; rem[N - i - 1] = rem[i]; }
   int cnt2[2] = {0, 0};
-  wbemu::launch_grid((total_p + 255) / 256, 1, 256, 0, [&]() {
-    synth_classify_kernel(ap, &f_off, &f_len, p_index.data(), p_vuv.data(), p_utt.data(), total_p, c, cnt2, list_per.data(), list_aper.data());
-  });
+  {
+    const int ncb = (total_p + 255) / 256;                         // count pass, scan, write pass: lists in pulse order
+    std::vector<int> blk(2 * (size_t)std::max(1, ncb), 0);
+    wbemu::launch_grid(ncb, 1, 256, 0, [&]() {
+      synth_classify_kernel<false>(ap, &f_off, &f_len, p_index.data(), p_vuv.data(), p_utt.data(), total_p, c, blk.data(), list_per.data(), list_aper.data());
+    });
+    wbemu::launch_grid(1, 1, 64, 0, [&]() { synth_classify_scan_kernel(blk.data(), ncb, cnt2); });
+    wbemu::launch_grid(ncb, 1, 256, 0, [&]() {
+      synth_classify_kernel<true>(ap, &f_off, &f_len, p_index.data(), p_vuv.data(), p_utt.data(), total_p, c, blk.data(), list_per.data(), list_aper.data());
+    });
+  }
   const int n_per = cnt2[0], n_aper = cnt2[1];
   const int n_items = n_per + (n_aper + 1) / 2;
   if (n_items > 0) {
