@@ -215,6 +215,7 @@ int option(const char* name) {
       {"lovetrain_fp32", "WB_D4C_LT32", 1, -1},        // LoveTrain's transform in FP32
       {"dio_fused", "WB_DIO_FUSED", 1, -1},            // Dio: zero crossings inside the filter kernel (0: band signals through HBM)
       {"harvest_fused", "WB_HARVEST_FUSED", 1, -1},
+      {"harvest_fix_warp", "WB_HARVEST_FIX_WARP", 1, -1},     // Harvest contour logic spread over a warp (0: lane 0 walks)
       {"harvest_refine_thread", "WB_HARVEST_REFINE_THREAD", 1, -1},   // Harvest refinement: one thread per candidate (0: one warp)    // Harvest: the same for its 152 band-pass channels
       {"stonemask_dft", "WB_STONEMASK_DFT", 1, -1},    // StoneMask: direct evaluation of the <= 8 bins (0: packed FP32 FFT)
   };

@@ -176,8 +176,8 @@ __device__ double dio_select_best(double current_f0, double past_f0, const doubl
 __global__ void __launch_bounds__(256)
 dio_fix_kernel(const double* __restrict__ cand, const double* __restrict__ score,
                const int* __restrict__ f_off, const int* __restrict__ f_len, DioConst c, int utt0,
-               int total_frames, double* __restrict__ tmp1, double* __restrict__ tmp2,
-               int* __restrict__ pos_idx, int* __restrict__ neg_idx, double* __restrict__ f0_out) {
+               int total_frames, double* tmp1, double* tmp2,          // exchanged between threads: not __restrict__
+               int* __restrict__ pos_idx, int* __restrict__ neg_idx, double* f0_out) {
   const int u = utt0 + blockIdx.x;
   const int off = f_off[u], F = f_len[u];
   const int tid = threadIdx.x, T = blockDim.x;

@@ -579,12 +579,12 @@ __device__ double harvest_select_best(double ref, const double* __restrict__ row
 __global__ void harvest_fix_a_kernel(const double* __restrict__ cand, const double* __restrict__ score,
                                      const int* __restrict__ g_off, const int* __restrict__ g_len,
                                      const int* __restrict__ nc_utt, const long long* __restrict__ cand_off,
-                                     double* __restrict__ tmp1, double* __restrict__ tmp2, int* __restrict__ bl_all,
+                                     double* tmp1, double* tmp2, int* bl_all,      // exchanged between threads: not __restrict__
                                      int* __restrict__ n_sections) {
   const int u = blockIdx.x;
   const int n = g_len[u], off = g_off[u], slots = nc_utt[u] * kOverlap;
-  double* __restrict__ basef = tmp1 + off;
-  double* __restrict__ step1 = tmp2 + off;
+  double* basef = tmp1 + off;
+  double* step1 = tmp2 + off;
   const double* __restrict__ cu = cand + cand_off[u];
   const double* __restrict__ su = score + cand_off[u];
   for (int i = threadIdx.x; i < n; i += blockDim.x) {              // SearchF0Base (:693-706)
@@ -647,14 +647,18 @@ __device__ __forceinline__ double harvest_select_best_warp(double ref, const dou
 __global__ void harvest_fix_b_kernel(const double* __restrict__ cand, const double* __restrict__ score,
                                      const int* __restrict__ g_off, const int* __restrict__ g_len,
                                      const int* __restrict__ nc_utt, const long long* __restrict__ cand_off,
-                                     double* __restrict__ tmp1, double* __restrict__ tmp2, int* __restrict__ bl_all,
-                                     const long long* __restrict__ mc_off, double* __restrict__ mc_all,
-                                     int* __restrict__ chan_all, int* __restrict__ order_all) {
+                                     double* tmp1, double* tmp2, int* bl_all,
+                                     const long long* __restrict__ mc_off, double* mc_all,
+                                     int* chan_all, int* order_all, int dbg_mode = 3, int stop_after = 0) {
+  // NOTE: the arrays the lanes exchange data through (tmp1 / tmp2 / bl / mc / chan / order) must NOT be
+  // __restrict__: that qualifier promises the compiler that nobody else -- which includes the other
+  // lanes -- writes the object, and it then keeps values in registers across __syncwarp() (measured: the
+  // merged contour differed from the one-lane version on real speech; the state after Extend did not).
   const int u = blockIdx.x;
   const int lane = threadIdx.x;
   const int n = g_len[u], off = g_off[u], slots = nc_utt[u] * kOverlap;
-  const double* __restrict__ step2 = tmp1 + off;
-  double* __restrict__ step3 = tmp2 + off;
+  const double* step2 = tmp1 + off;
+  double* step3 = tmp2 + off;
   const double* __restrict__ cu = cand + cand_off[u];
   const double* __restrict__ su = score + cand_off[u];
   int* bl = bl_all + 2 * off;
@@ -685,7 +689,13 @@ __global__ void harvest_fix_b_kernel(const double* __restrict__ cand, const doub
       __syncwarp();                                                 // bl / ext read by every lane before lane 0 rewrites them
       for (int i = 0; i <= distance; ++i) {
         const int idx = origin + shift * i + shift;
-        const double v = harvest_select_best_warp(tmp_f0, cu + (size_t)idx * slots, slots, 0.18, lane);
+        double v;
+        if (dbg_mode & 1) v = harvest_select_best_warp(tmp_f0, cu + (size_t)idx * slots, slots, 0.18, lane);
+        else {
+          v = 0.0;
+          if (lane == 0) v = harvest_select_best(tmp_f0, cu + (size_t)idx * slots, slots, 0.18);
+          v = __shfl_sync(0xffffffffu, v, 0);
+        }
         if (lane == 0) ext[idx] = v;
         if (v == 0.0) ++count;
         else { tmp_f0 = v; count = 0; shifted_origin = idx; }
@@ -695,6 +705,7 @@ __global__ void harvest_fix_b_kernel(const double* __restrict__ cand, const doub
       __syncwarp();
     }
   }
+  if (stop_after == 1) return;
   if (lane == 0) {
     // ExtendSub (:845-862); mean_f0 is deliberately not reset between sections (as in the reference)
     int nchn = 0;
@@ -722,6 +733,7 @@ __global__ void harvest_fix_b_kernel(const double* __restrict__ cand, const doub
     nchn_s = nchn;
   }
   __syncwarp();
+  if (stop_after == 2) return;
   const int nchn = nchn_s;
   if (nchn != 0) {
     // MergeF0 (:944-971)
@@ -744,7 +756,7 @@ __global__ void harvest_fix_b_kernel(const double* __restrict__ cand, const doub
         for (int j = st2; j <= ed1; ++j) {
           double s1 = 0.0, s2 = 0.0;                                // SearchScore (:906-912): a maximum, any order
           const double v1 = step3[j], v2 = f2[j];
-          for (int q = lane; q < slots; q += 32) {
+          for (int q = (dbg_mode & 2) ? lane : 0; q < slots; q += (dbg_mode & 2) ? 32 : 1) {
             const double cq = cu[(size_t)j * slots + q], sq = su[(size_t)j * slots + q];
             if (v1 == cq && s1 < sq) s1 = sq;
             if (v2 == cq && s2 < sq) s2 = sq;
@@ -771,6 +783,128 @@ __global__ void harvest_fix_b_kernel(const double* __restrict__ cand, const doub
   for (int i = lane; i < n; i += 32) step4[i] = step3[i];
   __syncwarp();
   if (lane == 0) {
+    const int nb4 = harvest_boundaries(step3, n, bl);
+    for (int i = 0; i < nb4 / 2 - 1; ++i) {
+      const int distance = bl[(i + 1) * 2] - bl[i * 2 + 1] - 1;
+      if (distance >= 9) continue;
+      const double t0 = step3[bl[i * 2 + 1]] + 1, t1 = step3[bl[(i + 1) * 2]] - 1;
+      const double coefficient = (t1 - t0) / (distance + 1.0);
+      int count = 1;
+      for (int j = bl[i * 2 + 1] + 1; j <= bl[(i + 1) * 2] - 1; ++j) step4[j] = t0 + coefficient * count++;
+    }
+  }
+}
+
+// phase B, reference implementation of the contour logic: lane 0 walks everything (WB_HARVEST_FIX_WARP=0).
+// mc: [sections][n] scratch of this utterance; chan: pointer permutation for Swap (:828-843).
+__global__ void harvest_fix_b_serial_kernel(const double* __restrict__ cand, const double* __restrict__ score,
+                                     const int* __restrict__ g_off, const int* __restrict__ g_len,
+                                     const int* __restrict__ nc_utt, const long long* __restrict__ cand_off,
+                                     double* __restrict__ tmp1, double* __restrict__ tmp2, int* __restrict__ bl_all,
+                                     const long long* __restrict__ mc_off, double* __restrict__ mc_all,
+                                     int* __restrict__ chan_all, int* __restrict__ order_all, int stop_after = 0) {
+  const int u = blockIdx.x;
+  const int n = g_len[u], off = g_off[u], slots = nc_utt[u] * kOverlap;
+  const double* __restrict__ step2 = tmp1 + off;
+  double* __restrict__ step3 = tmp2 + off;
+  const double* __restrict__ cu = cand + cand_off[u];
+  const double* __restrict__ su = score + cand_off[u];
+  int* bl = bl_all + 2 * off;
+  double* mc = mc_all + mc_off[u];
+  int* chan = chan_all + off;
+  int* order = order_all + off;
+  __shared__ int nb_s;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) step3[i] = step2[i];
+  if (threadIdx.x == 0) nb_s = harvest_boundaries(step2, n, bl);
+  __syncthreads();
+  const int nsec = nb_s / 2;
+  // GetMultiChannelF0 (:769-781)
+  for (int s = 0; s < nsec; ++s)
+    for (int j = threadIdx.x; j < n; j += blockDim.x)
+      mc[(size_t)s * n + j] = (j >= bl[2 * s] && j <= bl[2 * s + 1]) ? step2[j] : 0.0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nsec; ++s) chan[s] = s;
+    // Extend (:867-883) with ExtendF0 (:794-823), in place on mc and bl
+    for (int s = 0; s < nsec; ++s) {
+      double* ext = mc + (size_t)s * n;
+      for (int dir = 0; dir < 2; ++dir) {
+        const int shift = dir == 0 ? 1 : -1;
+        const int origin = dir == 0 ? bl[2 * s + 1] : bl[2 * s];
+        const int last_point = dir == 0 ? min(n - 2, bl[2 * s + 1] + 100) : max(1, bl[2 * s] - 100);
+        double tmp_f0 = ext[origin];
+        int shifted_origin = origin, count = 0;
+        const int distance = abs(last_point - origin);
+        for (int i = 0; i <= distance; ++i) {
+          const int idx = origin + shift * i + shift;
+          const double v = harvest_select_best(tmp_f0, cu + (size_t)idx * slots, slots, 0.18);
+          ext[idx] = v;
+          if (v == 0.0) ++count;
+          else { tmp_f0 = v; count = 0; shifted_origin = idx; }
+          if (count == 4) break;
+        }
+        if (dir == 0) bl[2 * s + 1] = shifted_origin; else bl[2 * s] = shifted_origin;
+      }
+    }
+    if (stop_after == 1) return;
+    // ExtendSub (:845-862); mean_f0 is deliberately not reset between sections (as in the reference)
+    int nchn = 0;
+    double mean_f0 = 0.0;
+    for (int s = 0; s < nsec; ++s) {
+      const int st = bl[2 * s], ed = bl[2 * s + 1];
+      const double* ext = mc + (size_t)chan[s] * n;
+      for (int j = st; j < ed; ++j) mean_f0 += ext[j];
+      mean_f0 /= ed - st;
+      if (2200.0 / mean_f0 < ed - st) {
+        const int a = nchn++, b2 = s;
+        int t = chan[a]; chan[a] = chan[b2]; chan[b2] = t;
+        t = bl[2 * a]; bl[2 * a] = bl[2 * b2]; bl[2 * b2] = t;
+        t = bl[2 * a + 1]; bl[2 * a + 1] = bl[2 * b2 + 1]; bl[2 * b2 + 1] = t;
+      }
+    }
+    if (stop_after == 2) return;
+    if (nchn != 0) {
+      // MergeF0 (:944-971)
+      for (int i = 0; i < nchn; ++i) order[i] = i;                  // MakeSortedOrder (:888-901)
+      for (int i = 1; i < nchn; ++i)
+        for (int j = i - 1; j >= 0; --j) {
+          if (bl[order[j] * 2] > bl[order[i] * 2]) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
+          else break;
+        }
+      const double* ch0 = mc + (size_t)chan[0] * n;
+      for (int i = 0; i < n; ++i) step3[i] = ch0[i];
+      for (int i = 1; i < nchn; ++i) {
+        const int oi = order[i];
+        const double* f2 = mc + (size_t)chan[oi] * n;
+        const int st2 = bl[oi * 2], ed2 = bl[oi * 2 + 1];
+        if (st2 - bl[1] > 0) {
+          for (int j = st2; j <= ed2; ++j) step3[j] = f2[j];
+          bl[0] = st2;
+          bl[1] = ed2;
+        } else {
+          const int st1 = bl[0], ed1 = bl[1];                       // MergeF0Sub (:917-939)
+          if (st1 <= st2 && ed1 >= ed2) { bl[1] = ed1; continue; }
+          double score1 = 0.0, score2 = 0.0;
+          for (int j = st2; j <= ed1; ++j) {
+            double s1 = 0.0, s2 = 0.0;                              // SearchScore (:906-912)
+            const double v1 = step3[j], v2 = f2[j];
+            for (int q = 0; q < slots; ++q) {
+              const double cq = cu[(size_t)j * slots + q], sq = su[(size_t)j * slots + q];
+              if (v1 == cq && s1 < sq) s1 = sq;
+              if (v2 == cq && s2 < sq) s2 = sq;
+            }
+            score1 += s1;
+            score2 += s2;
+          }
+          if (score1 > score2) { for (int j = ed1; j <= ed2; ++j) step3[j] = f2[j]; }
+          else { for (int j = st2; j <= ed2; ++j) step3[j] = f2[j]; }
+          bl[1] = ed2;
+        }
+      }
+    }
+    // FixStep4 (:1009-1032), threshold 9; result back into tmp1
+    double* step4 = tmp1 + off;
+    for (int i = 0; i < n; ++i) step4[i] = step3[i];
     const int nb4 = harvest_boundaries(step3, n, bl);
     for (int i = 0; i < nb4 / 2 - 1; ++i) {
       const int distance = bl[(i + 1) * 2] - bl[i * 2 + 1] - 1;
@@ -904,6 +1038,7 @@ bool build_harvest_bank(double actual_fs, double f0_floor, double f0_ceil, Harve
 // the filter table above for the host-side decimate() of wb_compat.cu
 bool decimate_filter_coefficients(int r, double* a, double* b) { return decimate_coefficients(r, a, b); }
 
+#ifndef WB_HOST_EMU      // the launchers; tests/emu has its own
 // decimate() of W/src/matlabfunctions.cpp:184-210 for every utterance of the batch (no edge
 // extension: lag = 0), as Dio uses it when option.speed > 1 (W/src/dio.cpp:69-71).  out_len[u] =
 // min(want_len[u], number of values the reference's loop writes); the caller treats the rest as 0.
@@ -1196,8 +1331,56 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
     if (!d_mcoff.alloc(n_utt) || !d_mc.alloc(mtot + 1) || !d_chan.alloc(gtot) || !d_order.alloc(gtot)) return false;
     if (!up(d_mcoff.p, h_mcoff.data(), n_utt * sizeof(long long))) return false;
     KernelTimer kt("harvest_fix_kernel");
-    harvest_fix_b_kernel<<<n_utt, 32, 0, st>>>(d_cand2.p, d_score2.p, d_goff.p, d_glen.p, d_nc.p, d_coff.p, d_tmp1.p, d_tmp2.p, d_bl.p,
-                                              d_mcoff.p, d_mc.p, d_chan.p, d_order.p);
+    if (getenv("WB_HARVEST_FIX_CHECK")) {
+      // debugging aid: both versions of the contour logic on copies of the same inputs, differences reported
+      DevBuf<double> t1b, t2b, mcb;
+      DevBuf<int> blb, chb, orb;
+      if (!t1b.alloc(gtot) || !t2b.alloc(gtot) || !mcb.alloc(mtot + 1) || !blb.alloc(d_bl.n) || !chb.alloc(gtot) || !orb.alloc(gtot)) return false;
+      cudaMemcpyAsync(t1b.p, d_tmp1.p, gtot * sizeof(double), cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(t2b.p, d_tmp2.p, gtot * sizeof(double), cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(blb.p, d_bl.p, d_bl.n * sizeof(int), cudaMemcpyDeviceToDevice, st);
+      const int stop = getenv("WB_HARVEST_FIX_STOP") ? atoi(getenv("WB_HARVEST_FIX_STOP")) : 0;
+      harvest_fix_b_serial_kernel<<<n_utt, 32, 0, st>>>(d_cand2.p, d_score2.p, d_goff.p, d_glen.p, d_nc.p, d_coff.p, t1b.p, t2b.p, blb.p,
+                                                       d_mcoff.p, mcb.p, chb.p, orb.p, stop);
+      harvest_fix_b_kernel<<<n_utt, 32, 0, st>>>(d_cand2.p, d_score2.p, d_goff.p, d_glen.p, d_nc.p, d_coff.p, d_tmp1.p, d_tmp2.p, d_bl.p,
+                                                d_mcoff.p, d_mc.p, d_chan.p, d_order.p, atoi(getenv("WB_HARVEST_FIX_CHECK")), stop);
+      if (stop) {
+        std::vector<double> ma(mtot + 1), mb(mtot + 1);
+        std::vector<int> ba(d_bl.n), bb(d_bl.n), ca(gtot), cb(gtot);
+        cudaMemcpyAsync(ma.data(), mcb.p, mtot * sizeof(double), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(mb.data(), d_mc.p, mtot * sizeof(double), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(ba.data(), blb.p, d_bl.n * sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(bb.data(), d_bl.p, d_bl.n * sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(ca.data(), chb.p, gtot * sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(cb.data(), d_chan.p, gtot * sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        long long dm = 0, db = 0, dc = 0;
+        const int nsec0 = h_nsec[0], n0 = h_glen[0];
+        for (long long i = 0; i < (long long)nsec0 * n0; ++i)
+          if (memcmp(&ma[i], &mb[i], 8) != 0 && dm++ < 6) fprintf(stderr, "[fix check] mc section %lld frame %lld: serial %.9g warp %.9g\n", i / n0, i % n0, ma[i], mb[i]);
+        for (int i = 0; i < 2 * nsec0; ++i) if (ba[i] != bb[i] && db++ < 6) fprintf(stderr, "[fix check] bl[%d]: serial %d warp %d\n", i, ba[i], bb[i]);
+        for (int i = 0; i < nsec0; ++i) if (ca[i] != cb[i] && dc++ < 6) fprintf(stderr, "[fix check] chan[%d]: serial %d warp %d\n", i, ca[i], cb[i]);
+        fprintf(stderr, "[fix check] stop %d, utterance 0: %d sections, %d frames: mc differs at %lld, bl at %lld, chan at %lld\n", stop, nsec0, n0, dm, db, dc);
+      }
+      std::vector<double> ha(gtot), hb2(gtot), h3a(gtot), h3b(gtot);
+      cudaMemcpyAsync(ha.data(), t1b.p, gtot * sizeof(double), cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(hb2.data(), d_tmp1.p, gtot * sizeof(double), cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(h3a.data(), t2b.p, gtot * sizeof(double), cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(h3b.data(), d_tmp2.p, gtot * sizeof(double), cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      long long nd4 = 0, nd3 = 0;
+      for (long long i = 0; i < gtot; ++i) {
+        if (memcmp(&h3a[i], &h3b[i], 8) != 0 && nd3++ < 5) fprintf(stderr, "[fix check] step3 frame %lld: serial %.9g warp %.9g\n", i, h3a[i], h3b[i]);
+        if (memcmp(&ha[i], &hb2[i], 8) != 0 && nd4++ < 5) fprintf(stderr, "[fix check] step4 frame %lld: serial %.9g warp %.9g\n", i, ha[i], hb2[i]);
+      }
+      fprintf(stderr, "[fix check] %lld frames: step3 differs at %lld, step4 at %lld\n", gtot, nd3, nd4);
+    } else if (option("harvest_fix_warp")) {
+      harvest_fix_b_kernel<<<n_utt, 32, 0, st>>>(d_cand2.p, d_score2.p, d_goff.p, d_glen.p, d_nc.p, d_coff.p, d_tmp1.p, d_tmp2.p, d_bl.p,
+                                                d_mcoff.p, d_mc.p, d_chan.p, d_order.p);
+    } else {
+      harvest_fix_b_serial_kernel<<<n_utt, 32, 0, st>>>(d_cand2.p, d_score2.p, d_goff.p, d_glen.p, d_nc.p, d_coff.p, d_tmp1.p, d_tmp2.p, d_bl.p,
+                                                       d_mcoff.p, d_mc.p, d_chan.p, d_order.p);
+    }
     WB_LAUNCH_CHECK(); kt.stop();
     WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
   }
@@ -1237,5 +1420,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
   return true;
 }
+
+#endif  // WB_HOST_EMU
 
 }  // namespace wb
