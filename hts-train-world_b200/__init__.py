@@ -127,6 +127,7 @@ def lib():
         "wb200_kernel_time": (i32, [C.c_char_p, _dp, C.POINTER(i64)]),
         "wb200_measure_fma_peak": (f64, [i32]),
         "wb200_option": (i32, [C.c_char_p]),
+        "wb200_trim": (i32, []),
         "wb200_batch_create": (vp, [i32, f64, i32, _ip]),
         "wb200_batch_destroy": (None, [vp]),
         "wb200_batch_total_frames": (i32, [vp]),
@@ -154,6 +155,7 @@ def lib():
         "wb200_batch_get_y": (i32, [vp, vp]),
         "wb200_batch_get_y_pcm16": (i32, [vp, vp]),
         "wb200_batch_get_utterance": (i32, [vp, i32, vp, vp, vp, vp, vp]),
+        "wb200_batch_wait_downloads": (i32, [vp]),
         "wb200_batch_device_ptr": (vp, [vp, C.c_char_p]),
         "wb200_batch_lf0_stats": (i32, [vp, _dp]),
         "wb200_batch_code": (i32, [vp, i32, i32]),
@@ -165,6 +167,7 @@ def lib():
         "wb200_batch_compose_cmp": (i32, [vp, C.POINTER(CmpStream), i32]),
         "wb200_batch_cmp_dim": (i32, [vp]),
         "wb200_batch_get_cmp": (i32, [vp, vp]),
+        "wb200_batch_get_cmp_async": (i32, [vp, vp]),
         "wb200_batch_cmp_stats": (i32, [vp, _dp]),
         "wb200_htk_header": (i32, [i32, i32, i32, i32, i32, C.POINTER(C.c_ubyte)]),
         "GetNumberOfAperiodicities": (i32, [i32]),
@@ -233,6 +236,11 @@ def build_info():
 
 def fma_peak_tflops(fp64=True):
     return float(lib().wb200_measure_fma_peak(int(bool(fp64))))
+
+
+def trim():
+    """Hand the library's cached scratch memory back to the driver (include/world_b200.h)."""
+    _check(lib().wb200_trim(), "trim")
 
 
 def sync():
@@ -393,6 +401,10 @@ class Corpus:
         _check(lib().wb200_batch_get_coded_async(self._h, *(a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
                                                             for a in (lf0, mgc, bap))), "get_coded_async")
 
+    def wait_downloads(self):
+        """Block until this batch's asynchronous result copies (coded_async, y_pcm16_async) have landed."""
+        _check(lib().wb200_batch_wait_downloads(self._h), "wait_downloads")
+
     def set_pcm16_device(self, dev_tensor):
         _check(lib().wb200_batch_set_pcm16_device(self._h, dev_tensor.data_ptr()), "set_pcm16_device")
 
@@ -547,7 +559,7 @@ class Corpus:
         _check(lib().wb200_batch_gv_stats(self._h, per.ctypes.data, part.ctypes.data), "gv_stats")
         return per, part
 
-    def compose_cmp(self, streams=("mgc", "lf0", "bap"), windows=None):
+    def compose_cmp(self, streams=("mgc", "lf0", "bap"), windows=None, fetch=True):
         """The `cmp` target of data/Makefile.in:276-321 for the whole batch: every stream extended by
         its delta windows (data/scripts/window.pl) and merged side by side.  `streams`: names of the
         batch's own coded features ("mgc", "lf0", "bap") or (name, array[total_frames, dim]) pairs
@@ -577,9 +589,16 @@ class Corpus:
                     arr[i].win_coef[w][k] = float(v)
         _check(lib().wb200_batch_compose_cmp(self._h, arr, n), "compose_cmp")
         self.cmp_dim = int(lib().wb200_batch_cmp_dim(self._h))
+        if not fetch:                       # the caller takes the matrix with cmp_async()
+            return None
         out = np.zeros((self.total_frames, self.cmp_dim), np.float32)
         _check(lib().wb200_batch_get_cmp(self._h, out.ctypes.data), "get_cmp")
         return out
+
+    def cmp_async(self, out):
+        """Queue the copy of the cmp matrix into the pinned [total_frames, cmp_dim] float32 buffer `out`."""
+        ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+        _check(lib().wb200_batch_get_cmp_async(self._h, ptr), "get_cmp_async")
 
     def cmp_stats(self):
         """[cmp_dim, 3] = {count, sum, sum of squares} of every cmp column (per-GPU partials)."""

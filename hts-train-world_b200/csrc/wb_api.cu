@@ -173,6 +173,7 @@ int GetSamplesForDIO(int fs, int x_length, double frame_period) {
 }
 void Dio(const double* x, int x_length, int fs, const DioOption* option,
          double* temporal_positions, double* f0) {
+  ApiGuard api_guard;
   const int n = samples_for_dio(fs, x_length, option->frame_period);
   for (int i = 0; i < n; ++i) temporal_positions[i] = i * option->frame_period / 1000.0;
   // W/src/dio.cpp:264-266: FixF0Contour returns without writing f0 for very short inputs
@@ -192,6 +193,7 @@ void Dio(const double* x, int x_length, int fs, const DioOption* option,
 
 void StoneMask(const double* x, int x_length, int fs, const double* temporal_positions,
                const double* f0, int f0_length, double* refined_f0) {
+  ApiGuard api_guard;
   if (f0_length <= 0) return;
   Batch b;
   bool ok = ctx() && single_utt_batch(&b, x, x_length, fs, 5.0, f0_length) &&
@@ -222,6 +224,7 @@ static void scatter_rows(const std::vector<double>& flat, int rows, int cols, do
 void CheapTrick(const double* x, int x_length, int fs, const double* temporal_positions,
                 const double* f0, int f0_length, const CheapTrickOption* option,
                 double** spectrogram) {
+  ApiGuard api_guard;
   if (f0_length <= 0) return;
   const int cols = option->fft_size / 2 + 1;
   Batch b;
@@ -244,6 +247,7 @@ void InitializeD4COption(D4COption* option) { option->threshold = kThreshold; }
 void D4C(const double* x, int x_length, int fs, const double* temporal_positions,
          const double* f0, int f0_length, int fft_size, const D4COption* option,
          double** aperiodicity) {
+  ApiGuard api_guard;
   if (f0_length <= 0) return;
   const int cols = fft_size / 2 + 1;
   Batch b;
@@ -264,6 +268,7 @@ void D4C(const double* x, int x_length, int fs, const double* temporal_positions
 void Synthesis(const double* f0, int f0_length, const double* const* spectrogram,
                const double* const* aperiodicity, int fft_size, double frame_period, int fs,
                int y_length, double* y) {
+  ApiGuard api_guard;
   if (y_length <= 0) return;
   const int cols = fft_size / 2 + 1;
   Batch b;
@@ -298,6 +303,7 @@ int GetSamplesForHarvest(int fs, int x_length, double frame_period) {
 }
 void Harvest(const double* x, int x_length, int fs, const HarvestOption* option,
              double* temporal_positions, double* f0) {
+  ApiGuard api_guard;
   const int n = GetSamplesForHarvest(fs, x_length, option->frame_period);
   for (int i = 0; i < n; ++i) temporal_positions[i] = i * option->frame_period / 1000.0;
   Batch b;
@@ -334,10 +340,12 @@ static void codec_host(const double* const* in, int f0_length, int fs, int fft_s
 }
 void CodeSpectralEnvelope(const double* const* spectrogram, int f0_length, int fs, int fft_size,
                           int number_of_dimensions, double** coded_spectral_envelope) {
+  ApiGuard api_guard;
   codec_host(spectrogram, f0_length, fs, fft_size, number_of_dimensions, true, coded_spectral_envelope);
 }
 void DecodeSpectralEnvelope(const double* const* coded_spectral_envelope, int f0_length, int fs, int fft_size,
                             int number_of_dimensions, double** spectrogram) {
+  ApiGuard api_guard;
   codec_host(coded_spectral_envelope, f0_length, fs, fft_size, number_of_dimensions, false, spectrogram);
 }
 
@@ -346,6 +354,7 @@ void DecodeSpectralEnvelope(const double* const* coded_spectral_envelope, int f0
 // =============================================================================================
 const char* wb200_last_error(void) { return last_error(); }
 int wb200_init(int device) {
+  ApiGuard api_guard;
   if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", device); return 1; }
   return ctx() ? 0 : 1;
 }
@@ -355,6 +364,7 @@ void wb200_stage_times(float* o) {
   o[3] = g_times.d4c; o[4] = g_times.synthesis; o[5] = g_times.harvest;
 }
 int wb200_set_stream(void* stream) {
+  ApiGuard api_guard;
   if (!ctx()) return 1;
   set_stream(reinterpret_cast<cudaStream_t>(stream));
   return 0;
@@ -364,9 +374,12 @@ void wb200_kernel_times_reset(void) { kernel_times_reset(); }
 int wb200_kernel_time(const char* name, double* ms_total, long long* launches) {
   return kernel_time_query(name, ms_total, launches) ? 0 : 1;
 }
-double wb200_measure_fma_peak(int fp64) { return measure_fma_peak(fp64 != 0); }
+double wb200_measure_fma_peak(int fp64) {
+  ApiGuard api_guard; return measure_fma_peak(fp64 != 0); }
 int wb200_option(const char* name) { return name ? option(name) : 0; }
+int wb200_trim(void) { return trim_pool() ? 0 : 1; }
 int wb200_sync(void) {
+  ApiGuard api_guard;
   Context* c = ctx();
   if (!c) return 1;
   bool ok = WB_CUDA(cudaStreamSynchronize(c->stream));
@@ -375,6 +388,7 @@ int wb200_sync(void) {
   return ok ? 0 : 1;
 }
 int wb200_randn_stream(double* out, long long n) {
+  ApiGuard api_guard;
   Context* c = ctx();
   if (!c || !ensure_randn((size_t)n)) return 1;
   std::vector<uint32_t> h((size_t)n);
@@ -384,6 +398,7 @@ int wb200_randn_stream(double* out, long long n) {
 }
 
 wb200_batch* wb200_batch_create(int fs, double frame_period, int n_utt, const int* x_lengths) {
+  ApiGuard api_guard;
   if (!ctx()) return nullptr;
   wb200_batch* h = new wb200_batch();
   std::vector<int> f_len(n_utt > 0 ? n_utt : 1);
@@ -396,6 +411,7 @@ wb200_batch* wb200_batch_create(int fs, double frame_period, int n_utt, const in
   return h;
 }
 void wb200_batch_destroy(wb200_batch* h) {
+  ApiGuard api_guard;
   if (!h) return;
   if (ctx()) wb200_sync();             // library, upload and download streams
   delete h;
@@ -426,6 +442,7 @@ static int convert_pcm(wb200_batch* h, const int16_t* dev_pcm) {
   return WB_CUDA(cudaStreamSynchronize(c->stream)) ? 0 : 1;
 }
 int wb200_batch_upload_pcm16(wb200_batch* h, const int16_t* host_pcm) {
+  ApiGuard api_guard;
   Context* c = ctx();
   if (!c) return 1;
   const long long n = wb200_batch_total_samples(h);
@@ -438,6 +455,7 @@ int wb200_batch_upload_pcm16(wb200_batch* h, const int16_t* host_pcm) {
 // batch wait for it on the device.  host_pcm must be pinned and stay valid until the first stage
 // of this batch has been launched.
 int wb200_batch_upload_pcm16_async(wb200_batch* h, const int16_t* host_pcm) {
+  ApiGuard api_guard;
   Context* c = ctx();
   if (!c || !ensure_copy_streams(c)) return 1;
   Batch& b = h->b;
@@ -464,10 +482,12 @@ int wb200_batch_upload_pcm16_async(wb200_batch* h, const int16_t* host_pcm) {
   return 0;
 }
 int wb200_batch_set_pcm16_device(wb200_batch* h, const int16_t* dev_pcm) {
+  ApiGuard api_guard;
   if (!ctx()) return 1;
   return convert_pcm(h, dev_pcm);
 }
 int wb200_batch_upload_f64(wb200_batch* h, const double* host_x) {
+  ApiGuard api_guard;
   Context* c = ctx();
   if (!c) return 1;
   Batch& b = h->b;
@@ -482,24 +502,28 @@ int wb200_batch_upload_f64(wb200_batch* h, const double* host_x) {
 }
 
 int wb200_batch_dio(wb200_batch* h, const DioOption* o) {
+  ApiGuard api_guard;
   if (!ctx() || !wait_upload(h)) return 1;
   DioParams p = {o->f0_floor, o->f0_ceil, o->channels_in_octave, o->frame_period, o->speed, o->allowed_range};
   StageTimer t(&g_times.dio);
   return dio_run(&h->b, p, h->b.f0_raw.p) ? 0 : 1;
 }
 int wb200_batch_stonemask(wb200_batch* h) {
+  ApiGuard api_guard;
   if (!ctx() || !wait_upload(h)) return 1;
   Batch& b = h->b;
   StageTimer t(&g_times.stonemask);
   return stonemask_run(b.view(), b.fs, b.total_frames, b.frame_utt.p, b.frame_t.p, b.f0_raw.p, b.f0.p) ? 0 : 1;
 }
 int wb200_batch_harvest(wb200_batch* h, const HarvestOption* o) {
+  ApiGuard api_guard;
   if (!ctx() || !wait_upload(h)) return 1;
   HarvestParams p = {o->f0_floor, o->f0_ceil, o->frame_period};
   StageTimer t(&g_times.harvest);
   return harvest_run(&h->b, p, h->b.f0.p) ? 0 : 1;
 }
 int wb200_batch_cheaptrick(wb200_batch* h, const CheapTrickOption* o) {
+  ApiGuard api_guard;
   if (!ctx() || !wait_upload(h)) return 1;
   Batch& b = h->b;
   b.fft_size = o->fft_size;
@@ -508,6 +532,7 @@ int wb200_batch_cheaptrick(wb200_batch* h, const CheapTrickOption* o) {
   return cheaptrick_run(b.view(), b.fs, b.total_frames, b.frame_utt.p, b.frame_t.p, b.f0.p, o->fft_size, o->q1, b.sp.p) ? 0 : 1;
 }
 int wb200_batch_d4c(wb200_batch* h, int fft_size, const D4COption* o) {
+  ApiGuard api_guard;
   if (!ctx() || !wait_upload(h)) return 1;
   Batch& b = h->b;
   b.fft_size = fft_size;
@@ -516,6 +541,7 @@ int wb200_batch_d4c(wb200_batch* h, int fft_size, const D4COption* o) {
   return d4c_run(b.view(), b.fs, b.total_frames, b.frame_utt.p, b.frame_t.p, b.f0.p, fft_size, o->threshold, b.ap.p) ? 0 : 1;
 }
 int wb200_batch_synthesis(wb200_batch* h, const int* y_lengths) {
+  ApiGuard api_guard;
   if (!ctx()) return 1;
   Batch& b = h->b;
   std::vector<int> yl(b.n_utt > 0 ? b.n_utt : 1);
@@ -539,18 +565,23 @@ static int h2d(void* dst, const void* src, size_t bytes) {
           WB_CUDA(cudaStreamSynchronize(c->stream))) ? 0 : 1;
 }
 int wb200_batch_get_f0(wb200_batch* h, double* out, int refined) {
+  ApiGuard api_guard;
   return d2h(out, refined ? h->b.f0.p : h->b.f0_raw.p, (size_t)h->b.total_frames * sizeof(double));
 }
 int wb200_batch_set_f0(wb200_batch* h, const double* in, int refined) {
+  ApiGuard api_guard;
   return h2d(refined ? h->b.f0.p : h->b.f0_raw.p, in, (size_t)h->b.total_frames * sizeof(double));
 }
 int wb200_batch_get_sp(wb200_batch* h, double* out) {
+  ApiGuard api_guard;
   return d2h(out, h->b.sp.p, (size_t)h->b.total_frames * (h->b.fft_size / 2 + 1) * sizeof(double));
 }
 int wb200_batch_get_ap(wb200_batch* h, double* out) {
+  ApiGuard api_guard;
   return d2h(out, h->b.ap.p, (size_t)h->b.total_frames * (h->b.fft_size / 2 + 1) * sizeof(double));
 }
 int wb200_batch_set_sp_ap(wb200_batch* h, int fft_size, const double* sp, const double* ap) {
+  ApiGuard api_guard;
   Batch& b = h->b;
   b.fft_size = fft_size;
   const size_t n = (size_t)b.total_frames * (fft_size / 2 + 1);
@@ -562,6 +593,7 @@ __global__ void widen_f32_kernel(const float* __restrict__ in, long long n, doub
     out[i] = (double)in[i];                                              // ToDouble, W/test/synth.cpp:66-70
 }
 int wb200_batch_set_params_f32(wb200_batch* h, int fft_size, const float* f0, const float* sp, const float* ap) {
+  ApiGuard api_guard;
   Context* c = ctx();
   if (!c) return 1;
   Batch& b = h->b;
@@ -593,6 +625,7 @@ int wb200_batch_y_layout(const wb200_batch* h, long long* y_off, int* y_len) {
   return 0;
 }
 int wb200_batch_get_y(wb200_batch* h, double* out) {
+  ApiGuard api_guard;
   Context* c = ctx();
   Batch& b = h->b;
   if (!c || !b.y.p) { set_error("synthesis has not been run"); return 1; }
@@ -626,6 +659,7 @@ static bool prepare_pcm_out(wb200_batch* h, long long n) {
   return true;
 }
 int wb200_batch_get_y_pcm16(wb200_batch* h, int16_t* out) {
+  ApiGuard api_guard;
   Context* c = ctx();
   Batch& b = h->b;
   if (!c || !b.y.p) { set_error("synthesis has not been run"); return 1; }
@@ -640,6 +674,7 @@ int wb200_batch_get_y_pcm16(wb200_batch* h, int16_t* out) {
 // The conversion runs on the library stream (after Synthesis), the copy on the download stream:
 // it overlaps the next batch's computation.  `out` must be pinned; valid after wb200_sync().
 int wb200_batch_get_y_pcm16_async(wb200_batch* h, int16_t* out) {
+  ApiGuard api_guard;
   Context* c = ctx();
   Batch& b = h->b;
   if (!c || !b.y.p) { set_error("synthesis has not been run"); return 1; }
@@ -655,6 +690,7 @@ int wb200_batch_get_y_pcm16_async(wb200_batch* h, int16_t* out) {
 }
 // one utterance's slice of every result (any pointer may be NULL)
 int wb200_batch_get_utterance(wb200_batch* h, int utt, double* f0_raw, double* f0, double* sp, double* ap, double* y) {
+  ApiGuard api_guard;
   Context* c = ctx();
   Batch& b = h->b;
   if (!c) return 1;
@@ -672,6 +708,16 @@ int wb200_batch_get_utterance(wb200_batch* h, int utt, double* f0_raw, double* f
   }
   return WB_CUDA(cudaStreamSynchronize(c->stream)) ? 0 : 1;
 }
+// Host-side wait for the asynchronous result copies of THIS batch only (coded features, 16-bit waveform):
+// a pipelined caller hands batch i's host buffers to its consumer while batch i + 1 already computes.
+int wb200_batch_wait_downloads(wb200_batch* h) {
+  ApiGuard api_guard;
+  if (!ctx()) return 1;
+  bool ok = true;
+  for (int k = 0; k < 2; ++k)
+    if (h->download_done[k]) ok = WB_CUDA(cudaEventSynchronize(h->download_done[k])) && ok;
+  return ok ? 0 : 1;
+}
 void* wb200_batch_device_ptr(wb200_batch* h, const char* which) {
   Batch& b = h->b;
   const std::string w(which);
@@ -684,10 +730,12 @@ void* wb200_batch_device_ptr(wb200_batch* h, const char* which) {
   return nullptr;
 }
 int wb200_batch_code(wb200_batch* h, int mgc_dim, int bap_dim) {
+  ApiGuard api_guard;
   if (!ctx() || !wait_downloads(h, kDlCoded)) return 1;   // the previous pass's copies may still read lf0 / mgc / bap
   return batch_code_features(&h->b, mgc_dim, bap_dim) ? 0 : 1;
 }
 int wb200_batch_get_coded(wb200_batch* h, float* lf0, float* mgc, float* bap) {
+  ApiGuard api_guard;
   Batch& b = h->b;
   const size_t F = (size_t)b.total_frames;
   if (lf0 && d2h(lf0, b.lf0.p, F * sizeof(float))) return 1;
@@ -699,6 +747,7 @@ int wb200_batch_get_coded(wb200_batch* h, float* lf0, float* mgc, float* bap) {
 // they run while later stages (Synthesis) compute.  Host buffers must be pinned and stay valid
 // until wb200_sync() returns.
 int wb200_batch_get_coded_async(wb200_batch* h, float* lf0, float* mgc, float* bap) {
+  ApiGuard api_guard;
   Context* c = ctx();
   if (!c) return 1;
   Batch& b = h->b;
@@ -722,6 +771,7 @@ __global__ void sp_unscale_kernel(double* __restrict__ sp, long long n) {
   if (i < n) sp[i] *= 1e-4;                                            // undo sp * 1e4 (analysis.cpp:297)
 }
 int wb200_batch_decode_mgc(wb200_batch* h, int fft_size, int mgc_dim, const float* host_mgc) {
+  ApiGuard api_guard;
   Context* c = ctx();
   if (!c) return 1;
   Batch& b = h->b;
@@ -740,14 +790,30 @@ int wb200_batch_decode_mgc(wb200_batch* h, int fft_size, int mgc_dim, const floa
   return WB_CUDA(cudaStreamSynchronize(c->stream)) ? 0 : 1;
 }
 int wb200_batch_compose_cmp(wb200_batch* h, const wb200_cmp_stream* streams, int n_streams) {
-  if (!ctx()) return 1;
+  ApiGuard api_guard;
+  if (!ctx() || !wait_downloads(h, kDlCoded)) return 1;
   return batch_compose_cmp(&h->b, streams, n_streams) ? 0 : 1;
 }
 int wb200_batch_cmp_dim(const wb200_batch* h) { return h->b.cmp_dim; }
 int wb200_batch_get_cmp(wb200_batch* h, float* out) {
+  ApiGuard api_guard;
   return d2h(out, h->b.cmp.p, (size_t)h->b.total_frames * h->b.cmp_dim * sizeof(float));
 }
+// the same copy on the download stream (pinned `out`, valid after wb200_batch_wait_downloads / wb200_sync)
+int wb200_batch_get_cmp_async(wb200_batch* h, float* out) {
+  ApiGuard api_guard;
+  Context* c = ctx();
+  if (!c) return 1;
+  Batch& b = h->b;
+  if (!b.cmp.p || b.cmp_dim < 1) { set_error("cmp: wb200_batch_compose_cmp has not been run"); return 1; }
+  if (!ensure_copy_streams(c)) return 1;
+  const size_t n = (size_t)b.total_frames * b.cmp_dim;
+  bool ok = WB_CUDA(cudaEventRecord(c->copy_event, c->stream)) && WB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_event, 0));
+  if (ok && n > 0) ok = WB_CUDA(cudaMemcpyAsync(out, b.cmp.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+  return ok && mark_downloads(h, kDlCoded) ? 0 : 1;
+}
 int wb200_batch_cmp_stats(wb200_batch* h, double* out) {
+  ApiGuard api_guard;
   if (!ctx()) return 1;
   return batch_cmp_stats(&h->b, out) ? 0 : 1;
 }
@@ -763,16 +829,19 @@ int wb200_htk_header(int n_frames, int samp_freq, int frame_shift, int byte_per_
   return 0;
 }
 int wb200_batch_gv_stats(wb200_batch* h, double* per_utt, double* partials) {
+  ApiGuard api_guard;
   if (!ctx()) return 1;
   return batch_gv_stats(&h->b, per_utt, partials) ? 0 : 1;
 }
 int wb200_batch_lf0_stats(wb200_batch* h, double* out3);
 int wb200_batch_feature_stats(wb200_batch* h, double* out) {
+  ApiGuard api_guard;
   if (!ctx()) return 1;
   if (!batch_feature_stats(&h->b, out)) return 1;
   return wb200_batch_lf0_stats(h, out);                                 // row 0: voiced lf0
 }
 int wb200_batch_lf0_stats(wb200_batch* h, double* out3) {
+  ApiGuard api_guard;
   Context* c = ctx();
   if (!c) return 1;
   DevBuf<double> d;

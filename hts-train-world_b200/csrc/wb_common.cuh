@@ -74,6 +74,19 @@ struct Context {
   size_t smem_optin = 0;
 };
 Context* ctx();                           // lazily initialised; nullptr on failure
+// Every exported entry point that touches the device holds one of these for its whole duration: the
+// library has ONE context (stream, scratch pool, tables), so concurrent callers are serialised -- the
+// reference is not reentrant at all (global RNG state); this makes the replacement safe to call from any
+// number of threads.  Recursive: the drop-in entry points call the batched ones.  It also
+// binds the calling thread to the context's device (CUDA's current device is per thread and defaults to 0).
+struct ApiGuard {
+  ApiGuard();
+  ~ApiGuard();
+  ApiGuard(const ApiGuard&) = delete;
+  ApiGuard& operator=(const ApiGuard&) = delete;
+};
+cudaMemPool_t scratch_pool();             // the library's own stream-ordered pool (DevBuf)
+bool trim_pool();                         // give the pool's cached memory back to the driver
 bool ensure_randn(size_t count);          // grow the randn table to >= count variates
 // Small device -> host read-back on the library stream, complete on return (per-utterance totals,
 // counters, statistics partials: the values the host needs to size the next launch).  bytes is a
@@ -99,10 +112,11 @@ void kernel_timing_enable(bool on);
 bool kernel_time_query(const char* name, double* ms_total, long long* launches);
 void kernel_times_reset();
 
-// Stream-ordered device buffer.  Memory comes from the device's default CUDA memory pool
-// (cudaMallocAsync on the library stream; the pool's release threshold is raised to "never" in
-// ctx()), so the per-stage scratch buffers -- gigabytes for a corpus-sized batch -- are recycled
-// between stages and calls instead of going through cudaMalloc / cudaFree every time.
+// Stream-ordered device buffer.  Memory comes from a CUDA memory pool of the library's own
+// (cudaMallocFromPoolAsync on the library stream; release threshold "never"), so the per-stage scratch
+// buffers -- gigabytes for a corpus-sized batch -- are recycled between stages and calls instead of going
+// through cudaMalloc / cudaFree every time, and the device's default pool (PyTorch, other libraries)
+// is left alone.  wb200_trim() hands the cached memory back to the driver.
 cudaStream_t pool_stream();
 template <typename T>
 struct DevBuf {
@@ -119,7 +133,7 @@ struct DevBuf {
   }
   void release() { free(p); p = nullptr; n = 0; }
 #else
-    if (!WB_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), pool_stream()))) { p = nullptr; n = 0; return false; }
+    if (!WB_CUDA(cudaMallocFromPoolAsync((void**)&p, count * sizeof(T), scratch_pool(), pool_stream()))) { p = nullptr; n = 0; return false; }
     n = count;
     return true;
   }

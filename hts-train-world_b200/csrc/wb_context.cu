@@ -241,6 +241,24 @@ double measure_fma_peak(bool fp64) {
 static std::mutex g_ctx_mutex;
 static Context g_ctx;
 static bool g_ctx_ok = false, g_ctx_failed = false;
+static cudaMemPool_t g_pool = nullptr;
+static std::recursive_mutex g_api_mutex;
+
+ApiGuard::ApiGuard() {
+  g_api_mutex.lock();
+  if (g_ctx_ok) {                          // the context lives on one device; make it this thread's current one
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != g_ctx.device) cudaSetDevice(g_ctx.device);
+  }
+}
+ApiGuard::~ApiGuard() { g_api_mutex.unlock(); }
+
+cudaMemPool_t scratch_pool() { return g_pool; }
+bool trim_pool() {
+  ApiGuard guard;
+  if (!g_ctx_ok || !g_pool) return true;
+  return WB_CUDA(cudaStreamSynchronize(g_ctx.stream)) && WB_CUDA(cudaMemPoolTrimTo(g_pool, 0));
+}
 
 cudaStream_t pool_stream() { return g_ctx_ok ? g_ctx.stream : nullptr; }
 
@@ -269,11 +287,17 @@ Context* ctx() {
   if (!WB_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking))) {
     g_ctx_failed = true; return nullptr;
   }
-  {   // keep freed scratch in the pool instead of returning it to the driver at every sync
-    cudaMemPool_t pool;
+  {   // the library's own pool: freed scratch stays in it instead of returning to the driver at every sync
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
     unsigned long long never = ~0ull;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never);
+    if (!WB_CUDA(cudaMemPoolCreate(&g_pool, &props)) ||
+        !WB_CUDA(cudaMemPoolSetAttribute(g_pool, cudaMemPoolAttrReleaseThreshold, &never))) {
+      g_ctx_failed = true; return nullptr;
+    }
   }
   // twiddles, rounded from long double
   std::vector<double2> tw(kTwN / 2 + 1);
@@ -313,6 +337,7 @@ Context* ctx() {
 }
 
 bool ensure_randn(size_t count) {
+  ApiGuard guard;                                      // the table swap below must not race with another caller
   Context* c = ctx();
   if (!c) return false;
   if (count <= c->randn_count) return true;

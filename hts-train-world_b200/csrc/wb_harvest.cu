@@ -421,96 +421,116 @@ harvest_refine_thread_kernel(const double* __restrict__ y_all, const long long* 
                              const long long* __restrict__ cand_off, int max_base, HarvestConst c, int n_utt,
                              long long total_work, const double2* __restrict__ tw_c_base,
                              double* __restrict__ cand, double* __restrict__ score) {
+  // One thread per (1 ms frame k, base candidate j); it serves the kOverlap slots q * nc + j of the frame,
+  // i.e. the candidates the same F0 track had at frames k-3 .. k+3 (OverlapF0Candidates :417-429).  Their
+  // values differ by a fraction of a per cent, so most of them share the window length and all six
+  // harmonic bins -- and then the two windowed spectra at those bins are the same numbers: the window walk
+  // is repeated only when (hwl, bins) changes (2-3 walks instead of 7), the rest of FixF0 (:504-536), which
+  // does depend on the candidate itself, runs per slot.  Bit-identical to one walk per slot.
   const long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (w >= total_work) return;
-  int lo = 0, hi = n_utt - 1;                       // cand_off doubles as the work prefix: g_len * slots per utterance
-  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (cand_off[mid] <= w) lo = mid; else hi = mid - 1; }
+  int lo = 0, hi = n_utt - 1;                       // cand_off / kOverlap is the work prefix: g_len * nc per utterance
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (cand_off[mid] <= w * kOverlap) lo = mid; else hi = mid - 1; }
   const int u = lo;
   const int nc = nc_utt[u], slots = nc * kOverlap, n_fr = g_len[u];
-  const long long local = w - cand_off[u];
-  const int s = (int)(local / n_fr), k = (int)(local - (long long)s * n_fr);      // frame fastest
-  const size_t o = cand_off[u] + (size_t)k * slots + s;
-  const double f0c = harvest_overlapped(base + (size_t)g_off[u] * max_base, max_base, nc, n_fr, k, s);
-  if (!(f0c > 0.0)) { cand[o] = 0.0; score[o] = 0.0; return; }
+  const long long local = w - cand_off[u] / kOverlap;
+  const int j = (int)(local / n_fr), k = (int)(local - (long long)j * n_fr);      // frame fastest
+  const double* __restrict__ base_u = base + (size_t)g_off[u] * max_base;
   const double* __restrict__ y = y_all + y_off[u];
   const int y_len = y_len_all[u];
   const double mean = mean_all[u];
   const double fs = c.actual_fs;
   const double pos = div_rn((double)k, 1000.0);
-  const int hwl = static_cast<int>(add_rn(div_rn(mul_rn(1.5, fs), f0c), 1.0));          // :586
-  const int W = 2 * hwl + 1;
-  const double wlen = div_rn(add_rn(mul_rn(2.0, (double)hwl), 1.0), fs);                // :587
-  const int log2fft = 2 + (31 - __clz(W));                                               // :591-592 (W odd)
-  const int nfft = 1 << log2fft, nhalf = nfft >> 1;
-  const int basic_index = matlab_round(add_rn(mul_rn(add_rn(pos, div_rn((double)(-hwl), fs)), fs), 0.001));   // :436-437
-  const int nh = min(static_cast<int>(fs / 2.0 / f0c), 6);                               // :570-571
-  int bins[6];
-  double pc[6], ps[6], qc[6], qs[6], acc[6][4];
-  {
-    const double2* __restrict__ tw = tw_c_base + Context::tw_c_offset(log2fft);
+  auto blackman = [](double cv) { return 0.42 + 0.5 * cv + 0.08 * (2.0 * cv * cv - 1.0); };
+  int key_hwl = -1, key_bins[6] = {0, 0, 0, 0, 0, 0};
+  double acc[6][4];
+#pragma unroll 1
+  for (int q = 0; q < kOverlap; ++q) {
+    const int s = q * nc + j;
+    const size_t o = cand_off[u] + (size_t)k * slots + s;
+    const double f0c = harvest_overlapped(base_u, max_base, nc, n_fr, k, s);
+    if (!(f0c > 0.0)) { cand[o] = 0.0; score[o] = 0.0; continue; }
+    const int hwl = static_cast<int>(add_rn(div_rn(mul_rn(1.5, fs), f0c), 1.0));          // :586
+    const int W = 2 * hwl + 1;
+    const int log2fft = 2 + (31 - __clz(W));                                               // :591-592 (W odd)
+    const int nfft = 1 << log2fft, nhalf = nfft >> 1;
+    const int nh = min(static_cast<int>(fs / 2.0 / f0c), 6);                               // :570-571
+    int bins[6];
+    bool same = hwl == key_hwl;
 #pragma unroll
     for (int h = 0; h < 6; ++h) {
       bins[h] = matlab_round(mul_rn(div_rn(mul_rn(f0c, (double)nfft), fs), (double)(h + 1)));   // :513
-      const int m1 = bins[h] & (nfft - 1);
-      double2 b = __ldg(&tw[m1 & (nhalf - 1)]);
-      if (m1 & nhalf) { b.x = -b.x; b.y = -b.y; }
-      pc[h] = 1.0; ps[h] = 0.0; qc[h] = b.x; qs[h] = b.y;
-      acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.0;
+      same = same && bins[h] == key_bins[h];
     }
-  }
-  auto blackman = [](double cv) { return 0.42 + 0.5 * cv + 0.08 * (2.0 * cv * cv - 1.0); };
-  // window phase a_n = 2 pi ((basic_index + n - 1) / fs - pos) / wlen (:447-452), advanced one sample at a time
-  const double dturn = 2.0 / (wlen * fs);
-  double cd, sd, cs, sn;
-  sincospi(dturn, &sd, &cd);
-  sincospi(2.0 * add_rn(div_rn(basic_index - 1.0, fs), -pos) / wlen, &sn, &cs);        // n = 0
-  double w_prev = blackman(cs * cd + sn * sd);                                          // n = -1 (only its slot is used)
-  double w_cur = blackman(cs);
-  for (int n = 0; n < W; ++n) {
-    {                                                               // phase of sample n + 1
-      const double t = cs * cd - sn * sd;
-      sn = sn * cd + cs * sd;
-      cs = t;
+    if (!same) {
+      key_hwl = hwl;
+      const double wlen = div_rn(add_rn(mul_rn(2.0, (double)hwl), 1.0), fs);              // :587
+      const int basic_index = matlab_round(add_rn(mul_rn(add_rn(pos, div_rn((double)(-hwl), fs)), fs), 0.001));   // :436-437
+      double pc[6], ps[6], qc[6], qs[6];
+      const double2* __restrict__ tw = tw_c_base + Context::tw_c_offset(log2fft);
+#pragma unroll
+      for (int h = 0; h < 6; ++h) {
+        key_bins[h] = bins[h];
+        const int m1 = bins[h] & (nfft - 1);
+        double2 b = __ldg(&tw[m1 & (nhalf - 1)]);
+        if (m1 & nhalf) { b.x = -b.x; b.y = -b.y; }
+        pc[h] = 1.0; ps[h] = 0.0; qc[h] = b.x; qs[h] = b.y;
+        acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.0;
+      }
+      // window phase a_n = 2 pi ((basic_index + n - 1) / fs - pos) / wlen (:447-452), advanced one sample at a
+      // time; the differentiated window (:459-465) needs w[n-1], w[n], w[n+1]: a three-value slide
+      const double dturn = 2.0 / (wlen * fs);
+      double cd, sd, cs, sn;
+      sincospi(dturn, &sd, &cd);
+      sincospi(2.0 * add_rn(div_rn(basic_index - 1.0, fs), -pos) / wlen, &sn, &cs);      // n = 0
+      double w_prev = 0.0, w_cur = blackman(cs);
+      for (int n = 0; n < W; ++n) {
+        {                                                             // phase of sample n + 1
+          const double t = cs * cd - sn * sd;
+          sn = sn * cd + cs * sd;
+          cs = t;
+        }
+        const double w_next = blackman(cs);
+        double dw;
+        if (n == 0) dw = -w_next / 2.0;
+        else if (n == W - 1) dw = w_prev / 2.0;
+        else dw = -(w_next - w_prev) / 2.0;
+        const int idx = max(0, min(y_len - 1, basic_index + n - 1));
+        const double xv = y[idx] - mean;
+        const double xm = xv * w_cur, xd = xv * dw;
+#pragma unroll
+        for (int h = 0; h < 6; ++h) {
+          acc[h][0] += xm * pc[h]; acc[h][1] += xm * ps[h];
+          acc[h][2] += xd * pc[h]; acc[h][3] += xd * ps[h];
+          const double t = pc[h] * qc[h] - ps[h] * qs[h];
+          ps[h] = ps[h] * qc[h] + pc[h] * qs[h];
+          pc[h] = t;
+        }
+        w_prev = w_cur;
+        w_cur = w_next;
+      }
     }
-    const double w_next = blackman(cs);
-    double dw;                                                      // GetDiffWindow (:459-465)
-    if (n == 0) dw = -w_next / 2.0;
-    else if (n == W - 1) dw = w_prev / 2.0;
-    else dw = -(w_next - w_prev) / 2.0;
-    const int idx = max(0, min(y_len - 1, basic_index + n - 1));
-    const double xv = y[idx] - mean;
-    const double xm = xv * w_cur, xd = xv * dw;
+    double numerator = 0.0, denominator = 0.0, sc = 0.0;           // FixF0 (:504-536)
 #pragma unroll
     for (int h = 0; h < 6; ++h) {
-      acc[h][0] += xm * pc[h]; acc[h][1] += xm * ps[h];
-      acc[h][2] += xd * pc[h]; acc[h][3] += xd * ps[h];
-      const double t = pc[h] * qc[h] - ps[h] * qs[h];
-      ps[h] = ps[h] * qc[h] + pc[h] * qs[h];
-      pc[h] = t;
+      if (h >= nh) break;
+      const double re = acc[h][0], im = acc[h][1], dre = acc[h][2], dim = acc[h][3];
+      const double power = re * re + im * im;
+      const double numer = re * dim - im * dre;
+      const double inst = power == 0.0 ? 0.0
+          : add_rn(div_rn(mul_rn((double)bins[h], fs), (double)nfft),
+                   div_rn(div_rn(mul_rn(div_rn(numer, power), fs), 2.0), kPi));
+      const double amp = sqrt(power);
+      numerator += amp * inst;
+      denominator += amp * (h + 1.0);
+      sc += fabs((inst / (h + 1.0) - f0c) / f0c);
     }
-    w_prev = w_cur;
-    w_cur = w_next;
+    double refined = numerator / (denominator + kMySafeGuardMinimum);
+    double rscore = 1.0 / (sc / nh + kMySafeGuardMinimum);
+    if (refined < c.f0_floor || refined > c.f0_ceil || rscore < 2.5) { refined = 0.0; rscore = 0.0; }   // :598-602
+    cand[o] = refined;
+    score[o] = rscore;
   }
-  double numerator = 0.0, denominator = 0.0, sc = 0.0;             // FixF0 (:504-536)
-#pragma unroll
-  for (int h = 0; h < 6; ++h) {
-    if (h >= nh) break;
-    const double re = acc[h][0], im = acc[h][1], dre = acc[h][2], dim = acc[h][3];
-    const double power = re * re + im * im;
-    const double numer = re * dim - im * dre;
-    const double inst = power == 0.0 ? 0.0
-        : add_rn(div_rn(mul_rn((double)bins[h], fs), (double)nfft),
-                 div_rn(div_rn(mul_rn(div_rn(numer, power), fs), 2.0), kPi));
-    const double amp = sqrt(power);
-    numerator += amp * inst;
-    denominator += amp * (h + 1.0);
-    sc += fabs((inst / (h + 1.0) - f0c) / f0c);
-  }
-  double refined = numerator / (denominator + kMySafeGuardMinimum);
-  double rscore = 1.0 / (sc / nh + kMySafeGuardMinimum);
-  if (refined < c.f0_floor || refined > c.f0_ceil || rscore < 2.5) { refined = 0.0; rscore = 0.0; }   // :598-602
-  cand[o] = refined;
-  score[o] = rscore;
 }
 
 // ---- RemoveUnreliableCandidates (:652-688) --------------------------------------------------------
@@ -1298,8 +1318,8 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
     {
       KernelTimer kt("harvest_refine_kernel");
       if (option("harvest_refine_thread")) {
-        harvest_refine_thread_kernel<<<(unsigned)((ctot + 127) / 128), 128, 0, st>>>(d_y.p, d_yoff.p, d_ylen.p, d_mean.p, d_base.p, d_goff.p, d_glen.p,
-                                                                                    d_nc.p, d_coff.p, max_base, c, n_utt, ctot, ctxp->d_twiddle_c, d_cand.p, d_score.p);
+        harvest_refine_thread_kernel<<<(unsigned)((ctot / kOverlap + 127) / 128), 128, 0, st>>>(d_y.p, d_yoff.p, d_ylen.p, d_mean.p, d_base.p, d_goff.p, d_glen.p,
+                                                                                    d_nc.p, d_coff.p, max_base, c, n_utt, ctot / kOverlap, ctxp->d_twiddle_c, d_cand.p, d_score.p);
       } else {
         const long long threads = gtot * 32;
         harvest_refine_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_y.p, d_yoff.p, d_ylen.p, d_mean.p, d_base.p, d_goff.p, d_glen.p,

@@ -161,7 +161,9 @@ synth_phase_kernel(const double* __restrict__ inc_all, const long long* __restri
       e = ilogb(s0);
       const double m = scalbn(inc, 52 - e);
       const double rr = rint(m);
-      slow = fabs(m - rr) == 0.5 || !(m < 4503599627370496.0);
+      // a negative increment (the extrapolated last F0 knot can be negative while the interpolated V/UV
+      // flag is still voiced) breaks the monotonicity the end-of-chunk binade test below relies on
+      slow = fabs(m - rr) == 0.5 || !(m < 4503599627370496.0) || inc < 0.0;
       r = static_cast<long long>(rr);
       s0int = static_cast<long long>(scalbn(s0, 52 - e));
     }

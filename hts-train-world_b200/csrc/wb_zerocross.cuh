@@ -155,16 +155,27 @@ static __global__ void zc_scan_kernel(int* __restrict__ counts, int n_lists, int
 // interp1 (matlabfunctions.cpp:157-182) of interval-F0 at time t; knots are the mid-points of
 // consecutive edges: loc_i = (e_i + e_{i+1}) / 2 / fs, val_i = fs / (e_{i+1} - e_i), i < n_int.
 __device__ __forceinline__ double zc_loc(const double* __restrict__ e, int i, double fs) {
-  return div_rn(div_rn(add_rn(e[i], e[i + 1]), 2.0), fs);
+  return div_rn(mul_rn(add_rn(e[i], e[i + 1]), 0.5), fs);       // halving is exact
 }
 __device__ __forceinline__ double zc_val(const double* __restrict__ e, int i, double fs) {
   return div_rn(fs, add_rn(e[i + 1], -e[i]));
+}
+// zc_loc(e, i, fs) <= t without the two divisions in all but borderline cases: with s = (e_i + e_{i+1}) / 2
+// (exact halving) the knot is rn(s / fs), and rounding is monotonic: s / fs <= t implies rn(s / fs) <= t;
+// s / fs > t allows rn(s / fs) == t only within half an ulp of t.  The sign of fma(t, fs, -s) is the exact
+// sign of t fs - s, so only |t fs - s| <= fs ulp(t) needs the reference's own arithmetic.
+__device__ __forceinline__ bool zc_loc_le(const double* __restrict__ e, int i, double fs, double t) {
+  const double s = mul_rn(add_rn(e[i], e[i + 1]), 0.5);
+  const double r = fma(t, fs, -s);
+  if (r >= 0.0) return true;
+  if (-r > fs * t * 4.5e-16) return false;
+  return div_rn(s, fs) <= t;
 }
 __device__ inline double zc_interp(const double* __restrict__ e, int n_int, double fs, double t) {
   int lo = 0, hi = n_int;                 // upper_bound: first knot with loc > t
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (zc_loc(e, mid, fs) <= t) lo = mid + 1; else hi = mid;
+    if (zc_loc_le(e, mid, fs, t)) lo = mid + 1; else hi = mid;
   }
   const int k = max(1, min(n_int - 1, lo));
   const double x0 = zc_loc(e, k - 1, fs), x1 = zc_loc(e, k, fs);

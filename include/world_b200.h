@@ -9,6 +9,10 @@
  *
  * All functions return 0 on success and non-zero on failure; wb200_last_error() then holds a
  * message.  There is no CPU fallback: without a CUDA device every call fails.
+ *
+ * Threads: every entry point (these and the drop-in WORLD functions) may be called from any thread; the
+ * library has one device context and serialises the calls internally, binding the calling thread to the
+ * context's device.  Asynchronous copies queued by one call stay valid across calls of other threads.
  */
 #ifndef WORLD_B200_H_
 #define WORLD_B200_H_
@@ -49,6 +53,10 @@ WORLD_API double wb200_measure_fma_peak(int fp64);
  * "harvest_fused", "harvest_refine_thread" (environment WB_D4C_LT32, WB_STONEMASK_DFT, WB_DIO_FUSED,
  * WB_HARVEST_FUSED, WB_HARVEST_REFINE_THREAD = 0 | 1 override the defaults); unknown names give 0 */
 WORLD_API int wb200_option(const char *name);
+/* The library keeps its scratch memory (per-stage buffers, gigabytes for a corpus-sized batch) in a CUDA
+ * memory pool of its own and never returns it on its own; wb200_trim() waits for the library stream and
+ * hands everything that is not in use back to the driver (e.g. before a training step that needs the HBM). */
+WORLD_API int wb200_trim(void);
 /* first `n` values of the randn table as doubles (test hook: must equal the reference's
  * randn() stream after randn_reseed(), W/src/matlabfunctions.cpp:247-277) */
 WORLD_API int wb200_randn_stream(double *out, long long n);
@@ -102,6 +110,9 @@ WORLD_API int wb200_batch_get_y(wb200_batch *b, double *host_y);     /* back to 
 WORLD_API int wb200_batch_get_y_pcm16(wb200_batch *b, int16_t *host_pcm);
 /* asynchronous variant on a download stream (pinned `host_pcm`, valid after wb200_sync()) */
 WORLD_API int wb200_batch_get_y_pcm16_async(wb200_batch *b, int16_t *host_pcm);
+/* block the calling thread until the asynchronous result copies queued for THIS batch (get_coded_async,
+ * get_y_pcm16_async) have landed in their host buffers; work queued for other batches keeps running */
+WORLD_API int wb200_batch_wait_downloads(wb200_batch *b);
 /* one utterance's slice of the results (any pointer may be NULL): f0_raw / f0 [f_len], sp / ap
  * [f_len][fft_size/2+1], y [y_len] -- spot checks of a corpus-sized batch without copying all of it */
 WORLD_API int wb200_batch_get_utterance(wb200_batch *b, int utt, double *host_f0_raw, double *host_f0,
@@ -157,6 +168,8 @@ typedef struct {
 WORLD_API int wb200_batch_compose_cmp(wb200_batch *b, const wb200_cmp_stream *streams, int n_streams);
 WORLD_API int wb200_batch_cmp_dim(const wb200_batch *b);           /* floats per frame */
 WORLD_API int wb200_batch_get_cmp(wb200_batch *b, float *host_cmp); /* [total_frames][cmp_dim] */
+/* the same copy on the download stream (pinned host_cmp; valid after wb200_batch_wait_downloads / wb200_sync) */
+WORLD_API int wb200_batch_get_cmp_async(wb200_batch *b, float *host_cmp);
 /* per-GPU partials {count, sum, sum of squares} of every cmp column: out[cmp_dim][3] */
 WORLD_API int wb200_batch_cmp_stats(wb200_batch *b, double *out);
 /* the 12-byte HTK header of data/scripts/addhtkheader.pl: int32 nframe, int32 frame shift in

@@ -554,3 +554,38 @@ def test_hard_inputs(wb, reference_lib, case):
     assert M.ap_abs_error(ap_ref, wb.d4c(x, fs, o["t"], o["f0"], o["fft_size"], threshold=0.85)) <= M.TOL_AP_ABS
     y_ref = reference_lib.synthesis(o["f0"], o["sp"], o["ap"], o["fft_size"], 5.0, fs)
     assert M.snr_db(y_ref, wb.synthesis(o["f0"], o["sp"], o["ap"], o["fft_size"], 5.0, fs)) >= M.TOL_SNR_DB
+
+
+def test_concurrent_callers(wb):
+    """the replacement is thread-safe per call.  Two host threads call the drop-in CheapTrick /
+    D4C / Synthesis on different utterances at the same time (ctypes releases the GIL during the calls);
+    every result must be bit-identical to the same call made alone."""
+    import threading
+    gs = [load_golden("synthetic16k_u11"), load_golden("arctic_a0001")]
+    want = []
+    for g in gs:
+        x, fs = _x(g), int(g["fs"])
+        sp = wb.cheaptrick(x, fs, g["t"], g["f0"])
+        ap = wb.d4c(x, fs, g["t"], g["f0"], int(g["fft_size"]))
+        want.append((sp, ap, wb.synthesis(g["f0"], sp, ap, int(g["fft_size"]), 5.0, fs)))
+    errors = []
+
+    def worker(k):
+        try:
+            g = gs[k]
+            x, fs = _x(g), int(g["fs"])
+            for _ in range(4):
+                sp = wb.cheaptrick(x, fs, g["t"], g["f0"])
+                ap = wb.d4c(x, fs, g["t"], g["f0"], int(g["fft_size"]))
+                y = wb.synthesis(g["f0"], sp, ap, int(g["fft_size"]), 5.0, fs)
+                if not (np.array_equal(sp, want[k][0]) and np.array_equal(ap, want[k][1]) and np.array_equal(y, want[k][2])):
+                    errors.append("thread %d: result differs from the single-threaded call" % k)
+        except Exception as e:                      # noqa: BLE001
+            errors.append("thread %d: %r" % (k, e))
+
+    ths = [threading.Thread(target=worker, args=(k,)) for k in (0, 1, 0, 1)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errors, errors

@@ -103,7 +103,8 @@ def test_corpus_driver_writes_the_tools_files(tmp_path):
     clipped.astype("<i2").tofile(str(raw_dir / "clipped.raw"))
     (raw_dir / "empty.raw").write_bytes(b"")
     paths = sorted(str(p) for p in raw_dir.glob("*.raw"))
-    rep = driver.extract_features(paths, str(tmp_path), fs=fs, log=lambda *_: None)
+    # batches of ~1 s: three batches go through the reader / GPU / writer pipeline with alternating buffer sets
+    rep = driver.extract_features(driver.raw_source(paths), str(tmp_path), fs=fs, log=lambda *_: None, batch_seconds=1.0)
     assert sorted(rep["skipped"]) == ["clipped", "empty"] and sorted(rep["done"]) == ["utt0", "utt1", "utt2"]
     assert not (tmp_path / "lf0" / "clipped.lf0").exists()
     n_voiced = 0
@@ -124,6 +125,14 @@ def test_corpus_driver_writes_the_tools_files(tmp_path):
         assert np.max(np.abs(bap_r[np.repeat(same, 24)] - bap_b[np.repeat(same, 24)])) <= 1.15e-3 * np.sqrt(512)
         n_voiced += int((lf0_b != 0).sum())
     assert rep["stats"][0, 0] == n_voiced
+    # --resume: nothing is recomputed, and the statistics of the existing files equal the device's partials
+    mtime = os.path.getmtime(str(tmp_path / "mgc" / "utt1.mgc"))
+    rep2 = driver.extract_features(driver.raw_source(paths), str(tmp_path), fs=fs, log=lambda *_: None, resume=True)
+    assert sorted(rep2["resumed"]) == ["utt0", "utt1", "utt2"] and rep2["done"] == []
+    assert os.path.getmtime(str(tmp_path / "mgc" / "utt1.mgc")) == mtime
+    s2, g2 = driver.stats_from_files(str(tmp_path), rep2["resumed"], 50, 24)
+    assert np.array_equal(s2[:, 0], rep["stats"][:, 0]) and np.allclose(s2[:, 1:], rep["stats"][:, 1:], rtol=1e-9, atol=1e-9)
+    assert np.array_equal(g2[:, 0], rep["gv"][:, 0]) and np.allclose(g2[:, 1:], rep["gv"][:, 1:], rtol=1e-5)
 
 
 @pytest.mark.gpu
@@ -141,7 +150,7 @@ def test_corpus_driver_composes_cmp_files(tmp_path):
     for i, d in enumerate([0.5, 0.8]):
         signals.make_utterance(90 + i, fs, duration=d)[0].numpy().astype("<i2").tofile(str(raw_dir / ("u%d.raw" % i)))
     paths = sorted(str(p) for p in raw_dir.glob("*.raw"))
-    rep = driver.extract_features(paths, str(tmp_path), fs=fs, log=lambda *_: None, cmp=True)
+    rep = driver.extract_features(driver.raw_source(paths), str(tmp_path), fs=fs, log=lambda *_: None, cmp=True)
     total = 0
     acc = np.zeros((3 * 75, 2))
     for base in ("u0", "u1"):

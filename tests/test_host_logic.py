@@ -95,10 +95,23 @@ lengths = rng.integers(1000, 5000, size=40)
 mine = corpus.shard_utterances(lengths, rank, 2)
 vals = [np.log(100.0 + u + np.arange(lengths[u] // 100)) for u in mine]
 loc = np.array([sum(len(v) for v in vals), sum(v.sum() for v in vals), sum((v * v).sum() for v in vals)])
+loc_mine = loc.copy()                       # (allreduce_stats reduces in place)
 m = corpus.allreduce_stats(loc)
 allv = np.concatenate([np.log(100.0 + u + np.arange(lengths[u] // 100)) for u in range(40)])
 assert m["count"] == len(allv), (m, len(allv))
 assert np.isclose(m["mean"], allv.mean()) and np.isclose(m["var"], allv.var())
+# the corpus driver's single all-reduce of all partials (feature statistics + global-variance partials):
+# every rank holds the per-utterance variances of its shard, the merged result is the variance of all of them
+from hts_train_world_b200 import driver
+per = np.stack([np.array([np.var(np.sin(np.arange(50 + u) * (0.1 + 0.01 * k))) for k in range(4)]) for u in range(40)])
+mine_v = per[mine].astype(np.float32).astype(np.float64)
+gv_part = np.stack([np.full(4, float(len(mine_v))), mine_v.sum(axis=0), (mine_v * mine_v).sum(axis=0)], axis=1)
+stats_part = np.stack([loc_mine, loc_mine * 2.0])
+got = driver.all_reduce_partials([stats_part, gv_part])
+assert got[0].shape == (2, 3) and np.isclose(got[0][0, 0], len(allv)) and np.isclose(got[0][1, 1], 2.0 * allv.sum())
+mean, var = corpus.merge_gv([got[1]])
+allp = per.astype(np.float32).astype(np.float64)
+assert np.allclose(mean, allp.mean(axis=0)) and np.allclose(var, allp.var(axis=0), rtol=1e-9, atol=1e-18)
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
