@@ -162,6 +162,7 @@ def lib():
         "wb200_batch_get_coded": (i32, [vp, vp, vp, vp]),
         "wb200_batch_get_coded_async": (i32, [vp, vp, vp, vp]),
         "wb200_batch_decode_mgc": (i32, [vp, i32, i32, vp]),
+        "wb200_batch_set_coded_f32": (i32, [vp, i32, i32, i32, vp, vp, vp]),
         "wb200_batch_feature_stats": (i32, [vp, _dp]),
         "wb200_batch_gv_stats": (i32, [vp, vp, vp]),
         "wb200_batch_compose_cmp": (i32, [vp, C.POINTER(CmpStream), i32]),
@@ -543,6 +544,15 @@ class Corpus:
         mgc = np.ascontiguousarray(mgc, np.float32)
         self.fft_size = int(fft_size)
         _check(lib().wb200_batch_decode_mgc(self._h, self.fft_size, mgc.shape[1], mgc.ctypes.data), "decode_mgc")
+
+    def set_coded_f32(self, fft_size, lf0=None, mgc=None, bap=None):
+        """The coded branch of the synth tool (include/world_b200.h): float32 lf0 / mgc / bap -> f0 / sp / ap."""
+        self.fft_size = int(fft_size)
+        arrs = [None if a is None else np.ascontiguousarray(a, np.float32) for a in (lf0, mgc, bap)]
+        mgc_dim = arrs[1].shape[1] if arrs[1] is not None else 0
+        bap_dim = arrs[2].shape[1] if arrs[2] is not None else 0
+        ptrs = [None if a is None else a.ctypes.data for a in arrs]
+        _check(lib().wb200_batch_set_coded_f32(self._h, self.fft_size, mgc_dim, bap_dim, *ptrs), "set_coded_f32")
 
     def feature_stats(self):
         """[(1 + mgc_dim), 3] = {count, sum, sum of squares}: row 0 voiced lf0, rows 1.. mgc dims."""

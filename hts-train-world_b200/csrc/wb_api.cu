@@ -789,6 +789,35 @@ int wb200_batch_decode_mgc(wb200_batch* h, int fft_size, int mgc_dim, const floa
   WB_LAUNCH_CHECK();
   return WB_CUDA(cudaStreamSynchronize(c->stream)) ? 0 : 1;
 }
+// The coded branch of the synth tool (W/test/synth.cpp:171-247, spec_dimension != 0): float32 lf0 / mgc / bap
+// files -> f0 = exp(lf0) (0 stays 0), sp = DecodeSpectralEnvelope(mgc with c0 - 12) / 1e4, ap = exp(mgc2sp(bap
+// with c0 + 9.210340)) / 1e4.  Any pointer may be NULL (that parameter of the batch is left as it is).
+int wb200_batch_set_coded_f32(wb200_batch* h, int fft_size, int mgc_dim, int bap_dim, const float* lf0, const float* mgc,
+                              const float* bap) {
+  ApiGuard api_guard;
+  Context* c = ctx();
+  if (!c) return 1;
+  Batch& b = h->b;
+  if (fft_size < 32 || (fft_size & (fft_size - 1))) { set_error("set_coded_f32: fft_size %d", fft_size); return 1; }
+  const size_t F = (size_t)b.total_frames, H = (size_t)(fft_size / 2 + 1);
+  if (mgc && wb200_batch_decode_mgc(h, fft_size, mgc_dim, mgc)) return 1;
+  b.fft_size = fft_size;
+  DevBuf<float> stage;
+  if (lf0) {
+    if (!stage.alloc(F + 1)) return 1;
+    if (F > 0 && (!WB_CUDA(cudaMemcpyAsync(stage.p, lf0, F * sizeof(float), cudaMemcpyHostToDevice, c->stream)) ||
+                  !lf0_to_f0_run(stage.p, (int)F, b.f0.p)))
+      return 1;
+  }
+  DevBuf<float> stage2;
+  if (bap) {
+    if (!stage2.alloc(F * bap_dim + 1) || !b.ap.alloc(F * H)) return 1;
+    if (F > 0 && (!WB_CUDA(cudaMemcpyAsync(stage2.p, bap, F * bap_dim * sizeof(float), cudaMemcpyHostToDevice, c->stream)) ||
+                  !bap_decode_run(stage2.p, (int)F, fft_size, bap_dim, b.ap.p)))
+      return 1;
+  }
+  return WB_CUDA(cudaStreamSynchronize(c->stream)) ? 0 : 1;
+}
 int wb200_batch_compose_cmp(wb200_batch* h, const wb200_cmp_stream* streams, int n_streams) {
   ApiGuard api_guard;
   if (!ctx() || !wait_downloads(h, kDlCoded)) return 1;

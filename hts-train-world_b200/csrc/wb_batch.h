@@ -83,6 +83,8 @@ bool codec_encode_run(const double* d_rows, int n_frames, int fs, int fft_size, 
                       double zero_floor, double c0_add, double* d_out, bool f32log = false);
 bool codec_decode_run(const double* d_coded, int n_frames, int fs, int fft_size, int ndim, double* d_rows);
 bool batch_code_features(Batch* b, int mgc_dim, int bap_dim);
+bool bap_decode_run(const float* d_bap, int n_frames, int fft_size, int bap_dim, double* d_rows);   // W/test/synth.cpp:221-247
+bool lf0_to_f0_run(const float* d_lf0, int n, double* d_f0);                                          // ToF0, W/test/synth.cpp:81-89
 bool batch_feature_stats(Batch* b, double* h_out);
 bool batch_gv_stats(Batch* b, double* h_per_utt, double* h_partials);
 

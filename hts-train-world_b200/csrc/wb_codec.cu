@@ -18,6 +18,7 @@
 #include <vector>
 #include "wb_batch.h"
 #include "wb_fft.cuh"
+#include "wb_zerocross.cuh"      // host_fft
 
 namespace wb {
 namespace {
@@ -277,6 +278,87 @@ gv_utterance_kernel(const float* __restrict__ mgc, const float* __restrict__ lf0
   }
 }
 
+
+// ---- the synth tool's decode of CODED aperiodicity (W/test/synth.cpp:221-247) ------------------------------
+// c[0] += 9.210340;  mgc2sp(c, m, 0.55, 0, x, y, fft_size)  =  freqt(c, m, c2, fft_size / 2, -0.55) followed by
+// x = Re FFT_fft_size(c2) (W/test/sptkfunctions.cpp:186-275; the gnorm / gc2gc / ignorm steps are the identity
+// for gamma = 0);  ap[j] = exp(x[j]) / 1e4.  The whole chain before the exponential is linear in c, so it is one
+// (fft_size / 2 + 1) x (m + 1) matrix B, built once on the host by running the reference's recursion on the unit
+// vectors and transforming the result: x = B c, 25 multiply-adds per bin instead of a 25 x 1024-step
+// sequential recursion and a transform per frame.  (Summation order differs from the recursion: 1e-15.)
+// The reference fills only the first m bins of a row (the rest is uninitialised) and, for an even
+// ap_dimension, reads one coefficient past the ones it loaded; here every bin gets exp(x[j]) / 1e4 and the
+// missing coefficient is 0.
+struct BapTables { int fft_size = 0, m = 0; DevBuf<double> B; };      // B[j][i], j <= fft_size / 2, i <= m
+std::map<std::pair<int, int>, BapTables*> g_bap;
+
+void host_freqt(const std::vector<double>& c1, int m2, double a, std::vector<double>* out) {   // sptkfunctions.cpp freqt
+  const int m1 = (int)c1.size() - 1;
+  const double b = 1 - a * a;
+  std::vector<double> g(m2 + 1, 0.0), d(m2 + 1, 0.0);
+  for (int i = -m1; i <= 0; ++i) {
+    g[0] = c1[-i] + a * (d[0] = g[0]);
+    if (1 <= m2) g[1] = b * d[0] + a * (d[1] = g[1]);
+    for (int j = 2; j <= m2; ++j) g[j] = d[j - 1] + a * ((d[j] = g[j]) - g[j - 1]);
+  }
+  *out = g;
+}
+
+BapTables* bap_tables(int fft_size, int m) {
+  auto it = g_bap.find({fft_size, m});
+  if (it != g_bap.end()) return it->second;
+  if (fft_size < 32 || (fft_size & (fft_size - 1)) || m < 1 || m > 255) { set_error("bap decode: fft_size %d / order %d", fft_size, m); return nullptr; }
+  const int H = fft_size / 2 + 1;
+  std::vector<double> B((size_t)H * (m + 1));
+  for (int i = 0; i <= m; ++i) {
+    std::vector<double> e(m + 1, 0.0), c2;
+    e[i] = 1.0;
+    host_freqt(e, fft_size / 2, -0.55, &c2);
+    std::vector<double> re(fft_size, 0.0), im(fft_size, 0.0);
+    for (int k = 0; k <= fft_size / 2; ++k) re[k] = c2[k];
+    host_fft(re, im);
+    for (int j = 0; j < H; ++j) B[(size_t)j * (m + 1) + i] = re[j];
+  }
+  BapTables* t = new BapTables();
+  t->fft_size = fft_size; t->m = m;
+  if (!t->B.alloc(B.size()) || !WB_CUDA(cudaMemcpy(t->B.p, B.data(), B.size() * sizeof(double), cudaMemcpyHostToDevice))) { delete t; return nullptr; }
+  g_bap[{fft_size, m}] = t;
+  return t;
+}
+
+constexpr int kBapFrames = 8;            // frames per CTA: a thread keeps its bin's row of B in registers
+template <int MAXM>
+__global__ void __launch_bounds__(256)
+bap_decode_kernel(const float* __restrict__ bap, int bap_dim, int m, int n_coef, const double* __restrict__ B, int H,
+                  int n_frames, double* __restrict__ ap_rows) {
+  __shared__ double c[kBapFrames][MAXM + 1];
+  const int f0 = blockIdx.x * kBapFrames;
+  for (int t = threadIdx.x; t < kBapFrames * (m + 1); t += blockDim.x) {
+    const int fr = t / (m + 1), i = t - fr * (m + 1);
+    double v = 0.0;
+    if (f0 + fr < n_frames && i < n_coef) v = static_cast<double>(bap[(size_t)(f0 + fr) * bap_dim + i]);   // ToDouble
+    if (i == 0) v += 9.210340;                                                                                 // :241
+    c[fr][i] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    double row[MAXM + 1];
+#pragma unroll
+    for (int i = 0; i <= MAXM; ++i) row[i] = i <= m ? B[(size_t)j * (m + 1) + i] : 0.0;
+    for (int fr = 0; fr < kBapFrames && f0 + fr < n_frames; ++fr) {
+      double x = 0.0;
+#pragma unroll
+      for (int i = 0; i <= MAXM; ++i) x += row[i] * c[fr][i];
+      ap_rows[(size_t)(f0 + fr) * H + j] = exp(x) / 1e4;                                                     // :244
+    }
+  }
+}
+
+__global__ void lf0_to_f0_kernel(const float* __restrict__ lf0, int n, double* __restrict__ f0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const double v = lf0[i]; f0[i] = v != 0.0 ? exp(v) : 0.0; }          // ToF0, W/test/synth.cpp:81-89
+}
+
 }  // namespace
 
 bool codec_encode_run(const double* d_rows, int n_frames, int fs, int fft_size, int ndim, double scale,
@@ -397,6 +479,32 @@ bool batch_gv_stats(Batch* b, double* h_per_utt, double* h_partials) {
       h_partials[3 * k] = cnt; h_partials[3 * k + 1] = sum; h_partials[3 * k + 2] = sq;
     }
   }
+  return true;
+}
+
+// coded aperiodicity [n_frames][bap_dim] float32 (device) -> aperiodicity rows [n_frames][fft_size/2+1]
+bool bap_decode_run(const float* d_bap, int n_frames, int fft_size, int bap_dim, double* d_rows) {
+  Context* c = ctx();
+  if (!c) return false;
+  if (n_frames <= 0) return true;
+  const int m = (bap_dim % 2 == 1) ? bap_dim - 1 : bap_dim;          // W/test/synth.cpp:221-223, 242
+  BapTables* t = bap_tables(fft_size, m);
+  if (!t) return false;
+  const int H = fft_size / 2 + 1, n_coef = std::min(bap_dim, m + 1);
+  const int grid = (n_frames + kBapFrames - 1) / kBapFrames;
+  KernelTimer kt("bap_decode_kernel");
+  if (m <= 32) bap_decode_kernel<32><<<grid, 256, 0, c->stream>>>(d_bap, bap_dim, m, n_coef, t->B.p, H, n_frames, d_rows);
+  else if (m <= 64) bap_decode_kernel<64><<<grid, 256, 0, c->stream>>>(d_bap, bap_dim, m, n_coef, t->B.p, H, n_frames, d_rows);
+  else { set_error("bap decode: order %d (<= 64 supported)", m); return false; }
+  WB_LAUNCH_CHECK(); kt.stop();
+  return true;
+}
+bool lf0_to_f0_run(const float* d_lf0, int n, double* d_f0) {
+  Context* c = ctx();
+  if (!c) return false;
+  if (n <= 0) return true;
+  lf0_to_f0_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_lf0, n, d_f0);
+  WB_LAUNCH_CHECK();
   return true;
 }
 

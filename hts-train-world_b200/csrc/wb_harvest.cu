@@ -159,31 +159,69 @@ __global__ void harvest_mean_kernel(const double* __restrict__ y_all, const long
 }
 
 // ---- 2. raw candidates per (utterance, channel, 1 ms frame) (:240-293) ---------------------------
-__global__ void harvest_raw_kernel(const double* __restrict__ edges, const long long* __restrict__ list_off,
-                                   const int* __restrict__ list_cnt, const int* __restrict__ g_off,
-                                   const int* __restrict__ g_len, const double* __restrict__ boundary,
-                                   HarvestConst c, int utt0, const long long* __restrict__ raw_off,
-                                   double* __restrict__ raw) {
+// One CTA = 128 consecutive 1 ms frames of one (utterance, channel).  Every frame interpolates the four
+// interval contours at its time: a binary search over the edge list each.  The frames of a CTA span 128 ms,
+// i.e. a handful to ~120 consecutive knots of each list, so the CTA first finds that range once (one thread
+// per list), copies the edges of the range into shared memory, and the frames search there -- ~10 dependent
+// L2 round trips per frame and list became one per CTA and list.
+constexpr int kRawWin = 224;                 // edges per list kept in shared memory (a CTA needs <= ~125)
+__global__ void __launch_bounds__(128)
+harvest_raw_kernel(const double* __restrict__ edges, const long long* __restrict__ list_off,
+                   const int* __restrict__ list_cnt, const int* __restrict__ g_off,
+                   const int* __restrict__ g_len, const double* __restrict__ boundary,
+                   HarvestConst c, int utt0, const long long* __restrict__ raw_off,
+                   double* __restrict__ raw) {
+  __shared__ double win[4][kRawWin];
+  __shared__ int w_g0[4], w_lo[4], w_hi[4], w_nint[4], w_ok;
   const int u_local = blockIdx.y / c.nch, ch = blockIdx.y % c.nch;
   const int u = utt0 + u_local;
   const int n_fr = g_len[u];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_fr) return;
+  const int i0 = blockIdx.x * blockDim.x;
+  if (i0 >= n_fr) return;
+  const int i = i0 + threadIdx.x;
   const size_t l0 = ((size_t)u_local * c.nch + ch) * 4;
-  int n_int[4];
-  bool ok = true;
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const int cnt = list_cnt[l0 + t];
-    n_int[t] = cnt < 2 ? 0 : cnt - 1;
-    ok = ok && (n_int[t] - 2 > 0);             // CheckEvent (:262-269)
+  const int i_last = min(n_fr, i0 + (int)blockDim.x) - 1;
+  if (threadIdx.x == 0) w_ok = 1;
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    const int q = threadIdx.x;
+    const int cnt = list_cnt[l0 + q];
+    const int n_int = cnt < 2 ? 0 : cnt - 1;
+    w_nint[q] = n_int;
+    if (!(n_int - 2 > 0)) atomicAnd(&w_ok, 0);       // CheckEvent (:262-269)
+    else {
+      const double* __restrict__ e = edges + list_off[l0 + q];
+      const int lo = zc_upper_bound(e, 0, n_int, c.actual_fs, div_rn((double)i0, 1000.0));
+      const int hi = zc_upper_bound(e, lo, n_int, c.actual_fs, div_rn((double)i_last, 1000.0));
+      w_lo[q] = lo; w_hi[q] = hi;
+      w_g0[q] = max(0, min(lo, n_int - 1) - 1);      // lowest edge any frame of the CTA reads: e[k - 1], k = clamp(ub, 1, n_int - 1)
+    }
   }
+  __syncthreads();
+  const bool ok = w_ok != 0;
+  bool fits = true;
+  if (ok) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int g1 = min(w_nint[q], max(1, min(w_hi[q], w_nint[q] - 1)) + 1);   // highest edge read: e[k + 1]
+      const int n = g1 - w_g0[q] + 1;
+      fits = fits && n <= kRawWin;
+      if (n <= kRawWin) {
+        const double* __restrict__ e = edges + list_off[l0 + q] + w_g0[q];
+        for (int j = threadIdx.x; j < n; j += blockDim.x) win[q][j] = e[j];
+      }
+    }
+  }
+  __syncthreads();
+  if (i >= n_fr) return;
   double cd = 0.0;
   if (ok) {
     const double t = div_rn((double)i, 1000.0);          // i * 1 / 1000.0 (:1176)
     double v[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = zc_interp(edges + list_off[l0 + q], n_int[q], c.actual_fs, t);
+    for (int q = 0; q < 4; ++q)
+      v[q] = fits ? zc_interp_window(win[q], w_g0[q], w_lo[q], w_hi[q], w_nint[q], c.actual_fs, t)
+                  : zc_interp(edges + list_off[l0 + q], w_nint[q], c.actual_fs, t);
     cd = div_rn(add_rn(add_rn(add_rn(v[0], v[1]), v[2]), v[3]), 4.0);
     const double bf = boundary[ch];
     if (cd > mul_rn(bf, 1.1) || cd < mul_rn(bf, 0.9) || cd > c.f0_ceil || cd < c.f0_floor) cd = 0.0;   // :243-253

@@ -171,6 +171,25 @@ __device__ __forceinline__ bool zc_loc_le(const double* __restrict__ e, int i, d
   if (-r > fs * t * 4.5e-16) return false;
   return div_rn(s, fs) <= t;
 }
+// first knot of e[0 .. n_int] whose location exceeds t (upper_bound), searched in [lo, hi)
+__device__ __forceinline__ int zc_upper_bound(const double* __restrict__ e, int lo, int hi, double fs, double t) {
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (zc_loc_le(e, mid, fs, t)) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+// interp1 at t when the upper bound is known to lie in [lo, hi] and the edges e[g0 ..] sit in `win`
+// (shared memory): the same arithmetic as zc_interp on the same values.
+__device__ __forceinline__ double zc_interp_window(const double* win, int g0, int lo, int hi, int n_int, double fs, double t) {
+  const double* e = win - g0;                 // e[i] for i in the window
+  const int ub = zc_upper_bound(e, lo, hi, fs, t);
+  const int k = max(1, min(n_int - 1, ub));
+  const double x0 = zc_loc(e, k - 1, fs), x1 = zc_loc(e, k, fs);
+  const double y0 = zc_val(e, k - 1, fs), y1 = zc_val(e, k, fs);
+  const double sfrac = div_rn(add_rn(t, -x0), add_rn(x1, -x0));
+  return add_rn(y0, mul_rn(sfrac, add_rn(y1, -y0)));
+}
 __device__ inline double zc_interp(const double* __restrict__ e, int n_int, double fs, double t) {
   int lo = 0, hi = n_int;                 // upper_bound: first knot with loc > t
   while (lo < hi) {

@@ -134,6 +134,15 @@ WORLD_API int wb200_batch_get_coded_async(wb200_batch *b, float *host_lf0, float
 /* decode mgc back into the batch's spectrogram (DecodeSpectralEnvelope, then the inverse of the
  * tool's scalings): the entry of Synthesis-only runs that start from float32 mgc files */
 WORLD_API int wb200_batch_decode_mgc(wb200_batch *b, int fft_size, int mgc_dim, const float *host_mgc);
+/* the coded branch of the synth tool (W/test/synth.cpp:171-247, spec_dimension != 0) for the whole batch: float32
+ * lf0 [frames], mgc [frames][mgc_dim], bap [frames][bap_dim] as the analysis tool writes them -> f0 = exp(lf0) (0
+ * stays 0), spectrogram = DecodeSpectralEnvelope(mgc with c0 - 12) / 1e4, aperiodicity = exp(mgc2sp(bap with
+ * c0 + 9.210340, order bap_dim or bap_dim - 1 when odd, alpha 0.55, gamma 0)) / 1e4 (W/test/sptkfunctions.cpp
+ * :186-275).  The reference fills only the first `order` bins of an aperiodicity row and, for an even bap_dim,
+ * reads one coefficient past its buffer; here every bin is defined by the same formula and the missing
+ * coefficient is 0.  Any pointer may be NULL.  The entry of Synthesis-only runs from coded files (config 4). */
+WORLD_API int wb200_batch_set_coded_f32(wb200_batch *b, int fft_size, int mgc_dim, int bap_dim,
+                                        const float *host_lf0, const float *host_mgc, const float *host_bap);
 /* per-GPU partials of the corpus statistics: out[(1 + mgc_dim)][3] = {count, sum, sum of squares}
  * of voiced lf0 (row 0) and of every mgc dimension over all frames (rows 1..mgc_dim); the NCCL
  * all-reduce of these rows gives the corpus mean / variance */
