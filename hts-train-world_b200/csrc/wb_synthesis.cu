@@ -548,11 +548,7 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
       const size_t row = ci.row0 + ((r & 1) ? ci.fr_ceil : ci.fr_floor);
       const char* ptr = reinterpret_cast<const char*>(((r & 2) ? ap_all : sp_all) + row * (half + 1)) + (size_t)(i % lines) * 128;
 #ifndef WB_HOST_EMU
-#ifdef WB_SYNTH_PF_L1
-      asm volatile("prefetch.global.L1 [%0];" :: "l"(ptr));
-#else
-      asm volatile("prefetch.global.L2 [%0];" :: "l"(ptr));
-#endif
+      asm volatile("prefetch.global.L2 [%0];" :: "l"(ptr));      // (an L1 prefetch measured the same)
 #endif
     }
   }
