@@ -32,7 +32,11 @@ extern "C" int emu_d4c(const double* x, int x_len, int fs, const double* t, cons
   c.nbands = static_cast<int>(fmin(kUpperLimit, fs / 2.0 - kFrequencyInterval) / kFrequencyInterval);
   c.window_length = static_cast<int>(kFrequencyInterval * nd / fs) * 2 + 1;
   c.sel_boundary = matlab_round(nd * 8.0 / c.window_length);
-  for (int i = 0; i < c.nbands; ++i) c.centers[i] = static_cast<int>(kFrequencyInterval * (i + 1) * nd / fs);
+  c.band_top = 0;
+  for (int i = 0; i < c.nbands; ++i) {
+    c.centers[i] = static_cast<int>(kFrequencyInterval * (i + 1) * nd / fs);
+    c.band_top = std::max(c.band_top, c.centers[i] - c.window_length / 2 + c.window_length - 1);
+  }
   c.lt_b0 = static_cast<int>(ceil(100.0 * nlt / fs));
   c.lt_b1 = static_cast<int>(ceil(4000.0 * nlt / fs));
   c.lt_b2 = static_cast<int>(ceil(7900.0 * nlt / fs));
