@@ -551,6 +551,27 @@ def ours_arm(args):
         audio_total = audio_s
     value = audio_total * args.steps / (ms * 1e-3)
 
+    if os.environ.get("WB_STEP_TRACE"):       # developer aid: wall time of every call of one resident step (stream drained in between)
+        def traced(name, fn):
+            torch.cuda.synchronize()
+            t_a = time.perf_counter()
+            r = fn()
+            torch.cuda.synchronize()
+            sys.stderr.write("[step] %-18s %8.2f ms\n" % (name, 1e3 * (time.perf_counter() - t_a)))
+            return r
+        for _ in range(2):
+            traced("set_pcm16_device", lambda: c.set_pcm16_device(pcm_dev))
+            if args.f0 == "harvest":
+                traced("harvest", c.harvest)
+            else:
+                traced("dio", c.dio)
+                traced("stonemask", c.stonemask)
+            traced("cheaptrick", c.cheaptrick)
+            traced("d4c", lambda: c.d4c(threshold=0.0))
+            traced("code", lambda: c.code(MGC_DIM, BAP_DIM))
+            traced("synthesis", c.synthesis)
+            traced("feature_stats", c.feature_stats)
+
     # ---- end to end from host memory --------------------------------------------------------------
     step_e2e()
     step_e2e(more_to_come=False)

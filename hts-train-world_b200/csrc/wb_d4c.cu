@@ -573,7 +573,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
           return z;
         };
         fft_first_pass_from<K0, false, LOG2ND, THREADS>(cbuf, load);
-        __syncthreads();
+        fft_sync_after<LOG2ND, MAXK, 0, THREADS>();
         fft_run_passes<LOG2ND, MAXK, 1, false, THREADS, TWL>(cbuf, tw);
       } else {
         for (int i = tid; i < Nd; i += T) {

@@ -77,10 +77,76 @@ __device__ __forceinline__ C rot16(C v, int e16) {
   }
 }
 
-// One pass of K radix-2 stages on 2^K points held in registers.  The K twiddles of the group
-// (W_{2^(STAGE+t+1)}^j, t < K) are loaded once; the other butterflies of a sub-stage use the
-// same twiddle times a multiple of 22.5 degrees (a constant).  The first pass (STAGE 0) has
-// j = 0 for every group and needs no table twiddle at all.
+// ---- butterflies in fused multiply-add form ------------------------------------------------------
+// a <- a + W b, b <- a - W b with SIX fused multiply-adds (Linzer & Feig): the sum is two FMAs per
+// component and the difference is 2a - (a + W b), one more.  The plain form (complex product, then
+// add and subtract) is eight instructions, four of them additions the FMA pipe cannot fuse; in FP64
+// every instruction is two issue cycles of the half-rate pipe, so this is -25 % on the arithmetic of
+// every twiddled pass.  The rounding of the difference is relative to |a + W b| instead of |a - W b|:
+// the same absolute bound (one ulp of the larger of the two) the usual FFT error analysis assumes.
+template <typename C>
+__device__ __forceinline__ void bfly_w(C& a, C& b, const C W) {
+  using R = scalar_t<C>;
+  const R px = fma(W.x, b.x, fma(-W.y, b.y, a.x));
+  const R py = fma(W.x, b.y, fma(W.y, b.x, a.y));
+  b = mk2(fma(static_cast<R>(2), a.x, -px), fma(static_cast<R>(2), a.y, -py));
+  a = mk2(px, py);
+}
+// the same with W = exp(-/+ 2 pi i e16 / 16), a compile-time constant: multiples of a quarter turn
+// are plain additions, everything else the six-FMA form with constant operands
+template <bool INV, typename C>
+__device__ __forceinline__ void bfly_const(C& a, C& b, int e16) {
+  using R = scalar_t<C>;
+  if (e16 == 0 || e16 == 4) {
+    const C x = rot16<INV>(b, e16);
+    b = csub(a, x);
+    a = cadd(a, x);
+  } else {
+    bfly_w(a, b, rot16<INV>(mk2(static_cast<R>(1), static_cast<R>(0)), e16));
+  }
+}
+
+// Stage T_ of a pass on 2^K points in registers.  Butterfly (m, m + 2^T_) multiplies its second input
+// by W_j = w[T_] exp(-/+ 2 pi i j / 2^(T_+1)), j = m mod 2^T_: the group's twiddle times a multiple of
+// 22.5 degrees.  The W_j of a stage are formed ONCE (a constant rotation of the twiddle: 4 operations,
+// and none at all for the second half, which is the first half times -/+ i) and each butterfly is
+// then six FMAs; the first pass has w = 1 and its W_j are constants.
+template <int T_, int K, bool INV, bool FIRST, typename C>
+__device__ __forceinline__ void fft_stage(C (&v)[1 << K], const C* w) {
+  constexpr int R = 1 << K, span = 1 << T_;
+  if constexpr (FIRST) {
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      if (m & span) continue;
+      bfly_const<INV>(v[m], v[m + span], (m & (span - 1)) * (8 >> T_));
+    }
+  } else {
+    C W[span];
+    W[0] = w[T_];
+#pragma unroll
+    for (int j = 1; j < span; ++j) {
+      const int e16 = j * (8 >> T_);
+      W[j] = e16 >= 4 ? rot16<INV>(W[j - span / 2 > 0 ? j - span / 2 : 0], 4) : rot16<INV>(w[T_], e16);
+    }
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      if (m & span) continue;
+      bfly_w(v[m], v[m + span], W[m & (span - 1)]);
+    }
+  }
+}
+template <int K, bool INV, bool FIRST, int T_ = 0, typename C>
+__device__ __forceinline__ void fft_stages(C (&v)[1 << K], const C* w) {
+  if constexpr (T_ < K) {
+    fft_stage<T_, K, INV, FIRST>(v, w);
+    fft_stages<K, INV, FIRST, T_ + 1>(v, w);
+  }
+}
+
+// One pass of K radix-2 stages on 2^K points held in registers.  The finest of the K twiddles of the
+// group (W_{2^(STAGE+t+1)}^j, t < K) is loaded, the coarser ones are its squares; the other butterflies
+// of a sub-stage use the same twiddle times a multiple of 22.5 degrees (fft_stage).  The first pass
+// (STAGE 0) has j = 0 for every group and needs no table twiddle at all.
 //
 // cpad() is additive over non-overlapping bit fields: the group base has zeros where
 // (m << STAGE) lives, hence cpad(base + (m << STAGE)) = cpad(base) + cpad(m << STAGE).
@@ -112,20 +178,7 @@ __device__ __forceinline__ void fft_pass(C* __restrict__ s, const C* __restrict_
       for (int t = K - 2; t >= 0; --t)
         w[t] = mk2((w[t + 1].x - w[t + 1].y) * (w[t + 1].x + w[t + 1].y), (w[t + 1].x + w[t + 1].x) * w[t + 1].y);
     }
-#pragma unroll
-    for (int t = 0; t < K; ++t) {
-      const int span = 1 << t;
-#pragma unroll
-      for (int m = 0; m < R; ++m) {
-        if (m & span) continue;
-        C x = v[m + span];
-        if (!FIRST) x = cmul(w[t], x);
-        x = rot16<INV>(x, (m & (span - 1)) * (8 >> t));
-        const C a = v[m];
-        v[m] = cadd(a, x);
-        v[m + span] = csub(a, x);
-      }
-    }
+    fft_stages<K, INV, FIRST>(v, w);
 #pragma unroll
     for (int m = 0; m < R; ++m) sb[cpadT<C>(m << STAGE)] = v[m];
   }
@@ -150,18 +203,7 @@ __device__ __forceinline__ void fft_first_pass_from(C* __restrict__ s, LOAD load
     C v[R];
 #pragma unroll
     for (int m = 0; m < R; ++m) v[m] = load(base, m);
-#pragma unroll
-    for (int t = 0; t < K; ++t) {
-      const int span = 1 << t;
-#pragma unroll
-      for (int m = 0; m < R; ++m) {
-        if (m & span) continue;
-        const C x = rot16<INV>(v[m + span], (m & (span - 1)) * (8 >> t));
-        const C a = v[m];
-        v[m] = cadd(a, x);
-        v[m + span] = csub(a, x);
-      }
-    }
+    fft_stages<K, INV, true>(v, static_cast<const C*>(nullptr));
 #pragma unroll
     for (int m = 0; m < R; ++m) sb[cpadT<C>(m)] = v[m];
   }
@@ -175,12 +217,31 @@ template <int LOG2N, int MAXK> struct fft_plan {
   __host__ __device__ static constexpr int stage_of(int p) { return p * base + (p < extra ? p : extra); }
 };
 
+// The barrier behind pass PASS.  Passes 0 and 1 of equal radix 2^K touch the same slots FROM THE SAME WARP:
+// thread b owns slots [b 2^K, (b + 1) 2^K) in pass 0 and column (b mod 2^K) of the 2^2K-slot block b >> K
+// in pass 1, so the 32 threads of a warp cover the 32 * 2^K consecutive slots starting at 32 w 2^K both times
+// (every iteration of a multi-iteration pass likewise): a warp barrier orders them, the block barrier
+// (and the wait for the slowest warp of the CTA) is not needed there.
+template <int LOG2N, int MAXK, int PASS, int THREADS>
+__device__ __forceinline__ void fft_sync_after() {
+  using plan = fft_plan<LOG2N, MAXK>;
+  if constexpr (PASS == 0 && plan::P > 1 && plan::k_of(0) == plan::k_of(plan::P > 1 ? 1 : 0) && plan::k_of(0) <= 5 && THREADS % 32 == 0) {
+#ifdef WB_FFT_BLOCK_SYNC
+    __syncthreads();
+#else
+    __syncwarp();
+#endif
+  } else {
+    __syncthreads();
+  }
+}
+
 template <int LOG2N, int MAXK, int PASS, bool INV, int THREADS, int TWL = kTwLog2, typename C>
 __device__ __forceinline__ void fft_run_passes(C* s, const C* __restrict__ tw) {
   using plan = fft_plan<LOG2N, MAXK>;
   if constexpr (PASS < plan::P) {
     fft_pass<plan::k_of(PASS), INV, LOG2N, plan::stage_of(PASS), THREADS, TWL>(s, tw);
-    __syncthreads();
+    fft_sync_after<LOG2N, MAXK, PASS, THREADS>();
     fft_run_passes<LOG2N, MAXK, PASS + 1, INV, THREADS, TWL>(s, tw);
   }
 }

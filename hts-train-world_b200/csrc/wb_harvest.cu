@@ -29,6 +29,7 @@
 #include <algorithm>
 #include <map>
 #include <vector>
+#include <chrono>
 #include "wb_batch.h"
 #include "wb_fft.cuh"
 #include "wb_zerocross.cuh"
@@ -1165,6 +1166,16 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
   }
   c.nch = hb->nch;
   const int max_base = matlab_round(c.nch / 10.0);                                                // :1186-1187
+  // WB_HARVEST_TRACE=1: wall time of every phase of this call (stream drained at each mark) on stderr
+  static const bool trace = getenv("WB_HARVEST_TRACE") != nullptr;
+  auto t_mark = std::chrono::steady_clock::now();
+  auto phase = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(st);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[harvest] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_mark).count());
+    t_mark = now;
+  };
 
   // ---- per-utterance sizes: decimated length, 1 ms frame grid -------------------------------------
   std::vector<int> h_ylen(n_utt), h_glen(n_utt), h_goff(n_utt);
@@ -1199,6 +1210,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
   WB_CUDA_OR_RETURN(cudaMemsetAsync(d_nc.p, 0, n_utt * sizeof(int), st), false);
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
 
+  phase("tables");
   // ---- 1. decimation -----------------------------------------------------------------------------------
   if (c.r > 1) {
     if (!d_B.alloc(btot)) return false;
@@ -1215,6 +1227,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
   harvest_mean_kernel<<<n_utt, 256, 0, st>>>(d_y.p, d_yoff.p, d_ylen.p, d_mean.p);
   WB_LAUNCH_CHECK();
 
+  phase("decimation + mean");
   // ---- 2./3. band filtering, zero crossings, raw and base candidates, in sub-batches -------------------
   OlsConst oc = {hb->nch, hb->bn, hb->log2bn, hb->D, hb->V};
   const size_t smem = 2 * cpad_size(hb->bn / 2) * sizeof(double2);
@@ -1247,6 +1260,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
     const int n_lists = nu * c.nch * 4;
     if (!d_roff.alloc(nu) || !d_ltot.alloc(n_lists + 1) || !d_loff.alloc(n_lists) || !d_raw.alloc(rtot)) return false;
     if (!up(d_roff.p, h_roff.data(), nu * sizeof(long long))) return false;
+    phase("sub-batch: allocations");
     std::vector<int> h_ltot(n_lists + 1);
     std::vector<long long> h_loff(n_lists);
     bool fused_done = false;
@@ -1264,6 +1278,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
         return false;
       WB_CUDA_OR_RETURN(cudaMemsetAsync(d_segcnt.p, 0, (size_t)n_lists * n_blocks * sizeof(int), st), false);
       WB_CUDA_OR_RETURN(cudaMemsetAsync(d_ltot.p + n_lists, 0, sizeof(int), st), false);
+      phase("sub-batch: segment buffers");
       {
         KernelTimer kt("harvest_filter_kernel");
         if (hb->log2bn == 11)
@@ -1274,9 +1289,11 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
                                                                         ctxp->d_twiddle, ocz, hb->shift.p, u0, n_blocks, kCap, d_segcnt.p, d_seg.p);
         WB_LAUNCH_CHECK(); kt.stop();
       }
+      phase("sub-batch: filter + zc");
       zc_seg_scan_kernel<<<(n_lists + 127) / 128, 128, 0, st>>>(d_segcnt.p, n_lists, n_blocks, kCap, d_segoff.p, d_ltot.p, d_ltot.p + n_lists);
       WB_LAUNCH_CHECK();
       if (!read_back(h_ltot.data(), d_ltot.p, (n_lists + 1) * sizeof(int))) return false;
+      phase("sub-batch: seg scan + read");
       if (h_ltot[n_lists] == 0) {
         long long etot = 0;
         for (int l = 0; l < n_lists; ++l) { h_loff[l] = etot; etot += h_ltot[l]; }
@@ -1286,6 +1303,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
         zc_seg_gather_kernel<<<n_lists, 128, 0, st>>>(d_segcnt.p, d_segoff.p, d_seg.p, n_blocks, kCap, d_loff.p, d_edges.p);
         WB_LAUNCH_CHECK(); kt.stop();
         WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);  // the segment buffers die with this scope
+        phase("sub-batch: gather");
         fused_done = true;
       }
     }
@@ -1331,6 +1349,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
                                                                            d_base.p, d_nc.p);
     WB_LAUNCH_CHECK(); ktr.stop();
     WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);      // scratch buffers die with this scope
+    phase("sub-batch: raw + detect");
     u0 = u1;
   }
 
@@ -1352,6 +1371,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
       !d_cand2.alloc(ctot + 1) || !d_score2.alloc(ctot + 1))
     return false;
   if (!up(d_coff.p, h_coff.data(), n_utt * sizeof(long long)) || !up(d_wfirst.p, h_wfirst.data(), n_utt * sizeof(long long))) return false;
+  phase("candidate buffers");
   if (ctot > 0) {
     {
       KernelTimer kt("harvest_refine_kernel");
@@ -1374,6 +1394,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
   // bl_all is indexed by 2 * g_off[u]; the smoothing stage needs 2 * (g_len + 600) entries at most, and
   // sections are at least 1 frame apart, so 2 * g_off[u] + ... stays inside because g_len >= 602 is not
   // guaranteed: use a separate, padded offset table for the smoothing boundaries below.
+  phase("refine + unreliable");
   KernelTimer kta("harvest_fix_a_kernel");
   harvest_fix_a_kernel<<<n_utt, 256, 0, st>>>(d_cand2.p, d_score2.p, d_goff.p, d_glen.p, d_nc.p, d_coff.p, d_tmp1.p, d_tmp2.p, d_bl.p, d_nsec.p);
   WB_LAUNCH_CHECK(); kta.stop();
@@ -1442,6 +1463,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
     WB_LAUNCH_CHECK(); kt.stop();
     WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
   }
+  phase("contour logic");
   // smoothing: step4 is in tmp1; the smoothed basic contour goes to tmp2 (zero where unvoiced)
   WB_CUDA_OR_RETURN(cudaMemsetAsync(d_tmp2.p, 0, (size_t)gtot * sizeof(double), st), false);
   harvest_sections_kernel<<<n_utt, 32, 0, st>>>(d_tmp1.p, d_goff.p, d_glen.p, d_bl.p, d_nsec.p);
@@ -1476,6 +1498,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
     WB_LAUNCH_CHECK();
   }
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
+  phase("smoothing + pick");
   return true;
 }
 

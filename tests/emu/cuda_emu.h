@@ -117,6 +117,7 @@ inline void launch_grid(int gx, int gy, int threads, size_t smem_bytes, F body) 
 #define blockDim (::wbemu::b_dim)
 #define gridDim (::wbemu::g_dim)
 #define __syncthreads() ::wbemu::syncthreads()
+#define __syncwarp() ::wbemu::warp_bar[::wbemu::t_idx.x >> 5]->arrive_and_wait()
 #define __shfl_xor_sync(m, v, o) ::wbemu::shfl_xor((v), (o))
 #define __shfl_up_sync(m, v, o) ::wbemu::shfl_up((v), (o))
 #define __shfl_down_sync(m, v, o) ::wbemu::shfl_down((v), (o))
