@@ -320,44 +320,121 @@ __device__ __forceinline__ void select_low_sums(const float* __restrict__ P, int
   }
 }
 
-// The same quantity for ONE array held in the registers of ONE warp (compile-time sizes): the
-// K-th largest key is found by an MSB-first binary search on the bit pattern, each step one
-// register sweep (key >= candidate) plus a warp reduction -- no shared memory, no atomics and no
-// block barriers, so the bands of a frame are selected concurrently by different warps.  The
-// search stops as soon as exactly K keys lie at or above the candidate (then they are the top
-// set); otherwise it ends with T = the K-th largest key and the low set receives its surplus
-// copies of T.
+// The same quantity for ONE array handled by ONE warp (compile-time sizes): the K-th largest key is
+// found by an MSB-first binary search on the bit pattern, each step one register sweep (key >= candidate)
+// plus a warp reduction -- no shared memory traffic, no atomics and no block barriers, so the bands of a
+// frame are selected concurrently by different warps.  The search stops as soon as exactly K keys lie at
+// or above the candidate (then they are the top set); otherwise it ends with T = the K-th largest key and
+// the low set receives its surplus copies of T.
+//
+// Two phases.  (1) The upper 16 bits of a non-negative float are its bfloat16 truncation, and bfloat16
+// values order like their bit patterns, so the first 16 bits are decided on PACKED keys: two upper halves
+// per register, one HSET2.BF16 (two comparisons, 1.0 / 0.0 per half) and one HADD2.BF16 (two counters, exact
+// up to 256) per PAIR of keys and step -- a quarter of the issue cycles of the compare / predicated-add pair
+// per key of the 32-bit sweep, which ran on the half-rate integer pipe.  (2) Only when the K-th and the
+// (K+1)-th largest key share their upper half (a bucket 0.8 % wide) do the full keys come back from shared
+// memory and the search continues on bits 15 .. 0 with 32-bit sweeps; inside one bucket the lower bits are
+// as good as random, so this takes a few steps.
+__device__ __forceinline__ unsigned bf16x2_count_ge(unsigned acc, unsigned keys, unsigned cand2) {
+#ifdef WB_HOST_EMU
+  const unsigned lo = (keys & 0xffffu) >= (cand2 & 0xffffu), hi = (keys >> 16) >= (cand2 >> 16);
+  return acc + lo + (hi << 16);                       // plain integer counters on the host
+#else
+  unsigned m;
+  asm("set.ge.bf16x2.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(keys), "r"(cand2));
+  asm("add.rn.bf16x2 %0, %0, %1;" : "+r"(acc) : "r"(m));
+  return acc;
+#endif
+}
+__device__ __forceinline__ int bf16x2_counts_total(unsigned a0, unsigned a1, unsigned a2, unsigned a3) {
+#ifdef WB_HOST_EMU
+  const unsigned s = a0 + a1 + a2 + a3;
+  return (int)((s & 0xffffu) + (s >> 16));
+#else
+  unsigned s01, s23, s;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(s01) : "r"(a0), "r"(a1));
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(s23) : "r"(a2), "r"(a3));
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(s) : "r"(s01), "r"(s23));
+  return __float2int_rn(__uint_as_float(s << 16) + __uint_as_float(s & 0xffff0000u));
+#endif
+}
+
 template <int NPL>     // keys per lane: ceil(n / 32)
 __device__ __forceinline__ void warp_select_low_sum(const float* __restrict__ P, int n, int K,
                                                     double* low, double* tot) {
   const int lane = threadIdx.x & 31;
+  unsigned T = 0u;
+  int at_or_above = 32 * NPL;                 // keys >= T
+  bool exact = false;
+#ifndef WB_SELECT_32BIT
+  {
+    constexpr int NPK = (NPL + 1) / 2;
+    unsigned h[NPK];
+    unsigned mx = 0u;
+#pragma unroll
+    for (int j = 0; j < NPK; ++j) {
+      const int k0 = lane + 64 * j, k1 = k0 + 32;
+      const unsigned a = k0 < n ? __float_as_uint(P[k0]) : 0u;
+      const unsigned b = (2 * j + 1 < NPL && k1 < n) ? __float_as_uint(P[k1]) : 0u;
+      mx = max(mx, max(a, b));
+#ifdef WB_HOST_EMU
+      h[j] = (a >> 16) | (b & 0xffff0000u);
+#else
+      h[j] = __byte_perm(a, b, 0x7632);        // upper half of a | upper half of b
+#endif
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx) >> 16;
+    unsigned T16 = 0u;
+#pragma unroll 1
+    for (int bit = 31 - __clz(mx | 1u); bit >= 0; --bit) {      // higher bits: no key reaches the candidate
+      const unsigned cand = T16 | (1u << bit);
+      const unsigned cand2 = cand * 0x10001u;
+      unsigned c[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int j = 0; j < NPK; ++j) c[j & 3] = bf16x2_count_ge(c[j & 3], h[j], cand2);   // the pad keys are 0 < cand
+      const int cnt = __reduce_add_sync(0xffffffffu, bf16x2_counts_total(c[0], c[1], c[2], c[3]));
+      if (cnt >= K) {
+        T16 = cand;
+        at_or_above = cnt;
+        if (cnt == K) { exact = true; break; }
+      }
+    }
+    T = T16 << 16;
+  }
+#endif
   unsigned key[NPL];
 #pragma unroll
   for (int j = 0; j < NPL; ++j) {
     const int k = lane + 32 * j;
     key[j] = k < n ? __float_as_uint(P[k]) : 0u;
   }
+#ifdef WB_SELECT_32BIT
   unsigned mx = 0u;
 #pragma unroll
   for (int j = 0; j < NPL; ++j) mx = max(mx, key[j]);
   mx = __reduce_max_sync(0xffffffffu, mx);
-  unsigned T = 0u;
-  int at_or_above = 32 * NPL;                 // keys >= T
-  for (int bit = 31 - __clz(mx | 1u); bit >= 0; --bit) {      // higher bits: no key reaches the candidate
-    const unsigned cand = T | (1u << bit);
-    int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int j = 0; j < NPL; ++j)              // one compare and one predicated increment per key
-#ifdef WB_HOST_EMU
-      c[j & 7] += key[j] >= cand;
+  const int first_bit = 31 - __clz(mx | 1u);
 #else
-      asm("{.reg .pred p; setp.ge.u32 p, %1, %2; @p add.s32 %0, %0, 1;}" : "+r"(c[j & 7]) : "r"(key[j]), "r"(cand));
+  const int first_bit = 15;
 #endif
-    const int cnt = __reduce_add_sync(0xffffffffu, ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7])));
-    if (cnt >= K) {
-      T = cand;
-      at_or_above = cnt;
-      if (cnt == K) break;
+  if (!exact) {
+#pragma unroll 1
+    for (int bit = first_bit; bit >= 0; --bit) {
+      const unsigned cand = T | (1u << bit);
+      int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int j = 0; j < NPL; ++j)              // one compare and one predicated increment per key
+#ifdef WB_HOST_EMU
+        c[j & 7] += key[j] >= cand;
+#else
+        asm("{.reg .pred p; setp.ge.u32 p, %1, %2; @p add.s32 %0, %0, 1;}" : "+r"(c[j & 7]) : "r"(key[j]), "r"(cand));
+#endif
+      const int cnt = __reduce_add_sync(0xffffffffu, ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7])));
+      if (cnt >= K) {
+        T = cand;
+        at_or_above = cnt;
+        if (cnt == K) break;
+      }
     }
   }
   double a_tot = 0.0, a_low = 0.0;
@@ -455,23 +532,23 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
   auto write_row = [&]() {
     if (tid == 0) { coarse[0] = -60.0; coarse[c.nbands + 1] = -kMySafeGuardMinimum; }
     __syncthreads();
-    const int nk = c.nbands + 2;
+    // The row leaves as exp() of a single-precision argument (6e-8 relative, tolerance 1e-4 absolute), so the
+    // piecewise-linear interpolation over the knots {0, 3k, ..., 3k nbands, fs/2} runs in single precision
+    // as well: bin frequencies k fs / (2 out_half) and knots are exact there, the segment is found by one
+    // multiplication; when its rounding puts a bin that sits ON a knot into the segment before it, s is 1
+    // there and the interpolant is continuous.
     const int N_out = 2 * c.out_half;
+    const float bin_hz = (float)c.fs / (float)N_out, top_hz = 0.5f * (float)c.fs;
+    const float last_x0 = (float)(c.nbands * kFrequencyInterval);
+    const float inv_last = 1.0f / (top_hz - last_x0);
     for (int k = tid; k <= c.out_half; k += T) {
-      const double xi = mul_rn((double)k, (double)c.fs) / N_out;
-      int seg = 1;                                   // clamp(upper_bound(axis, xi), 1, nk-1)
-      while (seg < nk - 1) {
-        const double knot = seg <= c.nbands ? seg * kFrequencyInterval : c.fs / 2.0;
-        if (xi < knot) break;
-        ++seg;
-      }
-      const double x0 = (seg - 1) * kFrequencyInterval;
-      const double x1 = seg <= c.nbands ? seg * kFrequencyInterval : c.fs / 2.0;
-      const double s = (xi - x0) / (x1 - x0);
-      const double v = add_rn(coarse[seg - 1], mul_rn(s, coarse[seg] - coarse[seg - 1]));
-      // 10^(v/20) = e^(v ln(10)/20): the row is an aperiodicity in (0, 1], tolerance 1e-4 absolute -- the
-      // single-precision exponential (1 ulp, 6e-8 relative) costs a quarter of the double one
-      out[k] = static_cast<double>(expf(static_cast<float>(v * 0.11512925464970228420)));
+      const float xi = (float)k * bin_hz;
+      const int seg = min(c.nbands + 1, 1 + (int)(xi * (float)(1.0 / kFrequencyInterval)));   // clamp(upper_bound(axis, xi), 1, nk-1)
+      const float x0 = (float)(seg - 1) * (float)kFrequencyInterval;
+      const float s = (xi - x0) * (seg <= c.nbands ? (float)(1.0 / kFrequencyInterval) : inv_last);
+      const float y0 = (float)coarse[seg - 1], y1 = (float)coarse[seg];
+      const float v = fmaf(s, y1 - y0, y0);
+      out[k] = static_cast<double>(expf(v * 0.11512925464970228420f));      // 10^(v/20)
     }
   };
   // fs < 12 kHz: no 3 kHz band fits below fs/2 - 3 kHz (d4c.cpp:351-353), the reference still runs

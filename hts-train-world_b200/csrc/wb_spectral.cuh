@@ -99,12 +99,22 @@ static __device__ __noinline__ void linear_smoothing(const double* in, double* o
     __syncthreads();
     block_inclusive_scan(cum, len, red);
   }
-  const double origin_axis = -(boundary - 0.5) * fs / N;
+  // out[k] = (cum(k + c1) - cum(k + c0)) / width with cum() the linear interpolant of the running sum:
+  // the reference evaluates interp1Q at fa = k df - width / 2 on an axis that starts at -(boundary - 1/2) df,
+  // i.e. at the position k + boundary - 1/2 - width / (2 df) -- the SAME offset for every k.  Its integer
+  // part and fraction are therefore computed once per call instead of twice per bin (two double -> int
+  // conversions, two int -> double, four more FP64 operations each); the reference's own rounding of the
+  // position moves the fraction by ~1e-13, and where that crosses an integer the interpolant is continuous.
+  const double c0 = (boundary - 0.5) - 0.5 * width * inv_df;
+  const double c1 = c0 + width * inv_df;
+  const int i0 = static_cast<int>(c0), i1 = static_cast<int>(c1);      // c0 > 0: boundary > width / df
+  const double f0 = c0 - i0, f1 = c1 - i1;
   const double inv_width = 1.0 / width;
   for (int k = tid; k <= n_out; k += T) {
-    const double fa = add_rn(mul_rn((double)k * inv_n, (double)fs), -width / 2.0);
-    const double low = interp1q_at(origin_axis, inv_df, cum, len, fa);
-    const double high = interp1q_at(origin_axis, inv_df, cum, len, add_rn(fa, width));
+    const int b0 = min(len - 1, k + i0), b1 = min(len - 1, k + i1);   // memory guards (as interp1q_at)
+    const double l0 = cum[b0], h0 = cum[b1];
+    const double low = fma(b0 + 1 < len ? cum[b0 + 1] - l0 : 0.0, f0, l0);
+    const double high = fma(b1 + 1 < len ? cum[b1 + 1] - h0 : 0.0, f1, h0);
     out[k] = (high - low) * inv_width;
   }
   __syncthreads();
