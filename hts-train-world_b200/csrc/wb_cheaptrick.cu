@@ -128,14 +128,7 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
   // DCCorrection (common.cpp:56-75)
   const double inv_df = (double)N / fs;
   const double inv_n = 1.0 / N;                 // N is a power of two: x * inv_n == x / N exactly
-  {
-    const int upper_limit = 2 + static_cast<int>(mul_rn(f0c, (double)N) / fs);
-    for (int i = tid; i < upper_limit - 1; i += T)
-      bufd[i] = interp1q_at(f0c, -inv_df, aux, upper_limit + 1, mul_rn((double)i, (double)fs) * inv_n);
-    __syncthreads();
-    for (int i = tid; i < upper_limit - 1; i += T) aux[i] += bufd[i];
-    __syncthreads();
-  }
+  dc_correction<true>(aux, bufd, f0c, fs, N);
   // ---- LinearSmoothing (common.cpp:77-111), width = f0 * 2 / 3 ------------------------------
   const double width = f0c * 2.0 / 3.0;
   const int len = half + 2 * boundary + 1;
@@ -151,13 +144,19 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
     block_inclusive_scan(bufd, len, red);
   }
   {
-    const double origin_axis = -(boundary - 0.5) * fs / N;
+    // (cum(k + c1) - cum(k + c0)) / width: the offsets of the two interpolation points are the same for every
+    // bin (wb_spectral.cuh, linear_smoothing), so their integer parts and fractions are computed once
+    const double c0 = (boundary - 0.5) - 0.5 * width * inv_df;
+    const double c1 = c0 + width * inv_df;
+    const int i0 = static_cast<int>(c0), i1 = static_cast<int>(c1);
+    const double fr0 = c0 - i0, fr1 = c1 - i1;
     const double inv_width = 1.0 / width;
     const uint32_t* __restrict__ rn2 = rn + W;
     for (int k = tid; k <= half; k += T) {
-      const double fa = add_rn(mul_rn((double)k * inv_n, (double)fs), -width / 2.0);
-      const double low = interp1q_at(origin_axis, inv_df, bufd, len, fa);
-      const double high = interp1q_at(origin_axis, inv_df, bufd, len, add_rn(fa, width));
+      const int b0 = min(len - 1, k + i0), b1 = min(len - 1, k + i1);
+      const double l0 = bufd[b0], h0 = bufd[b1];
+      const double low = fma(b0 + 1 < len ? bufd[b0 + 1] - l0 : 0.0, fr0, l0);
+      const double high = fma(b1 + 1 < len ? bufd[b1 + 1] - h0 : 0.0, fr1, h0);
       const double sm = (high - low) * inv_width;
       // AddInfinitesimalNoise (:147-151) then log (:38-39)
       // the logarithm feeds the FP32 liftering transforms: FP32 accuracy is all that survives

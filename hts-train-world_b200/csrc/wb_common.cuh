@@ -133,8 +133,18 @@ struct DevBuf {
   }
   void release() { free(p); p = nullptr; n = 0; }
 #else
-    if (!WB_CUDA(cudaMallocFromPoolAsync((void**)&p, count * sizeof(T), scratch_pool(), pool_stream()))) { p = nullptr; n = 0; return false; }
-    n = count;
+    // Sizes of 1 MiB and more are rounded up to four significant bits (< 12.5 % more): the data-dependent
+    // scratch sizes of consecutive batches then repeat, and a freed block of the pool fits the next request
+    // instead of the pool growing by a slightly larger block every call.
+    size_t bytes = count * sizeof(T);
+    if (bytes >= ((size_t)1 << 20)) {
+      int msb = 63;
+      while (!((bytes >> msb) & 1)) --msb;
+      const size_t q = (size_t)1 << (msb - 3);
+      bytes = (bytes + q - 1) & ~(q - 1);
+    }
+    if (!WB_CUDA(cudaMallocFromPoolAsync((void**)&p, bytes, scratch_pool(), pool_stream()))) { p = nullptr; n = 0; return false; }
+    n = bytes / sizeof(T);
     return true;
   }
   void release() { if (p) cudaFreeAsync(p, pool_stream()); p = nullptr; n = 0; }

@@ -437,12 +437,21 @@ __device__ __forceinline__ void warp_select_low_sum(const float* __restrict__ P,
       }
     }
   }
+  // sums: groups of 8 keys are added in single precision (relative error <= 4 ulp of a float, the size of the
+  // rounding of the FP32 transform that produced the powers), the groups in double -- one conversion and two
+  // FP64 additions per 8 keys instead of per key
   double a_tot = 0.0, a_low = 0.0;
 #pragma unroll
-  for (int j = 0; j < NPL; ++j) {
-    const double v = (double)__uint_as_float(key[j]);
-    a_tot += v;
-    if (key[j] < T) a_low += v;
+  for (int j0 = 0; j0 < NPL; j0 += 8) {
+    float g_tot = 0.f, g_low = 0.f;
+#pragma unroll
+    for (int j = j0; j < j0 + 8 && j < NPL; ++j) {
+      const float v = __uint_as_float(key[j]);
+      g_tot += v;
+      g_low += key[j] < T ? v : 0.f;
+    }
+    a_tot += (double)g_tot;
+    a_low += (double)g_low;
   }
   a_tot = warp_sum(a_tot);
   a_low = warp_sum(a_low);
@@ -669,7 +678,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
     }
   }
   __syncthreads();
-  dc_correction(cen, cbufd, cur_f0, c.fs, Nd);        // cbuf is idle here; pw holds the staged power-spectrum window
+  dc_correction<false>(cen, cbufd, cur_f0, c.fs, Nd);  // one warp; the centroid is next read after the power spectrum's barriers (cbuf is idle here as scratch for the block version; pw holds the staged power-spectrum window)
 
   // ---- GetSmoothedPowerSpectrum (:148-164) ----------------------------------------------------
   {
@@ -691,7 +700,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
       pw[k] = X.x * X.x + X.y * X.y;
     }
     __syncthreads();
-    dc_correction(pw, cbufd, cur_f0, c.fs, Nd);
+    dc_correction<true>(pw, cbufd, cur_f0, c.fs, Nd);
     linear_smoothing(pw, pw, cbufd, red, cur_f0, c.fs, Nd, k_ratio);
   }
   // ---- GetStaticGroupDelay (:170-186) ------------------------------------------------------------

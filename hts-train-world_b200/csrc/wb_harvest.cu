@@ -1236,6 +1236,15 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
   WB_CUDA_OR_RETURN(cudaFuncSetAttribute(ols_filter_zc_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
   WB_CUDA_OR_RETURN(cudaFuncSetAttribute(ols_filter_zc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
   const size_t kMaxScratchDoubles = (size_t)2 << 30;           // 16 GiB of filtered signals at a time
+  const size_t kMaxSegDoubles = (size_t)1 << 30;               // 8 GiB of zero-crossing segments at a time
+  constexpr int kSegCap = 256;                                 // events per (list, block): a block is ~1 550 samples at 8 kHz (0.19 s), the
+                                                               // highest channel (880 Hz) yields ~170 events of each type in it
+  const bool fused_wanted = option("harvest_fused") && hb->V > 64;
+  // scratch of the sub-batches: declared once, grow-only (DevBuf::alloc keeps a buffer that is large enough), so
+  // the sub-batches of a call -- and, through the pool, of the next call -- reuse the same blocks
+  DevBuf<double> d_F, d_edges, d_raw, d_seg;
+  DevBuf<long long> d_foff, d_loff, d_roff;
+  DevBuf<int> d_counts, d_ltot, d_segcnt, d_segoff;
   int u0 = 0;
   while (u0 < n_utt) {
     int u1 = u0;
@@ -1245,6 +1254,14 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
     while (u1 < n_utt) {
       const size_t need = (size_t)c.nch * h_ylen[u1] + 8;
       if (u1 > u0 && (tot + need > kMaxScratchDoubles || (long long)(u1 - u0 + 1) * c.nch > 65535)) break;   // grid.y of the per-(utterance, channel) kernels
+      if (u1 > u0 && fused_wanted) {
+        // the fused path's event segments: (lists) x (blocks of the longest utterance) x kSegCap doubles; bounded so
+        // that the scratch pool settles on a few GiB whatever the batch (a 1 132-utterance batch asked for 22 GB
+        // per sub-batch and the pool kept growing for several calls)
+        const int my = std::max(sub_max_y, h_ylen[u1]);
+        const size_t nb = (size_t)(my - 1 + (hb->V - 2) - 1) / (hb->V - 2);
+        if ((size_t)(u1 - u0 + 1) * c.nch * 4 * nb * kSegCap > kMaxSegDoubles) break;
+      }
       h_foff.push_back((long long)tot);
       h_roff.push_back((long long)rtot);
       tot += need;
@@ -1254,9 +1271,6 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
       ++u1;
     }
     const int nu = u1 - u0;
-    DevBuf<double> d_F, d_edges, d_raw;
-    DevBuf<long long> d_foff, d_loff, d_roff;
-    DevBuf<int> d_counts, d_ltot;
     const int n_lists = nu * c.nch * 4;
     if (!d_roff.alloc(nu) || !d_ltot.alloc(n_lists + 1) || !d_loff.alloc(n_lists) || !d_raw.alloc(rtot)) return false;
     if (!up(d_roff.p, h_roff.data(), nu * sizeof(long long))) return false;
@@ -1264,15 +1278,12 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
     std::vector<int> h_ltot(n_lists + 1);
     std::vector<long long> h_loff(n_lists);
     bool fused_done = false;
-    if (option("harvest_fused") && hb->V > 64) {
+    if (fused_wanted) {
       // band-pass filters + zero crossings in one kernel: the 152 channel signals never leave shared memory
-      constexpr int kCap = 256;                              // events per (list, block): a block is ~1 550 samples at 8 kHz (0.19 s), the
-                                                             // highest channel (880 Hz) yields ~170 events of each type in it
+      constexpr int kCap = kSegCap;
       OlsConst ocz = oc;
       ocz.V = hb->V - 2;
       const int n_blocks = (sub_max_y - 1 + ocz.V - 1) / ocz.V;
-      DevBuf<int> d_segcnt, d_segoff;
-      DevBuf<double> d_seg;
       if (!d_segcnt.alloc((size_t)n_lists * n_blocks) || !d_segoff.alloc((size_t)n_lists * n_blocks) ||
           !d_seg.alloc((size_t)n_lists * n_blocks * kCap))
         return false;

@@ -5,18 +5,56 @@
 
 namespace wb {
 
-// In-place DC correction of spec[0..N/2] held in shared memory.
-// tmp: scratch of >= 2 + f0*N/fs doubles.  Ends with __syncthreads().
-__device__ __forceinline__ void dc_correction(double* spec, double* tmp, double f0, int fs, int N) {
-  const int T = blockDim.x, tid = threadIdx.x;
+// In-place DC correction of spec[0..N/2] held in shared memory (common.cpp:56-75): the bins below f0 receive
+// the mirror image of the bins above it, spec[i] += interp1Q(spec)(f0 - i df) for i < upper_limit - 1.
+// The <= ~70 bins involved (f0 N / fs + 1) are the work of ONE warp: warp 0 computes its values into
+// registers, orders itself with a warp barrier and adds them; the other warps pass straight through, so a
+// caller whose next step does not read the low bins (D4C's centroid, whose consumer is three phases away)
+// pays nothing, and one that does pays one block barrier instead of two plus a round trip through scratch.
+// `spec` must be complete on entry (caller syncs).  Does NOT end with a barrier.  Returns false (nothing
+// done) when the range exceeds what a warp holds; the caller then uses dc_correction_block.
+__device__ __forceinline__ bool dc_correction_warp(double* spec, double f0, int fs, int N) {
   const double inv_df = (double)N / fs;
   const double inv_n = 1.0 / N;                 // N is a power of two: x * inv_n == x / N exactly
+  const int upper_limit = min(N / 2 - 1, 2 + static_cast<int>(mul_rn(f0, (double)N) / fs));
+  const int n = upper_limit - 1;
+  if (n > 128) return false;
+  if (threadIdx.x < 32) {
+    double v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = (int)threadIdx.x + 32 * j;
+      v[j] = i < n ? interp1q_at(f0, -inv_df, spec, upper_limit + 1, mul_rn((double)i, (double)fs) * inv_n) : 0.0;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = (int)threadIdx.x + 32 * j;
+      if (i < n) spec[i] += v[j];
+    }
+  }
+  return true;
+}
+// The same by the whole block through scratch.  tmp: >= 2 + f0*N/fs doubles.  Ends with __syncthreads().
+__device__ __forceinline__ void dc_correction_block(double* spec, double* tmp, double f0, int fs, int N) {
+  const int T = blockDim.x, tid = threadIdx.x;
+  const double inv_df = (double)N / fs;
+  const double inv_n = 1.0 / N;
   const int upper_limit = min(N / 2 - 1, 2 + static_cast<int>(mul_rn(f0, (double)N) / fs));
   for (int i = tid; i < upper_limit - 1; i += T)
     tmp[i] = interp1q_at(f0, -inv_df, spec, upper_limit + 1, mul_rn((double)i, (double)fs) * inv_n);
   __syncthreads();
   for (int i = tid; i < upper_limit - 1; i += T) spec[i] += tmp[i];
   __syncthreads();
+}
+// BARRIER_AFTER: the corrected bins are read by other warps right away
+template <bool BARRIER_AFTER>
+__device__ __forceinline__ void dc_correction(double* spec, double* tmp, double f0, int fs, int N) {
+  if (dc_correction_warp(spec, f0, fs, N)) {          // block-uniform
+    if (BARRIER_AFTER) __syncthreads();
+  } else {
+    dc_correction_block(spec, tmp, f0, fs, N);
+  }
 }
 
 __device__ __forceinline__ int smoothing_boundary(double width, int fs, int N) {
@@ -29,7 +67,8 @@ __device__ __forceinline__ int smoothing_boundary(double width, int fs, int N) {
 // into registers, sums it there, the chunk totals are scanned with warp shuffles and the
 // finished values are stored once -- no mirrored copy and no second read-modify-write pass.
 // Returns false (nothing written) when len > blockDim.x * PER; the caller then takes the generic
-// path.  `in` must be complete on entry; ends with __syncthreads().
+// path.  `in` must be complete on entry -- i.e. the caller has passed a block barrier since the last use
+// of `red` as well, which is why no barrier protects `red` here; ends with __syncthreads().
 template <int PER>
 __device__ __forceinline__ bool mirrored_cumsum(const double* in, double* cum, double* red, int half,
                                                 int boundary, int fs, double inv_n, int len_limit = 0x7fffffff) {
@@ -56,7 +95,6 @@ __device__ __forceinline__ bool mirrored_cumsum(const double* in, double* cum, d
     const double t = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= o) inc += t;
   }
-  __syncthreads();                       // `red` may still be read by an earlier reduction
   if (lane == 31) red[wid] = inc;
   __syncthreads();
   double offset = inc - s;               // exclusive within the warp
