@@ -502,8 +502,7 @@ __device__ __forceinline__ void band_fft_pruned(float2* __restrict__ fb, const d
       sb[cpadf(q + 8)] = hi;
     }
   }
-  __syncthreads();
-  fft_run_passes<LOG2N, 4, 1, false, THREADS, LOG2N>(fb, twf);
+  fft_finish_after_first_pass<LOG2N, 4, false, THREADS, LOG2N, false>(fb, twf);
 }
 
 // dynamic shared memory: [ cen: Hd+8 | cbuf: d4c_cbuf_slots double2 | pw: Hd+8 | red: 96 |
@@ -659,8 +658,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
           return z;
         };
         fft_first_pass_from<K0, false, LOG2ND, THREADS>(cbuf, load);
-        fft_sync_after<LOG2ND, MAXK, 0, THREADS>();
-        fft_run_passes<LOG2ND, MAXK, 1, false, THREADS, TWL>(cbuf, tw);
+        fft_finish_after_first_pass<LOG2ND, MAXK, false, THREADS, TWL>(cbuf, tw);
       } else {
         for (int i = tid; i < Nd; i += T) {
           double2 z = make_double2(0.0, 0.0);

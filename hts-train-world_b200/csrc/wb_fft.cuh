@@ -150,8 +150,50 @@ __device__ __forceinline__ void fft_stages(C (&v)[1 << K], const C* w) {
 //
 // cpad() is additive over non-overlapping bit fields: the group base has zeros where
 // (m << STAGE) lives, hence cpad(base + (m << STAGE)) = cpad(base) + cpad(m << STAGE).
+// A read-only load the compiler may not move: a volatile asm keeps its place relative to the barriers (which
+// are volatile too) -- a plain __ldg issued in front of a barrier was sunk behind it.
+__device__ __forceinline__ double2 ldg_pinned(const double2* p) {
+#ifdef WB_HOST_EMU
+  return *p;
+#else
+  double2 v;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+#endif
+}
+__device__ __forceinline__ float2 ldg_pinned(const float2* p) {
+#ifdef WB_HOST_EMU
+  return *p;
+#else
+  float2 v;
+  asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+#endif
+}
+
+// The K twiddles of group b of the pass at STAGE: one table load, w[K-1] = exp(-2 pi i j / 2^(STAGE+K)) with
+// j = b mod 2^STAGE is the finest, and every coarser one is the square of the next finer one -- 4 flops instead
+// of a load whose latency the whole group waits for (with ~28 KB of L1 left beside the shared memory the
+// tables miss; measured -7 % on the step).  The rounding error doubles per squaring: <= 2^(K-1) ulp.
+// They depend on the thread index only, NOT on the data: fft_run_passes forms the twiddles of pass p + 1
+// between the stores of pass p and the barrier, so the load's latency and the squaring chain hide behind the
+// wait for the other warps instead of standing in front of the first butterfly (7.5 % of the synthesis
+// kernel's stall samples sat on this load).
+template <int K, bool INV, int STAGE, int TWL, typename C>
+__device__ __forceinline__ void fft_twiddles(const C* __restrict__ tw, int b, C (&w)[4]) {
+  if constexpr (STAGE > 0) {
+    const int j = b & ((1 << STAGE) - 1);
+    w[K - 1] = ldg_pinned(&tw[j << (TWL - STAGE - K)]);
+    if (INV) w[K - 1].y = -w[K - 1].y;
+#pragma unroll
+    for (int t = K - 2; t >= 0; --t)
+      w[t] = mk2((w[t + 1].x - w[t + 1].y) * (w[t + 1].x + w[t + 1].y), (w[t + 1].x + w[t + 1].x) * w[t + 1].y);
+  }
+}
+
+// w0: the twiddles of this thread's first group (fft_twiddles with b = threadIdx.x), formed by the caller.
 template <int K, bool INV, int LOG2N, int STAGE, int THREADS, int TWL = kTwLog2, typename C>
-__device__ __forceinline__ void fft_pass(C* __restrict__ s, const C* __restrict__ tw) {
+__device__ __forceinline__ void fft_pass(C* __restrict__ s, const C* __restrict__ tw, const C (&w0)[4]) {
   constexpr int R = 1 << K;
   constexpr bool FIRST = STAGE == 0;
   constexpr int NB = 1 << (LOG2N - K);
@@ -166,19 +208,13 @@ __device__ __forceinline__ void fft_pass(C* __restrict__ s, const C* __restrict_
     C v[R];
 #pragma unroll
     for (int m = 0; m < R; ++m) v[m] = sb[cpadT<C>(m << STAGE)];
-    C w[K];
-    if (!FIRST) {
-      // one table load per group: w[K-1] = exp(-2 pi i j / 2^(STAGE+K)) is the finest of the K twiddles
-      // and every coarser one is the square of the next finer one -- 4 flops instead of a load whose
-      // latency the whole group waits for (with ~28 KB of L1 left beside the shared memory the tables
-      // miss; measured -7 % on the step).  The rounding error doubles per squaring: <= 2^(K-1) ulp.
-      w[K - 1] = __ldg(&tw[j << (TWL - STAGE - K)]);
-      if (INV) w[K - 1].y = -w[K - 1].y;
-#pragma unroll
-      for (int t = K - 2; t >= 0; --t)
-        w[t] = mk2((w[t + 1].x - w[t + 1].y) * (w[t + 1].x + w[t + 1].y), (w[t + 1].x + w[t + 1].x) * w[t + 1].y);
+    if (it == 0) {
+      fft_stages<K, INV, FIRST>(v, w0);
+    } else {
+      C w[4];
+      fft_twiddles<K, INV, STAGE, TWL>(tw, b, w);
+      fft_stages<K, INV, FIRST>(v, w);
     }
-    fft_stages<K, INV, FIRST>(v, w);
 #pragma unroll
     for (int m = 0; m < R; ++m) sb[cpadT<C>(m << STAGE)] = v[m];
   }
@@ -236,14 +272,39 @@ __device__ __forceinline__ void fft_sync_after() {
   }
 }
 
+// passes PASS .. P-1; w = the twiddles of pass PASS for this thread's first group (ignored by pass 0)
+template <int LOG2N, int MAXK, int PASS, bool INV, int THREADS, int TWL = kTwLog2, typename C>
+__device__ __forceinline__ void fft_run_passes_w(C* s, const C* __restrict__ tw, const C (&w)[4]) {
+  using plan = fft_plan<LOG2N, MAXK>;
+  if constexpr (PASS < plan::P) {
+    fft_pass<plan::k_of(PASS), INV, LOG2N, plan::stage_of(PASS), THREADS, TWL>(s, tw, w);
+    C wn[4];
+    if constexpr (PASS + 1 < plan::P)
+      fft_twiddles<plan::k_of(PASS + 1 < plan::P ? PASS + 1 : PASS), INV, plan::stage_of(PASS + 1 < plan::P ? PASS + 1 : PASS), TWL>(tw, threadIdx.x, wn);
+    fft_sync_after<LOG2N, MAXK, PASS, THREADS>();
+    fft_run_passes_w<LOG2N, MAXK, PASS + 1, INV, THREADS, TWL>(s, tw, wn);
+  }
+}
 template <int LOG2N, int MAXK, int PASS, bool INV, int THREADS, int TWL = kTwLog2, typename C>
 __device__ __forceinline__ void fft_run_passes(C* s, const C* __restrict__ tw) {
   using plan = fft_plan<LOG2N, MAXK>;
-  if constexpr (PASS < plan::P) {
-    fft_pass<plan::k_of(PASS), INV, LOG2N, plan::stage_of(PASS), THREADS, TWL>(s, tw);
-    fft_sync_after<LOG2N, MAXK, PASS, THREADS>();
-    fft_run_passes<LOG2N, MAXK, PASS + 1, INV, THREADS, TWL>(s, tw);
-  }
+  C w[4];
+  if constexpr (PASS > 0 && PASS < plan::P)
+    fft_twiddles<plan::k_of(PASS < plan::P ? PASS : 0), INV, plan::stage_of(PASS < plan::P ? PASS : 0), TWL>(tw, threadIdx.x, w);
+  fft_run_passes_w<LOG2N, MAXK, PASS, INV, THREADS, TWL>(s, tw, w);
+}
+// The passes after a first pass the caller ran itself (fft_first_pass_from, or a pruned first pass of its own):
+// the twiddles of pass 1 are formed BEFORE the barrier behind pass 0.  WARP_LOCAL: the caller's first pass
+// used the thread <-> slot mapping of fft_pass (fft_sync_after may relax the barrier to a warp barrier).
+template <int LOG2N, int MAXK, bool INV, int THREADS, int TWL = kTwLog2, bool WARP_LOCAL = true, typename C>
+__device__ __forceinline__ void fft_finish_after_first_pass(C* s, const C* __restrict__ tw) {
+  using plan = fft_plan<LOG2N, MAXK>;
+  C w[4];
+  if constexpr (plan::P > 1)
+    fft_twiddles<plan::k_of(plan::P > 1 ? 1 : 0), INV, plan::stage_of(plan::P > 1 ? 1 : 0), TWL>(tw, threadIdx.x, w);
+  if constexpr (WARP_LOCAL) fft_sync_after<LOG2N, MAXK, 0, THREADS>();
+  else __syncthreads();
+  fft_run_passes_w<LOG2N, MAXK, 1, INV, THREADS, TWL>(s, tw, w);
 }
 
 // In-place complex FFT of 2^LOG2N points held in shared memory at padded slots.

@@ -505,16 +505,25 @@ harvest_refine_thread_kernel(const double* __restrict__ y_all, const long long* 
       key_hwl = hwl;
       const double wlen = div_rn(add_rn(mul_rn(2.0, (double)hwl), 1.0), fs);              // :587
       const int basic_index = matlab_round(add_rn(mul_rn(add_rn(pos, div_rn((double)(-hwl), fs)), fs), 0.001));   // :436-437
-      double pc[6], ps[6], qc[6], qs[6];
+      // The two spectra (window, differentiated window) at the <= 6 harmonic bins by GOERTZEL recurrences:
+      // s[n] = x[n] + 2 cos(w) s[n-1] - s[n-2] costs one addition and one FMA per sample, bin and sequence
+      // (24 FP64 operations per sample for 6 bins x 2 sequences) where a rotating phasor with its four
+      // multiply-adds costs 48; at the end  sum x[n] e^{-i w n} = e^{-i w (W-1)} (s[W-1] - e^{-i w} s[W-2]),
+      // the closing phasor taken from the twiddle table (index bin (W - 1) mod nfft, exact).  The error of
+      // the recurrence grows like W / sin(w): <= 1e-12 here (W <= 340, w >= 0.05), F0 to ~1e-10.
+      double k2[6], qc[6], qs[6], sm1[6], sm2[6], sd1[6], sd2[6];
       const double2* __restrict__ tw = tw_c_base + Context::tw_c_offset(log2fft);
+      auto tw_at = [&](int m) {                                   // exp(-2 pi i m / nfft), m in [0, nfft)
+        double2 b = __ldg(&tw[m & (nhalf - 1)]);
+        if (m & nhalf) { b.x = -b.x; b.y = -b.y; }
+        return b;
+      };
 #pragma unroll
       for (int h = 0; h < 6; ++h) {
         key_bins[h] = bins[h];
-        const int m1 = bins[h] & (nfft - 1);
-        double2 b = __ldg(&tw[m1 & (nhalf - 1)]);
-        if (m1 & nhalf) { b.x = -b.x; b.y = -b.y; }
-        pc[h] = 1.0; ps[h] = 0.0; qc[h] = b.x; qs[h] = b.y;
-        acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.0;
+        const double2 b = tw_at(bins[h] & (nfft - 1));
+        qc[h] = b.x; qs[h] = b.y; k2[h] = 2.0 * b.x;
+        sm1[h] = sm2[h] = sd1[h] = sd2[h] = 0.0;
       }
       // window phase a_n = 2 pi ((basic_index + n - 1) / fs - pos) / wlen (:447-452), advanced one sample at a
       // time; the differentiated window (:459-465) needs w[n-1], w[n], w[n+1]: a three-value slide
@@ -523,7 +532,7 @@ harvest_refine_thread_kernel(const double* __restrict__ y_all, const long long* 
       sincospi(dturn, &sd, &cd);
       sincospi(2.0 * add_rn(div_rn(basic_index - 1.0, fs), -pos) / wlen, &sn, &cs);      // n = 0
       double w_prev = 0.0, w_cur = blackman(cs);
-      for (int n = 0; n < W; ++n) {
+      auto sample = [&](int n, double* xm, double* xd) {
         {                                                             // phase of sample n + 1
           const double t = cs * cd - sn * sd;
           sn = sn * cd + cs * sd;
@@ -536,17 +545,36 @@ harvest_refine_thread_kernel(const double* __restrict__ y_all, const long long* 
         else dw = -(w_next - w_prev) / 2.0;
         const int idx = max(0, min(y_len - 1, basic_index + n - 1));
         const double xv = y[idx] - mean;
-        const double xm = xv * w_cur, xd = xv * dw;
-#pragma unroll
-        for (int h = 0; h < 6; ++h) {
-          acc[h][0] += xm * pc[h]; acc[h][1] += xm * ps[h];
-          acc[h][2] += xd * pc[h]; acc[h][3] += xd * ps[h];
-          const double t = pc[h] * qc[h] - ps[h] * qs[h];
-          ps[h] = ps[h] * qc[h] + pc[h] * qs[h];
-          pc[h] = t;
-        }
+        *xm = xv * w_cur; *xd = xv * dw;
         w_prev = w_cur;
         w_cur = w_next;
+      };
+      // two samples per trip: the roles of s[n-1] / s[n-2] alternate, no register moves; W is odd
+      for (int n = 0; n + 1 < W; n += 2) {
+        double xm0, xd0, xm1, xd1;
+        sample(n, &xm0, &xd0);
+        sample(n + 1, &xm1, &xd1);
+#pragma unroll
+        for (int h = 0; h < 6; ++h) {
+          sm2[h] = fma(k2[h], sm1[h], xm0 - sm2[h]);
+          sd2[h] = fma(k2[h], sd1[h], xd0 - sd2[h]);
+          sm1[h] = fma(k2[h], sm2[h], xm1 - sm1[h]);
+          sd1[h] = fma(k2[h], sd2[h], xd1 - sd1[h]);
+        }
+      }
+      {
+        double xm0, xd0;
+        sample(W - 1, &xm0, &xd0);
+#pragma unroll
+        for (int h = 0; h < 6; ++h) {
+          const double tm = fma(k2[h], sm1[h], xm0 - sm2[h]), td = fma(k2[h], sd1[h], xd0 - sd2[h]);
+          // y = s[W-1] - e^{-i w} s[W-2];  X = e^{-i w (W-1)} y
+          const double ymr = tm - qc[h] * sm1[h], ymi = -qs[h] * sm1[h];
+          const double ydr = td - qc[h] * sd1[h], ydi = -qs[h] * sd1[h];
+          const double2 e = tw_at((int)(((long long)bins[h] * (W - 1)) & (nfft - 1)));
+          acc[h][0] = e.x * ymr - e.y * ymi; acc[h][1] = e.x * ymi + e.y * ymr;
+          acc[h][2] = e.x * ydr - e.y * ydi; acc[h][3] = e.x * ydi + e.y * ydr;
+        }
       }
     }
     double numerator = 0.0, denominator = 0.0, sc = 0.0;           // FixF0 (:504-536)
