@@ -150,40 +150,19 @@ __device__ __forceinline__ void fft_stages(C (&v)[1 << K], const C* w) {
 //
 // cpad() is additive over non-overlapping bit fields: the group base has zeros where
 // (m << STAGE) lives, hence cpad(base + (m << STAGE)) = cpad(base) + cpad(m << STAGE).
-// A read-only load the compiler may not move: a volatile asm keeps its place relative to the barriers (which
-// are volatile too) -- a plain __ldg issued in front of a barrier was sunk behind it.
-__device__ __forceinline__ double2 ldg_pinned(const double2* p) {
-#ifdef WB_HOST_EMU
-  return *p;
-#else
-  double2 v;
-  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-  return v;
-#endif
-}
-__device__ __forceinline__ float2 ldg_pinned(const float2* p) {
-#ifdef WB_HOST_EMU
-  return *p;
-#else
-  float2 v;
-  asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-  return v;
-#endif
-}
-
 // The K twiddles of group b of the pass at STAGE: one table load, w[K-1] = exp(-2 pi i j / 2^(STAGE+K)) with
 // j = b mod 2^STAGE is the finest, and every coarser one is the square of the next finer one -- 4 flops instead
 // of a load whose latency the whole group waits for (with ~28 KB of L1 left beside the shared memory the
 // tables miss; measured -7 % on the step).  The rounding error doubles per squaring: <= 2^(K-1) ulp.
-// They depend on the thread index only, NOT on the data: fft_run_passes forms the twiddles of pass p + 1
-// between the stores of pass p and the barrier, so the load's latency and the squaring chain hide behind the
-// wait for the other warps instead of standing in front of the first butterfly (7.5 % of the synthesis
-// kernel's stall samples sat on this load).
+// They depend on the thread index only, NOT on the data, so fft_run_passes forms the twiddles of pass p + 1
+// between the stores of pass p and the barrier.  (Measured: no gain -- ptxas sinks the load behind the
+// barrier again, also when it is a volatile asm; the stall samples that sit on this load are the barrier
+// wait itself, which ncu attributes to the first instruction behind BAR.SYNC.)
 template <int K, bool INV, int STAGE, int TWL, typename C>
 __device__ __forceinline__ void fft_twiddles(const C* __restrict__ tw, int b, C (&w)[4]) {
   if constexpr (STAGE > 0) {
     const int j = b & ((1 << STAGE) - 1);
-    w[K - 1] = ldg_pinned(&tw[j << (TWL - STAGE - K)]);
+    w[K - 1] = __ldg(&tw[j << (TWL - STAGE - K)]);
     if (INV) w[K - 1].y = -w[K - 1].y;
 #pragma unroll
     for (int t = K - 2; t >= 0; --t)
