@@ -329,34 +329,28 @@ __device__ __forceinline__ void select_low_sums(const float* __restrict__ P, int
 //
 // Two phases.  (1) The upper 16 bits of a non-negative float are its bfloat16 truncation, and bfloat16
 // values order like their bit patterns, so the first 16 bits are decided on PACKED keys: two upper halves
-// per register, one HSET2.BF16 (two comparisons, 1.0 / 0.0 per half) and one HADD2.BF16 (two counters, exact
-// up to 256) per PAIR of keys and step -- a quarter of the issue cycles of the compare / predicated-add pair
-// per key of the 32-bit sweep, which ran on the half-rate integer pipe.  (2) Only when the K-th and the
+// per register, one HSET2.BF16 (two comparisons, a 16-bit mask per half) per pair of keys and one three-input
+// integer addition per two pairs (bf16x2_ge_mask) -- a fifth of the issue cycles of the compare /
+// predicated-add pair per key of the 32-bit sweep, which ran on the half-rate integer pipe.  (2) Only when the K-th and the
 // (K+1)-th largest key share their upper half (a bucket 0.8 % wide) do the full keys come back from shared
 // memory and the search continues on bits 15 .. 0 with 32-bit sweeps; inside one bucket the lower bits are
 // as good as random, so this takes a few steps.
-__device__ __forceinline__ unsigned bf16x2_count_ge(unsigned acc, unsigned keys, unsigned cand2) {
+// (keys >= cand2) per half as a mask, 0xffff or 0.  Subtracting the masks of several registers from an integer
+// accumulator counts both halves at once: -0xffff = 1 - 0x10000, so the low half of the accumulator ends up
+// with the number of low hits and the high half with (high hits - low hits) mod 2^16 -- one three-input integer
+// addition takes two masks, i.e. 1.5 instructions per PAIR of keys and step.
+__device__ __forceinline__ unsigned bf16x2_ge_mask(unsigned keys, unsigned cand2) {
 #ifdef WB_HOST_EMU
-  const unsigned lo = (keys & 0xffffu) >= (cand2 & 0xffffu), hi = (keys >> 16) >= (cand2 >> 16);
-  return acc + lo + (hi << 16);                       // plain integer counters on the host
+  return ((keys & 0xffffu) >= (cand2 & 0xffffu) ? 0xffffu : 0u) | ((keys >> 16) >= (cand2 >> 16) ? 0xffff0000u : 0u);
 #else
   unsigned m;
-  asm("set.ge.bf16x2.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(keys), "r"(cand2));
-  asm("add.rn.bf16x2 %0, %0, %1;" : "+r"(acc) : "r"(m));
-  return acc;
+  asm("set.ge.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(keys), "r"(cand2));
+  return m;
 #endif
 }
-__device__ __forceinline__ int bf16x2_counts_total(unsigned a0, unsigned a1, unsigned a2, unsigned a3) {
-#ifdef WB_HOST_EMU
-  const unsigned s = a0 + a1 + a2 + a3;
-  return (int)((s & 0xffffu) + (s >> 16));
-#else
-  unsigned s01, s23, s;
-  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(s01) : "r"(a0), "r"(a1));
-  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(s23) : "r"(a2), "r"(a3));
-  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(s) : "r"(s01), "r"(s23));
-  return __float2int_rn(__uint_as_float(s << 16) + __uint_as_float(s & 0xffff0000u));
-#endif
+__device__ __forceinline__ int packed_counts_total(unsigned acc) {
+  const unsigned lo = acc & 0xffffu;
+  return (int)(lo + (((acc >> 16) + lo) & 0xffffu));
 }
 
 template <int NPL>     // keys per lane: ceil(n / 32)
@@ -391,8 +385,10 @@ __device__ __forceinline__ void warp_select_low_sum(const float* __restrict__ P,
       const unsigned cand2 = cand * 0x10001u;
       unsigned c[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-      for (int j = 0; j < NPK; ++j) c[j & 3] = bf16x2_count_ge(c[j & 3], h[j], cand2);   // the pad keys are 0 < cand
-      const int cnt = __reduce_add_sync(0xffffffffu, bf16x2_counts_total(c[0], c[1], c[2], c[3]));
+      for (int j = 0; j + 1 < NPK; j += 2)        // the pad keys are 0 < cand
+        c[(j >> 1) & 3] = c[(j >> 1) & 3] - bf16x2_ge_mask(h[j], cand2) - bf16x2_ge_mask(h[j + 1], cand2);
+      if (NPK & 1) c[0] -= bf16x2_ge_mask(h[NPK - 1], cand2);
+      const int cnt = __reduce_add_sync(0xffffffffu, packed_counts_total((c[0] + c[1]) + (c[2] + c[3])));
       if (cnt >= K) {
         T16 = cand;
         at_or_above = cnt;
