@@ -25,6 +25,7 @@ namespace wb {
 namespace {
 
 constexpr int kHanning = 1, kBlackman = 2;
+constexpr int kLtStage = 2048 + 2;          // LoveTrain: doubles of shared memory for the staged sample window
 constexpr int kMaxBands = 8;
 
 __device__ __forceinline__ int d4c_hwl(double ratio, int fs, double f0) {
@@ -50,7 +51,7 @@ __device__ __forceinline__ int windowed_waveform(const double* __restrict__ x, i
                                                  double f0, double position, int window_type,
                                                  double ratio, const uint32_t* __restrict__ rn,
                                                  S* base, WS wslot, VS vslot, double* red,
-                                                 const double* staged = nullptr) {
+                                                 const double* staged = nullptr, uint64_t* staged_bar = nullptr) {
   const int T = blockDim.x, tid = threadIdx.x;
   const int hwl = d4c_hwl(ratio, fs, f0);
   const int W = 2 * hwl + 1;
@@ -67,6 +68,7 @@ __device__ __forceinline__ int windowed_waveform(const double* __restrict__ x, i
     return window_type == kHanning ? 0.5 * cs + 0.5 : 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);
   };
   double cs = cs0, sn = sn0;
+  if (staged_bar) mbar_wait(staged_bar, 0);          // the bulk copy of the samples has landed (phase 0)
   for (int i = tid; i < W; i += T) {
     const double w = window_at(cs);
     {
@@ -148,7 +150,7 @@ d4c_lovetrain_kernel(UttView u, const int* __restrict__ frame_utt, const double*
 
 // LoveTrain with its transform in FP32 (tests/test_precision_budget.py: ap0 moves by < 1e-7 on
 // every input, the only use of ap0 is the comparison with the threshold).  Window, mean removal
-// and the band sums stay in FP64.  dynamic shared memory: [ buf: cpadf(M) + 4 float2 | red: 96 doubles ]
+// and the band sums stay in FP64.  dynamic shared memory: [ buf: cpadf(M) + 4 float2 | red: 96 doubles | stage: kLtStage doubles ]
 template <int LOG2LT>
 __global__ void __launch_bounds__(256)
 d4c_lovetrain32_kernel(UttView u, const int* __restrict__ frame_utt, const double* __restrict__ frame_t,
@@ -163,14 +165,29 @@ d4c_lovetrain32_kernel(UttView u, const int* __restrict__ frame_utt, const doubl
   float2* buf = reinterpret_cast<float2*>(smem2);
   float* buff = reinterpret_cast<float*>(buf);
   double* red = reinterpret_cast<double*>(buf + ((cpadf(M) + 4 + 1) & ~1));
+  double* stage = red + 96;                      // kLtStage doubles: the frame's sample window, by TMA
   const int tid = threadIdx.x, T = blockDim.x;
   const int utt = frame_utt[f];
   const double* __restrict__ x = u.x + u.x_off[utt];
   const double cur_f0 = fmax(f0, 40.0);
+  // the sample window is a contiguous range of the utterance: one bulk copy (cp.async.bulk + mbarrier) into
+  // shared memory, issued before the window coefficients are set up; windows that cross an utterance edge
+  // (the reference clamps the index) or exceed the staging area (f0 < ~70 Hz) take the clamped gather
+  __shared__ uint64_t mbar;
+  const int hwl = d4c_hwl(3.0, c.fs, cur_f0);
+  const int g0 = matlab_round(add_rn(mul_rn(frame_t[f], (double)c.fs), 0.001)) - hwl;
+  int st_a0 = 0, st_n = 0;
+  const bool st_ok = bulk_window_range(g0, 2 * hwl + 1, u.x_len[utt], kLtStage, &st_a0, &st_n);
+  if (st_ok) {
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    if (tid == 0) bulk_load_issue(stage, x + st_a0, (unsigned)st_n * 8u, &mbar);
+  }
   auto wslot = [](int i) { return rfft_in_slot_f(i, LM); };
   auto vslot = [](int i) { return i; };
   const int W = windowed_waveform<false>(x, u.x_len[utt], c.fs, cur_f0, frame_t[f], kBlackman, 3.0,
-                                         randn_tab + rng_off[f], buff, wslot, vslot, red);
+                                         randn_tab + rng_off[f], buff, wslot, vslot, red,
+                                         st_ok ? stage + (g0 - st_a0) : nullptr, st_ok ? &mbar : nullptr);
   for (int i = W + tid; i < N; i += T) buff[rfft_in_slot_f(i, LM)] = 0.f;
   fft_dit<LM, false, 256, 3, LOG2LT>(buf, LM, twf);
   double s[2] = {0.0, 0.0};
@@ -834,7 +851,7 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
   } while (0)
     const bool lt32 = option("lovetrain_fp32") != 0;
     if (lt32 && c.log2lt == 12) {
-      const size_t smem32 = (size_t)((cpadf(nl / 2) + 4 + 1) & ~1) * sizeof(float2) + 96 * sizeof(double);
+      const size_t smem32 = (size_t)((cpadf(nl / 2) + 4 + 1) & ~1) * sizeof(float2) + (96 + kLtStage) * sizeof(double);
       WB_CUDA_OR_RETURN(cudaFuncSetAttribute(d4c_lovetrain32_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32), false);
       d4c_lovetrain32_kernel<12><<<total_frames, 256, smem32, st>>>(u, frame_utt, frame_t, f0, offs_lt.p, ctxp->d_randn, ctxp->tw_cf(12), c, d_ap0.p);
     } else

@@ -66,8 +66,8 @@ extern "C" int emu_d4c(const double* x, int x_len, int fs, const double* t, cons
   const size_t smem_lt = (size_t)(2 * cpad_size(nl / 2) + 96) * sizeof(double);
   const size_t smem_main = d4c_cbuf_slots(nd, c.nbands) * sizeof(double2) + (size_t)(2 * (hd + 8) + 160) * sizeof(double) +
                            sizeof(SelectScratch) + (kMaxBands + 2) * sizeof(double);
+  const size_t smem_lt32 = (size_t)((cpadf(nl / 2) + 4 + 1) & ~1) * sizeof(float2) + (96 + kLtStage) * sizeof(double);
 #ifdef WB_D4C_HAS_SPLIT
-  const size_t smem_lt32 = (size_t)((cpadf(nl / 2) + 4 + 1) & ~1) * sizeof(float2) + 96 * sizeof(double);
   const size_t smem_gd = (size_t)(2 * (hd + 8) + 160) * sizeof(double) + (size_t)cpad_size(hd) * sizeof(double2);
   const size_t smem_tail = (size_t)d4c_tail_fb_slots(nd) * sizeof(float2) + (size_t)((c.nbands * (hd + 1) + 1) & ~1) * sizeof(float) +
                            (kMaxBands + 2) * sizeof(double);
@@ -98,12 +98,10 @@ extern "C" int emu_d4c(const double* x, int x_len, int fs, const double* t, cons
     for (auto& v : randn_tab) { uint32_t acc = 0; for (int j = 0; j < 12; ++j) acc += next(s) >> 4; v = acc; }
   }
 #ifndef WB_D4C_HAS_SPLIT
-  if (mode != 0) return 3;                                             // this source tree has only the main kernels
+  if (mode & 1) return 3;                                              // this source tree has no split main kernels
 #endif
-  if (mode & 2) {
-#ifdef WB_D4C_HAS_SPLIT
+  if (mode & 2) {                                                      // LoveTrain with the FP32 transform (the GPU default)
     wbemu::launch(lt_rows, F, 256, smem_lt32, [&]() { d4c_lovetrain32_kernel<12>(u, frame_utt.data(), t, f0, offs_lt.data(), randn_tab.data(), twf.data(), c, ap0.data()); });
-#endif
   } else {
     wbemu::launch(lt_rows, F, 256, smem_lt, [&]() { d4c_lovetrain_kernel<12>(u, frame_utt.data(), t, f0, offs_lt.data(), randn_tab.data(), tw.data(), c, ap0.data()); });
   }

@@ -6,7 +6,8 @@ barrier placement as far as logic goes -- without a GPU; the GPU parity tests ch
 
   mode 0: d4c_lovetrain_kernel + d4c_main_kernel (what the library runs)
   mode 1: d4c_gd_kernel + d4c_tail_kernel (the split draft, where the source tree has it)
-  mode 3: the same with the FP32 LoveTrain kernel
+  mode 2: d4c_lovetrain32_kernel (FP32 transform, TMA-staged window: the GPU default) + d4c_main_kernel
+  mode 3: the split draft with the FP32 LoveTrain kernel
 """
 import ctypes as C
 import os
@@ -64,7 +65,7 @@ def _x(g):
 
 
 def modes(has_split):
-    return [0, 1, 3] if has_split else [0]
+    return [0, 1, 2, 3] if has_split else [0, 2]        # bit 0: split main kernels (not in this tree), bit 1: FP32 LoveTrain
 
 
 def test_kernels_match_the_golden_rows(emu):
@@ -129,7 +130,7 @@ def test_no_data_races_under_thread_sanitizer(tmp_path, reference_lib):
 
     assert tsan(0, 0.0, skip=20)[1] > 0                    # the detector sees a dropped barrier
     has_split = "WB_D4C_HAS_SPLIT" in open(os.path.join(ROOT, "hts-train-world_b200", "csrc", "wb_d4c.cu")).read()
-    for mode, thr in [(0, 0.0), (0, 0.85)] + ([(1, 0.0), (3, 0.85)] if has_split else []):
+    for mode, thr in [(0, 0.0), (0, 0.85), (2, 0.85)] + ([(1, 0.0), (3, 0.85)] if has_split else []):
         rc, warnings = tsan(mode, thr)
         assert (rc, warnings) == (0, 0), (mode, thr)
         ap = np.fromfile(tmp_path / "ap.f64").reshape(len(rows), -1)
