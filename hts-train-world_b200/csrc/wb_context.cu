@@ -213,6 +213,7 @@ int option(const char* name) {
   struct Opt { const char* name; const char* env; int def; int val; };
   static Opt opts[] = {
       {"lovetrain_fp32", "WB_D4C_LT32", 1, -1},        // LoveTrain's transform in FP32
+      {"synth_phase4", "WB_SYNTH_PHASE4", 1, -1},      // Synthesis time base: four samples per thread (0: one sample per thread, 1 024-thread CTAs)
       {"dio_fused", "WB_DIO_FUSED", 1, -1},            // Dio: zero crossings inside the filter kernel (0: band signals through HBM)
       {"harvest_fused", "WB_HARVEST_FUSED", 1, -1},
       {"harvest_fix_warp", "WB_HARVEST_FIX_WARP", 1, -1},     // Harvest contour logic spread over a warp (0: lane 0 walks)

@@ -221,6 +221,121 @@ synth_phase_kernel(const double* __restrict__ inc_all, const long long* __restri
   }
 }
 
+// The same running sum with FOUR consecutive samples per thread (256 threads per chunk of 1 024): the
+// thread sums its own four increments first, so the two scans handle a quarter of the values, a CTA is 8
+// warps instead of 32 (cheaper barriers; every utterance of a 1 132-utterance batch is resident at once
+// instead of in four waves) and the powers of two are applied by exact multiplications instead of scalbn().
+// Bit-identical to synth_phase_kernel by construction: the same integer prefix sum in units of ulp(carry).
+constexpr int kTbPer = 4;
+__global__ void __launch_bounds__(kTbChunk / kTbPer)
+synth_phase4_kernel(const double* __restrict__ inc_all, const long long* __restrict__ y_off,
+                    const int* __restrict__ y_len_all, double* __restrict__ tot_all) {
+  constexpr int T = kTbChunk / kTbPer, NW = T / 32;
+  __shared__ double inc_s[kTbChunk];
+  __shared__ double tot_s[kTbChunk];
+  __shared__ long long wsum_s[2][NW];      // double-buffered by chunk parity (two barriers per chunk suffice)
+  __shared__ int wslow_s[2][NW];
+  const int u = blockIdx.x;
+  const int y_len = y_len_all[u];
+  const size_t off = (size_t)y_off[u];      // even: 16-byte aligned rows
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  double carry = 0.0;                       // running sum before this chunk, the same in every thread
+  auto load4 = [&](int i0, double* v) {
+    if (i0 + kTbPer <= y_len) {
+      const double2 a = *reinterpret_cast<const double2*>(inc_all + off + i0);
+      const double2 b = *reinterpret_cast<const double2*>(inc_all + off + i0 + 2);
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < kTbPer; ++j) v[j] = i0 + j < y_len ? inc_all[off + i0 + j] : 0.0;
+    }
+  };
+  double nxt[kTbPer];
+  load4(kTbPer * tid, nxt);
+  int par = 0;
+  for (int base = 0; base < y_len; base += kTbChunk, par ^= 1) {
+    const int i0 = base + kTbPer * tid;
+    double inc[kTbPer];
+#pragma unroll
+    for (int j = 0; j < kTbPer; ++j) inc[j] = nxt[j];
+    if (base + kTbChunk < y_len) load4(i0 + kTbChunk, nxt);          // the next chunk's load is in flight during this one
+    const double s0 = carry;
+    bool slow = !(s0 > 0.0);
+    long long p[kTbPer] = {0, 0, 0, 0}, s0int = 0;
+    double down = 0.0;                                               // 2^(e-52)
+    if (!slow) {
+      const int e = ((__double2hiint(s0) >> 20) & 0x7ff) - 1023;     // ilogb of a positive normal number
+      const double up = __hiloint2double((1023 + 52 - e) << 20, 0);  // 2^(52-e), exact
+      down = __hiloint2double((1023 + e - 52) << 20, 0);
+      long long run = 0;
+#pragma unroll
+      for (int j = 0; j < kTbPer; ++j) {
+        const double m = inc[j] * up;                                // exact (a power of two, no underflow here)
+        const double rr = rint(m);
+        slow = slow || fabs(m - rr) == 0.5 || !(m < 4503599627370496.0) || inc[j] < 0.0;
+        run += static_cast<long long>(rr);
+        p[j] = run;
+      }
+      s0int = static_cast<long long>(s0 * up);
+    }
+    long long pre = p[kTbPer - 1];                                   // inclusive scan of the thread totals inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += t;
+    }
+    const bool warp_slow = __any_sync(0xffffffffu, slow);
+    if (lane == 31) { wsum_s[par][wid] = pre; wslow_s[par][wid] = warp_slow; }
+    __syncthreads();
+    long long woff = 0, chunk_total = 0;
+    bool any_slow = false;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {                                   // 8 warp totals: every thread adds them itself
+      const long long v = wsum_s[par][w];
+      if (w < wid) woff += v;
+      chunk_total += v;
+      any_slow = any_slow || wslow_s[par][w] != 0;
+    }
+    // the sums are non-decreasing (inc >= 0): the chunk stays inside the binade iff its end does
+    const bool chunk_slow = any_slow || (s0int + chunk_total > 9007199254740992LL) || (s0int + chunk_total < 4503599627370496LL);
+    double total[kTbPer];
+    if (chunk_slow) {                                                // block-uniform
+#pragma unroll
+      for (int j = 0; j < kTbPer; ++j) inc_s[kTbPer * tid + j] = inc[j];
+      __syncthreads();
+      if (tid == 0) {
+        double run = carry;
+        for (int q = 0; q < kTbChunk; q += 8) {
+          double v[8];
+#pragma unroll
+          for (int r8 = 0; r8 < 8; ++r8) v[r8] = inc_s[q + r8];
+#pragma unroll
+          for (int r8 = 0; r8 < 8; ++r8) { run = add_rn(run, v[r8]); v[r8] = run; }
+#pragma unroll
+          for (int r8 = 0; r8 < 8; ++r8) tot_s[q + r8] = v[r8];
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < kTbPer; ++j) total[j] = tot_s[kTbPer * tid + j];
+      carry = tot_s[kTbChunk - 1];
+      __syncthreads();                                               // tot_s / inc_s are rewritten by the next slow chunk
+    } else {
+      const long long before = s0int + woff + (pre - p[kTbPer - 1]); // everything in front of this thread's samples
+#pragma unroll
+      for (int j = 0; j < kTbPer; ++j) total[j] = static_cast<double>(before + p[j]) * down;
+      carry = static_cast<double>(s0int + chunk_total) * down;
+    }
+    if (i0 + kTbPer <= y_len) {
+      *reinterpret_cast<double2*>(tot_all + off + i0) = make_double2(total[0], total[1]);
+      *reinterpret_cast<double2*>(tot_all + off + i0 + 2) = make_double2(total[2], total[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kTbPer; ++j) if (i0 + j < y_len) tot_all[off + i0 + j] = total[j];
+    }
+  }
+}
+
 // fmod(x, 2 pi) for 0 <= x < 2^20, exact like the C library's: with n = floor(x / 2 pi) (possibly off
 // by one) the residual x - n * y is a multiple of ulp(y) = 2^-50 and smaller than 8 in magnitude,
 // so it is representable and the FMA delivers it without rounding; one exact +- y repairs n.
@@ -757,7 +872,8 @@ bool synthesis_run(Batch* b, const int* y_len) {
     synth_inc_kernel<<<dim3((max_y + kTbChunk - 1) / kTbChunk, n_utt), 256, 0, st>>>(b->f0.p, b->f_off.p, b->f_len.p, b->y_len.p, b->y_off.p, c,
                                                                       d_inc.p, d_vuv.p);
     WB_LAUNCH_CHECK();
-    synth_phase_kernel<<<n_utt, kTbChunk, 0, st>>>(d_inc.p, b->y_off.p, b->y_len.p, d_tot.p);
+    if (option("synth_phase4")) synth_phase4_kernel<<<n_utt, kTbChunk / kTbPer, 0, st>>>(d_inc.p, b->y_off.p, b->y_len.p, d_tot.p);
+    else synth_phase_kernel<<<n_utt, kTbChunk, 0, st>>>(d_inc.p, b->y_off.p, b->y_len.p, d_tot.p);
     WB_LAUNCH_CHECK();
     synth_pulses_kernel<false><<<dim3(n_chunks_max, n_utt), 256, 0, st>>>(d_tot.p, d_vuv.p, b->y_off.p, b->y_len.p, c, n_chunks_max,
         d_counts.p, d_poff.p, d_cap.p, p_index.p, p_shift.p, p_vuv.p, p_utt.p);

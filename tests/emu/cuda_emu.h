@@ -137,6 +137,7 @@ inline double __ddiv_rn(double a, double b) { return a / b; }
 inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+inline int __double2hiint(double d) { uint64_t u; memcpy(&u, &d, 8); return (int)(u >> 32); }
 inline double __hiloint2double(int hi, int lo) {
   const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
   double d; memcpy(&d, &u, 8); return d;

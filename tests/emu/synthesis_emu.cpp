@@ -50,6 +50,11 @@ extern "C" int emu_synthesis(const double* f0, int F, const double* sp, const do
     wbemu::launch_grid((y_length + kTbChunk - 1) / kTbChunk, n_utt, 256, 0,
                        [&]() { synth_inc_kernel(f0, &f_off, &f_len, &y_len, &y_off, c, inc.data(), vuv.data()); });
     wbemu::launch_grid(n_utt, 1, kTbChunk, 0, [&]() { synth_phase_kernel(inc.data(), &y_off, &y_len, tot.data()); });
+    {   // the four-samples-per-thread version (the library's default) must give the same bits
+      std::vector<double> tot4(tot.size(), 0.0);
+      wbemu::launch_grid(n_utt, 1, kTbChunk / kTbPer, 0, [&]() { synth_phase4_kernel(inc.data(), &y_off, &y_len, tot4.data()); });
+      if (memcmp(tot4.data(), tot.data(), (size_t)y_length * sizeof(double)) != 0) return 7;
+    }
     wbemu::launch_grid(n_chunks_max, n_utt, 256, 0, [&]() {
       synth_pulses_kernel<false>(tot.data(), vuv.data(), &y_off, &y_len, c, n_chunks_max, counts.data(), &poff, &cap, p_index.data(),
                                  p_shift.data(), p_vuv.data(), p_utt.data());
