@@ -344,6 +344,21 @@ def other_configs(wb, c, args, audio_s, pcm_dev, lengths, stream):
                 "workload": "%d-utterance corpus, Harvest (71-800 Hz) + CheapTrick + D4C + codec + Synthesis + statistics" % len(lengths),
                 "value": audio_s / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "harvest_stage_ms": wb.stage_times()["harvest"],
                 "kernels_ms_per_step": {k: v[0] / 5.0 for k, v in hk.items() if v[1]}}
+            if args.verify > 0:       # F0 of the first and the last utterance of the batch against the reference's Harvest
+                from oracle import metrics as M
+                from oracle import ref
+                if os.path.exists(ref.ref_path()):
+                    R = ref.load()
+                    offs = np.concatenate([[0], np.cumsum(lengths)])
+                    agree, err = 1.0, 0.0
+                    for u in (0, len(lengths) - 1):
+                        x = pcm_dev[int(offs[u]):int(offs[u + 1])].cpu().numpy().astype(np.float64) / 32768.0
+                        _, f0_ref = R.harvest(x, FS, frame_period=FRAME_PERIOD)
+                        f0_u = c.utterance(u)["f0"]
+                        agree = min(agree, M.vuv_agreement(f0_ref, f0_u))
+                        err = max(err, M.f0_rel_error(f0_ref, f0_u))
+                    out["config3_harvest"]["parity"] = {"vuv_agreement": agree, "f0_rel_error": err,
+                                                        "within_tolerance": bool(agree >= M.TOL_VUV_AGREEMENT and err <= M.TOL_F0_REL)}
         except Exception as e:          # e.g. out of memory for the band signals of a very large batch
             out["config3_harvest"] = {"error": str(e)[:300]}
     # configs[0]: one 3 s 16 kHz utterance through the drop-in C API, host buffers, one call per stage
@@ -596,7 +611,7 @@ def ours_arm(args):
     # the reference's own Dio + StoneMask chain; CheapTrick / D4C / Synthesis stage by stage, the reference
     # fed the same upstream values our stage saw -- north_star's five metrics.
     parity = None
-    if rank == 0 and args.verify > 0 and args.f0 == "dio":
+    if rank == 0 and args.verify > 0:
         parity = verify_against_reference(wb, c, ids, pcm_host, lengths, args.verify, args.f0)
 
     # ---- the other BASELINE.json configurations (rank 0, N = 1) -------------------------------------------
