@@ -35,6 +35,10 @@ __global__ void cheaptrick_count_kernel(const double* __restrict__ f0, int total
 }
 
 // dynamic shared memory: [ buf: cpad_size(N/2) double2 | aux: N + 16 doubles | red: 96 doubles ]
+#ifndef WB_CT_MAXK32
+#define WB_CT_MAXK32 4
+#endif
+constexpr int kCtMaxK32 = WB_CT_MAXK32;      // radix 2^k of the two FP32 liftering transforms (experiments: build.py --variant)
 template <int LOG2N, int THREADS>      // LOG2N 0: size given at run time (log2n_rt)
 __global__ void __launch_bounds__(THREADS, 768 / THREADS)
 cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __restrict__ frame_t,
@@ -172,7 +176,7 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
     float2* fb = reinterpret_cast<float2*>(buf);
     float* fbs = reinterpret_cast<float*>(buf);
     for (int i = tid; i < N; i += T) fbs[rfft_in_slot_f(i, log2m)] = static_cast<float>(aux[i <= half ? i : N - i]);
-    fft_dit<LM, false, THREADS, 4, TWL>(fb, log2m, twf);
+    fft_dit<LM, false, THREADS, kCtMaxK32, TWL>(fb, log2m, twf);
     float* lif = reinterpret_cast<float*>(aux);         // liftered cepstrum, real
     __syncthreads();                                     // everyone has read aux
     for (int k = tid; k <= half; k += T) {
@@ -192,7 +196,7 @@ cheaptrick_kernel(UttView u, const int* __restrict__ frame_utt, const double* __
       const float2 z = c2r_pack<TWL>(make_float2(lif[k], 0.f), make_float2(lif[half - k], 0.f), k, log2m, twf);
       fb[cpadf(brev(k, log2m))] = z;
     }
-    fft_dit<LM, true, THREADS, 4, TWL>(fb, log2m, twf);
+    fft_dit<LM, true, THREADS, kCtMaxK32, TWL>(fb, log2m, twf);
     // the liftered log spectrum is a float: the single-precision exponential (1 ulp) keeps everything it
     // holds at a quarter of the cost; below e^-80 (digital silence: the dither's spectrum) floats would
     // go subnormal, there the double exponential is used

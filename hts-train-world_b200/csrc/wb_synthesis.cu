@@ -617,6 +617,10 @@ __global__ void synth_ola_finish_kernel(double* __restrict__ y, long long n) {
     y[i] = static_cast<double>(reinterpret_cast<const long long*>(y)[i]) * (1.0 / kOlaScale);
 }
 
+#ifndef WB_SYNTH_MAXK
+#define WB_SYNTH_MAXK 4
+#endif
+constexpr int kSynthMaxK = WB_SYNTH_MAXK;      // radix 2^k of the items' transform passes (experiments: build.py --variant)
 template <int LOG2N, typename C, int THREADS = 256, int MINB = (sizeof(C) == 8 ? 1024 : 768) / THREADS>      // LOG2N 0: size given at run time (c.log2n)
 __global__ void __launch_bounds__(THREADS, MINB)
 synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ ap_all,
@@ -680,7 +684,7 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
       nzb[cpadT<C>(brev(i, log2n))] = mk2(n0, n1);
     }
   }
-  fft_dit<LOG2N, false, T, 4, TWL>(nzb, log2n, tw);       // C
+  fft_dit<LOG2N, false, T, kSynthMaxK, TWL>(nzb, log2n, tw);       // C
   // ---- log spectra (:45-51, :115-117), written as the even extension in bit-reversed order ----
   for (int k = tid; k <= half; k += T) {
     R l0 = 0, l1 = 0;
@@ -700,7 +704,7 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
     cbuf[cpadT<C>(brev(k, log2n))] = z;
     if (k > 0 && k < half) cbuf[cpadT<C>(brev(N - k, log2n))] = z;
   }
-  fft_dit<LOG2N, false, T, 4, TWL>(cbuf, log2n, tw);      // A
+  fft_dit<LOG2N, false, T, kSynthMaxK, TWL>(cbuf, log2n, tw);      // A
   // ---- fold the cepstra (common.cpp:194-206) -----------------------------------------------------
   {
     C keep[kQ];
@@ -722,7 +726,7 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
     }
     for (int i = half + 1 + tid; i < N; i += T) cbuf[cpadT<C>(brev(i, log2n))] = mk2(static_cast<R>(0), static_cast<R>(0));
   }
-  fft_dit<LOG2N, false, T, 4, TWL>(cbuf, log2n, tw);      // B
+  fft_dit<LOG2N, false, T, kSynthMaxK, TWL>(cbuf, log2n, tw);      // B
   // ---- minimum-phase spectra, time shift / noise product (:56-65, :88-100, :120-131) ------------
   {
     const double coefficient = per_item
@@ -778,7 +782,7 @@ synth_item_kernel(const double* __restrict__ sp_all, const double* __restrict__ 
       if (k > 0 && k < half) cbuf[cpadT<C>(brev(N - k, log2n))] = mk2(a.x + b.y, b.x - a.y);
     }
   }
-  fft_dit<LOG2N, true, T, 4, TWL>(cbuf, log2n, tw);       // D
+  fft_dit<LOG2N, true, T, kSynthMaxK, TWL>(cbuf, log2n, tw);       // D
   // ---- fftshift, RemoveDCComponent (:73-82), mix (:214-217), overlap-add (:376-383) -------------
   if (per_item) {
     double dc[1] = {0.0};
@@ -936,7 +940,15 @@ bool synthesis_run(Batch* b, const int* y_len) {
   } else {
     switch (log2n) {
       case 10: WB_SP_LAUNCH(10, float2, ctxp->tw_cf(10)); break;
+#ifdef WB_SYNTH_T128      // experiment (build.py --variant): 128-thread CTAs, six per SM
+      case 11:
+        WB_CUDA_OR_RETURN(cudaFuncSetAttribute(synth_item_kernel<11, float2, 128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), false);
+        synth_item_kernel<11, float2, 128, 6><<<n_items, 128, smem, st>>>(b->sp.p, b->ap.p, b->f_off.p, b->f_len.p, b->y_off.p, b->y_len.p, d_poff.p, d_cnt.p,
+            p_index.p, p_shift.p, p_vuv.p, p_utt.p, list_per.p, list_aper.p, n_per, n_aper, ctxp->d_randn, ctxp->tw_cf(11), d_rem.p, c, b->y.p);
+        break;
+#else
       case 11: WB_SP_LAUNCH(11, float2, ctxp->tw_cf(11)); break;
+#endif
       case 12: WB_SP_LAUNCH(12, float2, ctxp->tw_cf(12)); break;
       default: WB_SP_LAUNCH(0, float2, ctxp->d_twiddle_f); break;
     }
