@@ -484,7 +484,11 @@ def ours_arm(args):
     out_sets.append({k: torch.empty_like(v).pin_memory() for k, v in out_sets[0].items()})
     e2e_state = dict(step=0, prefetched=False)
 
+    e2e_skip = set(filter(None, os.environ.get("WB_E2E_SKIP", "").split(",")))   # developer aid: leave copies out to see what each costs
+
     def upload_part(q):
+        if "up" in e2e_skip and e2e_state["step"] > 1:
+            return
         q["c"].upload_pcm16_async(pcm_host[q["s"][0]:q["s"][1]])
 
     def step_e2e(more_to_come=True):
@@ -506,12 +510,15 @@ def ours_arm(args):
             # queue for that copy's whole PCIe time, and the host cannot launch the next stage
             # meanwhile (that was the 15 ms per step the end-to-end leg lost, profiles/README.md).
             cp.analyze(f0=args.f0)
-            wb._check(wb.lib().wb200_batch_get_f0(cp._h, wb.C.cast(o["f0"][fa:fb].data_ptr(), wb._dp), 1), "get_f0")
+            if "f0" not in e2e_skip:
+                wb._check(wb.lib().wb200_batch_get_f0(cp._h, wb.C.cast(o["f0"][fa:fb].data_ptr(), wb._dp), 1), "get_f0")
             cp.code(MGC_DIM, BAP_DIM)
             st += cp.feature_stats()
-            cp.coded_async(o["lf0"][fa:fb], o["mgc"][fa:fb], o["bap"][fa:fb])
+            if "coded" not in e2e_skip:
+                cp.coded_async(o["lf0"][fa:fb], o["mgc"][fa:fb], o["bap"][fa:fb])
             cp.synthesis()
-            cp.y_pcm16_async(o["y"][ya:yb])
+            if "wave" not in e2e_skip:
+                cp.y_pcm16_async(o["y"][ya:yb])
         if not more_to_come:
             wb.sync()                           # every asynchronous copy has landed
         return reduce_stats(st)
@@ -599,7 +606,42 @@ def ours_arm(args):
         e2e_calls["n"] += 1
         return step_e2e(more_to_come=e2e_calls["n"] < args.steps)
 
+    if os.environ.get("WB_E2E_TRACE"):        # developer aid: wall time of every call of one end-to-end step, device drained in between
+        def traced_e(name, fn):
+            torch.cuda.synchronize()
+            t_a = time.perf_counter()
+            r = fn()
+            torch.cuda.synchronize()
+            sys.stderr.write("[e2e step] %-16s %8.2f ms\n" % (name, 1e3 * (time.perf_counter() - t_a)))
+            return r
+        o = out_sets[0]
+        for i, q in enumerate(parts):
+            cp, (fa, fb), (ya, yb) = q["c"], q["f"], q["y"]
+            traced_e("upload", lambda: upload_part(q))
+            traced_e("dio", cp.dio)
+            traced_e("stonemask", cp.stonemask)
+            traced_e("cheaptrick", cp.cheaptrick)
+            traced_e("d4c", lambda: cp.d4c(threshold=0.0))
+            traced_e("get_f0", lambda: wb._check(wb.lib().wb200_batch_get_f0(cp._h, wb.C.cast(o["f0"][fa:fb].data_ptr(), wb._dp), 1), "get_f0"))
+            traced_e("code", lambda: cp.code(MGC_DIM, BAP_DIM))
+            traced_e("feature_stats", cp.feature_stats)
+            traced_e("coded_async", lambda: cp.coded_async(o["lf0"][fa:fb], o["mgc"][fa:fb], o["bap"][fa:fb]))
+            traced_e("synthesis", cp.synthesis)
+            traced_e("y_pcm16_async", lambda: cp.y_pcm16_async(o["y"][ya:yb]))
+        wb.sync()
+        e2e_state["prefetched"] = False
+    e2e_ktime = None
+    if os.environ.get("WB_E2E_KTIME"):        # developer aid: the library's per-kernel event timers during the end-to-end leg
+        wb.kernel_timing(True)
+        wb.kernel_times_reset()
     ms_e, wall_e, _, _ = timed(step_e2e_timed, args.steps)
+    if os.environ.get("WB_E2E_KTIME"):
+        e2e_ktime = {k: wb.kernel_time(k)[0] / args.steps for k in kernel_ms}
+        e2e_ktime = {k: v for k, v in e2e_ktime.items() if v}
+        e2e_ktime["sum"] = sum(e2e_ktime.values())
+        e2e_ktime["stages_last_sub_batch"] = wb.stage_times()
+        wb.kernel_timing(False)
+        sys.stderr.write("[e2e] rank %d kernels %s\n" % (rank, json.dumps(e2e_ktime)))
     e2e_value = audio_total * args.steps / (max(ms_e, wall_e) * 1e-3)
     h2d = pcm_host.numel() * 2
     d2h = y_host.numel() * 2 + f0_host.numel() * 8 + (lf0_host.numel() + mgc_host.numel() + bap_host.numel()) * 4 + \

@@ -95,6 +95,10 @@ bool ensure_randn(size_t count);          // grow the randn table to >= count va
 // pipelined run) and stall the compute stream for that copy's whole PCIe time; instead a small
 // kernel stores the words into mapped pinned host memory, which involves no copy engine.
 bool read_back(void* h_dst, const void* d_src, size_t bytes);
+// Small host -> device copy on the library stream without a copy engine (mapped pinned ring + a copy kernel):
+// the tables a stage sends ahead of its kernels must not queue behind a bulk upload on the upload stream.
+// The source may be reused on return.  d_dst 4-byte aligned.
+bool write_dev(void* d_dst, const void* h_src, size_t bytes);
 
 // Optional per-kernel device timing (CUDA events on the library stream around one launch).
 // Off by default; bench.py switches it on to measure the dominant kernel live.

@@ -418,6 +418,53 @@ bool read_back(void* h_dst, const void* d_src, size_t bytes) {
   return true;
 }
 
+// The opposite direction for the small host -> device tables a stage sends ahead of its kernels (offsets,
+// lengths, window coefficients): a cudaMemcpyAsync would queue on the host-to-device copy engine BEHIND the bulk
+// upload of the next batch that a pipelined caller has in flight on the upload stream (hundreds of MB: the
+// stage that runs beside an upload -- Dio -- lost the upload's whole PCIe time, ~4 ms per sub-batch of the
+// end-to-end leg).  The bytes go into a ring of mapped pinned host memory and a small kernel on the library
+// stream copies them from there; no copy engine is involved.  Like cudaMemcpyAsync from pageable memory the
+// source may be reused as soon as the call returns.  bytes need not be a multiple of 4 (the ring is padded).
+static void* g_wd_host = nullptr;
+static uint32_t* g_wd_dev = nullptr;
+static size_t g_wd_cap = 0, g_wd_off = 0;
+__global__ void write_dev_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, size_t n_words, size_t tail_bytes) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_words; i += stride) dst[i] = src[i];
+  if (tail_bytes && blockIdx.x == 0 && threadIdx.x < tail_bytes)
+    reinterpret_cast<unsigned char*>(dst + n_words)[threadIdx.x] = reinterpret_cast<const unsigned char*>(src + n_words)[threadIdx.x];
+}
+bool write_dev(void* d_dst, const void* h_src, size_t bytes) {
+  Context* c = ctx();
+  if (!c) return false;
+  if (bytes == 0) return true;
+  if ((reinterpret_cast<uintptr_t>(d_dst) & 3) != 0) { set_error("write_dev: destination is not 4-byte aligned"); return false; }
+  std::lock_guard<std::mutex> lock(g_rb_mutex);
+  const size_t need = (bytes + 15) & ~(size_t)15;
+  if (need > g_wd_cap) {
+    size_t cap = (size_t)16 << 20;
+    while (cap < 2 * need) cap <<= 1;
+    if (g_wd_host) { cudaStreamSynchronize(c->stream); cudaFreeHost(g_wd_host); g_wd_host = nullptr; g_wd_dev = nullptr; g_wd_cap = 0; }
+    if (!WB_CUDA(cudaHostAlloc(&g_wd_host, cap, cudaHostAllocMapped))) { g_wd_host = nullptr; return false; }
+    if (!WB_CUDA(cudaHostGetDevicePointer((void**)&g_wd_dev, g_wd_host, 0))) {
+      cudaFreeHost(g_wd_host); g_wd_host = nullptr; g_wd_dev = nullptr;
+      return false;
+    }
+    g_wd_cap = cap; g_wd_off = 0;
+  }
+  if (g_wd_off + need > g_wd_cap) {                  // the ring wraps: everything queued so far must have read its slice
+    if (!WB_CUDA(cudaStreamSynchronize(c->stream))) return false;
+    g_wd_off = 0;
+  }
+  memcpy(static_cast<char*>(g_wd_host) + g_wd_off, h_src, bytes);
+  const size_t n_words = bytes / 4;
+  const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((n_words + 255) / 256, (size_t)c->sm_count));
+  write_dev_kernel<<<blocks, 256, 0, c->stream>>>(g_wd_dev + g_wd_off / 4, static_cast<uint32_t*>(d_dst), n_words, bytes & 3);
+  WB_LAUNCH_CHECK();
+  g_wd_off += need;
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // segmented exclusive scan over the frames of each utterance (one CTA per utterance)
 // ---------------------------------------------------------------------------------------------

@@ -824,7 +824,7 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
       !offs_lt.alloc(total_frames) || !offs_main.alloc(total_frames) || !tot_lt.alloc(u.n_utt) ||
       !tot_main.alloc(u.n_utt))
     return false;
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_win.p, h_win.data(), c.window_length * sizeof(double), cudaMemcpyHostToDevice, st), false);
+  if (!write_dev(d_win.p, h_win.data(), c.window_length * sizeof(double))) return false;
 
   const int nblk = (total_frames + 255) / 256;
   std::vector<long long> h_lt(u.n_utt), h_main(u.n_utt);

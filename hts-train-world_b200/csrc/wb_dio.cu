@@ -295,8 +295,8 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
       !d_cand.alloc((size_t)c.nb * TF) || !d_score.alloc((size_t)c.nb * TF) || !d_tmp1.alloc(TF) ||
       !d_tmp2.alloc(TF) || !d_pos.alloc(TF) || !d_neg.alloc(TF))
     return false;
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_ylen.p, h_ylen.data(), n_utt * sizeof(int), cudaMemcpyHostToDevice, st), false);
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_mask.p, h_mask.data(), n_utt * sizeof(int), cudaMemcpyHostToDevice, st), false);
+  if (!write_dev(d_ylen.p, h_ylen.data(), n_utt * sizeof(int))) return false;
+  if (!write_dev(d_mask.p, h_mask.data(), n_utt * sizeof(int))) return false;
   WB_CUDA_OR_RETURN(cudaMemsetAsync(d_f0_out, 0, (size_t)TF * sizeof(double), st), false);
   // the signal the bands are computed from: x itself, or its decimated copy when speed > 1 (:69-71)
   const double* xin = b->x.p;
@@ -324,7 +324,7 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
   for (int i = 0; i < c.nb; ++i) h_shift[i] = c.D + 2 * c.hal[i] + c.hN;
   DevBuf<int> d_shift;
   if (!d_shift.alloc(c.nb)) return false;
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_shift.p, h_shift.data(), c.nb * sizeof(int), cudaMemcpyHostToDevice, st), false);
+  if (!write_dev(d_shift.p, h_shift.data(), c.nb * sizeof(int))) return false;
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
 
   // sub-batches bounded by the size of the filtered-signal scratch (nb * y_len doubles per utterance)
@@ -381,7 +381,7 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
         long long etot = 0;
         for (int l = 0; l < n_lists; ++l) { h_loff[l] = etot; etot += h_ltot[l]; }
         if (!d_edges.alloc((size_t)etot + 2)) return false;
-        WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_loff.p, h_loff.data(), n_lists * sizeof(long long), cudaMemcpyHostToDevice, st), false);
+        if (!write_dev(d_loff.p, h_loff.data(), n_lists * sizeof(long long))) return false;
         KernelTimer kt3("dio_zc_kernel");
         zc_seg_gather_kernel<<<n_lists, 128, 0, st>>>(d_segcnt.p, d_segoff.p, d_seg.p, n_blocks, kZcSegCap, d_loff.p, d_edges.p);
         WB_LAUNCH_CHECK(); kt3.stop();
@@ -393,7 +393,7 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
       const int n_blocks = (max_y + c.V - 1) / c.V;
       const int n_chunks = (max_y + kZcChunk - 1) / kZcChunk;
       if (!d_F.alloc(tot) || !d_foff.alloc(nu) || !d_counts.alloc((size_t)n_lists * n_chunks)) return false;
-      WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_foff.p, h_foff.data(), nu * sizeof(long long), cudaMemcpyHostToDevice, st), false);
+      if (!write_dev(d_foff.p, h_foff.data(), nu * sizeof(long long))) return false;
       KernelTimer kt1("dio_filter_kernel");
       // 150 KB of shared memory per block leave one CTA per SM: 512 threads (16 warps) hide the latency of
       // the multiply / pack / store sweeps even though only 256 of them own a radix-16 group (-16 %)
@@ -413,7 +413,7 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
       long long etot = 0;
       for (int l = 0; l < n_lists; ++l) { h_loff[l] = etot; etot += h_ltot[l]; }
       if (!d_edges.alloc((size_t)etot + 2)) return false;
-      WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_loff.p, h_loff.data(), n_lists * sizeof(long long), cudaMemcpyHostToDevice, st), false);
+      if (!write_dev(d_loff.p, h_loff.data(), n_lists * sizeof(long long))) return false;
       KernelTimer kt3("dio_zc_kernel");
       zc_kernel<true><<<dim3(n_chunks, nu * c.nb), 256, 0, st>>>(d_F.p, d_foff.p, d_ylen.p, c.nb, u0, n_chunks, d_counts.p, d_loff.p, d_edges.p);
       WB_LAUNCH_CHECK(); kt3.stop();

@@ -1155,9 +1155,9 @@ bool decimate_run(const Batch* b, int r, const std::vector<int>& want_len, DevBu
   DevBuf<double> d_B;
   DevBuf<long long> d_boff;
   if (!y->alloc(ytot + 2) || !y_off->alloc(n_utt) || !y_len->alloc(n_utt) || !d_B.alloc(btot) || !d_boff.alloc(n_utt)) return false;
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(y_off->p, h_yoff.data(), n_utt * sizeof(long long), cudaMemcpyHostToDevice, st), false);
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(y_len->p, out_len->data(), n_utt * sizeof(int), cudaMemcpyHostToDevice, st), false);
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_boff.p, h_boff.data(), n_utt * sizeof(long long), cudaMemcpyHostToDevice, st), false);
+  if (!write_dev(y_off->p, h_yoff.data(), n_utt * sizeof(long long))) return false;
+  if (!write_dev(y_len->p, out_len->data(), n_utt * sizeof(int))) return false;
+  if (!write_dev(d_boff.p, h_boff.data(), n_utt * sizeof(long long))) return false;
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
   const int n_chunks = (max_M + kIirChunk - 1) / kIirChunk;
   harvest_iir_fwd_kernel<<<dim3((n_chunks + 63) / 64, n_utt), 64, 0, st>>>(b->x.p, b->x_off.p, b->x_len.p, d_boff.p, c, n_chunks, d_B.p);
@@ -1230,7 +1230,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
       !d_base.alloc((size_t)gtot * max_base))
     return false;
   std::vector<int> h_mask(n_utt, 0x3fffffff);
-  auto up = [&](void* dst, const void* src, size_t bytes) { return WB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st)); };
+  auto up = [&](void* dst, const void* src, size_t bytes) { return write_dev(dst, src, bytes); };
   if (!up(d_ylen.p, h_ylen.data(), n_utt * sizeof(int)) || !up(d_glen.p, h_glen.data(), n_utt * sizeof(int)) ||
       !up(d_goff.p, h_goff.data(), n_utt * sizeof(int)) || !up(d_mask.p, h_mask.data(), n_utt * sizeof(int)) ||
       !up(d_yoff.p, h_yoff.data(), n_utt * sizeof(long long)) || !up(d_boff.p, h_boff.data(), n_utt * sizeof(long long)))

@@ -835,8 +835,8 @@ bool synthesis_run(Batch* b, const int* y_len) {
   b->total_y = o;
   if (!b->y.alloc((size_t)o) || !b->y_off.alloc(n_utt) || !b->y_len.alloc(n_utt)) return false;
   if (n_utt == 0) return true;
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(b->y_off.p, b->h_y_off.data(), n_utt * sizeof(long long), cudaMemcpyHostToDevice, st), false);
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(b->y_len.p, b->h_y_len.data(), n_utt * sizeof(int), cudaMemcpyHostToDevice, st), false);
+  if (!write_dev(b->y_off.p, b->h_y_off.data(), n_utt * sizeof(long long))) return false;
+  if (!write_dev(b->y_len.p, b->h_y_len.data(), n_utt * sizeof(int))) return false;
   WB_CUDA_OR_RETURN(cudaMemsetAsync(b->y.p, 0, (size_t)o * sizeof(double), st), false);
 
   SynthConst c;
@@ -862,7 +862,7 @@ bool synthesis_run(Batch* b, const int* y_len) {
   DevBuf<double> p_shift, d_rem;
   DevBuf<unsigned char> p_vuv;
   if (!p_index.alloc(total_p) || !p_utt.alloc(total_p) || !p_shift.alloc(total_p) || !p_vuv.alloc(total_p) || !d_rem.alloc(N)) return false;
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_poff.p, h_poff.data(), n_utt * sizeof(int), cudaMemcpyHostToDevice, st), false);
+  if (!write_dev(d_poff.p, h_poff.data(), n_utt * sizeof(int))) return false;
   WB_CUDA_OR_RETURN(cudaMemsetAsync(p_utt.p, 0xff, (size_t)total_p * sizeof(int), st), false);   // -1 = unused slot
   {
     const int n_chunks_max = (max_y + kTbChunk - 1) / kTbChunk + 1;
@@ -898,7 +898,7 @@ bool synthesis_run(Batch* b, const int* y_len) {
     dc_component += rem[i] * 2.0;
   }
   for (int i = 0; i < N / 2; ++i) { rem[i] /= dc_component; rem[N - i - 1] = rem[i]; }
-  WB_CUDA_OR_RETURN(cudaMemcpyAsync(d_rem.p, rem.data(), N * sizeof(double), cudaMemcpyHostToDevice, st), false);
+  if (!write_dev(d_rem.p, rem.data(), N * sizeof(double))) return false;
   // classify the pulses into periodic / non-periodic work lists
   DevBuf<int> d_cnt2, list_per, list_aper, d_blk;
   const int n_cblocks = (int)((total_p + 255) / 256);
