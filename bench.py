@@ -514,11 +514,19 @@ def ours_arm(args):
                 wb._check(wb.lib().wb200_batch_get_f0(cp._h, wb.C.cast(o["f0"][fa:fb].data_ptr(), wb._dp), 1), "get_f0")
             cp.code(MGC_DIM, BAP_DIM)
             st += cp.feature_stats()
-            if "coded" not in e2e_skip:
+            # Both bulk copies are queued BEHIND Synthesis: its first milliseconds read three small counts back
+            # (pulse bounds, list sizes), and a read-back completes only when a bulk device-to-host copy that is
+            # in flight has drained -- the features' copy (114 MB per sub-batch) cost its whole PCIe time when it
+            # was queued in front of Synthesis (measured: 198.9 -> 194.5 ms per step).  Behind Synthesis the copies
+            # run beside the next sub-batch's Dio, whose first read-back comes after its 5 ms filter kernel.
+            early = "early" in e2e_skip
+            if "coded" not in e2e_skip and early:
                 cp.coded_async(o["lf0"][fa:fb], o["mgc"][fa:fb], o["bap"][fa:fb])
             cp.synthesis()
             if "wave" not in e2e_skip:
                 cp.y_pcm16_async(o["y"][ya:yb])
+            if "coded" not in e2e_skip and not early:
+                cp.coded_async(o["lf0"][fa:fb], o["mgc"][fa:fb], o["bap"][fa:fb])
         if not more_to_come:
             wb.sync()                           # every asynchronous copy has landed
         return reduce_stats(st)

@@ -44,6 +44,18 @@ bool ensure_copy_streams(Context* c) {
   return true;
 }
 enum { kDlCoded = 0, kDlWave = 1 };
+// A bulk copy between pinned host memory and the device as a sequence of 8 MiB pieces.  A small transfer that the
+// compute stream is waiting for (read_back's words, written by a kernel into mapped host memory) completed only
+// when a bulk copy in flight on another stream did -- the features' 114 MB cost the end-to-end leg their whole
+// PCIe time although nothing depended on them; between two pieces the small transfer gets through.
+static bool bulk_copy_async(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
+  const size_t piece = (size_t)8 << 20;
+  for (size_t o = 0; o < bytes; o += piece) {
+    const size_t n = bytes - o < piece ? bytes - o : piece;
+    if (!WB_CUDA(cudaMemcpyAsync(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, n, kind, st))) return false;
+  }
+  return true;
+}
 bool wait_downloads(wb200_batch* h, int which) {        // the buffer `which` is about to be rewritten
   if (!h->download_pending[which]) return true;
   h->download_pending[which] = false;
@@ -473,7 +485,7 @@ int wb200_batch_upload_pcm16_async(wb200_batch* h, const int16_t* host_pcm) {
   // x may still be read by work queued on the library stream: order the upload behind it
   if (!WB_CUDA(cudaEventRecord(c->copy_event, c->stream)) || !WB_CUDA(cudaStreamWaitEvent(c->upload_stream, c->copy_event, 0))) return 1;
   if (n > 0) {
-    if (!WB_CUDA(cudaMemcpyAsync(h->pcm_stage.p, host_pcm, (size_t)n * sizeof(int16_t), cudaMemcpyHostToDevice, c->upload_stream))) return 1;
+    if (!bulk_copy_async(h->pcm_stage.p, host_pcm, (size_t)n * sizeof(int16_t), cudaMemcpyHostToDevice, c->upload_stream)) return 1;
     pcm16_to_double_kernel<<<dim3(64, b.n_utt), 256, 0, c->upload_stream>>>(h->pcm_stage.p, h->src_off.p, b.x_off.p, b.x_len.p, b.x.p);
     WB_LAUNCH_CHECK();
   }
@@ -685,7 +697,7 @@ int wb200_batch_get_y_pcm16_async(wb200_batch* h, int16_t* out) {
   y_to_pcm16_kernel<<<dim3(64, b.n_utt), 256, 0, c->stream>>>(b.y.p, b.y_off.p, h->out_off.p, b.y_len.p, h->pcm_out.p);
   WB_LAUNCH_CHECK();
   return (WB_CUDA(cudaEventRecord(c->copy_event, c->stream)) && WB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_event, 0)) &&
-          WB_CUDA(cudaMemcpyAsync(out, h->pcm_out.p, (size_t)n * sizeof(int16_t), cudaMemcpyDeviceToHost, c->copy_stream)) &&
+          bulk_copy_async(out, h->pcm_out.p, (size_t)n * sizeof(int16_t), cudaMemcpyDeviceToHost, c->copy_stream) &&
           mark_downloads(h, kDlWave)) ? 0 : 1;
 }
 // one utterance's slice of every result (any pointer may be NULL)
@@ -756,9 +768,9 @@ int wb200_batch_get_coded_async(wb200_batch* h, float* lf0, float* mgc, float* b
   const size_t F = (size_t)b.total_frames;
   bool ok = WB_CUDA(cudaEventRecord(c->copy_event, c->stream)) &&
             WB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_event, 0));
-  if (ok && lf0) ok = WB_CUDA(cudaMemcpyAsync(lf0, b.lf0.p, F * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
-  if (ok && mgc) ok = WB_CUDA(cudaMemcpyAsync(mgc, b.mgc.p, F * b.mgc_dim * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
-  if (ok && bap) ok = WB_CUDA(cudaMemcpyAsync(bap, b.bap.p, F * b.bap_dim * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+  if (ok && lf0) ok = bulk_copy_async(lf0, b.lf0.p, F * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream);
+  if (ok && mgc) ok = bulk_copy_async(mgc, b.mgc.p, F * b.mgc_dim * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream);
+  if (ok && bap) ok = bulk_copy_async(bap, b.bap.p, F * b.bap_dim * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream);
   return ok && mark_downloads(h, kDlCoded) ? 0 : 1;
 }
 __global__ void mgc_unscale_kernel(const float* __restrict__ mgc, long long n, int ndim, double* __restrict__ out) {
@@ -838,7 +850,7 @@ int wb200_batch_get_cmp_async(wb200_batch* h, float* out) {
   if (!ensure_copy_streams(c)) return 1;
   const size_t n = (size_t)b.total_frames * b.cmp_dim;
   bool ok = WB_CUDA(cudaEventRecord(c->copy_event, c->stream)) && WB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_event, 0));
-  if (ok && n > 0) ok = WB_CUDA(cudaMemcpyAsync(out, b.cmp.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+  if (ok && n > 0) ok = bulk_copy_async(out, b.cmp.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream);
   return ok && mark_downloads(h, kDlCoded) ? 0 : 1;
 }
 int wb200_batch_cmp_stats(wb200_batch* h, double* out) {

@@ -163,7 +163,7 @@ bool batch_cmp_stats(Batch* b, double* h_out) {   // [cmp_dim][3]
   DevBuf<double> d;
   if (!d.alloc((size_t)nd * 3)) return false;
   cudaStream_t st = c->stream;
-  WB_CUDA_OR_RETURN(cudaMemsetAsync(d.p, 0, (size_t)nd * 3 * sizeof(double), st), false);
+  if (!dev_fill(d.p, 0, (size_t)nd * 3 * sizeof(double))) return false;
   if (F > 0) {
     if (nd > 1024) { set_error("cmp stats: %d columns (<= 1024 supported)", nd); return false; }
     const int threads = nd * (256 / nd > 0 ? 256 / nd : 1);

@@ -436,7 +436,7 @@ bool batch_feature_stats(Batch* b, double* h_out) {   // [(1 + mgc_dim)][3]: lf0
   DevBuf<double> d;
   if (!d.alloc((size_t)(nd + 1) * 3)) return false;
   cudaStream_t st = c->stream;
-  WB_CUDA_OR_RETURN(cudaMemsetAsync(d.p, 0, (size_t)(nd + 1) * 3 * sizeof(double), st), false);
+  if (!dev_fill(d.p, 0, (size_t)(nd + 1) * 3 * sizeof(double))) return false;
   if (F > 0) {
     if (nd > 1024) { set_error("stats: %d dimensions (<= 1024 supported)", nd); return false; }
     const int threads = nd * std::max(1, 256 / nd);

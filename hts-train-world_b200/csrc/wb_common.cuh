@@ -99,6 +99,8 @@ bool read_back(void* h_dst, const void* d_src, size_t bytes);
 // the tables a stage sends ahead of its kernels must not queue behind a bulk upload on the upload stream.
 // The source may be reused on return.  d_dst 4-byte aligned.
 bool write_dev(void* d_dst, const void* h_src, size_t bytes);
+// cudaMemsetAsync on the library stream as a kernel (never a copy engine, see wb_context.cu); 4-byte granularity.
+bool dev_fill(void* d_ptr, int byte_value, size_t bytes);
 
 // Optional per-kernel device timing (CUDA events on the library stream around one launch).
 // Off by default; bench.py switches it on to measure the dominant kernel live.

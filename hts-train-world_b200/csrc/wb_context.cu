@@ -418,6 +418,35 @@ bool read_back(void* h_dst, const void* d_src, size_t bytes) {
   return true;
 }
 
+// cudaMemsetAsync as a kernel.  The driver may execute a memset on a copy engine; when that engine is busy with
+// a bulk copy of another stream (the coded features leaving while Synthesis starts by zeroing its 1.6 GB of
+// accumulators) the memset -- and the compute stream behind it -- waits for the whole copy: the features cost
+// the end-to-end leg their full PCIe time.  ptr and bytes must be multiples of 4.
+__global__ void dev_fill_kernel(uint32_t* __restrict__ p, uint32_t v, size_t n_words) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    uint4* p4 = reinterpret_cast<uint4*>(p);
+    const size_t n4 = n_words / 4;
+    for (size_t k = i; k < n4; k += stride) p4[k] = make_uint4(v, v, v, v);
+    for (size_t k = n4 * 4 + i; k < n_words; k += stride) p[k] = v;
+  } else {
+    for (; i < n_words; i += stride) p[i] = v;
+  }
+}
+bool dev_fill(void* d_ptr, int byte_value, size_t bytes) {
+  Context* c = ctx();
+  if (!c) return false;
+  if (bytes == 0) return true;
+  if ((reinterpret_cast<uintptr_t>(d_ptr) & 3) || (bytes & 3)) { set_error("dev_fill: pointer / size not a multiple of 4"); return false; }
+  const uint32_t b = (uint32_t)(byte_value & 0xff), v = b | (b << 8) | (b << 16) | (b << 24);
+  const size_t n_words = bytes / 4;
+  const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((n_words / 4 + 255) / 256, (size_t)c->sm_count * 8));
+  dev_fill_kernel<<<blocks, 256, 0, c->stream>>>(static_cast<uint32_t*>(d_ptr), v, n_words);
+  WB_LAUNCH_CHECK();
+  return true;
+}
+
 // The opposite direction for the small host -> device tables a stage sends ahead of its kernels (offsets,
 // lengths, window coefficients): a cudaMemcpyAsync would queue on the host-to-device copy engine BEHIND the bulk
 // upload of the next batch that a pipelined caller has in flight on the upload stream (hundreds of MB: the

@@ -297,7 +297,7 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
     return false;
   if (!write_dev(d_ylen.p, h_ylen.data(), n_utt * sizeof(int))) return false;
   if (!write_dev(d_mask.p, h_mask.data(), n_utt * sizeof(int))) return false;
-  WB_CUDA_OR_RETURN(cudaMemsetAsync(d_f0_out, 0, (size_t)TF * sizeof(double), st), false);
+  if (!dev_fill(d_f0_out, 0, (size_t)TF * sizeof(double))) return false;
   // the signal the bands are computed from: x itself, or its decimated copy when speed > 1 (:69-71)
   const double* xin = b->x.p;
   const long long* xin_off = b->x_off.p;
@@ -362,8 +362,8 @@ bool dio_run(Batch* b, const DioParams& p, double* d_f0_out) {
       if (!d_segcnt.alloc((size_t)n_lists * n_blocks) || !d_segoff.alloc((size_t)n_lists * n_blocks) ||
           !d_seg.alloc((size_t)n_lists * n_blocks * kZcSegCap))
         return false;
-      WB_CUDA_OR_RETURN(cudaMemsetAsync(d_segcnt.p, 0, (size_t)n_lists * n_blocks * sizeof(int), st), false);
-      WB_CUDA_OR_RETURN(cudaMemsetAsync(d_ltot.p + n_lists, 0, sizeof(int), st), false);
+      if (!dev_fill(d_segcnt.p, 0, (size_t)n_lists * n_blocks * sizeof(int))) return false;
+      if (!dev_fill(d_ltot.p + n_lists, 0, sizeof(int))) return false;
       {
         KernelTimer kt1("dio_filter_kernel");
         if (c.log2bn == 13)

@@ -1235,7 +1235,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
       !up(d_goff.p, h_goff.data(), n_utt * sizeof(int)) || !up(d_mask.p, h_mask.data(), n_utt * sizeof(int)) ||
       !up(d_yoff.p, h_yoff.data(), n_utt * sizeof(long long)) || !up(d_boff.p, h_boff.data(), n_utt * sizeof(long long)))
     return false;
-  WB_CUDA_OR_RETURN(cudaMemsetAsync(d_nc.p, 0, n_utt * sizeof(int), st), false);
+  if (!dev_fill(d_nc.p, 0, n_utt * sizeof(int))) return false;
   WB_CUDA_OR_RETURN(cudaStreamSynchronize(st), false);
 
   phase("tables");
@@ -1315,8 +1315,8 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
       if (!d_segcnt.alloc((size_t)n_lists * n_blocks) || !d_segoff.alloc((size_t)n_lists * n_blocks) ||
           !d_seg.alloc((size_t)n_lists * n_blocks * kCap))
         return false;
-      WB_CUDA_OR_RETURN(cudaMemsetAsync(d_segcnt.p, 0, (size_t)n_lists * n_blocks * sizeof(int), st), false);
-      WB_CUDA_OR_RETURN(cudaMemsetAsync(d_ltot.p + n_lists, 0, sizeof(int), st), false);
+      if (!dev_fill(d_segcnt.p, 0, (size_t)n_lists * n_blocks * sizeof(int))) return false;
+      if (!dev_fill(d_ltot.p + n_lists, 0, sizeof(int))) return false;
       phase("sub-batch: segment buffers");
       {
         KernelTimer kt("harvest_filter_kernel");
@@ -1504,7 +1504,7 @@ bool harvest_run(Batch* b, const HarvestParams& p, double* d_f0_out) {
   }
   phase("contour logic");
   // smoothing: step4 is in tmp1; the smoothed basic contour goes to tmp2 (zero where unvoiced)
-  WB_CUDA_OR_RETURN(cudaMemsetAsync(d_tmp2.p, 0, (size_t)gtot * sizeof(double), st), false);
+  if (!dev_fill(d_tmp2.p, 0, (size_t)gtot * sizeof(double))) return false;
   harvest_sections_kernel<<<n_utt, 32, 0, st>>>(d_tmp1.p, d_goff.p, d_glen.p, d_bl.p, d_nsec.p);
   WB_LAUNCH_CHECK();
   if (!read_back(h_nsec.data(), d_nsec.p, n_utt * sizeof(int))) return false;

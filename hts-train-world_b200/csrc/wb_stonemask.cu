@@ -304,7 +304,7 @@ bool stonemask_run(const UttView& u, int fs, int total_frames, const int* frame_
   }
   DevBuf<int> d_max;
   if (!d_max.alloc(1)) return false;
-  WB_CUDA_OR_RETURN(cudaMemsetAsync(d_max.p, 0, sizeof(int), st), false);
+  if (!dev_fill(d_max.p, 0, sizeof(int))) return false;
   stonemask_maxfft_kernel<<<std::min(1024, (total_frames + 255) / 256), 256, 0, st>>>(f0_in, total_frames, fs, d_max.p);
   WB_LAUNCH_CHECK();
   int h_max = 0;

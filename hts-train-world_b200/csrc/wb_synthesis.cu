@@ -837,7 +837,7 @@ bool synthesis_run(Batch* b, const int* y_len) {
   if (n_utt == 0) return true;
   if (!write_dev(b->y_off.p, b->h_y_off.data(), n_utt * sizeof(long long))) return false;
   if (!write_dev(b->y_len.p, b->h_y_len.data(), n_utt * sizeof(int))) return false;
-  WB_CUDA_OR_RETURN(cudaMemsetAsync(b->y.p, 0, (size_t)o * sizeof(double), st), false);
+  if (!dev_fill(b->y.p, 0, (size_t)o * sizeof(double))) return false;
 
   SynthConst c;
   c.fs = b->fs;
@@ -863,7 +863,7 @@ bool synthesis_run(Batch* b, const int* y_len) {
   DevBuf<unsigned char> p_vuv;
   if (!p_index.alloc(total_p) || !p_utt.alloc(total_p) || !p_shift.alloc(total_p) || !p_vuv.alloc(total_p) || !d_rem.alloc(N)) return false;
   if (!write_dev(d_poff.p, h_poff.data(), n_utt * sizeof(int))) return false;
-  WB_CUDA_OR_RETURN(cudaMemsetAsync(p_utt.p, 0xff, (size_t)total_p * sizeof(int), st), false);   // -1 = unused slot
+  if (!dev_fill(p_utt.p, 0xff, (size_t)total_p * sizeof(int))) return false;   // -1 = unused slot
   {
     const int n_chunks_max = (max_y + kTbChunk - 1) / kTbChunk + 1;
     DevBuf<double> d_inc, d_tot;
@@ -903,7 +903,7 @@ bool synthesis_run(Batch* b, const int* y_len) {
   DevBuf<int> d_cnt2, list_per, list_aper, d_blk;
   const int n_cblocks = (int)((total_p + 255) / 256);
   if (!d_cnt2.alloc(2) || !list_per.alloc(total_p) || !list_aper.alloc(total_p) || !d_blk.alloc(2 * (size_t)std::max(1, n_cblocks))) return false;
-  WB_CUDA_OR_RETURN(cudaMemsetAsync(d_cnt2.p, 0, 2 * sizeof(int), st), false);
+  if (!dev_fill(d_cnt2.p, 0, 2 * sizeof(int))) return false;
   if (n_cblocks > 0) {
     synth_classify_kernel<false><<<n_cblocks, 256, 0, st>>>(b->ap.p, b->f_off.p, b->f_len.p, p_index.p, p_vuv.p, p_utt.p, (int)total_p, c,
                                                           d_blk.p, list_per.p, list_aper.p);

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Developer tool (GPU box), round 2 call Y: what each copy of the end-to-end leg costs (one left out at a time)
 mkdir -p gpurun_out
-for sk in "" up coded wave f0 "up,coded,wave,f0"; do
+for sk in "" up coded wave; do
 WB_E2E_SKIP=$sk timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-configs --verify 0 > gpurun_out/r2y.json 2> gpurun_out/r2y.err; 
 python - "$sk" <<'PY'
 import json, sys
