@@ -18,4 +18,3 @@ SMALL="python bench.py --utts 64 --steps 1 --warmup 1 --no-cpu-baseline --no-con
 KRE='regex:dio_|d4c_|cheaptrick|synth_|stonemask|seg_scan|pcm16|lf0_|stats|default_frames|randn_table|ols_filter|zc_|codec|gv_|feature_|widen|read_back'
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KRE" -c 600 --csv --log-file gpurun_out/r2p_launches.csv $SMALL > gpurun_out/r2p_ncu_small.log 2>&1; echo "launch list exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:d4c_main|synth_item|cheaptrick_kernel|stonemask_dft|lovetrain|ols_filter_zc|codec_encode|synth_phase" -c 10 -f -o gpurun_out/r2p_prof $SMALL > gpurun_out/r2p_ncu_full.log 2>&1; echo "ncu full (64 utts) exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:d4c_main_kernel" -c 1 -f -o gpurun_out/r2p_prof_d4c_1132 python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-configs --verify 0 > gpurun_out/r2p_ncu_d4c.log 2>&1; echo "ncu d4c_main (1132 utts) exit $?"
