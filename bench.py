@@ -606,6 +606,10 @@ def ours_arm(args):
             traced("feature_stats", c.feature_stats)
 
     # ---- end to end from host memory --------------------------------------------------------------
+    # deferred copies: the bulk uploads / downloads of the pipeline start right before D4C's main kernel instead
+    # of beside a stage whose read-backs they would delay (include/world_b200.h); WB_E2E_DEFER=0 switches it off
+    defer = os.environ.get("WB_E2E_DEFER", "1") != "0"
+    wb.set_copy_deferral(defer)
     step_e2e()
     step_e2e(more_to_come=False)
     e2e_calls = dict(n=0)
@@ -650,6 +654,7 @@ def ours_arm(args):
         e2e_ktime["stages_last_sub_batch"] = wb.stage_times()
         wb.kernel_timing(False)
         sys.stderr.write("[e2e] rank %d kernels %s\n" % (rank, json.dumps(e2e_ktime)))
+    wb.set_copy_deferral(False)
     e2e_value = audio_total * args.steps / (max(ms_e, wall_e) * 1e-3)
     h2d = pcm_host.numel() * 2
     d2h = y_host.numel() * 2 + f0_host.numel() * 8 + (lf0_host.numel() + mgc_host.numel() + bap_host.numel()) * 4 + \
@@ -753,7 +758,7 @@ def ours_arm(args):
                    "parallelism": "utterance-sharded x%d, no hot-path collective" % world,
                    "l2": "inputs larger than L2 (%.0f MB PCM, GBs of intermediates per step)" % (h2d / 1e6)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": max(ms_e, wall_e) / args.steps, "pipelined_sub_batches": n_parts,
+                "ms_per_step": max(ms_e, wall_e) / args.steps, "pipelined_sub_batches": n_parts, "deferred_copies": defer,
                 "pipelined_across_steps": "the next step's first upload overlaps this step's last sub-batch; results land in double-buffered pinned host memory",
                 "device_ms_per_step": ms_e / args.steps, "wall_ms_per_step": wall_e / args.steps,
                 "result": "the analysis tool's float32 lf0/mgc/bap + f0 + 16-bit resynthesised waveform + lf0/mgc statistics; "

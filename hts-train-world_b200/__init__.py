@@ -175,6 +175,7 @@ def lib():
         "CodeSpectralEnvelope": (None, [_dpp, i32, i32, i32, i32, _dpp]),
         "DecodeSpectralEnvelope": (None, [_dpp, i32, i32, i32, i32, _dpp]),
         "wb200_sync": (i32, []),
+        "wb200_set_copy_deferral": (i32, [i32]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -237,6 +238,12 @@ def build_info():
 
 def fma_peak_tflops(fp64=True):
     return float(lib().wb200_measure_fma_peak(int(bool(fp64))))
+
+
+def set_copy_deferral(on):
+    """Deferred bulk copies (include/world_b200.h): asynchronous uploads / downloads are issued right before D4C's main
+    kernel instead of beside a stage whose read-backs they would delay.  For pipelined callers."""
+    _check(lib().wb200_set_copy_deferral(int(bool(on))), "set_copy_deferral")
 
 
 def trim():

@@ -3,6 +3,7 @@
 // include/world_b200.h.  Host code only stages data; all arithmetic runs in the kernels.
 #include <math.h>
 #include <string.h>
+#include <functional>
 #include <limits>
 #include <string>
 #include "../../include/world_b200.h"
@@ -56,7 +57,34 @@ static bool bulk_copy_async(void* dst, const void* src, size_t bytes, cudaMemcpy
   }
   return true;
 }
+// ---- deferred bulk copies (wb200_set_copy_deferral) ---------------------------------------------------------
+// Measured on the end-to-end leg: while a bulk device-to-host copy is in flight, a stage's small read-backs
+// (list totals, pulse counts: a kernel writes them into mapped host memory and the host waits for it) complete
+// only when the copy has drained, so a copy queued beside Dio or Synthesis costs its whole PCIe time -- twice that
+// on an 8-GPU box whose GPUs share PCIe switches.  With deferral on, the asynchronous uploads / downloads are
+// only RECORDED when the caller asks for them and are issued at the next safe point: right before D4C launches
+// its main kernel (tens of milliseconds of compute without any host interaction), or at the latest when
+// something waits for them (wb200_batch_wait_downloads, wb200_sync, the next pass over the same batch, the stage
+// that needs the uploaded samples).  Host buffers must stay valid until then, as they must for any async copy.
+struct DeferredCopy { wb200_batch* h; std::function<bool()> issue; };
+std::vector<DeferredCopy> g_deferred;
+bool g_defer = false, g_in_flush = false;
+bool flush_deferred(wb200_batch* only) {
+  if (g_in_flush) return true;
+  g_in_flush = true;
+  bool ok = true;
+  for (size_t i = 0; i < g_deferred.size();) {
+    if (only && g_deferred[i].h != only) { ++i; continue; }
+    std::function<bool()> fn = std::move(g_deferred[i].issue);
+    g_deferred.erase(g_deferred.begin() + i);
+    ok = fn() && ok;
+  }
+  g_in_flush = false;
+  return ok;
+}
+bool defer_now() { return g_defer && !g_in_flush; }
 bool wait_downloads(wb200_batch* h, int which) {        // the buffer `which` is about to be rewritten
+  if (!flush_deferred(h)) return false;
   if (!h->download_pending[which]) return true;
   h->download_pending[which] = false;
   return WB_CUDA(cudaStreamWaitEvent(ctx()->stream, h->download_done[which], 0));
@@ -68,11 +96,21 @@ bool mark_downloads(wb200_batch* h, int which) {
 }
 // every stage that reads the samples first waits (on the device) for an asynchronous upload
 bool wait_upload(wb200_batch* h) {
+  if (!flush_deferred(h)) return false;
   if (!h->upload_pending) return true;
   h->upload_pending = false;
   return WB_CUDA(cudaStreamWaitEvent(ctx()->stream, h->upload_done, 0));
 }
 }  // namespace
+
+namespace wb {
+void flush_deferred_copies() { flush_deferred(nullptr); }      // d4c_run calls this right before its main kernel
+}
+int wb200_set_copy_deferral(int on) {
+  ApiGuard api_guard;
+  g_defer = on != 0;
+  return g_defer || flush_deferred(nullptr) ? 0 : 1;
+}
 
 namespace {
 
@@ -394,7 +432,8 @@ int wb200_sync(void) {
   ApiGuard api_guard;
   Context* c = ctx();
   if (!c) return 1;
-  bool ok = WB_CUDA(cudaStreamSynchronize(c->stream));
+  bool ok = flush_deferred(nullptr);
+  ok = WB_CUDA(cudaStreamSynchronize(c->stream)) && ok;
   if (c->copy_stream) ok = WB_CUDA(cudaStreamSynchronize(c->copy_stream)) && ok;
   if (c->upload_stream) ok = WB_CUDA(cudaStreamSynchronize(c->upload_stream)) && ok;
   return ok ? 0 : 1;
@@ -470,6 +509,10 @@ int wb200_batch_upload_pcm16_async(wb200_batch* h, const int16_t* host_pcm) {
   ApiGuard api_guard;
   Context* c = ctx();
   if (!c || !ensure_copy_streams(c)) return 1;
+  if (defer_now()) {
+    g_deferred.push_back({h, [h, host_pcm]() { return wb200_batch_upload_pcm16_async(h, host_pcm) == 0; }});
+    return 0;
+  }
   Batch& b = h->b;
   const long long n = wb200_batch_total_samples(h);
   if (!h->upload_done && !WB_CUDA(cudaEventCreateWithFlags(&h->upload_done, cudaEventDisableTiming))) return 1;
@@ -691,6 +734,10 @@ int wb200_batch_get_y_pcm16_async(wb200_batch* h, int16_t* out) {
   Batch& b = h->b;
   if (!c || !b.y.p) { set_error("synthesis has not been run"); return 1; }
   if (!ensure_copy_streams(c)) return 1;
+  if (defer_now()) {
+    g_deferred.push_back({h, [h, out]() { return wb200_batch_get_y_pcm16_async(h, out) == 0; }});
+    return 0;
+  }
   const long long n = wb200_batch_total_y(h);
   if (b.n_utt == 0 || n == 0) return 0;
   if (!prepare_pcm_out(h, n)) return 1;                // also: the previous pass's copy may still read pcm_out
@@ -725,7 +772,7 @@ int wb200_batch_get_utterance(wb200_batch* h, int utt, double* f0_raw, double* f
 int wb200_batch_wait_downloads(wb200_batch* h) {
   ApiGuard api_guard;
   if (!ctx()) return 1;
-  bool ok = true;
+  bool ok = flush_deferred(h);
   for (int k = 0; k < 2; ++k)
     if (h->download_done[k]) ok = WB_CUDA(cudaEventSynchronize(h->download_done[k])) && ok;
   return ok ? 0 : 1;
@@ -765,6 +812,10 @@ int wb200_batch_get_coded_async(wb200_batch* h, float* lf0, float* mgc, float* b
   Batch& b = h->b;
   if (!b.mgc.p) { set_error("features have not been coded"); return 1; }
   if (!ensure_copy_streams(c)) return 1;
+  if (defer_now()) {
+    g_deferred.push_back({h, [h, lf0, mgc, bap]() { return wb200_batch_get_coded_async(h, lf0, mgc, bap) == 0; }});
+    return 0;
+  }
   const size_t F = (size_t)b.total_frames;
   bool ok = WB_CUDA(cudaEventRecord(c->copy_event, c->stream)) &&
             WB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_event, 0));

@@ -101,6 +101,9 @@ bool read_back(void* h_dst, const void* d_src, size_t bytes);
 bool write_dev(void* d_dst, const void* h_src, size_t bytes);
 // cudaMemsetAsync on the library stream as a kernel (never a copy engine, see wb_context.cu); 4-byte granularity.
 bool dev_fill(void* d_ptr, int byte_value, size_t bytes);
+// Issues the bulk copies a caller queued under wb200_set_copy_deferral (wb_api.cu): a stage calls it right before
+// a long kernel that needs no host interaction, so the copies run under it instead of beside a read-back.
+void flush_deferred_copies();
 
 // Optional per-kernel device timing (CUDA events on the library stream around one launch).
 // Off by default; bench.py switches it on to measure the dominant kernel live.

@@ -874,6 +874,7 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
     const size_t smem = d4c_cbuf_slots(nd, c.nbands) * sizeof(double2) + (size_t)(2 * (hd + 8) + 160) * sizeof(double) +
                         sizeof(SelectScratch) + (kMaxBands + 2) * sizeof(double);
     const int threads = nd > 4096 ? 512 : 256;
+    flush_deferred_copies();      // deferred uploads / downloads of a pipelined caller start under this kernel
     KernelTimer kt2("d4c_main_kernel");
 #define WB_D4C_LAUNCH(L, TH, ...)                                                                                   \
   do {                                                                                                              \

@@ -337,6 +337,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wb.init(local)
+    wb.set_copy_deferral(True)      # bulk copies start under D4C's main kernel, not beside the next batch's Dio (world_b200.h)
     fp = 5.0 if args.frameshift is None else args.frameshift * 1000.0 / args.fs
     mgc_dim = args.mgc_order + 1
     if args.raw_dir:
