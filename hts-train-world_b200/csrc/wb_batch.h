@@ -14,6 +14,7 @@ struct UttView {
   const int* f_off;         // [n_utt] first frame of utterance u in the frame table
   const int* f_len;         // [n_utt]
   int n_utt;
+  int max_f_len = 0;        // host-side knowledge: the largest f_len (0 = unknown); sizes the randn table without a read-back
 };
 
 struct Batch {
@@ -52,6 +53,8 @@ struct Batch {
     UttView v;
     v.x = x.p; v.x_off = x_off.p; v.x_len = x_len.p; v.f_off = f_off.p; v.f_len = f_len.p;
     v.n_utt = n_utt;
+    v.max_f_len = 0;
+    for (int f : h_f_len) v.max_f_len = f > v.max_f_len ? f : v.max_f_len;
     return v;
   }
 };

@@ -227,10 +227,17 @@ bool cheaptrick_run(const UttView& u, int fs, int total_frames, const int* frame
   cheaptrick_count_kernel<<<(total_frames + 255) / 256, 256, 0, st>>>(f0, total_frames, fs, fft_size, f0_floor, counts.p);
   WB_LAUNCH_CHECK();
   if (!segmented_exclusive_scan(counts.p, u.f_off, u.f_len, u.n_utt, offs.p, totals.p)) return false;
-  std::vector<long long> h_tot(u.n_utt);
-  if (!read_back(h_tot.data(), totals.p, u.n_utt * sizeof(long long))) return false;
+  // The randn table must reach the largest per-utterance total.  With the frame counts known on the host an upper
+  // bound does (every frame draws 2 hwl + 1 + fft_size / 2 + 1 variates, hwl <= round(1.5 fs / f0_floor)): no
+  // read-back, the stage enqueues without a host round trip.  Unknown frame counts: read the totals.
   long long mx = 0;
-  for (long long v : h_tot) mx = v > mx ? v : mx;
+  if (u.max_f_len > 0) {
+    mx = (long long)u.max_f_len * (2LL * (static_cast<long long>(1.5 * fs / f0_floor + 0.5) + 1) + 1 + fft_size / 2 + 1);
+  } else {
+    std::vector<long long> h_tot(u.n_utt);
+    if (!read_back(h_tot.data(), totals.p, u.n_utt * sizeof(long long))) return false;
+    for (long long v : h_tot) mx = v > mx ? v : mx;
+  }
   if (!ensure_randn((size_t)mx)) return false;
   const size_t smem = cpad_size(fft_size / 2) * sizeof(double2) + (fft_size + 16 + 128) * sizeof(double);
   KernelTimer kt1("cheaptrick_kernel");

@@ -828,7 +828,17 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
 
   const int nblk = (total_frames + 255) / 256;
   std::vector<long long> h_lt(u.n_utt), h_main(u.n_utt);
+  // The randn table must reach the largest per-utterance total (LoveTrain draws + three windows per processed
+  // frame).  With the frame counts known on the host an upper bound does -- every voiced frame at the lowest F0
+  // each part clamps to -- and the two read-backs of the totals (with their host round trips) are not needed.
+  const bool bounded = u.max_f_len > 0;
+  if (bounded) {
+    const long long per_frame = 2LL * (static_cast<long long>(1.5 * fs / 40.0 + 0.5) + 1) + 1 +
+                                3LL * (2LL * (static_cast<long long>(2.0 * fs / kFloorF0D4C + 0.5) + 1) + 1);
+    if (!ensure_randn((size_t)((long long)u.max_f_len * per_frame))) return false;
+  }
   auto need_randn = [&]() {
+    if (bounded) return true;
     long long mx = 0;
     for (int i = 0; i < u.n_utt; ++i) mx = std::max(mx, h_lt[i] + h_main[i]);
     return ensure_randn((size_t)mx);
@@ -837,7 +847,7 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
   d4c_lt_count_kernel<<<nblk, 256, 0, st>>>(f0, total_frames, fs, counts.p);
   WB_LAUNCH_CHECK();
   if (!segmented_exclusive_scan(counts.p, u.f_off, u.f_len, u.n_utt, offs_lt.p, tot_lt.p)) return false;
-  if (!read_back(h_lt.data(), tot_lt.p, u.n_utt * sizeof(long long))) return false;
+  if (!bounded && !read_back(h_lt.data(), tot_lt.p, u.n_utt * sizeof(long long))) return false;
   std::fill(h_main.begin(), h_main.end(), 0);
   if (!need_randn()) return false;
   {
@@ -867,7 +877,7 @@ bool d4c_run(const UttView& u, int fs, int total_frames, const int* frame_utt,
   d4c_main_count_kernel<<<nblk, 256, 0, st>>>(f0, d_ap0.p, total_frames, fs, threshold, counts.p);
   WB_LAUNCH_CHECK();
   if (!segmented_exclusive_scan(counts.p, u.f_off, u.f_len, u.n_utt, offs_main.p, tot_main.p)) return false;
-  if (!read_back(h_main.data(), tot_main.p, u.n_utt * sizeof(long long))) return false;
+  if (!bounded && !read_back(h_main.data(), tot_main.p, u.n_utt * sizeof(long long))) return false;
   if (!need_randn()) return false;
   {
     const int hd = nd / 2;

@@ -427,8 +427,11 @@ def test_synthesis_from_float32_parameter_files(wb, reference_lib):
 
 
 @pytest.mark.gpu
-def test_back_to_back_passes_with_asynchronous_copies(wb):
-    """A long corpus run re-uses its batch objects without ever calling wb200_sync(): uploads on the
+@pytest.mark.parametrize("deferred", [False, True])
+def test_back_to_back_passes_with_asynchronous_copies(wb, deferred):
+    """deferred: wb200_set_copy_deferral(1) -- the copies are only recorded and start right before D4C's main kernel
+    of the next pass, or when something waits for them; the results must be the same.
+    A long corpus run re-uses its batch objects without ever calling wb200_sync(): uploads on the
     upload stream, result copies on the download stream, stages on the library stream.  Three passes
     over the same batch object (different inputs in turn) must deliver, in double-buffered pinned host
     memory, exactly what the synchronous calls deliver -- i.e. a pass never overwrites a buffer that an
@@ -456,6 +459,7 @@ def test_back_to_back_passes_with_asynchronous_copies(wb):
                  bap=torch.empty((F, 24), dtype=torch.float32).pin_memory(), y=torch.empty(n_y, dtype=torch.int16).pin_memory())
             for _ in range(2)]
     order = [0, 1, 0, 1]
+    wb.set_copy_deferral(deferred)
     c.upload_pcm16_async(sets[order[0]])
     for it, k in enumerate(order):
         c.analyze()
@@ -467,6 +471,7 @@ def test_back_to_back_passes_with_asynchronous_copies(wb):
         if it + 1 < len(order):
             c.upload_pcm16_async(sets[order[it + 1]])  # ordered behind the stages queued so far
     wb.sync()
+    wb.set_copy_deferral(False)
     for it in (len(order) - 2, len(order) - 1):        # the last two passes own the two buffer sets
         b, ((lf0, mgc, bap), y) = bufs[it % 2], want[order[it]]
         assert np.array_equal(b["lf0"].numpy(), lf0), it
