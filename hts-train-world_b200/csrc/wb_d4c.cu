@@ -51,7 +51,8 @@ __device__ __forceinline__ int windowed_waveform(const double* __restrict__ x, i
                                                  double f0, double position, int window_type,
                                                  double ratio, const uint32_t* __restrict__ rn,
                                                  S* base, WS wslot, VS vslot, double* red,
-                                                 const double* staged = nullptr, uint64_t* staged_bar = nullptr) {
+                                                 const double* staged = nullptr, uint64_t* staged_bar = nullptr,
+                                                 const double* phasors = nullptr) {   // {cs0, sn0, cs_step, sn_step} when the caller has them
   const int T = blockDim.x, tid = threadIdx.x;
   const int hwl = d4c_hwl(ratio, fs, f0);
   const int W = 2 * hwl + 1;
@@ -62,8 +63,11 @@ __device__ __forceinline__ int windowed_waveform(const double* __restrict__ x, i
   // the angle-addition recurrence with the block-uniform step T * ang_step (<= 16 steps, so
   // the accumulated rounding stays below 1e-15); cos(2a) = 2 cos^2(a) - 1.
   double cs0, sn0, cs_step, sn_step;
-  sincospi((double)(tid - hwl) * turn_step, &sn0, &cs0);
-  sincospi((double)T * turn_step, &sn_step, &cs_step);
+  if (phasors) { cs0 = phasors[0]; sn0 = phasors[1]; cs_step = phasors[2]; sn_step = phasors[3]; }
+  else {
+    sincospi((double)(tid - hwl) * turn_step, &sn0, &cs0);
+    sincospi((double)T * turn_step, &sn_step, &cs_step);
+  }
   auto window_at = [&](double cs) {
     return window_type == kHanning ? 0.5 * cs + 0.5 : 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);
   };
@@ -613,6 +617,15 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
   __syncthreads();
   if (st_ok && tid == 0) bulk_load_issue(pw, x + st_a0, (unsigned)st_n * 8u, &mbar);
 
+  // The three windows of the frame (two Blackman, one Hanning) have the same length and the same phase
+  // cos(pi (i - hwl) 2 f0 / (4 fs)) at sample i: the thread's start phasor and the step of T samples are
+  // computed once per frame (two double-precision sincospi instead of six).
+  double ph[4];
+  {
+    const double turn_step = 2.0 * cur_f0 / (4.0 * c.fs);   // angle step in units of pi
+    sincospi((double)(tid - hwl_w) * turn_step, &ph[1], &ph[0]);
+    sincospi((double)T * turn_step, &ph[3], &ph[2]);
+  }
   // ---- GetStaticCentroid (:125-142): two centroids, each one packed complex FFT ----------------
   for (int side = 0; side < 2; ++side) {
     const double pos = add_rn(t_pos, side == 0 ? -0.25 / cur_f0 : 0.25 / cur_f0);
@@ -624,11 +637,9 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
     const int W = 2 * hwl4 + 1;
     {
       const int origin = matlab_round(add_rn(mul_rn(pos, (double)c.fs), 0.001));
-      const double turn_step = 2.0 * cur_f0 / (4.0 * c.fs);   // angle step in units of pi
       const uint32_t* __restrict__ rns = rn + (size_t)side * W4;
-      double cs, sn, cs_step, sn_step;
-      sincospi((double)(tid - hwl4) * turn_step, &sn, &cs);
-      sincospi((double)T * turn_step, &sn_step, &cs_step);
+      double cs = ph[0], sn = ph[1];
+      const double cs_step = ph[2], sn_step = ph[3];
       double sums[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
       const bool staged = st_ok;
       const double* xs = pw + (window_origin(side) - st_a0);
@@ -703,7 +714,7 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
     if (st_ok) mbar_wait(&mbar, st_parity);
     const int W = windowed_waveform<true>(x, x_len, c.fs, cur_f0, t_pos, kHanning, 4.0,
                                     rn + 2 * (size_t)W4, cbufd, pwslot, pvslot, red,
-                                    st_ok ? pw + (window_origin(2) - st_a0) : nullptr);
+                                    st_ok ? pw + (window_origin(2) - st_a0) : nullptr, nullptr, ph);
     for (int i = W + tid; i < Nd; i += T) cbufd[rfft_in_slot(i, log2m)] = 0.0;
     fft_dit<LMD, false, THREADS, MAXK, TWL>(cbuf, log2m, tw);
     for (int k = tid; k <= k_pw; k += T) {
