@@ -4,7 +4,7 @@
 # the dominant kernel at the full 1 132 utterances.  Numbers printed under ncu are never bench values.
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r2p_pytest.log 2>&1; echo "pytest exit $?"; tail -5 gpurun_out/r2p_pytest.log
-UTTS=300 bash scripts/gpu_ab.sh "WB200_LIB=libworld_b200_base.so" "" "WB200_LIB=libworld_b200_base.so" ""
+UTTS=300 bash scripts/gpu_ab.sh "" ""
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/r2p_bench.json 2> gpurun_out/r2p_bench.err; echo "bench exit $?"; tail -3 gpurun_out/r2p_bench.err
 python - <<'PY'
 import json
