@@ -586,6 +586,11 @@ d4c_main_kernel(UttView u, const int* __restrict__ frame_utt, const double* __re
   const double cur_f0 = fmax(kFloorF0D4C, f0);
   const uint32_t* __restrict__ rn = randn_tab + lt_totals[utt] + rng_off[f];
   const int W4 = 2 * d4c_hwl(4.0, c.fs, cur_f0) + 1;
+#if !defined(WB_HOST_EMU) && !defined(WB_NO_RN_PREFETCH)
+  // the frame's 3 W4 dither words are read once, by this CTA only, straight from HBM: ask L2 for all of them now
+  // (one 128-byte line per thread and trip), the second and third window then find them there
+  for (int i = tid * 32; i < 3 * W4; i += T * 32) asm volatile("prefetch.global.L2 [%0];" :: "l"(rn + i));
+#endif
   if (W4 > Nd || Hd + 2 * smoothing_boundary(cur_f0, c.fs, Nd) + 1 > 2 * cpad_size(Nd)) {
     for (int k = tid; k <= c.out_half; k += T) out[k] = __longlong_as_double(0x7ff8000000000000LL);
     return;
