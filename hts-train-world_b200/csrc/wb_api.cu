@@ -62,8 +62,9 @@ static bool bulk_copy_async(void* dst, const void* src, size_t bytes, cudaMemcpy
 // (list totals, pulse counts: a kernel writes them into mapped host memory and the host waits for it) complete
 // only when the copy has drained, so a copy queued beside Dio or Synthesis costs its whole PCIe time -- twice that
 // on an 8-GPU box whose GPUs share PCIe switches.  With deferral on, the asynchronous uploads / downloads are
-// only RECORDED when the caller asks for them and are issued at the next safe point: right before D4C launches
-// its main kernel (tens of milliseconds of compute without any host interaction), or at the latest when
+// only RECORDED when the caller asks for them and are issued at the next safe point: at the start of StoneMask
+// (or CheapTrick, or right before D4C's main kernel, whichever comes first: StoneMask -> CheapTrick -> D4C is
+// ~60 ms per sub-batch of compute without a single read-back), or at the latest when
 // something waits for them (wb200_batch_wait_downloads, wb200_sync, the next pass over the same batch, the stage
 // that needs the uploaded samples).  Host buffers must stay valid until then, as they must for any async copy.
 struct DeferredCopy { wb200_batch* h; std::function<bool()> issue; };
@@ -104,7 +105,7 @@ bool wait_upload(wb200_batch* h) {
 }  // namespace
 
 namespace wb {
-void flush_deferred_copies() { flush_deferred(nullptr); }      // d4c_run calls this right before its main kernel
+void flush_deferred_copies() { flush_deferred(nullptr); }      // StoneMask / CheapTrick / D4C call this where no read-back follows
 }
 int wb200_set_copy_deferral(int on) {
   ApiGuard api_guard;

@@ -221,6 +221,7 @@ bool cheaptrick_run(const UttView& u, int fs, int total_frames, const int* frame
     return false;
   }
   const double f0_floor = 3.0 * fs / (fft_size - 3.0);      // GetF0FloorForCheapTrick :196-198
+  if (u.max_f_len > 0) flush_deferred_copies();             // no read-back below: deferred bulk copies may start (see stonemask_run)
   DevBuf<long long> counts, offs, totals;
   if (!counts.alloc(total_frames) || !offs.alloc(total_frames) || !totals.alloc(u.n_utt)) return false;
   cudaStream_t st = c->stream;

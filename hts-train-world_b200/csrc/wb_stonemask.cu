@@ -292,6 +292,9 @@ bool stonemask_run(const UttView& u, int fs, int total_frames, const int* frame_
   if (total_frames <= 0) return true;
   cudaStream_t st = c->stream;
   if (option("stonemask_dft")) {
+    // StoneMask -> CheapTrick -> D4C is the longest stretch of a pass without a single host round trip (~60 % of
+    // it): the deferred bulk copies of a pipelined caller start here (wb200_set_copy_deferral, wb_api.cu)
+    flush_deferred_copies();
     // largest transform size the bins refer to: f0 just above 40 Hz -> hwl = 1.5 fs / 40 + 1
     const int w_max = 2 * static_cast<int>(1.5 * fs / kFloorF0StoneMask + 1.0) + 1;
     int l2 = 0; while ((1 << (l2 + 1)) <= w_max) ++l2;

@@ -188,8 +188,8 @@ WORLD_API int wb200_htk_header(int n_frames, int samp_freq, int frame_shift, int
                                int kind, unsigned char *out12);
 /* block until everything queued on the library stream has finished */
 /* Deferred bulk copies (0 / 1, default 0).  With deferral on, wb200_batch_upload_pcm16_async, wb200_batch_get_coded_async
- * and wb200_batch_get_y_pcm16_async only record the request; the copies are issued at the next safe point -- right
- * before D4C launches its main kernel (no host interaction for tens of milliseconds) -- or at the latest when something
+ * and wb200_batch_get_y_pcm16_async only record the request; the copies are issued at the next safe point -- the start
+ * of StoneMask / CheapTrick / D4C's main kernel, the stretch of a pass without host interaction -- or at the latest when something
  * waits for them (wb200_batch_wait_downloads, wb200_sync, the next pass over the same batch, the stage that needs the
  * uploaded samples).  A bulk copy in flight delays the small read-backs of the stage that runs beside it by its whole
  * PCIe time (measured); a pipelined caller switches this on.  Host buffers must stay valid until the copies are done. */
