@@ -482,6 +482,7 @@ int wb200_batch_frame_layout(const wb200_batch* h, int* f_off, int* f_len) {
 static int convert_pcm(wb200_batch* h, const int16_t* dev_pcm) {
   Batch& b = h->b;
   Context* c = ctx();
+  if (!wait_upload(h)) return 1;           // a deferred / in-flight asynchronous upload of this batch comes first
   std::vector<long long> src(b.n_utt);
   long long o = 0;
   for (int u = 0; u < b.n_utt; ++u) { src[u] = o; o += b.h_x_len[u]; }
@@ -498,6 +499,7 @@ int wb200_batch_upload_pcm16(wb200_batch* h, const int16_t* host_pcm) {
   Context* c = ctx();
   if (!c) return 1;
   const long long n = wb200_batch_total_samples(h);
+  if (!wait_upload(h)) return 1;           // a deferred / in-flight asynchronous upload of this batch comes first
   if (!h->pcm_stage.alloc((size_t)n)) return 1;
   if (!WB_CUDA(cudaMemcpyAsync(h->pcm_stage.p, host_pcm, (size_t)n * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream))) return 1;
   return convert_pcm(h, h->pcm_stage.p);
@@ -547,6 +549,7 @@ int wb200_batch_upload_f64(wb200_batch* h, const double* host_x) {
   Context* c = ctx();
   if (!c) return 1;
   Batch& b = h->b;
+  if (!wait_upload(h)) return 1;           // a deferred / in-flight asynchronous upload of this batch comes first
   long long o = 0;
   for (int u = 0; u < b.n_utt; ++u) {
     if (b.h_x_len[u] > 0 &&
