@@ -81,6 +81,19 @@ def _worker_main(conn, opt):
         conn.send(acc)
 
 
+def deal_utterances(utts, cores):
+    """Longest utterance first onto the least loaded core: every core gets about the same seconds of audio, so
+    the wall time of a pass is the machine's throughput and not its unluckiest core (round 1 dealt round-robin)."""
+    from hts_train_world_b200 import signals
+    dur = {u: signals.utterance_params(u)["T"] for u in utts}
+    bins, load = [[] for _ in range(cores)], [0.0] * cores
+    for u in sorted(utts, key=lambda v: (-dur[v], v)):
+        i = min(range(cores), key=lambda k: (load[k], k))
+        bins[i].append(u)
+        load[i] += dur[u]
+    return bins
+
+
 class ReferencePool:
     """`cores` processes; utterances are dealt round-robin."""
 
@@ -96,20 +109,8 @@ class ReferencePool:
             self.conns.append(a)
             self.procs.append(p)
 
-    def _deal(self, utts):
-        """Longest utterance first onto the least loaded core: every core gets about the same seconds of audio, so
-        the wall time of a pass is the machine's throughput and not its unluckiest core (round 1 dealt round-robin)."""
-        from hts_train_world_b200 import signals
-        dur = {u: signals.utterance_params(u)["T"] for u in utts}
-        bins, load = [[] for _ in range(self.cores)], [0.0] * self.cores
-        for u in sorted(utts, key=lambda v: (-dur[v], v)):
-            i = min(range(self.cores), key=lambda k: (load[k], k))
-            bins[i].append(u)
-            load[i] += dur[u]
-        return bins
-
     def _all(self, cmd, utts):
-        for cn, mine in zip(self.conns, self._deal(utts)):
+        for cn, mine in zip(self.conns, deal_utterances(utts, self.cores)):
             cn.send((cmd, mine))
         return [cn.recv() for cn in self.conns]
 

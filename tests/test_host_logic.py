@@ -142,3 +142,18 @@ def test_driver_host_rules():
     assert not driver.passes_clip_check(np.array([-32768, 3], np.int16))
     assert not driver.passes_clip_check(np.zeros(0, np.int16))
     assert [driver.fftlen_for(fs) for fs in (16000, 22050, 44100, 48000)] == [1024, 1024, 2048, 2048]
+
+
+def test_reference_arm_deals_utterances_evenly():
+    """bench.py's CPU arm: every core gets about the same seconds of audio (longest first onto the least loaded core),
+    every utterance exactly once."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from hts_train_world_b200 import signals
+    utts = bench.reference_sample_utts(16, 4)
+    bins = bench.deal_utterances(utts, 16)
+    assert sorted(u for b in bins for u in b) == utts
+    loads = [sum(signals.utterance_params(u)["T"] for u in b) for b in bins]
+    assert max(loads) <= 1.15 * (sum(loads) / len(loads))
