@@ -281,3 +281,41 @@ def test_dio_kernels_source(tmp_path, reference_lib):
     refs = reference_lib.dio(xs, fs)[1]
     outs = np.fromfile(tmp_path / "f0_raw.f64")
     assert M.vuv_agreement(refs, outs) == 1.0 and M.f0_rel_error(refs, outs) <= 1e-12
+
+
+def test_harvest_refinement_kernel_source(tmp_path):
+    """harvest_refine_thread_kernel (Goertzel recurrences at the <= 6 harmonic bins, window walks shared between the
+    overlapped slots) on the CPU against the restatement of GetRefinedF0 in oracle/harvest_np.py (two FFTs per
+    candidate, W/src/harvest.cpp:587-616): a gliding harmonic signal at the 8 kHz Harvest decimates to, two base
+    candidates per 1 ms frame (one near the true F0, one at its octave or empty)."""
+    from oracle import harvest_np as H
+    so = str(tmp_path / "libhv_emu.so")
+    r = _build(["harvest_emu.cpp"], so, ["-shared", "-fPIC"])
+    assert r.returncode == 0, r.stderr[-3000:]
+    lib = C.CDLL(so)
+    dp = C.POINTER(C.c_double)
+    fs, n_fr, nc, max_base = 8000.0, 240, 2, 3
+    rng = np.random.default_rng(5)
+    n = int(fs * n_fr / 1000.0) + 1
+    tt = np.arange(n) / fs
+    f0_true = 120.0 + 260.0 * tt                                     # 120 -> 182 Hz
+    phase = 2.0 * np.pi * np.cumsum(f0_true) / fs
+    y = sum(np.sin(h * phase) / h for h in range(1, 9)) + 0.01 * rng.standard_normal(n) + 0.3
+    base = np.zeros((n_fr, max_base))
+    fk = np.interp(np.arange(n_fr) / 1000.0, tt, f0_true)
+    base[:, 0] = fk * (1.0 + 0.01 * rng.standard_normal(n_fr))
+    base[:, 1] = np.where(np.arange(n_fr) % 3 == 0, 0.0, 2.0 * fk)
+    slots = 7 * nc
+    cand = np.full((n_fr, slots), -1.0)
+    score = np.full((n_fr, slots), -1.0)
+    yc, bc = np.ascontiguousarray(y), np.ascontiguousarray(base)
+    rc = lib.emu_harvest_refine(yc.ctypes.data_as(dp), len(yc), C.c_double(fs), C.c_double(71.0), C.c_double(800.0),
+                                bc.ctypes.data_as(dp), n_fr, nc, max_base, cand.ctypes.data_as(dp), score.ctypes.data_as(dp))
+    assert rc == 0
+    want_c, want_s = H.refine_candidates(y, fs, base, nc, 71.0, 800.0)
+    firm = np.abs(want_s - 2.5) > 1e-6                               # away from the acceptance threshold of the score
+    assert np.array_equal((cand != 0.0)[firm], (want_c != 0.0)[firm])
+    both = firm & (want_c != 0.0) & (cand != 0.0)
+    assert both.sum() > 1000
+    assert np.max(np.abs(cand[both] - want_c[both]) / want_c[both]) <= 1e-9
+    assert np.max(np.abs(score[both] - want_s[both]) / want_s[both]) <= 1e-6
