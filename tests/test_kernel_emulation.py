@@ -319,3 +319,52 @@ def test_harvest_refinement_kernel_source(tmp_path):
     assert both.sum() > 1000
     assert np.max(np.abs(cand[both] - want_c[both]) / want_c[both]) <= 1e-9
     assert np.max(np.abs(score[both] - want_s[both]) / want_s[both]) <= 1e-6
+
+
+def _harvest_candidates(n_fr=700, nc=2, seed=3):
+    """Refined candidates / scores as the contour logic sees them: three voiced stretches with gaps, a main track with
+    0.2 % jitter, an octave track in some slots, empty slots, two short blips that FixStep2 must remove."""
+    rng = np.random.default_rng(seed)
+    slots = 7 * nc
+    cand, score = np.zeros((n_fr, slots)), np.zeros((n_fr, slots))
+    k = np.arange(n_fr)
+    track = 140.0 + 40.0 * np.sin(k / 90.0)
+    voiced = ((k > 40) & (k < 230)) | ((k > 260) & (k < 480)) | ((k > 520) & (k < 660)) | ((k > 240) & (k < 244)) | ((k > 500) & (k < 503))
+    for s in range(slots):
+        on = voiced & (rng.random(n_fr) > 0.15)
+        octave = (s % 3 == 2) & (rng.random(n_fr) > 0.5)
+        f = track * (1.0 + 0.002 * rng.standard_normal(n_fr)) * np.where(octave, 2.0, 1.0)
+        cand[:, s] = np.where(on, f, 0.0)
+        score[:, s] = np.where(on, 3.0 + 20.0 * rng.random(n_fr) * np.where(octave, 0.3, 1.0), 0.0)
+    cand[300:310, :] *= 1.05                                           # a jump FixStep1 rejects
+    return np.ascontiguousarray(cand), np.ascontiguousarray(score)
+
+
+def test_harvest_contour_kernels_source(tmp_path):
+    """The warp-cooperative contour logic (harvest_fix_b_kernel) against the one-lane version on the CPU: identical bit
+    for bit after FixStep3 and after the merge (FixStep4), and free of data races under ThreadSanitizer."""
+    so = str(tmp_path / "libhv_emu.so")
+    r = _build(["harvest_emu.cpp"], so, ["-shared", "-fPIC"])
+    assert r.returncode == 0, r.stderr[-3000:]
+    lib = C.CDLL(so)
+    dp = C.POINTER(C.c_double)
+    cand, score = _harvest_candidates()
+    n_fr, nc = cand.shape[0], cand.shape[1] // 7
+    outs = [np.zeros(n_fr) for _ in range(4)]
+    rc = lib.emu_harvest_contour(cand.ctypes.data_as(dp), score.ctypes.data_as(dp), n_fr, nc, *[o.ctypes.data_as(dp) for o in outs])
+    assert rc == 0
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[2], outs[3])
+    assert np.count_nonzero(outs[0]) > 300 and np.count_nonzero(outs[0][236:250]) == 0      # contours found, the blip is gone
+    exe = str(tmp_path / "hv_tsan")
+    r = _build(["harvest_emu.cpp"], exe, ["-g", "-fsanitize=thread", "-DEMU_HARVEST_MAIN"])
+    if r.returncode != 0:
+        pytest.skip("ThreadSanitizer build not available: " + r.stderr[-200:])
+    path = str(tmp_path / "cand.bin")
+    with open(path, "wb") as f:
+        f.write(np.array([n_fr, nc], np.int32).tobytes())
+        f.write(cand.tobytes())
+        f.write(score.tobytes())
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0")
+    p = subprocess.run([exe, path], capture_output=True, text=True, env=env, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert p.stderr.count("WARNING: ThreadSanitizer") == 0, p.stderr[-3000:]
